@@ -1,0 +1,244 @@
+"""ORACLE tooling: generate tests/golden/*.npz by running the UNMODIFIED reference.
+
+Run in the dev container only (needs /root/reference):
+
+    python -m oracle.make_golden            # from /root/repo
+
+The reference package is imported from /root/reference through the stand-in modules in
+oracle/shims/ (kornia -> oracle/kornia_restated.py, omegaconf, e2cnn, torch_scatter: none of
+them is installed in this image).  Every array written is an input to, or an output of, a
+reference class/function, named below with its file:line.  The fixtures are small on purpose
+(tests/golden/ is a few MB in total) and are what the `-m "not gpu"` tests pin the oracle against and
+what the `-m gpu` tests compare the CUDA path with on the GPU box, where /root/reference does
+not exist.
+"""
+from __future__ import annotations
+
+import os
+import sys
+from unittest import mock
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.environ.get("EQUIADAPT_REFERENCE", "/root/reference")
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def _import_reference():
+    sys.path[:0] = [os.path.join(ROOT, "oracle", "shims"), ROOT, REF]
+    import equiadapt  # noqa: F401
+
+    return equiadapt
+
+
+def _np(d):
+    out = {}
+    for k, v in d.items():
+        if torch.is_tensor(v):
+            v = v.detach().cpu().numpy()
+        out[k] = np.asarray(v)
+    return out
+
+
+def _save(name, d):
+    os.makedirs(OUT, exist_ok=True)
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, **_np(d))
+    print(f"{name}: {os.path.getsize(path) / 1024:.1f} KiB, keys={sorted(d)}")
+
+
+class _HP(dict):
+    __getattr__ = dict.__getitem__
+
+
+def smooth_images(b, c, h, w, seed):
+    """Smooth non-zero-mean synthetic images (wide argmax margins)."""
+    g = torch.Generator().manual_seed(seed)
+    low = torch.randn(b, c, max(h // 8, 2), max(w // 8, 2), generator=g)
+    return torch.nn.functional.interpolate(low, size=(h, w), mode="bicubic", align_corners=False) + 0.5
+
+
+def golden_gram_schmidt():
+    from equiadapt.common.utils import gram_schmidt  # common/utils.py:22-51
+
+    torch.manual_seed(0)
+    v = torch.randn(1, 3, 3)
+    out = gram_schmidt(v)
+    g = torch.Generator().manual_seed(7)
+    vb = torch.randn(32, 3, 3, generator=g)
+    _save("gram_schmidt", {"kat_in": v, "kat_out": out, "batch_in": vb, "batch_out": gram_schmidt(vb)})
+
+
+def _image_case(name, group_type, num_rotations, in_shape, batch, out_channels, kernel_size, num_layers,
+                crop_ratio, resize, beta, seed, regular_fields=1, fshape=(16, 16)):
+    from equiadapt.images.canonicalization.discrete_group import GroupEquivariantImageCanonicalization
+    from equiadapt.images.canonicalization_networks.custom_equivariant_networks import CustomEquivariantNetwork
+
+    torch.manual_seed(seed)
+    net = CustomEquivariantNetwork((in_shape[0], resize, resize), out_channels, kernel_size, group_type,
+                                   num_rotations, num_layers, device="cpu")
+    # quirk A.4-1: the reference class omits these two attributes the wrapper reads
+    net.group_type, net.num_rotations = group_type, num_rotations
+    with torch.no_grad():  # non-zero biases so the bias path is pinned too
+        for m in net.eqv_network:
+            if hasattr(m, "bias") and m.bias is not None:
+                m.bias.uniform_(-0.05, 0.05)
+    hp = _HP(beta=beta, input_crop_ratio=crop_ratio, resize_shape=resize)
+    can = GroupEquivariantImageCanonicalization(net, hp, in_shape).eval()
+    x = smooth_images(batch, *in_shape, seed=seed + 1)
+    num_group = can.num_group
+    gen = torch.Generator().manual_seed(seed + 2)
+    d = {"x": x, "group_type": group_type, "num_rotations": num_rotations, "in_shape": np.array(in_shape),
+         "crop_ratio": crop_ratio, "resize": resize, "beta": beta, "num_layers": num_layers}
+    for i, m in enumerate(net.eqv_network):
+        if hasattr(m, "weights"):
+            d[f"w{i}"] = m.weights
+            d[f"b{i}"] = m.bias
+    with torch.no_grad():
+        # discrete_group.py:174-188
+        d["x_pre"] = can.transformations_before_canonicalization_network_forward(x)
+        # custom_group_equivariant_layers.py:62-90 / :298-334 (orbit of the first two layers)
+        lift = net.eqv_network[0]
+        d["orbit_lift"] = (lift.get_rotated_weights(lift.weights, num_rotations) if group_type == "rotation"
+                           else lift.get_rotoreflected_weights(lift.weights, num_rotations))
+        if num_layers > 1:
+            reg = net.eqv_network[2]
+            d["orbit_reg"] = (reg.get_rotated_permuted_weights(reg.weights, num_rotations) if group_type == "rotation"
+                              else reg.get_rotoreflected_permuted_weights(reg.weights, num_rotations))
+        # full forward: discrete_group.py:190-238
+        y = can(x)
+        d["act"] = can.canonicalization_info_dict["group_activations"]
+        d["rotation"] = can.canonicalization_info_dict["group_element"]["rotation"]
+        if group_type == "roto-reflection":
+            d["reflection"] = can.canonicalization_info_dict["group_element"]["reflection"]
+        d["x_canon"] = y
+        # basecanonicalization.py:290-311
+        d["prior_loss"] = can.get_prior_regularization_loss()
+        d["identity_metric"] = can.get_identity_metric()
+        # images/utils.py:32-94 through discrete_group.py:240-259
+        f_reg = torch.randn(batch, regular_fields * num_group, *fshape, generator=gen)
+        f_sca = torch.randn(batch, 3, *fshape, generator=gen)
+        d["f_regular"], d["f_scalar"] = f_reg, f_sca
+        d["inv_regular"] = can.invert_canonicalization(f_reg, induced_rep_type="regular")
+        d["inv_scalar"] = can.invert_canonicalization(f_sca, induced_rep_type="scalar")
+
+        # every group element, by patching get_groupelement the way the reference's own
+        # fixture does (tests/images/canonicalization/test_continuous_group.py:94-121)
+        idx = torch.arange(batch) % num_group
+        angles = torch.linspace(0.0, 360.0, num_rotations + 1)[:num_rotations]
+        forced = {"rotation": angles[idx % num_rotations]}
+        if group_type == "roto-reflection":
+            forced["reflection"] = (idx >= num_rotations).float()
+        with mock.patch.object(can, "get_groupelement", return_value=forced):
+            d["forced_idx"] = idx
+            d["forced_canon"] = can.canonicalize(x)
+        can.canonicalization_info_dict["group_element"] = forced
+        d["forced_inv_regular"] = can.invert_canonicalization(f_reg, induced_rep_type="regular")
+        d["forced_inv_scalar"] = can.invert_canonicalization(f_sca, induced_rep_type="scalar")
+    _save(name, d)
+
+
+def golden_optimized(name, group_type, num_rotations, in_shape, batch, resize, crop_ratio, seed):
+    from equiadapt.images.canonicalization.discrete_group import OptimizedGroupEquivariantImageCanonicalization
+    from equiadapt.images.canonicalization_networks.custom_nonequivariant_networks import ConvNetwork
+
+    torch.manual_seed(seed)
+    net = ConvNetwork((in_shape[0], resize, resize), out_channels=8, kernel_size=3, num_layers=2, out_vector_size=16)
+    hp = _HP(beta=1.0, input_crop_ratio=crop_ratio, resize_shape=resize, group_type=group_type,
+             num_rotations=num_rotations, artifact_err_wt=0, learn_ref_vec=False)
+    can = OptimizedGroupEquivariantImageCanonicalization(net, hp, in_shape).eval()
+    x = smooth_images(batch, *in_shape, seed=seed + 1)
+    d = {"x": x, "group_type": group_type, "num_rotations": num_rotations, "in_shape": np.array(in_shape),
+         "crop_ratio": crop_ratio, "resize": resize, "reference_vector": can.reference_vector}
+    with torch.no_grad():
+        can.device = x.device
+        xp = can.transformations_before_canonicalization_network_forward(x)
+        d["x_pre"] = xp
+        d["x_orbit"] = can.group_augment(xp)  # discrete_group.py:411-427
+        y = can(x)
+        d["vector_out"] = can.canonicalization_info_dict["vector_out"]
+        d["act"] = can.canonicalization_info_dict["group_activations"]  # :475-481
+        d["rotation"] = can.canonicalization_info_dict["group_element"]["rotation"]
+        if group_type == "roto-reflection":
+            d["reflection"] = can.canonicalization_info_dict["group_element"]["reflection"]
+        d["x_canon"] = y
+        d["opt_loss"] = can.get_optimization_specific_loss()  # :483-512
+        d["prior_loss"] = can.get_prior_regularization_loss()
+    _save(name, d)
+
+
+def golden_pointcloud():
+    from equiadapt.pointcloud.canonicalization.continuous_group import EquivariantPointcloudCanonicalization
+
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(6, 3, 64, generator=g)
+    vecs = torch.randn(6, 3, 3, generator=g)
+
+    class Net(torch.nn.Module):
+        def forward(self, _x):
+            return vecs
+
+    can = EquivariantPointcloudCanonicalization(Net(), _HP()).eval()
+    with torch.no_grad():
+        y = can(x)  # pointcloud/canonicalization/continuous_group.py:51-81, :107-134
+        d = {"x": x, "vectors": vecs, "x_canon": y,
+             "rotation": can.canonicalization_info_dict["group_element_matrix_representation"],
+             "prior_loss": can.get_prior_regularization_loss(),  # basecanonicalization.py:390-408
+             "identity_metric": can.get_identity_metric()}
+    _save("pointcloud_so3", d)
+
+
+def golden_nbody():
+    from equiadapt.nbody.canonicalization.euclidean_group import EuclideanGroupNBody
+
+    g = torch.Generator().manual_seed(13)
+    systems, particles = 7, 5
+    m = systems * particles
+    loc = torch.randn(m, 3, generator=g)
+    vel = torch.randn(m, 3, generator=g)
+    rv = torch.randn(systems, 3, 3, generator=g).repeat_interleave(particles, dim=0)
+    t = torch.randn(systems, 3, generator=g).repeat_interleave(particles, dim=0)
+
+    class Net(torch.nn.Module):
+        def forward(self, *a):
+            return rv, t
+
+    can = EuclideanGroupNBody(Net()).eval()
+    nodes = torch.sqrt(torch.sum(vel ** 2, dim=1)).unsqueeze(1)
+    with torch.no_grad():
+        # nbody/canonicalization/euclidean_group.py:87-124 (kwarg ORDER matters, :104)
+        cl, cv = can(nodes, None, loc=loc, edges=None, vel=vel, edge_attr=None, charges=None)
+        pred = torch.randn(m, 3, generator=g)
+        inv = can.invert_canonicalization(pred)  # :126-137
+        d = {"loc": loc, "vel": vel, "rot_vectors": rv, "translation": t, "canon_loc": cl, "canon_vel": cv,
+             "rotation": can.canonicalization_info_dict["group_element"]["rotation_matrix"],
+             "pred": pred, "inverted": inv}
+    _save("nbody_e3", d)
+
+
+def main():
+    _import_reference()
+    golden_gram_schmidt()
+    # cfg1 of BASELINE.json (C4, 3x32x32, oc16/k5/L3, crop .9 -> 29 (offset 2), resize 32), batch cut to 4
+    _image_case("image_c4_cfg1", "rotation", 4, (3, 32, 32), 4, 16, 5, 3, 0.9, 32, 1.0, seed=0)
+    # cfg2 in miniature: C8, crop .8, down-sampling antialiased resize, k5, L3
+    _image_case("image_c8_small", "rotation", 8, (3, 40, 40), 8, 4, 5, 3, 0.8, 20, 1.0, seed=10)
+    # D4 (roto-reflection), 2 regular fields in the inverted feature map
+    _image_case("image_d4_small", "roto-reflection", 4, (3, 36, 36), 8, 4, 3, 2, 0.9, 24, 0.5, seed=20,
+                regular_fields=2, fshape=(12, 12))
+    # D8 exercises reflected 45-degree elements; single layer (lift only)
+    _image_case("image_d8_small", "roto-reflection", 8, (3, 24, 24), 16, 3, 3, 1, 1.0, 16, 1.0, seed=30, fshape=(10, 10))
+    # grayscale: no pad / crop / resize, zero-fill rotate (discrete_group.py:60-71)
+    _image_case("image_c4_gray", "rotation", 4, (1, 28, 28), 4, 4, 3, 2, 0.9, 28, 1.0, seed=40)
+    # non-square input
+    _image_case("image_c8_rect", "rotation", 8, (3, 24, 32), 8, 2, 3, 2, 1.0, (16, 16), 1.0, seed=50, fshape=(10, 14))
+    golden_optimized("image_opt_d4", "roto-reflection", 4, (3, 40, 40), 4, 24, 0.8, seed=60)
+    golden_optimized("image_opt_c8", "rotation", 8, (3, 32, 32), 3, 16, 0.9, seed=70)
+    golden_pointcloud()
+    golden_nbody()
+
+
+if __name__ == "__main__":
+    main()

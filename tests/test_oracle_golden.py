@@ -1,0 +1,128 @@
+"""CPU: pin the oracle (oracle/reference_path.py) against the reference's own outputs.
+
+The golden files were produced by running the unmodified reference (oracle/make_golden.py);
+the one numeric known-answer test of the reference (tests/common/test_utils.py:6-12) is here too.
+"""
+import pytest
+import torch
+
+from conftest import IMAGE_CASES, golden_layers, load_golden, rel_err, resize_arg
+from oracle import reference_path as O
+
+TOL = 1e-6  # same ops in the same order: differences are thread-count dependent summation order only
+
+
+def test_gram_schmidt_known_answer():
+    # /root/reference/tests/common/test_utils.py:6-12
+    torch.manual_seed(0)
+    out = O.gram_schmidt(torch.randn(1, 3, 3))
+    assert torch.allclose(out[0][0][0], torch.tensor(0.5740), atol=1e-4)
+
+
+def test_gram_schmidt_golden():
+    g = load_golden("gram_schmidt")
+    assert torch.allclose(g["kat_out"][0, 0, 0], torch.tensor(0.5740), atol=1e-4)
+    assert torch.equal(O.gram_schmidt(g["kat_in"]), g["kat_out"])
+    assert rel_err(O.gram_schmidt(g["batch_in"]), g["batch_out"]) < TOL
+
+
+@pytest.mark.parametrize("case", IMAGE_CASES)
+def test_image_path_matches_reference(case):
+    g = load_golden(case)
+    reflect = g["group_type"] == "roto-reflection"
+    n = g["num_rotations"]
+    num_group = n * (2 if reflect else 1)
+    in_shape = tuple(int(v) for v in g["in_shape"])
+    layers = golden_layers(g)
+
+    x_pre = O.pre_network_transform(g["x"], in_shape, g["crop_ratio"], resize_arg(g))
+    assert rel_err(x_pre, g["x_pre"]) < TOL
+    assert rel_err(O.lift_filter_orbit(layers[0][0], n, reflect), g["orbit_lift"]) < TOL
+    if len(layers) > 1:
+        assert rel_err(O.regular_filter_orbit(layers[1][0], n, reflect), g["orbit_reg"]) < TOL
+    act = O.custom_equivariant_network(x_pre, layers, n, reflect)
+    assert rel_err(act, g["act"]) < 1e-5
+    el = O.activations_to_group_element(g["act"], n, reflect, g["beta"])
+    assert torch.equal(el["rotation"], g["rotation"])
+    if reflect:
+        assert torch.equal(el["reflection"], g["reflection"])
+    y = O.canonicalize_image(g["x"], g["rotation"], g.get("reflection"))
+    assert rel_err(y, g["x_canon"]) < TOL
+    assert abs(float(O.prior_loss_discrete(g["act"]) - g["prior_loss"])) < 1e-6
+    assert float(O.identity_metric_discrete(g["act"])) == float(g["identity_metric"])
+    for rep in ("regular", "scalar"):
+        inv = O.invert_image_features(g[f"f_{rep}"], g["rotation"], g.get("reflection"), n, num_group, rep)
+        assert rel_err(inv, g[f"inv_{rep}"]) < TOL
+
+    # every group element (forced)
+    idx = g["forced_idx"]
+    ang = torch.linspace(0.0, 360.0, n + 1)[:n][idx % n]
+    refl = (idx >= n).float() if reflect else None
+    assert rel_err(O.canonicalize_image(g["x"], ang, refl), g["forced_canon"]) < TOL
+    for rep in ("regular", "scalar"):
+        inv = O.invert_image_features(g[f"f_{rep}"], ang, refl, n, num_group, rep)
+        assert rel_err(inv, g[f"forced_inv_{rep}"]) < TOL
+
+
+@pytest.mark.parametrize("case", ["image_opt_d4", "image_opt_c8"])
+def test_optimized_path_matches_reference(case):
+    g = load_golden(case)
+    reflect = g["group_type"] == "roto-reflection"
+    n = g["num_rotations"]
+    num_group = n * (2 if reflect else 1)
+    in_shape = tuple(int(v) for v in g["in_shape"])
+    x_pre = O.pre_network_transform(g["x"], in_shape, g["crop_ratio"], g["resize"])
+    assert rel_err(x_pre, g["x_pre"]) < TOL
+    assert rel_err(O.group_augment(x_pre, n, reflect, g["resize"]), g["x_orbit"]) < TOL
+    act = O.cosine_group_activations(g["vector_out"], g["reference_vector"], num_group)
+    assert rel_err(act, g["act"]) < TOL
+    el = O.activations_to_group_element(g["act"], n, reflect)
+    assert torch.equal(el["rotation"], g["rotation"])
+    assert rel_err(O.canonicalize_image(g["x"], g["rotation"], g.get("reflection")), g["x_canon"]) < TOL
+    v = g["vector_out"]
+    assert abs(float(O.optimization_specific_loss(v, num_group, v.shape[1]) - g["opt_loss"])) < 1e-6
+    assert abs(float(O.prior_loss_discrete(g["act"]) - g["prior_loss"])) < 1e-6
+
+
+def test_pointcloud_matches_reference():
+    g = load_golden("pointcloud_so3")
+    r = O.gram_schmidt(g["vectors"])
+    assert rel_err(r, g["rotation"]) < TOL
+    assert rel_err(O.so3_canonicalize(g["x"], r), g["x_canon"]) < TOL
+    assert abs(float(O.prior_loss_continuous(r) - g["prior_loss"])) < 1e-6
+    assert abs(float(O.identity_metric_continuous(r) - g["identity_metric"])) < 1e-6
+
+
+def test_nbody_matches_reference():
+    g = load_golden("nbody_e3")
+    r = O.modified_gram_schmidt(g["rot_vectors"])
+    assert rel_err(r, g["rotation"]) < TOL
+    cl, cv = O.e3_canonicalize(g["loc"], g["vel"], r, g["translation"])
+    assert rel_err(cl, g["canon_loc"]) < TOL
+    assert rel_err(cv, g["canon_vel"]) < TOL
+    assert rel_err(O.e3_invert(g["pred"], r, g["translation"]), g["inverted"]) < TOL
+
+
+def test_aa_resize_restatement_matches_torch():
+    """The closed-form separable filter the CUDA kernel implements == ATen _upsample_bilinear2d_aa."""
+    g = torch.Generator().manual_seed(3)
+    for (h, w, oh, ow) in [(180, 180, 96, 96), (29, 29, 32, 32), (32, 32, 20, 20), (24, 32, 16, 16), (17, 40, 33, 9)]:
+        x = torch.rand(2, 3, h, w, generator=g)
+        ref = torch.nn.functional.interpolate(x, size=(oh, ow), mode="bilinear", align_corners=False, antialias=True)
+        assert rel_err(O.aa_resize_restated(x, oh, ow), ref) < 2e-6
+
+
+def test_rotate_closed_form_bounds_reference_noise():
+    """kornia-style fp32 rotate vs the exact map (SURVEY.md section 7 hard part 2)."""
+    from oracle import kornia_restated as K
+
+    g = torch.Generator().manual_seed(5)
+    x = torch.rand(8, 3, 32, 32, generator=g)
+    ang = torch.linspace(0.0, 360.0, 9)[:8]
+    ref = K.rotate(x, ang)
+    exact = O.rotate_closed_form(x, ang, clamp=False)
+    assert rel_err(ref, exact) < 1e-4
+    assert torch.equal(exact[2].float(), torch.rot90(x[2], 1, (1, 2)))  # +90 deg == rot90(k=1)
+    y = O.canonicalize_image(x, ang, None)
+    exact_c = O.rotate_closed_form(x, -ang, clamp=True)
+    assert rel_err(y, exact_c) < 1e-4
