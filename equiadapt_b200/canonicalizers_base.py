@@ -1,0 +1,139 @@
+"""The reference's abstract canonicalization surface, kept verbatim in names and call contract.
+
+Mirrors equiadapt/common/basecanonicalization.py: BaseCanonicalization (:29-93),
+IdentityCanonicalization (:96-179), DiscreteGroupCanonicalization (:182-311),
+ContinuousGroupCanonicalization (:314-430).  What differs is underneath: the arg-max / one-hot /
+soft-max / cross-entropy chain and the MSE-to-identity reduction are single sm_100a kernels
+(eqb_group_pool_select, eqb_prior_stats_continuous) that also leave a 3-float statistic, which is
+all-reduced once across ranks when torch.distributed is initialised.
+"""
+from __future__ import annotations
+
+from typing import Any, Dict, List, Optional, Tuple, Union
+
+import torch
+
+from . import distributed as D
+from . import ops
+
+
+class BaseCanonicalization(torch.nn.Module):
+    """forward(x, targets=None, **kw) -> canonicalize(...); owns the network and the info dict."""
+
+    def __init__(self, canonicalization_network: torch.nn.Module):
+        super().__init__()
+        self.canonicalization_network = canonicalization_network
+        self.canonicalization_info_dict: Dict[str, torch.Tensor] = {}
+        # all-reduce the prior statistic across ranks (superset of reference behaviour)
+        self.sync_prior_across_ranks = True
+
+    def forward(self, x: torch.Tensor, targets: Optional[List] = None, **kwargs: Any):
+        return self.canonicalize(x, targets, **kwargs)
+
+    def canonicalize(self, x: torch.Tensor, targets: Optional[List] = None, **kwargs: Any):
+        raise NotImplementedError()
+
+    def invert_canonicalization(self, x_canonicalized_out: torch.Tensor, **kwargs: Any) -> torch.Tensor:
+        raise NotImplementedError()
+
+
+class IdentityCanonicalization(BaseCanonicalization):
+    """No-op canonicalizer (basecanonicalization.py:96-179)."""
+
+    def __init__(self, canonicalization_network: torch.nn.Module = torch.nn.Identity()):
+        super().__init__(canonicalization_network)
+
+    def canonicalize(self, x: torch.Tensor, targets: Optional[List] = None, **kwargs: Any):
+        if targets:
+            return x, targets
+        return x
+
+    def invert_canonicalization(self, x_canonicalized_out: torch.Tensor, **kwargs: Any) -> torch.Tensor:
+        return x_canonicalized_out
+
+    def get_prior_regularization_loss(self) -> torch.Tensor:
+        return torch.tensor(0.0)
+
+    def get_identity_metric(self) -> torch.Tensor:
+        return torch.tensor(1.0)
+
+
+class DiscreteGroupCanonicalization(BaseCanonicalization):
+    """Discrete groups: activations (B,|G|) -> one-hot group element, CE prior, identity metric."""
+
+    def __init__(self, canonicalization_network: torch.nn.Module, beta: float = 1.0,
+                 gradient_trick: str = "straight_through"):
+        super().__init__(canonicalization_network)
+        self.beta = beta
+        self.gradient_trick = gradient_trick
+
+    # filled by subclasses
+    num_group: int
+    num_rotations: int
+    group_type: str
+
+    def _select(self, group_activations: torch.Tensor):
+        """One kernel: arg-max index, angle, reflection flag, one-hot and the prior statistic."""
+        reflect = self.group_type == "roto-reflection"
+        idx, rot, refl, onehot, stats = ops.group_pool_select(group_activations, self.num_rotations, reflect)
+        self._selected = {"activations": group_activations, "idx": idx, "rotation": rot, "reflection": refl,
+                          "onehot": onehot, "stats": stats}
+        return self._selected
+
+    def _selection_for(self, group_activations: torch.Tensor):
+        sel = getattr(self, "_selected", None)
+        if sel is None or sel["activations"] is not group_activations:
+            sel = self._select(group_activations)
+        return sel
+
+    def groupactivations_to_groupelementonehot(self, group_activations: torch.Tensor) -> torch.Tensor:
+        """basecanonicalization.py:221-256.  eval: hard one-hot from the kernel; train: the
+        straight-through expression evaluates to the same values (soft - soft.detach() == 0)."""
+        if self.gradient_trick == "straight_through":
+            onehot = self._selection_for(group_activations)["onehot"]
+            if self.training:
+                soft = torch.nn.functional.softmax(self.beta * group_activations, dim=-1)
+                return onehot + soft - soft.detach()
+            return onehot
+        if self.gradient_trick == "gumbel_softmax":
+            return torch.nn.functional.gumbel_softmax(group_activations, tau=1, hard=True)
+        raise ValueError(f"Gradient trick {self.gradient_trick} not implemented")
+
+    def _discrete_stats(self) -> torch.Tensor:
+        act = self.canonicalization_info_dict["group_activations"]
+        return self._selection_for(act)["stats"]
+
+    def get_prior_regularization_loss(self) -> torch.Tensor:
+        """mean_b CE(act_b, class 0) (basecanonicalization.py:290-301), from [sum CE, sum id, B]."""
+        return D.mean_from_stats(self._discrete_stats(), 0, 2, self.sync_prior_across_ranks)
+
+    def get_identity_metric(self) -> torch.Tensor:
+        """mean_b [argmax == 0] (basecanonicalization.py:303-311)."""
+        return D.mean_from_stats(self._discrete_stats(), 1, 2, self.sync_prior_across_ranks)
+
+
+class ContinuousGroupCanonicalization(BaseCanonicalization):
+    """Continuous groups: MSE-to-identity prior on the (B,d,d) group-element representation."""
+
+    def __init__(self, canonicalization_network: torch.nn.Module, beta: float = 1.0):
+        super().__init__(canonicalization_network)
+        self.beta = beta
+
+    def canonicalizationnetworkout_to_groupelement(self, group_activations: torch.Tensor) -> torch.Tensor:
+        raise NotImplementedError()
+
+    def _continuous_stats(self) -> torch.Tensor:
+        rep = self.canonicalization_info_dict["group_element_matrix_representation"]
+        cached = getattr(self, "_rep_stats", None)
+        if cached is None or cached[0] is not rep:
+            cached = (rep, ops.prior_stats_continuous(rep))
+            self._rep_stats = cached
+        return cached[1]
+
+    def get_prior_regularization_loss(self) -> torch.Tensor:
+        """MSE(R, I) over B*d*d entries (basecanonicalization.py:390-408)."""
+        return D.mean_from_stats(self._continuous_stats(), 0, 1, self.sync_prior_across_ranks)
+
+    def get_identity_metric(self) -> torch.Tensor:
+        """1 - MSE(R, I) (basecanonicalization.py:410-430)."""
+        return 1.0 - self.get_prior_regularization_loss()

@@ -1,0 +1,80 @@
+// Shared helpers for the equiadapt_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/equiadapt_b200.h"
+
+namespace eqb {
+
+void set_error(const char *fmt, ...);
+
+inline int finish_launch(const char *what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("%s: %s", what, cudaGetErrorString(e));
+        return (int)e;
+    }
+    return 0;
+}
+
+#define EQB_REQUIRE(cond, ...)              \
+    do {                                    \
+        if (!(cond)) {                      \
+            eqb::set_error(__VA_ARGS__);    \
+            return EQB_ERR_INVALID;         \
+        }                                   \
+    } while (0)
+
+#define EQB_UNSUPPORTED(cond, ...)          \
+    do {                                    \
+        if (cond) {                         \
+            eqb::set_error(__VA_ARGS__);    \
+            return EQB_ERR_UNSUPPORTED;     \
+        }                                   \
+    } while (0)
+
+#define EQB_CUDA(call)                                                     \
+    do {                                                                   \
+        cudaError_t e__ = (call);                                          \
+        if (e__ != cudaSuccess) {                                          \
+            eqb::set_error("%s: %s", #call, cudaGetErrorString(e__));      \
+            return (int)e__;                                               \
+        }                                                                  \
+    } while (0)
+
+inline int num_sms() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess ||
+            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+            n = 148;
+    }
+    return n;
+}
+
+// 2x2 matrix + flags describing one discrete group element's action on pixel coordinates:
+//   src = centre + A * (dst - centre)
+struct Affine2 {
+    double a00, a01, a10, a11;
+    int exact;  // all entries in {0,+-1}: a pure index permutation when the offsets are integral
+};
+
+// cos/sin of (sign * 2*pi*r/N), exact at quarter turns (sincospi is exact at multiples of 1/2).
+__device__ __forceinline__ void rot_cs(int r, int N, double sign, double &c, double &s) {
+    sincospi(sign * 2.0 * (double)r / (double)N, &s, &c);
+}
+
+__device__ __forceinline__ float ld_stream(const float *p) {
+    float v;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+
+__device__ __forceinline__ void st_stream(float *p, float v) {
+    asm volatile("st.global.L1::no_allocate.f32 [%0], %1;" ::"l"(p), "f"(v));
+}
+
+}  // namespace eqb

@@ -1,0 +1,381 @@
+// Fused group-equivariant conv stack -> group activations (a4..a6).
+//
+// Reference: CustomEquivariantNetwork.forward (custom_equivariant_networks.py:80-93) =
+//   lift conv k x k -> [ReLU -> 1x1 regular group conv] x (L-1) -> mean over (Cout, H', W').
+// The reference materialises every (B, Cout*|G|, H', W') intermediate in HBM (4.4 GB each at
+// BASELINE cfg2) plus separate bias / ReLU passes.  Here the whole stack runs per tile of 64 output
+// pixels without leaving the SM:
+//   im2col tile (K0 x 64) in shared memory -> GEMM with the lifted filter orbit -> +bias, ReLU in
+//   registers -> written back to shared memory as the next layer's operand -> GEMM with the
+//   group-circulant 1x1 orbit -> ... -> masked column sums accumulated in fp64 registers.
+// The LAST layer is linear and followed only by the mean, so it is folded through the pool:
+//   act[g] = sum_k S[k] * (sum_o W'[(o,g),k]) / (Cout*P) + mean(b),   S = spatial sum of its input,
+// an |G| x K mat-vec per image in the finish kernel (same result up to fp32 summation order).
+//
+// This file is the fp32 SIMT implementation (8x8 register tiles, weights streamed K-major through a
+// cp.async double buffer).  It handles any Cout*|G| <= 256.
+#include "common.cuh"
+
+namespace eqb {
+
+int launch_lift_orbit(const float *w, float *out, int cout, int cin, int k, int N, int reflect, long long sn,
+                      long long sk, cudaStream_t st);
+int launch_regular_orbit(const float *w, float *out, int cout, int cin, int k, int N, int reflect, long long sn,
+                         long long sk, cudaStream_t st);
+
+constexpr int GT_TM = 64;      // pixels per tile
+constexpr int GT_PITCH = 68;   // floats per operand row (64 pixels + 4 pad: conflict-free float4 epilogue stores)
+constexpr int GT_KC = 16;      // K rows per streamed weight chunk
+constexpr int GT_THREADS = 256;
+constexpr int GT_MAX_GEMM = 8;
+
+struct StackArgs {
+    const float *x;
+    int B, cin, H, W, ksz, Ho, Wo, P;
+    int K0, K0pad, N, Npad, rows;
+    int n_gemm;
+    int relu_last;  // ReLU on the last executed GEMM layer (num_layers > 1)
+    const float *Wt[GT_MAX_GEMM];    // [Kpad][Npad], K-major
+    const float *bias[GT_MAX_GEMM];  // [Npad]
+    int Kpad[GT_MAX_GEMM];
+    double *S_part;  // [B][chunks][Npad]
+    int tiles, chunks, tiles_per_chunk;
+};
+
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
+
+template <int NT>
+__global__ void __launch_bounds__(GT_THREADS, 2) gconv_stack_kernel(const StackArgs a) {
+    extern __shared__ __align__(16) float sm[];
+    float *act = sm;                                   // [rows][GT_PITCH]
+    float *wbuf = sm + (size_t)a.rows * GT_PITCH;      // [2][GT_KC][Npad]
+    const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+    const int b = blockIdx.x / a.chunks, ch = blockIdx.x - b * a.chunks;
+    const int tile_begin = ch * a.tiles_per_chunk, tile_end = min(a.tiles, tile_begin + a.tiles_per_chunk);
+    const int chunk_f4 = GT_KC * a.Npad / 4;  // float4 per weight chunk
+    const int kk2 = a.ksz * a.ksz;
+    const float *xb = a.x + (size_t)b * a.cin * a.H * a.W;
+
+    double colsum[NT];
+#pragma unroll
+    for (int j = 0; j < NT; ++j) colsum[j] = 0.0;
+
+    for (int tile = tile_begin; tile < tile_end; ++tile) {
+        const int p0 = tile * GT_TM;
+        // ---- im2col: act[k][p] = x[c][oy+ky][ox+kx], zero rows up to K0pad, zero columns past P ------
+        {
+            const int p = tid & (GT_TM - 1), kq = tid >> 6;
+            const int pix = p0 + p;
+            const bool ok = pix < a.P;
+            const int oy = ok ? pix / a.Wo : 0, ox = ok ? pix - oy * a.Wo : 0;
+            const float *xp = xb + (size_t)oy * a.W + ox;
+            for (int k = kq; k < a.K0pad; k += GT_THREADS / GT_TM) {
+                float v = 0.f;
+                if (ok && k < a.K0) {
+                    const int c = k / kk2, rem = k - c * kk2, ky = rem / a.ksz, kx = rem - ky * a.ksz;
+                    v = __ldg(xp + ((size_t)c * a.H + ky) * a.W + kx);
+                }
+                act[k * GT_PITCH + p] = v;
+            }
+        }
+        __syncthreads();
+
+        for (int l = 0; l < a.n_gemm; ++l) {
+            float acc[8][NT];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < NT; ++j) acc[i][j] = 0.f;
+
+            const float *Wt = a.Wt[l];
+            const int nchunks = a.Kpad[l] / GT_KC;
+            for (int i = tid; i < chunk_f4; i += GT_THREADS) cp_async16(wbuf + 4 * i, Wt + 4 * i);
+            cp_async_commit();
+            for (int kc = 0; kc < nchunks; ++kc) {
+                float *wb = wbuf + (kc & 1) * (GT_KC * a.Npad);
+                if (kc + 1 < nchunks) {
+                    float *wn = wbuf + ((kc + 1) & 1) * (GT_KC * a.Npad);
+                    const float *src = Wt + (size_t)(kc + 1) * GT_KC * a.Npad;
+                    for (int i = tid; i < chunk_f4; i += GT_THREADS) cp_async16(wn + 4 * i, src + 4 * i);
+                    cp_async_commit();
+                    cp_async_wait<1>();
+                } else {
+                    cp_async_wait<0>();
+                }
+                __syncthreads();
+                const float *ap = act + (size_t)kc * GT_KC * GT_PITCH + ty * 8;
+#pragma unroll
+                for (int kk = 0; kk < GT_KC; ++kk) {
+                    const float4 a0 = *reinterpret_cast<const float4 *>(ap + kk * GT_PITCH);
+                    const float4 a1 = *reinterpret_cast<const float4 *>(ap + kk * GT_PITCH + 4);
+                    const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+                    float wv[NT];
+#pragma unroll
+                    for (int j = 0; j < NT; ++j) wv[j] = wb[kk * a.Npad + j * 32 + tx];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+#pragma unroll
+                        for (int j = 0; j < NT; ++j) acc[i][j] = fmaf(av[i], wv[j], acc[i][j]);
+                }
+                __syncthreads();  // all reads of wb (and, on the last chunk, of act) are done
+            }
+
+            const float *bias = a.bias[l];
+            if (l + 1 < a.n_gemm) {
+                // +bias, ReLU, becomes the next layer's operand (row = channel, column = pixel)
+#pragma unroll
+                for (int j = 0; j < NT; ++j) {
+                    const int n = j * 32 + tx;
+                    const float bv = bias[n];
+                    float4 o0, o1;
+                    o0.x = fmaxf(acc[0][j] + bv, 0.f); o0.y = fmaxf(acc[1][j] + bv, 0.f);
+                    o0.z = fmaxf(acc[2][j] + bv, 0.f); o0.w = fmaxf(acc[3][j] + bv, 0.f);
+                    o1.x = fmaxf(acc[4][j] + bv, 0.f); o1.y = fmaxf(acc[5][j] + bv, 0.f);
+                    o1.z = fmaxf(acc[6][j] + bv, 0.f); o1.w = fmaxf(acc[7][j] + bv, 0.f);
+                    *reinterpret_cast<float4 *>(act + n * GT_PITCH + ty * 8) = o0;
+                    *reinterpret_cast<float4 *>(act + n * GT_PITCH + ty * 8 + 4) = o1;
+                }
+                __syncthreads();
+            } else {
+                // last executed layer: masked spatial sum of this thread's 8 pixels
+#pragma unroll
+                for (int j = 0; j < NT; ++j) {
+                    const float bv = bias[j * 32 + tx];
+                    float s = 0.f;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        float v = acc[i][j] + bv;
+                        if (a.relu_last) v = fmaxf(v, 0.f);
+                        if (p0 + ty * 8 + i < a.P) s += v;
+                    }
+                    colsum[j] += (double)s;
+                }
+            }
+        }
+    }
+
+    // ---- reduce the 8 pixel groups (warps) and emit this chunk's partial sums ------------------------
+    __syncthreads();
+    double *red = reinterpret_cast<double *>(sm);  // [8][Npad] doubles, fits: rows*68*4 >= 8*Npad*8
+#pragma unroll
+    for (int j = 0; j < NT; ++j) red[ty * a.Npad + j * 32 + tx] = colsum[j];
+    __syncthreads();
+    for (int n = tid; n < a.Npad; n += GT_THREADS) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) s += red[w * a.Npad + n];
+        a.S_part[((size_t)b * a.chunks + ch) * a.Npad + n] = s;
+    }
+}
+
+// M[k][g]: what multiplies the spatial sums.  fold: sum_o W_last'[(o,g),k] for the 1x1 regular layer
+// (k = i*|G|+h, W'[(o,g),(i,h)] = W[o,i,slice(g,h)]);  no fold (single layer): indicator k%|G|==g.
+__device__ __forceinline__ int fold_src_slice(int g, int h, int N) {
+    if (g < N) return h < N ? (h - g + N) % N : N + (h - N + g) % N;
+    const int gp = g - N;
+    return h < N ? N + (h + gp) % N : (h - N - gp + N) % N;
+}
+
+__global__ void build_fold_matrix_kernel(const float *__restrict__ w_last, double *__restrict__ M, int cout, int N,
+                                         int G, int Npad, int fold) {
+    const int total = Npad * G;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+        const int k = t / G, g = t - k * G;
+        double v = 0.0;
+        if (k < cout * G) {
+            if (fold) {
+                const int i = k / G, h = k - i * G;
+                const int src = fold_src_slice(g, h, N);
+                for (int o = 0; o < cout; ++o) v += (double)w_last[((size_t)o * cout + i) * G + src];
+            } else {
+                v = (k % G == g) ? 1.0 : 0.0;
+            }
+        }
+        M[t] = v;
+    }
+}
+
+__global__ void expand_bias_kernel(const float *__restrict__ bias, float *__restrict__ out, int N, int G, int Npad) {
+    for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < Npad; n += gridDim.x * blockDim.x)
+        out[n] = (bias && n < N) ? bias[n / G] : 0.f;
+}
+
+// one block per image: S = sum of chunk partials; act[g] = S . M[:,g] / (Cout*P) + mean(last bias)
+__global__ void __launch_bounds__(256) gconv_finish_kernel(const double *__restrict__ S_part,
+                                                           const double *__restrict__ M,
+                                                           const float *__restrict__ last_bias, int cout, int chunks,
+                                                           int Npad, int G, double inv_count, float *__restrict__ act) {
+    extern __shared__ double S[];  // [Npad]
+    __shared__ double red[8];
+    const int b = blockIdx.x;
+    for (int n = threadIdx.x; n < Npad; n += blockDim.x) {
+        double s = 0.0;
+        for (int c = 0; c < chunks; ++c) s += S_part[((size_t)b * chunks + c) * Npad + n];
+        S[n] = s;
+    }
+    __syncthreads();
+    double bmean = 0.0;
+    if (last_bias) {
+        for (int o = 0; o < cout; ++o) bmean += (double)last_bias[o];
+        bmean /= cout;
+    }
+    for (int g = 0; g < G; ++g) {
+        double v = 0.0;
+        for (int n = threadIdx.x; n < Npad; n += blockDim.x) v += S[n] * M[(size_t)n * G + g];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double t = 0.0;
+            for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+            act[(size_t)b * G + g] = (float)(t * inv_count + bmean);
+        }
+        __syncthreads();
+    }
+}
+
+struct StackPlan {
+    int G, N, Npad, K0, K0pad, Ho, Wo, P, rows, n_gemm, tiles, chunks, tiles_per_chunk;
+    size_t off_wt[GT_MAX_GEMM], off_bias[GT_MAX_GEMM], off_M, off_S, total;
+    size_t smem;
+};
+
+static int make_plan(int B, int cin, int H, int W, int cout, int k, int N, int reflect, int L, StackPlan &p) {
+    EQB_REQUIRE(B >= 0 && cin > 0 && H > 0 && W > 0 && cout > 0 && k > 0 && N > 0 && L >= 1,
+                "eqb_gconv_stack: bad argument");
+    EQB_REQUIRE(H >= k && W >= k, "eqb_gconv_stack: image %dx%d smaller than the %dx%d kernel", H, W, k, k);
+    p.G = N * (reflect ? 2 : 1);
+    p.N = cout * p.G;
+    EQB_UNSUPPORTED(p.N > 256, "eqb_gconv_stack: out_channels*|G| = %d > 256 not supported by this build", p.N);
+    EQB_UNSUPPORTED(L - 1 > GT_MAX_GEMM, "eqb_gconv_stack: more than %d layers not supported", GT_MAX_GEMM + 1);
+    const int nt = p.N <= 32 ? 1 : p.N <= 64 ? 2 : p.N <= 128 ? 4 : 8;
+    p.Npad = 32 * nt;
+    p.K0 = cin * k * k;
+    p.K0pad = (p.K0 + GT_KC - 1) / GT_KC * GT_KC;
+    p.Ho = H - k + 1;
+    p.Wo = W - k + 1;
+    p.P = p.Ho * p.Wo;
+    p.rows = p.K0pad > p.Npad ? p.K0pad : p.Npad;
+    p.n_gemm = L == 1 ? 1 : L - 1;
+    p.tiles = (p.P + GT_TM - 1) / GT_TM;
+    // enough CTAs for ~8 waves at 2 CTAs/SM, but never fewer than ~4 tiles per CTA when avoidable
+    const int target = num_sms() * 2 * 8;
+    int chunks = B > 0 ? (target + B - 1) / B : 1;
+    if (chunks > p.tiles) chunks = p.tiles;
+    if (chunks < 1) chunks = 1;
+    p.tiles_per_chunk = (p.tiles + chunks - 1) / chunks;
+    p.chunks = (p.tiles + p.tiles_per_chunk - 1) / p.tiles_per_chunk;
+    p.smem = ((size_t)p.rows * GT_PITCH + 2 * GT_KC * p.Npad) * sizeof(float);
+    EQB_UNSUPPORTED(p.smem > 200 * 1024, "eqb_gconv_stack: Cin*k*k = %d too large for the shared-memory tile", p.K0);
+    size_t off = 0;
+    for (int l = 0; l < p.n_gemm; ++l) {
+        const size_t kp = l == 0 ? p.K0pad : p.Npad;
+        p.off_wt[l] = off;
+        off += kp * p.Npad * sizeof(float);
+    }
+    for (int l = 0; l < p.n_gemm; ++l) {
+        p.off_bias[l] = off;
+        off += (size_t)p.Npad * sizeof(float);
+    }
+    p.off_M = off;
+    off += (size_t)p.Npad * p.G * sizeof(double);
+    p.off_S = off;
+    off += (size_t)(B > 0 ? B : 1) * p.chunks * p.Npad * sizeof(double);
+    p.total = off;
+    return 0;
+}
+
+template <int NT>
+static int launch_stack(const StackArgs &a, size_t smem, cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        EQB_CUDA(cudaFuncSetAttribute(gconv_stack_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        configured = true;
+    }
+    gconv_stack_kernel<NT><<<(unsigned)(a.B * a.chunks), GT_THREADS, smem, st>>>(a);
+    return finish_launch("gconv_stack_kernel");
+}
+
+}  // namespace eqb
+
+using namespace eqb;
+
+extern "C" int64_t eqb_gconv_stack_workspace_bytes(int B, int cin, int H, int W, int cout, int k, int num_rotations,
+                                                   int reflect, int num_layers) {
+    StackPlan p;
+    const int rc = make_plan(B, cin, H, W, cout, k, num_rotations, reflect, num_layers, p);
+    if (rc) return rc;
+    return (int64_t)p.total;
+}
+
+extern "C" int eqb_gconv_stack_forward(const float *x, int B, int cin, int H, int W, const float *lift_w,
+                                       const float *lift_b, const float *const *reg_w, const float *const *reg_b,
+                                       int cout, int k, int num_rotations, int reflect, int num_layers, float *act,
+                                       void *workspace, int64_t workspace_bytes, void *stream) {
+    StackPlan p;
+    const int rc = make_plan(B, cin, H, W, cout, k, num_rotations, reflect, num_layers, p);
+    if (rc) return rc;
+    if (B == 0) return 0;
+    EQB_REQUIRE(x && lift_w && act && workspace, "eqb_gconv_stack_forward: null pointer");
+    EQB_REQUIRE(num_layers == 1 || (reg_w && reg_b), "eqb_gconv_stack_forward: null layer table");
+    EQB_REQUIRE(workspace_bytes >= (int64_t)p.total, "eqb_gconv_stack_forward: workspace %lld < %lld bytes",
+                (long long)workspace_bytes, (long long)p.total);
+    EQB_REQUIRE(((uintptr_t)workspace & 15) == 0, "eqb_gconv_stack_forward: workspace must be 16-byte aligned");
+    EQB_REQUIRE((long long)B * p.chunks < (1LL << 31), "eqb_gconv_stack_forward: grid too large");
+    cudaStream_t st = (cudaStream_t)stream;
+    char *ws = (char *)workspace;
+    const int L = num_layers, reflect01 = reflect != 0;
+
+    // ---- pack: filter orbits as zero-padded K-major GEMM operands, expanded biases, fold matrix ----
+    EQB_CUDA(cudaMemsetAsync(ws, 0, p.off_bias[0], st));
+    int e = launch_lift_orbit(lift_w, (float *)(ws + p.off_wt[0]), cout, cin, k, num_rotations, reflect01, 1, p.Npad, st);
+    if (e) return e;
+    for (int l = 1; l < p.n_gemm; ++l) {
+        EQB_REQUIRE(reg_w[l - 1], "eqb_gconv_stack_forward: null weight for layer %d", l);
+        e = launch_regular_orbit(reg_w[l - 1], (float *)(ws + p.off_wt[l]), cout, cout, 1, num_rotations, reflect01, 1,
+                                 p.Npad, st);
+        if (e) return e;
+    }
+    for (int l = 0; l < p.n_gemm; ++l) {
+        const float *bsrc = l == 0 ? lift_b : reg_b[l - 1];
+        expand_bias_kernel<<<1, 256, 0, st>>>(bsrc, (float *)(ws + p.off_bias[l]), p.N, p.G, p.Npad);
+    }
+    const float *w_last = L > 1 ? reg_w[L - 2] : nullptr;
+    const float *b_last = L > 1 ? reg_b[L - 2] : nullptr;
+    EQB_REQUIRE(L == 1 || w_last, "eqb_gconv_stack_forward: null weight for the last layer");
+    build_fold_matrix_kernel<<<(p.Npad * p.G + 255) / 256, 256, 0, st>>>(w_last, (double *)(ws + p.off_M), cout,
+                                                                         num_rotations, p.G, p.Npad, L > 1);
+    e = finish_launch("gconv pack");
+    if (e) return e;
+
+    // ---- fused stack ------------------------------------------------------------------------------
+    StackArgs a{};
+    a.x = x; a.B = B; a.cin = cin; a.H = H; a.W = W; a.ksz = k; a.Ho = p.Ho; a.Wo = p.Wo; a.P = p.P;
+    a.K0 = p.K0; a.K0pad = p.K0pad; a.N = p.N; a.Npad = p.Npad; a.rows = p.rows;
+    a.n_gemm = p.n_gemm; a.relu_last = L > 1;
+    for (int l = 0; l < p.n_gemm; ++l) {
+        a.Wt[l] = (const float *)(ws + p.off_wt[l]);
+        a.bias[l] = (const float *)(ws + p.off_bias[l]);
+        a.Kpad[l] = l == 0 ? p.K0pad : p.Npad;
+    }
+    a.S_part = (double *)(ws + p.off_S);
+    a.tiles = p.tiles; a.chunks = p.chunks; a.tiles_per_chunk = p.tiles_per_chunk;
+    switch (p.Npad / 32) {
+        case 1: e = launch_stack<1>(a, p.smem, st); break;
+        case 2: e = launch_stack<2>(a, p.smem, st); break;
+        case 4: e = launch_stack<4>(a, p.smem, st); break;
+        default: e = launch_stack<8>(a, p.smem, st); break;
+    }
+    if (e) return e;
+
+    const double inv_count = 1.0 / ((double)cout * (double)p.P);
+    gconv_finish_kernel<<<B, 256, p.Npad * sizeof(double), st>>>(a.S_part, (const double *)(ws + p.off_M), b_last, cout,
+                                                                p.chunks, p.Npad, p.G, inv_count, act);
+    return finish_launch("gconv_finish_kernel");
+}

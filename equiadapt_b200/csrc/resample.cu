@@ -1,0 +1,277 @@
+// Group-action image resampling: one kernel family behind eqb_warp_canonicalize (a10),
+// eqb_warp_invert (a11) and eqb_orbit_expand (a12).
+//
+// Every discrete group element acts on pixel coordinates as  src = centre + A (dst - centre)  with a
+// 2x2 matrix A built from (cos, sin) of a multiple of 360/N degrees and optional mirror signs.
+// What the reference does with pad(replicate) -> hflip blend -> kornia rotate -> crop
+// (discrete_group.py:207-215; images/utils.py:57-64; discrete_group.py:401-409) collapses to ONE
+// pass over the data: each output pixel is a 4-tap bilinear sample of the source image, taps clamped
+// into the image (replicate) while inside the padded extent and zero beyond it.  Quarter turns give
+// integral source coordinates, i.e. a pure permutation (the reference's fp32 matrix is +-4e-8 off
+// that, SURVEY.md section 7, hard part 2).
+//
+// HBM-bound design (B200): a CTA owns a 32x32 output tile of one image.  The source footprint of the
+// tile (<= 46x46 for any angle) is staged row-wise with coalesced loads into shared memory for up to
+// CG channels at once (odd pitch -> the diagonal / column gathers are bank-conflict free or 2-way),
+// the bilinear weights are computed once per pixel in fp64 and reused for every channel, and each
+// warp writes full 128-byte rows.  Algorithmic traffic: 1 read + 1 write of the image; the 2x
+// footprint overlap between neighbouring tiles is absorbed by L2.
+#include "common.cuh"
+
+namespace eqb {
+
+constexpr int TILE = 32;
+constexpr int BB = 48;       // max footprint side
+constexpr int PITCH = 49;    // odd pitch
+constexpr int THREADS = 256;
+constexpr int PIX = TILE * TILE / THREADS;  // 4 pixels per thread
+
+enum { MODE_CANON = 0, MODE_INV_SCALAR = 1, MODE_INV_REGULAR = 2, MODE_ORBIT = 3 };
+
+struct ResampleArgs {
+    const float *src;
+    float *dst;
+    const int32_t *idx;  // per source sample group element (unused for MODE_ORBIT)
+    int B;               // source samples
+    int C, Hs, Ws, Hd, Wd;
+    int N, reflect, G;
+    signed char roll[64];  // regular-rep channel shift per rotation index (see regular_roll_shift)
+    int mode;
+    int pad;        // >=0: taps inside [-pad, size-1+pad] are replicate-clamped, zero beyond
+    double ox, oy;  // dst pixel -> coordinate relative to the rotation centre: u = xd + ox
+    int tiles_x, tiles_y;
+};
+
+template <int CG>
+__global__ void __launch_bounds__(THREADS) resample_kernel(const ResampleArgs a) {
+    extern __shared__ float smem[];  // [CG][BB][PITCH]
+    const int tiles = a.tiles_x * a.tiles_y;
+    const int sample_d = blockIdx.x / tiles;  // destination sample
+    const int t = blockIdx.x - sample_d * tiles;
+    const int ty0 = (t / a.tiles_x) * TILE, tx0 = (t % a.tiles_x) * TILE;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    // ---- group element of this sample -> A ------------------------------------------------
+    int sample_s, r, mirror_src = 0, mirror_dst = 0;
+    double sign;
+    if (a.mode == MODE_ORBIT) {
+        const int g = sample_d / a.B;
+        sample_s = sample_d - g * a.B;
+        r = g % a.N;
+        mirror_dst = g >= a.N;  // rotate, THEN hflip (discrete_group.py:404-406)
+        sign = -1.0;
+    } else {
+        sample_s = sample_d;
+        const int g = min(max(a.idx[sample_s], 0), a.G - 1);
+        r = g % a.N;
+        const int refl = g >= a.N;
+        if (a.mode == MODE_CANON) {
+            mirror_src = refl;  // hflip, THEN rotate(-theta) (discrete_group.py:209-213)
+            sign = -1.0;
+        } else {
+            // rotate(+theta), then x*r + hflip(x)*(1-r): un-reflected samples of a reflection
+            // group come back mirrored (images/utils.py:59-64, reference quirk A.4-2)
+            mirror_dst = a.reflect && !refl;
+            sign = 1.0;
+        }
+    }
+    double c, s;
+    rot_cs(r, a.N, sign, c, s);
+    // src = centre + [[c,-s],[s,c]] (u,v);  mirror_dst: u -> -u;  mirror_src: xs -> (Ws-1) - xs
+    double a00 = c, a01 = -s, a10 = s, a11 = c;
+    if (mirror_dst) { a00 = -a00; a10 = -a10; }
+    if (mirror_src) { a00 = -a00; a01 = -a01; }
+    const double cx = 0.5 * (a.Ws - 1), cy = 0.5 * (a.Hs - 1);
+
+    // ---- source footprint of the tile --------------------------------------------------------
+    const int tw = min(TILE, a.Wd - tx0), th = min(TILE, a.Hd - ty0);
+    double xmin = 1e300, xmax = -1e300, ymin = 1e300, ymax = -1e300;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const double u = (double)(tx0 + ((k & 1) ? tw - 1 : 0)) + a.ox;
+        const double v = (double)(ty0 + ((k & 2) ? th - 1 : 0)) + a.oy;
+        const double xs = cx + a00 * u + a01 * v, ys = cy + a10 * u + a11 * v;
+        xmin = fmin(xmin, xs); xmax = fmax(xmax, xs);
+        ymin = fmin(ymin, ys); ymax = fmax(ymax, ys);
+    }
+    const int x_lo = min(max((int)floor(xmin), 0), a.Ws - 1);
+    const int x_hi = min(max((int)floor(xmax) + 1, 0), a.Ws - 1);
+    const int y_lo = min(max((int)floor(ymin), 0), a.Hs - 1);
+    const int y_hi = min(max((int)floor(ymax) + 1, 0), a.Hs - 1);
+    const int bw = x_hi - x_lo + 1, bh = y_hi - y_lo + 1;
+
+    // ---- per-pixel taps (shared by all channels) --------------------------------------------
+    float w00[PIX], w01[PIX], w10[PIX], w11[PIX];
+    int o00[PIX], o01[PIX], o10[PIX], o11[PIX];
+    const int xd = tx0 + lane;
+#pragma unroll
+    for (int p = 0; p < PIX; ++p) {
+        const int yd = ty0 + warp + p * (THREADS / 32);
+        const double u = (double)xd + a.ox, v = (double)yd + a.oy;
+        const double xs = cx + a00 * u + a01 * v, ys = cy + a10 * u + a11 * v;
+        const double xf = floor(xs), yf = floor(ys);
+        const float fx = (float)(xs - xf), fy = (float)(ys - yf);
+        const int x0 = (int)xf, y0 = (int)yf, x1 = x0 + 1, y1 = y0 + 1;
+        const int lo_x = -a.pad, hi_x = a.Ws - 1 + a.pad, lo_y = -a.pad, hi_y = a.Hs - 1 + a.pad;
+        const float vx0 = (x0 >= lo_x && x0 <= hi_x) ? 1.f : 0.f, vx1 = (x1 >= lo_x && x1 <= hi_x) ? 1.f : 0.f;
+        const float vy0 = (y0 >= lo_y && y0 <= hi_y) ? 1.f : 0.f, vy1 = (y1 >= lo_y && y1 <= hi_y) ? 1.f : 0.f;
+        // taps are clamped into the staged footprint (which itself is clamped into the image)
+        const int cx0 = min(max(x0, x_lo), x_hi) - x_lo, cx1 = min(max(x1, x_lo), x_hi) - x_lo;
+        const int cy0 = (min(max(y0, y_lo), y_hi) - y_lo) * PITCH, cy1 = (min(max(y1, y_lo), y_hi) - y_lo) * PITCH;
+        w00[p] = (1.f - fy) * (1.f - fx) * vy0 * vx0;
+        w01[p] = (1.f - fy) * fx * vy0 * vx1;
+        w10[p] = fy * (1.f - fx) * vy1 * vx0;
+        w11[p] = fy * fx * vy1 * vx1;
+        o00[p] = cy0 + cx0; o01[p] = cy0 + cx1; o10[p] = cy1 + cx0; o11[p] = cy1 + cx1;
+    }
+
+    const size_t plane_s = (size_t)a.Hs * a.Ws, plane_d = (size_t)a.Hd * a.Wd;
+    const float *src_n = a.src + (size_t)sample_s * a.C * plane_s;
+    float *dst_n = a.dst + (size_t)sample_d * a.C * plane_d;
+
+    for (int c0 = 0; c0 < a.C; c0 += CG) {
+        const int nc = min(CG, a.C - c0);
+        if (c0) __syncthreads();
+        // ---- stage the footprint, coalesced along rows ---------------------------------------
+        for (int cc = 0; cc < nc; ++cc) {
+            int cs = c0 + cc;
+            if (a.mode == MODE_INV_REGULAR) {
+                // out[:, f*G+g] = in[:, f*G + src_g(g)]   (roll_by_gather, images/utils.py:8-29,66-77)
+                const int f = cs / a.G, g = cs - f * a.G, sh = a.roll[r];
+                int sg;
+                if (g < a.N) sg = (g - sh + a.N) % a.N;
+                else sg = a.N + (g - a.N + sh) % a.N;
+                cs = f * a.G + sg;
+            }
+            const float *sp = src_n + (size_t)cs * plane_s + (size_t)y_lo * a.Ws + x_lo;
+            float *sm = smem + cc * (BB * PITCH);
+            for (int row = warp; row < bh; row += THREADS / 32) {
+                const float *rp = sp + (size_t)row * a.Ws;
+                if (lane < bw) sm[row * PITCH + lane] = __ldg(rp + lane);
+                if (lane + 32 < bw) sm[row * PITCH + lane + 32] = __ldg(rp + lane + 32);
+            }
+        }
+        __syncthreads();
+        // ---- gather + store ------------------------------------------------------------------
+        if (xd < a.Wd) {
+            for (int cc = 0; cc < nc; ++cc) {
+                const float *sm = smem + cc * (BB * PITCH);
+                float *dp = dst_n + (size_t)(c0 + cc) * plane_d + xd;
+#pragma unroll
+                for (int p = 0; p < PIX; ++p) {
+                    const int yd = ty0 + warp + p * (THREADS / 32);
+                    if (yd < a.Hd) {
+                        // same tap order as ATen grid_sample: nw, ne, sw, se
+                        float v = sm[o00[p]] * w00[p];
+                        v = fmaf(sm[o01[p]], w01[p], v);
+                        v = fmaf(sm[o10[p]], w10[p], v);
+                        v = fmaf(sm[o11[p]], w11[p], v);
+                        st_stream(dp + (size_t)yd * a.Wd, v);
+                    }
+                }
+            }
+        }
+    }
+}
+
+// The reference turns the angle back into a channel shift in fp32 and TRUNCATES it:
+//   shift = (angle / 360.0 * num_rotations).long()          (images/utils.py:67, :28)
+// with angle = torch.linspace(0, 360, N+1)[r] (discrete_group.py:110-112).  For N a power of two
+// this is exactly r; for other N the fp32 round trip can land just below r and truncate to r-1
+// (reference quirk).  Reproduced here op for op in IEEE float.
+static int regular_roll_shift(int r, int N) {
+    const volatile float step = (360.0f - 0.0f) / (float)N;  // at::linspace, step_t = float
+    const int steps = N + 1, halfway = steps / 2;
+    volatile float angle = (r < halfway) ? 0.0f + step * (float)r : 360.0f - step * (float)(steps - r - 1);
+    volatile float q = angle / 360.0f;
+    volatile float sh = q * (float)N;
+    return (int)sh;  // .long() truncates toward zero
+}
+
+static int launch_resample(ResampleArgs &a, int n_dst_samples, cudaStream_t st, const char *what) {
+    a.tiles_x = (a.Wd + TILE - 1) / TILE;
+    a.tiles_y = (a.Hd + TILE - 1) / TILE;
+    const long long blocks = (long long)a.tiles_x * a.tiles_y * n_dst_samples;
+    if (blocks == 0) return 0;
+    EQB_REQUIRE(blocks < (1LL << 31), "%s: grid too large (%lld tiles)", what, blocks);
+    const int cg = (a.C % 3 == 0 && a.C % 4 != 0) ? 3 : (a.C >= 4 ? 4 : a.C);
+    const size_t smem = (size_t)cg * BB * PITCH * sizeof(float);
+    switch (cg) {
+        case 1: resample_kernel<1><<<(unsigned)blocks, THREADS, smem, st>>>(a); break;
+        case 2: resample_kernel<2><<<(unsigned)blocks, THREADS, smem, st>>>(a); break;
+        case 3: resample_kernel<3><<<(unsigned)blocks, THREADS, smem, st>>>(a); break;
+        default: resample_kernel<4><<<(unsigned)blocks, THREADS, smem, st>>>(a); break;
+    }
+    return finish_launch(what);
+}
+
+}  // namespace eqb
+
+using namespace eqb;
+
+// host-only helper exported for tests: the truncated channel shift the reference derives from angle r*360/N
+extern "C" int eqb_regular_roll_shift(int r, int num_rotations) { return regular_roll_shift(r, num_rotations); }
+
+extern "C" int eqb_warp_canonicalize(const float *x, float *y, const int32_t *idx, int B, int C, int H, int W,
+                                     int num_rotations, int reflect, void *stream) {
+    EQB_REQUIRE(B >= 0 && C > 0 && H > 0 && W > 0, "eqb_warp_canonicalize: bad shape (%d,%d,%d,%d)", B, C, H, W);
+    EQB_REQUIRE(num_rotations > 0, "eqb_warp_canonicalize: num_rotations must be positive");
+    EQB_REQUIRE(B == 0 || (x && y && idx), "eqb_warp_canonicalize: null pointer");
+    ResampleArgs a{};
+    a.src = x; a.dst = y; a.idx = idx; a.B = B; a.C = C;
+    a.Hs = a.Hd = H; a.Ws = a.Wd = W;
+    a.N = num_rotations; a.reflect = reflect != 0; a.G = num_rotations * (reflect ? 2 : 1);
+    a.mode = MODE_CANON;
+    // Pad(ceil(W/2), edge) on all four sides for C != 1, Identity for grayscale (discrete_group.py:60-66)
+    a.pad = (C == 1) ? 0 : (W + 1) / 2;
+    a.ox = -0.5 * (W - 1); a.oy = -0.5 * (H - 1);
+    return launch_resample(a, B, (cudaStream_t)stream, "eqb_warp_canonicalize");
+}
+
+extern "C" int eqb_warp_invert(const float *f, float *out, const int32_t *idx, int B, int C, int H, int W,
+                               int num_rotations, int reflect, int rep, void *stream) {
+    EQB_REQUIRE(B >= 0 && C > 0 && H > 0 && W > 0, "eqb_warp_invert: bad shape (%d,%d,%d,%d)", B, C, H, W);
+    EQB_REQUIRE(num_rotations > 0, "eqb_warp_invert: num_rotations must be positive");
+    EQB_REQUIRE(rep == EQB_REP_SCALAR || rep == EQB_REP_REGULAR, "eqb_warp_invert: rep must be scalar or regular");
+    const int G = num_rotations * (reflect ? 2 : 1);
+    EQB_REQUIRE(rep != EQB_REP_REGULAR || C % G == 0,
+                "eqb_warp_invert: regular representation needs C %% |G| == 0 (C=%d, |G|=%d)", C, G);
+    EQB_REQUIRE(B == 0 || (f && out && idx), "eqb_warp_invert: null pointer");
+    ResampleArgs a{};
+    a.src = f; a.dst = out; a.idx = idx; a.B = B; a.C = C;
+    a.Hs = a.Hd = H; a.Ws = a.Wd = W;
+    a.N = num_rotations; a.reflect = reflect != 0; a.G = G;
+    a.mode = rep == EQB_REP_REGULAR ? MODE_INV_REGULAR : MODE_INV_SCALAR;
+    if (rep == EQB_REP_REGULAR) {
+        EQB_UNSUPPORTED(num_rotations > 64, "eqb_warp_invert: regular representation supports num_rotations <= 64");
+        for (int r = 0; r < num_rotations; ++r) a.roll[r] = (signed char)regular_roll_shift(r, num_rotations);
+    }
+    a.pad = 0;  // bare kornia rotate: zero fill (images/utils.py:57)
+    a.ox = -0.5 * (W - 1); a.oy = -0.5 * (H - 1);
+    return launch_resample(a, B, (cudaStream_t)stream, "eqb_warp_invert");
+}
+
+extern "C" int eqb_orbit_expand(const float *x, float *out, int B, int C, int h, int w, int pad, int out_size,
+                                int num_rotations, int reflect, void *stream) {
+    EQB_REQUIRE(B >= 0 && C > 0 && h > 0 && w > 0, "eqb_orbit_expand: bad shape (%d,%d,%d,%d)", B, C, h, w);
+    EQB_REQUIRE(num_rotations > 0 && pad >= 0, "eqb_orbit_expand: bad group / pad");
+    ResampleArgs a{};
+    a.src = x; a.dst = out; a.idx = nullptr; a.B = B; a.C = C;
+    a.Hs = h; a.Ws = w;
+    a.N = num_rotations; a.reflect = reflect != 0; a.G = num_rotations * (reflect ? 2 : 1);
+    a.mode = MODE_ORBIT;
+    if (C == 1) {  // grayscale: pad_group_augment / crop_group_augment are Identity (discrete_group.py:365-376)
+        a.pad = 0; a.Hd = h; a.Wd = w;
+        a.ox = -0.5 * (w - 1); a.oy = -0.5 * (h - 1);
+    } else {
+        EQB_REQUIRE(out_size > 0 && out_size <= h + 2 * pad && out_size <= w + 2 * pad,
+                    "eqb_orbit_expand: crop %d does not fit the padded image", out_size);
+        a.pad = pad; a.Hd = a.Wd = out_size;
+        // CenterCrop offsets in the padded frame (python round == rint, half to even)
+        const double left = rint((w + 2 * pad - out_size) / 2.0), top = rint((h + 2 * pad - out_size) / 2.0);
+        a.ox = left - 0.5 * (w + 2 * pad - 1);
+        a.oy = top - 0.5 * (h + 2 * pad - 1);
+    }
+    EQB_REQUIRE(B == 0 || (x && out), "eqb_orbit_expand: null pointer");
+    return launch_resample(a, B * a.G, (cudaStream_t)stream, "eqb_orbit_expand");
+}

@@ -1,0 +1,511 @@
+// Latency-bound pieces of the hot path: pre-network crop+resize (a3), filter orbits (a4/a5),
+// group pool / select + prior statistic (a9/a13), cosine activations (a12), frames (a14..a17).
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace eqb {
+
+static thread_local char g_err[512] = "";
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+// -------------------------------------------------------------------------------------------------
+// a3: CenterCrop + antialiased bilinear resize.  Separable triangle filter of ATen's
+// _upsample_bilinear2d_aa (align_corners=False): per output index i, centre = scale*(i+0.5),
+// support = max(scale,1), taps j in [max(0,int(centre-support+.5)), min(in,int(centre+support+.5))),
+// w_j = max(0, 1-|(j-centre+.5)/max(scale,1)|) normalised to sum 1.
+// One thread per output pixel; horizontal pass first, then vertical, as ATen does.
+// -------------------------------------------------------------------------------------------------
+constexpr int AA_MAX_TAPS = 16;
+
+struct AaAxis {
+    int lo, n;
+    float w[AA_MAX_TAPS];
+};
+
+__device__ __forceinline__ void aa_axis(int i, int in_size, float scale, AaAxis &ax) {
+    const float support = scale >= 1.f ? scale : 1.f;
+    const float invscale = scale >= 1.f ? 1.f / scale : 1.f;
+    const float center = scale * (i + 0.5f);
+    const int lo = max((int)(center - support + 0.5f), 0);
+    const int hi = min((int)(center + support + 0.5f), in_size);
+    ax.lo = lo;
+    ax.n = min(hi - lo, AA_MAX_TAPS);
+    float tot = 0.f;
+    for (int j = 0; j < ax.n; ++j) {
+        const float v = fmaxf(1.f - fabsf((j + lo - center + 0.5f) * invscale), 0.f);
+        ax.w[j] = v;
+        tot += v;
+    }
+    for (int j = 0; j < ax.n; ++j) ax.w[j] = tot != 0.f ? ax.w[j] / tot : 0.f;
+}
+
+__global__ void __launch_bounds__(256) crop_resize_aa_kernel(const float *__restrict__ x, float *__restrict__ y,
+                                                             int planes, int H, int W, int top, int left, int ch,
+                                                             int cw, int oh, int ow, float sy, float sx) {
+    const long long total = (long long)planes * oh * ow;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+         t += (long long)gridDim.x * blockDim.x) {
+        const int ox = (int)(t % ow);
+        const long long r = t / ow;
+        const int oy = (int)(r % oh);
+        const long long pl = r / oh;
+        AaAxis ax, ay;
+        aa_axis(ox, cw, sx, ax);
+        aa_axis(oy, ch, sy, ay);
+        const float *src = x + (size_t)pl * H * W + (size_t)(top + ay.lo) * W + left + ax.lo;
+        float acc = 0.f;
+        for (int j = 0; j < ay.n; ++j) {
+            float h = 0.f;
+            for (int i = 0; i < ax.n; ++i) h = fmaf(__ldg(src + (size_t)j * W + i), ax.w[i], h);
+            acc = fmaf(h, ay.w[j], acc);
+        }
+        y[t] = acc;
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// a4 / a5: filter orbits.  T_g(w)(y,x) = bilinear zero-fill sample of w rotated by angle_g about the
+// kernel centre (kornia.rotate, positive = counter-clockwise), then hflip for reflected elements.
+// Output element (n, kk) is written at out[n*sn + kk*sk] so the same kernel emits the conv2d layout
+// (sn = K, sk = 1) and the K-major, zero-padded GEMM operand of the fused stack (sn = 1, sk = Npad).
+// -------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float rotated_tap(const float *__restrict__ w, int k, int y, int x, int r, int N,
+                                             bool mirror) {
+    if (mirror) x = k - 1 - x;  // hflip AFTER the rotation: out(x) = rot(k-1-x)
+    double c, s;
+    rot_cs(r, N, 1.0, c, s);
+    const double ctr = 0.5 * (k - 1);
+    const double u = x - ctr, v = y - ctr;
+    const double xs = ctr + c * u - s * v, ys = ctr + s * u + c * v;
+    const double xf = floor(xs), yf = floor(ys);
+    const float fx = (float)(xs - xf), fy = (float)(ys - yf);
+    const int x0 = (int)xf, y0 = (int)yf;
+    float acc = 0.f;
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) {
+            const int xi = x0 + dx, yi = y0 + dy;
+            if (xi >= 0 && xi < k && yi >= 0 && yi < k) {
+                const float wt = (dy ? fy : 1.f - fy) * (dx ? fx : 1.f - fx);
+                acc = fmaf(w[yi * k + xi], wt, acc);
+            }
+        }
+    return acc;
+}
+
+__global__ void lift_orbit_kernel(const float *__restrict__ w, float *__restrict__ out, int cout, int cin, int k,
+                                  int N, int G, long long sn, long long sk) {
+    const int kk2 = k * k, K = cin * kk2;
+    const long long total = (long long)cout * G * K;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+         t += (long long)gridDim.x * blockDim.x) {
+        const int kk = (int)(t % K);
+        const int n = (int)(t / K);
+        const int o = n / G, g = n % G;
+        const int i = kk / kk2, yx = kk % kk2;
+        out[n * sn + kk * sk] = rotated_tap(w + ((size_t)o * cin + i) * kk2, k, yx / k, yx % k, g % N, N, g >= N);
+    }
+}
+
+// input-group slice of W feeding (g,h): C_N custom_group_equivariant_layers.py:283-293, D_N :420-449
+__device__ __forceinline__ int regular_src_slice(int g, int h, int N) {
+    if (g < N) return h < N ? (h - g + N) % N : N + (h - N + g) % N;
+    const int gp = g - N;
+    return h < N ? N + (h + gp) % N : (h - N - gp + N) % N;
+}
+
+__global__ void regular_orbit_kernel(const float *__restrict__ w, float *__restrict__ out, int cout, int cin, int k,
+                                     int N, int G, long long sn, long long sk) {
+    const int kk2 = k * k, K = cin * G * kk2;
+    const long long total = (long long)cout * G * K;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+         t += (long long)gridDim.x * blockDim.x) {
+        const int kk = (int)(t % K);
+        const int n = (int)(t / K);
+        const int o = n / G, g = n % G;
+        const int ih = kk / kk2, yx = kk % kk2;
+        const int i = ih / G, h = ih % G;
+        const int src = regular_src_slice(g, h, N);
+        out[n * sn + kk * sk] =
+            rotated_tap(w + (((size_t)o * cin + i) * G + src) * kk2, k, yx / k, yx % k, g % N, N, g >= N);
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// a9 + a13: group pool / select.  One thread per sample (|G| <= 64 values), grid-stride; CE and
+// identity counts are reduced per block with warp shuffles and finished, in block order (so the
+// result is run-to-run deterministic), by the last block to arrive.
+// -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) group_pool_select_kernel(const float *__restrict__ act, int B, int N, int G,
+                                                                int32_t *__restrict__ idx, float *__restrict__ rotation,
+                                                                float *__restrict__ reflection,
+                                                                float *__restrict__ onehot, float *__restrict__ stats,
+                                                                double *__restrict__ partial) {
+    double ce = 0.0, ident = 0.0;
+    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) {
+        const float *a = act + (size_t)b * G;
+        float best = a[0];
+        int bi = 0;
+        for (int g = 1; g < G; ++g) {
+            const float v = a[g];
+            if (v > best || (v != v && best == best)) {  // first max; NaN wins like torch.argmax
+                best = v;
+                bi = g;
+            }
+        }
+        float se = 0.f;
+        for (int g = 0; g < G; ++g) se += expf(a[g] - best);
+        ce += (double)((best + logf(se)) - a[0]);  // logsumexp(a) - a[0] == CE(a, class 0)
+        ident += bi == 0 ? 1.0 : 0.0;
+        idx[b] = bi;
+        // torch.linspace(0, 360, N+1)[r] in fp32 (two symmetric halves), discrete_group.py:110-112
+        const int r = bi % N;
+        const float step = 360.0f / (float)N;
+        rotation[b] = (r < (N + 1) / 2) ? __fmul_rn(step, (float)r) : 360.0f - __fmul_rn(step, (float)(N - r));
+        if (reflection) reflection[b] = bi >= N ? 1.f : 0.f;
+        if (onehot)
+            for (int g = 0; g < G; ++g) onehot[(size_t)b * G + g] = g == bi ? 1.f : 0.f;
+    }
+    __shared__ double s_ce[8], s_id[8];
+    for (int o = 16; o > 0; o >>= 1) {
+        ce += __shfl_xor_sync(0xffffffffu, ce, o);
+        ident += __shfl_xor_sync(0xffffffffu, ident, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        s_ce[threadIdx.x >> 5] = ce;
+        s_id[threadIdx.x >> 5] = ident;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double c = 0.0, d = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
+            c += s_ce[w];
+            d += s_id[w];
+        }
+        if (gridDim.x == 1) {
+            stats[0] = (float)c;
+            stats[1] = (float)d;
+            stats[2] = (float)B;
+        } else {
+            partial[2 * blockIdx.x] = c;
+            partial[2 * blockIdx.x + 1] = d;
+        }
+    }
+}
+
+// sums `n` block partials (stride-2 pairs) in block order: run-to-run deterministic
+__global__ void finish_stats_kernel(const double *__restrict__ partial, int n, int pairs, float third,
+                                    float *__restrict__ stats) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double c = 0.0, d = 0.0;
+    for (int k = 0; k < n; ++k) {
+        c += partial[pairs * k];
+        if (pairs == 2) d += partial[2 * k + 1];
+    }
+    stats[0] = (float)c;
+    stats[1] = pairs == 2 ? (float)d : third;
+    stats[2] = pairs == 2 ? third : 0.f;
+}
+
+// a12: cosine similarity to the reference vector, (|G|*B, V) -> (B,|G|).  One warp per row.
+// ATen cosine_similarity: x/max(||x||,eps) . y/max(||y||,eps), eps = 1e-8.
+__global__ void __launch_bounds__(256) cosine_act_kernel(const float *__restrict__ vec, const float *__restrict__ ref,
+                                                         float *__restrict__ act, int B, int G, int V) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= B * G) return;
+    const float *v = vec + (size_t)row * V;
+    float vv = 0.f, rr = 0.f;
+    for (int i = lane; i < V; i += 32) {
+        vv = fmaf(v[i], v[i], vv);
+        rr = fmaf(ref[i], ref[i], rr);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        vv += __shfl_xor_sync(0xffffffffu, vv, o);
+        rr += __shfl_xor_sync(0xffffffffu, rr, o);
+    }
+    const float nv = fmaxf(sqrtf(vv), 1e-8f), nr = fmaxf(sqrtf(rr), 1e-8f);
+    float dot = 0.f;
+    for (int i = lane; i < V; i += 32) dot = fmaf(ref[i] / nr, v[i] / nv, dot);
+    for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+    if (lane == 0) {
+        const int g = row / B, b = row - g * B;  // rows are group-major
+        act[(size_t)b * G + g] = dot;
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// a14..a17: frames
+// -------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float norm3(float x, float y, float z) {
+    // torch.norm over 3 elements: sqrt of the plain fp32 sum of squares
+    return sqrtf(x * x + y * y + z * z);
+}
+
+__device__ __forceinline__ void gs3(const float *v, float *R, bool modified) {
+    float a0 = v[0], a1 = v[1], a2 = v[2];
+    float n = norm3(a0, a1, a2);
+    a0 /= n; a1 /= n; a2 /= n;
+    float d = v[3] * a0 + v[4] * a1 + v[5] * a2;
+    float b0 = v[3] - d * a0, b1 = v[4] - d * a1, b2 = v[5] - d * a2;
+    n = norm3(b0, b1, b2);
+    b0 /= n; b1 /= n; b2 /= n;
+    float c0, c1, c2;
+    const float d1 = v[6] * a0 + v[7] * a1 + v[8] * a2;
+    if (!modified) {
+        const float d2 = v[6] * b0 + v[7] * b1 + v[8] * b2;
+        c0 = v[6] - d1 * a0 - d2 * b0;
+        c1 = v[7] - d1 * a1 - d2 * b1;
+        c2 = v[8] - d1 * a2 - d2 * b2;
+    } else {
+        c0 = v[6] - d1 * a0; c1 = v[7] - d1 * a1; c2 = v[8] - d1 * a2;
+        const float d2 = c0 * b0 + c1 * b1 + c2 * b2;
+        c0 -= d2 * b0; c1 -= d2 * b1; c2 -= d2 * b2;
+    }
+    n = norm3(c0, c1, c2);
+    R[0] = a0; R[1] = a1; R[2] = a2;
+    R[3] = b0; R[4] = b1; R[5] = b2;
+    R[6] = c0 / n; R[7] = c1 / n; R[8] = c2 / n;
+}
+
+__global__ void gram_schmidt3_kernel(const float *__restrict__ v, float *__restrict__ R, int B, int modified) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    float in[9], out[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) in[i] = v[(size_t)b * 9 + i];
+    gs3(in, out, modified != 0);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) R[(size_t)b * 9 + i] = out[i];
+}
+
+// y[b,:,n] = R[b] x[b,:,n]; x is (B,3,N): three coalesced streams per cloud, R in registers.
+__global__ void __launch_bounds__(256) so3_apply_kernel(const float *__restrict__ x, const float *__restrict__ R,
+                                                        float *__restrict__ y, int B, int N, int chunks) {
+    const int b = blockIdx.x / chunks, ch = blockIdx.x % chunks;
+    float r[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) r[i] = __ldg(R + (size_t)b * 9 + i);
+    const float *xb = x + (size_t)b * 3 * N;
+    float *yb = y + (size_t)b * 3 * N;
+    for (int n = ch * blockDim.x + threadIdx.x; n < N; n += chunks * blockDim.x) {
+        const float p0 = xb[n], p1 = xb[N + n], p2 = xb[2 * N + n];
+        // bmm(x^T, R^T): out_j = sum_k x_k R[j][k], k ascending
+        yb[n] = fmaf(p2, r[2], fmaf(p1, r[1], p0 * r[0]));
+        yb[N + n] = fmaf(p2, r[5], fmaf(p1, r[4], p0 * r[3]));
+        yb[2 * N + n] = fmaf(p2, r[8], fmaf(p1, r[7], p0 * r[6]));
+    }
+}
+
+__global__ void __launch_bounds__(256) e3_apply_kernel(const float *__restrict__ loc, const float *__restrict__ vel,
+                                                       const float *__restrict__ R, const float *__restrict__ t,
+                                                       float *__restrict__ lc, float *__restrict__ vc, int M) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= M) return;
+    float r[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) r[i] = R[(size_t)m * 9 + i];
+    const float l0 = loc[3 * m], l1 = loc[3 * m + 1], l2 = loc[3 * m + 2];
+    const float v0 = vel[3 * m], v1 = vel[3 * m + 1], v2 = vel[3 * m + 2];
+    const float t0 = t[3 * m], t1 = t[3 * m + 1], t2 = t[3 * m + 2];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        // row-vector times R^T: out_j = sum_k in_k R[j][k]; loc R^T - t R^T as two separate products
+        const float a = fmaf(l2, r[3 * j + 2], fmaf(l1, r[3 * j + 1], l0 * r[3 * j]));
+        const float b = fmaf(t2, r[3 * j + 2], fmaf(t1, r[3 * j + 1], t0 * r[3 * j]));
+        lc[3 * m + j] = a - b;
+        vc[3 * m + j] = fmaf(v2, r[3 * j + 2], fmaf(v1, r[3 * j + 1], v0 * r[3 * j]));
+    }
+}
+
+__global__ void __launch_bounds__(256) e3_invert_kernel(const float *__restrict__ x, const float *__restrict__ R,
+                                                        const float *__restrict__ t, float *__restrict__ y, int M) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= M) return;
+    const float x0 = x[3 * m], x1 = x[3 * m + 1], x2 = x[3 * m + 2];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        // x R + t: out_j = sum_k x_k R[k][j]
+        const float a = fmaf(x2, R[(size_t)m * 9 + 6 + j], fmaf(x1, R[(size_t)m * 9 + 3 + j], x0 * R[(size_t)m * 9 + j]));
+        y[3 * m + j] = a + t[3 * m + j];
+    }
+}
+
+__global__ void __launch_bounds__(256) prior_stats_continuous_kernel(const float *__restrict__ R, long long total, int d,
+                                                                     float count, float *__restrict__ stats,
+                                                                     double *__restrict__ partial) {
+    double acc = 0.0;
+    const int dd = d * d;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int e = (int)(i % dd);
+        const float diff = R[i] - ((e / d == e % d) ? 1.f : 0.f);
+        acc += (double)(diff * diff);
+    }
+    __shared__ double s[8];
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double c = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) c += s[w];
+        if (gridDim.x == 1) {
+            stats[0] = (float)c;
+            stats[1] = count;
+            stats[2] = 0.f;
+        } else {
+            partial[blockIdx.x] = c;
+        }
+    }
+}
+
+static inline unsigned grid_for(long long total, int threads, int max_blocks) {
+    long long b = (total + threads - 1) / threads;
+    if (b < 1) b = 1;
+    if (b > max_blocks) b = max_blocks;
+    return (unsigned)b;
+}
+
+}  // namespace eqb
+
+using namespace eqb;
+
+extern "C" int eqb_abi_version(void) { return EQB_ABI_VERSION; }
+extern "C" const char *eqb_last_error(void) { return g_err; }
+
+extern "C" int eqb_crop_resize_aa(const float *x, float *y, int B, int C, int H, int W, int top, int left, int crop_h,
+                                  int crop_w, int out_h, int out_w, void *stream) {
+    EQB_REQUIRE(B >= 0 && C > 0 && H > 0 && W > 0 && out_h > 0 && out_w > 0, "eqb_crop_resize_aa: bad shape");
+    EQB_REQUIRE(top >= 0 && left >= 0 && crop_h > 0 && crop_w > 0 && top + crop_h <= H && left + crop_w <= W,
+                "eqb_crop_resize_aa: crop window [%d+%d, %d+%d] outside %dx%d", top, crop_h, left, crop_w, H, W);
+    const float sy = (float)crop_h / (float)out_h, sx = (float)crop_w / (float)out_w;
+    const float sup_y = sy >= 1.f ? sy : 1.f, sup_x = sx >= 1.f ? sx : 1.f;
+    EQB_UNSUPPORTED((int)(2 * sup_y + 2) > AA_MAX_TAPS || (int)(2 * sup_x + 2) > AA_MAX_TAPS,
+                    "eqb_crop_resize_aa: down-scale factor above %d not supported", (AA_MAX_TAPS - 2) / 2);
+    if (B == 0) return 0;
+    EQB_REQUIRE(x && y, "eqb_crop_resize_aa: null pointer");
+    const long long total = (long long)B * C * out_h * out_w;
+    crop_resize_aa_kernel<<<grid_for(total, 256, num_sms() * 16), 256, 0, (cudaStream_t)stream>>>(
+        x, y, B * C, H, W, top, left, crop_h, crop_w, out_h, out_w, sy, sx);
+    return finish_launch("eqb_crop_resize_aa");
+}
+
+namespace eqb {
+int launch_lift_orbit(const float *w, float *out, int cout, int cin, int k, int N, int reflect, long long sn,
+                      long long sk, cudaStream_t st) {
+    const int G = N * (reflect ? 2 : 1);
+    const long long total = (long long)cout * G * cin * k * k;
+    lift_orbit_kernel<<<grid_for(total, 256, 4096), 256, 0, st>>>(w, out, cout, cin, k, N, G, sn, sk);
+    return finish_launch("lift_orbit");
+}
+int launch_regular_orbit(const float *w, float *out, int cout, int cin, int k, int N, int reflect, long long sn,
+                         long long sk, cudaStream_t st) {
+    const int G = N * (reflect ? 2 : 1);
+    const long long total = (long long)cout * G * cin * G * k * k;
+    regular_orbit_kernel<<<grid_for(total, 256, 4096), 256, 0, st>>>(w, out, cout, cin, k, N, G, sn, sk);
+    return finish_launch("regular_orbit");
+}
+}  // namespace eqb
+
+extern "C" int eqb_lift_filter_orbit(const float *w, float *orbit, int cout, int cin, int k, int num_rotations,
+                                     int reflect, void *stream) {
+    EQB_REQUIRE(cout > 0 && cin > 0 && k > 0 && num_rotations > 0 && w && orbit, "eqb_lift_filter_orbit: bad argument");
+    return launch_lift_orbit(w, orbit, cout, cin, k, num_rotations, reflect, (long long)cin * k * k, 1,
+                             (cudaStream_t)stream);
+}
+
+extern "C" int eqb_regular_filter_orbit(const float *w, float *orbit, int cout, int cin, int k, int num_rotations,
+                                        int reflect, void *stream) {
+    EQB_REQUIRE(cout > 0 && cin > 0 && k > 0 && num_rotations > 0 && w && orbit,
+                "eqb_regular_filter_orbit: bad argument");
+    const int G = num_rotations * (reflect ? 2 : 1);
+    return launch_regular_orbit(w, orbit, cout, cin, k, num_rotations, reflect, (long long)cin * G * k * k, 1,
+                                (cudaStream_t)stream);
+}
+
+extern "C" int eqb_group_pool_select(const float *act, int B, int num_rotations, int reflect, int32_t *idx,
+                                     float *rotation, float *reflection, float *onehot, float *stats, void *stream) {
+    EQB_REQUIRE(B >= 0 && num_rotations > 0, "eqb_group_pool_select: bad shape");
+    EQB_REQUIRE(stats && (B == 0 || (act && idx && rotation)), "eqb_group_pool_select: null pointer");
+    const int G = num_rotations * (reflect ? 2 : 1);
+    const unsigned blocks = grid_for(B, 256, 1024);
+    cudaStream_t st = (cudaStream_t)stream;
+    double *scratch = nullptr;
+    if (blocks > 1) EQB_CUDA(cudaMallocAsync((void **)&scratch, sizeof(double) * 2 * blocks, st));
+    group_pool_select_kernel<<<blocks, 256, 0, st>>>(act, B, num_rotations, G, idx, rotation,
+                                                     reflect ? reflection : nullptr, onehot, stats, scratch);
+    if (blocks > 1) {
+        finish_stats_kernel<<<1, 32, 0, st>>>(scratch, (int)blocks, 2, (float)B, stats);
+        EQB_CUDA(cudaFreeAsync(scratch, st));
+    }
+    return finish_launch("eqb_group_pool_select");
+}
+
+extern "C" int eqb_cosine_group_activations(const float *vec, const float *ref, float *act, int B, int num_group, int V,
+                                            void *stream) {
+    EQB_REQUIRE(B >= 0 && num_group > 0 && V > 0, "eqb_cosine_group_activations: bad shape");
+    if (B == 0) return 0;
+    EQB_REQUIRE(vec && ref && act, "eqb_cosine_group_activations: null pointer");
+    const int rows = B * num_group;
+    cosine_act_kernel<<<(rows + 7) / 8, 256, 0, (cudaStream_t)stream>>>(vec, ref, act, B, num_group, V);
+    return finish_launch("eqb_cosine_group_activations");
+}
+
+extern "C" int eqb_gram_schmidt3(const float *v, float *R, int B, int modified, void *stream) {
+    EQB_REQUIRE(B >= 0, "eqb_gram_schmidt3: bad batch");
+    if (B == 0) return 0;
+    EQB_REQUIRE(v && R, "eqb_gram_schmidt3: null pointer");
+    gram_schmidt3_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(v, R, B, modified);
+    return finish_launch("eqb_gram_schmidt3");
+}
+
+extern "C" int eqb_so3_apply(const float *x, const float *R, float *y, int B, int N, void *stream) {
+    EQB_REQUIRE(B >= 0 && N >= 0, "eqb_so3_apply: bad shape");
+    if (B == 0 || N == 0) return 0;
+    EQB_REQUIRE(x && R && y, "eqb_so3_apply: null pointer");
+    int chunks = (N + 1023) / 1024;  // 4 points per thread
+    if (chunks < 1) chunks = 1;
+    EQB_REQUIRE((long long)B * chunks < (1LL << 31), "eqb_so3_apply: grid too large");
+    so3_apply_kernel<<<(unsigned)(B * chunks), 256, 0, (cudaStream_t)stream>>>(x, R, y, B, N, chunks);
+    return finish_launch("eqb_so3_apply");
+}
+
+extern "C" int eqb_e3_apply(const float *loc, const float *vel, const float *R, const float *t, float *loc_c,
+                            float *vel_c, int M, void *stream) {
+    EQB_REQUIRE(M >= 0, "eqb_e3_apply: bad row count");
+    if (M == 0) return 0;
+    EQB_REQUIRE(loc && vel && R && t && loc_c && vel_c, "eqb_e3_apply: null pointer");
+    e3_apply_kernel<<<(M + 255) / 256, 256, 0, (cudaStream_t)stream>>>(loc, vel, R, t, loc_c, vel_c, M);
+    return finish_launch("eqb_e3_apply");
+}
+
+extern "C" int eqb_e3_invert(const float *x, const float *R, const float *t, float *y, int M, void *stream) {
+    EQB_REQUIRE(M >= 0, "eqb_e3_invert: bad row count");
+    if (M == 0) return 0;
+    EQB_REQUIRE(x && R && t && y, "eqb_e3_invert: null pointer");
+    e3_invert_kernel<<<(M + 255) / 256, 256, 0, (cudaStream_t)stream>>>(x, R, t, y, M);
+    return finish_launch("eqb_e3_invert");
+}
+
+extern "C" int eqb_prior_stats_continuous(const float *R, int B, int d, float *stats, void *stream) {
+    EQB_REQUIRE(B >= 0 && d > 0 && stats, "eqb_prior_stats_continuous: bad argument");
+    EQB_REQUIRE(B == 0 || R, "eqb_prior_stats_continuous: null pointer");
+    const long long total = (long long)B * d * d;
+    const unsigned blocks = grid_for(total, 256, 1024);
+    cudaStream_t st = (cudaStream_t)stream;
+    double *scratch = nullptr;
+    if (blocks > 1) EQB_CUDA(cudaMallocAsync((void **)&scratch, sizeof(double) * blocks, st));
+    prior_stats_continuous_kernel<<<blocks, 256, 0, st>>>(R, total, d, (float)total, stats, scratch);
+    if (blocks > 1) {
+        finish_stats_kernel<<<1, 32, 0, st>>>(scratch, (int)blocks, 1, (float)total, stats);
+        EQB_CUDA(cudaFreeAsync(scratch, st));
+    }
+    return finish_launch("eqb_prior_stats_continuous");
+}

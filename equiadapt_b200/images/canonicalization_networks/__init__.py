@@ -1,0 +1,3 @@
+from .custom_equivariant_networks import CustomEquivariantNetwork  # noqa: F401
+from .custom_group_equivariant_layers import (RotationEquivariantConv, RotationEquivariantConvLift,  # noqa: F401
+                                              RotoReflectionEquivariantConv, RotoReflectionEquivariantConvLift)

@@ -1,0 +1,254 @@
+"""Tensor-level calls into the C ABI (include/equiadapt_b200.h).
+
+PyTorch is only the allocator and the stream here: every function checks its tensors, takes
+`data_ptr()`s and the CURRENT torch stream, and enqueues the hand-written sm_100a kernels.
+Nothing synchronises the host and nothing falls back to torch arithmetic: CPU tensors raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import native
+
+# kernels launched through this module since import (bench.py reports the count per step)
+launch_count = 0
+
+
+def _need_cuda(*tensors: torch.Tensor) -> torch.device:
+    dev = None
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError(
+                "equiadapt_b200 runs on CUDA tensors only (there is no CPU fallback); got a tensor on " + str(t.device))
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise RuntimeError(f"tensors on different devices: {dev} and {t.device}")
+    return dev
+
+
+def _f32(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        raise TypeError(f"equiadapt_b200 computes in float32; got {t.dtype}")
+    return t.detach().contiguous()
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _stream(dev: torch.device) -> int:
+    return torch.cuda.current_stream(dev).cuda_stream
+
+
+def _call(name: str, n_launches: int, dev: torch.device, *args):
+    global launch_count
+    with torch.cuda.device(dev):
+        native.check(getattr(native.lib(), name)(*args), name)
+    launch_count += n_launches
+
+
+# ---- a3 -----------------------------------------------------------------------------------------
+def crop_resize_aa(x: torch.Tensor, top: int, left: int, crop_h: int, crop_w: int, out_h: int, out_w: int) -> torch.Tensor:
+    dev = _need_cuda(x)
+    x = _f32(x)
+    b, c, h, w = x.shape
+    y = torch.empty((b, c, out_h, out_w), dtype=torch.float32, device=dev)
+    _call("eqb_crop_resize_aa", 1, dev, _ptr(x), _ptr(y), b, c, h, w, top, left, crop_h, crop_w, out_h, out_w, _stream(dev))
+    return y
+
+
+# ---- a4 / a5 ------------------------------------------------------------------------------------
+def lift_filter_orbit(w: torch.Tensor, num_rotations: int, reflect: bool) -> torch.Tensor:
+    dev = _need_cuda(w)
+    w = _f32(w)
+    cout, cin, k, k2 = w.shape
+    assert k == k2
+    g = num_rotations * (2 if reflect else 1)
+    out = torch.empty((cout * g, cin, k, k), dtype=torch.float32, device=dev)
+    _call("eqb_lift_filter_orbit", 1, dev, _ptr(w), _ptr(out), cout, cin, k, num_rotations, int(reflect), _stream(dev))
+    return out
+
+
+def regular_filter_orbit(w: torch.Tensor, num_rotations: int, reflect: bool) -> torch.Tensor:
+    dev = _need_cuda(w)
+    w = _f32(w)
+    cout, cin, g, k, k2 = w.shape
+    assert k == k2 and g == num_rotations * (2 if reflect else 1)
+    out = torch.empty((cout * g, cin * g, k, k), dtype=torch.float32, device=dev)
+    _call("eqb_regular_filter_orbit", 1, dev, _ptr(w), _ptr(out), cout, cin, k, num_rotations, int(reflect), _stream(dev))
+    return out
+
+
+# ---- a4..a6 -------------------------------------------------------------------------------------
+def gconv_stack_forward(x: torch.Tensor, lift_w: torch.Tensor, lift_b: Optional[torch.Tensor],
+                        reg_w: Sequence[torch.Tensor], reg_b: Sequence[Optional[torch.Tensor]],
+                        num_rotations: int, reflect: bool) -> torch.Tensor:
+    dev = _need_cuda(x, lift_w, lift_b, *reg_w, *reg_b)
+    x = _f32(x)
+    lift_w = _f32(lift_w)
+    lift_b = None if lift_b is None else _f32(lift_b)
+    reg_w = [_f32(w) for w in reg_w]
+    reg_b = [None if b is None else _f32(b) for b in reg_b]
+    b, cin, h, w = x.shape
+    cout, cin2, k, _ = lift_w.shape
+    if cin2 != cin:
+        raise ValueError(f"lift weights expect {cin2} input channels, image has {cin}")
+    g = num_rotations * (2 if reflect else 1)
+    n_layers = 1 + len(reg_w)
+    for rw in reg_w:
+        if tuple(rw.shape) != (cout, cout, g, 1, 1):
+            raise ValueError(f"regular layer weights must be ({cout},{cout},{g},1,1), got {tuple(rw.shape)}")
+    lib = native.lib()
+    ws_bytes = lib.eqb_gconv_stack_workspace_bytes(b, cin, h, w, cout, k, num_rotations, int(reflect), n_layers)
+    if ws_bytes < 0:
+        native.check(int(ws_bytes), "eqb_gconv_stack_workspace_bytes")
+    ws = torch.empty((max(int(ws_bytes), 16),), dtype=torch.uint8, device=dev)
+    act = torch.empty((b, g), dtype=torch.float32, device=dev)
+    n = max(len(reg_w), 1)
+    wp = (C.c_void_p * n)(*[_ptr(t) for t in reg_w]) if reg_w else (C.c_void_p * 1)(None)
+    bp = (C.c_void_p * n)(*[_ptr(t) for t in reg_b]) if reg_w else (C.c_void_p * 1)(None)
+    n_gemm = max(n_layers - 1, 1)
+    _call("eqb_gconv_stack_forward", 3 + 2 * n_gemm, dev, _ptr(x), b, cin, h, w, _ptr(lift_w), _ptr(lift_b), wp, bp,
+          cout, k, num_rotations, int(reflect), n_layers, _ptr(act), _ptr(ws), int(ws_bytes), _stream(dev))
+    return act
+
+
+# ---- a9 + a13 -----------------------------------------------------------------------------------
+def group_pool_select(act: torch.Tensor, num_rotations: int, reflect: bool, want_onehot: bool = True):
+    """-> idx (B) int32, rotation (B) degrees, reflection (B) or None, onehot (B,|G|) or None, stats (3)."""
+    dev = _need_cuda(act)
+    act = _f32(act)
+    b, g = act.shape
+    if g != num_rotations * (2 if reflect else 1):
+        raise ValueError(f"activations have {g} columns, group has {num_rotations * (2 if reflect else 1)} elements")
+    idx = torch.empty((b,), dtype=torch.int32, device=dev)
+    rot = torch.empty((b,), dtype=torch.float32, device=dev)
+    refl = torch.empty((b,), dtype=torch.float32, device=dev) if reflect else None
+    onehot = torch.empty((b, g), dtype=torch.float32, device=dev) if want_onehot else None
+    stats = torch.empty((3,), dtype=torch.float32, device=dev)
+    _call("eqb_group_pool_select", 1 if b <= 256 else 2, dev, _ptr(act), b, num_rotations, int(reflect), _ptr(idx),
+          _ptr(rot), _ptr(refl), _ptr(onehot), _ptr(stats), _stream(dev))
+    return idx, rot, refl, onehot, stats
+
+
+# ---- a10 / a11 / a12 ------------------------------------------------------------------------------
+def _idx32(idx: torch.Tensor) -> torch.Tensor:
+    if idx.dtype != torch.int32:
+        idx = idx.to(torch.int32)
+    return idx.contiguous()
+
+
+def warp_canonicalize(x: torch.Tensor, idx: torch.Tensor, num_rotations: int, reflect: bool) -> torch.Tensor:
+    dev = _need_cuda(x, idx)
+    x = _f32(x)
+    idx = _idx32(idx)
+    b, c, h, w = x.shape
+    if idx.numel() != b:
+        raise ValueError("one group element per sample expected")
+    y = torch.empty_like(x)
+    _call("eqb_warp_canonicalize", 1, dev, _ptr(x), _ptr(y), _ptr(idx), b, c, h, w, num_rotations, int(reflect), _stream(dev))
+    return y
+
+
+def warp_invert(f: torch.Tensor, idx: torch.Tensor, num_rotations: int, reflect: bool, regular: bool) -> torch.Tensor:
+    dev = _need_cuda(f, idx)
+    f = _f32(f)
+    idx = _idx32(idx)
+    b, c, h, w = f.shape
+    if idx.numel() != b:
+        raise ValueError("one group element per sample expected")
+    out = torch.empty_like(f)
+    _call("eqb_warp_invert", 1, dev, _ptr(f), _ptr(out), _ptr(idx), b, c, h, w, num_rotations, int(reflect),
+          native.REP_REGULAR if regular else native.REP_SCALAR, _stream(dev))
+    return out
+
+
+def orbit_expand(x: torch.Tensor, pad: int, out_size: int, num_rotations: int, reflect: bool) -> torch.Tensor:
+    dev = _need_cuda(x)
+    x = _f32(x)
+    b, c, h, w = x.shape
+    g = num_rotations * (2 if reflect else 1)
+    oh, ow = (h, w) if c == 1 else (out_size, out_size)
+    out = torch.empty((g * b, c, oh, ow), dtype=torch.float32, device=dev)
+    _call("eqb_orbit_expand", 1, dev, _ptr(x), _ptr(out), b, c, h, w, pad, out_size, num_rotations, int(reflect), _stream(dev))
+    return out
+
+
+def cosine_group_activations(vec: torch.Tensor, ref: torch.Tensor, num_group: int) -> torch.Tensor:
+    dev = _need_cuda(vec, ref)
+    vec = _f32(vec)
+    ref = _f32(ref).reshape(-1)
+    rows, v = vec.shape
+    if rows % num_group or ref.numel() != v:
+        raise ValueError("vector_out must be (|G|*B, V) and the reference vector (1, V)")
+    b = rows // num_group
+    act = torch.empty((b, num_group), dtype=torch.float32, device=dev)
+    _call("eqb_cosine_group_activations", 1, dev, _ptr(vec), _ptr(ref), _ptr(act), b, num_group, v, _stream(dev))
+    return act
+
+
+# ---- a14 .. a17 -----------------------------------------------------------------------------------
+def gram_schmidt3(v: torch.Tensor, modified: bool = False) -> torch.Tensor:
+    dev = _need_cuda(v)
+    v = _f32(v)
+    if v.dim() != 3 or v.shape[1:] != (3, 3):
+        raise ValueError(f"expected (B,3,3) vectors, got {tuple(v.shape)}")
+    out = torch.empty_like(v)
+    _call("eqb_gram_schmidt3", 1, dev, _ptr(v), _ptr(out), v.shape[0], int(modified), _stream(dev))
+    return out
+
+
+def so3_apply(x: torch.Tensor, rot: torch.Tensor) -> torch.Tensor:
+    dev = _need_cuda(x, rot)
+    x = _f32(x)
+    rot = _f32(rot)
+    b, three, n = x.shape
+    if three != 3 or tuple(rot.shape) != (b, 3, 3):
+        raise ValueError("expected x (B,3,N) and rotation (B,3,3)")
+    y = torch.empty_like(x)
+    _call("eqb_so3_apply", 1, dev, _ptr(x), _ptr(rot), _ptr(y), b, n, _stream(dev))
+    return y
+
+
+def e3_apply(loc: torch.Tensor, vel: torch.Tensor, rot: torch.Tensor, t: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    dev = _need_cuda(loc, vel, rot, t)
+    loc, vel, rot, t = _f32(loc), _f32(vel), _f32(rot), _f32(t)
+    m = loc.shape[0]
+    if tuple(loc.shape) != (m, 3) or tuple(vel.shape) != (m, 3) or tuple(rot.shape) != (m, 3, 3) or tuple(t.shape) != (m, 3):
+        raise ValueError("expected loc, vel, t (M,3) and rotation (M,3,3)")
+    lc, vc = torch.empty_like(loc), torch.empty_like(vel)
+    _call("eqb_e3_apply", 1, dev, _ptr(loc), _ptr(vel), _ptr(rot), _ptr(t), _ptr(lc), _ptr(vc), m, _stream(dev))
+    return lc, vc
+
+
+def e3_invert(x: torch.Tensor, rot: torch.Tensor, t: torch.Tensor) -> torch.Tensor:
+    dev = _need_cuda(x, rot, t)
+    x, rot, t = _f32(x), _f32(rot), _f32(t)
+    m = x.shape[0]
+    if tuple(x.shape) != (m, 3) or tuple(rot.shape) != (m, 3, 3) or tuple(t.shape) != (m, 3):
+        raise ValueError("expected x, t (M,3) and rotation (M,3,3)")
+    y = torch.empty_like(x)
+    _call("eqb_e3_invert", 1, dev, _ptr(x), _ptr(rot), _ptr(t), _ptr(y), m, _stream(dev))
+    return y
+
+
+def prior_stats_continuous(rep: torch.Tensor) -> torch.Tensor:
+    """-> stats (3) = [sum (R-I)^2, B*d*d, 0]."""
+    dev = _need_cuda(rep)
+    rep = _f32(rep)
+    b, d, d2 = rep.shape
+    if d != d2:
+        raise ValueError("expected square group-element matrices")
+    stats = torch.empty((3,), dtype=torch.float32, device=dev)
+    _call("eqb_prior_stats_continuous", 1 if b * d * d <= 256 else 2, dev, _ptr(rep), b, d, _ptr(stats), _stream(dev))
+    return stats
+
+
+def regular_roll_shift(r: int, num_rotations: int) -> int:
+    return int(native.lib().eqb_regular_roll_shift(r, num_rotations))

@@ -1,0 +1,128 @@
+/* equiadapt_b200 -- C ABI of the B200-native canonicalization hot path.
+ *
+ * The reference (arnab39/equiadapt) is pure Python/PyTorch and has no FFI of its own; the
+ * "interface" each entry point replaces is therefore the reference Python function (or the
+ * chain of library kernels it dispatches), cited as file:line relative to /root/reference.
+ * INTEGRATION.md shows the ctypes stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to contiguous row-major float32 unless stated;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); all work is
+ *     enqueued on it, nothing synchronises the host;
+ *   - return value: 0 = ok, <0 = argument error (EQB_ERR_*), >0 = cudaError_t of the launch;
+ *     eqb_last_error() returns a thread-local message for the last non-zero return;
+ *   - a discrete group element is an int32 index g in [0,|G|): g <  N : rotation g*360/N degrees,
+ *                                                               g >= N : rotation (g-N)*360/N and a reflection
+ *     (N = num_rotations, |G| = N or 2N), the order the reference uses for one-hot vectors
+ *     (equiadapt/images/canonicalization/discrete_group.py:110-133).
+ */
+#ifndef EQUIADAPT_B200_H
+#define EQUIADAPT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EQB_ABI_VERSION 1
+#define EQB_API __attribute__((visibility("default")))
+
+#define EQB_ERR_INVALID (-1)     /* bad shape / size / enum */
+#define EQB_ERR_UNSUPPORTED (-2) /* valid in the reference, not covered by this build (message says what) */
+
+#define EQB_REP_SCALAR 0
+#define EQB_REP_REGULAR 1
+
+EQB_API int eqb_abi_version(void);
+EQB_API const char *eqb_last_error(void);
+
+/* ---- a3  pre-network transform ------------------------------------------------------------
+ * CenterCrop + antialiased bilinear Resize (torchvision transforms on tensors -> ATen
+ * _upsample_bilinear2d_aa).  Replaces discrete_group.py:174-188 (transforms built at :73-92).
+ * x (B,C,H,W) -> y (B,C,out_h,out_w); the crop window is [top,top+crop_h) x [left,left+crop_w). */
+EQB_API int eqb_crop_resize_aa(const float *x, float *y, int B, int C, int H, int W, int top, int left,
+                       int crop_h, int crop_w, int out_h, int out_w, void *stream);
+
+/* ---- a4 / a5  filter orbits ---------------------------------------------------------------
+ * Lift: w (Cout,Cin,k,k) -> orbit (Cout*|G|, Cin, k, k), channel = o*|G|+g.
+ * Replaces RotationEquivariantConvLift.get_rotated_weights /
+ * RotoReflectionEquivariantConvLift.get_rotoreflected_weights,
+ * custom_group_equivariant_layers.py:62-90, :169-199. */
+EQB_API int eqb_lift_filter_orbit(const float *w, float *orbit, int cout, int cin, int k, int num_rotations,
+                          int reflect, void *stream);
+/* Regular: w (Cout,Cin,|G|,k,k) -> orbit (Cout*|G|, Cin*|G|, k, k).
+ * Replaces get_rotated_permuted_weights / get_rotoreflected_permuted_weights, :298-334, :461-507. */
+EQB_API int eqb_regular_filter_orbit(const float *w, float *orbit, int cout, int cin, int k, int num_rotations,
+                             int reflect, void *stream);
+
+/* ---- a4..a6  fused group-conv stack -> group activations ----------------------------------
+ * CustomEquivariantNetwork.forward (custom_equivariant_networks.py:80-93):
+ *   lift conv k x k (valid) -> [ReLU -> 1x1 regular group conv] x (L-1) -> mean over (Cout,H',W').
+ * x (B,Cin,H,W); lift_w (Cout,Cin,k,k); reg_w[l] (Cout,Cout,|G|,1,1) for l = 0..L-2 given as a
+ * HOST array of device pointers; biases (Cout) each, a NULL bias pointer means "no bias".
+ * act (B,|G|).  `workspace` is device scratch of at least eqb_gconv_stack_workspace_bytes() bytes. */
+EQB_API int64_t eqb_gconv_stack_workspace_bytes(int B, int cin, int H, int W, int cout, int k, int num_rotations,
+                                        int reflect, int num_layers);
+EQB_API int eqb_gconv_stack_forward(const float *x, int B, int cin, int H, int W, const float *lift_w,
+                            const float *lift_b, const float *const *reg_w, const float *const *reg_b,
+                            int cout, int k, int num_rotations, int reflect, int num_layers, float *act,
+                            void *workspace, int64_t workspace_bytes, void *stream);
+
+/* ---- a9 + a13  group pool / select + prior statistic --------------------------------------
+ * act (B,|G|) -> idx int32 (B) = first arg-max, rotation (B) in degrees, reflection (B) 0/1 (may be
+ * NULL), onehot (B,|G|) (may be NULL), stats[3] = { sum_b CE(act_b, class 0), sum_b [idx_b == 0], B }.
+ * Replaces groupactivations_to_groupelementonehot (common/basecanonicalization.py:221-256, eval branch),
+ * groupactivations_to_groupelement (discrete_group.py:94-135) and the two reductions of
+ * get_prior_regularization_loss / get_identity_metric (basecanonicalization.py:290-311). */
+EQB_API int eqb_group_pool_select(const float *act, int B, int num_rotations, int reflect, int32_t *idx,
+                          float *rotation, float *reflection, float *onehot, float *stats, void *stream);
+
+/* ---- a10  canonicalize: inverse group action on the input image ---------------------------
+ * y = crop(rotate(flip?(pad_replicate(x)), -rotation)) for C != 1, bare zero-fill rotate for C == 1.
+ * Replaces discrete_group.py:207-215 (pad :62-66, crop :67-71).  x, y (B,C,H,W). */
+EQB_API int eqb_warp_canonicalize(const float *x, float *y, const int32_t *idx, int B, int C, int H, int W,
+                          int num_rotations, int reflect, void *stream);
+
+/* ---- a11  invert_canonicalization: forward group action on a feature map ------------------
+ * Replaces get_action_on_image_features + roll_by_gather (equiadapt/images/utils.py:8-94).
+ * f, out (B,C,H,W); rep = EQB_REP_SCALAR | EQB_REP_REGULAR (C % |G| == 0 required for regular). */
+EQB_API int eqb_warp_invert(const float *f, float *out, const int32_t *idx, int B, int C, int H, int W,
+                    int num_rotations, int reflect, int rep, void *stream);
+
+/* Host-only, no GPU work: the channel shift the reference derives for rotation index r by
+ * `(angle / 360.0 * num_rotations).long()` in float32 (images/utils.py:67,:28); equals r for
+ * power-of-two N, may truncate to r-1 otherwise (reference quirk reproduced by eqb_warp_invert). */
+EQB_API int eqb_regular_roll_shift(int r, int num_rotations);
+
+/* ---- a12  optimisation-based variant -------------------------------------------------------
+ * Orbit expand: x (B,C,h,w) -> out (|G|*B, C, out, out), group-major, each member =
+ * crop_out(hflip?(rotate(pad_replicate(x, pad), -deg_g))).  Replaces group_augment /
+ * rotate_and_maybe_reflect (discrete_group.py:387-427).  C == 1: no pad/crop (zero fill). */
+EQB_API int eqb_orbit_expand(const float *x, float *out, int B, int C, int h, int w, int pad, int out_size,
+                     int num_rotations, int reflect, void *stream);
+/* Cosine similarity to the reference vector + (|G|,B)->(B,|G|) transpose: vec (|G|*B, V), ref (V),
+ * act (B,|G|).  Replaces discrete_group.py:475-481. */
+EQB_API int eqb_cosine_group_activations(const float *vec, const float *ref, float *act, int B, int num_group,
+                                 int V, void *stream);
+
+/* ---- a14..a17  frames ----------------------------------------------------------------------
+ * Gram-Schmidt on the three rows of v (B,3,3) -> R (B,3,3).  modified = 0: common/utils.py:22-51;
+ * modified = 1: nbody/canonicalization/euclidean_group.py:139-157. */
+EQB_API int eqb_gram_schmidt3(const float *v, float *R, int B, int modified, void *stream);
+/* y = R x for clouds x (B,3,N): pointcloud/canonicalization/continuous_group.py:66-81. */
+EQB_API int eqb_so3_apply(const float *x, const float *R, float *y, int B, int N, void *stream);
+/* loc_c = (loc - t) R^T, vel_c = vel R^T, one (R,t) per ROW: euclidean_group.py:108-124.  M rows. */
+EQB_API int eqb_e3_apply(const float *loc, const float *vel, const float *R, const float *t, float *loc_c,
+                 float *vel_c, int M, void *stream);
+/* y = x R + t: euclidean_group.py:126-137. */
+EQB_API int eqb_e3_invert(const float *x, const float *R, const float *t, float *y, int M, void *stream);
+/* stats[3] = { sum (R - I)^2, B*d*d, 0 } for R (B,d,d): the reductions of
+ * ContinuousGroupCanonicalization.get_prior_regularization_loss / get_identity_metric
+ * (common/basecanonicalization.py:390-430). */
+EQB_API int eqb_prior_stats_continuous(const float *R, int B, int d, float *stats, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EQUIADAPT_B200_H */

