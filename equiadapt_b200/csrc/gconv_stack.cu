@@ -306,12 +306,99 @@ static int launch_stack(const StackArgs &a, size_t smem, cudaStream_t st) {
 
 using namespace eqb;
 
+// Workspace layout: [ packed weights | expanded biases | fold matrix ] = "packed" part (depends on the
+// parameters only) followed by the per-call partial sums.
 extern "C" int64_t eqb_gconv_stack_workspace_bytes(int B, int cin, int H, int W, int cout, int k, int num_rotations,
                                                    int reflect, int num_layers) {
     StackPlan p;
     const int rc = make_plan(B, cin, H, W, cout, k, num_rotations, reflect, num_layers, p);
     if (rc) return rc;
     return (int64_t)p.total;
+}
+
+extern "C" int64_t eqb_gconv_stack_packed_bytes(int cin, int cout, int k, int num_rotations, int reflect,
+                                                int num_layers) {
+    StackPlan p;
+    const int rc = make_plan(1, cin, k, k, cout, k, num_rotations, reflect, num_layers, p);
+    if (rc) return rc;
+    return (int64_t)p.off_S;
+}
+
+extern "C" int eqb_gconv_stack_pack(const float *lift_w, const float *lift_b, const float *const *reg_w,
+                                    const float *const *reg_b, int cin, int cout, int k, int num_rotations, int reflect,
+                                    int num_layers, void *packed, int64_t packed_bytes, void *stream) {
+    StackPlan p;
+    const int rc = make_plan(1, cin, k, k, cout, k, num_rotations, reflect, num_layers, p);
+    if (rc) return rc;
+    EQB_REQUIRE(lift_w && packed, "eqb_gconv_stack_pack: null pointer");
+    EQB_REQUIRE(num_layers == 1 || (reg_w && reg_b), "eqb_gconv_stack_pack: null layer table");
+    EQB_REQUIRE(packed_bytes >= (int64_t)p.off_S, "eqb_gconv_stack_pack: buffer %lld < %lld bytes",
+                (long long)packed_bytes, (long long)p.off_S);
+    EQB_REQUIRE(((uintptr_t)packed & 15) == 0, "eqb_gconv_stack_pack: buffer must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    char *ws = (char *)packed;
+    const int L = num_layers, reflect01 = reflect != 0;
+    // filter orbits as zero-padded K-major GEMM operands, expanded biases, fold matrix
+    EQB_CUDA(cudaMemsetAsync(ws, 0, p.off_bias[0], st));
+    int e = launch_lift_orbit(lift_w, (float *)(ws + p.off_wt[0]), cout, cin, k, num_rotations, reflect01, 1, p.Npad, st);
+    if (e) return e;
+    for (int l = 1; l < p.n_gemm; ++l) {
+        EQB_REQUIRE(reg_w[l - 1], "eqb_gconv_stack_pack: null weight for layer %d", l);
+        e = launch_regular_orbit(reg_w[l - 1], (float *)(ws + p.off_wt[l]), cout, cout, 1, num_rotations, reflect01, 1,
+                                 p.Npad, st);
+        if (e) return e;
+    }
+    for (int l = 0; l < p.n_gemm; ++l) {
+        const float *bsrc = l == 0 ? lift_b : reg_b[l - 1];
+        expand_bias_kernel<<<1, 256, 0, st>>>(bsrc, (float *)(ws + p.off_bias[l]), p.N, p.G, p.Npad);
+    }
+    const float *w_last = L > 1 ? reg_w[L - 2] : nullptr;
+    EQB_REQUIRE(L == 1 || w_last, "eqb_gconv_stack_pack: null weight for the last layer");
+    build_fold_matrix_kernel<<<(p.Npad * p.G + 255) / 256, 256, 0, st>>>(w_last, (double *)(ws + p.off_M), cout,
+                                                                         num_rotations, p.G, p.Npad, L > 1);
+    return finish_launch("eqb_gconv_stack_pack");
+}
+
+extern "C" int eqb_gconv_stack_run(const float *x, int B, int cin, int H, int W, const void *packed,
+                                   const float *last_bias, int cout, int k, int num_rotations, int reflect,
+                                   int num_layers, float *act, void *scratch, int64_t scratch_bytes, void *stream) {
+    StackPlan p;
+    const int rc = make_plan(B, cin, H, W, cout, k, num_rotations, reflect, num_layers, p);
+    if (rc) return rc;
+    if (B == 0) return 0;
+    EQB_REQUIRE(x && packed && act && scratch, "eqb_gconv_stack_run: null pointer");
+    EQB_REQUIRE(scratch_bytes >= (int64_t)(p.total - p.off_S), "eqb_gconv_stack_run: scratch %lld < %lld bytes",
+                (long long)scratch_bytes, (long long)(p.total - p.off_S));
+    EQB_REQUIRE(((uintptr_t)packed & 15) == 0 && ((uintptr_t)scratch & 7) == 0, "eqb_gconv_stack_run: misaligned buffer");
+    EQB_REQUIRE((long long)B * p.chunks < (1LL << 31), "eqb_gconv_stack_run: grid too large");
+    cudaStream_t st = (cudaStream_t)stream;
+    const char *ws = (const char *)packed;
+    const int L = num_layers;
+
+    StackArgs a{};
+    a.x = x; a.B = B; a.cin = cin; a.H = H; a.W = W; a.ksz = k; a.Ho = p.Ho; a.Wo = p.Wo; a.P = p.P;
+    a.K0 = p.K0; a.K0pad = p.K0pad; a.N = p.N; a.Npad = p.Npad; a.rows = p.rows;
+    a.n_gemm = p.n_gemm; a.relu_last = L > 1;
+    for (int l = 0; l < p.n_gemm; ++l) {
+        a.Wt[l] = (const float *)(ws + p.off_wt[l]);
+        a.bias[l] = (const float *)(ws + p.off_bias[l]);
+        a.Kpad[l] = l == 0 ? p.K0pad : p.Npad;
+    }
+    a.S_part = (double *)scratch;
+    a.tiles = p.tiles; a.chunks = p.chunks; a.tiles_per_chunk = p.tiles_per_chunk;
+    int e;
+    switch (p.Npad / 32) {
+        case 1: e = launch_stack<1>(a, p.smem, st); break;
+        case 2: e = launch_stack<2>(a, p.smem, st); break;
+        case 4: e = launch_stack<4>(a, p.smem, st); break;
+        default: e = launch_stack<8>(a, p.smem, st); break;
+    }
+    if (e) return e;
+    const double inv_count = 1.0 / ((double)cout * (double)p.P);
+    gconv_finish_kernel<<<B, 256, p.Npad * sizeof(double), st>>>(a.S_part, (const double *)(ws + p.off_M),
+                                                                L > 1 ? last_bias : nullptr, cout, p.chunks, p.Npad, p.G,
+                                                                inv_count, act);
+    return finish_launch("gconv_finish_kernel");
 }
 
 extern "C" int eqb_gconv_stack_forward(const float *x, int B, int cin, int H, int W, const float *lift_w,
@@ -322,60 +409,13 @@ extern "C" int eqb_gconv_stack_forward(const float *x, int B, int cin, int H, in
     const int rc = make_plan(B, cin, H, W, cout, k, num_rotations, reflect, num_layers, p);
     if (rc) return rc;
     if (B == 0) return 0;
-    EQB_REQUIRE(x && lift_w && act && workspace, "eqb_gconv_stack_forward: null pointer");
-    EQB_REQUIRE(num_layers == 1 || (reg_w && reg_b), "eqb_gconv_stack_forward: null layer table");
+    EQB_REQUIRE(workspace, "eqb_gconv_stack_forward: null workspace");
     EQB_REQUIRE(workspace_bytes >= (int64_t)p.total, "eqb_gconv_stack_forward: workspace %lld < %lld bytes",
                 (long long)workspace_bytes, (long long)p.total);
-    EQB_REQUIRE(((uintptr_t)workspace & 15) == 0, "eqb_gconv_stack_forward: workspace must be 16-byte aligned");
-    EQB_REQUIRE((long long)B * p.chunks < (1LL << 31), "eqb_gconv_stack_forward: grid too large");
-    cudaStream_t st = (cudaStream_t)stream;
-    char *ws = (char *)workspace;
-    const int L = num_layers, reflect01 = reflect != 0;
-
-    // ---- pack: filter orbits as zero-padded K-major GEMM operands, expanded biases, fold matrix ----
-    EQB_CUDA(cudaMemsetAsync(ws, 0, p.off_bias[0], st));
-    int e = launch_lift_orbit(lift_w, (float *)(ws + p.off_wt[0]), cout, cin, k, num_rotations, reflect01, 1, p.Npad, st);
+    int e = eqb_gconv_stack_pack(lift_w, lift_b, reg_w, reg_b, cin, cout, k, num_rotations, reflect, num_layers,
+                                 workspace, (int64_t)p.off_S, stream);
     if (e) return e;
-    for (int l = 1; l < p.n_gemm; ++l) {
-        EQB_REQUIRE(reg_w[l - 1], "eqb_gconv_stack_forward: null weight for layer %d", l);
-        e = launch_regular_orbit(reg_w[l - 1], (float *)(ws + p.off_wt[l]), cout, cout, 1, num_rotations, reflect01, 1,
-                                 p.Npad, st);
-        if (e) return e;
-    }
-    for (int l = 0; l < p.n_gemm; ++l) {
-        const float *bsrc = l == 0 ? lift_b : reg_b[l - 1];
-        expand_bias_kernel<<<1, 256, 0, st>>>(bsrc, (float *)(ws + p.off_bias[l]), p.N, p.G, p.Npad);
-    }
-    const float *w_last = L > 1 ? reg_w[L - 2] : nullptr;
-    const float *b_last = L > 1 ? reg_b[L - 2] : nullptr;
-    EQB_REQUIRE(L == 1 || w_last, "eqb_gconv_stack_forward: null weight for the last layer");
-    build_fold_matrix_kernel<<<(p.Npad * p.G + 255) / 256, 256, 0, st>>>(w_last, (double *)(ws + p.off_M), cout,
-                                                                         num_rotations, p.G, p.Npad, L > 1);
-    e = finish_launch("gconv pack");
-    if (e) return e;
-
-    // ---- fused stack ------------------------------------------------------------------------------
-    StackArgs a{};
-    a.x = x; a.B = B; a.cin = cin; a.H = H; a.W = W; a.ksz = k; a.Ho = p.Ho; a.Wo = p.Wo; a.P = p.P;
-    a.K0 = p.K0; a.K0pad = p.K0pad; a.N = p.N; a.Npad = p.Npad; a.rows = p.rows;
-    a.n_gemm = p.n_gemm; a.relu_last = L > 1;
-    for (int l = 0; l < p.n_gemm; ++l) {
-        a.Wt[l] = (const float *)(ws + p.off_wt[l]);
-        a.bias[l] = (const float *)(ws + p.off_bias[l]);
-        a.Kpad[l] = l == 0 ? p.K0pad : p.Npad;
-    }
-    a.S_part = (double *)(ws + p.off_S);
-    a.tiles = p.tiles; a.chunks = p.chunks; a.tiles_per_chunk = p.tiles_per_chunk;
-    switch (p.Npad / 32) {
-        case 1: e = launch_stack<1>(a, p.smem, st); break;
-        case 2: e = launch_stack<2>(a, p.smem, st); break;
-        case 4: e = launch_stack<4>(a, p.smem, st); break;
-        default: e = launch_stack<8>(a, p.smem, st); break;
-    }
-    if (e) return e;
-
-    const double inv_count = 1.0 / ((double)cout * (double)p.P);
-    gconv_finish_kernel<<<B, 256, p.Npad * sizeof(double), st>>>(a.S_part, (const double *)(ws + p.off_M), b_last, cout,
-                                                                p.chunks, p.Npad, p.G, inv_count, act);
-    return finish_launch("gconv_finish_kernel");
+    const float *b_last = num_layers > 1 ? reg_b[num_layers - 2] : nullptr;
+    return eqb_gconv_stack_run(x, B, cin, H, W, workspace, b_last, cout, k, num_rotations, reflect, num_layers, act,
+                               (char *)workspace + p.off_S, workspace_bytes - (int64_t)p.off_S, stream);
 }

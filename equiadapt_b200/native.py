@@ -28,6 +28,10 @@ _SIGNATURES = {
     "eqb_gconv_stack_workspace_bytes": (C.c_int64, [_i] * 9),
     "eqb_gconv_stack_forward": (C.c_int, [_fp] + [_i] * 4 + [_fp, _fp, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
                                 + [_i] * 5 + [_fp, _fp, C.c_int64, _fp]),
+    "eqb_gconv_stack_packed_bytes": (C.c_int64, [_i] * 6),
+    "eqb_gconv_stack_pack": (C.c_int, [_fp, _fp, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)] + [_i] * 6
+                             + [_fp, C.c_int64, _fp]),
+    "eqb_gconv_stack_run": (C.c_int, [_fp] + [_i] * 4 + [_fp, _fp] + [_i] * 5 + [_fp, _fp, C.c_int64, _fp]),
     "eqb_group_pool_select": (C.c_int, [_fp, _i, _i, _i, _fp, _fp, _fp, _fp, _fp, _fp]),
     "eqb_warp_canonicalize": (C.c_int, [_fp, _fp, _fp] + [_i] * 6 + [_fp]),
     "eqb_warp_invert": (C.c_int, [_fp, _fp, _fp] + [_i] * 7 + [_fp]),

@@ -118,5 +118,16 @@ class CustomEquivariantNetwork(nn.Module):
         """(B,Cin,H,W) -> group activations (B,|G|): custom_equivariant_networks.py:80-93, one fused call."""
         mods = [m for m in self.eqv_network if isinstance(m, _GroupConvParams)]
         lift, regs = mods[0], mods[1:]
-        return ops.gconv_stack_forward(x, lift.weights, lift.bias, [m.weights for m in regs], [m.bias for m in regs],
-                                       self.num_rotations, self.group_type == "roto-reflection")
+        reflect = self.group_type == "roto-reflection"
+        # The packed operands (filter orbits, expanded biases, folded last layer) depend on the parameters
+        # only: rebuilt when a parameter was modified in place or replaced, reused otherwise.  (The reference
+        # rebuilds its orbits on every forward: custom_group_equivariant_layers.py:103, :349-351.)
+        params = [p for m in mods for p in (m.weights, m.bias) if p is not None]
+        key = tuple((p.data_ptr(), p._version) for p in params)
+        if getattr(self, "_packed_key", None) != key:
+            self._packed = ops.gconv_stack_pack(lift.weights, lift.bias, [m.weights for m in regs],
+                                                [m.bias for m in regs], self.num_rotations, reflect)
+            self._packed_key = key
+        last_bias = regs[-1].bias if regs else None
+        return ops.gconv_stack_run(x, self._packed, last_bias, lift.out_channels, lift.kernel_size,
+                                   self.num_rotations, reflect, len(mods))

@@ -46,10 +46,22 @@ def _stream(dev: torch.device) -> int:
     return torch.cuda.current_stream(dev).cuda_stream
 
 
+# optional per-call device timing: set to a dict {abi name: [(start_event, end_event), ...]}; events are
+# recorded on the launching stream (used by bench.py for the live roofline figure, never on by default)
+event_log = None
+
+
 def _call(name: str, n_launches: int, dev: torch.device, *args):
     global launch_count
     with torch.cuda.device(dev):
-        native.check(getattr(native.lib(), name)(*args), name)
+        if event_log is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(torch.cuda.current_stream(dev))
+            native.check(getattr(native.lib(), name)(*args), name)
+            e1.record(torch.cuda.current_stream(dev))
+            event_log.setdefault(name, []).append((e0, e1))
+        else:
+            native.check(getattr(native.lib(), name)(*args), name)
     launch_count += n_launches
 
 
@@ -86,37 +98,69 @@ def regular_filter_orbit(w: torch.Tensor, num_rotations: int, reflect: bool) -> 
 
 
 # ---- a4..a6 -------------------------------------------------------------------------------------
-def gconv_stack_forward(x: torch.Tensor, lift_w: torch.Tensor, lift_b: Optional[torch.Tensor],
-                        reg_w: Sequence[torch.Tensor], reg_b: Sequence[Optional[torch.Tensor]],
-                        num_rotations: int, reflect: bool) -> torch.Tensor:
-    dev = _need_cuda(x, lift_w, lift_b, *reg_w, *reg_b)
-    x = _f32(x)
+def _stack_dims(lift_w, reg_w, num_rotations, reflect):
+    cout, cin, k, k2 = lift_w.shape
+    g = num_rotations * (2 if reflect else 1)
+    for rw in reg_w:
+        if tuple(rw.shape) != (cout, cout, g, 1, 1):
+            raise ValueError(f"regular layer weights must be ({cout},{cout},{g},1,1), got {tuple(rw.shape)}")
+    return cout, cin, k, g, 1 + len(reg_w)
+
+
+def gconv_stack_pack(lift_w: torch.Tensor, lift_b: Optional[torch.Tensor], reg_w: Sequence[torch.Tensor],
+                     reg_b: Sequence[Optional[torch.Tensor]], num_rotations: int, reflect: bool) -> torch.Tensor:
+    """Filter orbits as zero-padded K-major GEMM operands + expanded biases + folded last layer (uint8 buffer)."""
+    dev = _need_cuda(lift_w, lift_b, *reg_w, *reg_b)
     lift_w = _f32(lift_w)
     lift_b = None if lift_b is None else _f32(lift_b)
     reg_w = [_f32(w) for w in reg_w]
     reg_b = [None if b is None else _f32(b) for b in reg_b]
-    b, cin, h, w = x.shape
-    cout, cin2, k, _ = lift_w.shape
-    if cin2 != cin:
-        raise ValueError(f"lift weights expect {cin2} input channels, image has {cin}")
-    g = num_rotations * (2 if reflect else 1)
-    n_layers = 1 + len(reg_w)
-    for rw in reg_w:
-        if tuple(rw.shape) != (cout, cout, g, 1, 1):
-            raise ValueError(f"regular layer weights must be ({cout},{cout},{g},1,1), got {tuple(rw.shape)}")
-    lib = native.lib()
-    ws_bytes = lib.eqb_gconv_stack_workspace_bytes(b, cin, h, w, cout, k, num_rotations, int(reflect), n_layers)
-    if ws_bytes < 0:
-        native.check(int(ws_bytes), "eqb_gconv_stack_workspace_bytes")
-    ws = torch.empty((max(int(ws_bytes), 16),), dtype=torch.uint8, device=dev)
-    act = torch.empty((b, g), dtype=torch.float32, device=dev)
+    cout, cin, k, g, n_layers = _stack_dims(lift_w, reg_w, num_rotations, reflect)
+    nbytes = native.lib().eqb_gconv_stack_packed_bytes(cin, cout, k, num_rotations, int(reflect), n_layers)
+    if nbytes < 0:
+        native.check(int(nbytes), "eqb_gconv_stack_packed_bytes")
+    packed = torch.empty((int(nbytes),), dtype=torch.uint8, device=dev)
     n = max(len(reg_w), 1)
     wp = (C.c_void_p * n)(*[_ptr(t) for t in reg_w]) if reg_w else (C.c_void_p * 1)(None)
     bp = (C.c_void_p * n)(*[_ptr(t) for t in reg_b]) if reg_w else (C.c_void_p * 1)(None)
     n_gemm = max(n_layers - 1, 1)
-    _call("eqb_gconv_stack_forward", 3 + 2 * n_gemm, dev, _ptr(x), b, cin, h, w, _ptr(lift_w), _ptr(lift_b), wp, bp,
-          cout, k, num_rotations, int(reflect), n_layers, _ptr(act), _ptr(ws), int(ws_bytes), _stream(dev))
+    _call("eqb_gconv_stack_pack", 1 + 2 * n_gemm, dev, _ptr(lift_w), _ptr(lift_b), wp, bp, cin, cout, k, num_rotations,
+          int(reflect), n_layers, _ptr(packed), int(nbytes), _stream(dev))
+    return packed
+
+
+def gconv_stack_run(x: torch.Tensor, packed: torch.Tensor, last_bias: Optional[torch.Tensor], cout: int, k: int,
+                    num_rotations: int, reflect: bool, n_layers: int) -> torch.Tensor:
+    """x (B,Cin,H,W) -> group activations (B,|G|) with pre-packed parameters: 2 launches."""
+    dev = _need_cuda(x, packed, last_bias)
+    x = _f32(x)
+    last_bias = None if last_bias is None else _f32(last_bias)
+    b, cin, h, w = x.shape
+    g = num_rotations * (2 if reflect else 1)
+    lib = native.lib()
+    total = lib.eqb_gconv_stack_workspace_bytes(b, cin, h, w, cout, k, num_rotations, int(reflect), n_layers)
+    if total < 0:
+        native.check(int(total), "eqb_gconv_stack_workspace_bytes")
+    scratch_bytes = int(total) - packed.numel()
+    if scratch_bytes < 0:
+        raise ValueError("packed parameter buffer does not belong to this network configuration")
+    scratch = torch.empty((max(scratch_bytes, 16),), dtype=torch.uint8, device=dev)
+    act = torch.empty((b, g), dtype=torch.float32, device=dev)
+    _call("eqb_gconv_stack_run", 2, dev, _ptr(x), b, cin, h, w, _ptr(packed), _ptr(last_bias), cout, k, num_rotations,
+          int(reflect), n_layers, _ptr(act), _ptr(scratch), scratch_bytes, _stream(dev))
     return act
+
+
+def gconv_stack_forward(x: torch.Tensor, lift_w: torch.Tensor, lift_b: Optional[torch.Tensor],
+                        reg_w: Sequence[torch.Tensor], reg_b: Sequence[Optional[torch.Tensor]],
+                        num_rotations: int, reflect: bool) -> torch.Tensor:
+    """pack + run in one go (what the reference does on every forward)."""
+    if x.shape[1] != lift_w.shape[1]:
+        raise ValueError(f"lift weights expect {lift_w.shape[1]} input channels, image has {x.shape[1]}")
+    packed = gconv_stack_pack(lift_w, lift_b, reg_w, reg_b, num_rotations, reflect)
+    cout, _, k, _, n_layers = _stack_dims(lift_w, reg_w, num_rotations, reflect)
+    last_b = reg_b[-1] if len(reg_w) else None
+    return gconv_stack_run(x, packed, last_b, cout, k, num_rotations, reflect, n_layers)
 
 
 # ---- a9 + a13 -----------------------------------------------------------------------------------

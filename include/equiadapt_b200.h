@@ -63,11 +63,23 @@ EQB_API int eqb_regular_filter_orbit(const float *w, float *orbit, int cout, int
  * HOST array of device pointers; biases (Cout) each, a NULL bias pointer means "no bias".
  * act (B,|G|).  `workspace` is device scratch of at least eqb_gconv_stack_workspace_bytes() bytes. */
 EQB_API int64_t eqb_gconv_stack_workspace_bytes(int B, int cin, int H, int W, int cout, int k, int num_rotations,
-                                        int reflect, int num_layers);
+                                                int reflect, int num_layers);
 EQB_API int eqb_gconv_stack_forward(const float *x, int B, int cin, int H, int W, const float *lift_w,
-                            const float *lift_b, const float *const *reg_w, const float *const *reg_b,
-                            int cout, int k, int num_rotations, int reflect, int num_layers, float *act,
-                            void *workspace, int64_t workspace_bytes, void *stream);
+                                    const float *lift_b, const float *const *reg_w, const float *const *reg_b,
+                                    int cout, int k, int num_rotations, int reflect, int num_layers, float *act,
+                                    void *workspace, int64_t workspace_bytes, void *stream);
+/* The same in two steps, for frozen weights: pack ONCE (filter orbits as GEMM operands, expanded biases,
+ * folded last layer; the reference rebuilds its orbits on every forward, custom_group_equivariant_layers.py:103,
+ * :349-351), then run per batch.  `packed` needs eqb_gconv_stack_packed_bytes(); `scratch` needs
+ * eqb_gconv_stack_workspace_bytes() - eqb_gconv_stack_packed_bytes() for the batch at hand.
+ * `last_bias` = bias of the last layer (Cout) or NULL (ignored when num_layers == 1). */
+EQB_API int64_t eqb_gconv_stack_packed_bytes(int cin, int cout, int k, int num_rotations, int reflect, int num_layers);
+EQB_API int eqb_gconv_stack_pack(const float *lift_w, const float *lift_b, const float *const *reg_w,
+                                 const float *const *reg_b, int cin, int cout, int k, int num_rotations, int reflect,
+                                 int num_layers, void *packed, int64_t packed_bytes, void *stream);
+EQB_API int eqb_gconv_stack_run(const float *x, int B, int cin, int H, int W, const void *packed,
+                                const float *last_bias, int cout, int k, int num_rotations, int reflect,
+                                int num_layers, float *act, void *scratch, int64_t scratch_bytes, void *stream);
 
 /* ---- a9 + a13  group pool / select + prior statistic --------------------------------------
  * act (B,|G|) -> idx int32 (B) = first arg-max, rotation (B) in degrees, reflection (B) 0/1 (may be
