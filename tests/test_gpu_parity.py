@@ -272,16 +272,23 @@ def test_frames_vs_oracle(cuda_device):
     dev = cuda_device
     g = torch.Generator().manual_seed(3)
     v = torch.randn(1000, 3, 3, generator=g)
-    # Gram-Schmidt has no eps: nearly collinear random triples amplify fp32 rounding in BOTH implementations,
-    # so the bar is "no further from the fp64 oracle than 4x the fp32 oracle is", plus 1e-5 on the whole batch
+    # Gram-Schmidt has no eps: nearly collinear triples amplify fp32 rounding by 1/(r2*r3), r_i = the
+    # fraction of |v_i| left after projecting out the earlier vectors; the bar scales with that conditioning
+    v64 = v.double()
+    e1 = v64[:, 0] / v64[:, 0].norm(dim=1, keepdim=True)
+    u2 = v64[:, 1] - (v64[:, 1] * e1).sum(1, keepdim=True) * e1
+    e2 = u2 / u2.norm(dim=1, keepdim=True)
+    u3 = v64[:, 2] - (v64[:, 2] * e1).sum(1, keepdim=True) * e1 - (v64[:, 2] * e2).sum(1, keepdim=True) * e2
+    amp = 1.0 / ((u2.norm(dim=1) / v64[:, 1].norm(dim=1)) * (u3.norm(dim=1) / v64[:, 2].norm(dim=1)))
     for modified, fn in ((False, O.gram_schmidt), (True, O.modified_gram_schmidt)):
         ours = ops.gram_schmidt3(v.to(dev), modified=modified).cpu().double()
-        ref32, ref64 = fn(v).double(), fn(v.double())
+        ref32, ref64 = fn(v).double(), fn(v64)
         e_ours = (ours - ref64).abs().amax(dim=(1, 2))
         e_ref = (ref32 - ref64).abs().amax(dim=(1, 2))
-        assert bool((e_ours <= 4 * e_ref + 1e-6).all())
-        well = e_ref < 1e-6
-        assert int(well.sum()) > 900 and rel_err(ours[well], ref32[well]) < 1e-5
+        assert bool((e_ours <= 2e-6 * amp).all()), float((e_ours / amp).max())
+        assert bool((e_ref <= 2e-6 * amp).all())       # the fp32 oracle obeys the same bound
+        well = amp < 4
+        assert int(well.sum()) > 300 and rel_err(ours[well], ref32[well]) < 1e-5
     r = O.gram_schmidt(v[:128])
     x = torch.randn(128, 3, 1024, generator=g)   # BASELINE cfg4 shape
     assert rel_err(ops.so3_apply(x.to(dev), r.to(dev)).cpu(), O.so3_canonicalize(x, r)) < 1e-5
@@ -315,16 +322,18 @@ def test_edge_cases(cuda_device):
     x0 = torch.empty(0, 3, 16, 16, device=dev)
     assert ops.warp_canonicalize(x0, torch.empty(0, dtype=torch.int32, device=dev), 4, False).shape == (0, 3, 16, 16)
     assert ops.so3_apply(torch.empty(0, 3, 8, device=dev), torch.empty(0, 3, 3, device=dev)).shape == (0, 3, 8)
-    # single pixel / single row images, sizes that are not multiples of the 32x32 tile
+    # single pixel / two-row images, sizes that are not multiples of the 32x32 tile, H != W (where the
+    # reference's pad of ceil(W/2) is too small and zero fill shows up).  Single-ROW images are left out:
+    # kornia's pixel normalisation degenerates there (1e-14 denominator) and the reference output is noise.
     g = torch.Generator().manual_seed(5)
-    for shape in [(2, 3, 1, 1), (3, 2, 1, 37), (2, 1, 33, 65), (8, 3, 45, 45), (8, 4, 100, 31)]:
+    for shape in [(2, 3, 1, 1), (3, 2, 2, 37), (2, 1, 33, 65), (8, 3, 45, 45), (8, 4, 100, 31)]:
         x = torch.rand(*shape, generator=g)
         idx = torch.arange(shape[0]) % 8
         ang = torch.linspace(0.0, 360.0, 9)[:8][idx]
         y = ops.warp_canonicalize(x.to(dev), idx.to(dev).int(), 8, False)
-        assert rel_err(y.cpu(), O.canonicalize_image(x, ang, None)) < RTOL
+        assert rel_err(y.cpu(), O.canonicalize_image(x, ang, None)) < RTOL, shape
         yi = ops.warp_invert(x.to(dev), idx.to(dev).int(), 8, False, False)
-        assert rel_err(yi.cpu(), O.invert_image_features(x, ang, None, 8, 8, "scalar")) < RTOL
+        assert rel_err(yi.cpu(), O.invert_image_features(x, ang, None, 8, 8, "scalar")) < RTOL, shape
     # errors surface as the reference's exception types
     with pytest.raises(ValueError):
         ops.warp_invert(torch.rand(1, 5, 8, 8, device=dev), torch.zeros(1, dtype=torch.int32, device=dev), 4, False, True)
