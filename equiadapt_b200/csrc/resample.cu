@@ -16,34 +16,15 @@
 // the bilinear weights are computed once per pixel in fp64 and reused for every channel, and each
 // warp writes full 128-byte rows.  Algorithmic traffic: 1 read + 1 write of the image; the 2x
 // footprint overlap between neighbouring tiles is absorbed by L2.
-#include "common.cuh"
+#include <math.h>
+#include <stdlib.h>
+
+#include "resample.cuh"
 
 namespace eqb {
 
-constexpr int TILE = 32;
-constexpr int BB = 48;       // max footprint side
-constexpr int PITCH = 49;    // odd pitch
-constexpr int THREADS = 256;
-constexpr int PIX = TILE * TILE / THREADS;  // 4 pixels per thread
-
-enum { MODE_CANON = 0, MODE_INV_SCALAR = 1, MODE_INV_REGULAR = 2, MODE_ORBIT = 3 };
-
-struct ResampleArgs {
-    const float *src;
-    float *dst;
-    const int32_t *idx;  // per source sample group element (unused for MODE_ORBIT)
-    int B;               // source samples
-    int C, Hs, Ws, Hd, Wd;
-    int N, reflect, G;
-    signed char roll[64];  // regular-rep channel shift per rotation index (see regular_roll_shift)
-    int mode;
-    int pad;        // >=0: taps inside [-pad, size-1+pad] are replicate-clamped, zero beyond
-    double ox, oy;  // dst pixel -> coordinate relative to the rotation centre: u = xd + ox
-    int tiles_x, tiles_y;
-};
-
 template <int CG>
-__global__ void __launch_bounds__(THREADS) resample_kernel(const ResampleArgs a) {
+__global__ void __launch_bounds__(THREADS) resample_kernel(const __grid_constant__ ResampleArgs a) {
     extern __shared__ float smem[];  // [CG][BB][PITCH]
     const int tiles = a.tiles_x * a.tiles_y;
     const int sample_d = blockIdx.x / tiles;  // destination sample
@@ -76,7 +57,7 @@ __global__ void __launch_bounds__(THREADS) resample_kernel(const ResampleArgs a)
         }
     }
     double c, s;
-    rot_cs(r, a.N, sign, c, s);
+    group_cs(a, r, sign, c, s);
     // src = centre + [[c,-s],[s,c]] (u,v);  mirror_dst: u -> -u;  mirror_src: xs -> (Ws-1) - xs
     double a00 = c, a01 = -s, a10 = s, a11 = c;
     if (mirror_dst) { a00 = -a00; a10 = -a10; }
@@ -188,9 +169,32 @@ static int regular_roll_shift(int r, int N) {
     return (int)sh;  // .long() truncates toward zero
 }
 
-static int launch_resample(ResampleArgs &a, int n_dst_samples, cudaStream_t st, const char *what) {
+void finish_args(ResampleArgs &a) {
     a.tiles_x = (a.Wd + TILE - 1) / TILE;
     a.tiles_y = (a.Hd + TILE - 1) / TILE;
+    a.has_cs = a.N <= 16;
+    if (a.has_cs) {
+        static const double quarter[4][2] = {{1.0, 0.0}, {0.0, 1.0}, {-1.0, 0.0}, {0.0, -1.0}};
+        for (int r = 0; r < a.N; ++r) {
+            if ((4 * r) % a.N == 0) {
+                a.cs[2 * r] = quarter[4 * r / a.N][0];
+                a.cs[2 * r + 1] = quarter[4 * r / a.N][1];
+            } else {
+                const double ang = 2.0 * 3.14159265358979323846 * (double)r / (double)a.N;
+                a.cs[2 * r] = cos(ang);
+                a.cs[2 * r + 1] = sin(ang);
+            }
+        }
+    }
+}
+
+static int launch_resample(ResampleArgs &a, int n_dst_samples, cudaStream_t st, const char *what) {
+    finish_args(a);
+    if (!getenv("EQB_NO_TMA")) {
+        int handled = 0;
+        const int e = launch_resample_tma(a, n_dst_samples, st, what, &handled);
+        if (e || handled) return e;
+    }
     const long long blocks = (long long)a.tiles_x * a.tiles_y * n_dst_samples;
     if (blocks == 0) return 0;
     EQB_REQUIRE(blocks < (1LL << 31), "%s: grid too large (%lld tiles)", what, blocks);

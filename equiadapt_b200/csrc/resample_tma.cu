@@ -1,0 +1,331 @@
+// TMA-staged group-action resampling (the HBM-bound kernel behind eqb_warp_canonicalize / eqb_warp_invert /
+// eqb_orbit_expand when the source tensor meets the TMA layout rules; resample.cu holds the generic kernel).
+//
+// Same arithmetic contract as resample.cu (see its header): each output pixel is a 4-tap bilinear sample at
+//   src = centre + A (dst - centre),
+// taps replicate-clamped into the image inside the padded extent and zero beyond it
+// (discrete_group.py:207-215, images/utils.py:57-64, discrete_group.py:401-409 of the reference).
+//
+// B200 design.  One CTA = one 32x32 output tile of one sample, all channels (CG planes per pass):
+//   * the source footprint is fetched by the TMA unit (cp.async.bulk.tensor.3d, one instruction per plane,
+//     completion on an mbarrier) while all 256 threads compute their per-pixel taps - no LDG/STS staging
+//     instructions, no registers held for loads in flight;
+//   * quarter turns / mirrors with integral source coordinates ("exact" tiles) are pure permutations: the box
+//     is the 32x32 source tile itself, landed with the 128-byte swizzle so that both the row-wise and the
+//     column-wise (transposing) reads are at most 4-way bank conflicted, one LDS per output element;
+//   * every other tile uses a 52x48 box (bounding box of the rotated tile + 1 tap, start rounded down to the
+//     16-byte boundary the TMA unit requires), coordinates are evaluated
+//     in fp32 RELATIVE to the box origin (|coord| < 64 -> 4e-6 px resolution; the box origin itself comes from
+//     fp64), 4 LDS + 4 FMA per output element with offsets/weights shared by all channels;
+//   * each warp stores full 128-byte rows (st.global.L1::no_allocate).
+// Algorithmic traffic per sample: 1 read + 1 write of the image (SURVEY.md 8d "W"); the 2x footprint overlap of
+// rotated tiles is served by L2.
+#include <cuda.h>
+
+#include "resample.cuh"
+
+namespace eqb {
+
+// TMA rule measured on B200 (tools/tma_probe.cu): with INTERLEAVE_NONE the box must START on a 16-byte boundary
+// of global memory, i.e. its x coordinate must be a multiple of 4 floats (a misaligned start raises "illegal
+// instruction" at the UTMALDG).  The bilinear box is therefore 47 (+1 tap) + 3 (alignment slack) -> 52 wide.
+constexpr int BOXW = 52, BOXH = 48;            // bilinear source box (floats)
+constexpr int BOX_BYTES = BOXW * BOXH * 4;     // 9984 bytes landed per plane
+constexpr int PLANE_BYTES = 10 * 1024;         // plane stride in shared memory: keeps every plane 1024-byte aligned
+constexpr int TILE_BYTES = TILE * TILE * 4;    // exact path: 32 x 32 box, 128-byte rows, SWIZZLE_128B
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(bar), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int x, int y, int z) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"((uint64_t)map), "r"(bar), "r"(x), "r"(y), "r"(z)
+        : "memory");
+}
+
+template <int CG, bool ZERO>
+__global__ void __launch_bounds__(THREADS, 6) resample_tma_kernel(const __grid_constant__ CUtensorMap map_box,
+                                                               const __grid_constant__ CUtensorMap map_tile,
+                                                               const __grid_constant__ ResampleArgs a) {
+    extern __shared__ unsigned char smem_raw[];
+    // [CG planes, 10 KB apart, 1024-aligned][mbarrier]
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const float *planes = reinterpret_cast<const float *>(smem_raw + (base - smem_u32(smem_raw)));
+    const uint32_t bar = base + CG * PLANE_BYTES;
+
+    const int tiles = a.tiles_x * a.tiles_y;
+    const int sample_d = blockIdx.x / tiles;  // destination sample
+    const int t = blockIdx.x - sample_d * tiles;
+    const int ty0 = (t / a.tiles_x) * TILE, tx0 = (t % a.tiles_x) * TILE;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    // ---- group element of this sample -> A (CTA-uniform) -----------------------------------------
+    int sample_s, r, mirror_src = 0, mirror_dst = 0;
+    double sign;
+    if (a.mode == MODE_ORBIT) {
+        const int g = sample_d / a.B;
+        sample_s = sample_d - g * a.B;
+        r = g % a.N;
+        mirror_dst = g >= a.N;  // rotate, THEN hflip (discrete_group.py:404-406)
+        sign = -1.0;
+    } else {
+        sample_s = sample_d;
+        const int g = min(max(a.idx[sample_s], 0), a.G - 1);
+        r = g % a.N;
+        const int refl = g >= a.N;
+        if (a.mode == MODE_CANON) {
+            mirror_src = refl;  // hflip, THEN rotate(-theta) (discrete_group.py:209-213)
+            sign = -1.0;
+        } else {
+            mirror_dst = a.reflect && !refl;  // images/utils.py:59-64 (reference quirk A.4-2)
+            sign = 1.0;
+        }
+    }
+    double c, s;
+    group_cs(a, r, sign, c, s);
+    double a00 = c, a01 = -s, a10 = s, a11 = c;
+    if (mirror_dst) { a00 = -a00; a10 = -a10; }
+    if (mirror_src) { a00 = -a00; a01 = -a01; }
+    const double cx = 0.5 * (a.Ws - 1), cy = 0.5 * (a.Hs - 1);
+
+    // ---- source footprint of the tile --------------------------------------------------------------
+    const int tw = min(TILE, a.Wd - tx0), th = min(TILE, a.Hd - ty0);
+    const double u0 = (double)tx0 + a.ox, v0 = (double)ty0 + a.oy;
+    const double xs_org = cx + a00 * u0 + a01 * v0, ys_org = cy + a10 * u0 + a11 * v0;  // source of pixel (tx0,ty0)
+    double xmin = xs_org, xmax = xs_org, ymin = ys_org, ymax = ys_org;
+#pragma unroll
+    for (int k = 1; k < 4; ++k) {
+        const double du = (k & 1) ? (double)(tw - 1) : 0.0, dv = (k & 2) ? (double)(th - 1) : 0.0;
+        const double xs = xs_org + a00 * du + a01 * dv, ys = ys_org + a10 * du + a11 * dv;
+        xmin = fmin(xmin, xs); xmax = fmax(xmax, xs);
+        ymin = fmin(ymin, ys); ymax = fmax(ymax, ys);
+    }
+    const int fxmin = (int)floor(xmin), fxmax = (int)floor(xmax), fymin = (int)floor(ymin), fymax = (int)floor(ymax);
+    // exact tile: quarter turn (sincospi returns exact 0 / +-1 there), integral source coordinates, no clamping
+    // and a source tile that starts on a 16-byte boundary (always true for square images whose side is a multiple of 4)
+    const bool exact = (c == 0.0 || s == 0.0) && xs_org == floor(xs_org) && ys_org == floor(ys_org) && fxmin >= 0 &&
+                       fxmax <= a.Ws - 1 && fymin >= 0 && fymax <= a.Hs - 1 && (fxmin & 3) == 0;
+
+    const int xd = tx0 + lane;
+    const size_t plane_d = (size_t)a.Hd * a.Wd;
+    float *dst_n = a.dst + (size_t)sample_d * a.C * plane_d;
+    const int plane0 = sample_s * a.C;  // first source plane of this sample in the (W,H,B*C) tensor map
+
+    // CTA-uniform geometry of the box and of the coordinate map relative to its origin
+    int box_x, box_y;
+    int i00 = 0, i01 = 0, i10 = 0, i11 = 0, sx0 = 0, sy0 = 0;       // exact path
+    int cx_lo = 0, cx_hi = 0, bhm1 = 0, y_lo = 0;                    // bilinear path
+    float bx = 0.f, by = 0.f, f00 = 0.f, f01 = 0.f, f10 = 0.f, f11 = 0.f;
+    if (exact) {
+        box_x = fxmin; box_y = fymin;
+        i00 = (int)a00; i01 = (int)a01; i10 = (int)a10; i11 = (int)a11;
+        sx0 = (int)xs_org - box_x; sy0 = (int)ys_org - box_y;
+    } else {
+        const int x_lo = min(max(fxmin, 0), a.Ws - 1);
+        y_lo = min(max(fymin, 0), a.Hs - 1);
+        box_x = x_lo & ~3; box_y = y_lo;                                  // 16-byte aligned start
+        cx_lo = x_lo - box_x;                                            // taps are clamped into [cx_lo, cx_hi]
+        cx_hi = min(max(fxmax + 1, 0), a.Ws - 1) - box_x;                // <= 46 + 3
+        bhm1 = min(max(fymax + 1, 0), a.Hs - 1) - y_lo;                  // <= 46
+        bx = (float)(xs_org - (double)box_x); by = (float)(ys_org - (double)y_lo);
+        f00 = (float)a00; f01 = (float)a01; f10 = (float)a10; f11 = (float)a11;
+    }
+    const float fl = (float)lane;
+
+    uint32_t parity = 0;
+    for (int c0 = 0; c0 < a.C; c0 += CG) {
+        const int nc = min(CG, a.C - c0);
+        if (c0) __syncthreads();  // every thread is done reading the planes of the previous pass
+        if (threadIdx.x == 0) {
+            mbar_expect_tx(bar, (uint32_t)nc * (exact ? TILE_BYTES : BOX_BYTES));
+            for (int cc = 0; cc < nc; ++cc) {
+                int cs = c0 + cc;
+                if (a.mode == MODE_INV_REGULAR) {
+                    // out[:, f*G+g] = in[:, f*G + src_g(g)]   (roll_by_gather, images/utils.py:8-29,66-77)
+                    const int f = cs / a.G, g = cs - f * a.G, sh = a.roll[r];
+                    int sg;
+                    if (g < a.N) sg = (g - sh + a.N) % a.N;
+                    else sg = a.N + (g - a.N + sh) % a.N;
+                    cs = f * a.G + sg;
+                }
+                tma_load_3d(base + cc * PLANE_BYTES, exact ? &map_tile : &map_box, bar, box_x, box_y, plane0 + cs);
+            }
+        }
+        mbar_wait(bar, parity);
+        parity ^= 1u;
+        if (xd >= a.Wd) continue;  // (no barrier below this point inside the pass)
+        float *dp = dst_n + (size_t)c0 * plane_d + xd;
+        if (exact) {
+#pragma unroll
+            for (int p = 0; p < PIX; ++p) {
+                const int row = warp + p * (THREADS / 32);
+                if (ty0 + row >= a.Hd) break;
+                const int sx = (sx0 + i00 * lane + i01 * row) & (TILE - 1), sy = (sy0 + i10 * lane + i11 * row) & (TILE - 1);
+                // SWIZZLE_128B: 16-byte chunk index XOR (row & 7); rows are 128 bytes, planes 1024-byte aligned
+                const int o = sy * TILE + ((((sx >> 2) ^ (sy & 7)) << 2) | (sx & 3));
+                float *dpp = dp + (size_t)(ty0 + row) * a.Wd;
+#pragma unroll
+                for (int cc = 0; cc < CG; ++cc)
+                    if (cc < nc) st_stream(dpp + (size_t)cc * plane_d, planes[cc * (PLANE_BYTES / 4) + o]);
+            }
+        } else {
+            // taps of one pixel at a time (offsets / weights shared by the CG channels): 8 live registers per
+            // pixel instead of 32 keeps 6+ CTAs resident per SM, which is what hides the TMA latency
+#pragma unroll 1
+            for (int p = 0; p < PIX; ++p) {
+                const int row = warp + p * (THREADS / 32);
+                if (ty0 + row >= a.Hd) break;
+                const float fr = (float)row;
+                const float xr = fmaf(f00, fl, fmaf(f01, fr, bx)), yr = fmaf(f10, fl, fmaf(f11, fr, by));
+                const float xf = floorf(xr), yf = floorf(yr);
+                const float fx = xr - xf, fy = yr - yf;
+                const int x0 = (int)xf, y0 = (int)yf;
+                const int cx0 = min(max(x0, cx_lo), cx_hi), cx1 = min(max(x0 + 1, cx_lo), cx_hi);
+                const int cy0 = min(max(y0, 0), bhm1) * BOXW, cy1 = min(max(y0 + 1, 0), bhm1) * BOXW;
+                float wx0 = 1.f - fx, wx1 = fx, wy0 = 1.f - fy, wy1 = fy;
+                if (ZERO) {
+                    // absolute tap coordinates against the padded extent [-pad, size-1+pad]
+                    const int ax0 = x0 + box_x, ay0 = y0 + y_lo;
+                    const int lo = -a.pad, hx = a.Ws - 1 + a.pad, hy = a.Hs - 1 + a.pad;
+                    if (ax0 < lo || ax0 > hx) wx0 = 0.f;
+                    if (ax0 + 1 < lo || ax0 + 1 > hx) wx1 = 0.f;
+                    if (ay0 < lo || ay0 > hy) wy0 = 0.f;
+                    if (ay0 + 1 < lo || ay0 + 1 > hy) wy1 = 0.f;
+                }
+                const float w00 = wy0 * wx0, w01 = wy0 * wx1, w10 = wy1 * wx0, w11 = wy1 * wx1;
+                const int o00 = cy0 + cx0, o01 = cy0 + cx1, o10 = cy1 + cx0, o11 = cy1 + cx1;
+                float *dpp = dp + (size_t)(ty0 + row) * a.Wd;
+#pragma unroll
+                for (int cc = 0; cc < CG; ++cc) {
+                    if (cc < nc) {
+                        const float *sm = planes + cc * (PLANE_BYTES / 4);
+                        // same tap order as ATen grid_sample: nw, ne, sw, se
+                        float v = sm[o00] * w00;
+                        v = fmaf(sm[o01], w01, v);
+                        v = fmaf(sm[o10], w10, v);
+                        v = fmaf(sm[o11], w11, v);
+                        st_stream(dpp + (size_t)cc * plane_d, v);
+                    }
+                }
+            }
+        }
+    }
+}
+
+// ---- host side ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        (void)cudaGetLastError();
+        return (EncodeTiledFn)p;
+    }();
+    return fn;
+}
+
+static int make_plane_map(CUtensorMap *m, const float *src, int W, int H, long long planes, int box_w, int box_h,
+                          CUtensorMapSwizzle swz) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) {
+        set_error("cuTensorMapEncodeTiled is not available from the CUDA driver");
+        return (int)cudaErrorNotSupported;
+    }
+    const cuuint64_t gdim[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)planes};
+    const cuuint64_t gstride[2] = {(cuuint64_t)W * 4, (cuuint64_t)W * (cuuint64_t)H * 4};
+    const cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void *)src, gdim, gstride, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed with CUresult %d (W=%d H=%d planes=%lld box=%dx%d)", (int)r, W, H, planes,
+                  box_w, box_h);
+        return (int)cudaErrorInvalidValue;
+    }
+    return 0;
+}
+
+template <int CG, bool ZERO>
+static int launch_cfg(const CUtensorMap &mb, const CUtensorMap &mt, const ResampleArgs &a, unsigned blocks,
+                      cudaStream_t st) {
+    const size_t smem = (size_t)CG * PLANE_BYTES + 1024 + 16;
+    static bool configured = false;
+    if (!configured) {
+        EQB_CUDA(cudaFuncSetAttribute(resample_tma_kernel<CG, ZERO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)smem));
+        configured = true;
+    }
+    resample_tma_kernel<CG, ZERO><<<blocks, THREADS, smem, st>>>(mb, mt, a);
+    return 0;
+}
+
+int launch_resample_tma(const ResampleArgs &a, int n_dst_samples, cudaStream_t st, const char *what, int *handled) {
+    *handled = 0;
+    const long long planes = (long long)a.B * a.C;
+    if (((uintptr_t)a.src & 15) != 0 || (a.Ws & 3) != 0 || a.Ws < BOXW || a.Hs < BOXH || planes <= 0 ||
+        planes >= (1LL << 31))
+        return 0;
+    const long long blocks = (long long)a.tiles_x * a.tiles_y * n_dst_samples;
+    if (blocks == 0) {
+        *handled = 1;
+        return 0;
+    }
+    EQB_REQUIRE(blocks < (1LL << 31), "%s: grid too large (%lld tiles)", what, blocks);
+    CUtensorMap mb, mt;
+    int e = make_plane_map(&mb, a.src, a.Ws, a.Hs, planes, BOXW, BOXH, CU_TENSOR_MAP_SWIZZLE_NONE);
+    if (e) return e;
+    e = make_plane_map(&mt, a.src, a.Ws, a.Hs, planes, TILE, TILE, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (e) return e;
+    // can a tap leave the padded extent (zero region)?  radius of the destination rectangle about the centre
+    const double ux = fmax(fabs(a.ox), fabs(a.Wd - 1 + a.ox)), uy = fmax(fabs(a.oy), fabs(a.Hd - 1 + a.oy));
+    const double rad = sqrt(ux * ux + uy * uy) + 1.0;
+    const bool zero = rad > 0.5 * (a.Ws - 1) + a.pad || rad > 0.5 * (a.Hs - 1) + a.pad;
+    const int cg = (a.C % 3 == 0 && a.C % 4 != 0) ? 3 : (a.C >= 4 ? 4 : a.C);
+    const unsigned nb = (unsigned)blocks;
+    switch (cg * 2 + (zero ? 1 : 0)) {
+        case 2: e = launch_cfg<1, false>(mb, mt, a, nb, st); break;
+        case 3: e = launch_cfg<1, true>(mb, mt, a, nb, st); break;
+        case 4: e = launch_cfg<2, false>(mb, mt, a, nb, st); break;
+        case 5: e = launch_cfg<2, true>(mb, mt, a, nb, st); break;
+        case 6: e = launch_cfg<3, false>(mb, mt, a, nb, st); break;
+        case 7: e = launch_cfg<3, true>(mb, mt, a, nb, st); break;
+        case 8: e = launch_cfg<4, false>(mb, mt, a, nb, st); break;
+        default: e = launch_cfg<4, true>(mb, mt, a, nb, st); break;
+    }
+    if (e) return e;
+    *handled = 1;
+    return finish_launch(what);
+}
+
+}  // namespace eqb

@@ -2,6 +2,8 @@
 // group pool / select + prior statistic (a9/a13), cosine activations (a12), frames (a14..a17).
 #include <stdarg.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace eqb {
@@ -19,12 +21,19 @@ void set_error(const char *fmt, ...) {
 // _upsample_bilinear2d_aa (align_corners=False): per output index i, centre = scale*(i+0.5),
 // support = max(scale,1), taps j in [max(0,int(centre-support+.5)), min(in,int(centre+support+.5))),
 // w_j = max(0, 1-|(j-centre+.5)/max(scale,1)|) normalised to sum 1.
-// One thread per output pixel; horizontal pass first, then vertical, as ATen does.
+// Horizontal pass first, then vertical, as ATen does (same fma order per output as one thread per pixel).
+//
+// One CTA = one plane x a band of RS_ROWS output rows x up to RS_COLS output columns.  The tap tables of the
+// band are built once into shared memory; thread (x, y) owns output column x: it keeps that column's
+// horizontal weights in registers, filters the band's input rows straight from global memory (neighbouring
+// lanes read overlapping 128-byte lines -> L1 hits) into a shared-memory strip, then the strip is filtered
+// vertically.  Reads: the crop window once (+ band overlap), writes: the resized plane once.
 // -------------------------------------------------------------------------------------------------
 constexpr int AA_MAX_TAPS = 16;
+constexpr int RS_ROWS = 16, RS_COLS = 128;
 
-struct AaAxis {
-    int lo, n;
+struct AaAxis {   // 17 words: odd stride -> conflict-free per-lane reads
+    int lo_n;     // lo | n << 20
     float w[AA_MAX_TAPS];
 };
 
@@ -34,38 +43,67 @@ __device__ __forceinline__ void aa_axis(int i, int in_size, float scale, AaAxis 
     const float center = scale * (i + 0.5f);
     const int lo = max((int)(center - support + 0.5f), 0);
     const int hi = min((int)(center + support + 0.5f), in_size);
-    ax.lo = lo;
-    ax.n = min(hi - lo, AA_MAX_TAPS);
+    const int n = min(hi - lo, AA_MAX_TAPS);
     float tot = 0.f;
-    for (int j = 0; j < ax.n; ++j) {
+    for (int j = 0; j < n; ++j) {
         const float v = fmaxf(1.f - fabsf((j + lo - center + 0.5f) * invscale), 0.f);
         ax.w[j] = v;
         tot += v;
     }
-    for (int j = 0; j < ax.n; ++j) ax.w[j] = tot != 0.f ? ax.w[j] / tot : 0.f;
+    for (int j = 0; j < n; ++j) ax.w[j] = tot != 0.f ? ax.w[j] / tot : 0.f;
+    for (int j = n > 0 ? n : 0; j < AA_MAX_TAPS; ++j) ax.w[j] = 0.f;
+    ax.lo_n = lo | (max(n, 0) << 20);
 }
 
-__global__ void __launch_bounds__(256) crop_resize_aa_kernel(const float *__restrict__ x, float *__restrict__ y,
-                                                             int planes, int H, int W, int top, int left, int ch,
-                                                             int cw, int oh, int ow, float sy, float sx) {
-    const long long total = (long long)planes * oh * ow;
-    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
-         t += (long long)gridDim.x * blockDim.x) {
-        const int ox = (int)(t % ow);
-        const long long r = t / ow;
-        const int oy = (int)(r % oh);
-        const long long pl = r / oh;
-        AaAxis ax, ay;
-        aa_axis(ox, cw, sx, ax);
-        aa_axis(oy, ch, sy, ay);
-        const float *src = x + (size_t)pl * H * W + (size_t)(top + ay.lo) * W + left + ax.lo;
-        float acc = 0.f;
-        for (int j = 0; j < ay.n; ++j) {
+template <int MAXT>
+__global__ void __launch_bounds__(256) crop_resize_aa_kernel(const float *__restrict__ x, float *__restrict__ y, int H,
+                                                             int W, int top, int left, int ch, int cw, int oh, int ow,
+                                                             float sy, float sx, int bands, int chunks, int strip_rows) {
+    extern __shared__ __align__(16) unsigned char rs_smem[];
+    AaAxis *tx = reinterpret_cast<AaAxis *>(rs_smem);         // [RS_COLS]
+    AaAxis *ty = tx + RS_COLS;                                // [RS_ROWS]
+    float *strip = reinterpret_cast<float *>(ty + RS_ROWS);   // [strip_rows][RS_COLS]
+    int b = blockIdx.x;
+    const int chunk = b % chunks; b /= chunks;
+    const int band = b % bands;
+    const size_t plane = b / bands;
+    const int ox0 = chunk * RS_COLS, oy0 = band * RS_ROWS;
+    const int ncols = min(RS_COLS, ow - ox0), nrows = min(RS_ROWS, oh - oy0);
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x, nthreads = blockDim.x * blockDim.y;
+
+    for (int t = tid; t < ncols + nrows; t += nthreads) {
+        if (t < ncols) aa_axis(ox0 + t, cw, sx, tx[t]);
+        else aa_axis(oy0 + t - ncols, ch, sy, ty[t - ncols]);
+    }
+    __syncthreads();
+    const int row_lo = ty[0].lo_n & 0xfffff;
+    const int row_hi = (ty[nrows - 1].lo_n & 0xfffff) + (ty[nrows - 1].lo_n >> 20);
+    const int nr = min(row_hi - row_lo, strip_rows);
+    const int ox = threadIdx.x;
+    if (ox < ncols) {
+        // horizontal pass: this thread's column weights live in registers
+        const int lo = tx[ox].lo_n & 0xfffff, n = tx[ox].lo_n >> 20;
+        float w[MAXT];
+#pragma unroll
+        for (int i = 0; i < MAXT; ++i) w[i] = tx[ox].w[i];
+        const float *src = x + plane * (size_t)H * W + (size_t)(top + row_lo) * W + left + lo;
+        for (int r = threadIdx.y; r < nr; r += blockDim.y) {
+            const float *rp = src + (size_t)r * W;
             float h = 0.f;
-            for (int i = 0; i < ax.n; ++i) h = fmaf(__ldg(src + (size_t)j * W + i), ax.w[i], h);
-            acc = fmaf(h, ay.w[j], acc);
+#pragma unroll
+            for (int i = 0; i < MAXT; ++i)
+                if (i < n) h = fmaf(__ldg(rp + i), w[i], h);
+            strip[r * RS_COLS + ox] = h;
         }
-        y[t] = acc;
+    }
+    __syncthreads();
+    if (ox < ncols) {
+        for (int oy = threadIdx.y; oy < nrows; oy += blockDim.y) {
+            const int lo = (ty[oy].lo_n & 0xfffff) - row_lo, n = ty[oy].lo_n >> 20;
+            float acc = 0.f;
+            for (int j = 0; j < n; ++j) acc = fmaf(strip[(lo + j) * RS_COLS + ox], ty[oy].w[j], acc);
+            y[(plane * oh + (oy0 + oy)) * (size_t)ow + ox0 + ox] = acc;
+        }
     }
 }
 
@@ -391,9 +429,20 @@ extern "C" int eqb_crop_resize_aa(const float *x, float *y, int B, int C, int H,
                     "eqb_crop_resize_aa: down-scale factor above %d not supported", (AA_MAX_TAPS - 2) / 2);
     if (B == 0) return 0;
     EQB_REQUIRE(x && y, "eqb_crop_resize_aa: null pointer");
-    const long long total = (long long)B * C * out_h * out_w;
-    crop_resize_aa_kernel<<<grid_for(total, 256, num_sms() * 16), 256, 0, (cudaStream_t)stream>>>(
-        x, y, B * C, H, W, top, left, crop_h, crop_w, out_h, out_w, sy, sx);
+    const int bands = (out_h + RS_ROWS - 1) / RS_ROWS, chunks = (out_w + RS_COLS - 1) / RS_COLS;
+    const long long blocks = (long long)B * C * bands * chunks;
+    EQB_REQUIRE(blocks < (1LL << 31), "eqb_crop_resize_aa: grid too large");
+    // input rows one band can touch: RS_ROWS output rows apart by sy, plus the filter support on both sides
+    const int strip_rows = (int)((RS_ROWS - 1) * sy + 2 * sup_y + 3);
+    const size_t smem = (size_t)(RS_COLS + RS_ROWS) * sizeof(AaAxis) + (size_t)strip_rows * RS_COLS * sizeof(float);
+    EQB_UNSUPPORTED(smem > 200 * 1024, "eqb_crop_resize_aa: down-scale factor too large for the shared-memory strip");
+    const int bx = 32 * ((std::min(out_w, RS_COLS) + 31) / 32);
+    const dim3 block(bx, 256 / bx);
+    const bool narrow = (int)(2 * sup_x + 2) <= 6;
+    auto kern = narrow ? crop_resize_aa_kernel<6> : crop_resize_aa_kernel<AA_MAX_TAPS>;
+    if (smem > 48 * 1024) EQB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(unsigned)blocks, block, smem, (cudaStream_t)stream>>>(x, y, H, W, top, left, crop_h, crop_w, out_h, out_w, sy,
+                                                                 sx, bands, chunks, strip_rows);
     return finish_launch("eqb_crop_resize_aa");
 }
 

@@ -339,3 +339,98 @@ def test_edge_cases(cuda_device):
         ops.warp_invert(torch.rand(1, 5, 8, 8, device=dev), torch.zeros(1, dtype=torch.int32, device=dev), 4, False, True)
     with pytest.raises(RuntimeError):
         ops.warp_canonicalize(torch.rand(1, 3, 8, 8), torch.zeros(1, dtype=torch.int32), 4, False)
+
+
+# ---------------------------------------------------------------------------------------------------
+# TMA-staged warp kernels (resample_tma.cu): every element of C8 / D4 / D8 on TMA-eligible shapes, against the
+# oracle and against the generic kernel (EQB_NO_TMA=1), plus bit-exactness of the quarter-turn permutations
+# ---------------------------------------------------------------------------------------------------
+def _no_tma(fn):
+    import os
+    os.environ["EQB_NO_TMA"] = "1"
+    try:
+        return fn()
+    finally:
+        del os.environ["EQB_NO_TMA"]
+
+
+@pytest.mark.parametrize("n,reflect,shape", [
+    (8, False, (16, 3, 224, 224)),     # BASELINE cfg2 image shape
+    (4, True, (8, 3, 224, 224)),       # D4 (cfg3 group)
+    (8, True, (16, 3, 96, 64)),        # D8, H != W: zero fill reachable, quarter turns are not permutations of the grid
+    (8, False, (8, 2, 52, 60)),
+    (6, False, (6, 4, 64, 64)),        # N not a power of two
+])
+def test_warp_tma_vs_oracle_and_generic(n, reflect, shape, cuda_device):
+    ops = _mods()[0]
+    dev = cuda_device
+    num_group = n * (2 if reflect else 1)
+    g = torch.Generator().manual_seed(11)
+    b = shape[0]
+    x = torch.rand(*shape, generator=g)
+    idx = torch.arange(b) % num_group
+    ang = torch.linspace(0.0, 360.0, n + 1)[:n][idx % n]
+    refl = (idx >= n).float() if reflect else None
+    xd, idxd = x.to(dev), idx.to(dev).int()
+    y = ops.warp_canonicalize(xd, idxd, n, reflect)
+    assert rel_err(y.cpu(), O.canonicalize_image(x, ang, refl)) < RTOL
+    y_gen = _no_tma(lambda: ops.warp_canonicalize(xd, idxd, n, reflect))
+    assert rel_err(y.cpu(), y_gen.cpu()) < 2e-5
+    yi = ops.warp_invert(xd, idxd, n, reflect, False)
+    assert rel_err(yi.cpu(), O.invert_image_features(x, ang, refl, n, num_group, "scalar")) < RTOL
+    f = torch.randn(b, 2 * num_group, shape[2], shape[3], generator=g)
+    fr = ops.warp_invert(f.to(dev), idxd, n, reflect, True)
+    assert rel_err(fr.cpu(), O.invert_image_features(f, ang, refl, n, num_group, "regular")) < RTOL
+    fr_gen = _no_tma(lambda: ops.warp_invert(f.to(dev), idxd, n, reflect, True))
+    assert rel_err(fr.cpu(), fr_gen.cpu()) < 2e-5
+    if shape[2] == shape[3] and n % 4 == 0:
+        # quarter turns of a square image are exact permutations: canonicalize rotates by -angle
+        for i in range(b):
+            r = int(idx[i]) % n
+            if (4 * r) % n == 0 and not (reflect and int(idx[i]) >= n):
+                assert torch.equal(y[i].cpu(), torch.rot90(x[i], -(4 * r // n), (1, 2))), (i, r)
+
+
+def test_orbit_expand_tma_vs_oracle(cuda_device):
+    ops = _mods()[0]
+    g = torch.Generator().manual_seed(12)
+    for n, reflect, r in [(4, True, 96), (8, False, 64)]:
+        x = torch.rand(5, 3, r, r, generator=g)
+        out = ops.orbit_expand(x.to(cuda_device), (r + 1) // 2, r, n, reflect)
+        ref = O.group_augment(x, n, reflect, r)
+        assert out.shape == ref.shape
+        assert rel_err(out.cpu(), ref) < RTOL
+        out_gen = _no_tma(lambda: ops.orbit_expand(x.to(cuda_device), (r + 1) // 2, r, n, reflect))
+        assert rel_err(out.cpu(), out_gen.cpu()) < 2e-5
+
+
+def test_full_size_round_trip_properties(cuda_device):
+    """BASELINE cfg2 size (512 x 3 x 224 x 224): size-independent properties instead of an oracle run."""
+    ops = _mods()[0]
+    dev = cuda_device
+    n = 8
+    x = torch.rand(512, 3, 224, 224, generator=torch.Generator().manual_seed(13)).to(dev)
+    idx = (torch.arange(512) % n).to(dev).int()
+    y = ops.warp_canonicalize(x, idx, n, False)
+    back = ops.warp_invert(y, idx, n, False, False)
+    quarter = (idx % 2 == 0)
+    # quarter turns: canonicalize is a permutation (== rot90 by -angle) and invert undoes it bit for bit
+    for r in range(0, n, 2):
+        sel = idx == r
+        assert torch.equal(y[sel], torch.rot90(x[sel], -(r // 2), (2, 3)))
+    assert torch.equal(back[quarter], x[quarter])
+    # 45-degree elements: two bilinear resamplings of iid noise do not return x, but they commute with the group:
+    # rotating by g then by h equals rotating by g+h up to interpolation, and means are preserved inside the disc
+    odd = ~quarter
+    assert float((y[odd].mean() - x[odd].mean()).abs()) < 5e-3
+    # linearity: warp(a*x1 + x2) == a*warp(x1) + warp(x2) (same taps, fp32 rounding only)
+    x2 = torch.rand(512, 3, 224, 224, generator=torch.Generator().manual_seed(14)).to(dev)
+    lhs = ops.warp_canonicalize(0.5 * x + x2, idx, n, False)
+    rhs = 0.5 * y + ops.warp_canonicalize(x2, idx, n, False)
+    assert float((lhs - rhs).abs().max()) < 1e-6
+    # regular representation: channel roll by the group index composes with the inverse roll to the identity
+    f = torch.randn(64, 16, 224, 224, generator=torch.Generator().manual_seed(15)).to(dev)
+    i4 = ((torch.arange(64) % 4) * 2).to(dev).int()                      # quarter turns of C8
+    fwd = ops.warp_invert(f, i4, n, False, True)
+    inv = ops.warp_invert(fwd, (n - i4) % n, n, False, True)
+    assert torch.equal(inv, f)
