@@ -24,6 +24,7 @@ struct ResampleArgs {
     int pad;        // >=0: taps inside [-pad, size-1+pad] are replicate-clamped, zero beyond
     double ox, oy;  // dst pixel -> coordinate relative to the rotation centre: u = xd + ox
     int tiles_x, tiles_y;
+    int sample0;    // first destination sample of this launch (TMA path: the batch is chunked over gridDim.z)
     // (cos, sin) of 2*pi*r/N for r < N <= 16, filled on the host (exact 0 / +-1 at quarter turns); has_cs = 0 ->
     // the kernels evaluate sincospi themselves
     int has_cs;

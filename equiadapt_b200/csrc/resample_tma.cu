@@ -22,6 +22,8 @@
 // rotated tiles is served by L2.
 #include <cuda.h>
 
+#include <algorithm>
+
 #include "resample.cuh"
 
 namespace eqb {
@@ -54,6 +56,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "}\n" ::"r"(bar), "r"(parity)
         : "memory");
 }
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int x, int y, int z) {
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
@@ -61,155 +68,181 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map
         : "memory");
 }
 
-template <int CG, bool ZERO>
-__global__ void __launch_bounds__(THREADS, 6) resample_tma_kernel(const __grid_constant__ CUtensorMap map_box,
-                                                               const __grid_constant__ CUtensorMap map_tile,
-                                                               const __grid_constant__ ResampleArgs a) {
-    extern __shared__ unsigned char smem_raw[];
-    // [CG planes, 10 KB apart, 1024-aligned][mbarrier]
-    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const float *planes = reinterpret_cast<const float *>(smem_raw + (base - smem_u32(smem_raw)));
-    const uint32_t bar = base + CG * PLANE_BYTES;
+// Geometry of one tile, computed once per CTA by warp 0 and broadcast through shared memory
+// (it costs ~400 instructions incl. fp64: done by all 8 warps it was 45 % of the kernel's issue slots).
+struct TileGeom {
+    int exact, interior, box_x, box_y, y_lo;
+    int cx_lo, cx_hi, bhm1;             // bilinear: clamp range of the taps inside the box
+    float bx, by, f00, f01, f10, f11;   // bilinear: box-relative source coordinate of pixel (tx0,ty0) and the matrix
+    int i00, i01, i10, i11, sx0, sy0;   // exact: integer matrix and box-relative source of pixel (tx0,ty0)
+    int r, plane0;                      // rotation index (regular-rep roll) and first source plane
+};
 
-    const int tiles = a.tiles_x * a.tiles_y;
-    const int sample_d = blockIdx.x / tiles;  // destination sample
-    const int t = blockIdx.x - sample_d * tiles;
-    const int ty0 = (t / a.tiles_x) * TILE, tx0 = (t % a.tiles_x) * TILE;
+__device__ __forceinline__ int regular_src_channel(const ResampleArgs &a, int cs, int r) {
+    // out[:, f*G+g] = in[:, f*G + src_g(g)]   (roll_by_gather, images/utils.py:8-29,66-77)
+    const int f = cs / a.G, g = cs - f * a.G, sh = a.roll[r];
+    int sg;
+    if (g < a.N) sg = (g - sh + a.N) % a.N;
+    else sg = a.N + (g - a.N + sh) % a.N;
+    return f * a.G + sg;
+}
+
+template <int CG, bool ZERO>
+__global__ void __launch_bounds__(THREADS, 5) resample_tma_kernel(const __grid_constant__ CUtensorMap map_box,
+                                                                  const __grid_constant__ CUtensorMap map_tile,
+                                                                  const __grid_constant__ ResampleArgs a) {
+    extern __shared__ unsigned char smem_raw[];
+    // [CG planes, 10 KB apart, 1024-aligned][mbarrier][TileGeom]
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    unsigned char *aligned = smem_raw + (base - smem_u32(smem_raw));
+    const uint32_t bar = base + CG * PLANE_BYTES;
+    TileGeom &geo = *reinterpret_cast<TileGeom *>(aligned + CG * PLANE_BYTES + 16);
+
+    const int sample_d = blockIdx.z + a.sample0;  // destination sample
+    const int ty0 = blockIdx.y * TILE, tx0 = blockIdx.x * TILE;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
-    if (threadIdx.x == 0) {
-        mbar_init(bar, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_init(bar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        // ---- group element of this sample -> A ------------------------------------------------------
+        int sample_s, r, mirror_src = 0, mirror_dst = 0;
+        double sign;
+        if (a.mode == MODE_ORBIT) {
+            const int g = sample_d / a.B;
+            sample_s = sample_d - g * a.B;
+            r = g % a.N;
+            mirror_dst = g >= a.N;  // rotate, THEN hflip (discrete_group.py:404-406)
+            sign = -1.0;
+        } else {
+            sample_s = sample_d;
+            const int g = min(max(a.idx[sample_s], 0), a.G - 1);
+            r = g % a.N;
+            const int refl = g >= a.N;
+            if (a.mode == MODE_CANON) {
+                mirror_src = refl;  // hflip, THEN rotate(-theta) (discrete_group.py:209-213)
+                sign = -1.0;
+            } else {
+                mirror_dst = a.reflect && !refl;  // images/utils.py:59-64 (reference quirk A.4-2)
+                sign = 1.0;
+            }
+        }
+        double c, s;
+        group_cs(a, r, sign, c, s);
+        double a00 = c, a01 = -s, a10 = s, a11 = c;
+        if (mirror_dst) { a00 = -a00; a10 = -a10; }
+        if (mirror_src) { a00 = -a00; a01 = -a01; }
+        const double cx = 0.5 * (a.Ws - 1), cy = 0.5 * (a.Hs - 1);
+        // ---- source footprint of the tile ----------------------------------------------------------
+        const int tw = min(TILE, a.Wd - tx0), th = min(TILE, a.Hd - ty0);
+        const double u0 = (double)tx0 + a.ox, v0 = (double)ty0 + a.oy;
+        const double xs_org = cx + a00 * u0 + a01 * v0, ys_org = cy + a10 * u0 + a11 * v0;  // source of (tx0,ty0)
+        const double dw = (double)(tw - 1), dh = (double)(th - 1);
+        const double xmin = xs_org + fmin(a00 * dw, 0.0) + fmin(a01 * dh, 0.0);
+        const double xmax = xs_org + fmax(a00 * dw, 0.0) + fmax(a01 * dh, 0.0);
+        const double ymin = ys_org + fmin(a10 * dw, 0.0) + fmin(a11 * dh, 0.0);
+        const double ymax = ys_org + fmax(a10 * dw, 0.0) + fmax(a11 * dh, 0.0);
+        const int fxmin = (int)floor(xmin), fxmax = (int)floor(xmax), fymin = (int)floor(ymin), fymax = (int)floor(ymax);
+        // exact tile: quarter turn (cos / sin are exact 0 / +-1 there), integral source coordinates, no clamping,
+        // source tile starting on a 16-byte boundary (always true for square images whose side is a multiple of 4)
+        const bool exact = (c == 0.0 || s == 0.0) && xs_org == floor(xs_org) && ys_org == floor(ys_org) && fxmin >= 0 &&
+                           fxmax <= a.Ws - 1 && fymin >= 0 && fymax <= a.Hs - 1 && (fxmin & 3) == 0;
+        // interior tile: every tap, even one pixel beyond the fp64 footprint (fp32 rounding of the per-pixel
+        // coordinates may floor() to the neighbour), lies inside the image -> no clamping in the pixel loop
+        const bool interior = !exact && fxmin >= 1 && fxmax + 2 <= a.Ws - 1 && fymin >= 1 && fymax + 2 <= a.Hs - 1;
+        int box_x, box_y, y_lo = 0, cx_lo = 0, cx_hi = 0, bhm1 = 0;
+        if (exact) {
+            box_x = fxmin; box_y = fymin;
+        } else if (interior) {
+            box_x = (fxmin - 1) & ~3; box_y = fymin - 1; y_lo = box_y;     // <= 1 + 46 + 1 + 3 = 51 < 52 wide
+        } else {
+            const int x_lo = min(max(fxmin, 0), a.Ws - 1);
+            y_lo = min(max(fymin, 0), a.Hs - 1);
+            box_x = x_lo & ~3; box_y = y_lo;                               // 16-byte aligned start
+            cx_lo = x_lo - box_x;                                          // taps are clamped into [cx_lo, cx_hi]
+            cx_hi = min(max(fxmax + 1, 0), a.Ws - 1) - box_x;              // <= 46 + 3
+            bhm1 = min(max(fymax + 1, 0), a.Hs - 1) - y_lo;                // <= 46
+        }
+        const int plane0 = sample_s * a.C;  // first source plane of this sample in the (W,H,B*C) tensor map
+        if (lane == 0) {
+            // first pass of the TMA loads goes out before anybody else needs the geometry
+            const int nc = min(CG, a.C);
+            mbar_expect_tx(bar, (uint32_t)nc * (exact ? TILE_BYTES : BOX_BYTES));
+            for (int cc = 0; cc < nc; ++cc) {
+                const int cs = a.mode == MODE_INV_REGULAR ? regular_src_channel(a, cc, r) : cc;
+                tma_load_3d(base + cc * PLANE_BYTES, exact ? &map_tile : &map_box, bar, box_x, box_y, plane0 + cs);
+            }
+            geo.exact = exact; geo.interior = interior; geo.box_x = box_x; geo.box_y = box_y; geo.y_lo = y_lo;
+            geo.cx_lo = cx_lo; geo.cx_hi = cx_hi; geo.bhm1 = bhm1;
+            geo.bx = (float)(xs_org - (double)box_x); geo.by = (float)(ys_org - (double)box_y);
+            geo.f00 = (float)a00; geo.f01 = (float)a01; geo.f10 = (float)a10; geo.f11 = (float)a11;
+            geo.i00 = (int)a00; geo.i01 = (int)a01; geo.i10 = (int)a10; geo.i11 = (int)a11;
+            geo.sx0 = (int)xs_org - box_x; geo.sy0 = (int)ys_org - box_y;
+            geo.r = r; geo.plane0 = plane0;
+        }
     }
     __syncthreads();
 
-    // ---- group element of this sample -> A (CTA-uniform) -----------------------------------------
-    int sample_s, r, mirror_src = 0, mirror_dst = 0;
-    double sign;
-    if (a.mode == MODE_ORBIT) {
-        const int g = sample_d / a.B;
-        sample_s = sample_d - g * a.B;
-        r = g % a.N;
-        mirror_dst = g >= a.N;  // rotate, THEN hflip (discrete_group.py:404-406)
-        sign = -1.0;
-    } else {
-        sample_s = sample_d;
-        const int g = min(max(a.idx[sample_s], 0), a.G - 1);
-        r = g % a.N;
-        const int refl = g >= a.N;
-        if (a.mode == MODE_CANON) {
-            mirror_src = refl;  // hflip, THEN rotate(-theta) (discrete_group.py:209-213)
-            sign = -1.0;
-        } else {
-            mirror_dst = a.reflect && !refl;  // images/utils.py:59-64 (reference quirk A.4-2)
-            sign = 1.0;
-        }
-    }
-    double c, s;
-    group_cs(a, r, sign, c, s);
-    double a00 = c, a01 = -s, a10 = s, a11 = c;
-    if (mirror_dst) { a00 = -a00; a10 = -a10; }
-    if (mirror_src) { a00 = -a00; a01 = -a01; }
-    const double cx = 0.5 * (a.Ws - 1), cy = 0.5 * (a.Hs - 1);
-
-    // ---- source footprint of the tile --------------------------------------------------------------
-    const int tw = min(TILE, a.Wd - tx0), th = min(TILE, a.Hd - ty0);
-    const double u0 = (double)tx0 + a.ox, v0 = (double)ty0 + a.oy;
-    const double xs_org = cx + a00 * u0 + a01 * v0, ys_org = cy + a10 * u0 + a11 * v0;  // source of pixel (tx0,ty0)
-    double xmin = xs_org, xmax = xs_org, ymin = ys_org, ymax = ys_org;
-#pragma unroll
-    for (int k = 1; k < 4; ++k) {
-        const double du = (k & 1) ? (double)(tw - 1) : 0.0, dv = (k & 2) ? (double)(th - 1) : 0.0;
-        const double xs = xs_org + a00 * du + a01 * dv, ys = ys_org + a10 * du + a11 * dv;
-        xmin = fmin(xmin, xs); xmax = fmax(xmax, xs);
-        ymin = fmin(ymin, ys); ymax = fmax(ymax, ys);
-    }
-    const int fxmin = (int)floor(xmin), fxmax = (int)floor(xmax), fymin = (int)floor(ymin), fymax = (int)floor(ymax);
-    // exact tile: quarter turn (sincospi returns exact 0 / +-1 there), integral source coordinates, no clamping
-    // and a source tile that starts on a 16-byte boundary (always true for square images whose side is a multiple of 4)
-    const bool exact = (c == 0.0 || s == 0.0) && xs_org == floor(xs_org) && ys_org == floor(ys_org) && fxmin >= 0 &&
-                       fxmax <= a.Ws - 1 && fymin >= 0 && fymax <= a.Hs - 1 && (fxmin & 3) == 0;
-
+    const bool exact = geo.exact != 0;
     const int xd = tx0 + lane;
-    const size_t plane_d = (size_t)a.Hd * a.Wd;
-    float *dst_n = a.dst + (size_t)sample_d * a.C * plane_d;
-    const int plane0 = sample_s * a.C;  // first source plane of this sample in the (W,H,B*C) tensor map
-
-    // CTA-uniform geometry of the box and of the coordinate map relative to its origin
-    int box_x, box_y;
-    int i00 = 0, i01 = 0, i10 = 0, i11 = 0, sx0 = 0, sy0 = 0;       // exact path
-    int cx_lo = 0, cx_hi = 0, bhm1 = 0, y_lo = 0;                    // bilinear path
-    float bx = 0.f, by = 0.f, f00 = 0.f, f01 = 0.f, f10 = 0.f, f11 = 0.f;
-    if (exact) {
-        box_x = fxmin; box_y = fymin;
-        i00 = (int)a00; i01 = (int)a01; i10 = (int)a10; i11 = (int)a11;
-        sx0 = (int)xs_org - box_x; sy0 = (int)ys_org - box_y;
-    } else {
-        const int x_lo = min(max(fxmin, 0), a.Ws - 1);
-        y_lo = min(max(fymin, 0), a.Hs - 1);
-        box_x = x_lo & ~3; box_y = y_lo;                                  // 16-byte aligned start
-        cx_lo = x_lo - box_x;                                            // taps are clamped into [cx_lo, cx_hi]
-        cx_hi = min(max(fxmax + 1, 0), a.Ws - 1) - box_x;                // <= 46 + 3
-        bhm1 = min(max(fymax + 1, 0), a.Hs - 1) - y_lo;                  // <= 46
-        bx = (float)(xs_org - (double)box_x); by = (float)(ys_org - (double)y_lo);
-        f00 = (float)a00; f01 = (float)a01; f10 = (float)a10; f11 = (float)a11;
-    }
-    const float fl = (float)lane;
+    const int plane_d = a.Hd * a.Wd;                       // host guarantees C * Hd * Wd < 2^31
+    float *dst_px = a.dst + (size_t)sample_d * a.C * plane_d + (size_t)(ty0 + warp) * a.Wd + xd;
+    const int row_step = (THREADS / 32) * a.Wd;            // this thread's pixels are 8 rows apart
+    const int rows_left = a.Hd - ty0 - warp;               // pixel p is inside the image iff p*8 < rows_left
+    const uint32_t sm0 = base;
 
     uint32_t parity = 0;
     for (int c0 = 0; c0 < a.C; c0 += CG) {
         const int nc = min(CG, a.C - c0);
-        if (c0) __syncthreads();  // every thread is done reading the planes of the previous pass
-        if (threadIdx.x == 0) {
-            mbar_expect_tx(bar, (uint32_t)nc * (exact ? TILE_BYTES : BOX_BYTES));
-            for (int cc = 0; cc < nc; ++cc) {
-                int cs = c0 + cc;
-                if (a.mode == MODE_INV_REGULAR) {
-                    // out[:, f*G+g] = in[:, f*G + src_g(g)]   (roll_by_gather, images/utils.py:8-29,66-77)
-                    const int f = cs / a.G, g = cs - f * a.G, sh = a.roll[r];
-                    int sg;
-                    if (g < a.N) sg = (g - sh + a.N) % a.N;
-                    else sg = a.N + (g - a.N + sh) % a.N;
-                    cs = f * a.G + sg;
+        if (c0) {
+            __syncthreads();  // every thread is done reading the planes of the previous pass
+            if (threadIdx.x == 0) {
+                mbar_expect_tx(bar, (uint32_t)nc * (exact ? TILE_BYTES : BOX_BYTES));
+                for (int cc = 0; cc < nc; ++cc) {
+                    const int cs = a.mode == MODE_INV_REGULAR ? regular_src_channel(a, c0 + cc, geo.r) : c0 + cc;
+                    tma_load_3d(base + cc * PLANE_BYTES, exact ? &map_tile : &map_box, bar, geo.box_x, geo.box_y,
+                                geo.plane0 + cs);
                 }
-                tma_load_3d(base + cc * PLANE_BYTES, exact ? &map_tile : &map_box, bar, box_x, box_y, plane0 + cs);
             }
         }
         mbar_wait(bar, parity);
         parity ^= 1u;
         if (xd >= a.Wd) continue;  // (no barrier below this point inside the pass)
-        float *dp = dst_n + (size_t)c0 * plane_d + xd;
+        float *dp = dst_px + (size_t)c0 * plane_d;
         if (exact) {
+            const int sxl = geo.sx0 + geo.i00 * lane + geo.i01 * warp, syl = geo.sy0 + geo.i10 * lane + geo.i11 * warp;
+            const int dsx = geo.i01 * (THREADS / 32), dsy = geo.i11 * (THREADS / 32);
 #pragma unroll
             for (int p = 0; p < PIX; ++p) {
-                const int row = warp + p * (THREADS / 32);
-                if (ty0 + row >= a.Hd) break;
-                const int sx = (sx0 + i00 * lane + i01 * row) & (TILE - 1), sy = (sy0 + i10 * lane + i11 * row) & (TILE - 1);
-                // SWIZZLE_128B: 16-byte chunk index XOR (row & 7); rows are 128 bytes, planes 1024-byte aligned
-                const int o = sy * TILE + ((((sx >> 2) ^ (sy & 7)) << 2) | (sx & 3));
-                float *dpp = dp + (size_t)(ty0 + row) * a.Wd;
+                if (p * (THREADS / 32) < rows_left) {
+                    const int sx = (sxl + p * dsx) & (TILE - 1), sy = (syl + p * dsy) & (TILE - 1);
+                    // SWIZZLE_128B: 16-byte chunk index XOR (row & 7); rows are 128 bytes, planes 1024-byte aligned
+                    const uint32_t o = sm0 + 4u * (uint32_t)(sy * TILE + ((((sx >> 2) ^ (sy & 7)) << 2) | (sx & 3)));
 #pragma unroll
-                for (int cc = 0; cc < CG; ++cc)
-                    if (cc < nc) st_stream(dpp + (size_t)cc * plane_d, planes[cc * (PLANE_BYTES / 4) + o]);
+                    for (int cc = 0; cc < CG; ++cc)
+                        if (cc < nc) st_stream(dp + p * row_step + cc * plane_d, lds_f32(o + cc * PLANE_BYTES));
+                }
             }
         } else {
-            // taps of one pixel at a time (offsets / weights shared by the CG channels): 8 live registers per
-            // pixel instead of 32 keeps 6+ CTAs resident per SM, which is what hides the TMA latency
-#pragma unroll 1
-            for (int p = 0; p < PIX; ++p) {
-                const int row = warp + p * (THREADS / 32);
-                if (ty0 + row >= a.Hd) break;
-                const float fr = (float)row;
-                const float xr = fmaf(f00, fl, fmaf(f01, fr, bx)), yr = fmaf(f10, fl, fmaf(f11, fr, by));
+            // taps of one pixel at a time (offsets / weights shared by the CG channels); the 4 pixels of a thread
+            // are 8 rows apart, so their source coordinates advance by 8 * (f01, f11)
+            float xr = fmaf(geo.f00, (float)lane, fmaf(geo.f01, (float)warp, geo.bx));
+            float yr = fmaf(geo.f10, (float)lane, fmaf(geo.f11, (float)warp, geo.by));
+            const float dxr = geo.f01 * (float)(THREADS / 32), dyr = geo.f11 * (float)(THREADS / 32);
+            const bool interior = geo.interior != 0;
+            const int cx_lo = geo.cx_lo, cx_hi = geo.cx_hi, bhm1 = geo.bhm1;
+#pragma unroll
+            for (int p = 0; p < PIX; ++p, xr += dxr, yr += dyr) {
+                if (p * (THREADS / 32) >= rows_left) break;
                 const float xf = floorf(xr), yf = floorf(yr);
                 const float fx = xr - xf, fy = yr - yf;
                 const int x0 = (int)xf, y0 = (int)yf;
-                const int cx0 = min(max(x0, cx_lo), cx_hi), cx1 = min(max(x0 + 1, cx_lo), cx_hi);
-                const int cy0 = min(max(y0, 0), bhm1) * BOXW, cy1 = min(max(y0 + 1, 0), bhm1) * BOXW;
                 float wx0 = 1.f - fx, wx1 = fx, wy0 = 1.f - fy, wy1 = fy;
                 if (ZERO) {
                     // absolute tap coordinates against the padded extent [-pad, size-1+pad]
-                    const int ax0 = x0 + box_x, ay0 = y0 + y_lo;
+                    const int ax0 = x0 + geo.box_x, ay0 = y0 + geo.y_lo;
                     const int lo = -a.pad, hx = a.Ws - 1 + a.pad, hy = a.Hs - 1 + a.pad;
                     if (ax0 < lo || ax0 > hx) wx0 = 0.f;
                     if (ax0 + 1 < lo || ax0 + 1 > hx) wx1 = 0.f;
@@ -217,18 +250,35 @@ __global__ void __launch_bounds__(THREADS, 6) resample_tma_kernel(const __grid_c
                     if (ay0 + 1 < lo || ay0 + 1 > hy) wy1 = 0.f;
                 }
                 const float w00 = wy0 * wx0, w01 = wy0 * wx1, w10 = wy1 * wx0, w11 = wy1 * wx1;
-                const int o00 = cy0 + cx0, o01 = cy0 + cx1, o10 = cy1 + cx0, o11 = cy1 + cx1;
-                float *dpp = dp + (size_t)(ty0 + row) * a.Wd;
+                float *dpp = dp + p * row_step;
+                if (interior) {
+                    const uint32_t o = sm0 + 4u * (uint32_t)(y0 * BOXW + x0);
 #pragma unroll
-                for (int cc = 0; cc < CG; ++cc) {
-                    if (cc < nc) {
-                        const float *sm = planes + cc * (PLANE_BYTES / 4);
-                        // same tap order as ATen grid_sample: nw, ne, sw, se
-                        float v = sm[o00] * w00;
-                        v = fmaf(sm[o01], w01, v);
-                        v = fmaf(sm[o10], w10, v);
-                        v = fmaf(sm[o11], w11, v);
-                        st_stream(dpp + (size_t)cc * plane_d, v);
+                    for (int cc = 0; cc < CG; ++cc) {
+                        if (cc < nc) {
+                            const uint32_t oc = o + cc * PLANE_BYTES;
+                            // same tap order as ATen grid_sample: nw, ne, sw, se
+                            float v = lds_f32(oc) * w00;
+                            v = fmaf(lds_f32(oc + 4), w01, v);
+                            v = fmaf(lds_f32(oc + 4 * BOXW), w10, v);
+                            v = fmaf(lds_f32(oc + 4 * BOXW + 4), w11, v);
+                            st_stream(dpp + cc * plane_d, v);
+                        }
+                    }
+                } else {
+                    const int cx0 = min(max(x0, cx_lo), cx_hi) * 4, cx1 = min(max(x0 + 1, cx_lo), cx_hi) * 4;
+                    const uint32_t cy0 = sm0 + (uint32_t)(min(max(y0, 0), bhm1) * (4 * BOXW));
+                    const uint32_t cy1 = sm0 + (uint32_t)(min(max(y0 + 1, 0), bhm1) * (4 * BOXW));
+                    const uint32_t o00 = cy0 + cx0, o01 = cy0 + cx1, o10 = cy1 + cx0, o11 = cy1 + cx1;
+#pragma unroll
+                    for (int cc = 0; cc < CG; ++cc) {
+                        if (cc < nc) {
+                            float v = lds_f32(o00 + cc * PLANE_BYTES) * w00;
+                            v = fmaf(lds_f32(o01 + cc * PLANE_BYTES), w01, v);
+                            v = fmaf(lds_f32(o10 + cc * PLANE_BYTES), w10, v);
+                            v = fmaf(lds_f32(o11 + cc * PLANE_BYTES), w11, v);
+                            st_stream(dpp + cc * plane_d, v);
+                        }
                     }
                 }
             }
@@ -277,16 +327,21 @@ static int make_plane_map(CUtensorMap *m, const float *src, int W, int H, long l
 }
 
 template <int CG, bool ZERO>
-static int launch_cfg(const CUtensorMap &mb, const CUtensorMap &mt, const ResampleArgs &a, unsigned blocks,
+static int launch_cfg(const CUtensorMap &mb, const CUtensorMap &mt, ResampleArgs a, int n_dst_samples,
                       cudaStream_t st) {
-    const size_t smem = (size_t)CG * PLANE_BYTES + 1024 + 16;
+    const size_t smem = (size_t)CG * PLANE_BYTES + 1024 + 16 + sizeof(TileGeom);
     static bool configured = false;
     if (!configured) {
         EQB_CUDA(cudaFuncSetAttribute(resample_tma_kernel<CG, ZERO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)smem));
         configured = true;
     }
-    resample_tma_kernel<CG, ZERO><<<blocks, THREADS, smem, st>>>(mb, mt, a);
+    // grid = (tile x, tile y, sample): no integer division in the kernel; gridDim.z <= 65535 -> chunk the batch
+    for (int z0 = 0; z0 < n_dst_samples; z0 += 32768) {
+        a.sample0 = z0;
+        const dim3 grid(a.tiles_x, a.tiles_y, std::min(32768, n_dst_samples - z0));
+        resample_tma_kernel<CG, ZERO><<<grid, THREADS, smem, st>>>(mb, mt, a);
+    }
     return 0;
 }
 
@@ -294,14 +349,13 @@ int launch_resample_tma(const ResampleArgs &a, int n_dst_samples, cudaStream_t s
     *handled = 0;
     const long long planes = (long long)a.B * a.C;
     if (((uintptr_t)a.src & 15) != 0 || (a.Ws & 3) != 0 || a.Ws < BOXW || a.Hs < BOXH || planes <= 0 ||
-        planes >= (1LL << 31))
+        planes >= (1LL << 31) || (long long)a.C * a.Hd * a.Wd >= (1LL << 31) || a.tiles_y > 65535)
         return 0;
     const long long blocks = (long long)a.tiles_x * a.tiles_y * n_dst_samples;
     if (blocks == 0) {
         *handled = 1;
         return 0;
     }
-    EQB_REQUIRE(blocks < (1LL << 31), "%s: grid too large (%lld tiles)", what, blocks);
     CUtensorMap mb, mt;
     int e = make_plane_map(&mb, a.src, a.Ws, a.Hs, planes, BOXW, BOXH, CU_TENSOR_MAP_SWIZZLE_NONE);
     if (e) return e;
@@ -312,7 +366,7 @@ int launch_resample_tma(const ResampleArgs &a, int n_dst_samples, cudaStream_t s
     const double rad = sqrt(ux * ux + uy * uy) + 1.0;
     const bool zero = rad > 0.5 * (a.Ws - 1) + a.pad || rad > 0.5 * (a.Hs - 1) + a.pad;
     const int cg = (a.C % 3 == 0 && a.C % 4 != 0) ? 3 : (a.C >= 4 ? 4 : a.C);
-    const unsigned nb = (unsigned)blocks;
+    const int nb = n_dst_samples;
     switch (cg * 2 + (zero ? 1 : 0)) {
         case 2: e = launch_cfg<1, false>(mb, mt, a, nb, st); break;
         case 3: e = launch_cfg<1, true>(mb, mt, a, nb, st); break;
