@@ -15,6 +15,7 @@
 // This file is the fp32 SIMT implementation (8x8 register tiles, weights streamed K-major through a
 // cp.async double buffer).  It handles any Cout*|G| <= 256.
 #include "common.cuh"
+#include "gconv_stack_tc.cuh"
 
 namespace eqb {
 
@@ -242,8 +243,11 @@ __global__ void __launch_bounds__(256) gconv_finish_kernel(const double *__restr
 
 struct StackPlan {
     int G, N, Npad, K0, K0pad, Ho, Wo, P, rows, n_gemm, tiles, chunks, tiles_per_chunk;
-    size_t off_wt[GT_MAX_GEMM], off_bias[GT_MAX_GEMM], off_M, off_S, total;
+    size_t off_wt[GT_MAX_GEMM], off_bias[GT_MAX_GEMM], off_M, off_tc, off_S, total;
     size_t smem;
+    // tcgen05 path (gconv_stack_tc.cu): 128-pixel tiles, its own chunking
+    bool tc;
+    int tc_tiles, tc_chunks, tc_tiles_per_chunk;
 };
 
 static int make_plan(int B, int cin, int H, int W, int cout, int k, int N, int reflect, int L, StackPlan &p) {
@@ -285,8 +289,22 @@ static int make_plan(int B, int cin, int H, int W, int cout, int k, int N, int r
     }
     p.off_M = off;
     off += (size_t)p.Npad * p.G * sizeof(double);
+    p.tc = tc_eligible(p.N, p.K0, p.n_gemm);
+    p.off_tc = off;
+    int max_chunks = p.chunks;
+    if (p.tc) {
+        off = (off + 1023) & ~(size_t)1023;
+        p.off_tc = off;
+        off += tc_pack_bytes(p.N, p.K0);
+        p.tc_tiles = (p.P + 127) / 128;
+        // work items of <= 8 tiles; finer when the batch alone cannot occupy every SM four times over
+        long long tpc = ((long long)(B > 0 ? B : 1) * p.tc_tiles + 4LL * num_sms() - 1) / (4LL * num_sms());
+        p.tc_tiles_per_chunk = (int)(tpc < 1 ? 1 : tpc > 8 ? 8 : tpc);
+        p.tc_chunks = (p.tc_tiles + p.tc_tiles_per_chunk - 1) / p.tc_tiles_per_chunk;
+        if (p.tc_chunks > max_chunks) max_chunks = p.tc_chunks;
+    }
     p.off_S = off;
-    off += (size_t)(B > 0 ? B : 1) * p.chunks * p.Npad * sizeof(double);
+    off += (size_t)(B > 0 ? B : 1) * max_chunks * p.Npad * sizeof(double);
     p.total = off;
     return 0;
 }
@@ -356,7 +374,12 @@ extern "C" int eqb_gconv_stack_pack(const float *lift_w, const float *lift_b, co
     EQB_REQUIRE(L == 1 || w_last, "eqb_gconv_stack_pack: null weight for the last layer");
     build_fold_matrix_kernel<<<(p.Npad * p.G + 255) / 256, 256, 0, st>>>(w_last, (double *)(ws + p.off_M), cout,
                                                                          num_rotations, p.G, p.Npad, L > 1);
-    return finish_launch("eqb_gconv_stack_pack");
+    e = finish_launch("eqb_gconv_stack_pack");
+    if (e) return e;
+    if (p.tc)  // the same operands as UMMA hi / lo images for the tcgen05 kernel
+        return tc_pack((const float *)(ws + p.off_wt[0]), p.K0, (const float *)(ws + p.off_wt[1]), p.Npad, p.N,
+                       (unsigned char *)(ws + p.off_tc), st);
+    return 0;
 }
 
 extern "C" int eqb_gconv_stack_run(const float *x, int B, int cin, int H, int W, const void *packed,
@@ -386,20 +409,34 @@ extern "C" int eqb_gconv_stack_run(const float *x, int B, int cin, int H, int W,
     }
     a.S_part = (double *)scratch;
     a.tiles = p.tiles; a.chunks = p.chunks; a.tiles_per_chunk = p.tiles_per_chunk;
-    int e;
-    switch (p.Npad / 32) {
-        case 1: e = launch_stack<1>(a, p.smem, st); break;
-        case 2: e = launch_stack<2>(a, p.smem, st); break;
-        case 4: e = launch_stack<4>(a, p.smem, st); break;
-        default: e = launch_stack<8>(a, p.smem, st); break;
+    int e, chunks = p.chunks;
+    if (p.tc) {
+        TcArgs t{};
+        t.x = x; t.B = B; t.cin = cin; t.H = H; t.W = W; t.ksz = k; t.Wo = p.Wo; t.P = p.P;
+        t.K0 = p.K0; t.N = p.N; t.Npad = p.Npad;
+        t.bias1 = a.bias[0]; t.bias2 = a.bias[1];
+        t.wpack = (const unsigned char *)(ws + p.off_tc);
+        t.S_part = a.S_part;
+        t.tiles = p.tc_tiles; t.chunks = p.tc_chunks; t.tiles_per_chunk = p.tc_tiles_per_chunk;
+        chunks = p.tc_chunks;
+        e = tc_launch(t, st);
+    } else {
+        switch (p.Npad / 32) {
+            case 1: e = launch_stack<1>(a, p.smem, st); break;
+            case 2: e = launch_stack<2>(a, p.smem, st); break;
+            case 4: e = launch_stack<4>(a, p.smem, st); break;
+            default: e = launch_stack<8>(a, p.smem, st); break;
+        }
     }
     if (e) return e;
     const double inv_count = 1.0 / ((double)cout * (double)p.P);
     gconv_finish_kernel<<<B, 256, p.Npad * sizeof(double), st>>>(a.S_part, (const double *)(ws + p.off_M),
-                                                                L > 1 ? last_bias : nullptr, cout, p.chunks, p.Npad, p.G,
+                                                                L > 1 ? last_bias : nullptr, cout, chunks, p.Npad, p.G,
                                                                 inv_count, act);
     return finish_launch("gconv_finish_kernel");
 }
+
+extern "C" int eqb_debug_last_stall(int *out5) { return tc_last_stall(out5); }
 
 extern "C" int eqb_gconv_stack_forward(const float *x, int B, int cin, int H, int W, const float *lift_w,
                                        const float *lift_b, const float *const *reg_w, const float *const *reg_b,

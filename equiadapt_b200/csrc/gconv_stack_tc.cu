@@ -1,0 +1,570 @@
+// tcgen05 implementation of the fused group-conv stack (a4..a6) for the 3-layer CustomEquivariantNetwork:
+//   lift conv k x k  ->  ReLU  ->  1x1 regular group conv  ->  ReLU  ->  spatial sum   (last layer folded, see
+//   gconv_stack.cu).  Reference: custom_equivariant_networks.py:80-93, custom_group_equivariant_layers.py:92-111,
+//   :336-361.
+//
+// Both contractions are dense ( [128 pixels x K] x [K x N], K = Cin*k*k and K = N = Cout*|G| <= 256 ), so they
+// run on the 5th-generation tensor cores: tcgen05.mma kind::tf32, M = 128, N = Cout*|G|, accumulators in TMEM.
+// Group activations are means of ~270 000 values whose top-2 gap is ~1e-6 (hard part 1):
+// single-pass TF32 is not accurate enough, so every product is evaluated with the 3xTF32 split
+//     a*w ~= a_hi*w_hi + a_lo*w_hi + a_hi*w_lo,   x_hi = rna_tf32(x), x_lo = x - x_hi  (exact in fp32),
+// i.e. three MMAs per K-step; the dropped a_lo*w_lo term is 2^-24 relative.
+//
+// One persistent CTA per SM, 16 warps, warp-specialised, everything between the resized image and the per-image
+// channel sums stays on chip:
+//   warp 0      weight producer: streams the pre-packed filter-orbit operands (hi / lo images, already in the UMMA
+//               swizzled K-major layout: 16-wide K slabs / 64-byte swizzle for the lift layer, 32-wide K atoms /
+//               128-byte swizzle for the 1x1 layer) from L2 with cp.async.bulk into a 3-stage ring of N x 128 bytes
+//   warp 1      MMA issuer (one elected lane): lift GEMM into TMEM accumulator D1, 1x1 GEMM into D2
+//   warp 2      TMEM allocator
+//   warps 4-7   epilogue 1: D1 -> +bias, ReLU -> hi/lo split -> next layer's A operand, written in 32-column chunks
+//               straight into the A ring (the 256-wide activation never exists in full anywhere)
+//   warps 8-11  epilogue 2: D2 -> +bias, ReLU -> masked column sums (warp-shuffle transpose-reduce), fp64 accumulation
+//   warps 12-15 im2col producers: gather the 128 x K patch matrix of the next tile from the image (L1/L2 hits),
+//               split, and write it into the A ring
+// Pipelines: W ring (3 x N*128 B; full = TMA tx-count, empty = tcgen05.commit), A0 ring (3 x 16 KB, im2col -> MMA),
+// A1 ring (2 x 32 KB, epilogue 1 -> MMA; full = 128 producer arrivals, empty = tcgen05.commit), D1 / D2 full (commit)
+// and empty (128 epilogue arrivals).  Every ring has exactly one producer role and one consumer role, so the usual
+// (stage, phase-parity) bookkeeping is sufficient.
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "gconv_stack_tc.cuh"
+
+namespace eqb {
+
+namespace tc {
+
+constexpr int THREADS = 512;
+constexpr int TILE_M = 128;                 // pixels per tile = TMEM lanes
+constexpr int ATOM_K = 32;                  // 1x1 layer: fp32 elements per 128-byte swizzle row
+constexpr int SLAB_K = 16;                  // lift layer: fp32 elements per 64-byte swizzle row
+constexpr int A1_HALF = TILE_M * 128;       // bytes of one A1 image (hi or lo) of one K atom: 16 KB
+constexpr int A1_STAGE = 2 * A1_HALF;       // hi + lo
+constexpr int A0_HALF = TILE_M * 64;        // bytes of one A0 image (hi or lo) of one K slab: 8 KB
+constexpr int A0_STAGE = 2 * A0_HALF;
+constexpr int W_RING = 3, A0_RING = 3, A1_RING = 2;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ---- mbarrier ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a pipeline bug must fail fast and say where, never hang the GPU.  After ~2 s without progress the
+// waiter records (block, warp, barrier id, parity) in a host-mapped buffer (eqb_debug_last_stall) and traps.
+__device__ int *g_stall_report = nullptr;
+__device__ __noinline__ void mbar_stall(int id, uint32_t parity) {
+    int *r = g_stall_report;
+    if (r && atomicCAS(r, 0, 1) == 0) {
+        r[1] = (int)blockIdx.x; r[2] = (int)(threadIdx.x >> 5); r[3] = id; r[4] = (int)parity;
+        __threadfence_system();
+    }
+    __trap();
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int id = -1) {
+    if (mbar_try(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try(bar, parity))
+        if (clock64() - t0 > 4000000000LL) mbar_stall(id, parity);
+}
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ---- tcgen05 ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// 32 consecutive accumulator columns of this thread's TMEM lane
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, float *v) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address >> 4 in bits
+// [0,14), leading byte offset (unused for swizzled K-major) in [16,30), stride byte offset = 1024 (8 rows of 128 B)
+// in [32,46), version 1 in [46,48), layout type 2 = SWIZZLE_128B in [61,64).  Atom bases are 1024-byte aligned;
+// K-steps inside the atom advance the start address by 32 bytes (8 tf32).
+// SWIZZLE_64B (lift layer): rows of 64 B, stride byte offset 512, layout type 4, 16-byte chunk index XOR ((row>>1)&3).
+// Both forms verified bit-exact on B200 with tools/umma_probe.cu.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+           ((uint64_t)2 << 61);
+}
+__device__ __forceinline__ uint64_t umma_desc64(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(512 >> 4) << 32) | ((uint64_t)1 << 46) |
+           ((uint64_t)4 << 61);
+}
+
+__device__ __forceinline__ float tf32_rna(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, float a, float b, float c, float d) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+template <int DEPTH>
+struct Ring {
+    int stage = 0;
+    uint32_t phase = 0;
+    __device__ __forceinline__ void advance() {
+        if (++stage == DEPTH) {
+            stage = 0;
+            phase ^= 1u;
+        }
+    }
+};
+
+// shared-memory map (offsets from the 1024-aligned base)
+struct Smem {
+    uint32_t a0_ring, a1_ring, w_ring, koff, bias1, bias2, part, bars, tmem_slot, total;
+};
+__host__ __device__ inline Smem smem_map(int N, int K0pad) {
+    Smem s;
+    uint32_t o = 0;
+    s.a1_ring = o; o += A1_RING * A1_STAGE;               // 64 KB
+    s.a0_ring = o; o += A0_RING * A0_STAGE;               // 48 KB
+    s.w_ring = o; o += W_RING * (uint32_t)N * 128;        // <= 96 KB
+    s.koff = o; o += (uint32_t)K0pad * 4;
+    s.bias1 = o; o += (uint32_t)N * 4;
+    s.bias2 = o; o += (uint32_t)N * 4;
+    o = (o + 15u) & ~15u;
+    s.part = o; o += 4u * (uint32_t)N * 8;                // 4 warps x N doubles
+    s.bars = o; o += 24 * 8;
+    s.tmem_slot = o; o += 16;
+    s.total = o;
+    return s;
+}
+enum { B_WFULL = 0, B_WEMPTY = 3, B_A0FULL = 6, B_A0EMPTY = 9, B_A1FULL = 12, B_A1EMPTY = 14, B_D1FULL = 16, B_D1EMPTY = 17,
+       B_D2FULL = 18, B_D2EMPTY = 19 };
+
+__global__ void __launch_bounds__(THREADS, 1) gconv_stack_tc_kernel(const TcArgs a) {
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    unsigned char *sm = smem_raw + (base - smem_u32(smem_raw));
+    const int N = a.N;
+    const Smem M = smem_map(N, a.K0pad);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t bars = base + M.bars;
+    auto bar = [&](int i) { return bars + 8u * (uint32_t)i; };
+    const int NS0 = a.K0pad / SLAB_K;        // 16-wide K slabs of the lift GEMM
+    const int NC1 = N / ATOM_K;              // 32-wide K atoms of the 1x1 GEMM (= 32-column chunks of D1)
+    const uint32_t w_stage_bytes = (uint32_t)N * 128u;
+
+    // ---- one-time setup -------------------------------------------------------------------------------------
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < W_RING; ++i) {
+            mbar_init(bar(B_WFULL + i), 1);
+            mbar_init(bar(B_WEMPTY + i), 1);
+        }
+        for (int i = 0; i < A0_RING; ++i) {
+            mbar_init(bar(B_A0FULL + i), 128);
+            mbar_init(bar(B_A0EMPTY + i), 1);
+        }
+        for (int i = 0; i < A1_RING; ++i) {
+            mbar_init(bar(B_A1FULL + i), 128);
+            mbar_init(bar(B_A1EMPTY + i), 1);
+        }
+        mbar_init(bar(B_D1FULL), 1);
+        mbar_init(bar(B_D1EMPTY), 128);
+        mbar_init(bar(B_D2FULL), 1);
+        mbar_init(bar(B_D2EMPTY), 128);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    {
+        int *koff = reinterpret_cast<int *>(sm + M.koff);
+        float *b1 = reinterpret_cast<float *>(sm + M.bias1), *b2 = reinterpret_cast<float *>(sm + M.bias2);
+        const int kk2 = a.ksz * a.ksz;
+        for (int k = threadIdx.x; k < a.K0pad; k += THREADS) {
+            int off = -1;  // padding column
+            if (k < a.K0) {
+                const int c = k / kk2, rem = k - c * kk2, ky = rem / a.ksz, kx = rem - ky * a.ksz;
+                off = (c * a.H + ky) * a.W + kx;
+            }
+            koff[k] = off;
+        }
+        for (int n = threadIdx.x; n < N; n += THREADS) {
+            b1[n] = a.bias1[n];
+            b2[n] = a.bias2[n];
+        }
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(base + M.tmem_slot), "r"(512)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *reinterpret_cast<volatile uint32_t *>(sm + M.tmem_slot);
+    const uint32_t tmem_d1 = tmem, tmem_d2 = tmem + 256;
+
+    // work items: (image, chunk of tiles); static round-robin over the persistent CTAs
+    const int items = a.B * a.chunks;
+
+    if (warp == 0) {
+        // ===== weight producer ===================================================================================
+        if (lane == 0) {
+            Ring<W_RING> w;
+            const int stages_per_tile = NS0 + 2 * NC1;
+            for (int it = blockIdx.x; it < items; it += gridDim.x) {
+                const int ch = it % a.chunks;
+                const int t0 = ch * a.tiles_per_chunk, t1 = min(a.tiles, t0 + a.tiles_per_chunk);
+                for (int t = t0; t < t1; ++t) {
+                    for (int s = 0; s < stages_per_tile; ++s) {
+                        mbar_wait(bar(B_WEMPTY + w.stage), w.phase ^ 1u, B_WEMPTY + w.stage);
+                        mbar_expect_tx(bar(B_WFULL + w.stage), w_stage_bytes);
+                        bulk_load(base + M.w_ring + w.stage * w_stage_bytes, a.wpack + (size_t)s * w_stage_bytes,
+                                  w_stage_bytes, bar(B_WFULL + w.stage));
+                        w.advance();
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer ========================================================================================
+        if (lane == 0) {
+            Ring<W_RING> w;
+            Ring<A0_RING> r0;
+            Ring<A1_RING> r1;
+            uint32_t tile_phase = 0;
+            // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32 [4,6) = 1, A = B = TF32 [7,10), [10,13) = 2,
+            // both K-major, N >> 3 in [17,23), M >> 4 in [24,29)
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+            for (int it = blockIdx.x; it < items; it += gridDim.x) {
+                const int ch = it % a.chunks;
+                const int t0 = ch * a.tiles_per_chunk, t1 = min(a.tiles, t0 + a.tiles_per_chunk);
+                for (int t = t0; t < t1; ++t) {
+                    // ---- lift GEMM: D1 = A0 . W0^T, K slabs of 16 (hi and lo weights share one W stage) ----------
+                    mbar_wait(bar(B_D1EMPTY), tile_phase ^ 1u, B_D1EMPTY);  // epilogue 1 has drained D1 of the previous tile
+                    tc_fence_after();
+                    for (int sl = 0; sl < NS0; ++sl) {
+                        const int ksteps = min(2, (a.K0 - sl * SLAB_K + 7) / 8);
+                        mbar_wait(bar(B_A0FULL + r0.stage), r0.phase, B_A0FULL + r0.stage);
+                        mbar_wait(bar(B_WFULL + w.stage), w.phase, B_WFULL + w.stage);
+                        tc_fence_after();
+                        const uint32_t a_hi = base + M.a0_ring + r0.stage * A0_STAGE, a_lo = a_hi + A0_HALF;
+                        const uint32_t w_hi = base + M.w_ring + w.stage * w_stage_bytes, w_lo = w_hi + (uint32_t)N * 64u;
+                        for (int j = 0; j < ksteps; ++j)
+                            tc_mma_tf32(tmem_d1, umma_desc64(a_hi + 32 * j), umma_desc64(w_hi + 32 * j), idesc, (sl | j) != 0);
+                        for (int j = 0; j < ksteps; ++j)
+                            tc_mma_tf32(tmem_d1, umma_desc64(a_lo + 32 * j), umma_desc64(w_hi + 32 * j), idesc, 1);
+                        for (int j = 0; j < ksteps; ++j)
+                            tc_mma_tf32(tmem_d1, umma_desc64(a_hi + 32 * j), umma_desc64(w_lo + 32 * j), idesc, 1);
+                        tc_commit(bar(B_WEMPTY + w.stage));
+                        tc_commit(bar(B_A0EMPTY + r0.stage));
+                        w.advance();
+                        r0.advance();
+                    }
+                    tc_commit(bar(B_D1FULL));
+                    // ---- 1x1 GEMM: D2 = A1 . W1^T, K atoms of 32 (hi stage, then lo stage) -----------------------
+                    mbar_wait(bar(B_D2EMPTY), tile_phase ^ 1u, B_D2EMPTY);  // epilogue 2 has drained D2 of the previous tile
+                    tc_fence_after();
+                    for (int kc = 0; kc < NC1; ++kc) {
+                        mbar_wait(bar(B_A1FULL + r1.stage), r1.phase, B_A1FULL + r1.stage);
+                        const uint32_t a_hi = base + M.a1_ring + r1.stage * A1_STAGE, a_lo = a_hi + A1_HALF;
+                        mbar_wait(bar(B_WFULL + w.stage), w.phase, B_WFULL + w.stage);
+                        tc_fence_after();
+                        uint32_t wb = base + M.w_ring + w.stage * w_stage_bytes;
+                        for (int j = 0; j < 4; ++j)
+                            tc_mma_tf32(tmem_d2, umma_desc(a_hi + 32 * j), umma_desc(wb + 32 * j), idesc, (kc | j) != 0);
+                        for (int j = 0; j < 4; ++j)
+                            tc_mma_tf32(tmem_d2, umma_desc(a_lo + 32 * j), umma_desc(wb + 32 * j), idesc, 1);
+                        tc_commit(bar(B_WEMPTY + w.stage));
+                        w.advance();
+                        mbar_wait(bar(B_WFULL + w.stage), w.phase, B_WFULL + w.stage);
+                        tc_fence_after();
+                        wb = base + M.w_ring + w.stage * w_stage_bytes;
+                        for (int j = 0; j < 4; ++j)
+                            tc_mma_tf32(tmem_d2, umma_desc(a_hi + 32 * j), umma_desc(wb + 32 * j), idesc, 1);
+                        tc_commit(bar(B_WEMPTY + w.stage));
+                        w.advance();
+                        tc_commit(bar(B_A1EMPTY + r1.stage));
+                        r1.advance();
+                    }
+                    tc_commit(bar(B_D2FULL));
+                    tile_phase ^= 1u;
+                }
+            }
+        }
+    } else if (warp >= 4 && warp < 8) {
+        // ===== epilogue 1: D1 -> relu(. + b1) -> hi/lo -> A ring (K atoms of the 1x1 GEMM) ======================
+        const int q = warp & 3, row = q * 32 + lane;
+        const float *b1 = reinterpret_cast<const float *>(sm + M.bias1);
+        Ring<A1_RING> ar;
+        uint32_t tile_phase = 0;
+        const uint32_t row_off = (uint32_t)row * 128u, sw = (uint32_t)(row & 7);
+        for (int it = blockIdx.x; it < items; it += gridDim.x) {
+            const int ch = it % a.chunks;
+            const int t0 = ch * a.tiles_per_chunk, t1 = min(a.tiles, t0 + a.tiles_per_chunk);
+            for (int t = t0; t < t1; ++t) {
+                mbar_wait(bar(B_D1FULL), tile_phase, B_D1FULL);
+                tc_fence_after();
+                for (int c = 0; c < NC1; ++c) {
+                    float v[32];
+                    tc_ld32(tmem_d1 + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+                    mbar_wait(bar(B_A1EMPTY + ar.stage), ar.phase ^ 1u, B_A1EMPTY + ar.stage);
+                    const uint32_t hi_row = base + M.a1_ring + ar.stage * A1_STAGE + row_off, lo_row = hi_row + A1_HALF;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        float h[4], l[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float x = fmaxf(v[4 * j + i] + b1[c * 32 + 4 * j + i], 0.f);
+                            h[i] = tf32_rna(x);
+                            l[i] = x - h[i];
+                        }
+                        const uint32_t col = ((uint32_t)j ^ sw) << 4;
+                        st_shared_v4(hi_row + col, h[0], h[1], h[2], h[3]);
+                        st_shared_v4(lo_row + col, l[0], l[1], l[2], l[3]);
+                    }
+                    fence_async_smem();
+                    mbar_arrive(bar(B_A1FULL + ar.stage));
+                    ar.advance();
+                }
+                tc_fence_before();
+                mbar_arrive(bar(B_D1EMPTY));
+                tile_phase ^= 1u;
+            }
+        }
+    } else if (warp >= 8 && warp < 12) {
+        // ===== epilogue 2: D2 -> relu(. + b2) -> masked column sums ==========================================
+        const int q = warp & 3, row = q * 32 + lane;
+        const float *b2 = reinterpret_cast<const float *>(sm + M.bias2);
+        double *part = reinterpret_cast<double *>(sm + M.part);
+        uint32_t tile_phase = 0;
+        for (int it = blockIdx.x; it < items; it += gridDim.x) {
+            const int b = it / a.chunks, ch = it % a.chunks;
+            const int t0 = ch * a.tiles_per_chunk, t1 = min(a.tiles, t0 + a.tiles_per_chunk);
+            double dacc[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) dacc[c] = 0.0;
+            for (int t = t0; t < t1; ++t) {
+                const bool valid = t * TILE_M + row < a.P;
+                mbar_wait(bar(B_D2FULL), tile_phase, B_D2FULL);
+                tc_fence_after();
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    if (c < NC1) {
+                        float v[32];
+                        tc_ld32(tmem_d2 + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] = valid ? fmaxf(v[i] + b2[c * 32 + i], 0.f) : 0.f;
+                        // transpose-reduce: afterwards lane i holds the sum over the 32 lanes (pixels) of column i
+#pragma unroll
+                        for (int s = 16; s >= 1; s >>= 1) {
+                            const bool up = (lane & s) != 0;
+#pragma unroll
+                            for (int i = 0; i < s; ++i) {
+                                const float keep = up ? v[i + s] : v[i];
+                                const float send = up ? v[i] : v[i + s];
+                                v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+                            }
+                        }
+                        dacc[c] += (double)v[0];
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive(bar(B_D2EMPTY));
+                tile_phase ^= 1u;
+            }
+            // item done: sum the 4 warps (pixel quarters) and emit this chunk's partial sums
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+                if (c < NC1) part[q * N + c * 32 + lane] = dacc[c];
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            for (int n = threadIdx.x - 256; n < a.Npad; n += 128)
+                a.S_part[((size_t)b * a.chunks + ch) * a.Npad + n] =
+                    n < N ? part[n] + part[N + n] + part[2 * N + n] + part[3 * N + n] : 0.0;
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
+    } else if (warp >= 12) {
+        // ===== im2col producers: A0 = patches of the next tile, hi/lo split, into the A0 ring ==================
+        const int row = (warp - 12) * 32 + lane;
+        const int *koff = reinterpret_cast<const int *>(sm + M.koff);
+        Ring<A0_RING> ar;
+        const uint32_t row_off = (uint32_t)row * 64u, sw = (uint32_t)((row >> 1) & 3);
+        for (int it = blockIdx.x; it < items; it += gridDim.x) {
+            const int b = it / a.chunks, ch = it % a.chunks;
+            const int t0 = ch * a.tiles_per_chunk, t1 = min(a.tiles, t0 + a.tiles_per_chunk);
+            const float *xb = a.x + (size_t)b * a.cin * a.H * a.W;
+            for (int t = t0; t < t1; ++t) {
+                const int p = t * TILE_M + row;
+                const bool valid = p < a.P;
+                const int oy = valid ? p / a.Wo : 0, ox = valid ? p - oy * a.Wo : 0;
+                const float *xp = xb + (size_t)oy * a.W + ox;
+                for (int sl = 0; sl < NS0; ++sl) {
+                    float x[SLAB_K];
+#pragma unroll
+                    for (int i = 0; i < SLAB_K; ++i) {
+                        const int off = koff[sl * SLAB_K + i];
+                        x[i] = (valid && off >= 0) ? __ldg(xp + off) : 0.f;
+                    }
+                    mbar_wait(bar(B_A0EMPTY + ar.stage), ar.phase ^ 1u, B_A0EMPTY + ar.stage);
+                    const uint32_t hi_row = base + M.a0_ring + ar.stage * A0_STAGE + row_off, lo_row = hi_row + A0_HALF;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        float h[4], l[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            h[i] = tf32_rna(x[4 * j + i]);
+                            l[i] = x[4 * j + i] - h[i];
+                        }
+                        const uint32_t col = ((uint32_t)j ^ sw) << 4;
+                        st_shared_v4(hi_row + col, h[0], h[1], h[2], h[3]);
+                        st_shared_v4(lo_row + col, l[0], l[1], l[2], l[3]);
+                    }
+                    fence_async_smem();
+                    mbar_arrive(bar(B_A0FULL + ar.stage));
+                    ar.advance();
+                }
+            }
+        }
+    }
+
+    // ---- teardown -------------------------------------------------------------------------------------------
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+    }
+}
+
+// Pre-pack one layer's K-major operand Wt[Kpad_src][Npad] (k rows, n columns; built by the filter-orbit kernels)
+// into UMMA images: for every 32-wide K atom an N x 128-byte hi image followed by the lo image, 128-byte swizzle
+// (16-byte chunk index XOR (n & 7)).
+__global__ void pack_tc_weights_kernel(const float *__restrict__ Wt, int K, int Npad, int N, int atoms,
+                                       unsigned char *__restrict__ out) {
+    const int total = atoms * N * ATOM_K;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+        const int ks = t % ATOM_K, n = (t / ATOM_K) % N, atom = t / (ATOM_K * N);
+        const int k = atom * ATOM_K + ks;
+        const float w = k < K ? Wt[(size_t)k * Npad + n] : 0.f;
+        const float hi = tf32_rna(w), lo = w - hi;
+        const size_t stage = (size_t)N * 128;
+        const size_t off = (size_t)n * 128 + (size_t)((((ks >> 2) ^ (n & 7)) << 4) | ((ks & 3) << 2));
+        *reinterpret_cast<float *>(out + (size_t)(2 * atom) * stage + off) = hi;
+        *reinterpret_cast<float *>(out + (size_t)(2 * atom + 1) * stage + off) = lo;
+    }
+}
+
+// Lift layer: 16-wide K slabs, one stage per slab = N x 64-byte hi image followed by the lo image, 64-byte swizzle
+// (16-byte chunk index XOR ((n >> 1) & 3)).
+__global__ void pack_tc_lift_kernel(const float *__restrict__ Wt, int K, int Npad, int N, int slabs,
+                                    unsigned char *__restrict__ out) {
+    const int total = slabs * N * SLAB_K;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+        const int ks = t % SLAB_K, n = (t / SLAB_K) % N, slab = t / (SLAB_K * N);
+        const int k = slab * SLAB_K + ks;
+        const float w = k < K ? Wt[(size_t)k * Npad + n] : 0.f;
+        const float hi = tf32_rna(w), lo = w - hi;
+        const size_t stage = (size_t)N * 128, half = (size_t)N * 64;
+        const size_t off = (size_t)n * 64 + (size_t)((((ks >> 2) ^ ((n >> 1) & 3)) << 4) | ((ks & 3) << 2));
+        *reinterpret_cast<float *>(out + (size_t)slab * stage + off) = hi;
+        *reinterpret_cast<float *>(out + (size_t)slab * stage + half + off) = lo;
+    }
+}
+
+}  // namespace tc
+
+bool tc_eligible(int N, int K0, int n_gemm) {
+    if (getenv("EQB_NO_TC")) return false;
+    return n_gemm == 2 && N % 32 == 0 && N >= 32 && N <= 256 && K0 >= 1 && K0 <= 1024;
+}
+
+size_t tc_pack_bytes(int N, int K0) {
+    const int ns0 = (K0 + tc::SLAB_K - 1) / tc::SLAB_K, nc1 = N / tc::ATOM_K;
+    return (size_t)(ns0 + 2 * nc1) * N * 128;
+}
+
+int tc_pack(const float *Wt0, int K0, const float *Wt1, int Npad, int N, unsigned char *out, cudaStream_t st) {
+    const int ns0 = (K0 + tc::SLAB_K - 1) / tc::SLAB_K, nc1 = N / tc::ATOM_K;
+    tc::pack_tc_lift_kernel<<<64, 256, 0, st>>>(Wt0, K0, Npad, N, ns0, out);
+    tc::pack_tc_weights_kernel<<<64, 256, 0, st>>>(Wt1, N, Npad, N, nc1, out + (size_t)ns0 * N * 128);
+    return finish_launch("pack_tc_weights");
+}
+
+static int *g_stall_host = nullptr;
+
+int tc_last_stall(int *out5) {
+    if (!g_stall_host) return 0;
+    for (int i = 0; i < 5; ++i) out5[i] = g_stall_host[i];
+    return g_stall_host[0];
+}
+
+int tc_launch(TcArgs a, cudaStream_t st) {
+    if (!g_stall_host) {
+        int *dptr = nullptr;
+        EQB_CUDA(cudaHostAlloc((void **)&g_stall_host, 8 * sizeof(int), cudaHostAllocMapped));
+        for (int i = 0; i < 8; ++i) g_stall_host[i] = 0;
+        EQB_CUDA(cudaHostGetDevicePointer((void **)&dptr, g_stall_host, 0));
+        EQB_CUDA(cudaMemcpyToSymbol(tc::g_stall_report, &dptr, sizeof(dptr)));
+    }
+    a.K0pad = (a.K0 + tc::SLAB_K - 1) / tc::SLAB_K * tc::SLAB_K;
+    const tc::Smem M = tc::smem_map(a.N, a.K0pad);
+    const size_t smem = (size_t)M.total + 1024;
+    EQB_UNSUPPORTED(smem > 227 * 1024, "gconv_stack (tcgen05): Cin*k*k = %d too large for the shared-memory rings", a.K0);
+    static bool configured = false;
+    if (!configured) {
+        EQB_CUDA(cudaFuncSetAttribute(tc::gconv_stack_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        configured = true;
+    }
+    const int items = a.B * a.chunks;
+    const int grid = items < num_sms() ? items : num_sms();
+    tc::gconv_stack_tc_kernel<<<grid, tc::THREADS, smem, st>>>(a);
+    return finish_launch("gconv_stack_tc_kernel");
+}
+
+}  // namespace eqb

@@ -81,6 +81,10 @@ EQB_API int eqb_gconv_stack_run(const float *x, int B, int cin, int H, int W, co
                                 const float *last_bias, int cout, int k, int num_rotations, int reflect,
                                 int num_layers, float *act, void *scratch, int64_t scratch_bytes, void *stream);
 
+/* Diagnostics: the tcgen05 stack kernel bounds every pipeline wait (~2 s); if one expires the kernel traps instead of
+ * hanging and leaves {flag, block, warp, barrier id, parity} here (host memory).  Returns flag (0 = no stall seen). */
+EQB_API int eqb_debug_last_stall(int *out5);
+
 /* ---- a9 + a13  group pool / select + prior statistic --------------------------------------
  * act (B,|G|) -> idx int32 (B) = first arg-max, rotation (B) in degrees, reflection (B) 0/1 (may be
  * NULL), onehot (B,|G|) (may be NULL), stats[3] = { sum_b CE(act_b, class 0), sum_b [idx_b == 0], B }.

@@ -434,3 +434,74 @@ def test_full_size_round_trip_properties(cuda_device):
     fwd = ops.warp_invert(f, i4, n, False, True)
     inv = ops.warp_invert(fwd, (n - i4) % n, n, False, True)
     assert torch.equal(inv, f)
+
+
+# ---------------------------------------------------------------------------------------------------
+# tcgen05 conv stack (gconv_stack_tc.cu) against the fp32 SIMT kernel (EQB_NO_TC=1) and the fp64 oracle
+# ---------------------------------------------------------------------------------------------------
+def _stack_act(net_cpu, x, dev, no_tc):
+    import copy
+    import os
+    if no_tc:
+        os.environ["EQB_NO_TC"] = "1"
+    try:
+        net = copy.deepcopy(net_cpu).to(dev)   # a fresh module packs its operands under the current setting
+        with torch.no_grad():
+            out = net(x.to(dev)).cpu()
+        torch.cuda.synchronize()
+        return out
+    finally:
+        os.environ.pop("EQB_NO_TC", None)
+
+
+@pytest.mark.parametrize("group_type,n,cout,k,res,b", [
+    ("rotation", 8, 32, 5, 96, 6),          # cfg2 network: N = 256, lift K = 75
+    ("rotation", 4, 16, 5, 32, 9),          # cfg1 network: N = 64
+    ("roto-reflection", 4, 8, 3, 40, 5),    # D4: N = 64, lift K = 27
+    ("rotation", 8, 12, 7, 50, 3),          # N = 96 (Npad 128), lift K = 147 (10 slabs), partial last tile
+    ("roto-reflection", 8, 16, 1, 20, 4),   # D8: N = 256, 1x1 lift (K = 3)
+])
+def test_tcgen05_stack_vs_simt_and_oracle(group_type, n, cout, k, res, b, cuda_device):
+    _, _, _, Net = _mods()
+    reflect = group_type == "roto-reflection"
+    torch.manual_seed(20)
+    net = Net((3, res, res), cout, k, group_type, n, 3, device="cpu")
+    with torch.no_grad():
+        for m in net.eqv_network:
+            if hasattr(m, "bias"):
+                m.bias.uniform_(-0.1, 0.1)
+    lay = [(m.weights.detach().clone(), m.bias.detach().clone()) for m in net.eqv_network if hasattr(m, "weights")]
+    x = torch.rand(b, 3, res, res, generator=torch.Generator().manual_seed(21))
+    act_tc = _stack_act(net, x, cuda_device, no_tc=False)
+    act_simt = _stack_act(net, x, cuda_device, no_tc=True)
+    act64 = O.custom_equivariant_network(x.double(), [(w.double(), bb.double()) for w, bb in lay], n, reflect)
+    act32 = O.custom_equivariant_network(x, lay, n, reflect)
+    assert rel_err(act_simt, act64) < 1e-5
+    # 3xTF32 products are fp32-grade; the tensor core's accumulator rounds differently from an fp32 FMA chain
+    assert rel_err(act_tc, act64) < 2e-5
+    assert rel_err(act_tc, act32) < RTOL
+    assert_index_parity(act_tc, act32, act64, act_tc.argmax(-1))
+
+
+def test_tcgen05_stack_full_batch_properties(cuda_device):
+    """cfg2 batch (512 x 3 x 96 x 96 after the pre-network transform): the stack is per-sample independent and
+    rotation-equivariant, which pins it at a size the oracle cannot reach in seconds."""
+    _, _, _, Net = _mods()
+    dev = cuda_device
+    torch.manual_seed(22)
+    net = Net((3, 96, 96), 32, 5, "rotation", 8, 3, device="cpu").to(dev)
+    x = torch.rand(512, 3, 96, 96, generator=torch.Generator().manual_seed(23)).to(dev)
+    with torch.no_grad():
+        act = net(x)
+        # per-sample independence: any sub-batch gives the same rows (different work-item partition)
+        sub = net(x[37:45])
+        assert torch.equal(act[37:45], sub)
+        # C4 subgroup equivariance (exact for quarter turns of the input): activations roll by 2 positions of C8
+        act_r = net(torch.rot90(x[:64], 1, (2, 3)))
+    scale = float(act.abs().max())
+    for shift in (2, -2):
+        err = float((act_r - torch.roll(act[:64], shift, dims=1)).abs().max())
+        if err < 2e-5 * scale:
+            break
+    else:
+        raise AssertionError("activations of a 90-degree rotated batch are not a roll by two group positions")
