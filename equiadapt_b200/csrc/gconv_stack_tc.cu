@@ -15,11 +15,15 @@
 //   warp 0      weight producer: streams the pre-packed filter-orbit operands (hi / lo images, already in the UMMA
 //               swizzled K-major layout: 16-wide K slabs / 64-byte swizzle for the lift layer, 32-wide K atoms /
 //               128-byte swizzle for the 1x1 layer) from L2 with cp.async.bulk into a 3-stage ring of N x 128 bytes
-//   warp 1      MMA issuer (one elected lane): lift GEMM into TMEM accumulator D1, 1x1 GEMM into D2
+//   warp 1      MMA issuer (one elected lane): lift GEMM  D1[pixel][channel] = A0 . W0^T  (M = 128 pixels, N = channels),
+//               1x1 GEMM TRANSPOSED  D2t[channel][pixel] = W1 . A1^T  (M = 128 channels per half, N = 128 pixels):
+//               the accumulator lanes are channels, so the spatial sum is a serial in-thread sum (no shuffles)
 //   warp 2      TMEM allocator
 //   warps 4-7   epilogue 1: D1 -> +bias, ReLU -> hi/lo split -> next layer's A operand, written in 32-column chunks
 //               straight into the A ring (the 256-wide activation never exists in full anywhere)
-//   warps 8-11  epilogue 2: D2 -> +bias, ReLU -> masked column sums (warp-shuffle transpose-reduce), fp64 accumulation
+//   warps 8-11  epilogue 2: D2t -> +bias, ReLU -> sum over the valid pixel columns of this thread's channel row,
+//               fp64 accumulation per work item (r1b profile: the former pixel-lane layout needed a 31-shuffle
+//               transpose-reduce per 32 columns, 4 800 instructions per tile, and paced the whole pipeline)
 //   warps 12-15 im2col producers: gather the 128 x K patch matrix of the next tile from the image (L1/L2 hits),
 //               split, and write it into the A ring
 // Pipelines: W ring (3 x N*128 B; full = TMA tx-count, empty = tcgen05.commit), A0 ring (3 x 16 KB, im2col -> MMA),
@@ -170,17 +174,19 @@ struct Ring {
 struct Smem {
     uint32_t a0_ring, a1_ring, w_ring, koff, bias1, bias2, part, bars, tmem_slot, total;
 };
+// weight stages hold Nw = N rounded up to whole 128-channel halves (the M of the transposed 1x1 GEMM); rows >= N are zero
+__host__ __device__ inline int weight_rows(int N) { return (N + 127) / 128 * 128; }
 __host__ __device__ inline Smem smem_map(int N, int K0pad) {
     Smem s;
     uint32_t o = 0;
     s.a1_ring = o; o += A1_RING * A1_STAGE;               // 64 KB
     s.a0_ring = o; o += A0_RING * A0_STAGE;               // 48 KB
-    s.w_ring = o; o += W_RING * (uint32_t)N * 128;        // <= 96 KB
+    s.w_ring = o; o += W_RING * (uint32_t)weight_rows(N) * 128;   // <= 96 KB
     s.koff = o; o += (uint32_t)K0pad * 4;
     s.bias1 = o; o += (uint32_t)N * 4;
     s.bias2 = o; o += (uint32_t)N * 4;
     o = (o + 15u) & ~15u;
-    s.part = o; o += 4u * (uint32_t)N * 8;                // 4 warps x N doubles
+    s.part = o;                                           // (unused)
     s.bars = o; o += 24 * 8;
     s.tmem_slot = o; o += 16;
     s.total = o;
@@ -200,7 +206,8 @@ __global__ void __launch_bounds__(THREADS, 1) gconv_stack_tc_kernel(const TcArgs
     auto bar = [&](int i) { return bars + 8u * (uint32_t)i; };
     const int NS0 = a.K0pad / SLAB_K;        // 16-wide K slabs of the lift GEMM
     const int NC1 = N / ATOM_K;              // 32-wide K atoms of the 1x1 GEMM (= 32-column chunks of D1)
-    const uint32_t w_stage_bytes = (uint32_t)N * 128u;
+    const int halves = weight_rows(N) / 128;  // 128-channel halves of the transposed 1x1 GEMM
+    const uint32_t w_stage_bytes = (uint32_t)weight_rows(N) * 128u;
 
     // ---- one-time setup -------------------------------------------------------------------------------------
     if (threadIdx.x == 0) {
@@ -248,7 +255,7 @@ __global__ void __launch_bounds__(THREADS, 1) gconv_stack_tc_kernel(const TcArgs
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *reinterpret_cast<volatile uint32_t *>(sm + M.tmem_slot);
-    const uint32_t tmem_d1 = tmem, tmem_d2 = tmem + 256;
+    const uint32_t tmem_d1 = tmem, tmem_d2 = tmem + 256;  // D2t half h: columns [256 + 128 h, +128)
 
     // work items: (image, chunk of tiles); static round-robin over the persistent CTAs
     const int items = a.B * a.chunks;
@@ -282,6 +289,8 @@ __global__ void __launch_bounds__(THREADS, 1) gconv_stack_tc_kernel(const TcArgs
             // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32 [4,6) = 1, A = B = TF32 [7,10), [10,13) = 2,
             // both K-major, N >> 3 in [17,23), M >> 4 in [24,29)
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+            // transposed 1x1 GEMM: M = 128 channels, N = 128 pixels
+            const uint32_t idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TILE_M >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
             for (int it = blockIdx.x; it < items; it += gridDim.x) {
                 const int ch = it % a.chunks;
                 const int t0 = ch * a.tiles_per_chunk, t1 = min(a.tiles, t0 + a.tiles_per_chunk);
@@ -308,8 +317,8 @@ __global__ void __launch_bounds__(THREADS, 1) gconv_stack_tc_kernel(const TcArgs
                         r0.advance();
                     }
                     tc_commit(bar(B_D1FULL));
-                    // ---- 1x1 GEMM: D2 = A1 . W1^T, K atoms of 32 (hi stage, then lo stage) -----------------------
-                    mbar_wait(bar(B_D2EMPTY), tile_phase ^ 1u, B_D2EMPTY);  // epilogue 2 has drained D2 of the previous tile
+                    // ---- 1x1 GEMM, transposed: D2t[h] = W1[h] . A1^T, K atoms of 32 (hi stage, then lo stage) -----
+                    mbar_wait(bar(B_D2EMPTY), tile_phase ^ 1u, B_D2EMPTY);  // epilogue 2 has drained D2t of the previous tile
                     tc_fence_after();
                     for (int kc = 0; kc < NC1; ++kc) {
                         mbar_wait(bar(B_A1FULL + r1.stage), r1.phase, B_A1FULL + r1.stage);
@@ -317,17 +326,23 @@ __global__ void __launch_bounds__(THREADS, 1) gconv_stack_tc_kernel(const TcArgs
                         mbar_wait(bar(B_WFULL + w.stage), w.phase, B_WFULL + w.stage);
                         tc_fence_after();
                         uint32_t wb = base + M.w_ring + w.stage * w_stage_bytes;
-                        for (int j = 0; j < 4; ++j)
-                            tc_mma_tf32(tmem_d2, umma_desc(a_hi + 32 * j), umma_desc(wb + 32 * j), idesc, (kc | j) != 0);
-                        for (int j = 0; j < 4; ++j)
-                            tc_mma_tf32(tmem_d2, umma_desc(a_lo + 32 * j), umma_desc(wb + 32 * j), idesc, 1);
+                        for (int h = 0; h < halves; ++h)
+                            for (int j = 0; j < 4; ++j)
+                                tc_mma_tf32(tmem_d2 + 128 * h, umma_desc(wb + h * (128 * 128) + 32 * j), umma_desc(a_hi + 32 * j),
+                                            idesc2, (kc | j) != 0);
+                        for (int h = 0; h < halves; ++h)
+                            for (int j = 0; j < 4; ++j)
+                                tc_mma_tf32(tmem_d2 + 128 * h, umma_desc(wb + h * (128 * 128) + 32 * j), umma_desc(a_lo + 32 * j),
+                                            idesc2, 1);
                         tc_commit(bar(B_WEMPTY + w.stage));
                         w.advance();
                         mbar_wait(bar(B_WFULL + w.stage), w.phase, B_WFULL + w.stage);
                         tc_fence_after();
                         wb = base + M.w_ring + w.stage * w_stage_bytes;
-                        for (int j = 0; j < 4; ++j)
-                            tc_mma_tf32(tmem_d2, umma_desc(a_hi + 32 * j), umma_desc(wb + 32 * j), idesc, 1);
+                        for (int h = 0; h < halves; ++h)
+                            for (int j = 0; j < 4; ++j)
+                                tc_mma_tf32(tmem_d2 + 128 * h, umma_desc(wb + h * (128 * 128) + 32 * j), umma_desc(a_hi + 32 * j),
+                                            idesc2, 1);
                         tc_commit(bar(B_WEMPTY + w.stage));
                         w.advance();
                         tc_commit(bar(B_A1EMPTY + r1.stage));
@@ -379,55 +394,62 @@ __global__ void __launch_bounds__(THREADS, 1) gconv_stack_tc_kernel(const TcArgs
             }
         }
     } else if (warp >= 8 && warp < 12) {
-        // ===== epilogue 2: D2 -> relu(. + b2) -> masked column sums ==========================================
-        const int q = warp & 3, row = q * 32 + lane;
+        // ===== epilogue 2: D2t -> relu(. + b2) -> sum over the valid pixels of this thread's channel ==========
+        const int q = warp & 3;
         const float *b2 = reinterpret_cast<const float *>(sm + M.bias2);
-        double *part = reinterpret_cast<double *>(sm + M.part);
+        float bias[2];
+        int chan[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            chan[h] = h * 128 + q * 32 + lane;
+            bias[h] = chan[h] < N ? b2[chan[h]] : 0.f;
+        }
         uint32_t tile_phase = 0;
         for (int it = blockIdx.x; it < items; it += gridDim.x) {
             const int b = it / a.chunks, ch = it % a.chunks;
             const int t0 = ch * a.tiles_per_chunk, t1 = min(a.tiles, t0 + a.tiles_per_chunk);
-            double dacc[8];
-#pragma unroll
-            for (int c = 0; c < 8; ++c) dacc[c] = 0.0;
+            double dacc[2] = {0.0, 0.0};
             for (int t = t0; t < t1; ++t) {
-                const bool valid = t * TILE_M + row < a.P;
+                const int nvalid = min(TILE_M, a.P - t * TILE_M);  // pixel columns of this tile inside the image
                 mbar_wait(bar(B_D2FULL), tile_phase, B_D2FULL);
                 tc_fence_after();
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    if (c < NC1) {
-                        float v[32];
-                        tc_ld32(tmem_d2 + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+                for (int h = 0; h < 2; ++h) {
+                    if (h < halves) {
+                        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+                        const float bv = bias[h];
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) v[i] = valid ? fmaxf(v[i] + b2[c * 32 + i], 0.f) : 0.f;
-                        // transpose-reduce: afterwards lane i holds the sum over the 32 lanes (pixels) of column i
+                        for (int c = 0; c < 4; ++c) {
+                            if (c * 32 < nvalid) {  // (uniform)
+                                float v[32];
+                                tc_ld32(tmem_d2 + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * 128 + c * 32), v);
+                                if (c * 32 + 32 <= nvalid) {
 #pragma unroll
-                        for (int s = 16; s >= 1; s >>= 1) {
-                            const bool up = (lane & s) != 0;
+                                    for (int i = 0; i < 32; i += 4) {
+                                        s0 += fmaxf(v[i] + bv, 0.f);
+                                        s1 += fmaxf(v[i + 1] + bv, 0.f);
+                                        s2 += fmaxf(v[i + 2] + bv, 0.f);
+                                        s3 += fmaxf(v[i + 3] + bv, 0.f);
+                                    }
+                                } else {
 #pragma unroll
-                            for (int i = 0; i < s; ++i) {
-                                const float keep = up ? v[i + s] : v[i];
-                                const float send = up ? v[i] : v[i + s];
-                                v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+                                    for (int i = 0; i < 32; ++i)
+                                        if (c * 32 + i < nvalid) s0 += fmaxf(v[i] + bv, 0.f);
+                                }
                             }
                         }
-                        dacc[c] += (double)v[0];
+                        dacc[h] += (double)((s0 + s1) + (s2 + s3));
                     }
                 }
                 tc_fence_before();
                 mbar_arrive(bar(B_D2EMPTY));
                 tile_phase ^= 1u;
             }
-            // item done: sum the 4 warps (pixel quarters) and emit this chunk's partial sums
+            // item done: every channel is owned by exactly one thread -> emit this chunk's partial sums directly
 #pragma unroll
-            for (int c = 0; c < 8; ++c)
-                if (c < NC1) part[q * N + c * 32 + lane] = dacc[c];
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            for (int n = threadIdx.x - 256; n < a.Npad; n += 128)
-                a.S_part[((size_t)b * a.chunks + ch) * a.Npad + n] =
-                    n < N ? part[n] + part[N + n] + part[2 * N + n] + part[3 * N + n] : 0.0;
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            for (int h = 0; h < 2; ++h)
+                if (h < halves && chan[h] < a.Npad)
+                    a.S_part[((size_t)b * a.chunks + ch) * a.Npad + chan[h]] = chan[h] < N ? dacc[h] : 0.0;
         }
     } else if (warp >= 12) {
         // ===== im2col producers: A0 = patches of the next tile, hi/lo split, into the A0 ring ==================
@@ -483,26 +505,26 @@ __global__ void __launch_bounds__(THREADS, 1) gconv_stack_tc_kernel(const TcArgs
 }
 
 // Pre-pack one layer's K-major operand Wt[Kpad_src][Npad] (k rows, n columns; built by the filter-orbit kernels)
-// into UMMA images: for every 32-wide K atom an N x 128-byte hi image followed by the lo image, 128-byte swizzle
-// (16-byte chunk index XOR (n & 7)).
-__global__ void pack_tc_weights_kernel(const float *__restrict__ Wt, int K, int Npad, int N, int atoms,
+// into UMMA images: for every 32-wide K atom an Nw x 128-byte hi image (one stage) followed by the lo image (next
+// stage), 128-byte swizzle (16-byte chunk index XOR (n & 7)); rows N..Nw are zero.
+__global__ void pack_tc_weights_kernel(const float *__restrict__ Wt, int K, int Npad, int N, int Nw, int atoms,
                                        unsigned char *__restrict__ out) {
-    const int total = atoms * N * ATOM_K;
+    const int total = atoms * Nw * ATOM_K;
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
-        const int ks = t % ATOM_K, n = (t / ATOM_K) % N, atom = t / (ATOM_K * N);
+        const int ks = t % ATOM_K, n = (t / ATOM_K) % Nw, atom = t / (ATOM_K * Nw);
         const int k = atom * ATOM_K + ks;
-        const float w = k < K ? Wt[(size_t)k * Npad + n] : 0.f;
+        const float w = (k < K && n < N) ? Wt[(size_t)k * Npad + n] : 0.f;
         const float hi = tf32_rna(w), lo = w - hi;
-        const size_t stage = (size_t)N * 128;
+        const size_t stage = (size_t)Nw * 128;
         const size_t off = (size_t)n * 128 + (size_t)((((ks >> 2) ^ (n & 7)) << 4) | ((ks & 3) << 2));
         *reinterpret_cast<float *>(out + (size_t)(2 * atom) * stage + off) = hi;
         *reinterpret_cast<float *>(out + (size_t)(2 * atom + 1) * stage + off) = lo;
     }
 }
 
-// Lift layer: 16-wide K slabs, one stage per slab = N x 64-byte hi image followed by the lo image, 64-byte swizzle
-// (16-byte chunk index XOR ((n >> 1) & 3)).
-__global__ void pack_tc_lift_kernel(const float *__restrict__ Wt, int K, int Npad, int N, int slabs,
+// Lift layer: 16-wide K slabs, one stage (Nw x 128 bytes) per slab = N x 64-byte hi image followed by the lo image,
+// 64-byte swizzle (16-byte chunk index XOR ((n >> 1) & 3)).
+__global__ void pack_tc_lift_kernel(const float *__restrict__ Wt, int K, int Npad, int N, int Nw, int slabs,
                                     unsigned char *__restrict__ out) {
     const int total = slabs * N * SLAB_K;
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
@@ -510,7 +532,7 @@ __global__ void pack_tc_lift_kernel(const float *__restrict__ Wt, int K, int Npa
         const int k = slab * SLAB_K + ks;
         const float w = k < K ? Wt[(size_t)k * Npad + n] : 0.f;
         const float hi = tf32_rna(w), lo = w - hi;
-        const size_t stage = (size_t)N * 128, half = (size_t)N * 64;
+        const size_t stage = (size_t)Nw * 128, half = (size_t)N * 64;
         const size_t off = (size_t)n * 64 + (size_t)((((ks >> 2) ^ ((n >> 1) & 3)) << 4) | ((ks & 3) << 2));
         *reinterpret_cast<float *>(out + (size_t)slab * stage + off) = hi;
         *reinterpret_cast<float *>(out + (size_t)slab * stage + half + off) = lo;
@@ -526,13 +548,15 @@ bool tc_eligible(int N, int K0, int n_gemm) {
 
 size_t tc_pack_bytes(int N, int K0) {
     const int ns0 = (K0 + tc::SLAB_K - 1) / tc::SLAB_K, nc1 = N / tc::ATOM_K;
-    return (size_t)(ns0 + 2 * nc1) * N * 128;
+    return (size_t)(ns0 + 2 * nc1) * tc::weight_rows(N) * 128;
 }
 
 int tc_pack(const float *Wt0, int K0, const float *Wt1, int Npad, int N, unsigned char *out, cudaStream_t st) {
     const int ns0 = (K0 + tc::SLAB_K - 1) / tc::SLAB_K, nc1 = N / tc::ATOM_K;
-    tc::pack_tc_lift_kernel<<<64, 256, 0, st>>>(Wt0, K0, Npad, N, ns0, out);
-    tc::pack_tc_weights_kernel<<<64, 256, 0, st>>>(Wt1, N, Npad, N, nc1, out + (size_t)ns0 * N * 128);
+    const int Nw = tc::weight_rows(N);
+    if (Nw != N) EQB_CUDA(cudaMemsetAsync(out, 0, (size_t)ns0 * Nw * 128, st));  // lift stages: bytes past the N rows
+    tc::pack_tc_lift_kernel<<<64, 256, 0, st>>>(Wt0, K0, Npad, N, Nw, ns0, out);
+    tc::pack_tc_weights_kernel<<<64, 256, 0, st>>>(Wt1, N, Npad, N, Nw, nc1, out + (size_t)ns0 * Nw * 128);
     return finish_launch("pack_tc_weights");
 }
 
