@@ -29,6 +29,7 @@ constexpr int GT_PITCH = 68;   // floats per operand row (64 pixels + 4 pad: con
 constexpr int GT_KC = 16;      // K rows per streamed weight chunk
 constexpr int GT_THREADS = 256;
 constexpr int GT_MAX_GEMM = 8;
+constexpr size_t SCRATCH_HEAD = 16;
 
 struct StackArgs {
     const float *x;
@@ -304,6 +305,7 @@ static int make_plan(int B, int cin, int H, int W, int cout, int k, int N, int r
         if (p.tc_chunks > max_chunks) max_chunks = p.tc_chunks;
     }
     p.off_S = off;
+    off += SCRATCH_HEAD;  // per-call scalars ahead of the partial sums: max |x| of the batch (tcgen05 path)
     off += (size_t)(B > 0 ? B : 1) * max_chunks * p.Npad * sizeof(double);
     p.total = off;
     return 0;
@@ -377,8 +379,8 @@ extern "C" int eqb_gconv_stack_pack(const float *lift_w, const float *lift_b, co
     e = finish_launch("eqb_gconv_stack_pack");
     if (e) return e;
     if (p.tc)  // the same operands as UMMA hi / lo images for the tcgen05 kernel
-        return tc_pack((const float *)(ws + p.off_wt[0]), p.K0, (const float *)(ws + p.off_wt[1]), p.Npad, p.N,
-                       (unsigned char *)(ws + p.off_tc), st);
+        return tc_pack((const float *)(ws + p.off_wt[0]), p.K0, (const float *)(ws + p.off_wt[1]),
+                       (const float *)(ws + p.off_bias[0]), p.Npad, p.N, (unsigned char *)(ws + p.off_tc), st);
     return 0;
 }
 
@@ -407,7 +409,7 @@ extern "C" int eqb_gconv_stack_run(const float *x, int B, int cin, int H, int W,
         a.bias[l] = (const float *)(ws + p.off_bias[l]);
         a.Kpad[l] = l == 0 ? p.K0pad : p.Npad;
     }
-    a.S_part = (double *)scratch;
+    a.S_part = (double *)((char *)scratch + SCRATCH_HEAD);
     a.tiles = p.tiles; a.chunks = p.chunks; a.tiles_per_chunk = p.tiles_per_chunk;
     int e, chunks = p.chunks;
     if (p.tc) {
@@ -416,7 +418,10 @@ extern "C" int eqb_gconv_stack_run(const float *x, int B, int cin, int H, int W,
         t.K0 = p.K0; t.N = p.N; t.Npad = p.Npad;
         t.bias1 = a.bias[0]; t.bias2 = a.bias[1];
         t.wpack = (const unsigned char *)(ws + p.off_tc);
+        t.absmax = (const float *)scratch;
         t.S_part = a.S_part;
+        e = tc_absmax(x, (size_t)B * cin * H * W, (float *)scratch, st);
+        if (e) return e;
         t.tiles = p.tc_tiles; t.chunks = p.tc_chunks; t.tiles_per_chunk = p.tc_tiles_per_chunk;
         chunks = p.tc_chunks;
         e = tc_launch(t, st);

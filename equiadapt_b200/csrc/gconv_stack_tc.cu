@@ -4,32 +4,38 @@
 //   :336-361.
 //
 // Both contractions are dense ( [128 pixels x K] x [K x N], K = Cin*k*k and K = N = Cout*|G| <= 256 ), so they
-// run on the 5th-generation tensor cores: tcgen05.mma kind::tf32, M = 128, N = Cout*|G|, accumulators in TMEM.
+// run on the 5th-generation tensor cores: tcgen05.mma kind::f16 (fp16 operands, fp32 accumulate in TMEM), M = 128.
 // Group activations are means of ~270 000 values whose top-2 gap is ~1e-6 (hard part 1):
-// single-pass TF32 is not accurate enough, so every product is evaluated with the 3xTF32 split
-//     a*w ~= a_hi*w_hi + a_lo*w_hi + a_hi*w_lo,   x_hi = rna_tf32(x), x_lo = x - x_hi  (exact in fp32),
-// i.e. three MMAs per K-step; the dropped a_lo*w_lo term is 2^-24 relative.
+// a single half-precision pass is not accurate enough, so every fp32 operand is split into two fp16 numbers
+//     x * s = x_hi + x_lo,   x_hi = rn_f16(x * s),  x_lo = rn_f16(x * s - x_hi)        (22 significand bits)
+// and every product is evaluated as  a_hi*w_hi + a_lo*w_hi + a_hi*w_lo  (three MMAs per K-step at the fp16 rate,
+// half the tensor time of the 3xTF32 scheme this replaces; the dropped a_lo*w_lo term is 2^-22 relative).
+// fp16 has a 5-bit exponent, so every operand is pre-scaled by a power of two (exact) that puts its largest
+// magnitude in [2^13, 2^14): weights at pack time (header of the packed buffer), the image from its per-call
+// absolute maximum (tc_absmax), the hidden activation from the bound  max|x| * max_n sum_k |W0[k][n]| + max|b1|.
+// Small values keep their absolute accuracy through fp16 subnormals (quantum 2^-24 of a range that tops at 2^14).
+// The scales are undone exactly in the epilogues (one FFMA with a power-of-two factor).
 //
 // One persistent CTA per SM, 16 warps, warp-specialised, everything between the resized image and the per-image
 // channel sums stays on chip:
-//   warp 0      weight producer: streams the pre-packed filter-orbit operands (hi / lo images, already in the UMMA
-//               swizzled K-major layout: 16-wide K slabs / 64-byte swizzle for the lift layer, 32-wide K atoms /
-//               128-byte swizzle for the 1x1 layer) from L2 with cp.async.bulk into a 3-stage ring of N x 128 bytes
+//   warp 0      weight producer: streams the pre-packed filter-orbit operands (hi / lo fp16 images, already in the
+//               UMMA swizzled K-major layout: 16-wide K slabs / 32-byte swizzle for the lift layer, 32-wide K atoms /
+//               64-byte swizzle for the 1x1 layer) from L2 with cp.async.bulk into a ring of Nw x 64-byte stages
 //   warp 1      MMA issuer (one elected lane): lift GEMM  D1[pixel][channel] = A0 . W0^T  (M = 128 pixels, N = channels),
 //               1x1 GEMM TRANSPOSED  D2t[channel][pixel] = W1 . A1^T  (M = 128 channels per half, N = 128 pixels):
 //               the accumulator lanes are channels, so the spatial sum is a serial in-thread sum (no shuffles)
 //   warp 2      TMEM allocator
-//   warps 4-7   epilogue 1: D1 -> +bias, ReLU -> hi/lo split -> next layer's A operand, written in 32-column chunks
-//               straight into the A ring (the 256-wide activation never exists in full anywhere)
-//   warps 8-11  epilogue 2: D2t -> +bias, ReLU -> sum over the valid pixel columns of this thread's channel row,
-//               fp64 accumulation per work item (r1b profile: the former pixel-lane layout needed a 31-shuffle
-//               transpose-reduce per 32 columns, 4 800 instructions per tile, and paced the whole pipeline)
+//   warps 4-7   epilogue 1: D1 -> scale, +bias, ReLU -> hi/lo split -> next layer's A operand, written in 32-column
+//               chunks straight into the A ring (the 256-wide activation never exists in full anywhere)
+//   warps 8-11  epilogue 2: D2t -> scale, +bias, ReLU -> sum over the valid pixel columns of this thread's channel
+//               row, fp64 accumulation per work item
 //   warps 12-15 im2col producers: gather the 128 x K patch matrix of the next tile from the image (L1/L2 hits),
-//               split, and write it into the A ring
-// Pipelines: W ring (3 x N*128 B; full = TMA tx-count, empty = tcgen05.commit), A0 ring (3 x 16 KB, im2col -> MMA),
-// A1 ring (2 x 32 KB, epilogue 1 -> MMA; full = 128 producer arrivals, empty = tcgen05.commit), D1 / D2 full (commit)
-// and empty (128 epilogue arrivals).  Every ring has exactly one producer role and one consumer role, so the usual
-// (stage, phase-parity) bookkeeping is sufficient.
+//               scale, split, and write it into the A ring
+// Pipelines: W ring (full = TMA tx-count, empty = tcgen05.commit), A0 ring (im2col -> MMA), A1 ring (epilogue 1 ->
+// MMA; full = 128 producer arrivals, empty = tcgen05.commit), D1 / D2 full (commit) and empty (128 epilogue
+// arrivals).  Every ring has exactly one producer role and one consumer role, so the usual (stage, phase-parity)
+// bookkeeping is sufficient.
+#include <cuda_fp16.h>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -41,13 +47,14 @@ namespace tc {
 
 constexpr int THREADS = 512;
 constexpr int TILE_M = 128;                 // pixels per tile = TMEM lanes
-constexpr int ATOM_K = 32;                  // 1x1 layer: fp32 elements per 128-byte swizzle row
-constexpr int SLAB_K = 16;                  // lift layer: fp32 elements per 64-byte swizzle row
-constexpr int A1_HALF = TILE_M * 128;       // bytes of one A1 image (hi or lo) of one K atom: 16 KB
+constexpr int ATOM_K = 32;                  // 1x1 layer: fp16 elements per 64-byte swizzle row (two K-steps of 16)
+constexpr int SLAB_K = 16;                  // lift layer: fp16 elements per 32-byte swizzle row (one K-step)
+constexpr int A1_HALF = TILE_M * 64;        // bytes of one A1 image (hi or lo) of one K atom: 8 KB
 constexpr int A1_STAGE = 2 * A1_HALF;       // hi + lo
-constexpr int A0_HALF = TILE_M * 64;        // bytes of one A0 image (hi or lo) of one K slab: 8 KB
+constexpr int A0_HALF = TILE_M * 32;        // bytes of one A0 image (hi or lo) of one K slab: 4 KB
 constexpr int A0_STAGE = 2 * A0_HALF;
-constexpr int W_RING = 3, A0_RING = 3, A1_RING = 2;
+constexpr int W_RING = 6, A0_RING = 4, A1_RING = 4;
+constexpr int HDR_BYTES = 1024;             // packed-buffer header: {sw0, sw1, R0, max|b1|} as floats (tc_pack)
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -104,13 +111,13 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                             uint32_t accumulate) {
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
         "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
         "}\n" ::"r"(d_tmem),
         "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
@@ -133,29 +140,40 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, float *v) {
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address >> 4 in bits
-// [0,14), leading byte offset (unused for swizzled K-major) in [16,30), stride byte offset = 1024 (8 rows of 128 B)
-// in [32,46), version 1 in [46,48), layout type 2 = SWIZZLE_128B in [61,64).  Atom bases are 1024-byte aligned;
-// K-steps inside the atom advance the start address by 32 bytes (8 tf32).
-// SWIZZLE_64B (lift layer): rows of 64 B, stride byte offset 512, layout type 4, 16-byte chunk index XOR ((row>>1)&3).
-// Both forms verified bit-exact on B200 with tools/umma_probe.cu.
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
-    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
-           ((uint64_t)2 << 61);
-}
+// K-major swizzled shared-memory matrix descriptors (cute::UMMA::SmemDescriptor): start address >> 4 in bits [0,14),
+// leading byte offset (unused for swizzled K-major) in [16,30), stride byte offset = 8 rows in [32,46), version 1 in
+// [46,48), layout type in [61,64).
+//   SWIZZLE_64B (1x1 layer): rows of 64 B = 32 fp16, SBO 512, layout type 4, 16-byte chunk index XOR ((row >> 1) & 3);
+//                            the second K-step of the atom advances the start address by 32 bytes
+//   SWIZZLE_32B (lift layer): rows of 32 B = 16 fp16, SBO 256, layout type 6, 16-byte chunk index XOR ((row >> 2) & 1)
+// Both forms verified bit-exact on B200 with tools/umma_probe16.cu.
 __device__ __forceinline__ uint64_t umma_desc64(uint32_t saddr) {
     return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(512 >> 4) << 32) | ((uint64_t)1 << 46) |
            ((uint64_t)4 << 61);
 }
-
-__device__ __forceinline__ float tf32_rna(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
+__device__ __forceinline__ uint64_t umma_desc32(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(256 >> 4) << 32) | ((uint64_t)1 << 46) |
+           ((uint64_t)6 << 61);
 }
 
-__device__ __forceinline__ void st_shared_v4(uint32_t addr, float a, float b, float c, float d) {
-    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+// x -> (hi, lo) fp16 pair images of two neighbouring elements, packed for a 32-bit store
+__device__ __forceinline__ void split2(float x0, float x1, uint32_t &hi, uint32_t &lo) {
+    const __half2 h = __floats2half2_rn(x0, x1);
+    const float2 hf = __half22float2(h);
+    const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+    hi = *reinterpret_cast<const uint32_t *>(&h);
+    lo = *reinterpret_cast<const uint32_t *>(&l);
+}
+// power of two s with m * s in [2^13, 2^14) (1 for m == 0 or non-finite m)
+__host__ __device__ __forceinline__ float pow2_scale(float m) {
+    if (!(m > 0.f) || !(m < 3.0e38f)) return 1.f;
+    int e;
+    frexpf(m, &e);  // m = f * 2^e, f in [0.5, 1)
+    return ldexpf(1.f, 14 - e);
+}
+
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
 template <int DEPTH>
@@ -172,7 +190,7 @@ struct Ring {
 
 // shared-memory map (offsets from the 1024-aligned base)
 struct Smem {
-    uint32_t a0_ring, a1_ring, w_ring, koff, bias1, bias2, part, bars, tmem_slot, total;
+    uint32_t a0_ring, a1_ring, w_ring, koff, bias1, bias2, scal, bars, tmem_slot, total;
 };
 // weight stages hold Nw = N rounded up to whole 128-channel halves (the M of the transposed 1x1 GEMM); rows >= N are zero
 __host__ __device__ inline int weight_rows(int N) { return (N + 127) / 128 * 128; }
@@ -180,20 +198,22 @@ __host__ __device__ inline Smem smem_map(int N, int K0pad) {
     Smem s;
     uint32_t o = 0;
     s.a1_ring = o; o += A1_RING * A1_STAGE;               // 64 KB
-    s.a0_ring = o; o += A0_RING * A0_STAGE;               // 48 KB
-    s.w_ring = o; o += W_RING * (uint32_t)weight_rows(N) * 128;   // <= 96 KB
+    s.a0_ring = o; o += A0_RING * A0_STAGE;               // 32 KB
+    s.w_ring = o; o += W_RING * (uint32_t)weight_rows(N) * 64;    // <= 96 KB
     s.koff = o; o += (uint32_t)K0pad * 4;
     s.bias1 = o; o += (uint32_t)N * 4;
     s.bias2 = o; o += (uint32_t)N * 4;
     o = (o + 15u) & ~15u;
-    s.part = o;                                           // (unused)
-    s.bars = o; o += 24 * 8;
+    s.scal = o; o += 16;                                  // {sx, c1, c2, -}
+    s.bars = o; o += 32 * 8;
     s.tmem_slot = o; o += 16;
     s.total = o;
     return s;
 }
-enum { B_WFULL = 0, B_WEMPTY = 3, B_A0FULL = 6, B_A0EMPTY = 9, B_A1FULL = 12, B_A1EMPTY = 14, B_D1FULL = 16, B_D1EMPTY = 17,
-       B_D2FULL = 18, B_D2EMPTY = 19 };
+enum { B_WFULL = 0, B_WEMPTY = B_WFULL + W_RING, B_A0FULL = B_WEMPTY + W_RING, B_A0EMPTY = B_A0FULL + A0_RING,
+       B_A1FULL = B_A0EMPTY + A0_RING, B_A1EMPTY = B_A1FULL + A1_RING, B_D1FULL = B_A1EMPTY + A1_RING, B_D1EMPTY, B_D2FULL,
+       B_D2EMPTY, B_COUNT };
+static_assert(B_COUNT <= 32, "barrier table");
 
 __global__ void __launch_bounds__(THREADS, 1) gconv_stack_tc_kernel(const TcArgs a) {
     extern __shared__ unsigned char smem_raw[];
@@ -207,7 +227,7 @@ __global__ void __launch_bounds__(THREADS, 1) gconv_stack_tc_kernel(const TcArgs
     const int NS0 = a.K0pad / SLAB_K;        // 16-wide K slabs of the lift GEMM
     const int NC1 = N / ATOM_K;              // 32-wide K atoms of the 1x1 GEMM (= 32-column chunks of D1)
     const int halves = weight_rows(N) / 128;  // 128-channel halves of the transposed 1x1 GEMM
-    const uint32_t w_stage_bytes = (uint32_t)weight_rows(N) * 128u;
+    const uint32_t w_stage_bytes = (uint32_t)weight_rows(N) * 64u;
 
     // ---- one-time setup -------------------------------------------------------------------------------------
     if (threadIdx.x == 0) {
@@ -241,9 +261,19 @@ __global__ void __launch_bounds__(THREADS, 1) gconv_stack_tc_kernel(const TcArgs
             }
             koff[k] = off;
         }
+        // operand scales (all exact powers of two): image by its per-call maximum, hidden activation by its bound
+        const float *hdr = reinterpret_cast<const float *>(a.wpack);
+        const float sw0 = hdr[0], sw1 = hdr[1], R0 = hdr[2], b1max = hdr[3];
+        const float amax = *a.absmax;
+        const float sx = pow2_scale(amax), s1 = pow2_scale(amax * R0 + b1max);
+        const float c1 = s1 / (sx * sw0), c2 = 1.f / (s1 * sw1);
         for (int n = threadIdx.x; n < N; n += THREADS) {
-            b1[n] = a.bias1[n];
+            b1[n] = a.bias1[n] * s1;
             b2[n] = a.bias2[n];
+        }
+        if (threadIdx.x == 0) {
+            float *sc = reinterpret_cast<float *>(sm + M.scal);
+            sc[0] = sx; sc[1] = c1; sc[2] = c2;
         }
     }
     if (warp == 2) {
@@ -272,7 +302,7 @@ __global__ void __launch_bounds__(THREADS, 1) gconv_stack_tc_kernel(const TcArgs
                     for (int s = 0; s < stages_per_tile; ++s) {
                         mbar_wait(bar(B_WEMPTY + w.stage), w.phase ^ 1u, B_WEMPTY + w.stage);
                         mbar_expect_tx(bar(B_WFULL + w.stage), w_stage_bytes);
-                        bulk_load(base + M.w_ring + w.stage * w_stage_bytes, a.wpack + (size_t)s * w_stage_bytes,
+                        bulk_load(base + M.w_ring + w.stage * w_stage_bytes, a.wpack + HDR_BYTES + (size_t)s * w_stage_bytes,
                                   w_stage_bytes, bar(B_WFULL + w.stage));
                         w.advance();
                     }
@@ -286,31 +316,27 @@ __global__ void __launch_bounds__(THREADS, 1) gconv_stack_tc_kernel(const TcArgs
             Ring<A0_RING> r0;
             Ring<A1_RING> r1;
             uint32_t tile_phase = 0;
-            // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32 [4,6) = 1, A = B = TF32 [7,10), [10,13) = 2,
+            // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32 [4,6) = 1, A = B = F16 [7,10), [10,13) = 0,
             // both K-major, N >> 3 in [17,23), M >> 4 in [24,29)
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+            const uint32_t idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
             // transposed 1x1 GEMM: M = 128 channels, N = 128 pixels
-            const uint32_t idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TILE_M >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            const uint32_t idesc2 = (1u << 4) | ((uint32_t)(TILE_M >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
             for (int it = blockIdx.x; it < items; it += gridDim.x) {
                 const int ch = it % a.chunks;
                 const int t0 = ch * a.tiles_per_chunk, t1 = min(a.tiles, t0 + a.tiles_per_chunk);
                 for (int t = t0; t < t1; ++t) {
-                    // ---- lift GEMM: D1 = A0 . W0^T, K slabs of 16 (hi and lo weights share one W stage) ----------
+                    // ---- lift GEMM: D1 = A0 . W0^T, one K-step of 16 per slab (hi and lo weights share one W stage) --
                     mbar_wait(bar(B_D1EMPTY), tile_phase ^ 1u, B_D1EMPTY);  // epilogue 1 has drained D1 of the previous tile
                     tc_fence_after();
                     for (int sl = 0; sl < NS0; ++sl) {
-                        const int ksteps = min(2, (a.K0 - sl * SLAB_K + 7) / 8);
                         mbar_wait(bar(B_A0FULL + r0.stage), r0.phase, B_A0FULL + r0.stage);
                         mbar_wait(bar(B_WFULL + w.stage), w.phase, B_WFULL + w.stage);
                         tc_fence_after();
                         const uint32_t a_hi = base + M.a0_ring + r0.stage * A0_STAGE, a_lo = a_hi + A0_HALF;
-                        const uint32_t w_hi = base + M.w_ring + w.stage * w_stage_bytes, w_lo = w_hi + (uint32_t)N * 64u;
-                        for (int j = 0; j < ksteps; ++j)
-                            tc_mma_tf32(tmem_d1, umma_desc64(a_hi + 32 * j), umma_desc64(w_hi + 32 * j), idesc, (sl | j) != 0);
-                        for (int j = 0; j < ksteps; ++j)
-                            tc_mma_tf32(tmem_d1, umma_desc64(a_lo + 32 * j), umma_desc64(w_hi + 32 * j), idesc, 1);
-                        for (int j = 0; j < ksteps; ++j)
-                            tc_mma_tf32(tmem_d1, umma_desc64(a_hi + 32 * j), umma_desc64(w_lo + 32 * j), idesc, 1);
+                        const uint32_t w_hi = base + M.w_ring + w.stage * w_stage_bytes, w_lo = w_hi + (uint32_t)N * 32u;
+                        tc_mma_f16(tmem_d1, umma_desc32(a_hi), umma_desc32(w_hi), idesc, sl != 0);
+                        tc_mma_f16(tmem_d1, umma_desc32(a_lo), umma_desc32(w_hi), idesc, 1);
+                        tc_mma_f16(tmem_d1, umma_desc32(a_hi), umma_desc32(w_lo), idesc, 1);
                         tc_commit(bar(B_WEMPTY + w.stage));
                         tc_commit(bar(B_A0EMPTY + r0.stage));
                         w.advance();
@@ -327,22 +353,22 @@ __global__ void __launch_bounds__(THREADS, 1) gconv_stack_tc_kernel(const TcArgs
                         tc_fence_after();
                         uint32_t wb = base + M.w_ring + w.stage * w_stage_bytes;
                         for (int h = 0; h < halves; ++h)
-                            for (int j = 0; j < 4; ++j)
-                                tc_mma_tf32(tmem_d2 + 128 * h, umma_desc(wb + h * (128 * 128) + 32 * j), umma_desc(a_hi + 32 * j),
-                                            idesc2, (kc | j) != 0);
+                            for (int j = 0; j < 2; ++j)
+                                tc_mma_f16(tmem_d2 + 128 * h, umma_desc64(wb + h * (128 * 64) + 32 * j), umma_desc64(a_hi + 32 * j),
+                                           idesc2, (kc | j) != 0);
                         for (int h = 0; h < halves; ++h)
-                            for (int j = 0; j < 4; ++j)
-                                tc_mma_tf32(tmem_d2 + 128 * h, umma_desc(wb + h * (128 * 128) + 32 * j), umma_desc(a_lo + 32 * j),
-                                            idesc2, 1);
+                            for (int j = 0; j < 2; ++j)
+                                tc_mma_f16(tmem_d2 + 128 * h, umma_desc64(wb + h * (128 * 64) + 32 * j), umma_desc64(a_lo + 32 * j),
+                                           idesc2, 1);
                         tc_commit(bar(B_WEMPTY + w.stage));
                         w.advance();
                         mbar_wait(bar(B_WFULL + w.stage), w.phase, B_WFULL + w.stage);
                         tc_fence_after();
                         wb = base + M.w_ring + w.stage * w_stage_bytes;
                         for (int h = 0; h < halves; ++h)
-                            for (int j = 0; j < 4; ++j)
-                                tc_mma_tf32(tmem_d2 + 128 * h, umma_desc(wb + h * (128 * 128) + 32 * j), umma_desc(a_hi + 32 * j),
-                                            idesc2, 1);
+                            for (int j = 0; j < 2; ++j)
+                                tc_mma_f16(tmem_d2 + 128 * h, umma_desc64(wb + h * (128 * 64) + 32 * j), umma_desc64(a_hi + 32 * j),
+                                           idesc2, 1);
                         tc_commit(bar(B_WEMPTY + w.stage));
                         w.advance();
                         tc_commit(bar(B_A1EMPTY + r1.stage));
@@ -354,12 +380,13 @@ __global__ void __launch_bounds__(THREADS, 1) gconv_stack_tc_kernel(const TcArgs
             }
         }
     } else if (warp >= 4 && warp < 8) {
-        // ===== epilogue 1: D1 -> relu(. + b1) -> hi/lo -> A ring (K atoms of the 1x1 GEMM) ======================
+        // ===== epilogue 1: D1 -> relu(c1 * . + s1 b1) -> fp16 hi/lo -> A ring (K atoms of the 1x1 GEMM) ==========
         const int q = warp & 3, row = q * 32 + lane;
         const float *b1 = reinterpret_cast<const float *>(sm + M.bias1);
+        const float c1 = reinterpret_cast<const float *>(sm + M.scal)[1];
         Ring<A1_RING> ar;
         uint32_t tile_phase = 0;
-        const uint32_t row_off = (uint32_t)row * 128u, sw = (uint32_t)(row & 7);
+        const uint32_t row_off = (uint32_t)row * 64u, sw = (uint32_t)((row >> 1) & 3);
         for (int it = blockIdx.x; it < items; it += gridDim.x) {
             const int ch = it % a.chunks;
             const int t0 = ch * a.tiles_per_chunk, t1 = min(a.tiles, t0 + a.tiles_per_chunk);
@@ -369,20 +396,20 @@ __global__ void __launch_bounds__(THREADS, 1) gconv_stack_tc_kernel(const TcArgs
                 for (int c = 0; c < NC1; ++c) {
                     float v[32];
                     tc_ld32(tmem_d1 + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+                    uint32_t hi[16], lo[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const float x0 = fmaxf(fmaf(v[2 * i], c1, b1[c * 32 + 2 * i]), 0.f);
+                        const float x1 = fmaxf(fmaf(v[2 * i + 1], c1, b1[c * 32 + 2 * i + 1]), 0.f);
+                        split2(x0, x1, hi[i], lo[i]);
+                    }
                     mbar_wait(bar(B_A1EMPTY + ar.stage), ar.phase ^ 1u, B_A1EMPTY + ar.stage);
                     const uint32_t hi_row = base + M.a1_ring + ar.stage * A1_STAGE + row_off, lo_row = hi_row + A1_HALF;
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        float h[4], l[4];
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const float x = fmaxf(v[4 * j + i] + b1[c * 32 + 4 * j + i], 0.f);
-                            h[i] = tf32_rna(x);
-                            l[i] = x - h[i];
-                        }
+                    for (int j = 0; j < 4; ++j) {   // 16-byte chunk j = columns 8j .. 8j+7 of the atom
                         const uint32_t col = ((uint32_t)j ^ sw) << 4;
-                        st_shared_v4(hi_row + col, h[0], h[1], h[2], h[3]);
-                        st_shared_v4(lo_row + col, l[0], l[1], l[2], l[3]);
+                        st_shared_v4(hi_row + col, hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+                        st_shared_v4(lo_row + col, lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
                     }
                     fence_async_smem();
                     mbar_arrive(bar(B_A1FULL + ar.stage));
@@ -397,6 +424,7 @@ __global__ void __launch_bounds__(THREADS, 1) gconv_stack_tc_kernel(const TcArgs
         // ===== epilogue 2: D2t -> relu(. + b2) -> sum over the valid pixels of this thread's channel ==========
         const int q = warp & 3;
         const float *b2 = reinterpret_cast<const float *>(sm + M.bias2);
+        const float c2 = reinterpret_cast<const float *>(sm + M.scal)[2];
         float bias[2];
         int chan[2];
 #pragma unroll
@@ -426,15 +454,15 @@ __global__ void __launch_bounds__(THREADS, 1) gconv_stack_tc_kernel(const TcArgs
                                 if (c * 32 + 32 <= nvalid) {
 #pragma unroll
                                     for (int i = 0; i < 32; i += 4) {
-                                        s0 += fmaxf(v[i] + bv, 0.f);
-                                        s1 += fmaxf(v[i + 1] + bv, 0.f);
-                                        s2 += fmaxf(v[i + 2] + bv, 0.f);
-                                        s3 += fmaxf(v[i + 3] + bv, 0.f);
+                                        s0 += fmaxf(fmaf(v[i], c2, bv), 0.f);
+                                        s1 += fmaxf(fmaf(v[i + 1], c2, bv), 0.f);
+                                        s2 += fmaxf(fmaf(v[i + 2], c2, bv), 0.f);
+                                        s3 += fmaxf(fmaf(v[i + 3], c2, bv), 0.f);
                                     }
                                 } else {
 #pragma unroll
                                     for (int i = 0; i < 32; ++i)
-                                        if (c * 32 + i < nvalid) s0 += fmaxf(v[i] + bv, 0.f);
+                                        if (c * 32 + i < nvalid) s0 += fmaxf(fmaf(v[i], c2, bv), 0.f);
                                 }
                             }
                         }
@@ -452,11 +480,12 @@ __global__ void __launch_bounds__(THREADS, 1) gconv_stack_tc_kernel(const TcArgs
                     a.S_part[((size_t)b * a.chunks + ch) * a.Npad + chan[h]] = chan[h] < N ? dacc[h] : 0.0;
         }
     } else if (warp >= 12) {
-        // ===== im2col producers: A0 = patches of the next tile, hi/lo split, into the A0 ring ==================
+        // ===== im2col producers: A0 = scaled patches of the next tile, fp16 hi/lo split, into the A0 ring =====
         const int row = (warp - 12) * 32 + lane;
         const int *koff = reinterpret_cast<const int *>(sm + M.koff);
+        const float sx = reinterpret_cast<const float *>(sm + M.scal)[0];
         Ring<A0_RING> ar;
-        const uint32_t row_off = (uint32_t)row * 64u, sw = (uint32_t)((row >> 1) & 3);
+        const uint32_t row_off = (uint32_t)row * 32u, sw = (uint32_t)((row >> 2) & 1);
         for (int it = blockIdx.x; it < items; it += gridDim.x) {
             const int b = it / a.chunks, ch = it % a.chunks;
             const int t0 = ch * a.tiles_per_chunk, t1 = min(a.tiles, t0 + a.tiles_per_chunk);
@@ -471,21 +500,18 @@ __global__ void __launch_bounds__(THREADS, 1) gconv_stack_tc_kernel(const TcArgs
 #pragma unroll
                     for (int i = 0; i < SLAB_K; ++i) {
                         const int off = koff[sl * SLAB_K + i];
-                        x[i] = (valid && off >= 0) ? __ldg(xp + off) : 0.f;
+                        x[i] = (valid && off >= 0) ? __ldg(xp + off) * sx : 0.f;
                     }
+                    uint32_t hi[8], lo[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) split2(x[2 * i], x[2 * i + 1], hi[i], lo[i]);
                     mbar_wait(bar(B_A0EMPTY + ar.stage), ar.phase ^ 1u, B_A0EMPTY + ar.stage);
                     const uint32_t hi_row = base + M.a0_ring + ar.stage * A0_STAGE + row_off, lo_row = hi_row + A0_HALF;
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        float h[4], l[4];
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            h[i] = tf32_rna(x[4 * j + i]);
-                            l[i] = x[4 * j + i] - h[i];
-                        }
+                    for (int j = 0; j < 2; ++j) {   // 16-byte chunk j = K columns 8j .. 8j+7 of the slab
                         const uint32_t col = ((uint32_t)j ^ sw) << 4;
-                        st_shared_v4(hi_row + col, h[0], h[1], h[2], h[3]);
-                        st_shared_v4(lo_row + col, l[0], l[1], l[2], l[3]);
+                        st_shared_v4(hi_row + col, hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+                        st_shared_v4(lo_row + col, lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
                     }
                     fence_async_smem();
                     mbar_arrive(bar(B_A0FULL + ar.stage));
@@ -504,38 +530,94 @@ __global__ void __launch_bounds__(THREADS, 1) gconv_stack_tc_kernel(const TcArgs
     }
 }
 
-// Pre-pack one layer's K-major operand Wt[Kpad_src][Npad] (k rows, n columns; built by the filter-orbit kernels)
-// into UMMA images: for every 32-wide K atom an Nw x 128-byte hi image (one stage) followed by the lo image (next
-// stage), 128-byte swizzle (16-byte chunk index XOR (n & 7)); rows N..Nw are zero.
+// Header of the packed buffer: power-of-two operand scales and the pieces of the hidden-activation bound.
+//   hdr[0] = sw0 (lift weights), hdr[1] = sw1 (1x1 weights), hdr[2] = R0 = max_n sum_k |W0[k][n]|, hdr[3] = max |b1|
+__global__ void __launch_bounds__(256) tc_header_kernel(const float *__restrict__ Wt0, int K0, const float *__restrict__ Wt1,
+                                                        const float *__restrict__ bias1, int Npad, int N,
+                                                        float *__restrict__ hdr) {
+    __shared__ float red[4][256];
+    float m0 = 0.f, m1 = 0.f, r0 = 0.f, mb = 0.f;
+    for (int n = threadIdx.x; n < N; n += blockDim.x) {
+        float rs = 0.f;
+        for (int k = 0; k < K0; ++k) {
+            const float w = fabsf(Wt0[(size_t)k * Npad + n]);
+            m0 = fmaxf(m0, w);
+            rs += w;
+        }
+        r0 = fmaxf(r0, rs);
+        for (int k = 0; k < N; ++k) m1 = fmaxf(m1, fabsf(Wt1[(size_t)k * Npad + n]));
+        mb = fmaxf(mb, fabsf(bias1[n]));
+    }
+    red[0][threadIdx.x] = m0; red[1][threadIdx.x] = m1; red[2][threadIdx.x] = r0; red[3][threadIdx.x] = mb;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o)
+            for (int q = 0; q < 4; ++q) red[q][threadIdx.x] = fmaxf(red[q][threadIdx.x], red[q][threadIdx.x + o]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        hdr[0] = pow2_scale(red[0][0]);
+        hdr[1] = pow2_scale(red[1][0]);
+        hdr[2] = red[2][0] * 1.0001f;   // bound, not estimate: cover the rounding of the sum
+        hdr[3] = red[3][0];
+    }
+}
+
+// Pre-pack the 1x1 layer's K-major operand Wt[K][Npad] (k rows, n columns; built by the filter-orbit kernels) into
+// UMMA images: for every 32-wide K atom an Nw x 64-byte fp16 hi image (one stage) followed by the lo image (next
+// stage), 64-byte swizzle (16-byte chunk index XOR ((n >> 1) & 3)); rows N..Nw are zero.
 __global__ void pack_tc_weights_kernel(const float *__restrict__ Wt, int K, int Npad, int N, int Nw, int atoms,
-                                       unsigned char *__restrict__ out) {
+                                       const float *__restrict__ hdr, unsigned char *__restrict__ out) {
+    const float sw = hdr[1];
     const int total = atoms * Nw * ATOM_K;
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
         const int ks = t % ATOM_K, n = (t / ATOM_K) % Nw, atom = t / (ATOM_K * Nw);
         const int k = atom * ATOM_K + ks;
-        const float w = (k < K && n < N) ? Wt[(size_t)k * Npad + n] : 0.f;
-        const float hi = tf32_rna(w), lo = w - hi;
-        const size_t stage = (size_t)Nw * 128;
-        const size_t off = (size_t)n * 128 + (size_t)((((ks >> 2) ^ (n & 7)) << 4) | ((ks & 3) << 2));
-        *reinterpret_cast<float *>(out + (size_t)(2 * atom) * stage + off) = hi;
-        *reinterpret_cast<float *>(out + (size_t)(2 * atom + 1) * stage + off) = lo;
+        const float w = (k < K && n < N) ? Wt[(size_t)k * Npad + n] * sw : 0.f;
+        const __half hi = __float2half_rn(w), lo = __float2half_rn(w - __half2float(hi));
+        const size_t stage = (size_t)Nw * 64;
+        const size_t off = (size_t)n * 64 + (size_t)((((ks >> 3) ^ ((n >> 1) & 3)) << 4) | ((ks & 7) << 1));
+        *reinterpret_cast<__half *>(out + (size_t)(2 * atom) * stage + off) = hi;
+        *reinterpret_cast<__half *>(out + (size_t)(2 * atom + 1) * stage + off) = lo;
     }
 }
 
-// Lift layer: 16-wide K slabs, one stage (Nw x 128 bytes) per slab = N x 64-byte hi image followed by the lo image,
-// 64-byte swizzle (16-byte chunk index XOR ((n >> 1) & 3)).
+// Lift layer: 16-wide K slabs, one stage (Nw x 64 bytes) per slab = N x 32-byte hi image followed by the lo image,
+// 32-byte swizzle (16-byte chunk index XOR ((n >> 2) & 1)).
 __global__ void pack_tc_lift_kernel(const float *__restrict__ Wt, int K, int Npad, int N, int Nw, int slabs,
-                                    unsigned char *__restrict__ out) {
+                                    const float *__restrict__ hdr, unsigned char *__restrict__ out) {
+    const float sw = hdr[0];
     const int total = slabs * N * SLAB_K;
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
         const int ks = t % SLAB_K, n = (t / SLAB_K) % N, slab = t / (SLAB_K * N);
         const int k = slab * SLAB_K + ks;
-        const float w = k < K ? Wt[(size_t)k * Npad + n] : 0.f;
-        const float hi = tf32_rna(w), lo = w - hi;
-        const size_t stage = (size_t)Nw * 128, half = (size_t)N * 64;
-        const size_t off = (size_t)n * 64 + (size_t)((((ks >> 2) ^ ((n >> 1) & 3)) << 4) | ((ks & 3) << 2));
-        *reinterpret_cast<float *>(out + (size_t)slab * stage + off) = hi;
-        *reinterpret_cast<float *>(out + (size_t)slab * stage + half + off) = lo;
+        const float w = k < K ? Wt[(size_t)k * Npad + n] * sw : 0.f;
+        const __half hi = __float2half_rn(w), lo = __float2half_rn(w - __half2float(hi));
+        const size_t stage = (size_t)Nw * 64, half = (size_t)N * 32;
+        const size_t off = (size_t)n * 32 + (size_t)((((ks >> 3) ^ ((n >> 2) & 1)) << 4) | ((ks & 7) << 1));
+        *reinterpret_cast<__half *>(out + (size_t)slab * stage + off) = hi;
+        *reinterpret_cast<__half *>(out + (size_t)slab * stage + half + off) = lo;
+    }
+}
+
+// max |x| over n floats -> *out (must be zeroed first); non-negative floats order like their bit patterns
+__global__ void __launch_bounds__(256) absmax_kernel(const float *__restrict__ x, size_t n, int vec,
+                                                     float *__restrict__ out) {
+    float m = 0.f;
+    const size_t n4 = vec ? n / 4 : 0, stride = (size_t)gridDim.x * blockDim.x;
+    const float4 *x4 = reinterpret_cast<const float4 *>(x);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        const float4 v = __ldg(x4 + i);
+        m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+    }
+    for (size_t i = n4 * 4 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) m = fmaxf(m, fabsf(x[i]));
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    __shared__ float red[8];
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) m = fmaxf(m, red[w]);
+        atomicMax(reinterpret_cast<unsigned int *>(out), __float_as_uint(m));
     }
 }
 
@@ -548,16 +630,30 @@ bool tc_eligible(int N, int K0, int n_gemm) {
 
 size_t tc_pack_bytes(int N, int K0) {
     const int ns0 = (K0 + tc::SLAB_K - 1) / tc::SLAB_K, nc1 = N / tc::ATOM_K;
-    return (size_t)(ns0 + 2 * nc1) * tc::weight_rows(N) * 128;
+    return tc::HDR_BYTES + (size_t)(ns0 + 2 * nc1) * tc::weight_rows(N) * 64;
 }
 
-int tc_pack(const float *Wt0, int K0, const float *Wt1, int Npad, int N, unsigned char *out, cudaStream_t st) {
+int tc_pack(const float *Wt0, int K0, const float *Wt1, const float *bias1, int Npad, int N, unsigned char *out,
+            cudaStream_t st) {
     const int ns0 = (K0 + tc::SLAB_K - 1) / tc::SLAB_K, nc1 = N / tc::ATOM_K;
     const int Nw = tc::weight_rows(N);
-    if (Nw != N) EQB_CUDA(cudaMemsetAsync(out, 0, (size_t)ns0 * Nw * 128, st));  // lift stages: bytes past the N rows
-    tc::pack_tc_lift_kernel<<<64, 256, 0, st>>>(Wt0, K0, Npad, N, Nw, ns0, out);
-    tc::pack_tc_weights_kernel<<<64, 256, 0, st>>>(Wt1, N, Npad, N, Nw, nc1, out + (size_t)ns0 * Nw * 128);
+    float *hdr = reinterpret_cast<float *>(out);
+    unsigned char *img = out + tc::HDR_BYTES;
+    EQB_CUDA(cudaMemsetAsync(out, 0, tc::HDR_BYTES + (size_t)ns0 * Nw * 64, st));  // header pad + lift bytes past the N rows
+    tc::tc_header_kernel<<<1, 256, 0, st>>>(Wt0, K0, Wt1, bias1, Npad, N, hdr);
+    tc::pack_tc_lift_kernel<<<64, 256, 0, st>>>(Wt0, K0, Npad, N, Nw, ns0, hdr, img);
+    tc::pack_tc_weights_kernel<<<64, 256, 0, st>>>(Wt1, N, Npad, N, Nw, nc1, hdr, img + (size_t)ns0 * Nw * 64);
     return finish_launch("pack_tc_weights");
+}
+
+int tc_absmax(const float *x, size_t n, float *absmax, cudaStream_t st) {
+    EQB_CUDA(cudaMemsetAsync(absmax, 0, sizeof(float), st));
+    size_t blocks = (n / 4 + 255) / 256;
+    const size_t cap = (size_t)num_sms() * 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    tc::absmax_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, n, ((uintptr_t)x & 15) == 0, absmax);
+    return finish_launch("absmax_kernel");
 }
 
 static int *g_stall_host = nullptr;

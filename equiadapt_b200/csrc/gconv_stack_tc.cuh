@@ -10,14 +10,18 @@ struct TcArgs {
     int B, cin, H, W, ksz, Wo, P;
     int K0, K0pad, N, Npad;      // lift K = cin*k*k (padded to 32), N = Cout*|G|, Npad = stride of bias / S_part rows
     const float *bias1, *bias2;  // expanded biases (Npad)
-    const unsigned char *wpack;  // UMMA weight images (tc_pack)
+    const unsigned char *wpack;  // header + fp16 UMMA weight images (tc_pack)
+    const float *absmax;         // device scalar: max |x| over this call's batch (tc_absmax)
     double *S_part;              // [B][chunks][Npad] channel sums of the last executed layer
     int tiles, chunks, tiles_per_chunk;  // 128-pixel tiles per image, grouped into chunks (= work items)
 };
 
 bool tc_eligible(int N, int K0, int n_gemm);
 size_t tc_pack_bytes(int N, int K0);
-int tc_pack(const float *Wt0, int K0, const float *Wt1, int Npad, int N, unsigned char *out, cudaStream_t st);
+// Wt0 [K0pad][Npad], Wt1 [Npad][Npad]: K-major fp32 operands built by the filter-orbit kernels; bias1: expanded (Npad)
+int tc_pack(const float *Wt0, int K0, const float *Wt1, const float *bias1, int Npad, int N, unsigned char *out,
+            cudaStream_t st);
+int tc_absmax(const float *x, size_t n, float *absmax, cudaStream_t st);
 int tc_launch(TcArgs a, cudaStream_t st);
 int tc_last_stall(int *out5);  // {flag, block, warp, barrier id, parity} of the first pipeline stall that trapped
 

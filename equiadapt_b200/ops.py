@@ -124,14 +124,15 @@ def gconv_stack_pack(lift_w: torch.Tensor, lift_b: Optional[torch.Tensor], reg_w
     wp = (C.c_void_p * n)(*[_ptr(t) for t in reg_w]) if reg_w else (C.c_void_p * 1)(None)
     bp = (C.c_void_p * n)(*[_ptr(t) for t in reg_b]) if reg_w else (C.c_void_p * 1)(None)
     n_gemm = max(n_layers - 1, 1)
-    _call("eqb_gconv_stack_pack", 1 + 2 * n_gemm, dev, _ptr(lift_w), _ptr(lift_b), wp, bp, cin, cout, k, num_rotations,
+    _call("eqb_gconv_stack_pack", 4 + 2 * n_gemm, dev, _ptr(lift_w), _ptr(lift_b), wp, bp, cin, cout, k, num_rotations,
           int(reflect), n_layers, _ptr(packed), int(nbytes), _stream(dev))
     return packed
 
 
 def gconv_stack_run(x: torch.Tensor, packed: torch.Tensor, last_bias: Optional[torch.Tensor], cout: int, k: int,
                     num_rotations: int, reflect: bool, n_layers: int) -> torch.Tensor:
-    """x (B,Cin,H,W) -> group activations (B,|G|) with pre-packed parameters: 2 launches."""
+    """x (B,Cin,H,W) -> group activations (B,|G|) with pre-packed parameters: 3 launches on the tcgen05 path
+    (batch max |x|, fused stack, finish), 2 on the SIMT path."""
     dev = _need_cuda(x, packed, last_bias)
     x = _f32(x)
     last_bias = None if last_bias is None else _f32(last_bias)
@@ -146,7 +147,7 @@ def gconv_stack_run(x: torch.Tensor, packed: torch.Tensor, last_bias: Optional[t
         raise ValueError("packed parameter buffer does not belong to this network configuration")
     scratch = torch.empty((max(scratch_bytes, 16),), dtype=torch.uint8, device=dev)
     act = torch.empty((b, g), dtype=torch.float32, device=dev)
-    _call("eqb_gconv_stack_run", 2, dev, _ptr(x), b, cin, h, w, _ptr(packed), _ptr(last_bias), cout, k, num_rotations,
+    _call("eqb_gconv_stack_run", 3, dev, _ptr(x), b, cin, h, w, _ptr(packed), _ptr(last_bias), cout, k, num_rotations,
           int(reflect), n_layers, _ptr(act), _ptr(scratch), scratch_bytes, _stream(dev))
     return act
 
