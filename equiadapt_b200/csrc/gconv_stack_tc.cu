@@ -122,6 +122,37 @@ __device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uin
         "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// One MMA from the LOW words of the two shared-memory descriptors (start address >> 4 | LBO) and their common,
+// compile-time HIGH word: advancing an operand by `bytes` is a 32-bit add of bytes >> 4 to the low word.
+template <uint32_t DESC_HI>
+__device__ __forceinline__ void tc_mma_f16_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc,
+                                              uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        ".reg .b64 da, db;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "mov.b64 da, {%1, %5};\n"
+        "mov.b64 db, {%2, %5};\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "n"(DESC_HI)
+        : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n"
+        ".reg .b32 rx;\n"
+        ".reg .pred px;\n"
+        "elect.sync rx|px, %1;\n"
+        "@px mov.s32 %0, 1;\n"
+        "}\n"
+        : "+r"(pred)
+        : "r"(0xFFFFFFFFu));
+    return pred != 0;
+}
+
 // 32 consecutive accumulator columns of this thread's TMEM lane
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, float *v) {
     uint32_t r[32];
@@ -147,6 +178,9 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, float *v) {
 //                            the second K-step of the atom advances the start address by 32 bytes
 //   SWIZZLE_32B (lift layer): rows of 32 B = 16 fp16, SBO 256, layout type 6, 16-byte chunk index XOR ((row >> 2) & 1)
 // Both forms verified bit-exact on B200 with tools/umma_probe16.cu.
+constexpr uint32_t DESC_HI_64B = (512u >> 4) | (1u << 14) | (4u << 29);   // bits [32,64) of the SWIZZLE_64B descriptor
+constexpr uint32_t DESC_HI_32B = (256u >> 4) | (1u << 14) | (6u << 29);   // ... of the SWIZZLE_32B descriptor
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr) { return ((saddr & 0x3FFFFu) >> 4) | (1u << 16); }
 __device__ __forceinline__ uint64_t umma_desc64(uint32_t saddr) {
     return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(512 >> 4) << 32) | ((uint64_t)1 << 46) |
            ((uint64_t)4 << 61);
@@ -311,7 +345,11 @@ __global__ void __launch_bounds__(THREADS, 1) gconv_stack_tc_kernel(const TcArgs
         }
     } else if (warp == 1) {
         // ===== MMA issuer ========================================================================================
-        if (lane == 0) {
+        // The whole warp walks the pipeline (barrier waits are warp-uniform); one elected lane issues the MMAs and
+        // commits of a stage.  Descriptors are (low word, constant high word) pairs: stepping to another stage / K-step
+        // / channel half is one 32-bit add, so a tile costs ~10 instructions per MMA instead of rebuilding 64-bit
+        // descriptors (r1f profile: the issuing thread, not the tensor pipe, paced the kernel at ~170 cycles per MMA).
+        {
             Ring<W_RING> w;
             Ring<A0_RING> r0;
             Ring<A1_RING> r1;
@@ -321,60 +359,75 @@ __global__ void __launch_bounds__(THREADS, 1) gconv_stack_tc_kernel(const TcArgs
             const uint32_t idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
             // transposed 1x1 GEMM: M = 128 channels, N = 128 pixels
             const uint32_t idesc2 = (1u << 4) | ((uint32_t)(TILE_M >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            const uint32_t a0_lo0 = desc_lo(base + M.a0_ring), a1_lo0 = desc_lo(base + M.a1_ring), w_lo0 = desc_lo(base + M.w_ring);
+            const uint32_t w_step = w_stage_bytes >> 4, wlo_off = ((uint32_t)N * 32u) >> 4;
             for (int it = blockIdx.x; it < items; it += gridDim.x) {
                 const int ch = it % a.chunks;
                 const int t0 = ch * a.tiles_per_chunk, t1 = min(a.tiles, t0 + a.tiles_per_chunk);
                 for (int t = t0; t < t1; ++t) {
                     // ---- lift GEMM: D1 = A0 . W0^T, one K-step of 16 per slab (hi and lo weights share one W stage) --
                     mbar_wait(bar(B_D1EMPTY), tile_phase ^ 1u, B_D1EMPTY);  // epilogue 1 has drained D1 of the previous tile
-                    tc_fence_after();
                     for (int sl = 0; sl < NS0; ++sl) {
                         mbar_wait(bar(B_A0FULL + r0.stage), r0.phase, B_A0FULL + r0.stage);
                         mbar_wait(bar(B_WFULL + w.stage), w.phase, B_WFULL + w.stage);
                         tc_fence_after();
-                        const uint32_t a_hi = base + M.a0_ring + r0.stage * A0_STAGE, a_lo = a_hi + A0_HALF;
-                        const uint32_t w_hi = base + M.w_ring + w.stage * w_stage_bytes, w_lo = w_hi + (uint32_t)N * 32u;
-                        tc_mma_f16(tmem_d1, umma_desc32(a_hi), umma_desc32(w_hi), idesc, sl != 0);
-                        tc_mma_f16(tmem_d1, umma_desc32(a_lo), umma_desc32(w_hi), idesc, 1);
-                        tc_mma_f16(tmem_d1, umma_desc32(a_hi), umma_desc32(w_lo), idesc, 1);
-                        tc_commit(bar(B_WEMPTY + w.stage));
-                        tc_commit(bar(B_A0EMPTY + r0.stage));
+                        if (elect_one()) {
+                            const uint32_t a_hi = a0_lo0 + (uint32_t)r0.stage * (A0_STAGE >> 4), a_lo = a_hi + (A0_HALF >> 4);
+                            const uint32_t w_hi = w_lo0 + (uint32_t)w.stage * w_step, w_lo = w_hi + wlo_off;
+                            tc_mma_f16_lo<DESC_HI_32B>(tmem_d1, a_hi, w_hi, idesc, sl != 0);
+                            tc_mma_f16_lo<DESC_HI_32B>(tmem_d1, a_lo, w_hi, idesc, 1);
+                            tc_mma_f16_lo<DESC_HI_32B>(tmem_d1, a_hi, w_lo, idesc, 1);
+                            tc_commit(bar(B_WEMPTY + w.stage));
+                            tc_commit(bar(B_A0EMPTY + r0.stage));
+                            if (sl == NS0 - 1) tc_commit(bar(B_D1FULL));
+                        }
+                        __syncwarp();
                         w.advance();
                         r0.advance();
                     }
-                    tc_commit(bar(B_D1FULL));
                     // ---- 1x1 GEMM, transposed: D2t[h] = W1[h] . A1^T, K atoms of 32 (hi stage, then lo stage) -----
                     mbar_wait(bar(B_D2EMPTY), tile_phase ^ 1u, B_D2EMPTY);  // epilogue 2 has drained D2t of the previous tile
-                    tc_fence_after();
                     for (int kc = 0; kc < NC1; ++kc) {
                         mbar_wait(bar(B_A1FULL + r1.stage), r1.phase, B_A1FULL + r1.stage);
-                        const uint32_t a_hi = base + M.a1_ring + r1.stage * A1_STAGE, a_lo = a_hi + A1_HALF;
                         mbar_wait(bar(B_WFULL + w.stage), w.phase, B_WFULL + w.stage);
                         tc_fence_after();
-                        uint32_t wb = base + M.w_ring + w.stage * w_stage_bytes;
-                        for (int h = 0; h < halves; ++h)
-                            for (int j = 0; j < 2; ++j)
-                                tc_mma_f16(tmem_d2 + 128 * h, umma_desc64(wb + h * (128 * 64) + 32 * j), umma_desc64(a_hi + 32 * j),
-                                           idesc2, (kc | j) != 0);
-                        for (int h = 0; h < halves; ++h)
-                            for (int j = 0; j < 2; ++j)
-                                tc_mma_f16(tmem_d2 + 128 * h, umma_desc64(wb + h * (128 * 64) + 32 * j), umma_desc64(a_lo + 32 * j),
-                                           idesc2, 1);
-                        tc_commit(bar(B_WEMPTY + w.stage));
+                        const uint32_t a_hi = a1_lo0 + (uint32_t)r1.stage * (A1_STAGE >> 4), a_lo = a_hi + (A1_HALF >> 4);
+                        if (elect_one()) {
+                            const uint32_t wb = w_lo0 + (uint32_t)w.stage * w_step;
+#pragma unroll
+                            for (int h = 0; h < 2; ++h)
+                                if (h < halves) {
+#pragma unroll
+                                    for (int j = 0; j < 2; ++j)
+                                        tc_mma_f16_lo<DESC_HI_64B>(tmem_d2 + 128 * h, wb + h * ((128 * 64) >> 4) + 2 * j, a_hi + 2 * j, idesc2,
+                                                                   j ? 1u : (uint32_t)(kc != 0));
+#pragma unroll
+                                    for (int j = 0; j < 2; ++j)
+                                        tc_mma_f16_lo<DESC_HI_64B>(tmem_d2 + 128 * h, wb + h * ((128 * 64) >> 4) + 2 * j, a_lo + 2 * j, idesc2, 1);
+                                }
+                            tc_commit(bar(B_WEMPTY + w.stage));
+                        }
+                        __syncwarp();
                         w.advance();
                         mbar_wait(bar(B_WFULL + w.stage), w.phase, B_WFULL + w.stage);
                         tc_fence_after();
-                        wb = base + M.w_ring + w.stage * w_stage_bytes;
-                        for (int h = 0; h < halves; ++h)
-                            for (int j = 0; j < 2; ++j)
-                                tc_mma_f16(tmem_d2 + 128 * h, umma_desc64(wb + h * (128 * 64) + 32 * j), umma_desc64(a_hi + 32 * j),
-                                           idesc2, 1);
-                        tc_commit(bar(B_WEMPTY + w.stage));
+                        if (elect_one()) {
+                            const uint32_t wb = w_lo0 + (uint32_t)w.stage * w_step;
+#pragma unroll
+                            for (int h = 0; h < 2; ++h)
+                                if (h < halves) {
+#pragma unroll
+                                    for (int j = 0; j < 2; ++j)
+                                        tc_mma_f16_lo<DESC_HI_64B>(tmem_d2 + 128 * h, wb + h * ((128 * 64) >> 4) + 2 * j, a_hi + 2 * j, idesc2, 1);
+                                }
+                            tc_commit(bar(B_WEMPTY + w.stage));
+                            tc_commit(bar(B_A1EMPTY + r1.stage));
+                            if (kc == NC1 - 1) tc_commit(bar(B_D2FULL));
+                        }
+                        __syncwarp();
                         w.advance();
-                        tc_commit(bar(B_A1EMPTY + r1.stage));
                         r1.advance();
                     }
-                    tc_commit(bar(B_D2FULL));
                     tile_phase ^= 1u;
                 }
             }
