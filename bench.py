@@ -39,6 +39,10 @@ OUT_CH, KSIZE, LAYERS = 32, 5, 3
 IMG_BYTES = 2 * 3 * 224 * 224 * 4                      # warp: 1 read + 1 write (SURVEY.md 8d "W")
 STACK_FLOP_EXECUTED = 2 * 92 * 92 * 256 * (75 + 256)   # lift + one 1x1 layer; the last layer is folded
 STACK_FLOP_REFERENCE = 2 * 92 * 92 * 256 * (75 + 256 + 256)
+# dram__bytes_read.sum + dram__bytes_write.sum per launch at the default batch of 512, from the ncu --set full
+# captures summarised under profiles/ (r1h: conv stack; r1b: warp kernels); None = not captured
+NCU_TRAFFIC = {"eqb_gconv_stack_run": 57.0e6 + 0.9e6, "eqb_warp_canonicalize": None, "eqb_warp_invert": None,
+               "eqb_crop_resize_aa": None}
 
 
 def peaks():
@@ -280,20 +284,24 @@ def run_b200(args):
         dom = max(kernels, key=lambda n: kernels[n]["avg_us"] * kernels[n]["calls_per_step"])
         rooflines = {}
         if "eqb_gconv_stack_run" in kernels:
+            # SURVEY.md 8d "N": algorithmic work = the contraction as the REFERENCE computes it (2.544 GFLOP/img);
+            # the kernel executes 1.434 GFLOP/img (last layer folded through the mean) x 3 (fp16 hi/lo operand split)
             us = kernels["eqb_gconv_stack_run"]["avg_us"]
-            ach = STACK_FLOP_EXECUTED * B / (us * 1e-6) / 1e12
+            ach = STACK_FLOP_REFERENCE * B / (us * 1e-6) / 1e12
             rooflines["eqb_gconv_stack_run"] = {
                 "bound": "tensor", "achieved": ach, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                "frac": ach / pk["bf16_tflops_sustained"], "traffic": None,
-                "note": ("fp32 SIMT FMA kernel measured against the bf16 tensor peak (" + pk["source"] + ", sustained); "
-                         "FLOPs counted as EXECUTED (last layer folded: 1.434 GFLOP/img); as the reference computes it "
-                         f"(2.544 GFLOP/img) the same time reads {STACK_FLOP_REFERENCE * B / (us * 1e-6) / 1e12:.1f} TFLOP/s")}
+                "frac": ach / pk["bf16_tflops_sustained"], "traffic": NCU_TRAFFIC.get("eqb_gconv_stack_run"),
+                "note": ("algorithmic FLOPs = the reference's dense contraction, 2.544 GFLOP/img (SURVEY 8d), against the bf16 "
+                         "tensor peak (" + pk["source"] + ", sustained); executed on the tensor pipe: 1.434 GFLOP/img (last "
+                         "layer folded) x 3 fp16 hi/lo products = "
+                         f"{3 * STACK_FLOP_EXECUTED * B / (us * 1e-6) / 1e12:.1f} TFLOP/s of kind::f16 MMA; "
+                         "call = absmax + tcgen05 stack + finish kernels")}
         for name, byt in (("eqb_warp_canonicalize", IMG_BYTES), ("eqb_warp_invert", IMG_BYTES),
                           ("eqb_crop_resize_aa", (3 * 180 * 180 + 3 * 96 * 96) * 4)):
             if name in kernels:
                 ach = byt * B / (kernels[name]["avg_us"] * 1e-6) / 1e9
                 rooflines[name] = {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                                   "frac": ach / pk["hbm_gbs"], "traffic": None}
+                                   "frac": ach / pk["hbm_gbs"], "traffic": NCU_TRAFFIC.get(name)}
         for name in kernels:
             kernels[name]["share_of_step"] = kernels[name]["avg_us"] * kernels[name]["calls_per_step"] / step_us
         cpu = None

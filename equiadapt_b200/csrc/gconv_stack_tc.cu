@@ -45,7 +45,7 @@ namespace eqb {
 
 namespace tc {
 
-constexpr int THREADS = 512;
+constexpr int THREADS = 512;                // 640 when EQB_TC_EPI1_GROUPS=2 (second epilogue-1 group = warps 16-19)
 constexpr int TILE_M = 128;                 // pixels per tile = TMEM lanes
 constexpr int ATOM_K = 32;                  // 1x1 layer: fp16 elements per 64-byte swizzle row (two K-steps of 16)
 constexpr int SLAB_K = 16;                  // lift layer: fp16 elements per 32-byte swizzle row (one K-step)
@@ -249,7 +249,32 @@ enum { B_WFULL = 0, B_WEMPTY = B_WFULL + W_RING, B_A0FULL = B_WEMPTY + W_RING, B
        B_D2EMPTY, B_COUNT };
 static_assert(B_COUNT <= 32, "barrier table");
 
-__global__ void __launch_bounds__(THREADS, 1) gconv_stack_tc_kernel(const TcArgs a) {
+// This CTA's tiles as one flat sequence: work items it = blockIdx.x, blockIdx.x + gridDim.x, ... (image b, chunk ch),
+// tiles [t, t1) inside each.  Every role walks the same sequence, so ring positions and phases line up by count.
+struct TileWalk {
+    const TcArgs &a;
+    int items, it, b, ch, t, t1;
+    __device__ TileWalk(const TcArgs &a_, int items_) : a(a_), items(items_), it((int)blockIdx.x - (int)gridDim.x), b(0), ch(0), t(0), t1(0) {
+        next_item();
+    }
+    __device__ __forceinline__ void next_item() {
+        it += gridDim.x;
+        if (it < items) {
+            b = it / a.chunks;
+            ch = it - b * a.chunks;
+            t = ch * a.tiles_per_chunk;
+            t1 = min(a.tiles, t + a.tiles_per_chunk);
+        }
+    }
+    __device__ __forceinline__ bool valid() const { return it < items; }
+    __device__ __forceinline__ bool has_next() const { return t + 1 < t1 || it + (int)gridDim.x < items; }
+    __device__ __forceinline__ bool last_of_item() const { return t + 1 >= t1; }
+    __device__ __forceinline__ void next() {
+        if (++t >= t1) next_item();
+    }
+};
+
+__global__ void __launch_bounds__(640, 1) gconv_stack_tc_kernel(const TcArgs a) {
     extern __shared__ unsigned char smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     unsigned char *sm = smem_raw + (base - smem_u32(smem_raw));
@@ -278,7 +303,7 @@ __global__ void __launch_bounds__(THREADS, 1) gconv_stack_tc_kernel(const TcArgs
             mbar_init(bar(B_A1EMPTY + i), 1);
         }
         mbar_init(bar(B_D1FULL), 1);
-        mbar_init(bar(B_D1EMPTY), 128);
+        mbar_init(bar(B_D1EMPTY), 128 * a.epi1_groups);   // every epilogue-1 group
         mbar_init(bar(B_D2FULL), 1);
         mbar_init(bar(B_D2EMPTY), 128);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -287,7 +312,7 @@ __global__ void __launch_bounds__(THREADS, 1) gconv_stack_tc_kernel(const TcArgs
         int *koff = reinterpret_cast<int *>(sm + M.koff);
         float *b1 = reinterpret_cast<float *>(sm + M.bias1), *b2 = reinterpret_cast<float *>(sm + M.bias2);
         const int kk2 = a.ksz * a.ksz;
-        for (int k = threadIdx.x; k < a.K0pad; k += THREADS) {
+        for (int k = threadIdx.x; k < a.K0pad; k += blockDim.x) {
             int off = -1;  // padding column
             if (k < a.K0) {
                 const int c = k / kk2, rem = k - c * kk2, ky = rem / a.ksz, kx = rem - ky * a.ksz;
@@ -301,7 +326,7 @@ __global__ void __launch_bounds__(THREADS, 1) gconv_stack_tc_kernel(const TcArgs
         const float amax = *a.absmax;
         const float sx = pow2_scale(amax), s1 = pow2_scale(amax * R0 + b1max);
         const float c1 = s1 / (sx * sw0), c2 = 1.f / (s1 * sw1);
-        for (int n = threadIdx.x; n < N; n += THREADS) {
+        for (int n = threadIdx.x; n < N; n += blockDim.x) {
             b1[n] = a.bias1[n] * s1;
             b2[n] = a.bias2[n];
         }
@@ -323,24 +348,36 @@ __global__ void __launch_bounds__(THREADS, 1) gconv_stack_tc_kernel(const TcArgs
 
     // work items: (image, chunk of tiles); static round-robin over the persistent CTAs
     const int items = a.B * a.chunks;
+    // The lift GEMM of tile i+1 is issued INSIDE the 1x1 GEMM of tile i, ahead of its K atom `ins`: by then both
+    // epilogue-1 groups hold their last D1 chunk of tile i in registers (they release D1 right after that load), so
+    // the lift runs on the tensor pipe while the last atoms are still being converted and D1 of the next tile is
+    // ready when epilogue 1 turns to it.
+    const int ins = a.lift_early ? (NC1 >= 2 ? NC1 - 2 : 0) : NC1;
 
     if (warp == 0) {
         // ===== weight producer ===================================================================================
         if (lane == 0) {
             Ring<W_RING> w;
-            const int stages_per_tile = NS0 + 2 * NC1;
-            for (int it = blockIdx.x; it < items; it += gridDim.x) {
-                const int ch = it % a.chunks;
-                const int t0 = ch * a.tiles_per_chunk, t1 = min(a.tiles, t0 + a.tiles_per_chunk);
-                for (int t = t0; t < t1; ++t) {
-                    for (int s = 0; s < stages_per_tile; ++s) {
-                        mbar_wait(bar(B_WEMPTY + w.stage), w.phase ^ 1u, B_WEMPTY + w.stage);
-                        mbar_expect_tx(bar(B_WFULL + w.stage), w_stage_bytes);
-                        bulk_load(base + M.w_ring + w.stage * w_stage_bytes, a.wpack + HDR_BYTES + (size_t)s * w_stage_bytes,
-                                  w_stage_bytes, bar(B_WFULL + w.stage));
-                        w.advance();
-                    }
+            auto load_stage = [&](int src_stage) {
+                mbar_wait(bar(B_WEMPTY + w.stage), w.phase ^ 1u, B_WEMPTY + w.stage);
+                mbar_expect_tx(bar(B_WFULL + w.stage), w_stage_bytes);
+                bulk_load(base + M.w_ring + w.stage * w_stage_bytes, a.wpack + HDR_BYTES + (size_t)src_stage * w_stage_bytes,
+                          w_stage_bytes, bar(B_WFULL + w.stage));
+                w.advance();
+            };
+            TileWalk tw(a, items);
+            if (tw.valid())
+                for (int sl = 0; sl < NS0; ++sl) load_stage(sl);
+            for (; tw.valid(); tw.next()) {
+                const bool more = tw.has_next();
+                for (int kc = 0; kc < NC1; ++kc) {
+                    if (kc == ins && more)
+                        for (int sl = 0; sl < NS0; ++sl) load_stage(sl);
+                    load_stage(NS0 + 2 * kc);
+                    load_stage(NS0 + 2 * kc + 1);
                 }
+                if (ins == NC1 && more)
+                    for (int sl = 0; sl < NS0; ++sl) load_stage(sl);
             }
         }
     } else if (warp == 1) {
@@ -361,117 +398,130 @@ __global__ void __launch_bounds__(THREADS, 1) gconv_stack_tc_kernel(const TcArgs
             const uint32_t idesc2 = (1u << 4) | ((uint32_t)(TILE_M >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
             const uint32_t a0_lo0 = desc_lo(base + M.a0_ring), a1_lo0 = desc_lo(base + M.a1_ring), w_lo0 = desc_lo(base + M.w_ring);
             const uint32_t w_step = w_stage_bytes >> 4, wlo_off = ((uint32_t)N * 32u) >> 4;
-            for (int it = blockIdx.x; it < items; it += gridDim.x) {
-                const int ch = it % a.chunks;
-                const int t0 = ch * a.tiles_per_chunk, t1 = min(a.tiles, t0 + a.tiles_per_chunk);
-                for (int t = t0; t < t1; ++t) {
-                    // ---- lift GEMM: D1 = A0 . W0^T, one K-step of 16 per slab (hi and lo weights share one W stage) --
-                    mbar_wait(bar(B_D1EMPTY), tile_phase ^ 1u, B_D1EMPTY);  // epilogue 1 has drained D1 of the previous tile
-                    for (int sl = 0; sl < NS0; ++sl) {
-                        mbar_wait(bar(B_A0FULL + r0.stage), r0.phase, B_A0FULL + r0.stage);
-                        mbar_wait(bar(B_WFULL + w.stage), w.phase, B_WFULL + w.stage);
-                        tc_fence_after();
-                        if (elect_one()) {
-                            const uint32_t a_hi = a0_lo0 + (uint32_t)r0.stage * (A0_STAGE >> 4), a_lo = a_hi + (A0_HALF >> 4);
-                            const uint32_t w_hi = w_lo0 + (uint32_t)w.stage * w_step, w_lo = w_hi + wlo_off;
-                            tc_mma_f16_lo<DESC_HI_32B>(tmem_d1, a_hi, w_hi, idesc, sl != 0);
-                            tc_mma_f16_lo<DESC_HI_32B>(tmem_d1, a_lo, w_hi, idesc, 1);
-                            tc_mma_f16_lo<DESC_HI_32B>(tmem_d1, a_hi, w_lo, idesc, 1);
-                            tc_commit(bar(B_WEMPTY + w.stage));
-                            tc_commit(bar(B_A0EMPTY + r0.stage));
-                            if (sl == NS0 - 1) tc_commit(bar(B_D1FULL));
-                        }
-                        __syncwarp();
-                        w.advance();
-                        r0.advance();
+            uint32_t lift_phase = 0;
+            // lift GEMM of one tile: D1 = A0 . W0^T, one K-step of 16 per slab (hi and lo weights share one W stage)
+            auto issue_lift = [&]() {
+                mbar_wait(bar(B_D1EMPTY), lift_phase ^ 1u, B_D1EMPTY);  // epilogue 1 holds the rest of the previous D1 in registers
+                lift_phase ^= 1u;
+                for (int sl = 0; sl < NS0; ++sl) {
+                    mbar_wait(bar(B_A0FULL + r0.stage), r0.phase, B_A0FULL + r0.stage);
+                    mbar_wait(bar(B_WFULL + w.stage), w.phase, B_WFULL + w.stage);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint32_t a_hi = a0_lo0 + (uint32_t)r0.stage * (A0_STAGE >> 4), a_lo = a_hi + (A0_HALF >> 4);
+                        const uint32_t w_hi = w_lo0 + (uint32_t)w.stage * w_step, w_lo = w_hi + wlo_off;
+                        tc_mma_f16_lo<DESC_HI_32B>(tmem_d1, a_hi, w_hi, idesc, sl != 0);
+                        tc_mma_f16_lo<DESC_HI_32B>(tmem_d1, a_lo, w_hi, idesc, 1);
+                        tc_mma_f16_lo<DESC_HI_32B>(tmem_d1, a_hi, w_lo, idesc, 1);
+                        tc_commit(bar(B_WEMPTY + w.stage));
+                        tc_commit(bar(B_A0EMPTY + r0.stage));
+                        if (sl == NS0 - 1) tc_commit(bar(B_D1FULL));
                     }
-                    // ---- 1x1 GEMM, transposed: D2t[h] = W1[h] . A1^T, K atoms of 32 (hi stage, then lo stage) -----
-                    mbar_wait(bar(B_D2EMPTY), tile_phase ^ 1u, B_D2EMPTY);  // epilogue 2 has drained D2t of the previous tile
-                    for (int kc = 0; kc < NC1; ++kc) {
-                        mbar_wait(bar(B_A1FULL + r1.stage), r1.phase, B_A1FULL + r1.stage);
-                        mbar_wait(bar(B_WFULL + w.stage), w.phase, B_WFULL + w.stage);
-                        tc_fence_after();
-                        const uint32_t a_hi = a1_lo0 + (uint32_t)r1.stage * (A1_STAGE >> 4), a_lo = a_hi + (A1_HALF >> 4);
-                        if (elect_one()) {
-                            const uint32_t wb = w_lo0 + (uint32_t)w.stage * w_step;
-#pragma unroll
-                            for (int h = 0; h < 2; ++h)
-                                if (h < halves) {
-#pragma unroll
-                                    for (int j = 0; j < 2; ++j)
-                                        tc_mma_f16_lo<DESC_HI_64B>(tmem_d2 + 128 * h, wb + h * ((128 * 64) >> 4) + 2 * j, a_hi + 2 * j, idesc2,
-                                                                   j ? 1u : (uint32_t)(kc != 0));
-#pragma unroll
-                                    for (int j = 0; j < 2; ++j)
-                                        tc_mma_f16_lo<DESC_HI_64B>(tmem_d2 + 128 * h, wb + h * ((128 * 64) >> 4) + 2 * j, a_lo + 2 * j, idesc2, 1);
-                                }
-                            tc_commit(bar(B_WEMPTY + w.stage));
-                        }
-                        __syncwarp();
-                        w.advance();
-                        mbar_wait(bar(B_WFULL + w.stage), w.phase, B_WFULL + w.stage);
-                        tc_fence_after();
-                        if (elect_one()) {
-                            const uint32_t wb = w_lo0 + (uint32_t)w.stage * w_step;
-#pragma unroll
-                            for (int h = 0; h < 2; ++h)
-                                if (h < halves) {
-#pragma unroll
-                                    for (int j = 0; j < 2; ++j)
-                                        tc_mma_f16_lo<DESC_HI_64B>(tmem_d2 + 128 * h, wb + h * ((128 * 64) >> 4) + 2 * j, a_hi + 2 * j, idesc2, 1);
-                                }
-                            tc_commit(bar(B_WEMPTY + w.stage));
-                            tc_commit(bar(B_A1EMPTY + r1.stage));
-                            if (kc == NC1 - 1) tc_commit(bar(B_D2FULL));
-                        }
-                        __syncwarp();
-                        w.advance();
-                        r1.advance();
-                    }
-                    tile_phase ^= 1u;
+                    __syncwarp();
+                    w.advance();
+                    r0.advance();
                 }
+            };
+            TileWalk tw(a, items);
+            if (tw.valid()) issue_lift();
+            for (; tw.valid(); tw.next()) {
+                const bool more = tw.has_next();
+                // ---- 1x1 GEMM, transposed: D2t[h] = W1[h] . A1^T, K atoms of 32 (hi stage, then lo stage) -----
+                mbar_wait(bar(B_D2EMPTY), tile_phase ^ 1u, B_D2EMPTY);  // epilogue 2 has drained D2t of the previous tile
+                for (int kc = 0; kc < NC1; ++kc) {
+                    if (kc == ins && more) issue_lift();
+                    mbar_wait(bar(B_A1FULL + r1.stage), r1.phase, B_A1FULL + r1.stage);
+                    mbar_wait(bar(B_WFULL + w.stage), w.phase, B_WFULL + w.stage);
+                    tc_fence_after();
+                    const uint32_t a_hi = a1_lo0 + (uint32_t)r1.stage * (A1_STAGE >> 4), a_lo = a_hi + (A1_HALF >> 4);
+                    if (elect_one()) {
+                        const uint32_t wb = w_lo0 + (uint32_t)w.stage * w_step;
+#pragma unroll
+                        for (int h = 0; h < 2; ++h)
+                            if (h < halves) {
+#pragma unroll
+                                for (int j = 0; j < 2; ++j)
+                                    tc_mma_f16_lo<DESC_HI_64B>(tmem_d2 + 128 * h, wb + h * ((128 * 64) >> 4) + 2 * j, a_hi + 2 * j, idesc2,
+                                                               j ? 1u : (uint32_t)(kc != 0));
+#pragma unroll
+                                for (int j = 0; j < 2; ++j)
+                                    tc_mma_f16_lo<DESC_HI_64B>(tmem_d2 + 128 * h, wb + h * ((128 * 64) >> 4) + 2 * j, a_lo + 2 * j, idesc2, 1);
+                            }
+                        tc_commit(bar(B_WEMPTY + w.stage));
+                    }
+                    __syncwarp();
+                    w.advance();
+                    mbar_wait(bar(B_WFULL + w.stage), w.phase, B_WFULL + w.stage);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint32_t wb = w_lo0 + (uint32_t)w.stage * w_step;
+#pragma unroll
+                        for (int h = 0; h < 2; ++h)
+                            if (h < halves) {
+#pragma unroll
+                                for (int j = 0; j < 2; ++j)
+                                    tc_mma_f16_lo<DESC_HI_64B>(tmem_d2 + 128 * h, wb + h * ((128 * 64) >> 4) + 2 * j, a_hi + 2 * j, idesc2, 1);
+                            }
+                        tc_commit(bar(B_WEMPTY + w.stage));
+                        tc_commit(bar(B_A1EMPTY + r1.stage));
+                        if (kc == NC1 - 1) tc_commit(bar(B_D2FULL));
+                    }
+                    __syncwarp();
+                    w.advance();
+                    r1.advance();
+                }
+                if (ins == NC1 && more) issue_lift();
+                tile_phase ^= 1u;
             }
         }
-    } else if (warp >= 4 && warp < 8) {
+    } else if ((warp >= 4 && warp < 8) || warp >= 16) {
         // ===== epilogue 1: D1 -> relu(c1 * . + s1 b1) -> fp16 hi/lo -> A ring (K atoms of the 1x1 GEMM) ==========
+        // Two groups of four warps (TMEM lane quarter = warp & 3): group 0 converts the even 32-column chunks,
+        // group 1 the odd ones, each into the ring stage the chunk's sequence number selects.  A group releases D1
+        // as soon as its LAST chunk of the tile is in registers.
+        const int grp = warp >= 16 ? 1 : 0, ngrp = a.epi1_groups;
         const int q = warp & 3, row = q * 32 + lane;
         const float *b1 = reinterpret_cast<const float *>(sm + M.bias1);
         const float c1 = reinterpret_cast<const float *>(sm + M.scal)[1];
-        Ring<A1_RING> ar;
         uint32_t tile_phase = 0;
         const uint32_t row_off = (uint32_t)row * 64u, sw = (uint32_t)((row >> 1) & 3);
-        for (int it = blockIdx.x; it < items; it += gridDim.x) {
-            const int ch = it % a.chunks;
-            const int t0 = ch * a.tiles_per_chunk, t1 = min(a.tiles, t0 + a.tiles_per_chunk);
-            for (int t = t0; t < t1; ++t) {
-                mbar_wait(bar(B_D1FULL), tile_phase, B_D1FULL);
-                tc_fence_after();
-                for (int c = 0; c < NC1; ++c) {
-                    float v[32];
-                    tc_ld32(tmem_d1 + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
-                    uint32_t hi[16], lo[16];
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const float x0 = fmaxf(fmaf(v[2 * i], c1, b1[c * 32 + 2 * i]), 0.f);
-                        const float x1 = fmaxf(fmaf(v[2 * i + 1], c1, b1[c * 32 + 2 * i + 1]), 0.f);
-                        split2(x0, x1, hi[i], lo[i]);
-                    }
-                    mbar_wait(bar(B_A1EMPTY + ar.stage), ar.phase ^ 1u, B_A1EMPTY + ar.stage);
-                    const uint32_t hi_row = base + M.a1_ring + ar.stage * A1_STAGE + row_off, lo_row = hi_row + A1_HALF;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {   // 16-byte chunk j = columns 8j .. 8j+7 of the atom
-                        const uint32_t col = ((uint32_t)j ^ sw) << 4;
-                        st_shared_v4(hi_row + col, hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
-                        st_shared_v4(lo_row + col, lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
-                    }
-                    fence_async_smem();
-                    mbar_arrive(bar(B_A1FULL + ar.stage));
-                    ar.advance();
-                }
+        const int last_c = NC1 - 1 - ((NC1 - 1 - grp) % ngrp + ngrp) % ngrp;   // last chunk of this group (< grp: none)
+        uint32_t seq0 = 0;                                     // sequence number of chunk 0 of the current tile
+        for (TileWalk tw(a, items); tw.valid() && grp < ngrp; tw.next()) {
+            mbar_wait(bar(B_D1FULL), tile_phase, B_D1FULL);
+            tc_fence_after();
+            if (last_c < grp) {
                 tc_fence_before();
                 mbar_arrive(bar(B_D1EMPTY));
-                tile_phase ^= 1u;
             }
+            for (int c = grp; c < NC1; c += ngrp) {
+                float v[32];
+                tc_ld32(tmem_d1 + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+                if (c == last_c) {
+                    tc_fence_before();
+                    mbar_arrive(bar(B_D1EMPTY));
+                }
+                uint32_t hi[16], lo[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const float x0 = fmaxf(fmaf(v[2 * i], c1, b1[c * 32 + 2 * i]), 0.f);
+                    const float x1 = fmaxf(fmaf(v[2 * i + 1], c1, b1[c * 32 + 2 * i + 1]), 0.f);
+                    split2(x0, x1, hi[i], lo[i]);
+                }
+                const uint32_t seq = seq0 + (uint32_t)c, stage = seq % A1_RING, phase = (seq / A1_RING) & 1u;
+                mbar_wait(bar(B_A1EMPTY + stage), phase ^ 1u, B_A1EMPTY + stage);
+                const uint32_t hi_row = base + M.a1_ring + stage * A1_STAGE + row_off, lo_row = hi_row + A1_HALF;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {   // 16-byte chunk j = columns 8j .. 8j+7 of the atom
+                    const uint32_t col = ((uint32_t)j ^ sw) << 4;
+                    st_shared_v4(hi_row + col, hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+                    st_shared_v4(lo_row + col, lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+                }
+                fence_async_smem();
+                mbar_arrive(bar(B_A1FULL + stage));
+            }
+            seq0 += (uint32_t)NC1;
+            tile_phase ^= 1u;
         }
     } else if (warp >= 8 && warp < 12) {
         // ===== epilogue 2: D2t -> relu(. + b2) -> sum over the valid pixels of this thread's channel ==========
@@ -532,44 +582,60 @@ __global__ void __launch_bounds__(THREADS, 1) gconv_stack_tc_kernel(const TcArgs
                 if (h < halves && chan[h] < a.Npad)
                     a.S_part[((size_t)b * a.chunks + ch) * a.Npad + chan[h]] = chan[h] < N ? dacc[h] : 0.0;
         }
-    } else if (warp >= 12) {
+    } else if (warp >= 12 && warp < 16) {
         // ===== im2col producers: A0 = scaled patches of the next tile, fp16 hi/lo split, into the A0 ring =====
         const int row = (warp - 12) * 32 + lane;
         const int *koff = reinterpret_cast<const int *>(sm + M.koff);
         const float sx = reinterpret_cast<const float *>(sm + M.scal)[0];
         Ring<A0_RING> ar;
         const uint32_t row_off = (uint32_t)row * 32u, sw = (uint32_t)((row >> 2) & 1);
-        for (int it = blockIdx.x; it < items; it += gridDim.x) {
-            const int b = it / a.chunks, ch = it % a.chunks;
-            const int t0 = ch * a.tiles_per_chunk, t1 = min(a.tiles, t0 + a.tiles_per_chunk);
-            const float *xb = a.x + (size_t)b * a.cin * a.H * a.W;
-            for (int t = t0; t < t1; ++t) {
-                const int p = t * TILE_M + row;
-                const bool valid = p < a.P;
-                const int oy = valid ? p / a.Wo : 0, ox = valid ? p - oy * a.Wo : 0;
-                const float *xp = xb + (size_t)oy * a.W + ox;
-                for (int sl = 0; sl < NS0; ++sl) {
-                    float x[SLAB_K];
+        // loads of slab s+1 are in flight while slab s is converted and stored (global latency off the critical path)
+        auto tile_ptr = [&](const TileWalk &w, bool &valid) {
+            const int p = w.t * TILE_M + row;
+            valid = p < a.P;
+            const int oy = valid ? p / a.Wo : 0, ox = valid ? p - oy * a.Wo : 0;
+            return a.x + (size_t)w.b * a.cin * a.H * a.W + (size_t)oy * a.W + ox;
+        };
+        auto load_slab = [&](const float *xp, bool valid, int sl, float *x) {
 #pragma unroll
-                    for (int i = 0; i < SLAB_K; ++i) {
-                        const int off = koff[sl * SLAB_K + i];
-                        x[i] = (valid && off >= 0) ? __ldg(xp + off) * sx : 0.f;
+            for (int i = 0; i < SLAB_K; ++i) {
+                const int off = koff[sl * SLAB_K + i];
+                x[i] = (valid && off >= 0) ? __ldg(xp + off) : 0.f;
+            }
+        };
+        TileWalk tw(a, items);
+        bool valid = false;
+        const float *xp = tw.valid() ? tile_ptr(tw, valid) : a.x;
+        float xn[SLAB_K];
+        if (tw.valid()) load_slab(xp, valid, 0, xn);
+        while (tw.valid()) {
+            for (int sl = 0; sl < NS0; ++sl) {
+                float x[SLAB_K];
+#pragma unroll
+                for (int i = 0; i < SLAB_K; ++i) x[i] = xn[i] * sx;
+                if (sl + 1 < NS0) {
+                    load_slab(xp, valid, sl + 1, xn);
+                } else {
+                    tw.next();
+                    if (tw.valid()) {
+                        xp = tile_ptr(tw, valid);
+                        load_slab(xp, valid, 0, xn);
                     }
-                    uint32_t hi[8], lo[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) split2(x[2 * i], x[2 * i + 1], hi[i], lo[i]);
-                    mbar_wait(bar(B_A0EMPTY + ar.stage), ar.phase ^ 1u, B_A0EMPTY + ar.stage);
-                    const uint32_t hi_row = base + M.a0_ring + ar.stage * A0_STAGE + row_off, lo_row = hi_row + A0_HALF;
-#pragma unroll
-                    for (int j = 0; j < 2; ++j) {   // 16-byte chunk j = K columns 8j .. 8j+7 of the slab
-                        const uint32_t col = ((uint32_t)j ^ sw) << 4;
-                        st_shared_v4(hi_row + col, hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
-                        st_shared_v4(lo_row + col, lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
-                    }
-                    fence_async_smem();
-                    mbar_arrive(bar(B_A0FULL + ar.stage));
-                    ar.advance();
                 }
+                uint32_t hi[8], lo[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) split2(x[2 * i], x[2 * i + 1], hi[i], lo[i]);
+                mbar_wait(bar(B_A0EMPTY + ar.stage), ar.phase ^ 1u, B_A0EMPTY + ar.stage);
+                const uint32_t hi_row = base + M.a0_ring + ar.stage * A0_STAGE + row_off, lo_row = hi_row + A0_HALF;
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {   // 16-byte chunk j = K columns 8j .. 8j+7 of the slab
+                    const uint32_t col = ((uint32_t)j ^ sw) << 4;
+                    st_shared_v4(hi_row + col, hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+                    st_shared_v4(lo_row + col, lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+                }
+                fence_async_smem();
+                mbar_arrive(bar(B_A0FULL + ar.stage));
+                ar.advance();
             }
         }
     }
@@ -726,6 +792,13 @@ int tc_launch(TcArgs a, cudaStream_t st) {
         EQB_CUDA(cudaMemcpyToSymbol(tc::g_stall_report, &dptr, sizeof(dptr)));
     }
     a.K0pad = (a.K0 + tc::SLAB_K - 1) / tc::SLAB_K * tc::SLAB_K;
+    // Pipeline-shape knobs, defaults = the measured best (profiles/r1h_summary.md): with the kernel bound by
+    // shared-memory bandwidth (UMMA operand reads + weight stages + epilogue stores) a second epilogue-1 group
+    // changes nothing (1791 vs 1820 us) and overlapping the next lift GEMM with the 1x1 GEMM costs 10 % (1974 us).
+    const char *eg = getenv("EQB_TC_EPI1_GROUPS"), *le = getenv("EQB_TC_LIFT_EARLY");
+    a.epi1_groups = eg && eg[0] == '2' ? 2 : 1;
+    a.lift_early = le && le[0] == '1' ? 1 : 0;
+    const int threads = a.epi1_groups == 2 ? 640 : tc::THREADS;
     const tc::Smem M = tc::smem_map(a.N, a.K0pad);
     const size_t smem = (size_t)M.total + 1024;
     EQB_UNSUPPORTED(smem > 227 * 1024, "gconv_stack (tcgen05): Cin*k*k = %d too large for the shared-memory rings", a.K0);
@@ -736,7 +809,7 @@ int tc_launch(TcArgs a, cudaStream_t st) {
     }
     const int items = a.B * a.chunks;
     const int grid = items < num_sms() ? items : num_sms();
-    tc::gconv_stack_tc_kernel<<<grid, tc::THREADS, smem, st>>>(a);
+    tc::gconv_stack_tc_kernel<<<grid, threads, smem, st>>>(a);
     return finish_launch("gconv_stack_tc_kernel");
 }
 

@@ -14,6 +14,7 @@ struct TcArgs {
     const float *absmax;         // device scalar: max |x| over this call's batch (tc_absmax)
     double *S_part;              // [B][chunks][Npad] channel sums of the last executed layer
     int tiles, chunks, tiles_per_chunk;  // 128-pixel tiles per image, grouped into chunks (= work items)
+    int epi1_groups, lift_early;         // pipeline shape (set by tc_launch)
 };
 
 bool tc_eligible(int N, int K0, int n_gemm);

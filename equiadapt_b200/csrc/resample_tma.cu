@@ -88,7 +88,7 @@ __device__ __forceinline__ int regular_src_channel(const ResampleArgs &a, int cs
 }
 
 template <int CG, bool ZERO>
-__global__ void __launch_bounds__(THREADS, 5) resample_tma_kernel(const __grid_constant__ CUtensorMap map_box,
+__global__ void __launch_bounds__(THREADS, 6) resample_tma_kernel(const __grid_constant__ CUtensorMap map_box,
                                                                   const __grid_constant__ CUtensorMap map_tile,
                                                                   const __grid_constant__ ResampleArgs a) {
     extern __shared__ unsigned char smem_raw[];
