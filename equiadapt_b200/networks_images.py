@@ -131,3 +131,113 @@ class CustomEquivariantNetwork(nn.Module):
         last_bias = regs[-1].bias if regs else None
         return ops.gconv_stack_run(x, self._packed, last_bias, lift.out_channels, lift.kernel_size,
                                    self.num_rotations, reflect, len(mods))
+
+
+class ESCNNEquivariantNetwork(nn.Module):
+    """The reference's e2cnn network (escnn_networks.py:8-117) on the expanded-filter conv stack (eqb_conv_stack_forward).
+
+    Reference layout: R2Conv(k) -> InnerBatchNorm -> ReLU -> PointwiseDropout(.5), (L-2) more such blocks,
+    a final R2Conv(k); output reshaped to (B, Cout, |G|, H', W') and averaged over (Cout, H', W').
+    In eval() every module is a dense op on tensors e2cnn caches (`R2Conv.filter`, `R2Conv.expanded_bias`), batch
+    norm is one affine per field shared by its |G| channels, dropout is the identity.  This class holds exactly
+    those tensors per layer:
+        filters[l] (Cout*|G|, Cin_l, k, k), biases[l] (Cout*|G|),
+        bn_weight / bn_bias / bn_running_mean / bn_running_var [l] (Cout)  for l < L-1
+    and runs them as one C-ABI call.  e2cnn is not available to this build, so
+      * a fresh instance is initialised with a group-symmetrised random filter bank (the filter-orbit construction
+        of the custom layers, custom_group_equivariant_layers.py:62-90, :298-334, applied to k x k kernels), which is
+        equivariant by construction; its values differ from e2cnn's steerable-basis initialisation;
+      * `load_e2cnn(reference_network)` copies the cached tensors out of a reference ESCNNEquivariantNetwork in eval
+        mode when e2cnn IS importable (checkpoint hand-over);
+      * training-mode behaviour (batch statistics, dropout) is not implemented: forward raises in train().
+    Parity of e2cnn's own basis expansion is unpinned; what is pinned is the dense arithmetic on
+    the expanded tensors (oracle.reference_path.expanded_conv_network).
+    """
+
+    bn_eps = 1e-5
+
+    def __init__(self, in_shape: tuple, out_channels: int, kernel_size: int, group_type: str = "rotation",
+                 num_rotations: int = 4, num_layers: int = 1, device: str = "cuda" if torch.cuda.is_available() else "cpu"):
+        super().__init__()
+        if group_type not in ("rotation", "roto-reflection"):
+            raise ValueError("group_type must be rotation or roto-reflection for now.")
+        self.in_channels = in_shape[0]
+        self.out_channels = out_channels
+        self.kernel_size = kernel_size
+        self.group_type = group_type
+        self.num_rotations = num_rotations
+        self.num_layers = num_layers
+        self.num_group_elements = num_rotations if group_type == "rotation" else 2 * num_rotations
+        g, n = self.num_group_elements, out_channels * self.num_group_elements
+        self.filters = nn.ParameterList()
+        self.biases = nn.ParameterList()
+        self.bn_weight = nn.ParameterList()
+        self.bn_bias = nn.ParameterList()
+        for l in range(num_layers):
+            cin = self.in_channels if l == 0 else n
+            self.filters.append(nn.Parameter(torch.zeros(n, cin, kernel_size, kernel_size, device=device)))
+            self.biases.append(nn.Parameter(torch.zeros(n, device=device)))
+            if l < num_layers - 1:
+                self.bn_weight.append(nn.Parameter(torch.ones(out_channels, device=device)))
+                self.bn_bias.append(nn.Parameter(torch.zeros(out_channels, device=device)))
+                self.register_buffer(f"bn_running_mean_{l}", torch.zeros(out_channels, device=device))
+                self.register_buffer(f"bn_running_var_{l}", torch.ones(out_channels, device=device))
+        self._symmetrised_init(device)
+
+    def _symmetrised_init(self, device: str) -> None:
+        """filters[0] = lift orbit, filters[l>0] = regular orbit of kaiming-uniform base weights (needs CUDA: the
+        orbit builders are kernels); on a CPU-only host the filters stay zero until loaded."""
+        if not torch.device(device).type == "cuda":
+            return
+        reflect = self.group_type == "roto-reflection"
+        g, k = self.num_group_elements, self.kernel_size
+        with torch.no_grad():
+            for l in range(self.num_layers):
+                if l == 0:
+                    base = torch.empty(self.out_channels, self.in_channels, k, k, device=device)
+                    torch.nn.init.kaiming_uniform_(base, a=math.sqrt(5))
+                    self.filters[l].copy_(ops.lift_filter_orbit(base, self.num_rotations, reflect))
+                else:
+                    base = torch.empty(self.out_channels, self.out_channels, g, k, k, device=device)
+                    torch.nn.init.kaiming_uniform_(base, a=math.sqrt(5))
+                    self.filters[l].copy_(ops.regular_filter_orbit(base, self.num_rotations, reflect))
+
+    def load_e2cnn(self, reference_network: nn.Module) -> "ESCNNEquivariantNetwork":
+        """Copy `filter` / `expanded_bias` / batch-norm statistics out of a reference ESCNNEquivariantNetwork
+        (escnn_networks.py:66-91) that was put in eval() (e2cnn fills those buffers there)."""
+        convs = [m for m in reference_network.eqv_network if hasattr(m, "expanded_bias")]
+        bns = [m for m in reference_network.eqv_network if m.__class__.__name__ == "InnerBatchNorm"]
+        if len(convs) != self.num_layers:
+            raise ValueError(f"reference network has {len(convs)} conv layers, this one {self.num_layers}")
+        with torch.no_grad():
+            for l, c in enumerate(convs):
+                self.filters[l].copy_(c.filter)
+                self.biases[l].copy_(c.expanded_bias)
+            for l, b in enumerate(bns):
+                # one torch BatchNorm3d per representation size; all fields here are regular -> a single group
+                bn = next(m for m in b.children() if hasattr(m, "running_mean"))
+                self.bn_weight[l].copy_(bn.weight)
+                self.bn_bias[l].copy_(bn.bias)
+                getattr(self, f"bn_running_mean_{l}").copy_(bn.running_mean)
+                getattr(self, f"bn_running_var_{l}").copy_(bn.running_var)
+                self.bn_eps = bn.eps
+        return self
+
+    def folded_affine(self):
+        """Per-channel (scale, shift) of every inner layer's batch norm in eval mode, expanded over the group axis."""
+        g = self.num_group_elements
+        scales, shifts = [], []
+        for l in range(self.num_layers - 1):
+            mean, var = getattr(self, f"bn_running_mean_{l}"), getattr(self, f"bn_running_var_{l}")
+            sc = self.bn_weight[l] / torch.sqrt(var + self.bn_eps)
+            scales.append(sc.repeat_interleave(g))
+            shifts.append((self.bn_bias[l] - mean * sc).repeat_interleave(g))
+        return scales, shifts
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        """(B,Cin,H,W) -> group activations (B,|G|): escnn_networks.py:93-117, one fused call per batch."""
+        if self.training:
+            raise NotImplementedError("ESCNNEquivariantNetwork on the B200 path is inference-only: call .eval() "
+                                      "(batch statistics and dropout of train mode are not implemented)")
+        scales, shifts = self.folded_affine()
+        return ops.conv_stack_forward(x, list(self.filters), list(self.biases), scales, shifts, self.num_group_elements)

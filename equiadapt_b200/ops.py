@@ -164,6 +164,50 @@ def gconv_stack_forward(x: torch.Tensor, lift_w: torch.Tensor, lift_b: Optional[
     return gconv_stack_run(x, packed, last_b, cout, k, num_rotations, reflect, n_layers)
 
 
+# ---- a7 -----------------------------------------------------------------------------------------
+def conv_stack_forward(x: torch.Tensor, filters: Sequence[torch.Tensor], biases: Sequence[Optional[torch.Tensor]],
+                       scales: Sequence[Optional[torch.Tensor]], shifts: Sequence[Optional[torch.Tensor]],
+                       num_group: int) -> torch.Tensor:
+    """x (B,Cin,H,W) -> group activations (B,|G|) through L valid k x k convs with expanded filters
+    (N, Cin_l, k, k), N = Cout*|G|; affine + ReLU after every layer but the last."""
+    dev = _need_cuda(x, *filters, *biases, *scales, *shifts)
+    x = _f32(x)
+    filters = [_f32(f) for f in filters]
+    L = len(filters)
+    if L < 1:
+        raise ValueError("at least one layer expected")
+    n, cin, k, k2 = filters[0].shape
+    if k != k2 or n % num_group or cin != x.shape[1]:
+        raise ValueError(f"first filter {tuple(filters[0].shape)} does not fit input {tuple(x.shape)} / |G| = {num_group}")
+    for f in filters[1:]:
+        if tuple(f.shape) != (n, n, k, k):
+            raise ValueError(f"inner filters must be ({n},{n},{k},{k}), got {tuple(f.shape)}")
+
+    def vecs(seq, count):
+        seq = list(seq) + [None] * (count - len(seq))
+        out = []
+        for v in seq[:count]:
+            if v is not None:
+                v = _f32(v).reshape(-1)
+                if v.numel() != n:
+                    raise ValueError(f"per-channel vectors must have {n} entries")
+            out.append(v)
+        return out
+
+    biases, scales, shifts = vecs(biases, L), vecs(scales, L), vecs(shifts, L)
+    b, _, h, w = x.shape
+    cout = n // num_group
+    nbytes = native.lib().eqb_conv_stack_workspace_bytes(b, cin, h, w, cout, k, num_group, L)
+    if nbytes < 0:
+        native.check(int(nbytes), "eqb_conv_stack_workspace_bytes")
+    ws = torch.empty((max(int(nbytes), 16),), dtype=torch.uint8, device=dev)
+    act = torch.empty((b, num_group), dtype=torch.float32, device=dev)
+    arr = lambda ts: (C.c_void_p * L)(*[_ptr(t) for t in ts])
+    _call("eqb_conv_stack_forward", 3 * L + 1, dev, _ptr(x), b, cin, h, w, arr(filters), arr(biases), arr(scales), arr(shifts),
+          cout, k, num_group, L, _ptr(act), _ptr(ws), int(nbytes), _stream(dev))
+    return act
+
+
 # ---- a9 + a13 -----------------------------------------------------------------------------------
 def group_pool_select(act: torch.Tensor, num_rotations: int, reflect: bool, want_onehot: bool = True):
     """-> idx (B) int32, rotation (B) degrees, reflection (B) or None, onehot (B,|G|) or None, stats (3)."""

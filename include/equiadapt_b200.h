@@ -81,6 +81,21 @@ EQB_API int eqb_gconv_stack_run(const float *x, int B, int cin, int H, int W, co
                                 const float *last_bias, int cout, int k, int num_rotations, int reflect,
                                 int num_layers, float *act, void *scratch, int64_t scratch_bytes, void *stream);
 
+/* ---- a7  e2cnn-style conv stack with EXPANDED filters -> group activations ------------------
+ * ESCNNEquivariantNetwork.forward in eval() (escnn_networks.py:93-117; modules built at :66-91):
+ *   [ conv2d k x k (valid) + bias -> scale * . + shift (InnerBatchNorm, eval) -> ReLU ] x (L-1)
+ *   -> conv2d k x k + bias -> reshape (B, Cout, |G|, H', W') -> mean over (Cout, H', W').
+ * filters[l]: (Cout*|G|, Cin_l, k, k) with Cin_0 = cin and Cin_l = Cout*|G| after (what e2cnn caches as
+ * R2Conv.filter); biases[l]: (Cout*|G|) (R2Conv.expanded_bias) or NULL; scales[l] / shifts[l]: per-channel affine of
+ * layer l < L-1 or NULL.  All four are HOST arrays of L device pointers (`biases`, `scales`, `shifts` may be NULL).
+ * act (B, |G|); `workspace` >= eqb_conv_stack_workspace_bytes() bytes of device scratch, 16-byte aligned. */
+EQB_API int64_t eqb_conv_stack_workspace_bytes(int B, int cin, int H, int W, int cout, int k, int num_group,
+                                               int num_layers);
+EQB_API int eqb_conv_stack_forward(const float *x, int B, int cin, int H, int W, const float *const *filters,
+                                   const float *const *biases, const float *const *scales,
+                                   const float *const *shifts, int cout, int k, int num_group, int num_layers,
+                                   float *act, void *workspace, int64_t workspace_bytes, void *stream);
+
 /* Diagnostics: the tcgen05 stack kernel bounds every pipeline wait (~2 s); if one expires the kernel traps instead of
  * hanging and leaves {flag, block, warp, barrier id, parity} here (host memory).  Returns flag (0 = no stall seen). */
 EQB_API int eqb_debug_last_stall(int *out5);

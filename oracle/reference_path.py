@@ -203,6 +203,29 @@ def custom_equivariant_network(x: torch.Tensor, layers: Sequence[Tuple[torch.Ten
     return torch.mean(x, dim=(1, 3, 4))
 
 
+def expanded_conv_network(x: torch.Tensor, filters: Sequence[torch.Tensor], biases: Sequence[Optional[torch.Tensor]],
+                          scales: Sequence[Optional[torch.Tensor]], shifts: Sequence[Optional[torch.Tensor]],
+                          num_group: int) -> torch.Tensor:
+    """ESCNNEquivariantNetwork.forward in eval(), escnn_networks.py:93-117 (modules :66-91), on the EXPANDED
+    tensors e2cnn caches: R2Conv = conv2d(filter, expanded_bias), valid padding, stride 1; InnerBatchNorm (eval) =
+    per-channel affine, equal within a field; ReLU; PointwiseDropout = identity; then
+    reshape (B, Cout, |G|, H', W') and mean over (1, 3, 4) (:107-115).  e2cnn itself is absent here: the basis
+    expansion that produces `filter` is NOT restated (parity unpinned); this restates what follows it.
+    """
+    n_layers = len(filters)
+    for li, w in enumerate(filters):
+        x = F.conv2d(x, w, None if biases[li] is None else biases[li])
+        if li < n_layers - 1:
+            if scales[li] is not None:
+                x = x * scales[li][None, :, None, None]
+            if shifts[li] is not None:
+                x = x + shifts[li][None, :, None, None]
+            x = torch.relu(x)
+    b, n = x.shape[0], x.shape[1]
+    x = x.reshape(b, n // num_group, num_group, x.shape[2], x.shape[3])
+    return torch.mean(x, dim=(1, 3, 4))
+
+
 # --------------------------------------------------------------------------------------------
 # a9  activations -> group element
 # --------------------------------------------------------------------------------------------

@@ -505,3 +505,67 @@ def test_tcgen05_stack_full_batch_properties(cuda_device):
             break
     else:
         raise AssertionError("activations of a 90-degree rotated batch are not a roll by two group positions")
+
+
+# ---------------------------------------------------------------------------------------------------
+# a7: e2cnn-style expanded-filter conv stack (conv_stack.cu) vs the oracle's dense restatement
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("group_type,n,cout,k,layers,res,b", [
+    ("rotation", 4, 32, 3, 2, 32, 3),        # the reference's own test fixture (tests/.../test_discrete_group.py:22-40)
+    ("rotation", 4, 8, 5, 3, 40, 5),         # N = 32, inner K = 800
+    ("roto-reflection", 4, 6, 3, 3, 29, 4),  # D4: N = 48 (Npad 64), odd sizes, partial tiles
+    ("rotation", 8, 32, 3, 2, 24, 2),        # N = 256
+    ("rotation", 4, 4, 3, 1, 20, 3),         # single layer: conv + pool only
+])
+def test_escnn_expanded_stack_vs_oracle(group_type, n, cout, k, layers, res, b, cuda_device):
+    from equiadapt_b200.images.canonicalization_networks.escnn_networks import ESCNNEquivariantNetwork
+    dev = cuda_device
+    g = n * (2 if group_type == "roto-reflection" else 1)
+    torch.manual_seed(30)
+    net = ESCNNEquivariantNetwork((3, res, res), cout, k, group_type, n, layers, device=str(dev)).eval()
+    with torch.no_grad():
+        for l in range(layers):
+            net.biases[l].copy_(torch.empty(cout).uniform_(-0.2, 0.2).repeat_interleave(g))
+            if l < layers - 1:
+                net.bn_weight[l].uniform_(0.5, 1.5)
+                net.bn_bias[l].uniform_(-0.3, 0.3)
+                getattr(net, f"bn_running_mean_{l}").uniform_(-0.2, 0.2)
+                getattr(net, f"bn_running_var_{l}").uniform_(0.5, 2.0)
+    x = torch.rand(b, 3, res, res, generator=torch.Generator().manual_seed(31))
+    with torch.no_grad():
+        act = net(x.to(dev)).cpu()
+        scales, shifts = net.folded_affine()
+    torch.cuda.synchronize()
+    filt = [f.detach().cpu() for f in net.filters]
+    bias = [t.detach().cpu() for t in net.biases]
+    sc, sh = [t.cpu() for t in scales] + [None], [t.cpu() for t in shifts] + [None]
+    act32 = O.expanded_conv_network(x, filt, bias, sc, sh, g)
+    dd = lambda ts: [None if t is None else t.double() for t in ts]
+    act64 = O.expanded_conv_network(x.double(), dd(filt), dd(bias), dd(sc), dd(sh), g)
+    assert act.shape == (b, g)
+    assert rel_err(act, act64) < 1e-5
+    assert rel_err(act, act32) < RTOL
+    assert_index_parity(act, act32, act64, act.argmax(-1))
+
+
+def test_escnn_network_drops_into_canonicalizer_and_is_equivariant(cuda_device):
+    """The reference's smoke test (tests/images/canonicalization/test_discrete_group.py:13-69) with its fixture
+    hyper-parameters, plus what it does not assert: C4 equivariance of the group activations."""
+    from equiadapt_b200.images.canonicalization_networks.escnn_networks import ESCNNEquivariantNetwork
+    _, GEIC, _, _ = _mods()
+    dev = cuda_device
+    torch.manual_seed(32)
+    net = ESCNNEquivariantNetwork((3, 32, 32), 32, 3, "rotation", 4, 2, device=str(dev))
+    can = GEIC(net, SimpleNamespace(beta=0.1, input_crop_ratio=0.9, resize_shape=(32, 32)), (3, 64, 64)).eval()
+    x = torch.randn(1, 3, 64, 64, generator=torch.Generator().manual_seed(33)).to(dev)
+    with torch.no_grad():
+        y = can(x)
+        assert y.shape == x.shape
+        for rep, c in (("regular", 12), ("scalar", 3)):
+            f = torch.randn(1, c, 64, 64, generator=torch.Generator().manual_seed(34)).to(dev)
+            assert can.invert_canonicalization(f, induced_rep_type=rep).shape == f.shape
+        xs = torch.rand(4, 3, 32, 32, generator=torch.Generator().manual_seed(35)).to(dev)
+        a0 = net(xs)
+        a1 = net(torch.rot90(xs, 1, (2, 3)))
+    scale = float(a0.abs().max())
+    assert min(float((a1 - torch.roll(a0, s, dims=1)).abs().max()) for s in (1, -1)) < 2e-5 * scale

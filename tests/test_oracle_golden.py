@@ -126,3 +126,18 @@ def test_rotate_closed_form_bounds_reference_noise():
     y = O.canonicalize_image(x, ang, None)
     exact_c = O.rotate_closed_form(x, -ang, clamp=True)
     assert rel_err(y, exact_c) < 1e-4
+
+
+def test_expanded_conv_restatement_agrees_with_pinned_custom_network():
+    """a7's oracle (dense ops on expanded filters) reproduces the golden-pinned a6 oracle when it is handed the
+    custom network's own filter orbits: ties the un-pinnable e2cnn path to arithmetic that IS pinned."""
+    torch.manual_seed(5)
+    n, cout, k = 4, 6, 3
+    w0, b0 = torch.randn(cout, 3, k, k) * 0.2, torch.randn(cout) * 0.1
+    w1, b1 = torch.randn(cout, cout, n, 1, 1) * 0.2, torch.randn(cout) * 0.1
+    x = torch.rand(3, 3, 20, 20)
+    ref = O.custom_equivariant_network(x, [(w0, b0), (w1, b1)], n, False)
+    filt = [O.lift_filter_orbit(w0, n, False), O.regular_filter_orbit(w1, n, False)]
+    bias = [b0.repeat_interleave(n), b1.repeat_interleave(n)]
+    got = O.expanded_conv_network(x, filt, bias, [None, None], [None, None], n)
+    assert torch.allclose(got, ref, rtol=1e-5, atol=1e-7)
