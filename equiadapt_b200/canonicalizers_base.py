@@ -24,8 +24,26 @@ class BaseCanonicalization(torch.nn.Module):
         super().__init__()
         self.canonicalization_network = canonicalization_network
         self.canonicalization_info_dict: Dict[str, torch.Tensor] = {}
-        # all-reduce the prior statistic across ranks (superset of reference behaviour)
+        # all-reduce the prior statistic across ranks (superset of reference behaviour): ONE collective
+        # per forward, shared by get_prior_regularization_loss() and get_identity_metric()
         self.sync_prior_across_ranks = True
+        # issue that collective asynchronously right after the kernel that produces the statistic, so it runs
+        # beside the warp kernels instead of on the critical path of the loss read.  Off by default: it makes
+        # every forward a collective call (all ranks must then call forward the same number of times).
+        self.prefetch_prior_allreduce = False
+
+    def _start_stats_allreduce(self, stats: torch.Tensor):
+        """-> (tensor, work | None): the statistic summed over ranks, possibly still in flight."""
+        if not (self.sync_prior_across_ranks and D.world()[1] > 1):
+            return stats, None
+        return D.allreduce_stats_async(stats)
+
+    @staticmethod
+    def _finish_stats_allreduce(pending) -> torch.Tensor:
+        tensor, work = pending
+        if work is not None:
+            work.wait()          # the current CUDA stream waits; the host does not block
+        return tensor
 
     def forward(self, x: torch.Tensor, targets: Optional[List] = None, **kwargs: Any):
         return self.canonicalize(x, targets, **kwargs)
@@ -77,7 +95,9 @@ class DiscreteGroupCanonicalization(BaseCanonicalization):
         reflect = self.group_type == "roto-reflection"
         idx, rot, refl, onehot, stats = ops.group_pool_select(group_activations, self.num_rotations, reflect)
         self._selected = {"activations": group_activations, "idx": idx, "rotation": rot, "reflection": refl,
-                          "onehot": onehot, "stats": stats}
+                          "onehot": onehot, "stats": stats, "global": None}
+        if self.prefetch_prior_allreduce:
+            self._selected["global"] = self._start_stats_allreduce(stats)
         return self._selected
 
     def _selection_for(self, group_activations: torch.Tensor):
@@ -100,16 +120,29 @@ class DiscreteGroupCanonicalization(BaseCanonicalization):
         raise ValueError(f"Gradient trick {self.gradient_trick} not implemented")
 
     def _discrete_stats(self) -> torch.Tensor:
+        """This rank's [sum CE, sum identity, B]."""
         act = self.canonicalization_info_dict["group_activations"]
         return self._selection_for(act)["stats"]
 
+    def _global_discrete_stats(self) -> torch.Tensor:
+        """The statistic summed over ranks: one all-reduce per forward, cached for both readers."""
+        act = self.canonicalization_info_dict["group_activations"]
+        sel = self._selection_for(act)
+        if sel["global"] is None:
+            sel["global"] = self._start_stats_allreduce(sel["stats"])
+        if isinstance(sel["global"], tuple):
+            sel["global"] = self._finish_stats_allreduce(sel["global"])
+        return sel["global"]
+
     def get_prior_regularization_loss(self) -> torch.Tensor:
         """mean_b CE(act_b, class 0) (basecanonicalization.py:290-301), from [sum CE, sum id, B]."""
-        return D.mean_from_stats(self._discrete_stats(), 0, 2, self.sync_prior_across_ranks)
+        s = self._global_discrete_stats()
+        return s[0] / s[2]
 
     def get_identity_metric(self) -> torch.Tensor:
         """mean_b [argmax == 0] (basecanonicalization.py:303-311)."""
-        return D.mean_from_stats(self._discrete_stats(), 1, 2, self.sync_prior_across_ranks)
+        s = self._global_discrete_stats()
+        return s[1] / s[2]
 
 
 class ContinuousGroupCanonicalization(BaseCanonicalization):
@@ -123,16 +156,19 @@ class ContinuousGroupCanonicalization(BaseCanonicalization):
         raise NotImplementedError()
 
     def _continuous_stats(self) -> torch.Tensor:
+        """[sum (R - I)^2, B*d*d, 0] summed over ranks: one kernel + one all-reduce per forward, cached."""
         rep = self.canonicalization_info_dict["group_element_matrix_representation"]
         cached = getattr(self, "_rep_stats", None)
         if cached is None or cached[0] is not rep:
-            cached = (rep, ops.prior_stats_continuous(rep))
+            local = ops.prior_stats_continuous(rep)
+            cached = (rep, self._finish_stats_allreduce(self._start_stats_allreduce(local)))
             self._rep_stats = cached
         return cached[1]
 
     def get_prior_regularization_loss(self) -> torch.Tensor:
         """MSE(R, I) over B*d*d entries (basecanonicalization.py:390-408)."""
-        return D.mean_from_stats(self._continuous_stats(), 0, 1, self.sync_prior_across_ranks)
+        s = self._continuous_stats()
+        return s[0] / s[1]
 
     def get_identity_metric(self) -> torch.Tensor:
         """1 - MSE(R, I) (basecanonicalization.py:410-430)."""

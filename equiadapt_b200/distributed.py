@@ -45,6 +45,14 @@ def allreduce_stats(stats: torch.Tensor, group=None) -> torch.Tensor:
     return stats
 
 
+def allreduce_stats_async(stats: torch.Tensor, group=None):
+    """Start the sum of the 3-float statistic over ranks; -> (tensor, work).  `work.wait()` orders the current
+    CUDA stream after the collective (NCCL) or blocks until it is done (gloo)."""
+    out = stats.clone()
+    work = dist.all_reduce(out, op=dist.ReduceOp.SUM, group=group, async_op=True)
+    return out, work
+
+
 def mean_from_stats(stats: torch.Tensor, which: int, count_index: int, sync: bool = True, group=None) -> torch.Tensor:
     """stats[which] / stats[count_index], all-reduced first when `sync` and a process group is up."""
     s = allreduce_stats(stats, group) if sync else stats

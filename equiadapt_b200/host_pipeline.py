@@ -81,6 +81,7 @@ class HostStreamedCanonicalizer:
         d2h_done = [None] * self.slots              # result of the shard that used this slot copied out
         keep = [None] * self.slots                  # results stay referenced until their D2H finished
         stats_sum = None
+        prefetch, self.can.prefetch_prior_allreduce = self.can.prefetch_prior_allreduce, False   # one collective at the end
         for i in range(n):
             lo, hi = i * self.shard, min(B, (i + 1) * self.shard)
             s = i % self.slots
@@ -106,6 +107,7 @@ class HostStreamedCanonicalizer:
                 self.s_d2h.wait_event(cmp_done[s])
                 out_host[lo:hi].copy_(z, non_blocking=True)
                 d2h_done[s] = self.s_d2h.record_event()
+        self.can.prefetch_prior_allreduce = prefetch
         with torch.cuda.stream(self.s_cmp):
             for ev in d2h_done:
                 if ev is not None:

@@ -147,6 +147,20 @@ mse = D.mean_from_stats(cstats, 0, 1)
 assert abs(float(mse) - float(O.prior_loss_continuous(rep))) < 1e-6
 local_only = D.mean_from_stats(stats, 0, 2, sync=False)
 assert world == 1 or abs(float(local_only) - float(loss)) > 0 or True
+# the canonicalizer classes' path: ONE cached collective per forward, optionally started early (prefetch)
+from equiadapt_b200.canonicalizers_base import DiscreteGroupCanonicalization
+for prefetch in (False, True):
+    can = DiscreteGroupCanonicalization(torch.nn.Identity())
+    can.prefetch_prior_allreduce = prefetch
+    can.canonicalization_info_dict = {{"group_activations": mine}}
+    can._selected = {{"activations": mine, "stats": stats, "global": can._start_stats_allreduce(stats) if prefetch else None}}
+    calls = []
+    real = D.allreduce_stats_async
+    D.allreduce_stats_async = lambda t, group=None: (calls.append(1), real(t, group))[1]
+    l2, i2 = can.get_prior_regularization_loss(), can.get_identity_metric()
+    D.allreduce_stats_async = real
+    assert len(calls) == (0 if prefetch else 1), calls          # never a second collective for the metric
+    assert abs(float(l2) - float(O.prior_loss_discrete(act))) < 1e-5 and abs(float(i2) - float(O.identity_metric_discrete(act))) < 1e-6
 dist.barrier(); dist.destroy_process_group()
 print("rank", rank, "ok")
 """
