@@ -249,6 +249,9 @@ struct StackPlan {
     // tcgen05 path (gconv_stack_tc.cu): 128-pixel tiles, its own chunking
     bool tc;
     int tc_tiles, tc_chunks, tc_tiles_per_chunk;
+    // CTA-pair kernel: 256-pixel pair-tiles
+    bool tc_pair;
+    int tc2_tiles, tc2_chunks, tc2_tiles_per_chunk;
 };
 
 static int make_plan(int B, int cin, int H, int W, int cout, int k, int N, int reflect, int L, StackPlan &p) {
@@ -291,6 +294,7 @@ static int make_plan(int B, int cin, int H, int W, int cout, int k, int N, int r
     p.off_M = off;
     off += (size_t)p.Npad * p.G * sizeof(double);
     p.tc = tc_eligible(p.N, p.K0, p.n_gemm);
+    p.tc_pair = false;
     p.off_tc = off;
     int max_chunks = p.chunks;
     if (p.tc) {
@@ -303,6 +307,11 @@ static int make_plan(int B, int cin, int H, int W, int cout, int k, int N, int r
         p.tc_tiles_per_chunk = (int)(tpc < 1 ? 1 : tpc > 8 ? 8 : tpc);
         p.tc_chunks = (p.tc_tiles + p.tc_tiles_per_chunk - 1) / p.tc_tiles_per_chunk;
         if (p.tc_chunks > max_chunks) max_chunks = p.tc_chunks;
+        p.tc_pair = tc_use_pair(p.N, p.K0);
+        p.tc2_tiles = (p.P + 255) / 256;
+        p.tc2_tiles_per_chunk = p.tc_tiles_per_chunk / 2 > 0 ? p.tc_tiles_per_chunk / 2 : 1;
+        p.tc2_chunks = (p.tc2_tiles + p.tc2_tiles_per_chunk - 1) / p.tc2_tiles_per_chunk;
+        if (p.tc2_chunks > max_chunks) max_chunks = p.tc2_chunks;
     }
     p.off_S = off;
     off += SCRATCH_HEAD;  // per-call scalars ahead of the partial sums: max |x| of the batch (tcgen05 path)
@@ -423,7 +432,8 @@ extern "C" int eqb_gconv_stack_run(const float *x, int B, int cin, int H, int W,
         e = tc_absmax(x, (size_t)B * cin * H * W, (float *)scratch, st);
         if (e) return e;
         t.tiles = p.tc_tiles; t.chunks = p.tc_chunks; t.tiles_per_chunk = p.tc_tiles_per_chunk;
-        chunks = p.tc_chunks;
+        t.tiles2 = p.tc2_tiles; t.chunks2 = p.tc2_chunks; t.tiles_per_chunk2 = p.tc2_tiles_per_chunk;
+        chunks = p.tc_pair ? p.tc2_chunks : p.tc_chunks;
         e = tc_launch(t, st);
     } else {
         switch (p.Npad / 32) {

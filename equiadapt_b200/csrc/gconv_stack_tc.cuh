@@ -14,10 +14,12 @@ struct TcArgs {
     const float *absmax;         // device scalar: max |x| over this call's batch (tc_absmax)
     double *S_part;              // [B][chunks][Npad] channel sums of the last executed layer
     int tiles, chunks, tiles_per_chunk;  // 128-pixel tiles per image, grouped into chunks (= work items)
+    int tiles2, chunks2, tiles_per_chunk2;  // the same in 256-pixel pair-tiles (CTA-pair kernel)
     int epi1_groups, lift_early;         // pipeline shape (set by tc_launch)
 };
 
 bool tc_eligible(int N, int K0, int n_gemm);
+bool tc_use_pair(int N, int K0);       // the CTA-pair kernel (cta_group::2, stationary weights) covers this shape
 size_t tc_pack_bytes(int N, int K0);
 // Wt0 [K0pad][Npad], Wt1 [Npad][Npad]: K-major fp32 operands built by the filter-orbit kernels; bias1: expanded (Npad)
 int tc_pack(const float *Wt0, int K0, const float *Wt1, const float *bias1, int Npad, int N, unsigned char *out,
