@@ -311,7 +311,7 @@ static int make_plan(int B, int cin, int H, int W, int cout, int k, int N, int r
         p.tc2_tiles = (p.P + 255) / 256;
         p.tc2_tiles_per_chunk = p.tc_tiles_per_chunk / 2 > 0 ? p.tc_tiles_per_chunk / 2 : 1;
         p.tc2_chunks = (p.tc2_tiles + p.tc2_tiles_per_chunk - 1) / p.tc2_tiles_per_chunk;
-        if (p.tc2_chunks > max_chunks) max_chunks = p.tc2_chunks;
+        if (2 * p.tc2_chunks > max_chunks) max_chunks = 2 * p.tc2_chunks;   // two partial-sum rows per chunk
     }
     p.off_S = off;
     off += SCRATCH_HEAD;  // per-call scalars ahead of the partial sums: max |x| of the batch (tcgen05 path)
@@ -433,7 +433,7 @@ extern "C" int eqb_gconv_stack_run(const float *x, int B, int cin, int H, int W,
         if (e) return e;
         t.tiles = p.tc_tiles; t.chunks = p.tc_chunks; t.tiles_per_chunk = p.tc_tiles_per_chunk;
         t.tiles2 = p.tc2_tiles; t.chunks2 = p.tc2_chunks; t.tiles_per_chunk2 = p.tc2_tiles_per_chunk;
-        chunks = p.tc_pair ? p.tc2_chunks : p.tc_chunks;
+        chunks = p.tc_pair ? 2 * p.tc2_chunks : p.tc_chunks;
         e = tc_launch(t, st);
     } else {
         switch (p.Npad / 32) {

@@ -724,8 +724,12 @@ __device__ __forceinline__ uint32_t map_to_rank(uint32_t saddr, uint32_t rank) {
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
     return r;
 }
+// Arrive on a barrier of a (possibly remote) CTA of the cluster.  Default semantics (release at CTA scope), as
+// CUTLASS's ClusterBarrier::arrive(cta_id) issues it: the data these arrivals publish is read by the tensor core
+// (async proxy) and was already pushed there by the producer's fence.proxy.async; a .release.cluster arrive makes
+// ptxas emit MEMBAR.ALL.GPU + ERRBAR per arrival (r1l profile: 24 % of the epilogue-1 warps' time).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_cluster(uint32_t bar, uint32_t parity) {
     uint32_t ok;
@@ -767,7 +771,7 @@ __device__ __forceinline__ void tc_mma2_f16_lo(uint32_t d_tmem, uint32_t a_lo, u
         : "memory");
 }
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(640, 1) gconv_stack_pair_kernel(const TcArgs a) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(768, 1) gconv_stack_pair_kernel(const TcArgs a) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const uint32_t base = smem_u32(smem_raw);
     unsigned char *sm = smem_raw;
@@ -794,7 +798,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(640, 1) gconv_stack_
         mbar_init(bar(B_D1FULL), 1);
         mbar_init(bar(B_D1EMPTY), 256 * groups);
         mbar_init(bar(B_D2FULL), 1);
-        mbar_init(bar(B_D2EMPTY), 256);
+        mbar_init(bar(B_D2EMPTY), 512);      // two epilogue-2 groups of 128 threads in each CTA
         mbar_init(bar(B_WLOAD), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         // stationary weights: this CTA's 128-channel halves of the packed hi / lo images (layout of tc_pack: a
@@ -917,7 +921,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(640, 1) gconv_stack_
                 tile_phase ^= 1u;
             }
         }
-    } else if ((warp >= 4 && warp < 8) || warp >= 16) {
+    } else if ((warp >= 4 && warp < 8) || (warp >= 16 && warp < 20)) {
         // ===== epilogue 1: this CTA's pixels of D1 -> A1 K atoms in this CTA's shared memory ====================
         const int grp = warp >= 16 ? 1 : 0;
         if (grp < groups) {
@@ -963,8 +967,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(640, 1) gconv_stack_
                 tile_phase ^= 1u;
             }
         }
-    } else if (warp >= 8 && warp < 12) {
+    } else if ((warp >= 8 && warp < 12) || (warp >= 20 && warp < 24)) {
         // ===== epilogue 2: this CTA's 128 channels of D2t -> spatial sums over the 256 pixel columns ============
+        // two groups: warps 8-11 take pixel columns [0,128), warps 20-23 columns [128,256) (the drain of D2t is on
+        // the critical path between two 1x1 GEMMs); each group emits its own partial-sum row
+        const int grp = warp >= 20 ? 1 : 0;
         const int q = warp & 3;
         const float c2 = reinterpret_cast<const float *>(sm + M.scal)[2];
         const float bv = reinterpret_cast<const float *>(sm + M.bias2)[q * 32 + lane];
@@ -977,15 +984,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(640, 1) gconv_stack_
             double dacc = 0.0;
             bool item_done = false;
             while (!item_done) {
-                const int nvalid = min(256, a.P - tw.t * 256);
+                const int nvalid = min(256, a.P - tw.t * 256) - 128 * grp;   // valid columns of this group's half
                 mbar_wait(bar(B_D2FULL), tile_phase, B_D2FULL);
                 tc_fence_after();
                 float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
+                for (int c = 0; c < 4; ++c) {
                     if (c * 32 < nvalid) {  // (uniform)
                         float v[32];
-                        tc_ld32(tmem_d2 + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+                        tc_ld32(tmem_d2 + ((uint32_t)(q * 32) << 16) + (uint32_t)(128 * grp + c * 32), v);
                         if (c * 32 + 32 <= nvalid) {
 #pragma unroll
                             for (int i = 0; i < 32; i += 4) {
@@ -1008,7 +1015,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(640, 1) gconv_stack_
                 item_done = tw.last_of_item();
                 tw.next();
             }
-            a.S_part[((size_t)b * a.chunks2 + ch) * a.Npad + chan] = dacc;
+            a.S_part[((size_t)b * (2 * a.chunks2) + 2 * ch + grp) * a.Npad + chan] = dacc;
         }
     } else if (warp >= 12 && warp < 16) {
         // ===== im2col producers: this CTA's 128 pixels of the pair-tile ============================================
@@ -1247,7 +1254,7 @@ int tc_launch(TcArgs a, cudaStream_t st) {
         }
         const int items2 = a.B * a.chunks2, max_clusters = num_sms() / 2;
         const int clusters = items2 < max_clusters ? items2 : max_clusters;
-        tc::pair::gconv_stack_pair_kernel<<<2 * clusters, a.epi1_groups == 2 ? 640 : 512, M.total, st>>>(a);
+        tc::pair::gconv_stack_pair_kernel<<<2 * clusters, 768, M.total, st>>>(a);
         return finish_launch("gconv_stack_pair_kernel");
     }
     a.epi1_groups = eg && eg[0] == '2' ? 2 : 1;
