@@ -324,7 +324,7 @@ def run_b200(args):
                          "tensor peak (" + pk["source"] + ", sustained); executed on the tensor pipe: 1.434 GFLOP/img (last "
                          "layer folded) x 3 fp16 hi/lo products = "
                          f"{3 * STACK_FLOP_EXECUTED * B / (us * 1e-6) / 1e12:.1f} TFLOP/s of kind::f16 MMA; "
-                         "call = absmax + tcgen05 stack + finish kernels")}
+                         "call = absmax + tcgen05 CTA-pair stack (cta_group::2, stationary weights) + finish kernels")}
         for name, byt in (("eqb_warp_canonicalize", IMG_BYTES), ("eqb_warp_invert", IMG_BYTES),
                           ("eqb_crop_resize_aa", (3 * 180 * 180 + 3 * 96 * 96) * 4)):
             if name in kernels:

@@ -32,11 +32,14 @@ class BaseCanonicalization(torch.nn.Module):
         # every forward a collective call (all ranks must then call forward the same number of times).
         self.prefetch_prior_allreduce = False
 
+    def _multi_rank(self) -> bool:
+        return bool(self.sync_prior_across_ranks and D.world()[1] > 1)
+
     def _start_stats_allreduce(self, stats: torch.Tensor):
-        """-> (tensor, work | None): the statistic summed over ranks, possibly still in flight."""
-        if not (self.sync_prior_across_ranks and D.world()[1] > 1):
+        """-> (tensor, work | None): the 3-float statistic summed over ranks, possibly still in flight."""
+        if not self._multi_rank():
             return stats, None
-        return D.allreduce_stats_async(stats)
+        return D.allreduce_stats_async(stats[:3])
 
     @staticmethod
     def _finish_stats_allreduce(pending) -> torch.Tensor:
@@ -137,12 +140,12 @@ class DiscreteGroupCanonicalization(BaseCanonicalization):
     def get_prior_regularization_loss(self) -> torch.Tensor:
         """mean_b CE(act_b, class 0) (basecanonicalization.py:290-301), from [sum CE, sum id, B]."""
         s = self._global_discrete_stats()
-        return s[0] / s[2]
+        return s[0] / s[2] if self._multi_rank() else s[3]   # one rank: the kernel already divided
 
     def get_identity_metric(self) -> torch.Tensor:
         """mean_b [argmax == 0] (basecanonicalization.py:303-311)."""
         s = self._global_discrete_stats()
-        return s[1] / s[2]
+        return s[1] / s[2] if self._multi_rank() else s[4]
 
 
 class ContinuousGroupCanonicalization(BaseCanonicalization):
@@ -168,7 +171,7 @@ class ContinuousGroupCanonicalization(BaseCanonicalization):
     def get_prior_regularization_loss(self) -> torch.Tensor:
         """MSE(R, I) over B*d*d entries (basecanonicalization.py:390-408)."""
         s = self._continuous_stats()
-        return s[0] / s[1]
+        return s[0] / s[1] if self._multi_rank() else s[3]
 
     def get_identity_metric(self) -> torch.Tensor:
         """1 - MSE(R, I) (basecanonicalization.py:410-430)."""

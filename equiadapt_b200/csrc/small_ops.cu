@@ -231,6 +231,8 @@ __global__ void __launch_bounds__(256) group_pool_select_kernel(const float *__r
             stats[0] = (float)c;
             stats[1] = (float)d;
             stats[2] = (float)B;
+            stats[3] = (float)(c / (double)B);   // this batch's own means: read directly when there is one rank
+            stats[4] = (float)(d / (double)B);
         } else {
             partial[2 * blockIdx.x] = c;
             partial[2 * blockIdx.x + 1] = d;
@@ -250,6 +252,13 @@ __global__ void finish_stats_kernel(const double *__restrict__ partial, int n, i
     stats[0] = (float)c;
     stats[1] = pairs == 2 ? (float)d : third;
     stats[2] = pairs == 2 ? third : 0.f;
+    if (pairs == 2) {
+        stats[3] = (float)(c / (double)third);
+        stats[4] = (float)(d / (double)third);
+    } else {
+        stats[3] = (float)(c / (double)third);
+        stats[4] = 1.f - stats[3];
+    }
 }
 
 // a12: cosine similarity to the reference vector, (|G|*B, V) -> (B,|G|).  One warp per row.
@@ -398,6 +407,8 @@ __global__ void __launch_bounds__(256) prior_stats_continuous_kernel(const float
             stats[0] = (float)c;
             stats[1] = count;
             stats[2] = 0.f;
+            stats[3] = (float)(c / (double)count);
+            stats[4] = 1.f - stats[3];
         } else {
             partial[blockIdx.x] = c;
         }

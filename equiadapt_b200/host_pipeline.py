@@ -100,7 +100,7 @@ class HostStreamedCanonicalizer:
                 f = y if self.fn is None else self.fn(y)
                 z = self.can.invert_canonicalization(f, induced_rep_type=self.rep)
                 st = self.can._discrete_stats()
-                stats_sum = st.clone() if stats_sum is None else stats_sum.add_(st)
+                stats_sum = st[:3].clone() if stats_sum is None else stats_sum.add_(st[:3])
                 cmp_done[s] = self.s_cmp.record_event()
                 keep[s] = (y, f, z)
             with torch.cuda.stream(self.s_d2h):

@@ -210,7 +210,8 @@ def conv_stack_forward(x: torch.Tensor, filters: Sequence[torch.Tensor], biases:
 
 # ---- a9 + a13 -----------------------------------------------------------------------------------
 def group_pool_select(act: torch.Tensor, num_rotations: int, reflect: bool, want_onehot: bool = True):
-    """-> idx (B) int32, rotation (B) degrees, reflection (B) or None, onehot (B,|G|) or None, stats (3)."""
+    """-> idx (B) int32, rotation (B) degrees, reflection (B) or None, onehot (B,|G|) or None,
+    stats (5) = [sum CE, sum identity, B, mean CE, mean identity]."""
     dev = _need_cuda(act)
     act = _f32(act)
     b, g = act.shape
@@ -220,7 +221,7 @@ def group_pool_select(act: torch.Tensor, num_rotations: int, reflect: bool, want
     rot = torch.empty((b,), dtype=torch.float32, device=dev)
     refl = torch.empty((b,), dtype=torch.float32, device=dev) if reflect else None
     onehot = torch.empty((b, g), dtype=torch.float32, device=dev) if want_onehot else None
-    stats = torch.empty((3,), dtype=torch.float32, device=dev)
+    stats = torch.empty((5,), dtype=torch.float32, device=dev)
     _call("eqb_group_pool_select", 1 if b <= 256 else 2, dev, _ptr(act), b, num_rotations, int(reflect), _ptr(idx),
           _ptr(rot), _ptr(refl), _ptr(onehot), _ptr(stats), _stream(dev))
     return idx, rot, refl, onehot, stats
@@ -328,13 +329,13 @@ def e3_invert(x: torch.Tensor, rot: torch.Tensor, t: torch.Tensor) -> torch.Tens
 
 
 def prior_stats_continuous(rep: torch.Tensor) -> torch.Tensor:
-    """-> stats (3) = [sum (R-I)^2, B*d*d, 0]."""
+    """-> stats (5) = [sum (R-I)^2, B*d*d, 0, mse, 1 - mse]."""
     dev = _need_cuda(rep)
     rep = _f32(rep)
     b, d, d2 = rep.shape
     if d != d2:
         raise ValueError("expected square group-element matrices")
-    stats = torch.empty((3,), dtype=torch.float32, device=dev)
+    stats = torch.empty((5,), dtype=torch.float32, device=dev)
     _call("eqb_prior_stats_continuous", 1 if b * d * d <= 256 else 2, dev, _ptr(rep), b, d, _ptr(stats), _stream(dev))
     return stats
 

@@ -102,7 +102,8 @@ EQB_API int eqb_debug_last_stall(int *out5);
 
 /* ---- a9 + a13  group pool / select + prior statistic --------------------------------------
  * act (B,|G|) -> idx int32 (B) = first arg-max, rotation (B) in degrees, reflection (B) 0/1 (may be
- * NULL), onehot (B,|G|) (may be NULL), stats[3] = { sum_b CE(act_b, class 0), sum_b [idx_b == 0], B }.
+ * NULL), onehot (B,|G|) (may be NULL), stats[5] = { sum_b CE(act_b, class 0), sum_b [idx_b == 0], B, and this
+ * batch's own means stats[0]/B, stats[1]/B } (the first three are what is all-reduced across ranks).
  * Replaces groupactivations_to_groupelementonehot (common/basecanonicalization.py:221-256, eval branch),
  * groupactivations_to_groupelement (discrete_group.py:94-135) and the two reductions of
  * get_prior_regularization_loss / get_identity_metric (basecanonicalization.py:290-311). */
@@ -148,7 +149,7 @@ EQB_API int eqb_e3_apply(const float *loc, const float *vel, const float *R, con
                  float *vel_c, int M, void *stream);
 /* y = x R + t: euclidean_group.py:126-137. */
 EQB_API int eqb_e3_invert(const float *x, const float *R, const float *t, float *y, int M, void *stream);
-/* stats[3] = { sum (R - I)^2, B*d*d, 0 } for R (B,d,d): the reductions of
+/* stats[5] = { sum (R - I)^2, B*d*d, 0, mse = stats[0]/stats[1], 1 - mse } for R (B,d,d): the reductions of
  * ContinuousGroupCanonicalization.get_prior_regularization_loss / get_identity_metric
  * (common/basecanonicalization.py:390-430). */
 EQB_API int eqb_prior_stats_continuous(const float *R, int B, int d, float *stats, void *stream);

@@ -265,6 +265,8 @@ def test_group_pool_select_vs_oracle(cuda_device):
         assert float(s[2]) == b
         assert float(s[0] / s[2]) == pytest.approx(float(O.prior_loss_discrete(act)), rel=1e-5)
         assert float(s[1] / s[2]) == pytest.approx(float(O.identity_metric_discrete(act)), rel=1e-6)
+        assert float(s[3]) == pytest.approx(float(O.prior_loss_discrete(act)), rel=1e-5)      # the kernel's own means
+        assert float(s[4]) == pytest.approx(float(O.identity_metric_discrete(act)), rel=1e-6)
 
 
 def test_frames_vs_oracle(cuda_device):
@@ -303,6 +305,8 @@ def test_frames_vs_oracle(cuda_device):
     assert rel_err(ops.e3_invert(ol.to(dev), rm.to(dev), t.to(dev)).cpu(), O.e3_invert(ol, rm, t)) < 1e-5
     s = ops.prior_stats_continuous(rm.to(dev)).cpu()
     assert float(s[0] / s[1]) == pytest.approx(float(O.prior_loss_continuous(rm)), rel=1e-5)
+    assert float(s[3]) == pytest.approx(float(O.prior_loss_continuous(rm)), rel=1e-5)
+    assert float(s[4]) == pytest.approx(float(O.identity_metric_continuous(rm)), rel=1e-5)
 
 
 def test_cosine_activations_vs_oracle(cuda_device):
@@ -439,11 +443,13 @@ def test_full_size_round_trip_properties(cuda_device):
 # ---------------------------------------------------------------------------------------------------
 # tcgen05 conv stack (gconv_stack_tc.cu) against the fp32 SIMT kernel (EQB_NO_TC=1) and the fp64 oracle
 # ---------------------------------------------------------------------------------------------------
-def _stack_act(net_cpu, x, dev, no_tc):
+def _stack_act(net_cpu, x, dev, no_tc, no_pair=False):
     import copy
     import os
     if no_tc:
         os.environ["EQB_NO_TC"] = "1"
+    if no_pair:
+        os.environ["EQB_TC_PAIR"] = "0"
     try:
         net = copy.deepcopy(net_cpu).to(dev)   # a fresh module packs its operands under the current setting
         with torch.no_grad():
@@ -452,6 +458,7 @@ def _stack_act(net_cpu, x, dev, no_tc):
         return out
     finally:
         os.environ.pop("EQB_NO_TC", None)
+        os.environ.pop("EQB_TC_PAIR", None)
 
 
 @pytest.mark.parametrize("group_type,n,cout,k,res,b", [
@@ -481,6 +488,11 @@ def test_tcgen05_stack_vs_simt_and_oracle(group_type, n, cout, k, res, b, cuda_d
     assert rel_err(act_tc, act64) < 2e-5
     assert rel_err(act_tc, act32) < RTOL
     assert_index_parity(act_tc, act32, act64, act_tc.argmax(-1))
+    if cout * n * (2 if reflect else 1) == 256 and 3 * k * k <= 80:
+        # this shape runs the CTA-pair kernel (cta_group::2) by default: pin it against the single-CTA kernel too
+        act_single = _stack_act(net, x, cuda_device, no_tc=False, no_pair=True)
+        assert rel_err(act_single, act64) < 2e-5
+        assert rel_err(act_tc, act_single) < 2e-6
 
 
 def test_tcgen05_stack_full_batch_properties(cuda_device):
