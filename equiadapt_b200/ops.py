@@ -342,3 +342,51 @@ def prior_stats_continuous(rep: torch.Tensor) -> torch.Tensor:
 
 def regular_roll_shift(r: int, num_rotations: int) -> int:
     return int(native.lib().eqb_regular_roll_shift(r, num_rotations))
+
+
+# ---- N1: frame-predicting networks ------------------------------------------------------------------
+def vnsmall_forward(x: torch.Tensor, params: torch.Tensor, n_knn: int, bn_eps: float = 1e-5) -> torch.Tensor:
+    """x (B,3,N) clouds -> (B,3,3) equivariant vectors; `params` = the flat block eqb_vnsmall_forward documents."""
+    dev = _need_cuda(x, params)
+    x, params = _f32(x), _f32(params)
+    if x.dim() != 3 or x.shape[1] != 3:
+        raise ValueError(f"expected clouds (B,3,N), got {tuple(x.shape)}")
+    if params.numel() != native.lib().eqb_vnsmall_param_count():
+        raise ValueError("parameter block has the wrong size")
+    b, _, n = x.shape
+    out = torch.empty((b, 3, 3), dtype=torch.float32, device=dev)
+    _call("eqb_vnsmall_forward", 1, dev, _ptr(x), b, n, _ptr(params), int(n_knn), float(bn_eps), _ptr(out), _stream(dev))
+    return out
+
+
+def vndeepsets_forward(loc: torch.Tensor, vel: Optional[torch.Tensor], charges: Optional[torch.Tensor], edges: torch.Tensor,
+                       params: torch.Tensor, in_dim: int, hidden: int, num_layers: int, feat_v: bool, feat_a: bool,
+                       feat_c: bool, nonlinearity: int, layer_pool_mean: bool, final_pool_mean: bool,
+                       canon_translation: bool) -> Tuple[torch.Tensor, torch.Tensor]:
+    """-> rotation vectors (M,3,3), translation (M,3) for M = 5 S particle rows."""
+    dev = _need_cuda(loc, vel, charges, edges, params)
+    loc, params = _f32(loc), _f32(params)
+    vel = None if vel is None else _f32(vel)
+    charges = None if charges is None else _f32(charges).reshape(-1)
+    m = loc.shape[0]
+    if loc.dim() != 2 or loc.shape[1] != 3 or m % 5:
+        raise ValueError(f"expected loc (5*S,3), got {tuple(loc.shape)}")
+    s = m // 5
+    if edges is None:
+        edges = torch.zeros((2, 0), dtype=torch.int64, device=dev)
+    if edges.dtype != torch.int64:
+        edges = edges.to(torch.int64)
+    if isinstance(edges, (list, tuple)):
+        edges = torch.stack(list(edges))
+    edges = edges.contiguous()
+    e = edges.shape[1]
+    lib = native.lib()
+    if params.numel() != lib.eqb_vndeepsets_param_count(in_dim, hidden, num_layers):
+        raise ValueError("parameter block has the wrong size")
+    ws = torch.empty((int(lib.eqb_vndeepsets_workspace_bytes(s)),), dtype=torch.uint8, device=dev)
+    rot = torch.empty((m, 3, 3), dtype=torch.float32, device=dev)
+    trans = torch.empty((m, 3), dtype=torch.float32, device=dev)
+    _call("eqb_vndeepsets_forward", 2, dev, _ptr(loc), _ptr(vel), _ptr(charges), _ptr(edges), e, s, _ptr(params), in_dim,
+          hidden, num_layers, int(feat_v), int(feat_a), int(feat_c), int(nonlinearity), int(layer_pool_mean),
+          int(final_pool_mean), int(canon_translation), _ptr(rot), _ptr(trans), _ptr(ws), ws.numel(), None, _stream(dev))
+    return rot, trans

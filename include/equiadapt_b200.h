@@ -154,6 +154,35 @@ EQB_API int eqb_e3_invert(const float *x, const float *R, const float *t, float 
  * (common/basecanonicalization.py:390-430). */
 EQB_API int eqb_prior_stats_continuous(const float *R, int B, int d, float *stats, void *stream);
 
+/* ---- N1  frame-predicting vector-neuron networks (eval mode) --------------------------------
+ * VNSmall.forward (pointcloud/canonicalization_networks/equivariant_networks.py:128-150; knn :15-33,
+ * get_graph_feature_cross :36-76; VNLinearLeakyReLU / VNBatchNorm vector_neuron_layers.py:210-324), pooling "mean":
+ * x (B,3,N) -> out (B,3,3), the three equivariant vectors eqb_gram_schmidt3 turns into a frame.
+ * `params`: eqb_vnsmall_param_count() floats = the raw tensors of the reference module, concatenated in the order
+ *   conv_pos.{map_to_feat.weight, map_to_dir.weight, batchnorm.bn2d.{weight, bias, running_mean, running_var}},
+ *   conv1.{map_to_feat.weight, map_to_dir.weight, batchnorm.bn1d.{...}}, bn1.bn1d.{...},
+ *   conv2.{map_to_feat.weight, map_to_dir.weight, batchnorm.bn1d.{...}};   bn_eps = the batch norms' eps. */
+EQB_API int eqb_vnsmall_param_count(void);
+EQB_API int eqb_vnsmall_forward(const float *x, int B, int N, const float *params, int n_knn, float bn_eps, float *out,
+                                void *stream);
+/* VNDeepSets.forward (nbody/canonicalization_networks/custom_equivariant_networks.py:106-172; VNDeepSetLayer
+ * :175-252; VNLeakyReLU / VNSoftplus custom_group_equivariant_layers.py:7-99) for S systems of 5 consecutive rows:
+ * loc, vel (5S,3), charges (5S) (vel / charges may be NULL when no feature uses them), edges (2,E) int64 = rows
+ * (source, destination) as the reference passes them; every edge must stay inside one system (bad_edges, if not
+ * NULL, receives the number that do not and are ignored).  Feature channels: canonical location, then velocity
+ * (feat_v), angular momentum (feat_a), charge-weighted location (feat_c) - canon_feature "p" / "pv" / "pva" /
+ * "pvc" / "pvac".  nonlinearity 0 = relu, 1 = leakyrelu(0.2), 2 = softplus.  -> rot_vectors (5S,3,3), translation (5S,3).
+ * `params`: eqb_vndeepsets_param_count() floats: per layer {identity_linear.weight, .bias, pooling_linear.weight,
+ * .bias, nonlinear_function.map_to_dir.weight}, then output_layer.{weight (4 x H), bias (4)}.
+ * `workspace` >= eqb_vndeepsets_workspace_bytes(S) bytes. */
+EQB_API int eqb_vndeepsets_param_count(int in_dim, int hidden, int num_layers);
+EQB_API int64_t eqb_vndeepsets_workspace_bytes(int S);
+EQB_API int eqb_vndeepsets_forward(const float *loc, const float *vel, const float *charges, const int64_t *edges,
+                                   int64_t E, int S, const float *params, int in_dim, int hidden, int num_layers,
+                                   int feat_v, int feat_a, int feat_c, int nonlinearity, int layer_pool_mean,
+                                   int final_pool_mean, int canon_translation, float *rot_vectors, float *translation,
+                                   void *workspace, int64_t workspace_bytes, int32_t *bad_edges, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

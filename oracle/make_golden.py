@@ -218,8 +218,68 @@ def golden_nbody():
     _save("nbody_e3", d)
 
 
+def _randomise_bn(net, g):
+    """eval-mode batch norms with non-trivial running statistics and affine parameters"""
+    for mod in net.modules():
+        if isinstance(mod, (torch.nn.BatchNorm1d, torch.nn.BatchNorm2d)):
+            n = mod.num_features
+            mod.weight.data = torch.rand(n, generator=g) * 0.8 + 0.6
+            mod.bias.data = torch.randn(n, generator=g) * 0.2
+            mod.running_mean.data = torch.rand(n, generator=g) * 0.5
+            mod.running_var.data = torch.rand(n, generator=g) * 1.5 + 0.5
+
+
+def golden_vnsmall():
+    from equiadapt.pointcloud.canonicalization_networks.equivariant_networks import VNSmall
+
+    g = torch.Generator().manual_seed(17)
+    torch.manual_seed(17)
+    net = VNSmall(_HP(n_knn=20, pooling="mean")).eval()   # equivariant_networks.py:79-150
+    _randomise_bn(net, g)
+    x = torch.randn(3, 3, 160, generator=g)
+    with torch.no_grad():
+        out = net(x)
+    d = {"x": x, "out": out, "n_knn": 20}
+    d.update({"sd." + k: v for k, v in net.state_dict().items() if "num_batches_tracked" not in k})
+    _save("vnsmall", d)
+
+
+def golden_vndeepsets():
+    from equiadapt.nbody.canonicalization_networks.custom_equivariant_networks import VNDeepSets
+
+    for tag, nonlin, feat, pool, trans, seed in (("relu_p", "relu", "p", "mean", False, 19),
+                                                 ("softplus_pvac", "softplus", "pvac", "sum", True, 23)):
+        g = torch.Generator().manual_seed(seed)
+        torch.manual_seed(seed)
+        systems = 9
+        from types import SimpleNamespace
+        hp = SimpleNamespace(out_dim=4, hidden_dim=16, layer_pooling=pool, final_pooling="mean", num_layers=4, nonlinearity=nonlin,
+                 canon_feature=feat, canon_translation=trans, angular_feature=0, dropout=0.5, batch_size=systems)
+        net = VNDeepSets(hp, device="cpu").eval()          # nbody custom_equivariant_networks.py:13-172
+        m = systems * 5
+        loc, vel = torch.randn(m, 3, generator=g), torch.randn(m, 3, generator=g)
+        charges = (torch.randint(0, 2, (m, 1), generator=g) * 2 - 1).float()
+        rows, cols = [], []                                # K5 per system, examples/nbody/model_utils.py:60-89
+        for s in range(systems):
+            for i in range(5):
+                for j in range(5):
+                    if i != j:
+                        rows.append(s * 5 + i)
+                        cols.append(s * 5 + j)
+        edges = torch.tensor([rows, cols], dtype=torch.long)
+        with torch.no_grad():
+            rv, t = net(None, loc, edges, vel, None, charges)
+        d = {"loc": loc, "vel": vel, "charges": charges, "edges": edges, "rot_vectors": rv, "translation": t}
+        d.update({"sd." + k: v for k, v in net.state_dict().items()})
+        _save("vndeepsets_" + tag, d)
+
+
 def main():
     _import_reference()
+    if "--only-vn" in sys.argv:
+        golden_vnsmall()
+        golden_vndeepsets()
+        return
     golden_gram_schmidt()
     # cfg1 of BASELINE.json (C4, 3x32x32, oc16/k5/L3, crop .9 -> 29 (offset 2), resize 32), batch cut to 4
     _image_case("image_c4_cfg1", "rotation", 4, (3, 32, 32), 4, 16, 5, 3, 0.9, 32, 1.0, seed=0)
@@ -238,6 +298,8 @@ def main():
     golden_optimized("image_opt_c8", "rotation", 8, (3, 32, 32), 3, 16, 0.9, seed=70)
     golden_pointcloud()
     golden_nbody()
+    golden_vnsmall()
+    golden_vndeepsets()
 
 
 if __name__ == "__main__":

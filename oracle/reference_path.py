@@ -462,3 +462,106 @@ def e3_canonicalize(loc: torch.Tensor, vel: torch.Tensor, rotation: torch.Tensor
 def e3_invert(x: torch.Tensor, rotation: torch.Tensor, translation: torch.Tensor) -> torch.Tensor:
     """euclidean_group.py:126-137: x R + t."""
     return torch.bmm(x[:, None, :], rotation).squeeze(1) + translation
+
+
+# --------------------------------------------------------------------------------------------
+# N1  frame-predicting vector-neuron networks (eval mode), on the reference modules' state dicts
+# --------------------------------------------------------------------------------------------
+VN_EPS = 1e-6  # vector_neuron_layers.py:13, nbody custom_group_equivariant_layers.py:4
+
+
+def _vn_batchnorm(x: torch.Tensor, sd: dict, prefix: str, bn_eps: float = 1e-5) -> torch.Tensor:
+    """VNBatchNorm in eval mode (vector_neuron_layers.py:309-322): x (B, C, 3, ...)."""
+    kind = "bn2d" if prefix + "bn2d.weight" in sd else "bn1d"
+    w, b = sd[f"{prefix}{kind}.weight"], sd[f"{prefix}{kind}.bias"]
+    rm, rv = sd[f"{prefix}{kind}.running_mean"], sd[f"{prefix}{kind}.running_var"]
+    norm = torch.norm(x, dim=2) + VN_EPS
+    norm_bn = torch.nn.functional.batch_norm(norm, rm, rv, w, b, False, 0.0, bn_eps)   # nn.BatchNorm{1,2}d in eval()
+    return x / norm.unsqueeze(2) * norm_bn.unsqueeze(2)
+
+
+def _vn_linear_leaky_relu(x: torch.Tensor, sd: dict, prefix: str, negative_slope: float = 0.0) -> torch.Tensor:
+    """VNLinearLeakyReLU.forward (vector_neuron_layers.py:253-273)."""
+    p = torch.nn.functional.linear(x.transpose(1, -1), sd[prefix + "map_to_feat.weight"]).transpose(1, -1)
+    p = _vn_batchnorm(p, sd, prefix + "batchnorm.")
+    d = torch.nn.functional.linear(x.transpose(1, -1), sd[prefix + "map_to_dir.weight"]).transpose(1, -1)
+    dotprod = (p * d).sum(2, keepdim=True)
+    mask = (dotprod >= 0).to(x.dtype)
+    d_norm_sq = (d * d).sum(2, keepdim=True)
+    return negative_slope * p + (1 - negative_slope) * (mask * p + (1 - mask) * (p - (dotprod / (d_norm_sq + VN_EPS)) * d))
+
+
+def vnsmall_forward(x: torch.Tensor, sd: dict, n_knn: int) -> torch.Tensor:
+    """VNSmall.forward, pooling "mean", eval (equivariant_networks.py:128-150; knn :15-33; get_graph_feature_cross
+    :36-76).  x (B,3,N) -> (B,3,3)."""
+    b, _, n = x.shape
+    inner = -2 * torch.matmul(x.transpose(2, 1), x)
+    xx = torch.sum(x ** 2, dim=1, keepdim=True)
+    idx = (-xx - inner - xx.transpose(2, 1)).topk(k=n_knn, dim=-1)[1]                    # (B, N, k)
+    xt = x.transpose(2, 1).contiguous()                                                   # (B, N, 3)
+    feature = torch.gather(xt.unsqueeze(1).expand(b, n, n, 3), 2, idx.unsqueeze(-1).expand(b, n, n_knn, 3))
+    feature = feature.view(b, n, n_knn, 1, 3)
+    xr = xt.view(b, n, 1, 1, 3).repeat(1, 1, n_knn, 1, 1)
+    cross = torch.cross(feature, xr, dim=-1)
+    feat = torch.cat((feature - xr, xr, cross), dim=3).permute(0, 3, 4, 1, 2).contiguous()  # (B, 3, 3, N, k)
+    out = _vn_linear_leaky_relu(feat, sd, "conv_pos.")
+    out = out.mean(dim=-1)                                                                 # mean_pool (:141)
+    out = _vn_batchnorm(_vn_linear_leaky_relu(out, sd, "conv1."), sd, "bn1.")
+    out = _vn_linear_leaky_relu(out, sd, "conv2.")
+    return out.mean(dim=-1)[:, :3]
+
+
+def _segment_reduce(src: torch.Tensor, index: torch.Tensor, n: int, reduce: str) -> torch.Tensor:
+    """torch_scatter.scatter(src, index, 0, reduce=) (third-party, absent here; unambiguous segment sum / mean)."""
+    res = torch.zeros((n,) + tuple(src.shape[1:]), dtype=src.dtype)
+    res.index_add_(0, index, src)
+    if reduce == "mean":
+        cnt = torch.zeros(n, dtype=src.dtype).index_add_(0, index, torch.ones(index.shape[0], dtype=src.dtype))
+        res = res / cnt.clamp(min=1).view((n,) + (1,) * (src.dim() - 1))
+    return res
+
+
+def vndeepsets_forward(loc: torch.Tensor, vel: torch.Tensor, charges: torch.Tensor, edges: torch.Tensor, sd: dict,
+                       num_layers: int, nonlinearity: str, canon_feature: str, layer_pooling: str, final_pooling: str,
+                       canon_translation: bool):
+    """VNDeepSets.forward, eval (nbody custom_equivariant_networks.py:106-172; VNDeepSetLayer :228-252; VNLeakyReLU /
+    VNSoftplus custom_group_equivariant_layers.py:31-52, :84-99) -> rotation vectors (M,3,3), translation (M,3)."""
+    m = loc.shape[0]
+    systems = m // 5
+    batch_indices = torch.arange(systems).reshape(-1, 1).repeat(1, 5).reshape(-1)
+    mean_loc = _segment_reduce(loc, batch_indices, systems, layer_pooling)
+    mean_loc = mean_loc.repeat(5, 1, 1).transpose(0, 1).reshape(-1, 3)
+    cl = loc - mean_loc
+    chans = [cl]
+    if "v" in canon_feature:
+        chans.append(vel)
+    if "a" in canon_feature:
+        chans.append(torch.linalg.cross(cl, vel, dim=1))
+    if "c" in canon_feature:
+        chans.append(cl * charges)
+    x = torch.stack(chans, dim=2)                                                          # (M, 3, Cin)
+    ns = 0.2 if nonlinearity == "leakyrelu" else 0.0
+    for l in range(num_layers):
+        pre = "first_set_layer." if l == 0 else f"set_layers.{l - 1}."
+        identity = torch.nn.functional.linear(x, sd[pre + "identity_linear.weight"], sd[pre + "identity_linear.bias"])
+        pooled = _segment_reduce(torch.index_select(x, 0, edges[0]), edges[1], m, layer_pooling)
+        pooling = torch.nn.functional.linear(pooled, sd[pre + "pooling_linear.weight"], sd[pre + "pooling_linear.bias"])
+        y = (identity + pooling).transpose(1, -1)                                          # (M, H, 3)
+        d = torch.nn.functional.linear(y.transpose(1, -1), sd[pre + "nonlinear_function.map_to_dir.weight"]).transpose(1, -1)
+        dotprod = (y * d).sum(2, keepdim=True)
+        if nonlinearity == "softplus":
+            ang = torch.acos(dotprod / (torch.norm(y, dim=2, keepdim=True) * torch.norm(d, dim=2, keepdim=True) + VN_EPS))
+            mask = torch.cos(ang / 2) ** 2
+        else:
+            mask = (dotprod >= 0).to(y.dtype)
+        d_norm_sq = (d * d).sum(2, keepdim=True)
+        out = ns * y + (1 - ns) * (mask * y + (1 - mask) * (y - (dotprod / (d_norm_sq + VN_EPS)) * d))
+        out = out.transpose(1, -1)
+        x = out + x if l > 0 else out
+    xs = _segment_reduce(x, batch_indices, systems, final_pooling)
+    output = torch.nn.functional.linear(xs, sd["output_layer.weight"], sd["output_layer.bias"])
+    output = output.repeat(5, 1, 1, 1).transpose(0, 1).reshape(-1, 3, 4)
+    rotation_vectors = output[:, :, :3]
+    translation = output[:, :, 3:] if canon_translation else 0.0
+    translation = translation + mean_loc[:, :, None]
+    return rotation_vectors, translation.squeeze()

@@ -581,3 +581,68 @@ def test_escnn_network_drops_into_canonicalizer_and_is_equivariant(cuda_device):
         a1 = net(torch.rot90(xs, 1, (2, 3)))
     scale = float(a0.abs().max())
     assert min(float((a1 - torch.roll(a0, s, dims=1)).abs().max()) for s in (1, -1)) < 2e-5 * scale
+
+
+# ---------------------------------------------------------------------------------------------------
+# N1: frame-predicting networks (vn_networks.cu) vs golden vectors of the unmodified reference modules
+# ---------------------------------------------------------------------------------------------------
+def _sd(g):
+    return {k[3:]: v for k, v in g.items() if k.startswith("sd.")}
+
+
+def test_vnsmall_vs_reference_golden_and_end_to_end(cuda_device):
+    from equiadapt_b200.pointcloud.canonicalization.continuous_group import EquivariantPointcloudCanonicalization
+    from equiadapt_b200.pointcloud.canonicalization_networks.equivariant_networks import VNSmall
+    g = load_golden("vnsmall")
+    dev = cuda_device
+    net = VNSmall(SimpleNamespace(n_knn=int(g["n_knn"]), pooling="mean"))
+    missing = net.load_state_dict(_sd(g), strict=False)          # the reference's own state-dict keys
+    assert not missing.unexpected_keys and all("num_batches_tracked" in k for k in missing.missing_keys)
+    net = net.to(dev).eval()
+    with torch.no_grad():
+        out = net(g["x"].to(dev)).cpu()
+    assert rel_err(out, g["out"]) < RTOL
+    # BASELINE configs[3] end to end: clouds -> VNSmall -> Gram-Schmidt -> R x, against the oracle chain
+    x = torch.randn(5, 3, 1024, generator=torch.Generator().manual_seed(40))
+    can = EquivariantPointcloudCanonicalization(net, SimpleNamespace()).eval()
+    with torch.no_grad():
+        y = can(x.to(dev)).cpu()
+    vec = O.vnsmall_forward(x, _sd(g), int(g["n_knn"]))
+    rot = O.gram_schmidt(vec)
+    assert rel_err(can.canonicalization_info_dict["group_element_matrix_representation"].cpu(), rot) < 5e-4
+    assert rel_err(y, O.so3_canonicalize(x, rot)) < 5e-4
+    # SO(3) equivariance of the predicted frame: rotating the cloud rotates the canonical cloud not at all
+    q = O.gram_schmidt(torch.randn(1, 3, 3, generator=torch.Generator().manual_seed(41)))[0]
+    if torch.det(q) < 0:
+        q[2] = -q[2]
+    with torch.no_grad():
+        y_rot = can(torch.einsum("ij,bjn->bin", q, x).to(dev)).cpu()
+    assert rel_err(y_rot, y) < 5e-4
+
+
+@pytest.mark.parametrize("tag,nonlin,feat,pool,trans", [("relu_p", "relu", "p", "mean", False),
+                                                        ("softplus_pvac", "softplus", "pvac", "sum", True)])
+def test_vndeepsets_vs_reference_golden_and_end_to_end(tag, nonlin, feat, pool, trans, cuda_device):
+    from equiadapt_b200.nbody.canonicalization.euclidean_group import EuclideanGroupNBody
+    from equiadapt_b200.nbody.canonicalization_networks.custom_equivariant_networks import VNDeepSets
+    g = load_golden("vndeepsets_" + tag)
+    dev = cuda_device
+    hp = SimpleNamespace(out_dim=4, hidden_dim=16, layer_pooling=pool, final_pooling="mean", num_layers=4, nonlinearity=nonlin,
+                         canon_feature=feat, canon_translation=trans, angular_feature=0, dropout=0.5, batch_size=9)
+    net = VNDeepSets(hp, device=str(dev))
+    net.load_state_dict(_sd(g))
+    net.eval()
+    loc, vel, ch, edges = g["loc"].to(dev), g["vel"].to(dev), g["charges"].to(dev), g["edges"].long().to(dev)
+    with torch.no_grad():
+        rv, t = net(None, loc, edges, vel, None, ch)
+    assert rel_err(rv.cpu(), g["rot_vectors"]) < RTOL
+    assert rel_err(t.cpu(), g["translation"]) < RTOL
+    # BASELINE configs[4] end to end through the canonicalizer (kwarg order as the reference's caller)
+    can = EuclideanGroupNBody(net).eval()
+    nodes = torch.sqrt(torch.sum(vel ** 2, dim=1)).unsqueeze(1)
+    with torch.no_grad():
+        cl, cv = can(nodes, None, loc=loc, edges=edges, vel=vel, edge_attr=None, charges=ch)
+    rot = O.modified_gram_schmidt(g["rot_vectors"])
+    ol, ov = O.e3_canonicalize(g["loc"], g["vel"], rot, g["translation"])
+    assert rel_err(cl.cpu(), ol) < 5e-4 and rel_err(cv.cpu(), ov) < 5e-4
+    assert torch.isfinite(can.get_prior_regularization_loss()).item()

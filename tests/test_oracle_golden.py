@@ -141,3 +141,24 @@ def test_expanded_conv_restatement_agrees_with_pinned_custom_network():
     bias = [b0.repeat_interleave(n), b1.repeat_interleave(n)]
     got = O.expanded_conv_network(x, filt, bias, [None, None], [None, None], n)
     assert torch.allclose(got, ref, rtol=1e-5, atol=1e-7)
+
+
+def _sd(g):
+    return {k[3:]: v for k, v in g.items() if k.startswith("sd.")}
+
+
+def test_vnsmall_matches_reference():
+    """N1: oracle restatement of VNSmall vs the unmodified reference module (oracle/make_golden.py::golden_vnsmall)."""
+    g = load_golden("vnsmall")
+    out = O.vnsmall_forward(g["x"], _sd(g), int(g["n_knn"]))
+    assert out.shape == (3, 3, 3)
+    assert rel_err(out, g["out"]) < 1e-5
+
+
+@pytest.mark.parametrize("tag,nonlin,feat,pool,trans", [("relu_p", "relu", "p", "mean", False),
+                                                        ("softplus_pvac", "softplus", "pvac", "sum", True)])
+def test_vndeepsets_matches_reference(tag, nonlin, feat, pool, trans):
+    g = load_golden("vndeepsets_" + tag)
+    rv, t = O.vndeepsets_forward(g["loc"], g["vel"], g["charges"], g["edges"].long(), _sd(g), 4, nonlin, feat, pool, "mean", trans)
+    assert rel_err(rv, g["rot_vectors"]) < 1e-5
+    assert rel_err(t, g["translation"]) < 1e-5
