@@ -12,6 +12,8 @@
 // Nothing but the cloud is read and nothing but 9 floats per cloud is written.
 //
 // VNDeepSets (nbody/canonicalization_networks/custom_equivariant_networks.py:13-252): see the second half of the file.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace eqb {
@@ -19,7 +21,7 @@ namespace eqb {
 constexpr int VN_C1 = 21;   // 64 // 3 hidden vector channels (fixed by the reference, equivariant_networks.py:115-118)
 constexpr int VN_C2 = 4;    // 12 // 3 output vector channels, the first 3 are used (:150)
 constexpr float VN_EPS = 1e-6f;
-constexpr int VN_THREADS = 256;
+constexpr int VN_MAX_THREADS = 512;
 
 // flat parameter block (floats), raw tensors of the reference module in this order:
 //   conv_pos: map_to_feat (21x3), map_to_dir (21x3), batchnorm.bn2d {weight, bias, running_mean, running_var} (4x21)
@@ -48,7 +50,7 @@ __device__ __forceinline__ void vn_relu(float p[3], const float d[3]) {
     }
 }
 
-template <int K>
+template <int K, int VN_THREADS>
 __global__ void __launch_bounds__(VN_THREADS, 1) vnsmall_kernel(const float *__restrict__ x, const float *__restrict__ prm,
                                                                 float *__restrict__ out, int N, int k, float bn_eps) {
     extern __shared__ __align__(16) float vsm[];
@@ -439,15 +441,23 @@ extern "C" int eqb_vnsmall_forward(const float *x, int B, int N, const float *pa
     EQB_UNSUPPORTED(n_knn > 32, "eqb_vnsmall_forward: n_knn = %d > 32 not supported by this build", n_knn);
     if (B == 0) return 0;
     EQB_REQUIRE(x && params && out, "eqb_vnsmall_forward: null pointer");
-    const size_t smem = ((size_t)4 * N + VP_TOTAL + (size_t)(n_knn == 20 ? 20 : 32) * VN_THREADS) * sizeof(float);
+    // 512 threads (128 registers, a few hundred bytes of spills) hide latency better than 256 (255 registers) when
+    // there is at most one cloud per SM; EQB_VN_THREADS=256 selects the other build
+    const char *tv = getenv("EQB_VN_THREADS");
+    const int threads = tv && atoi(tv) == 256 ? 256 : 512;
+    const size_t smem = ((size_t)4 * N + VP_TOTAL + (size_t)(n_knn == 20 ? 20 : 32) * threads) * sizeof(float);
     EQB_UNSUPPORTED(smem > 200 * 1024, "eqb_vnsmall_forward: clouds of %d points do not fit in shared memory", N);
     cudaStream_t st = (cudaStream_t)stream;
+#define EQB_VN_LAUNCH(KK, TT)                                                                                          \
+    do {                                                                                                               \
+        EQB_CUDA(cudaFuncSetAttribute(vnsmall_kernel<KK, TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
+        vnsmall_kernel<KK, TT><<<B, TT, smem, st>>>(x, params, out, N, n_knn, bn_eps);                                   \
+    } while (0)
     if (n_knn == 20) {
-        EQB_CUDA(cudaFuncSetAttribute(vnsmall_kernel<20>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        vnsmall_kernel<20><<<B, VN_THREADS, smem, st>>>(x, params, out, N, n_knn, bn_eps);
+        if (threads == 256) EQB_VN_LAUNCH(20, 256); else EQB_VN_LAUNCH(20, 512);
     } else {
-        EQB_CUDA(cudaFuncSetAttribute(vnsmall_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        vnsmall_kernel<32><<<B, VN_THREADS, smem, st>>>(x, params, out, N, n_knn, bn_eps);
+        if (threads == 256) EQB_VN_LAUNCH(32, 256); else EQB_VN_LAUNCH(32, 512);
     }
+#undef EQB_VN_LAUNCH
     return finish_launch("vnsmall_kernel");
 }
