@@ -33,9 +33,11 @@ __global__ void __launch_bounds__(THREADS) resample_kernel(const __grid_constant
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
     // ---- group element of this sample -> A ------------------------------------------------
-    int sample_s, r, mirror_src = 0, mirror_dst = 0;
-    double sign;
-    if (a.mode == MODE_ORBIT) {
+    int sample_s, r = 0, mirror_src = 0, mirror_dst = 0;
+    double sign = 1.0;
+    if (a.mode == MODE_AFFINE) {
+        sample_s = sample_d;
+    } else if (a.mode == MODE_ORBIT) {
         const int g = sample_d / a.B;
         sample_s = sample_d - g * a.B;
         r = g % a.N;
@@ -56,13 +58,30 @@ __global__ void __launch_bounds__(THREADS) resample_kernel(const __grid_constant
             sign = 1.0;
         }
     }
-    double c, s;
-    group_cs(a, r, sign, c, s);
-    // src = centre + [[c,-s],[s,c]] (u,v);  mirror_dst: u -> -u;  mirror_src: xs -> (Ws-1) - xs
-    double a00 = c, a01 = -s, a10 = s, a11 = c;
-    if (mirror_dst) { a00 = -a00; a10 = -a10; }
-    if (mirror_src) { a00 = -a00; a01 = -a01; }
-    const double cx = 0.5 * (a.Ws - 1), cy = 0.5 * (a.Hs - 1);
+    double a00, a01, a10, a11;
+    double cx = 0.5 * (a.Ws - 1), cy = 0.5 * (a.Hs - 1);
+    if (a.mode == MODE_AFFINE) {
+        const float *m = a.mats + 4 * (size_t)sample_s;
+        const double m00 = m[0], m01 = m[1], m10 = m[2], m11 = m[3];
+        if (a.mats_forward) {   // dst - c = M (src - c)  ->  src - c = M^-1 (dst - c)
+            const double det = m00 * m11 - m01 * m10;
+            a00 = m11 / det; a01 = -m01 / det; a10 = -m10 / det; a11 = m00 / det;
+        } else {
+            a00 = m00; a01 = m01; a10 = m10; a11 = m11;
+        }
+        cx = a.scx; cy = a.scy;
+        if (a.refl && a.refl[sample_s] > 0.5f) {   // the source was mirrored first: xs -> (Ws-1) - xs
+            a00 = -a00; a01 = -a01;
+            cx = (double)(a.Ws - 1) - cx;
+        }
+    } else {
+        double c, s;
+        group_cs(a, r, sign, c, s);
+        // src = centre + [[c,-s],[s,c]] (u,v);  mirror_dst: u -> -u;  mirror_src: xs -> (Ws-1) - xs
+        a00 = c; a01 = -s; a10 = s; a11 = c;
+        if (mirror_dst) { a00 = -a00; a10 = -a10; }
+        if (mirror_src) { a00 = -a00; a01 = -a01; }
+    }
 
     // ---- source footprint of the tile --------------------------------------------------------
     const int tw = min(TILE, a.Wd - tx0), th = min(TILE, a.Hd - ty0);
@@ -75,10 +94,12 @@ __global__ void __launch_bounds__(THREADS) resample_kernel(const __grid_constant
         xmin = fmin(xmin, xs); xmax = fmax(xmax, xs);
         ymin = fmin(ymin, ys); ymax = fmax(ymax, ys);
     }
+    // (a non-finite or expanding matrix cannot be a group element; its footprint is cut to the staging box)
+    if (!(xmin > -1e9 && xmax < 1e9 && ymin > -1e9 && ymax < 1e9)) { xmin = xmax = ymin = ymax = 0.0; }
     const int x_lo = min(max((int)floor(xmin), 0), a.Ws - 1);
-    const int x_hi = min(max((int)floor(xmax) + 1, 0), a.Ws - 1);
+    const int x_hi = min(min(max((int)floor(xmax) + 1, 0), a.Ws - 1), x_lo + BB - 1);
     const int y_lo = min(max((int)floor(ymin), 0), a.Hs - 1);
-    const int y_hi = min(max((int)floor(ymax) + 1, 0), a.Hs - 1);
+    const int y_hi = min(min(max((int)floor(ymax) + 1, 0), a.Hs - 1), y_lo + BB - 1);
     const int bw = x_hi - x_lo + 1, bh = y_hi - y_lo + 1;
 
     // ---- per-pixel taps (shared by all channels) --------------------------------------------
@@ -278,4 +299,21 @@ extern "C" int eqb_orbit_expand(const float *x, float *out, int B, int C, int h,
     }
     EQB_REQUIRE(B == 0 || (x && out), "eqb_orbit_expand: null pointer");
     return launch_resample(a, B * a.G, (cudaStream_t)stream, "eqb_orbit_expand");
+}
+
+// ---- N2: continuous rotations / roto-reflections of images ---------------------------------------
+extern "C" int eqb_warp_affine(const float *x, float *y, const float *mats, const float *refl, int mats_forward, int B,
+                               int C, int H, int W, int pad, double cx, double cy, void *stream) {
+    EQB_REQUIRE(B >= 0 && C > 0 && H > 0 && W > 0 && pad >= 0, "eqb_warp_affine: bad shape (%d,%d,%d,%d) / pad %d", B, C, H, W, pad);
+    EQB_REQUIRE(B == 0 || (x && y && mats), "eqb_warp_affine: null pointer");
+    ResampleArgs a{};
+    a.src = x; a.dst = y; a.idx = nullptr; a.B = B; a.C = C;
+    a.Hs = a.Hd = H; a.Ws = a.Wd = W;
+    a.N = 1; a.G = 1; a.reflect = 0;
+    a.mode = MODE_AFFINE;
+    a.mats = mats; a.refl = refl; a.mats_forward = mats_forward != 0;
+    a.pad = pad;
+    a.scx = cx; a.scy = cy;
+    a.ox = -cx; a.oy = -cy;     // destination pixel relative to the same centre
+    return launch_resample(a, B, (cudaStream_t)stream, "eqb_warp_affine");
 }

@@ -10,7 +10,7 @@ constexpr int PITCH = 49;    // odd pitch
 constexpr int THREADS = 256;
 constexpr int PIX = TILE * TILE / THREADS;  // 4 pixels per thread
 
-enum { MODE_CANON = 0, MODE_INV_SCALAR = 1, MODE_INV_REGULAR = 2, MODE_ORBIT = 3 };
+enum { MODE_CANON = 0, MODE_INV_SCALAR = 1, MODE_INV_REGULAR = 2, MODE_ORBIT = 3, MODE_AFFINE = 4 };
 
 struct ResampleArgs {
     const float *src;
@@ -29,6 +29,14 @@ struct ResampleArgs {
     // the kernels evaluate sincospi themselves
     int has_cs;
     double cs[32];
+    // MODE_AFFINE (continuous groups): per-sample 2x2 matrices instead of a group index.  mats_forward = 1: the
+    // matrix maps source to destination about the centre (warp_affine convention) and is inverted here;
+    // 0: it maps destination to source directly (affine_grid convention).  refl (may be null): per-sample 0/1,
+    // the source is mirrored first.  (scx, scy): rotation centre in source pixel coordinates.
+    const float *mats;
+    const float *refl;
+    int mats_forward;
+    double scx, scy;
 };
 
 // fills tiles_x / tiles_y / cs

@@ -108,9 +108,11 @@ __global__ void __launch_bounds__(THREADS, 6) resample_tma_kernel(const __grid_c
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         // ---- group element of this sample -> A ------------------------------------------------------
-        int sample_s, r, mirror_src = 0, mirror_dst = 0;
-        double sign;
-        if (a.mode == MODE_ORBIT) {
+        int sample_s, r = 0, mirror_src = 0, mirror_dst = 0;
+        double sign = 1.0;
+        if (a.mode == MODE_AFFINE) {
+            sample_s = sample_d;
+        } else if (a.mode == MODE_ORBIT) {
             const int g = sample_d / a.B;
             sample_s = sample_d - g * a.B;
             r = g % a.N;
@@ -129,12 +131,32 @@ __global__ void __launch_bounds__(THREADS, 6) resample_tma_kernel(const __grid_c
                 sign = 1.0;
             }
         }
-        double c, s;
-        group_cs(a, r, sign, c, s);
-        double a00 = c, a01 = -s, a10 = s, a11 = c;
-        if (mirror_dst) { a00 = -a00; a10 = -a10; }
-        if (mirror_src) { a00 = -a00; a01 = -a01; }
-        const double cx = 0.5 * (a.Ws - 1), cy = 0.5 * (a.Hs - 1);
+        double a00, a01, a10, a11;
+        double cx = 0.5 * (a.Ws - 1), cy = 0.5 * (a.Hs - 1);
+        if (a.mode == MODE_AFFINE) {   // per-sample 2x2 matrix (continuous groups), see resample.cu
+            const float *m = a.mats + 4 * (size_t)sample_s;
+            const double m00 = m[0], m01 = m[1], m10 = m[2], m11 = m[3];
+            if (a.mats_forward) {
+                const double det = m00 * m11 - m01 * m10;
+                a00 = m11 / det; a01 = -m01 / det; a10 = -m10 / det; a11 = m00 / det;
+            } else {
+                a00 = m00; a01 = m01; a10 = m10; a11 = m11;
+            }
+            cx = a.scx; cy = a.scy;
+            if (a.refl && a.refl[sample_s] > 0.5f) {
+                a00 = -a00; a01 = -a01;
+                cx = (double)(a.Ws - 1) - cx;
+            }
+        } else {
+            double c, s;
+            group_cs(a, r, sign, c, s);
+            a00 = c; a01 = -s; a10 = s; a11 = c;
+            if (mirror_dst) { a00 = -a00; a10 = -a10; }
+            if (mirror_src) { a00 = -a00; a01 = -a01; }
+        }
+        // a signed permutation matrix (quarter turns / mirrors): candidates for the exact path
+        const bool unit = (fabs(a00) == 1.0 && a01 == 0.0 && a10 == 0.0 && fabs(a11) == 1.0) ||
+                          (a00 == 0.0 && fabs(a01) == 1.0 && fabs(a10) == 1.0 && a11 == 0.0);
         // ---- source footprint of the tile ----------------------------------------------------------
         const int tw = min(TILE, a.Wd - tx0), th = min(TILE, a.Hd - ty0);
         const double u0 = (double)tx0 + a.ox, v0 = (double)ty0 + a.oy;
@@ -147,11 +169,13 @@ __global__ void __launch_bounds__(THREADS, 6) resample_tma_kernel(const __grid_c
         const int fxmin = (int)floor(xmin), fxmax = (int)floor(xmax), fymin = (int)floor(ymin), fymax = (int)floor(ymax);
         // exact tile: quarter turn (cos / sin are exact 0 / +-1 there), integral source coordinates, no clamping,
         // source tile starting on a 16-byte boundary (always true for square images whose side is a multiple of 4)
-        const bool exact = (c == 0.0 || s == 0.0) && xs_org == floor(xs_org) && ys_org == floor(ys_org) && fxmin >= 0 &&
+        // footprint of any rotation fits the 52 x 48 box; a matrix that expands the tile (not a group element) cannot
+        const bool fits = (xmax - xmin) <= 46.0 && (ymax - ymin) <= 46.0 && xmin > -1e9 && xmax < 1e9 && ymin > -1e9 && ymax < 1e9;
+        const bool exact = unit && xs_org == floor(xs_org) && ys_org == floor(ys_org) && fxmin >= 0 &&
                            fxmax <= a.Ws - 1 && fymin >= 0 && fymax <= a.Hs - 1 && (fxmin & 3) == 0;
         // interior tile: every tap, even one pixel beyond the fp64 footprint (fp32 rounding of the per-pixel
         // coordinates may floor() to the neighbour), lies inside the image -> no clamping in the pixel loop
-        const bool interior = !exact && fxmin >= 1 && fxmax + 2 <= a.Ws - 1 && fymin >= 1 && fymax + 2 <= a.Hs - 1;
+        const bool interior = !exact && fits && fxmin >= 1 && fxmax + 2 <= a.Ws - 1 && fymin >= 1 && fymax + 2 <= a.Hs - 1;
         int box_x, box_y, y_lo = 0, cx_lo = 0, cx_hi = 0, bhm1 = 0;
         if (exact) {
             box_x = fxmin; box_y = fymin;
@@ -162,8 +186,9 @@ __global__ void __launch_bounds__(THREADS, 6) resample_tma_kernel(const __grid_c
             y_lo = min(max(fymin, 0), a.Hs - 1);
             box_x = x_lo & ~3; box_y = y_lo;                               // 16-byte aligned start
             cx_lo = x_lo - box_x;                                          // taps are clamped into [cx_lo, cx_hi]
-            cx_hi = min(max(fxmax + 1, 0), a.Ws - 1) - box_x;              // <= 46 + 3
-            bhm1 = min(max(fymax + 1, 0), a.Hs - 1) - y_lo;                // <= 46
+            cx_hi = min(min(max(fxmax + 1, 0), a.Ws - 1) - box_x, BOXW - 1);   // <= 46 + 3 for a group element
+            bhm1 = min(min(max(fymax + 1, 0), a.Hs - 1) - y_lo, BOXH - 1);     // <= 46
+            cx_lo = min(cx_lo, cx_hi);
         }
         const int plane0 = sample_s * a.C;  // first source plane of this sample in the (W,H,B*C) tensor map
         if (lane == 0) {

@@ -390,3 +390,19 @@ def vndeepsets_forward(loc: torch.Tensor, vel: Optional[torch.Tensor], charges: 
           hidden, num_layers, int(feat_v), int(feat_a), int(feat_c), int(nonlinearity), int(layer_pool_mean),
           int(final_pool_mean), int(canon_translation), _ptr(rot), _ptr(trans), _ptr(ws), ws.numel(), None, _stream(dev))
     return rot, trans
+
+
+# ---- N2: continuous image warps ------------------------------------------------------------------------
+def warp_affine(x: torch.Tensor, mats: torch.Tensor, refl: Optional[torch.Tensor], mats_forward: bool, pad: int,
+                cx: float, cy: float) -> torch.Tensor:
+    """y(dst) = x sampled at c + A (dst - c); mats (B,2,2) = M with A = M^-1 (mats_forward) or A itself."""
+    dev = _need_cuda(x, mats, refl)
+    x, mats = _f32(x), _f32(mats)
+    refl = None if refl is None else _f32(refl).reshape(-1)
+    b, c, h, w = x.shape
+    if tuple(mats.shape) != (b, 2, 2) or (refl is not None and refl.numel() != b):
+        raise ValueError("one 2x2 matrix (and one reflection flag) per sample expected")
+    y = torch.empty_like(x)
+    _call("eqb_warp_affine", 1, dev, _ptr(x), _ptr(y), _ptr(mats), _ptr(refl), int(mats_forward), b, c, h, w, int(pad),
+          float(cx), float(cy), _stream(dev))
+    return y

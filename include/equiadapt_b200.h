@@ -154,6 +154,17 @@ EQB_API int eqb_e3_invert(const float *x, const float *R, const float *t, float 
  * (common/basecanonicalization.py:390-430). */
 EQB_API int eqb_prior_stats_continuous(const float *R, int B, int d, float *stats, void *stream);
 
+/* ---- N2  continuous rotations / roto-reflections of images -----------------------------------
+ * y(dst) = bilinear sample of x at  src = c + A (dst - c), taps replicate-clamped into the image while inside the
+ * extent padded by `pad` pixels and zero beyond; refl (B floats 0/1, may be NULL): the source is mirrored
+ * horizontally first.  mats (B,2,2): mats_forward = 1 -> M with dst - c = M (src - c) (kornia warp_affine's 2x2 block;
+ * A = M^-1), 0 -> A itself (F.affine_grid's theta).  (cx, cy) = c in pixel coordinates of the un-padded image.
+ * Replaces ContinuousGroupImageCanonicalization.canonicalize (images/canonicalization/continuous_group.py:162-210:
+ * flip blend, Pad(edge), K.geometry.warp_affine, CenterCrop) and the warp of
+ * OptimizedSteerableImageCanonicalization.group_augment (:362-412: Pad, affine_grid + grid_sample, CenterCrop). */
+EQB_API int eqb_warp_affine(const float *x, float *y, const float *mats, const float *refl, int mats_forward, int B,
+                            int C, int H, int W, int pad, double cx, double cy, void *stream);
+
 /* ---- N1  frame-predicting vector-neuron networks (eval mode) --------------------------------
  * VNSmall.forward (pointcloud/canonicalization_networks/equivariant_networks.py:128-150; knn :15-33,
  * get_graph_feature_cross :36-76; VNLinearLeakyReLU / VNBatchNorm vector_neuron_layers.py:210-324), pooling "mean":

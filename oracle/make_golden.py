@@ -274,8 +274,51 @@ def golden_vndeepsets():
         _save("vndeepsets_" + tag, d)
 
 
+def golden_continuous_images():
+    from equiadapt.images.canonicalization.continuous_group import (ContinuousGroupImageCanonicalization,
+                                                                    OptimizedSteerableImageCanonicalization)
+
+    for tag, shape, with_reflection, seed in (("rot", (3, 40, 40), False, 31), ("refl", (3, 36, 36), True, 33),
+                                              ("gray", (1, 28, 28), False, 35)):
+        g = torch.Generator().manual_seed(seed)
+        b = 6
+        x = smooth_images(b, *shape, seed=seed)
+        ang = torch.rand(b, generator=g) * 2 * torch.pi
+        rot = torch.stack([torch.stack([torch.cos(ang), torch.sin(ang)], 1), torch.stack([-torch.sin(ang), torch.cos(ang)], 1)], 1)
+        element = {"rotation": rot.clone()}
+        if with_reflection:
+            element["reflection"] = torch.randint(0, 2, (b, 1, 1, 1), generator=g).float()
+        hp = _HP(input_crop_ratio=0.9, resize_shape=(16, 16))
+        can = ContinuousGroupImageCanonicalization(torch.nn.Identity(), hp, shape)
+        # the reference's own test fixture mocks get_groupelement the same way (tests/.../test_continuous_group.py:94-121)
+        with mock.patch.object(can, "get_groupelement", return_value=element), torch.no_grad():
+            y = can.canonicalize(x)           # images/canonicalization/continuous_group.py:162-210
+        d = {"x": x, "rotation": rot, "y": y, "rotation_after": element["rotation"]}
+        if with_reflection:
+            d["reflection"] = element["reflection"]
+        _save("image_cont_" + tag, d)
+    for tag, group_type, seed in (("rot", "rotation", 37), ("refl", "roto-reflection", 39)):
+        shape, b = (3, 32, 32), 5
+        x = smooth_images(b, *shape, seed=seed)
+        hp = _HP(input_crop_ratio=0.9, resize_shape=(16, 16), group_type=group_type)
+        can = OptimizedSteerableImageCanonicalization(torch.nn.Identity(), hp, shape)
+        can.device = "cpu"
+        torch.manual_seed(seed)
+        with torch.no_grad():
+            aug, mats = can.group_augment(x)  # continuous_group.py:362-412
+        torch.manual_seed(seed)               # replay the reference's draws (:375, :386-388)
+        angles = torch.rand(b) * 2 * torch.pi
+        d = {"x": x, "angles": angles, "aug": aug, "mats": mats}
+        if group_type == "roto-reflection":
+            d["reflect"] = torch.randint(0, 2, (b,)).float() * 2 - 1
+        _save("image_cont_augment_" + tag, d)
+
+
 def main():
     _import_reference()
+    if "--only-cont" in sys.argv:
+        golden_continuous_images()
+        return
     if "--only-vn" in sys.argv:
         golden_vnsmall()
         golden_vndeepsets()
@@ -300,6 +343,7 @@ def main():
     golden_nbody()
     golden_vnsmall()
     golden_vndeepsets()
+    golden_continuous_images()
 
 
 if __name__ == "__main__":

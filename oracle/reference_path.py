@@ -565,3 +565,50 @@ def vndeepsets_forward(loc: torch.Tensor, vel: torch.Tensor, charges: torch.Tens
     translation = output[:, :, 3:] if canon_translation else 0.0
     translation = translation + mean_loc[:, :, None]
     return rotation_vectors, translation.squeeze()
+
+
+# --------------------------------------------------------------------------------------------
+# N2  continuous-group image canonicalization
+# --------------------------------------------------------------------------------------------
+def canonicalize_image_continuous(x: torch.Tensor, rotation_matrices: torch.Tensor,
+                                  reflection: Optional[torch.Tensor]) -> torch.Tensor:
+    """ContinuousGroupImageCanonicalization.canonicalize, images/canonicalization/continuous_group.py:162-210, given the
+    group element (rotation (B,2,2) as get_group_from_out_vectors returns it, reflection (B,1,1,1) or None).
+    Does NOT modify `rotation_matrices` (the reference negates its off-diagonal entries in place, :180)."""
+    from oracle import kornia_restated as K
+    rot = rotation_matrices.clone()
+    rot[:, [0, 1], [1, 0]] *= -1
+    if reflection is not None:
+        x = (1 - reflection) * x + reflection * K.hflip(x)
+    c, h, w = x.shape[1:]
+    if c != 1:
+        p = math.ceil(w * 0.5)
+        x = F.pad(x, (p, p, p, p), mode="replicate")
+    alpha, beta = rot[:, 0, 0], rot[:, 0, 1]
+    cx, cy = x.shape[-2] // 2, x.shape[-1] // 2
+    affine_part = torch.stack([(1 - alpha) * cx - beta * cy, beta * cx + (1 - alpha) * cy], dim=1)
+    m = torch.cat([rot, affine_part.unsqueeze(-1)], dim=-1)
+    x = K.warp_affine(x, m, dsize=(x.shape[-2], x.shape[-1]))
+    if c != 1:
+        x = center_crop(x, h, w)
+    return x
+
+
+def group_augment_continuous(x: torch.Tensor, angles: torch.Tensor, reflect: Optional[torch.Tensor]):
+    """OptimizedSteerableImageCanonicalization.group_augment, continuous_group.py:362-412, with the random draws
+    (`angles` in radians, `reflect` = +-1 or None) supplied -> (augmented images, (B,2,2) matrices)."""
+    b, c, h, w = x.shape
+    cos_a, sin_a = torch.cos(angles), torch.sin(angles)
+    rm = torch.zeros(b, 2, 3, dtype=x.dtype)
+    rm[:, :2, :2] = torch.stack((cos_a, -sin_a, sin_a, cos_a)).reshape(-1, 2, 2)
+    if reflect is not None:
+        rm[:, 0, 0] *= reflect
+    if c != 1:
+        p = math.ceil(w * 0.5)
+        x = F.pad(x, (p, p, p, p), mode="replicate")
+    grid = F.affine_grid(rm, list(x.size()), align_corners=False)
+    aug = F.grid_sample(x, grid, align_corners=False)
+    if c != 1:
+        aug = center_crop(aug, h, w)
+    rm[:, [0, 1], [1, 0]] *= -1
+    return aug, rm[:, :, :2]

@@ -646,3 +646,80 @@ def test_vndeepsets_vs_reference_golden_and_end_to_end(tag, nonlin, feat, pool, 
     ol, ov = O.e3_canonicalize(g["loc"], g["vel"], rot, g["translation"])
     assert rel_err(cl.cpu(), ol) < 5e-4 and rel_err(cv.cpu(), ov) < 5e-4
     assert torch.isfinite(can.get_prior_regularization_loss()).item()
+
+
+# ---------------------------------------------------------------------------------------------------
+# N2: continuous-group image canonicalization (eqb_warp_affine) vs goldens of the unmodified reference
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tag", ["rot", "refl", "gray"])
+def test_continuous_canonicalize_vs_reference_golden(tag, cuda_device):
+    from unittest import mock
+    from equiadapt_b200.images.canonicalization.continuous_group import ContinuousGroupImageCanonicalization
+    g = load_golden("image_cont_" + tag)
+    dev = cuda_device
+    x = g["x"]
+    can = ContinuousGroupImageCanonicalization(torch.nn.Identity(),
+                                               SimpleNamespace(input_crop_ratio=0.9, resize_shape=(16, 16)), tuple(x.shape[1:]))
+    element = {"rotation": g["rotation"].clone().to(dev)}
+    if "reflection" in g:
+        element["reflection"] = g["reflection"].to(dev)
+    with mock.patch.object(can, "get_groupelement", return_value=element), torch.no_grad():
+        y = can.canonicalize(x.to(dev))
+    assert rel_err(y.cpu(), g["y"]) < RTOL
+    assert torch.equal(element["rotation"].cpu(), g["rotation_after"])     # same in-place side effect as the reference
+    # the generic (non-TMA) kernel gives the same image
+    element2 = {k: (v.clone() if k != "rotation" else g["rotation"].clone().to(dev)) for k, v in element.items()}
+    with mock.patch.object(can, "get_groupelement", return_value=element2), torch.no_grad():
+        y2 = _no_tma(lambda: can.canonicalize(x.to(dev)))
+    assert rel_err(y2.cpu(), y.cpu()) < 1e-5
+    # pre-network transform of the class (reference test: tests/.../test_continuous_group.py:72-91)
+    if x.shape[1] != 1:
+        pre = can.transformations_before_canonicalization_network_forward(x.to(dev))
+        assert tuple(pre.shape[-2:]) == (16, 16)
+
+
+@pytest.mark.parametrize("tag,group_type", [("rot", "rotation"), ("refl", "roto-reflection")])
+def test_continuous_group_augment_vs_reference_golden(tag, group_type, cuda_device):
+    from equiadapt_b200.images.canonicalization.continuous_group import OptimizedSteerableImageCanonicalization
+    g = load_golden("image_cont_augment_" + tag)
+    dev = cuda_device
+    can = OptimizedSteerableImageCanonicalization(
+        torch.nn.Identity(), SimpleNamespace(input_crop_ratio=0.9, resize_shape=(16, 16), group_type=group_type), (3, 32, 32))
+    refl = g["reflect"].to(dev) if "reflect" in g else None
+    with torch.no_grad():
+        aug, mats = can.group_augment(g["x"].to(dev), angles=g["angles"].to(dev), reflect=refl)
+    assert rel_err(aug.cpu(), g["aug"]) < RTOL
+    assert rel_err(mats.cpu(), g["mats"]) < 1e-6
+
+
+def test_steerable_canonicalizer_end_to_end(cuda_device):
+    """SteerableImageCanonicalization with a stand-in network (the reference's e2cnn steerable network is out of scope):
+    canonicalize == oracle chain, prior loss / identity metric == a14, and the full-size batch is rotation-consistent."""
+    from equiadapt_b200.images.canonicalization.continuous_group import SteerableImageCanonicalization
+    dev = cuda_device
+
+    class Net(torch.nn.Module):
+        group_type = "rotation"
+
+        def forward(self, x):   # two 2-vectors per sample from image moments (any deterministic function will do)
+            m = x.mean(dim=(1,))
+            gx = (m[:, :, 1:] - m[:, :, :-1]).mean(dim=(1, 2))
+            gy = (m[:, 1:, :] - m[:, :-1, :]).mean(dim=(1, 2))
+            v = torch.stack([gx + 0.3, gy - 0.2], dim=1)
+            return torch.stack([v, v.flip(1)], dim=1)
+
+    can = SteerableImageCanonicalization(Net(), SimpleNamespace(input_crop_ratio=0.8, resize_shape=(32, 32)), (3, 64, 64)).eval()
+    x = torch.rand(7, 3, 64, 64, generator=torch.Generator().manual_seed(50))
+    with torch.no_grad():
+        y = can(x.to(dev))
+        rep = can.canonicalization_info_dict["group_element_matrix_representation"].cpu()
+        loss, ident = float(can.get_prior_regularization_loss()), float(can.get_identity_metric())
+    vec = Net()(O.pre_network_transform(x, (3, 64, 64), 0.8, (32, 32)))[:, 0]
+    v1 = vec / vec.norm(dim=1, keepdim=True)
+    rot = torch.stack([v1, torch.stack([-v1[:, 1], v1[:, 0]], 1)], 1)
+    assert rel_err(y.cpu(), O.canonicalize_image_continuous(x, rot, None)) < 5e-4   # the stand-in net runs in torch on both sides
+    neg = rot.clone()
+    neg[:, [0, 1], [1, 0]] *= -1
+    assert abs(loss - float(O.prior_loss_continuous(neg))) < 1e-4 and abs(ident - (1 - loss)) < 1e-6
+    with pytest.raises(NotImplementedError):
+        can.invert_canonicalization(y)

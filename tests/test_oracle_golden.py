@@ -162,3 +162,21 @@ def test_vndeepsets_matches_reference(tag, nonlin, feat, pool, trans):
     rv, t = O.vndeepsets_forward(g["loc"], g["vel"], g["charges"], g["edges"].long(), _sd(g), 4, nonlin, feat, pool, "mean", trans)
     assert rel_err(rv, g["rot_vectors"]) < 1e-5
     assert rel_err(t, g["translation"]) < 1e-5
+
+
+@pytest.mark.parametrize("tag", ["rot", "refl", "gray"])
+def test_continuous_canonicalize_matches_reference(tag):
+    """N2: restated canonicalize (continuous_group.py:162-210) vs the unmodified reference class."""
+    g = load_golden("image_cont_" + tag)
+    y = O.canonicalize_image_continuous(g["x"], g["rotation"], g.get("reflection"))
+    assert rel_err(y, g["y"]) < TOL
+    neg = g["rotation"].clone()
+    neg[:, [0, 1], [1, 0]] *= -1
+    assert torch.equal(neg, g["rotation_after"])      # the reference's in-place sign flip
+
+
+@pytest.mark.parametrize("tag", ["rot", "refl"])
+def test_continuous_group_augment_matches_reference(tag):
+    g = load_golden("image_cont_augment_" + tag)
+    aug, mats = O.group_augment_continuous(g["x"], g["angles"], g.get("reflect"))
+    assert rel_err(aug, g["aug"]) < TOL and rel_err(mats, g["mats"]) < TOL
