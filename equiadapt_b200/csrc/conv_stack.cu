@@ -13,6 +13,8 @@
 // This is the first correct CUDA path for a7: fp32 SIMT, 64-pixel x Npad tiles, 8 x NT register blocks, K streamed
 // in chunks of 16 (weights by cp.async, the im2col chunk gathered one chunk ahead into registers so the global
 // latency hides behind the FMAs).  A tcgen05 variant along the lines of gconv_stack_tc.cu is the planned successor.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace eqb {
@@ -198,11 +200,88 @@ __global__ void conv_pool_finish_kernel(const double *__restrict__ S_part, int c
     act[(size_t)b * G + g] = (float)(s * inv_count);
 }
 
+// ---- the last layer is linear and followed only by the mean: fold it through the pool ------------------------------
+//   mean_{o,y,x} (W * in + b)[(o,g)] = sum_{c,ky,kx} Wfold[g][c][ky][kx] * S[c][ky][kx] / (Cout * P) + mean_o b[(o,g)]
+//   S[c][ky][kx]   = sum of in[c] over the window [ky, ky + Ho) x [kx, kx + Wo)      (k x k shifted box sums)
+//   Wfold[g][...]  = sum_o W[(o,g)][c][ky][kx]
+// so the last conv (half of the FLOPs of the reference's default 3-layer network) is never executed.
+// One block per (image, input channel): the plane is staged in shared memory, row window sums by a sliding sum per
+// row, then k*k column window sums; fp64 throughout.
+__global__ void __launch_bounds__(128) conv_window_sums_kernel(const float *__restrict__ in, int C, int H, int W, int k,
+                                                               double *__restrict__ S) {
+    extern __shared__ __align__(16) unsigned char wsm[];
+    float *plane = reinterpret_cast<float *>(wsm);                                            // [H][W]
+    double *rows = reinterpret_cast<double *>(wsm + (((size_t)H * W * sizeof(float) + 7) & ~(size_t)7));   // [H][k]
+    const int bc = blockIdx.x, Ho = H - k + 1, Wo = W - k + 1;
+    const float *src = in + (size_t)bc * H * W;
+    for (int i = threadIdx.x; i < H * W; i += blockDim.x) plane[i] = src[i];
+    __syncthreads();
+    for (int y = threadIdx.x; y < H; y += blockDim.x) {
+        const float *r = plane + (size_t)y * W;
+        double s = 0.0;
+        for (int x = 0; x < Wo; ++x) s += (double)r[x];
+        rows[y * k] = s;
+        for (int kx = 1; kx < k; ++kx) {
+            s += (double)r[kx + Wo - 1] - (double)r[kx - 1];
+            rows[y * k + kx] = s;
+        }
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < k * k; t += blockDim.x) {
+        const int ky = t / k, kx = t - ky * k;
+        double s = 0.0;
+        for (int y = ky; y < ky + Ho; ++y) s += rows[y * k + kx];
+        S[(size_t)bc * k * k + t] = s;
+    }
+}
+
+// Wfold[g][kk] = sum_o w[(o*G+g)][kk], kk over (c, ky, kx);  bmean[g] = mean_o bias[o*G+g]
+__global__ void conv_fold_weights_kernel(const float *__restrict__ w, const float *__restrict__ bias, int cout, int G, int K,
+                                         double *__restrict__ Wfold, double *__restrict__ bmean) {
+    const int total = G * K;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+        const int g = t / K, kk = t - g * K;
+        double s = 0.0;
+        for (int o = 0; o < cout; ++o) s += (double)w[(size_t)(o * G + g) * K + kk];
+        Wfold[t] = s;
+    }
+    if (blockIdx.x == 0 && (int)threadIdx.x < G) {
+        double s = 0.0;
+        if (bias)
+            for (int o = 0; o < cout; ++o) s += (double)bias[o * G + threadIdx.x];
+        bmean[threadIdx.x] = s / (double)cout;
+    }
+}
+
+// act[b][g] = Wfold[g] . S[b] * inv_count + bmean[g]; one block per image
+__global__ void __launch_bounds__(256) conv_fold_apply_kernel(const double *__restrict__ S, const double *__restrict__ Wfold,
+                                                              const double *__restrict__ bmean, int K, int G, double inv_count,
+                                                              float *__restrict__ act) {
+    __shared__ double red[8];
+    const int b = blockIdx.x;
+    const double *Sb = S + (size_t)b * K;
+    for (int g = 0; g < G; ++g) {
+        double v = 0.0;
+        for (int kk = threadIdx.x; kk < K; kk += blockDim.x) v += Sb[kk] * Wfold[(size_t)g * K + kk];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double t = 0.0;
+            for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+            act[(size_t)b * G + g] = (float)(t * inv_count + bmean[g]);
+        }
+        __syncthreads();
+    }
+}
+
 struct ConvPlan {
     int N, Npad, P[16], Ho[16], Wo[16], cin[16], K[16], Kpad[16];
     int tiles, chunks, tiles_per_chunk;   // of the pooled (last) layer
-    size_t off_wt[16], off_vec[16], off_buf[2], off_S, total;
+    size_t off_wt[16], off_vec[16], off_buf[2], off_S, off_fold, off_bmean, off_win, total;
     size_t smem[16];
+    bool fold;             // last layer folded through the pool (its input plane fits the window-sum kernel's staging)
+    size_t win_smem;
 };
 
 static int conv_make_plan(int B, int cin, int H, int W, int cout, int k, int G, int L, ConvPlan &p) {
@@ -238,6 +317,14 @@ static int conv_make_plan(int B, int cin, int H, int W, int cout, int k, int G, 
     p.tiles_per_chunk = (p.tiles + chunks - 1) / chunks;
     p.chunks = (p.tiles + p.tiles_per_chunk - 1) / p.tiles_per_chunk;
     p.off_S = off; off += (size_t)(B > 0 ? B : 1) * p.chunks * p.Npad * sizeof(double);
+    // fold of the last layer: input plane (H_in x W_in of layer L-1) staged in shared memory
+    const int Hin = p.Ho[L - 1] + k - 1, Win = p.Wo[L - 1] + k - 1;
+    p.win_smem = (((size_t)Hin * Win * sizeof(float) + 7) & ~(size_t)7) + (size_t)Hin * k * sizeof(double);
+    p.fold = p.win_smem <= 200 * 1024 && !getenv("EQB_CONV_NO_FOLD");
+    off = (off + 255) & ~(size_t)255;
+    p.off_fold = off; off += (size_t)G * p.K[L - 1] * sizeof(double);
+    p.off_bmean = off; off += 64 * sizeof(double);
+    p.off_win = off; off += (size_t)(B > 0 ? B : 1) * p.K[L - 1] * sizeof(double);
     p.total = off;
     return 0;
 }
@@ -281,6 +368,17 @@ extern "C" int eqb_conv_stack_forward(const float *x, int B, int cin, int H, int
     int h = H, w = W;
     for (int l = 0; l < L; ++l) {
         EQB_REQUIRE(filters[l], "eqb_conv_stack_forward: null filter for layer %d", l);
+        if (l == L - 1 && p.fold) {
+            // `in` = input of the last layer, (B, cin_l, h, w) fp32
+            const int Kl = p.K[l];
+            double *Wfold = (double *)(ws + p.off_fold), *bmean = (double *)(ws + p.off_bmean), *Swin = (double *)(ws + p.off_win);
+            conv_fold_weights_kernel<<<64, 256, 0, st>>>(filters[l], biases ? biases[l] : nullptr, cout, num_group, Kl, Wfold, bmean);
+            EQB_CUDA(cudaFuncSetAttribute(conv_window_sums_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            conv_window_sums_kernel<<<(unsigned)(B * p.cin[l]), 128, p.win_smem, st>>>(in, p.cin[l], h, w, k, Swin);
+            const double inv = 1.0 / ((double)cout * (double)p.P[l]);
+            conv_fold_apply_kernel<<<B, 256, 0, st>>>(Swin, Wfold, bmean, Kl, num_group, inv, act);
+            return finish_launch("conv_fold_apply_kernel");
+        }
         float *Wt = (float *)(ws + p.off_wt[l]), *vec = (float *)(ws + p.off_vec[l]);
         conv_pack_kernel<<<64, 256, 0, st>>>(filters[l], Wt, p.N, p.K[l], p.Kpad[l], p.Npad);
         const bool last = l == L - 1;
