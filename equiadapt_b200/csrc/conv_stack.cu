@@ -16,6 +16,8 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "conv_stack_tc.cuh"
+#include "gconv_stack_tc.cuh"
 
 namespace eqb {
 
@@ -32,6 +34,8 @@ struct ConvArgs {
     const float *scale;    // [Npad] (1 when no affine)
     const float *shift;    // [Npad]
     double *S_part;        // [B][chunks][Npad] (pooled layer)
+    __half *y_hi, *y_lo;   // (B, Ho, Wo, Npad) fp16 hi / lo pair of s_out * value (input of a tcgen05 layer), or null
+    const float *lay;      // device layer record (LAY_SOUT) when y_hi is set
     int B, cin, H, W, ksz, Ho, Wo, P, K, Kpad, N, Npad, relu;
     int tiles, chunks, tiles_per_chunk;
 };
@@ -135,6 +139,7 @@ __global__ void __launch_bounds__(CV_THREADS, 2) conv_layer_kernel(const ConvArg
         }
 
         // ---- epilogue -----------------------------------------------------------------------------------
+        const float s_out = a.y_hi ? a.lay[LAY_SOUT] : 1.f;
 #pragma unroll
         for (int j = 0; j < NT; ++j) {
             const int n = j * 32 + tx;
@@ -146,7 +151,13 @@ __global__ void __launch_bounds__(CV_THREADS, 2) conv_layer_kernel(const ConvArg
                 if (a.relu) v = fmaxf(v, 0.f);
                 const int p = p0 + ty * 8 + i;
                 if (p < a.P) {
-                    if (a.y) {
+                    if (a.y_hi) {   // NHWC: the 32 lanes of a warp write 32 consecutive channels of one pixel
+                        const float vs = v * s_out;
+                        const __half hi = __float2half_rn(vs);
+                        const size_t o = ((size_t)b * a.P + p) * a.Npad + n;
+                        a.y_hi[o] = hi;
+                        a.y_lo[o] = __float2half_rn(vs - __half2float(hi));
+                    } else if (a.y) {
                         if (n < a.N) a.y[((size_t)b * a.N + n) * a.P + p] = v;
                     } else {
                         s += v;
@@ -157,7 +168,7 @@ __global__ void __launch_bounds__(CV_THREADS, 2) conv_layer_kernel(const ConvArg
         }
     }
 
-    if (!a.y) {
+    if (!a.y && !a.y_hi) {
         __syncthreads();
         double *red = reinterpret_cast<double *>(sm);  // [8][Npad] doubles <= the two weight buffers
 #pragma unroll
@@ -282,6 +293,9 @@ struct ConvPlan {
     size_t smem[16];
     bool fold;             // last layer folded through the pool (its input plane fits the window-sum kernel's staging)
     size_t win_smem;
+    // tcgen05 inner layers (conv_stack_tc.cu): fp16 hi/lo NHWC ping-pong buffers, packed weights, layer records
+    bool tc;
+    size_t off_h[2][2], off_wp[16], off_lay, off_absmax;
 };
 
 static int conv_make_plan(int B, int cin, int H, int W, int cout, int k, int G, int L, ConvPlan &p) {
@@ -325,6 +339,24 @@ static int conv_make_plan(int B, int cin, int H, int W, int cout, int k, int G, 
     p.off_fold = off; off += (size_t)G * p.K[L - 1] * sizeof(double);
     p.off_bmean = off; off += 64 * sizeof(double);
     p.off_win = off; off += (size_t)(B > 0 ? B : 1) * p.K[L - 1] * sizeof(double);
+    p.tc = p.fold && ctc_eligible(p.Npad, L);
+    for (int l = 1; l <= L - 2; ++l)   // every tcgen05 layer's input must hold at least one 16 x 8 TMA box
+        if (p.Ho[l - 1] < 8 || p.Wo[l - 1] < 16) p.tc = false;
+    if (p.tc) {
+        off = (off + 1023) & ~(size_t)1023;
+        const size_t hbytes = (((size_t)(B > 0 ? B : 1) * p.P[0] * p.Npad * sizeof(__half)) + 1023) & ~(size_t)1023;
+        for (int i = 0; i < 2; ++i)
+            for (int j = 0; j < 2; ++j) {
+                p.off_h[i][j] = off;
+                off += (i == 0 || L > 3) ? hbytes : 0;
+            }
+        for (int l = 1; l <= L - 2; ++l) {
+            p.off_wp[l] = off;
+            off += (ctc_pack_bytes(p.Npad, p.N, k) + 1023) & ~(size_t)1023;
+        }
+        p.off_lay = off; off += (size_t)(L + 1) * LAY_FLOATS * sizeof(float);
+        p.off_absmax = off; off += 64;
+    }
     p.total = off;
     return 0;
 }
@@ -366,8 +398,36 @@ extern "C" int eqb_conv_stack_forward(const float *x, int B, int cin, int H, int
     const int L = num_layers;
     const float *in = x;
     int h = H, w = W;
+    float *lay = p.tc ? (float *)(ws + p.off_lay) : nullptr;
+    const __half *tin_hi = nullptr, *tin_lo = nullptr;   // fp16 pair feeding the next tcgen05 layer
+    if (p.tc) {
+        // operand scales are chained on the device from max |x| (conv_stack_tc.cu)
+        int e = tc_absmax(x, (size_t)B * cin * H * W, (float *)(ws + p.off_absmax), st);
+        if (e) return e;
+    }
     for (int l = 0; l < L; ++l) {
         EQB_REQUIRE(filters[l], "eqb_conv_stack_forward: null filter for layer %d", l);
+        if (p.tc && l >= 1 && l <= L - 2) {
+            // ---- inner layer on the tensor cores: fp16 hi/lo NHWC in, fp16 pair or (last inner layer) fp32 NCHW out ----
+            float *vec = (float *)(ws + p.off_vec[l]);
+            conv_vec_kernel<<<1, 256, 0, st>>>(biases ? biases[l] : nullptr, scales ? scales[l] : nullptr,
+                                               shifts ? shifts[l] : nullptr, vec, p.N, p.Npad);
+            float *lay_l = lay + (size_t)l * LAY_FLOATS;
+            int e = ctc_layer_stats(filters[l], vec, p.N, p.Npad, p.K[l], lay_l + LAY_INBOUND, 1, lay_l, lay_l + LAY_FLOATS, st);
+            if (e) return e;
+            unsigned char *wp = (unsigned char *)(ws + p.off_wp[l]);
+            e = ctc_pack(filters[l], lay_l, p.N, p.N, k, p.Npad, wp, st);
+            if (e) return e;
+            const bool last_inner = l == L - 2;
+            float *out32 = last_inner ? (float *)(ws + p.off_buf[0]) : nullptr;
+            __half *oh = last_inner ? nullptr : (__half *)(ws + p.off_h[l & 1][0]);
+            __half *ol = last_inner ? nullptr : (__half *)(ws + p.off_h[l & 1][1]);
+            e = ctc_conv_layer(tin_hi, tin_lo, B, p.Npad, h, w, k, wp, vec, lay_l, p.N, p.Npad, 1, out32, oh, ol, p.Npad, st);
+            if (e) return e;
+            in = out32; tin_hi = oh; tin_lo = ol;
+            h = p.Ho[l]; w = p.Wo[l];
+            continue;
+        }
         if (l == L - 1 && p.fold) {
             // `in` = input of the last layer, (B, cin_l, h, w) fp32
             const int Kl = p.K[l];
@@ -385,6 +445,14 @@ extern "C" int eqb_conv_stack_forward(const float *x, int B, int cin, int H, int
         conv_vec_kernel<<<1, 256, 0, st>>>(biases ? biases[l] : nullptr, (!last && scales) ? scales[l] : nullptr,
                                            (!last && shifts) ? shifts[l] : nullptr, vec, p.N, p.Npad);
         ConvArgs a{};
+        if (p.tc && l == 0) {
+            // layer 0 (K = Cin*k*k is tiny) stays on the SIMT kernel but emits the fp16 pair the tensor layer reads
+            float *lay0 = lay;
+            int e = ctc_layer_stats(filters[0], vec, p.N, p.Npad, p.K[0], (const float *)(ws + p.off_absmax), 0, lay0,
+                                    lay0 + LAY_FLOATS, st);
+            if (e) return e;
+            a.y_hi = (__half *)(ws + p.off_h[0][0]); a.y_lo = (__half *)(ws + p.off_h[0][1]); a.lay = lay0;
+        }
         a.x = in; a.B = B; a.cin = p.cin[l]; a.H = h; a.W = w; a.ksz = k; a.Ho = p.Ho[l]; a.Wo = p.Wo[l]; a.P = p.P[l];
         a.K = p.K[l]; a.Kpad = p.Kpad[l]; a.N = p.N; a.Npad = p.Npad; a.relu = !last;
         a.Wt = Wt; a.bias = vec; a.scale = vec + p.Npad; a.shift = vec + 2 * p.Npad;
@@ -392,7 +460,7 @@ extern "C" int eqb_conv_stack_forward(const float *x, int B, int cin, int H, int
             a.y = nullptr; a.S_part = (double *)(ws + p.off_S);
             a.tiles = p.tiles; a.chunks = p.chunks; a.tiles_per_chunk = p.tiles_per_chunk;
         } else {
-            a.y = (float *)(ws + p.off_buf[l & 1]); a.S_part = nullptr;
+            a.y = a.y_hi ? nullptr : (float *)(ws + p.off_buf[l & 1]); a.S_part = nullptr;
             a.tiles = (p.P[l] + CV_TM - 1) / CV_TM;
             const int target = num_sms() * 2 * 4;
             int chunks = (target + B - 1) / B;
@@ -408,7 +476,7 @@ extern "C" int eqb_conv_stack_forward(const float *x, int B, int cin, int H, int
             default: e = conv_launch<8>(a, p.smem[l], st); break;
         }
         if (e) return e;
-        in = a.y;
+        in = a.y; tin_hi = a.y_hi; tin_lo = a.y_lo;
         h = p.Ho[l]; w = p.Wo[l];
     }
     const double inv_count = 1.0 / ((double)cout * (double)p.P[L - 1]);

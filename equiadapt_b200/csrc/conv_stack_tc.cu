@@ -1,0 +1,443 @@
+// a7 on the tensor cores: the INNER layers of the e2cnn-style conv stack (conv_stack.cu) as a tcgen05 implicit GEMM.
+//
+//   out[b, n, oy, ox] = relu( scale_n * ( sum_{c,ky,kx} W[n,c,ky,kx] * in[b, c, oy+ky, ox+kx] + bias_n ) + shift_n )
+//   M = 128 output pixels (an 8 x 16 patch of one image), N = Cout*|G| (padded to 32..256), K = Cin * k * k.
+//
+// Activations travel between layers as two fp16 tensors in NHWC (hi / lo halves of the power-of-two scaled fp32 value,
+// the same 22-bit split as gconv_stack_tc.cu), so the A operand of every (ky, kx, 32-channel) K atom is ONE TMA box:
+//   cp.async.bulk.tensor.4d over (C, W, H, B), box 32 x 16 x 8 x 1, SWIZZLE_64B
+// which lands exactly as the 128-row K-major SWIZZLE_64B tile the UMMA descriptor expects (rows = patch pixels,
+// 64 bytes = 32 channels); the (ky, kx) shift is just the box origin, image borders are TMA zero fill.  Weights are
+// pre-packed per atom as hi / lo UMMA images and streamed by cp.async.bulk.  Each product is a_hi*w_hi + a_lo*w_hi +
+// a_hi*w_lo (three kind::f16 MMAs, fp32 accumulation in TMEM).  Two accumulators (2 x Npad columns) let the epilogue
+// of tile t overlap the main loop of tile t+1.
+//   warp 0  producer (one lane): 2 TMA boxes + 1 bulk weight copy per stage, mbarrier tx-count
+//   warp 1  MMA issuer (elected lane)      warp 2  TMEM allocator      warps 4-7  epilogue
+// The epilogue undoes the operand scales, applies bias / folded batch norm / ReLU and writes either the next layer's
+// NHWC fp16 hi / lo pair or (for the layer that feeds the folded last layer) fp32 NCHW.
+// Operand scales (exact powers of two) are chained on the device from max|x| and the weights' absolute row sums
+// (ctc_layer_stats_kernel), no host synchronisation.
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "conv_stack_tc.cuh"
+
+namespace eqb {
+namespace ctc {
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// bounded wait (~2 s): a pipeline bug traps instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (mbar_try(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try(bar, parity))
+        if (clock64() - t0 > 4000000000LL) __trap();
+}
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+constexpr uint32_t DESC_HI_64B = (512u >> 4) | (1u << 14) | (4u << 29);
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr) { return ((saddr & 0x3FFFFu) >> 4) | (1u << 16); }
+__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        ".reg .b64 da, db;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "mov.b64 da, {%1, %5};\n"
+        "mov.b64 db, {%2, %5};\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "n"(DESC_HI_64B)
+        : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n"
+        ".reg .b32 rx;\n"
+        ".reg .pred px;\n"
+        "elect.sync rx|px, %1;\n"
+        "@px mov.s32 %0, 1;\n"
+        "}\n"
+        : "+r"(pred)
+        : "r"(0xFFFFFFFFu));
+    return pred != 0;
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, float *v) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void split2(float x0, float x1, uint32_t &hi, uint32_t &lo) {
+    const __half2 h = __floats2half2_rn(x0, x1);
+    const float2 hf = __half22float2(h);
+    const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+    hi = *reinterpret_cast<const uint32_t *>(&h);
+    lo = *reinterpret_cast<const uint32_t *>(&l);
+}
+__host__ __device__ __forceinline__ float pow2_scale(float m) {
+    if (!(m > 0.f) || !(m < 3.0e38f)) return 1.f;
+    int e;
+    frexpf(m, &e);
+    return ldexpf(1.f, 14 - e);
+}
+
+constexpr int THREADS = 256;
+constexpr int A_HALF = 128 * 64;          // one 128-pixel x 32-channel fp16 box: 8 KB
+constexpr int MAX_STAGES = 8;
+
+struct Args {
+    const unsigned char *wpack;            // [atoms][hi: Npad x 64 B | lo: Npad x 64 B]
+    const float *bias, *scale, *shift;     // [Npad] (scale 1 / shift 0 when the layer has no affine)
+    const float *lay;                      // device: layer record (see LAY_*)
+    float *out_nchw;                       // (B, N, Ho, Wo) fp32, or null
+    __half *out_hi, *out_lo;               // (B, Ho, Wo, Cpad_out) fp16 pair, or null
+    int B, k, Ho, Wo, N, Npad, catoms, atoms, tiles_x, tiles_y, tiles, relu, Cpad_out, stages;
+};
+
+__global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap map_hi,
+                                                             const __grid_constant__ CUtensorMap map_lo, const Args a) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    const uint32_t base = smem_u32(smem_raw);
+    if ((base & 1023u) != 0) __trap();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t stage_bytes = 2u * A_HALF + (uint32_t)a.Npad * 128u;
+    const uint32_t misc = base + (uint32_t)a.stages * stage_bytes;          // barriers, TMEM slot, per-channel vectors
+    auto full = [&](int s) { return misc + 8u * (uint32_t)s; };
+    auto empty = [&](int s) { return misc + 8u * (uint32_t)(MAX_STAGES + s); };
+    auto accfull = [&](int b) { return misc + 8u * (uint32_t)(2 * MAX_STAGES + b); };
+    auto accempty = [&](int b) { return misc + 8u * (uint32_t)(2 * MAX_STAGES + 2 + b); };
+    const uint32_t tmem_slot = misc + 8u * (2 * MAX_STAGES + 4);
+    float *vec = reinterpret_cast<float *>(smem_raw + (misc - base) + 8 * (2 * MAX_STAGES + 4) + 16);   // [3][Npad]
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < a.stages; ++s) {
+            mbar_init(full(s), 1);
+            mbar_init(empty(s), 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(accfull(b), 1);
+            mbar_init(accempty(b), 128);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int n = threadIdx.x; n < a.Npad; n += THREADS) {
+        vec[n] = a.bias[n];
+        vec[a.Npad + n] = a.scale[n];
+        vec[2 * a.Npad + n] = a.shift[n];
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *reinterpret_cast<volatile uint32_t *>(smem_raw + (tmem_slot - base));
+    const int per_img = a.tiles_x * a.tiles_y;
+
+    if (warp == 0) {
+        // ===== producer ==========================================================================================
+        if (lane == 0) {
+            int s = 0;
+            uint32_t ph = 0;
+            for (int tile = blockIdx.x; tile < a.tiles; tile += gridDim.x) {
+                const int b = tile / per_img, r = tile - b * per_img, ty = r / a.tiles_x, tx = r - ty * a.tiles_x;
+                const int oy0 = ty * 8, ox0 = tx * 16;
+                int atom = 0;
+                for (int ky = 0; ky < a.k; ++ky)
+                    for (int kx = 0; kx < a.k; ++kx)
+                        for (int ca = 0; ca < a.catoms; ++ca, ++atom) {
+                            mbar_wait(empty(s), ph ^ 1u);
+                            mbar_expect_tx(full(s), stage_bytes);
+                            const uint32_t dst = base + (uint32_t)s * stage_bytes;
+                            tma_load_4d(dst, &map_hi, full(s), ca * 32, ox0 + kx, oy0 + ky, b);
+                            tma_load_4d(dst + A_HALF, &map_lo, full(s), ca * 32, ox0 + kx, oy0 + ky, b);
+                            bulk_load(dst + 2 * A_HALF, a.wpack + (size_t)atom * a.Npad * 128, (uint32_t)a.Npad * 128u, full(s));
+                            if (++s == a.stages) { s = 0; ph ^= 1u; }
+                        }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer ========================================================================================
+        const uint32_t idesc = (1u << 4) | ((uint32_t)(a.Npad >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        int s = 0;
+        uint32_t ph = 0, accph[2] = {0, 0};
+        int buf = 0;
+        for (int tile = blockIdx.x; tile < a.tiles; tile += gridDim.x) {
+            mbar_wait(accempty(buf), accph[buf] ^ 1u);      // the epilogue has drained this accumulator
+            tc_fence_after();
+            const uint32_t d = tmem + (uint32_t)(buf * a.Npad);
+            for (int atom = 0; atom < a.atoms; ++atom) {
+                mbar_wait(full(s), ph);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t st = base + (uint32_t)s * stage_bytes;
+                    const uint32_t a_hi = desc_lo(st), a_lo = desc_lo(st + A_HALF);
+                    const uint32_t w_hi = desc_lo(st + 2 * A_HALF), w_lo = desc_lo(st + 2 * A_HALF + (uint32_t)a.Npad * 64u);
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) tc_mma(d, a_hi + 2 * j, w_hi + 2 * j, idesc, (atom | j) != 0);
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) tc_mma(d, a_lo + 2 * j, w_hi + 2 * j, idesc, 1);
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) tc_mma(d, a_hi + 2 * j, w_lo + 2 * j, idesc, 1);
+                    tc_commit(empty(s));
+                    if (atom == a.atoms - 1) tc_commit(accfull(buf));
+                }
+                __syncwarp();
+                if (++s == a.stages) { s = 0; ph ^= 1u; }
+            }
+            accph[buf] ^= 1u;
+            buf ^= 1;
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue ==========================================================================================
+        const int q = warp & 3, row = q * 32 + lane, py = row >> 4, px = row & 15;
+        const float cinv = a.lay[LAY_CINV], s_out = a.lay[LAY_SOUT];
+        uint32_t accph[2] = {0, 0};
+        int buf = 0;
+        for (int tile = blockIdx.x; tile < a.tiles; tile += gridDim.x) {
+            const int b = tile / per_img, r = tile - b * per_img, ty = r / a.tiles_x, tx = r - ty * a.tiles_x;
+            const int oy = ty * 8 + py, ox = tx * 16 + px;
+            const bool valid = oy < a.Ho && ox < a.Wo;
+            mbar_wait(accfull(buf), accph[buf]);
+            tc_fence_after();
+            for (int c = 0; c < a.Npad / 32; ++c) {
+                float v[32];
+                tc_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * a.Npad + c * 32), v);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const int n = c * 32 + i;
+                    float y = fmaf(fmaf(v[i], cinv, vec[n]), vec[a.Npad + n], vec[2 * a.Npad + n]);
+                    v[i] = a.relu ? fmaxf(y, 0.f) : y;
+                }
+                if (valid) {
+                    if (a.out_nchw) {
+                        float *o = a.out_nchw + (((size_t)b * a.N + c * 32) * a.Ho + oy) * a.Wo + ox;
+                        const size_t plane = (size_t)a.Ho * a.Wo;
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            if (c * 32 + i < a.N) o[(size_t)i * plane] = v[i];
+                    } else {
+                        const size_t off = (((size_t)b * a.Ho + oy) * a.Wo + ox) * a.Cpad_out + c * 32;
+                        uint32_t hi[16], lo[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) split2(v[2 * i] * s_out, v[2 * i + 1] * s_out, hi[i], lo[i]);
+                        uint4 *ph4 = reinterpret_cast<uint4 *>(a.out_hi + off), *pl4 = reinterpret_cast<uint4 *>(a.out_lo + off);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            ph4[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+                            pl4[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(accempty(buf));
+            accph[buf] ^= 1u;
+            buf ^= 1;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+    }
+}
+
+// One layer's operand scales and output bound, chained on the device (lay = this layer's record, nxt = the next one's).
+//   in_bound = *in_bound_ptr;  s_in = pow2(in_bound);  sw = pow2(max |W|);  cinv = 1 / (s_in * sw)
+//   out_bound = max_n ( |scale_n| (in_bound * sum_k |W[n,k]| + |bias_n|) + |shift_n| );  s_out = pow2(out_bound)
+__global__ void __launch_bounds__(256) ctc_layer_stats_kernel(const float *__restrict__ w, const float *__restrict__ vecs, int N,
+                                                              int Npad, int K, const float *__restrict__ in_bound_ptr,
+                                                              int tensor_in, float *__restrict__ lay, float *__restrict__ nxt) {
+    __shared__ float red[2][256];
+    const float in_bound = *in_bound_ptr;
+    float wmax = 0.f, ob = 0.f;
+    for (int n = threadIdx.x; n < N; n += blockDim.x) {
+        float rs = 0.f;
+        for (int kk = 0; kk < K; ++kk) {
+            const float v = fabsf(w[(size_t)n * K + kk]);
+            wmax = fmaxf(wmax, v);
+            rs += v;
+        }
+        const float o = fabsf(vecs[Npad + n]) * (in_bound * rs * 1.0001f + fabsf(vecs[n])) + fabsf(vecs[2 * Npad + n]);
+        ob = fmaxf(ob, o);
+    }
+    red[0][threadIdx.x] = wmax; red[1][threadIdx.x] = ob;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) {
+            red[0][threadIdx.x] = fmaxf(red[0][threadIdx.x], red[0][threadIdx.x + o]);
+            red[1][threadIdx.x] = fmaxf(red[1][threadIdx.x], red[1][threadIdx.x + o]);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const float s_in = tensor_in ? pow2_scale(in_bound) : 1.f, sw = tensor_in ? pow2_scale(red[0][0]) : 1.f;
+        const float out_bound = red[1][0] * 1.0001f, s_out = pow2_scale(out_bound);
+        lay[LAY_INBOUND] = in_bound; lay[LAY_SIN] = s_in; lay[LAY_SW] = sw; lay[LAY_CINV] = 1.f / (s_in * sw);
+        lay[LAY_OUTBOUND] = out_bound; lay[LAY_SOUT] = s_out;
+        nxt[LAY_INBOUND] = out_bound;
+    }
+}
+
+// filter (N, C, k, k) fp32 -> per atom (ky, kx, 32-channel group) an Npad x 64-byte hi image followed by the lo image,
+// SWIZZLE_64B (16-byte chunk index XOR ((n >> 1) & 3)), scaled by sw; rows >= N and channels >= C are zero
+__global__ void ctc_pack_kernel(const float *__restrict__ w, const float *__restrict__ lay, int N, int C, int k, int Npad,
+                                int catoms, unsigned char *__restrict__ out) {
+    const float sw = lay[LAY_SW];
+    const long long total = (long long)k * k * catoms * Npad * 32;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int ks = (int)(t % 32), n = (int)((t / 32) % Npad);
+        const int atom = (int)(t / (32LL * Npad));
+        const int ca = atom % catoms, kk = atom / catoms, ky = kk / k, kx = kk - ky * k;
+        const int c = ca * 32 + ks;
+        const float v = (n < N && c < C) ? w[(((size_t)n * C + c) * k + ky) * k + kx] * sw : 0.f;
+        const __half hi = __float2half_rn(v), lo = __float2half_rn(v - __half2float(hi));
+        const size_t stage = (size_t)Npad * 128;
+        const size_t off = (size_t)n * 64 + (size_t)((((ks >> 3) ^ ((n >> 1) & 3)) << 4) | ((ks & 7) << 1));
+        *reinterpret_cast<__half *>(out + (size_t)atom * stage + off) = hi;
+        *reinterpret_cast<__half *>(out + (size_t)atom * stage + (size_t)Npad * 64 + off) = lo;
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        (void)cudaGetLastError();
+        return (EncodeTiledFn)p;
+    }();
+    return fn;
+}
+// (C, W, H, B) fp16 NHWC tensor, box 32 x 16 x 8 x 1, SWIZZLE_64B
+static int make_act_map(CUtensorMap *m, const void *ptr, int Cpad, int W, int H, int B) {
+    EncodeTiledFn enc = encode_fn();
+    if (!enc) {
+        set_error("cuTensorMapEncodeTiled is not available from the CUDA driver");
+        return (int)cudaErrorNotSupported;
+    }
+    const cuuint64_t gdim[4] = {(cuuint64_t)Cpad, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    const cuuint64_t gstride[3] = {(cuuint64_t)Cpad * 2, (cuuint64_t)W * Cpad * 2, (cuuint64_t)H * W * Cpad * 2};
+    const cuuint32_t box[4] = {32, 16, 8, 1}, estr[4] = {1, 1, 1, 1};
+    const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void *>(ptr), gdim, gstride, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed with CUresult %d (C=%d W=%d H=%d B=%d)", (int)r, Cpad, W, H, B);
+        return (int)cudaErrorInvalidValue;
+    }
+    return 0;
+}
+
+}  // namespace ctc
+
+bool ctc_eligible(int Npad, int num_layers) {
+    if (getenv("EQB_CONV_NO_TC")) return false;
+    return num_layers >= 3 && Npad >= 32 && Npad <= 256;
+}
+
+size_t ctc_pack_bytes(int Npad, int C, int k) { return (size_t)k * k * ((C + 31) / 32) * Npad * 128; }
+
+int ctc_layer_stats(const float *w, const float *vecs, int N, int Npad, int K, const float *in_bound_ptr, int tensor_in,
+                    float *lay, float *nxt, cudaStream_t st) {
+    ctc::ctc_layer_stats_kernel<<<1, 256, 0, st>>>(w, vecs, N, Npad, K, in_bound_ptr, tensor_in, lay, nxt);
+    return finish_launch("ctc_layer_stats_kernel");
+}
+
+int ctc_pack(const float *w, const float *lay, int N, int C, int k, int Npad, unsigned char *out, cudaStream_t st) {
+    ctc::ctc_pack_kernel<<<256, 256, 0, st>>>(w, lay, N, C, k, Npad, (C + 31) / 32, out);
+    return finish_launch("ctc_pack_kernel");
+}
+
+int ctc_conv_layer(const __half *in_hi, const __half *in_lo, int B, int Cpad, int H, int W, int k, const unsigned char *wpack,
+                   const float *vecs, const float *lay, int N, int Npad, int relu, float *out_nchw, __half *out_hi,
+                   __half *out_lo, int Cpad_out, cudaStream_t st) {
+    CUtensorMap mh, ml;
+    int e = ctc::make_act_map(&mh, in_hi, Cpad, W, H, B);
+    if (e) return e;
+    e = ctc::make_act_map(&ml, in_lo, Cpad, W, H, B);
+    if (e) return e;
+    ctc::Args a{};
+    a.wpack = wpack; a.bias = vecs; a.scale = vecs + Npad; a.shift = vecs + 2 * Npad; a.lay = lay;
+    a.out_nchw = out_nchw; a.out_hi = out_hi; a.out_lo = out_lo;
+    a.B = B; a.k = k; a.Ho = H - k + 1; a.Wo = W - k + 1; a.N = N; a.Npad = Npad;
+    a.catoms = Cpad / 32; a.atoms = k * k * a.catoms;
+    a.tiles_x = (a.Wo + 15) / 16; a.tiles_y = (a.Ho + 7) / 8; a.tiles = B * a.tiles_x * a.tiles_y;
+    a.relu = relu; a.Cpad_out = Cpad_out;
+    const size_t stage = 2 * (size_t)ctc::A_HALF + (size_t)Npad * 128;
+    const size_t misc = 8 * (2 * ctc::MAX_STAGES + 4) + 16 + 3 * (size_t)Npad * sizeof(float);
+    int stages = (int)((227 * 1024 - misc) / stage);
+    if (stages > ctc::MAX_STAGES) stages = ctc::MAX_STAGES;
+    EQB_UNSUPPORTED(stages < 2, "eqb_conv_stack (tcgen05): stage of %zu bytes does not fit twice", stage);
+    a.stages = stages;
+    const size_t smem = (size_t)stages * stage + misc;
+    static bool configured = false;
+    if (!configured) {
+        EQB_CUDA(cudaFuncSetAttribute(ctc::conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        configured = true;
+    }
+    if (a.tiles == 0) return 0;
+    const int grid = a.tiles < num_sms() ? a.tiles : num_sms();
+    ctc::conv_tc_kernel<<<grid, ctc::THREADS, smem, st>>>(mh, ml, a);
+    return finish_launch("conv_tc_kernel");
+}
+
+}  // namespace eqb

@@ -523,6 +523,9 @@ def test_tcgen05_stack_full_batch_properties(cuda_device):
 # a7: e2cnn-style expanded-filter conv stack (conv_stack.cu) vs the oracle's dense restatement
 # ---------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("group_type,n,cout,k,layers,res,b", [
+    ("rotation", 4, 32, 5, 3, 44, 3),        # the example config's network (N = 128, inner K = 3200): tcgen05 inner layer
+    ("rotation", 4, 8, 3, 4, 36, 4),         # 4 layers: two tcgen05 layers, fp16-pair hand-over between them
+    ("rotation", 8, 32, 3, 3, 30, 2),        # N = 256 on the tensor path
     ("rotation", 4, 32, 3, 2, 32, 3),        # the reference's own test fixture (tests/.../test_discrete_group.py:22-40)
     ("rotation", 4, 8, 5, 3, 40, 5),         # N = 32, inner K = 800
     ("roto-reflection", 4, 6, 3, 3, 29, 4),  # D4: N = 48 (Npad 64), odd sizes, partial tiles
@@ -555,9 +558,22 @@ def test_escnn_expanded_stack_vs_oracle(group_type, n, cout, k, layers, res, b, 
     dd = lambda ts: [None if t is None else t.double() for t in ts]
     act64 = O.expanded_conv_network(x.double(), dd(filt), dd(bias), dd(sc), dd(sh), g)
     assert act.shape == (b, g)
-    assert rel_err(act, act64) < 1e-5
+    # inner layers on the tensor cores (L >= 3): TMEM accumulation truncates, the error grows with K = Cin*k*k
+    # (1.4e-5 at K = 3200); SIMT fp32 FMA chains stay below 1e-5
+    assert rel_err(act, act64) < (3e-5 if layers >= 3 else 1e-5)
     assert rel_err(act, act32) < RTOL
     assert_index_parity(act, act32, act64, act.argmax(-1))
+    # the all-SIMT path (no tcgen05 inner layers, no fold) computes the same activations
+    import os
+    os.environ["EQB_CONV_NO_TC"] = "1"
+    os.environ["EQB_CONV_NO_FOLD"] = "1"
+    try:
+        with torch.no_grad():
+            act_simt = net(x.to(dev)).cpu()
+        torch.cuda.synchronize()
+    finally:
+        del os.environ["EQB_CONV_NO_TC"], os.environ["EQB_CONV_NO_FOLD"]
+    assert rel_err(act_simt, act64) < 1e-5 and rel_err(act, act_simt) < 3e-5
 
 
 def test_escnn_network_drops_into_canonicalizer_and_is_equivariant(cuda_device):
