@@ -739,3 +739,61 @@ def test_steerable_canonicalizer_end_to_end(cuda_device):
     assert abs(loss - float(O.prior_loss_continuous(neg))) < 1e-4 and abs(ident - (1 - loss)) < 1e-6
     with pytest.raises(NotImplementedError):
         can.invert_canonicalization(y)
+
+
+# ---------------------------------------------------------------------------------------------------
+# stream / graph behaviour of the public path
+# ---------------------------------------------------------------------------------------------------
+def test_step_is_cuda_graph_capturable(cuda_device):
+    """canonicalize + invert + prior statistic enqueue kernels only (no host synchronisation, no allocation outside
+    torch's allocator), so a step can be captured once and replayed on new data in the same buffers."""
+    _, GEIC, _, Net = _mods()
+    dev = cuda_device
+    torch.manual_seed(60)
+    net = Net((3, 32, 32), 8, 5, "rotation", 8, 3, device="cpu").to(dev)
+    can = GEIC(net, SimpleNamespace(beta=1.0, input_crop_ratio=0.8, resize_shape=32), (3, 64, 64)).eval()
+    gen = torch.Generator().manual_seed(61)
+    x0, x1 = torch.rand(16, 3, 64, 64, generator=gen), torch.rand(16, 3, 64, 64, generator=gen)
+    xs = x0.to(dev).clone()
+
+    def step():
+        y = can(xs)
+        z = can.invert_canonicalization(y, induced_rep_type="scalar")
+        return y, z, can.get_prior_regularization_loss(), can.get_identity_metric()
+
+    with torch.no_grad():
+        s = torch.cuda.Stream(dev)
+        s.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(s):
+            for _ in range(2):
+                step()                                   # warm-up: packs the parameters, sizes the allocator pools
+        torch.cuda.current_stream(dev).wait_stream(s)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            y, z, loss, ident = step()
+        xs.copy_(x1.to(dev))
+        graph.replay()
+        torch.cuda.synchronize()
+        got = (y.clone(), z.clone(), float(loss), float(ident))
+        ref = step()
+        torch.cuda.synchronize()
+    assert torch.equal(got[0], ref[0]) and torch.equal(got[1], ref[1])
+    assert got[2] == float(ref[2]) and got[3] == float(ref[3])
+
+
+def test_empty_batches_of_the_network_entry_points(cuda_device):
+    from equiadapt_b200.images.canonicalization_networks.escnn_networks import ESCNNEquivariantNetwork
+    from equiadapt_b200.pointcloud.canonicalization_networks.equivariant_networks import VNSmall
+    ops = _mods()[0]
+    dev = cuda_device
+    net = ESCNNEquivariantNetwork((3, 20, 20), 4, 3, "rotation", 4, 2, device=str(dev)).eval()
+    vn = VNSmall(SimpleNamespace(n_knn=20, pooling="mean")).to(dev).eval()
+    with torch.no_grad():
+        assert net(torch.empty(0, 3, 20, 20, device=dev)).shape == (0, 4)
+        assert vn(torch.empty(0, 3, 64, device=dev)).shape == (0, 3, 3)
+        assert ops.warp_affine(torch.empty(0, 3, 56, 56, device=dev), torch.empty(0, 2, 2, device=dev), None, True, 28, 28.0, 28.0).shape == (0, 3, 56, 56)
+    with pytest.raises(ValueError):
+        vn(torch.rand(2, 3, 8, device=dev))              # fewer points than n_knn
+    with pytest.raises(NotImplementedError):
+        net.train()(torch.rand(1, 3, 20, 20, device=dev))
