@@ -265,7 +265,7 @@ __global__ void __launch_bounds__(THREADS, 6) resample_tma_kernel(const __grid_c
                 const float fx = xr - xf, fy = yr - yf;
                 const int x0 = (int)xf, y0 = (int)yf;
                 float wx0 = 1.f - fx, wx1 = fx, wy0 = 1.f - fy, wy1 = fy;
-                if (ZERO) {
+                if (ZERO && !interior) {   // (every tap of an interior tile lies inside the image: nothing to zero)
                     // absolute tap coordinates against the padded extent [-pad, size-1+pad]
                     const int ax0 = x0 + geo.box_x, ay0 = y0 + geo.y_lo;
                     const int lo = -a.pad, hx = a.Ws - 1 + a.pad, hy = a.Hs - 1 + a.pad;
