@@ -797,3 +797,33 @@ def test_empty_batches_of_the_network_entry_points(cuda_device):
         vn(torch.rand(2, 3, 8, device=dev))              # fewer points than n_knn
     with pytest.raises(NotImplementedError):
         net.train()(torch.rand(1, 3, 20, 20, device=dev))
+
+
+def test_cfg2_index_parity_on_smooth_images(cuda_device):
+    """SURVEY.md section 7 (hard part 1): the headline parity run - BASELINE configs[1] network and image size, 32 smooth
+    non-zero-mean images (wide arg-max margins).  The discrete index must equal the fp64 oracle's on every sample
+    whose margin exceeds the combined fp32 noise, and our agreement with fp64 must not be worse than the fp32
+    reference's own."""
+    _, GEIC, _, Net = _mods()
+    dev = cuda_device
+    torch.manual_seed(0)
+    net = Net((3, 96, 96), 32, 5, "rotation", 8, 3, device="cpu")
+    lay = [(m.weights.detach().clone(), m.bias.detach().clone()) for m in net.eqv_network if hasattr(m, "weights")]
+    can = GEIC(net.to(dev), SimpleNamespace(beta=1.0, input_crop_ratio=0.8, resize_shape=96), (3, 224, 224)).eval()
+    g = torch.Generator().manual_seed(7)
+    low = torch.randn(32, 3, 14, 14, generator=g)
+    x = torch.nn.functional.interpolate(low, size=(224, 224), mode="bicubic", align_corners=False) + 0.5
+    with torch.no_grad():
+        y = can(x.to(dev))
+    act = can.canonicalization_info_dict["group_activations"].cpu()
+    idx = can.canonicalization_info_dict["group_element"].index.cpu().long()
+    act32 = O.custom_equivariant_network(O.pre_network_transform(x, (3, 224, 224), 0.8, 96), lay, 8, False)
+    act64 = O.custom_equivariant_network(O.pre_network_transform(x.double(), (3, 224, 224), 0.8, 96),
+                                         [(w.double(), b.double()) for w, b in lay], 8, False)
+    assert rel_err(act, act64) < 2e-5
+    assert_index_parity(act, act32, act64, idx)
+    agree_ours = int((idx == act64.argmax(-1)).sum())
+    agree_ref = int((act32.argmax(-1) == act64.argmax(-1)).sum())
+    assert agree_ours >= agree_ref
+    ang = torch.linspace(0.0, 360.0, 9)[:8][idx]
+    assert rel_err(y.cpu(), O.canonicalize_image(x, ang, None)) < RTOL
