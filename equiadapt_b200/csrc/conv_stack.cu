@@ -216,32 +216,42 @@ __global__ void conv_pool_finish_kernel(const double *__restrict__ S_part, int c
 //   S[c][ky][kx]   = sum of in[c] over the window [ky, ky + Ho) x [kx, kx + Wo)      (k x k shifted box sums)
 //   Wfold[g][...]  = sum_o W[(o,g)][c][ky][kx]
 // so the last conv (half of the FLOPs of the reference's default 3-layer network) is never executed.
-// One block per (image, input channel): the plane is staged in shared memory, row window sums by a sliding sum per
-// row, then k*k column window sums; fp64 throughout.
-__global__ void __launch_bounds__(128) conv_window_sums_kernel(const float *__restrict__ in, int C, int H, int W, int k,
+// One block per (image, input channel), one thread per COLUMN: thread x streams in[0..H)[x] (row-contiguous across the
+// block -> coalesced, all loads independent), keeps the column total in fp64 and turns it into the k vertical window
+// sums by removing the leading / trailing k-1 elements (re-read, L1 hits); k*k threads then add the columns of their
+// horizontal window.  HBM-bound: one read of the plane.
+__global__ void __launch_bounds__(256) conv_window_sums_kernel(const float *__restrict__ in, int C, int H, int W, int k,
                                                                double *__restrict__ S) {
     extern __shared__ __align__(16) unsigned char wsm[];
-    float *plane = reinterpret_cast<float *>(wsm);                                            // [H][W]
-    double *rows = reinterpret_cast<double *>(wsm + (((size_t)H * W * sizeof(float) + 7) & ~(size_t)7));   // [H][k]
+    double *cols = reinterpret_cast<double *>(wsm);     // [k][W]  vertical window sums per column
     const int bc = blockIdx.x, Ho = H - k + 1, Wo = W - k + 1;
     const float *src = in + (size_t)bc * H * W;
-    for (int i = threadIdx.x; i < H * W; i += blockDim.x) plane[i] = src[i];
-    __syncthreads();
-    for (int y = threadIdx.x; y < H; y += blockDim.x) {
-        const float *r = plane + (size_t)y * W;
-        double s = 0.0;
-        for (int x = 0; x < Wo; ++x) s += (double)r[x];
-        rows[y * k] = s;
-        for (int kx = 1; kx < k; ++kx) {
-            s += (double)r[kx + Wo - 1] - (double)r[kx - 1];
-            rows[y * k + kx] = s;
+    for (int x = threadIdx.x; x < W; x += blockDim.x) {
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+        int y = 0;
+        for (; y + 3 < H; y += 4) {
+            s0 += (double)__ldg(src + (size_t)y * W + x);
+            s1 += (double)__ldg(src + (size_t)(y + 1) * W + x);
+            s2 += (double)__ldg(src + (size_t)(y + 2) * W + x);
+            s3 += (double)__ldg(src + (size_t)(y + 3) * W + x);
+        }
+        for (; y < H; ++y) s0 += (double)__ldg(src + (size_t)y * W + x);
+        const double total = (s0 + s1) + (s2 + s3);
+        double tail = 0.0, head = 0.0;
+        for (int yy = Ho; yy < H; ++yy) tail += (double)__ldg(src + (size_t)yy * W + x);
+        for (int ky = 0; ky < k; ++ky) {
+            cols[ky * W + x] = total - head - tail;      // rows [ky, ky + Ho)
+            if (ky + 1 < k) {
+                head += (double)__ldg(src + (size_t)ky * W + x);
+                tail -= (double)__ldg(src + (size_t)(ky + Ho) * W + x);
+            }
         }
     }
     __syncthreads();
     for (int t = threadIdx.x; t < k * k; t += blockDim.x) {
         const int ky = t / k, kx = t - ky * k;
         double s = 0.0;
-        for (int y = ky; y < ky + Ho; ++y) s += rows[y * k + kx];
+        for (int x = kx; x < kx + Wo; ++x) s += cols[ky * W + x];
         S[(size_t)bc * k * k + t] = s;
     }
 }
@@ -295,7 +305,8 @@ struct ConvPlan {
     size_t win_smem;
     // tcgen05 inner layers (conv_stack_tc.cu): fp16 hi/lo NHWC ping-pong buffers, packed weights, layer records
     bool tc;
-    size_t off_h[2][2], off_wp[16], off_lay, off_absmax;
+    size_t off_h[2][2], off_wp[16], off_lay, off_absmax, off_rowstat, off_xin[2];
+    int cpad0;             // input channels padded to 32 (layer 0 on the tensor path)
 };
 
 static int conv_make_plan(int B, int cin, int H, int W, int cout, int k, int G, int L, ConvPlan &p) {
@@ -333,15 +344,17 @@ static int conv_make_plan(int B, int cin, int H, int W, int cout, int k, int G, 
     p.off_S = off; off += (size_t)(B > 0 ? B : 1) * p.chunks * p.Npad * sizeof(double);
     // fold of the last layer: input plane (H_in x W_in of layer L-1) staged in shared memory
     const int Hin = p.Ho[L - 1] + k - 1, Win = p.Wo[L - 1] + k - 1;
-    p.win_smem = (((size_t)Hin * Win * sizeof(float) + 7) & ~(size_t)7) + (size_t)Hin * k * sizeof(double);
+    p.win_smem = (size_t)Win * k * sizeof(double);
+    (void)Hin;
     p.fold = p.win_smem <= 200 * 1024 && !getenv("EQB_CONV_NO_FOLD");
     off = (off + 255) & ~(size_t)255;
     p.off_fold = off; off += (size_t)G * p.K[L - 1] * sizeof(double);
     p.off_bmean = off; off += 64 * sizeof(double);
     p.off_win = off; off += (size_t)(B > 0 ? B : 1) * p.K[L - 1] * sizeof(double);
     p.tc = p.fold && ctc_eligible(p.Npad, L);
-    for (int l = 1; l <= L - 2; ++l)   // every tcgen05 layer's input must hold at least one 16 x 8 TMA box
-        if (p.Ho[l - 1] < 8 || p.Wo[l - 1] < 16) p.tc = false;
+    for (int l = 1; l <= L - 2; ++l)   // every tcgen05 layer's input must hold at least one halo box (8+k-1) x (16+k-1)
+        if (p.Wo[l - 1] < 8 + k - 1 || p.Ho[l - 1] < 16 + k - 1) p.tc = false;
+    if (W < 8 + k - 1 || H < 16 + k - 1) p.tc = false;
     if (p.tc) {
         off = (off + 1023) & ~(size_t)1023;
         const size_t hbytes = (((size_t)(B > 0 ? B : 1) * p.P[0] * p.Npad * sizeof(__half)) + 1023) & ~(size_t)1023;
@@ -354,8 +367,14 @@ static int conv_make_plan(int B, int cin, int H, int W, int cout, int k, int G, 
             p.off_wp[l] = off;
             off += (ctc_pack_bytes(p.Npad, p.N, k) + 1023) & ~(size_t)1023;
         }
+        p.cpad0 = (cin + 31) / 32 * 32;
+        p.off_wp[0] = off; off += (ctc_pack_bytes(p.Npad, cin, k) + 1023) & ~(size_t)1023;
+        const size_t xbytes = (((size_t)(B > 0 ? B : 1) * H * W * p.cpad0 * sizeof(__half)) + 1023) & ~(size_t)1023;
+        p.off_xin[0] = off; off += xbytes;
+        p.off_xin[1] = off; off += xbytes;
         p.off_lay = off; off += (size_t)(L + 1) * LAY_FLOATS * sizeof(float);
         p.off_absmax = off; off += 64;
+        p.off_rowstat = off; off += (size_t)2 * p.Npad * sizeof(float);
     }
     p.total = off;
     return 0;
@@ -407,22 +426,32 @@ extern "C" int eqb_conv_stack_forward(const float *x, int B, int cin, int H, int
     }
     for (int l = 0; l < L; ++l) {
         EQB_REQUIRE(filters[l], "eqb_conv_stack_forward: null filter for layer %d", l);
-        if (p.tc && l >= 1 && l <= L - 2) {
-            // ---- inner layer on the tensor cores: fp16 hi/lo NHWC in, fp16 pair or (last inner layer) fp32 NCHW out ----
+        if (p.tc && l <= L - 2) {
+            // ---- layer on the tensor cores: fp16 hi/lo NHWC in, fp16 pair or (last such layer) fp32 NCHW out ----------
             float *vec = (float *)(ws + p.off_vec[l]);
             conv_vec_kernel<<<1, 256, 0, st>>>(biases ? biases[l] : nullptr, scales ? scales[l] : nullptr,
                                                shifts ? shifts[l] : nullptr, vec, p.N, p.Npad);
             float *lay_l = lay + (size_t)l * LAY_FLOATS;
-            int e = ctc_layer_stats(filters[l], vec, p.N, p.Npad, p.K[l], lay_l + LAY_INBOUND, 1, lay_l, lay_l + LAY_FLOATS, st);
+            const float *bound_in = l == 0 ? (const float *)(ws + p.off_absmax) : lay_l + LAY_INBOUND;
+            int e = ctc_layer_stats(filters[l], vec, p.N, p.Npad, p.K[l], bound_in, 1, lay_l, lay_l + LAY_FLOATS,
+                                    (float *)(ws + p.off_rowstat), st);
             if (e) return e;
             unsigned char *wp = (unsigned char *)(ws + p.off_wp[l]);
-            e = ctc_pack(filters[l], lay_l, p.N, p.N, k, p.Npad, wp, st);
+            e = ctc_pack(filters[l], lay_l, p.N, p.cin[l], k, p.Npad, wp, st);
             if (e) return e;
+            int cpad_in = p.Npad;
+            if (l == 0) {   // the network input becomes the first fp16 pair (channels padded to 32)
+                cpad_in = p.cpad0;
+                __half *xh = (__half *)(ws + p.off_xin[0]), *xl = (__half *)(ws + p.off_xin[1]);
+                e = ctc_input_split(x, (const float *)(ws + p.off_absmax), B, cin, H, W, cpad_in, xh, xl, st);
+                if (e) return e;
+                tin_hi = xh; tin_lo = xl;
+            }
             const bool last_inner = l == L - 2;
             float *out32 = last_inner ? (float *)(ws + p.off_buf[0]) : nullptr;
             __half *oh = last_inner ? nullptr : (__half *)(ws + p.off_h[l & 1][0]);
             __half *ol = last_inner ? nullptr : (__half *)(ws + p.off_h[l & 1][1]);
-            e = ctc_conv_layer(tin_hi, tin_lo, B, p.Npad, h, w, k, wp, vec, lay_l, p.N, p.Npad, 1, out32, oh, ol, p.Npad, st);
+            e = ctc_conv_layer(tin_hi, tin_lo, B, cpad_in, h, w, k, wp, vec, lay_l, p.N, p.Npad, 1, out32, oh, ol, p.Npad, st);
             if (e) return e;
             in = out32; tin_hi = oh; tin_lo = ol;
             h = p.Ho[l]; w = p.Wo[l];
@@ -434,7 +463,7 @@ extern "C" int eqb_conv_stack_forward(const float *x, int B, int cin, int H, int
             double *Wfold = (double *)(ws + p.off_fold), *bmean = (double *)(ws + p.off_bmean), *Swin = (double *)(ws + p.off_win);
             conv_fold_weights_kernel<<<64, 256, 0, st>>>(filters[l], biases ? biases[l] : nullptr, cout, num_group, Kl, Wfold, bmean);
             EQB_CUDA(cudaFuncSetAttribute(conv_window_sums_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            conv_window_sums_kernel<<<(unsigned)(B * p.cin[l]), 128, p.win_smem, st>>>(in, p.cin[l], h, w, k, Swin);
+            conv_window_sums_kernel<<<(unsigned)(B * p.cin[l]), w <= 96 ? 96 : w <= 128 ? 128 : 256, p.win_smem, st>>>(in, p.cin[l], h, w, k, Swin);
             const double inv = 1.0 / ((double)cout * (double)p.P[l]);
             conv_fold_apply_kernel<<<B, 256, 0, st>>>(Swin, Wfold, bmean, Kl, num_group, inv, act);
             return finish_launch("conv_fold_apply_kernel");
@@ -445,14 +474,6 @@ extern "C" int eqb_conv_stack_forward(const float *x, int B, int cin, int H, int
         conv_vec_kernel<<<1, 256, 0, st>>>(biases ? biases[l] : nullptr, (!last && scales) ? scales[l] : nullptr,
                                            (!last && shifts) ? shifts[l] : nullptr, vec, p.N, p.Npad);
         ConvArgs a{};
-        if (p.tc && l == 0) {
-            // layer 0 (K = Cin*k*k is tiny) stays on the SIMT kernel but emits the fp16 pair the tensor layer reads
-            float *lay0 = lay;
-            int e = ctc_layer_stats(filters[0], vec, p.N, p.Npad, p.K[0], (const float *)(ws + p.off_absmax), 0, lay0,
-                                    lay0 + LAY_FLOATS, st);
-            if (e) return e;
-            a.y_hi = (__half *)(ws + p.off_h[0][0]); a.y_lo = (__half *)(ws + p.off_h[0][1]); a.lay = lay0;
-        }
         a.x = in; a.B = B; a.cin = p.cin[l]; a.H = h; a.W = w; a.ksz = k; a.Ho = p.Ho[l]; a.Wo = p.Wo[l]; a.P = p.P[l];
         a.K = p.K[l]; a.Kpad = p.Kpad[l]; a.N = p.N; a.Npad = p.Npad; a.relu = !last;
         a.Wt = Wt; a.bias = vec; a.scale = vec + p.Npad; a.shift = vec + 2 * p.Npad;

@@ -4,11 +4,15 @@
 //   M = 128 output pixels (an 8 x 16 patch of one image), N = Cout*|G| (padded to 32..256), K = Cin * k * k.
 //
 // Activations travel between layers as two fp16 tensors in NHWC (hi / lo halves of the power-of-two scaled fp32 value,
-// the same 22-bit split as gconv_stack_tc.cu), so the A operand of every (ky, kx, 32-channel) K atom is ONE TMA box:
-//   cp.async.bulk.tensor.4d over (C, W, H, B), box 32 x 16 x 8 x 1, SWIZZLE_64B
-// which lands exactly as the 128-row K-major SWIZZLE_64B tile the UMMA descriptor expects (rows = patch pixels,
-// 64 bytes = 32 channels); the (ky, kx) shift is just the box origin, image borders are TMA zero fill.  Weights are
-// pre-packed per atom as hi / lo UMMA images and streamed by cp.async.bulk.  Each product is a_hi*w_hi + a_lo*w_hi +
+// the same 22-bit split as gconv_stack_tc.cu).  A tile is a 16 x 8 patch of output pixels; for every 32-channel group
+// ONE TMA box fetches the patch WITH ITS HALO,
+//   cp.async.bulk.tensor.4d over (C, W, H, B), box 32 x (8 + k - 1) x (16 + k - 1) x 1, SWIZZLE_64B,
+// and all k*k (ky, kx) K atoms read their A operand from it: rows (py + ky) * HW + kx + 0..7 of the box are exactly the
+// 8-row core groups of a K-major SWIZZLE_64B operand with group stride HW * 64 bytes, so the (ky, kx) shift is nothing
+// but the descriptor's start address (the UMMA swizzle is a function of the absolute shared-memory address: any row
+// shift and any group pitch work with base_offset 0 - verified bit-exact with tools/umma_shift_probe.cu).  Each input
+// element crosses L2 -> SM once instead of k*k times; image borders are TMA zero fill.  Weights are pre-packed per
+// atom as hi / lo UMMA images and streamed by cp.async.bulk through their own ring.  Each product is a_hi*w_hi + a_lo*w_hi +
 // a_hi*w_lo (three kind::f16 MMAs, fp32 accumulation in TMEM).  Two accumulators (2 x Npad columns) let the epilogue
 // of tile t overlap the main loop of tile t+1.
 //   warp 0  producer (one lane): 2 TMA boxes + 1 bulk weight copy per stage, mbarrier tx-count
@@ -88,6 +92,20 @@ __device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint32_t a_lo, uint32_t 
         "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "n"(DESC_HI_64B)
         : "memory");
 }
+__device__ __forceinline__ void tc_mma_hw(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hiw, uint32_t b_lo, uint32_t b_hiw,
+                                          uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        ".reg .b64 da, db;\n"
+        "setp.ne.b32 p, %6, 0;\n"
+        "mov.b64 da, {%1, %2};\n"
+        "mov.b64 db, {%3, %4};\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "r"(a_lo), "r"(a_hiw), "r"(b_lo), "r"(b_hiw), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred = 0;
     asm volatile(
@@ -132,16 +150,16 @@ __host__ __device__ __forceinline__ float pow2_scale(float m) {
 }
 
 constexpr int THREADS = 256;
-constexpr int A_HALF = 128 * 64;          // one 128-pixel x 32-channel fp16 box: 8 KB
-constexpr int MAX_STAGES = 8;
+constexpr int MAX_W_STAGES = 8, A_STAGES = 2;
 
 struct Args {
-    const unsigned char *wpack;            // [atoms][hi: Npad x 64 B | lo: Npad x 64 B]
+    const unsigned char *wpack;            // [c-atom][ky*k+kx][hi: Npad x 64 B | lo: Npad x 64 B]
     const float *bias, *scale, *shift;     // [Npad] (scale 1 / shift 0 when the layer has no affine)
     const float *lay;                      // device: layer record (see LAY_*)
     float *out_nchw;                       // (B, N, Ho, Wo) fp32, or null
     __half *out_hi, *out_lo;               // (B, Ho, Wo, Cpad_out) fp16 pair, or null
-    int B, k, Ho, Wo, N, Npad, catoms, atoms, tiles_x, tiles_y, tiles, relu, Cpad_out, stages;
+    int B, k, Ho, Wo, N, Npad, catoms, tiles_x, tiles_y, tiles, relu, Cpad_out;
+    int HW, a_half, w_stages;              // halo width (8 + k - 1), bytes of one halo box (1024-rounded), weight ring depth
 };
 
 __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap map_hi,
@@ -150,23 +168,28 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const __grid_consta
     const uint32_t base = smem_u32(smem_raw);
     if ((base & 1023u) != 0) __trap();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t stage_bytes = 2u * A_HALF + (uint32_t)a.Npad * 128u;
-    const uint32_t misc = base + (uint32_t)a.stages * stage_bytes;          // barriers, TMEM slot, per-channel vectors
-    auto full = [&](int s) { return misc + 8u * (uint32_t)s; };
-    auto empty = [&](int s) { return misc + 8u * (uint32_t)(MAX_STAGES + s); };
-    auto accfull = [&](int b) { return misc + 8u * (uint32_t)(2 * MAX_STAGES + b); };
-    auto accempty = [&](int b) { return misc + 8u * (uint32_t)(2 * MAX_STAGES + 2 + b); };
-    const uint32_t tmem_slot = misc + 8u * (2 * MAX_STAGES + 4);
-    float *vec = reinterpret_cast<float *>(smem_raw + (misc - base) + 8 * (2 * MAX_STAGES + 4) + 16);   // [3][Npad]
+    const uint32_t a_stage = 2u * (uint32_t)a.a_half, w_stage = (uint32_t)a.Npad * 128u;
+    const uint32_t a_ring = base, w_ring = base + A_STAGES * a_stage;
+    const uint32_t misc = w_ring + (uint32_t)a.w_stages * w_stage;          // barriers, TMEM slot, per-channel vectors
+    enum { B_AFULL = 0, B_AEMPTY = A_STAGES, B_WFULL = 2 * A_STAGES, B_WEMPTY = B_WFULL + MAX_W_STAGES,
+           B_ACCFULL = B_WEMPTY + MAX_W_STAGES, B_ACCEMPTY = B_ACCFULL + 2, B_COUNT = B_ACCEMPTY + 2 };
+    auto bar = [&](int i) { return misc + 8u * (uint32_t)i; };
+    const uint32_t tmem_slot = misc + 8u * B_COUNT;
+    float *vec = reinterpret_cast<float *>(smem_raw + (misc - base) + 8 * B_COUNT + 16);   // [3][Npad]
+    const int kk2 = a.k * a.k;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < a.stages; ++s) {
-            mbar_init(full(s), 1);
-            mbar_init(empty(s), 1);
+        for (int s = 0; s < A_STAGES; ++s) {
+            mbar_init(bar(B_AFULL + s), 1);
+            mbar_init(bar(B_AEMPTY + s), 1);
+        }
+        for (int s = 0; s < a.w_stages; ++s) {
+            mbar_init(bar(B_WFULL + s), 1);
+            mbar_init(bar(B_WEMPTY + s), 1);
         }
         for (int b = 0; b < 2; ++b) {
-            mbar_init(accfull(b), 1);
-            mbar_init(accempty(b), 128);
+            mbar_init(bar(B_ACCFULL + b), 1);
+            mbar_init(bar(B_ACCEMPTY + b), 128);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -186,70 +209,85 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const __grid_consta
     const int per_img = a.tiles_x * a.tiles_y;
 
     if (warp == 0) {
-        // ===== producer ==========================================================================================
+        // ===== producer: one halo box pair per channel group, one weight stage per (channel group, ky, kx) =========
         if (lane == 0) {
-            int s = 0;
-            uint32_t ph = 0;
+            int as = 0, ws = 0;
+            uint32_t aph = 0, wph = 0;
             for (int tile = blockIdx.x; tile < a.tiles; tile += gridDim.x) {
                 const int b = tile / per_img, r = tile - b * per_img, ty = r / a.tiles_x, tx = r - ty * a.tiles_x;
-                const int oy0 = ty * 8, ox0 = tx * 16;
-                int atom = 0;
-                for (int ky = 0; ky < a.k; ++ky)
-                    for (int kx = 0; kx < a.k; ++kx)
-                        for (int ca = 0; ca < a.catoms; ++ca, ++atom) {
-                            mbar_wait(empty(s), ph ^ 1u);
-                            mbar_expect_tx(full(s), stage_bytes);
-                            const uint32_t dst = base + (uint32_t)s * stage_bytes;
-                            tma_load_4d(dst, &map_hi, full(s), ca * 32, ox0 + kx, oy0 + ky, b);
-                            tma_load_4d(dst + A_HALF, &map_lo, full(s), ca * 32, ox0 + kx, oy0 + ky, b);
-                            bulk_load(dst + 2 * A_HALF, a.wpack + (size_t)atom * a.Npad * 128, (uint32_t)a.Npad * 128u, full(s));
-                            if (++s == a.stages) { s = 0; ph ^= 1u; }
-                        }
+                const int oy0 = ty * 16, ox0 = tx * 8;
+                for (int ca = 0; ca < a.catoms; ++ca) {
+                    mbar_wait(bar(B_AEMPTY + as), aph ^ 1u);
+                    mbar_expect_tx(bar(B_AFULL + as), 2u * (uint32_t)(a.HW * (16 + a.k - 1) * 64));
+                    const uint32_t dst = a_ring + (uint32_t)as * a_stage;
+                    tma_load_4d(dst, &map_hi, bar(B_AFULL + as), ca * 32, ox0, oy0, b);
+                    tma_load_4d(dst + (uint32_t)a.a_half, &map_lo, bar(B_AFULL + as), ca * 32, ox0, oy0, b);
+                    if (++as == A_STAGES) { as = 0; aph ^= 1u; }
+                    for (int kk = 0; kk < kk2; ++kk) {
+                        mbar_wait(bar(B_WEMPTY + ws), wph ^ 1u);
+                        mbar_expect_tx(bar(B_WFULL + ws), w_stage);
+                        bulk_load(w_ring + (uint32_t)ws * w_stage, a.wpack + (size_t)(ca * kk2 + kk) * w_stage, w_stage,
+                                  bar(B_WFULL + ws));
+                        if (++ws == a.w_stages) { ws = 0; wph ^= 1u; }
+                    }
+                }
             }
         }
     } else if (warp == 1) {
         // ===== MMA issuer ========================================================================================
         const uint32_t idesc = (1u << 4) | ((uint32_t)(a.Npad >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-        int s = 0;
-        uint32_t ph = 0, accph[2] = {0, 0};
+        // A: group stride = one halo row (HW pixels of 64 bytes); B: 8 rows of 64 bytes
+        const uint32_t a_hiw = ((uint32_t)(a.HW * 64) >> 4) | (1u << 14) | (4u << 29), b_hiw = DESC_HI_64B;
+        int as = 0, ws = 0;
+        uint32_t aph = 0, wph = 0, accph[2] = {0, 0};
         int buf = 0;
         for (int tile = blockIdx.x; tile < a.tiles; tile += gridDim.x) {
-            mbar_wait(accempty(buf), accph[buf] ^ 1u);      // the epilogue has drained this accumulator
+            mbar_wait(bar(B_ACCEMPTY + buf), accph[buf] ^ 1u);      // the epilogue has drained this accumulator
             tc_fence_after();
             const uint32_t d = tmem + (uint32_t)(buf * a.Npad);
-            for (int atom = 0; atom < a.atoms; ++atom) {
-                mbar_wait(full(s), ph);
-                tc_fence_after();
-                if (elect_one()) {
-                    const uint32_t st = base + (uint32_t)s * stage_bytes;
-                    const uint32_t a_hi = desc_lo(st), a_lo = desc_lo(st + A_HALF);
-                    const uint32_t w_hi = desc_lo(st + 2 * A_HALF), w_lo = desc_lo(st + 2 * A_HALF + (uint32_t)a.Npad * 64u);
+            for (int ca = 0; ca < a.catoms; ++ca) {
+                mbar_wait(bar(B_AFULL + as), aph);
+                const uint32_t ah = a_ring + (uint32_t)as * a_stage, al = ah + (uint32_t)a.a_half;
+                for (int kk = 0; kk < kk2; ++kk) {
+                    const int ky = kk / a.k, kx = kk - ky * a.k;
+                    mbar_wait(bar(B_WFULL + ws), wph);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint32_t shift = (uint32_t)((ky * a.HW + kx) * 64);
+                        const uint32_t a_hi = desc_lo(ah + shift), a_lo = desc_lo(al + shift);
+                        const uint32_t wb = w_ring + (uint32_t)ws * w_stage;
+                        const uint32_t w_hi = desc_lo(wb), w_lo = desc_lo(wb + (uint32_t)a.Npad * 64u);
 #pragma unroll
-                    for (int j = 0; j < 2; ++j) tc_mma(d, a_hi + 2 * j, w_hi + 2 * j, idesc, (atom | j) != 0);
+                        for (int j = 0; j < 2; ++j) tc_mma_hw(d, a_hi + 2 * j, a_hiw, w_hi + 2 * j, b_hiw, idesc, (ca | kk | j) != 0);
 #pragma unroll
-                    for (int j = 0; j < 2; ++j) tc_mma(d, a_lo + 2 * j, w_hi + 2 * j, idesc, 1);
+                        for (int j = 0; j < 2; ++j) tc_mma_hw(d, a_lo + 2 * j, a_hiw, w_hi + 2 * j, b_hiw, idesc, 1);
 #pragma unroll
-                    for (int j = 0; j < 2; ++j) tc_mma(d, a_hi + 2 * j, w_lo + 2 * j, idesc, 1);
-                    tc_commit(empty(s));
-                    if (atom == a.atoms - 1) tc_commit(accfull(buf));
+                        for (int j = 0; j < 2; ++j) tc_mma_hw(d, a_hi + 2 * j, a_hiw, w_lo + 2 * j, b_hiw, idesc, 1);
+                        tc_commit(bar(B_WEMPTY + ws));
+                        if (kk == kk2 - 1) {
+                            tc_commit(bar(B_AEMPTY + as));
+                            if (ca == a.catoms - 1) tc_commit(bar(B_ACCFULL + buf));
+                        }
+                    }
+                    __syncwarp();
+                    if (++ws == a.w_stages) { ws = 0; wph ^= 1u; }
                 }
-                __syncwarp();
-                if (++s == a.stages) { s = 0; ph ^= 1u; }
+                if (++as == A_STAGES) { as = 0; aph ^= 1u; }
             }
             accph[buf] ^= 1u;
             buf ^= 1;
         }
     } else if (warp >= 4) {
         // ===== epilogue ==========================================================================================
-        const int q = warp & 3, row = q * 32 + lane, py = row >> 4, px = row & 15;
+        const int q = warp & 3, row = q * 32 + lane, py = row >> 3, px = row & 7;   // TMEM lane = py * 8 + px
         const float cinv = a.lay[LAY_CINV], s_out = a.lay[LAY_SOUT];
         uint32_t accph[2] = {0, 0};
         int buf = 0;
         for (int tile = blockIdx.x; tile < a.tiles; tile += gridDim.x) {
             const int b = tile / per_img, r = tile - b * per_img, ty = r / a.tiles_x, tx = r - ty * a.tiles_x;
-            const int oy = ty * 8 + py, ox = tx * 16 + px;
+            const int oy = ty * 16 + py, ox = tx * 8 + px;
             const bool valid = oy < a.Ho && ox < a.Wo;
-            mbar_wait(accfull(buf), accph[buf]);
+            mbar_wait(bar(B_ACCFULL + buf), accph[buf]);
             tc_fence_after();
             for (int c = 0; c < a.Npad / 32; ++c) {
                 float v[32];
@@ -282,7 +320,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const __grid_consta
                 }
             }
             tc_fence_before();
-            mbar_arrive(accempty(buf));
+            mbar_arrive(bar(B_ACCEMPTY + buf));
             accph[buf] ^= 1u;
             buf ^= 1;
         }
@@ -298,19 +336,36 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const __grid_consta
 // One layer's operand scales and output bound, chained on the device (lay = this layer's record, nxt = the next one's).
 //   in_bound = *in_bound_ptr;  s_in = pow2(in_bound);  sw = pow2(max |W|);  cinv = 1 / (s_in * sw)
 //   out_bound = max_n ( |scale_n| (in_bound * sum_k |W[n,k]| + |bias_n|) + |shift_n| );  s_out = pow2(out_bound)
-__global__ void __launch_bounds__(256) ctc_layer_stats_kernel(const float *__restrict__ w, const float *__restrict__ vecs, int N,
-                                                              int Npad, int K, const float *__restrict__ in_bound_ptr,
+// (two kernels: one block per output channel reduces its filter row, one block combines the rows)
+__global__ void __launch_bounds__(128) ctc_row_stats_kernel(const float *__restrict__ w, int K, float *__restrict__ rowstat) {
+    __shared__ float red[2][4];
+    const int n = blockIdx.x;
+    float wmax = 0.f, rs = 0.f;
+    for (int kk = threadIdx.x; kk < K; kk += blockDim.x) {
+        const float v = fabsf(w[(size_t)n * K + kk]);
+        wmax = fmaxf(wmax, v);
+        rs += v;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        wmax = fmaxf(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
+        rs += __shfl_xor_sync(0xffffffffu, rs, o);
+    }
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = wmax; red[1][threadIdx.x >> 5] = rs; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        rowstat[2 * n] = fmaxf(fmaxf(red[0][0], red[0][1]), fmaxf(red[0][2], red[0][3]));
+        rowstat[2 * n + 1] = (red[1][0] + red[1][1]) + (red[1][2] + red[1][3]);
+    }
+}
+__global__ void __launch_bounds__(256) ctc_layer_stats_kernel(const float *__restrict__ rowstat, const float *__restrict__ vecs,
+                                                              int N, int Npad, const float *__restrict__ in_bound_ptr,
                                                               int tensor_in, float *__restrict__ lay, float *__restrict__ nxt) {
     __shared__ float red[2][256];
     const float in_bound = *in_bound_ptr;
     float wmax = 0.f, ob = 0.f;
     for (int n = threadIdx.x; n < N; n += blockDim.x) {
-        float rs = 0.f;
-        for (int kk = 0; kk < K; ++kk) {
-            const float v = fabsf(w[(size_t)n * K + kk]);
-            wmax = fmaxf(wmax, v);
-            rs += v;
-        }
+        wmax = fmaxf(wmax, rowstat[2 * n]);
+        const float rs = rowstat[2 * n + 1];
         const float o = fabsf(vecs[Npad + n]) * (in_bound * rs * 1.0001f + fabsf(vecs[n])) + fabsf(vecs[2 * Npad + n]);
         ob = fmaxf(ob, o);
     }
@@ -332,7 +387,7 @@ __global__ void __launch_bounds__(256) ctc_layer_stats_kernel(const float *__res
     }
 }
 
-// filter (N, C, k, k) fp32 -> per atom (ky, kx, 32-channel group) an Npad x 64-byte hi image followed by the lo image,
+// filter (N, C, k, k) fp32 -> per atom (32-channel group, then ky, kx) an Npad x 64-byte hi image followed by the lo image,
 // SWIZZLE_64B (16-byte chunk index XOR ((n >> 1) & 3)), scaled by sw; rows >= N and channels >= C are zero
 __global__ void ctc_pack_kernel(const float *__restrict__ w, const float *__restrict__ lay, int N, int C, int k, int Npad,
                                 int catoms, unsigned char *__restrict__ out) {
@@ -341,7 +396,7 @@ __global__ void ctc_pack_kernel(const float *__restrict__ w, const float *__rest
     for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
         const int ks = (int)(t % 32), n = (int)((t / 32) % Npad);
         const int atom = (int)(t / (32LL * Npad));
-        const int ca = atom % catoms, kk = atom / catoms, ky = kk / k, kx = kk - ky * k;
+        const int ca = atom / (k * k), kk = atom - ca * (k * k), ky = kk / k, kx = kk - ky * k;
         const int c = ca * 32 + ks;
         const float v = (n < N && c < C) ? w[(((size_t)n * C + c) * k + ky) * k + kx] * sw : 0.f;
         const __half hi = __float2half_rn(v), lo = __float2half_rn(v - __half2float(hi));
@@ -349,6 +404,27 @@ __global__ void ctc_pack_kernel(const float *__restrict__ w, const float *__rest
         const size_t off = (size_t)n * 64 + (size_t)((((ks >> 3) ^ ((n >> 1) & 3)) << 4) | ((ks & 7) << 1));
         *reinterpret_cast<__half *>(out + (size_t)atom * stage + off) = hi;
         *reinterpret_cast<__half *>(out + (size_t)atom * stage + (size_t)Npad * 64 + off) = lo;
+    }
+}
+
+// network input (B, C, H, W) fp32 -> the fp16 hi / lo NHWC pair with C padded to Cpad (zeros), scaled by s_in = pow2(max |x|)
+// (writes the first layer's record fields it needs: LAY_INBOUND is set by the caller's stats chain)
+__global__ void __launch_bounds__(256) ctc_input_split_kernel(const float *__restrict__ x, const float *__restrict__ absmax,
+                                                              int B, int C, int H, int W, int Cpad, __half *__restrict__ hi,
+                                                              __half *__restrict__ lo) {
+    const float s = pow2_scale(*absmax);
+    const size_t npix = (size_t)B * H * W, plane = (size_t)H * W;
+    const int pairs = Cpad / 2;
+    for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < npix * pairs; t += (size_t)gridDim.x * blockDim.x) {
+        const size_t pix = t / pairs;
+        const int c = 2 * (int)(t - pix * pairs);
+        const size_t b = pix / plane, r = pix - b * plane;
+        const float v0 = c < C ? x[(b * C + c) * plane + r] * s : 0.f;
+        const float v1 = c + 1 < C ? x[(b * C + c + 1) * plane + r] * s : 0.f;
+        uint32_t h, l;
+        split2(v0, v1, h, l);
+        reinterpret_cast<uint32_t *>(hi)[pix * pairs + (c >> 1)] = h;
+        reinterpret_cast<uint32_t *>(lo)[pix * pairs + (c >> 1)] = l;
     }
 }
 
@@ -367,8 +443,8 @@ static EncodeTiledFn encode_fn() {
     }();
     return fn;
 }
-// (C, W, H, B) fp16 NHWC tensor, box 32 x 16 x 8 x 1, SWIZZLE_64B
-static int make_act_map(CUtensorMap *m, const void *ptr, int Cpad, int W, int H, int B) {
+// (C, W, H, B) fp16 NHWC tensor, box 32 x HW x HH x 1 (the 8 x 16 output patch with its halo), SWIZZLE_64B
+static int make_act_map(CUtensorMap *m, const void *ptr, int Cpad, int W, int H, int B, int HW, int HH) {
     EncodeTiledFn enc = encode_fn();
     if (!enc) {
         set_error("cuTensorMapEncodeTiled is not available from the CUDA driver");
@@ -376,7 +452,7 @@ static int make_act_map(CUtensorMap *m, const void *ptr, int Cpad, int W, int H,
     }
     const cuuint64_t gdim[4] = {(cuuint64_t)Cpad, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
     const cuuint64_t gstride[3] = {(cuuint64_t)Cpad * 2, (cuuint64_t)W * Cpad * 2, (cuuint64_t)H * W * Cpad * 2};
-    const cuuint32_t box[4] = {32, 16, 8, 1}, estr[4] = {1, 1, 1, 1};
+    const cuuint32_t box[4] = {32, (cuuint32_t)HW, (cuuint32_t)HH, 1}, estr[4] = {1, 1, 1, 1};
     const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void *>(ptr), gdim, gstride, box, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -391,15 +467,26 @@ static int make_act_map(CUtensorMap *m, const void *ptr, int Cpad, int W, int H,
 
 bool ctc_eligible(int Npad, int num_layers) {
     if (getenv("EQB_CONV_NO_TC")) return false;
-    return num_layers >= 3 && Npad >= 32 && Npad <= 256;
+    return num_layers >= 2 && Npad >= 32 && Npad <= 256;
 }
 
 size_t ctc_pack_bytes(int Npad, int C, int k) { return (size_t)k * k * ((C + 31) / 32) * Npad * 128; }
 
 int ctc_layer_stats(const float *w, const float *vecs, int N, int Npad, int K, const float *in_bound_ptr, int tensor_in,
-                    float *lay, float *nxt, cudaStream_t st) {
-    ctc::ctc_layer_stats_kernel<<<1, 256, 0, st>>>(w, vecs, N, Npad, K, in_bound_ptr, tensor_in, lay, nxt);
+                    float *lay, float *nxt, float *rowstat, cudaStream_t st) {
+    ctc::ctc_row_stats_kernel<<<N, 128, 0, st>>>(w, K, rowstat);
+    ctc::ctc_layer_stats_kernel<<<1, 256, 0, st>>>(rowstat, vecs, N, Npad, in_bound_ptr, tensor_in, lay, nxt);
     return finish_launch("ctc_layer_stats_kernel");
+}
+
+int ctc_input_split(const float *x, const float *absmax, int B, int C, int H, int W, int Cpad, __half *hi, __half *lo,
+                    cudaStream_t st) {
+    const size_t work = (size_t)B * H * W * (Cpad / 2);
+    size_t blocks = (work + 255) / 256;
+    if (blocks > (size_t)num_sms() * 16) blocks = (size_t)num_sms() * 16;
+    if (blocks == 0) return 0;
+    ctc::ctc_input_split_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, absmax, B, C, H, W, Cpad, hi, lo);
+    return finish_launch("ctc_input_split_kernel");
 }
 
 int ctc_pack(const float *w, const float *lay, int N, int C, int k, int Npad, unsigned char *out, cudaStream_t st) {
@@ -410,25 +497,29 @@ int ctc_pack(const float *w, const float *lay, int N, int C, int k, int Npad, un
 int ctc_conv_layer(const __half *in_hi, const __half *in_lo, int B, int Cpad, int H, int W, int k, const unsigned char *wpack,
                    const float *vecs, const float *lay, int N, int Npad, int relu, float *out_nchw, __half *out_hi,
                    __half *out_lo, int Cpad_out, cudaStream_t st) {
+    const int HW = 8 + k - 1, HH = 16 + k - 1;
+    EQB_UNSUPPORTED(HW > 256 || HH > 256, "eqb_conv_stack (tcgen05): kernel size %d too large for one TMA box", k);
     CUtensorMap mh, ml;
-    int e = ctc::make_act_map(&mh, in_hi, Cpad, W, H, B);
+    int e = ctc::make_act_map(&mh, in_hi, Cpad, W, H, B, HW, HH);
     if (e) return e;
-    e = ctc::make_act_map(&ml, in_lo, Cpad, W, H, B);
+    e = ctc::make_act_map(&ml, in_lo, Cpad, W, H, B, HW, HH);
     if (e) return e;
     ctc::Args a{};
     a.wpack = wpack; a.bias = vecs; a.scale = vecs + Npad; a.shift = vecs + 2 * Npad; a.lay = lay;
     a.out_nchw = out_nchw; a.out_hi = out_hi; a.out_lo = out_lo;
     a.B = B; a.k = k; a.Ho = H - k + 1; a.Wo = W - k + 1; a.N = N; a.Npad = Npad;
-    a.catoms = Cpad / 32; a.atoms = k * k * a.catoms;
-    a.tiles_x = (a.Wo + 15) / 16; a.tiles_y = (a.Ho + 7) / 8; a.tiles = B * a.tiles_x * a.tiles_y;
+    a.catoms = Cpad / 32;
+    a.tiles_x = (a.Wo + 7) / 8; a.tiles_y = (a.Ho + 15) / 16; a.tiles = B * a.tiles_x * a.tiles_y;
     a.relu = relu; a.Cpad_out = Cpad_out;
-    const size_t stage = 2 * (size_t)ctc::A_HALF + (size_t)Npad * 128;
-    const size_t misc = 8 * (2 * ctc::MAX_STAGES + 4) + 16 + 3 * (size_t)Npad * sizeof(float);
-    int stages = (int)((227 * 1024 - misc) / stage);
-    if (stages > ctc::MAX_STAGES) stages = ctc::MAX_STAGES;
-    EQB_UNSUPPORTED(stages < 2, "eqb_conv_stack (tcgen05): stage of %zu bytes does not fit twice", stage);
-    a.stages = stages;
-    const size_t smem = (size_t)stages * stage + misc;
+    a.HW = HW;
+    a.a_half = (HW * HH * 64 + 1023) & ~1023;
+    const size_t a_bytes = (size_t)ctc::A_STAGES * 2 * a.a_half, w_stage = (size_t)Npad * 128;
+    const size_t misc = 8 * (2 * ctc::A_STAGES + 2 * ctc::MAX_W_STAGES + 4) + 16 + 3 * (size_t)Npad * sizeof(float);
+    int w_stages = (int)((227 * 1024 - misc - a_bytes) / w_stage);
+    if (w_stages > ctc::MAX_W_STAGES) w_stages = ctc::MAX_W_STAGES;
+    EQB_UNSUPPORTED(w_stages < 2, "eqb_conv_stack (tcgen05): operand rings do not fit in shared memory (k = %d, N = %d)", k, Npad);
+    a.w_stages = w_stages;
+    const size_t smem = a_bytes + (size_t)w_stages * w_stage + misc;
     static bool configured = false;
     if (!configured) {
         EQB_CUDA(cudaFuncSetAttribute(ctc::conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
