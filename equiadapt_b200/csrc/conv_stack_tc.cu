@@ -150,7 +150,7 @@ __host__ __device__ __forceinline__ float pow2_scale(float m) {
 }
 
 constexpr int THREADS = 256;
-constexpr int MAX_W_STAGES = 8, A_STAGES = 2;
+constexpr int MAX_W_STAGES = 10, A_STAGES = 2;
 
 struct Args {
     const unsigned char *wpack;            // [c-atom][ky*k+kx][hi: Npad x 64 B | lo: Npad x 64 B]
@@ -238,6 +238,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const __grid_consta
         const uint32_t idesc = (1u << 4) | ((uint32_t)(a.Npad >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
         // A: group stride = one halo row (HW pixels of 64 bytes); B: 8 rows of 64 bytes
         const uint32_t a_hiw = ((uint32_t)(a.HW * 64) >> 4) | (1u << 14) | (4u << 29), b_hiw = DESC_HI_64B;
+        const uint32_t w_lo0 = desc_lo(w_ring), w_step = w_stage >> 4, w_lo_off = ((uint32_t)a.Npad * 64u) >> 4;
         int as = 0, ws = 0;
         uint32_t aph = 0, wph = 0, accph[2] = {0, 0};
         int buf = 0;
@@ -247,30 +248,34 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const __grid_consta
             const uint32_t d = tmem + (uint32_t)(buf * a.Npad);
             for (int ca = 0; ca < a.catoms; ++ca) {
                 mbar_wait(bar(B_AFULL + as), aph);
-                const uint32_t ah = a_ring + (uint32_t)as * a_stage, al = ah + (uint32_t)a.a_half;
-                for (int kk = 0; kk < kk2; ++kk) {
-                    const int ky = kk / a.k, kx = kk - ky * a.k;
-                    mbar_wait(bar(B_WFULL + ws), wph);
-                    tc_fence_after();
-                    if (elect_one()) {
-                        const uint32_t shift = (uint32_t)((ky * a.HW + kx) * 64);
-                        const uint32_t a_hi = desc_lo(ah + shift), a_lo = desc_lo(al + shift);
-                        const uint32_t wb = w_ring + (uint32_t)ws * w_stage;
-                        const uint32_t w_hi = desc_lo(wb), w_lo = desc_lo(wb + (uint32_t)a.Npad * 64u);
-#pragma unroll
-                        for (int j = 0; j < 2; ++j) tc_mma_hw(d, a_hi + 2 * j, a_hiw, w_hi + 2 * j, b_hiw, idesc, (ca | kk | j) != 0);
-#pragma unroll
-                        for (int j = 0; j < 2; ++j) tc_mma_hw(d, a_lo + 2 * j, a_hiw, w_hi + 2 * j, b_hiw, idesc, 1);
-#pragma unroll
-                        for (int j = 0; j < 2; ++j) tc_mma_hw(d, a_hi + 2 * j, a_hiw, w_lo + 2 * j, b_hiw, idesc, 1);
-                        tc_commit(bar(B_WEMPTY + ws));
-                        if (kk == kk2 - 1) {
-                            tc_commit(bar(B_AEMPTY + as));
-                            if (ca == a.catoms - 1) tc_commit(bar(B_ACCFULL + buf));
+                // descriptor low words advance by (bytes >> 4): 4 per pixel column (kx), 4 * HW per pixel row (ky);
+                // everything per K atom is adds on running values (an issue thread that rebuilds descriptors paces
+                // the tensor pipe: r1f finding on the stack kernel)
+                const uint32_t ah0 = desc_lo(a_ring + (uint32_t)as * a_stage), al0 = ah0 + ((uint32_t)a.a_half >> 4);
+                uint32_t row = 0;
+                int kk = 0;
+                for (int ky = 0; ky < a.k; ++ky, row += 4u * (uint32_t)a.HW) {
+                    for (int kx = 0; kx < a.k; ++kx, ++kk) {
+                        mbar_wait(bar(B_WFULL + ws), wph);
+                        tc_fence_after();
+                        if (elect_one()) {
+                            const uint32_t a_hi = ah0 + row + 4u * (uint32_t)kx, a_lo = al0 + row + 4u * (uint32_t)kx;
+                            const uint32_t w_hi = w_lo0 + (uint32_t)ws * w_step, w_lo = w_hi + w_lo_off;
+                            tc_mma_hw(d, a_hi, a_hiw, w_hi, b_hiw, idesc, (ca | kk) != 0);
+                            tc_mma_hw(d, a_hi + 2, a_hiw, w_hi + 2, b_hiw, idesc, 1);
+                            tc_mma_hw(d, a_lo, a_hiw, w_hi, b_hiw, idesc, 1);
+                            tc_mma_hw(d, a_lo + 2, a_hiw, w_hi + 2, b_hiw, idesc, 1);
+                            tc_mma_hw(d, a_hi, a_hiw, w_lo, b_hiw, idesc, 1);
+                            tc_mma_hw(d, a_hi + 2, a_hiw, w_lo + 2, b_hiw, idesc, 1);
+                            tc_commit(bar(B_WEMPTY + ws));
+                            if (kk == kk2 - 1) {
+                                tc_commit(bar(B_AEMPTY + as));
+                                if (ca == a.catoms - 1) tc_commit(bar(B_ACCFULL + buf));
+                            }
                         }
+                        __syncwarp();
+                        if (++ws == a.w_stages) { ws = 0; wph ^= 1u; }
                     }
-                    __syncwarp();
-                    if (++ws == a.w_stages) { ws = 0; wph ^= 1u; }
                 }
                 if (++as == A_STAGES) { as = 0; aph ^= 1u; }
             }
