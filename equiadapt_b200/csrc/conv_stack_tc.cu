@@ -160,6 +160,7 @@ struct Args {
     __half *out_hi, *out_lo;               // (B, Ho, Wo, Cpad_out) fp16 pair, or null
     int B, k, Ho, Wo, N, Npad, catoms, tiles_x, tiles_y, tiles, relu, Cpad_out;
     int HW, a_half, w_stages;              // halo width (8 + k - 1), bytes of one halo box (1024-rounded), weight ring depth
+    int dual;                              // two tiles per weight pass, one MMA issuer warp each (Npad <= 128)
 };
 
 __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap map_hi,
@@ -169,25 +170,27 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const __grid_consta
     if ((base & 1023u) != 0) __trap();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t a_stage = 2u * (uint32_t)a.a_half, w_stage = (uint32_t)a.Npad * 128u;
-    const uint32_t a_ring = base, w_ring = base + A_STAGES * a_stage;
+    const int nq = a.dual ? 2 : 1;                                           // MMA issuers = tiles in flight per weight pass
+    const uint32_t a_ring = base, w_ring = base + (uint32_t)nq * A_STAGES * a_stage;   // A ring of issuer q at a_ring + q * A_STAGES * a_stage
     const uint32_t misc = w_ring + (uint32_t)a.w_stages * w_stage;          // barriers, TMEM slot, per-channel vectors
-    enum { B_AFULL = 0, B_AEMPTY = A_STAGES, B_WFULL = 2 * A_STAGES, B_WEMPTY = B_WFULL + MAX_W_STAGES,
-           B_ACCFULL = B_WEMPTY + MAX_W_STAGES, B_ACCEMPTY = B_ACCFULL + 2, B_COUNT = B_ACCEMPTY + 2 };
+    // barrier table: A full / empty per (issuer, stage), W full / empty per stage, accumulator full / empty per (issuer, buffer)
+    enum { B_AFULL = 0, B_AEMPTY = 2 * A_STAGES, B_WFULL = 4 * A_STAGES, B_WEMPTY = B_WFULL + MAX_W_STAGES,
+           B_ACCFULL = B_WEMPTY + MAX_W_STAGES, B_ACCEMPTY = B_ACCFULL + 4, B_COUNT = B_ACCEMPTY + 4 };
     auto bar = [&](int i) { return misc + 8u * (uint32_t)i; };
     const uint32_t tmem_slot = misc + 8u * B_COUNT;
     float *vec = reinterpret_cast<float *>(smem_raw + (misc - base) + 8 * B_COUNT + 16);   // [3][Npad]
     const int kk2 = a.k * a.k;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < A_STAGES; ++s) {
+        for (int s = 0; s < 2 * A_STAGES; ++s) {
             mbar_init(bar(B_AFULL + s), 1);
             mbar_init(bar(B_AEMPTY + s), 1);
         }
         for (int s = 0; s < a.w_stages; ++s) {
             mbar_init(bar(B_WFULL + s), 1);
-            mbar_init(bar(B_WEMPTY + s), 1);
+            mbar_init(bar(B_WEMPTY + s), (uint32_t)nq);      // every issuer releases a weight stage
         }
-        for (int b = 0; b < 2; ++b) {
+        for (int b = 0; b < 4; ++b) {
             mbar_init(bar(B_ACCFULL + b), 1);
             mbar_init(bar(B_ACCEMPTY + b), 128);
         }
@@ -213,15 +216,22 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const __grid_consta
         if (lane == 0) {
             int as = 0, ws = 0;
             uint32_t aph = 0, wph = 0;
-            for (int tile = blockIdx.x; tile < a.tiles; tile += gridDim.x) {
-                const int b = tile / per_img, r = tile - b * per_img, ty = r / a.tiles_x, tx = r - ty * a.tiles_x;
-                const int oy0 = ty * 16, ox0 = tx * 8;
+            const uint32_t box_bytes = 2u * (uint32_t)(a.HW * (16 + a.k - 1) * 64);
+            // tiles are taken nq at a time: issuer q works on tile0 + q * gridDim.x with the SAME weight stages
+            for (int tile0 = blockIdx.x; tile0 < a.tiles; tile0 += nq * gridDim.x) {
                 for (int ca = 0; ca < a.catoms; ++ca) {
-                    mbar_wait(bar(B_AEMPTY + as), aph ^ 1u);
-                    mbar_expect_tx(bar(B_AFULL + as), 2u * (uint32_t)(a.HW * (16 + a.k - 1) * 64));
-                    const uint32_t dst = a_ring + (uint32_t)as * a_stage;
-                    tma_load_4d(dst, &map_hi, bar(B_AFULL + as), ca * 32, ox0, oy0, b);
-                    tma_load_4d(dst + (uint32_t)a.a_half, &map_lo, bar(B_AFULL + as), ca * 32, ox0, oy0, b);
+                    for (int q = 0; q < nq; ++q) {
+                        const int tile = tile0 + q * (int)gridDim.x;
+                        if (tile >= a.tiles) break;
+                        const int b = tile / per_img, r = tile - b * per_img, ty = r / a.tiles_x, tx = r - ty * a.tiles_x;
+                        const int oy0 = ty * 16, ox0 = tx * 8;
+                        const int bi = q * A_STAGES + as;
+                        mbar_wait(bar(B_AEMPTY + bi), aph ^ 1u);
+                        mbar_expect_tx(bar(B_AFULL + bi), box_bytes);
+                        const uint32_t dst = a_ring + (uint32_t)bi * a_stage;
+                        tma_load_4d(dst, &map_hi, bar(B_AFULL + bi), ca * 32, ox0, oy0, b);
+                        tma_load_4d(dst + (uint32_t)a.a_half, &map_lo, bar(B_AFULL + bi), ca * 32, ox0, oy0, b);
+                    }
                     if (++as == A_STAGES) { as = 0; aph ^= 1u; }
                     for (int kk = 0; kk < kk2; ++kk) {
                         mbar_wait(bar(B_WEMPTY + ws), wph ^ 1u);
@@ -233,8 +243,9 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const __grid_consta
                 }
             }
         }
-    } else if (warp == 1) {
-        // ===== MMA issuer ========================================================================================
+    } else if (warp == 1 || (warp == 3 && a.dual)) {
+        // ===== MMA issuer q (warp 1: q = 0, warp 3: q = 1): its own A ring and accumulators, shared weight stages =====
+        const int q = warp == 3 ? 1 : 0;
         const uint32_t idesc = (1u << 4) | ((uint32_t)(a.Npad >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
         // A: group stride = one halo row (HW pixels of 64 bytes); B: 8 rows of 64 bytes
         const uint32_t a_hiw = ((uint32_t)(a.HW * 64) >> 4) | (1u << 14) | (4u << 29), b_hiw = DESC_HI_64B;
@@ -242,16 +253,28 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const __grid_consta
         int as = 0, ws = 0;
         uint32_t aph = 0, wph = 0, accph[2] = {0, 0};
         int buf = 0;
-        for (int tile = blockIdx.x; tile < a.tiles; tile += gridDim.x) {
-            mbar_wait(bar(B_ACCEMPTY + buf), accph[buf] ^ 1u);      // the epilogue has drained this accumulator
-            tc_fence_after();
-            const uint32_t d = tmem + (uint32_t)(buf * a.Npad);
+        for (int tile0 = blockIdx.x; tile0 < a.tiles; tile0 += nq * gridDim.x) {
+            const bool have = tile0 + q * (int)gridDim.x < a.tiles;   // the last group may have no tile for issuer 1
+            if (have) {
+                mbar_wait(bar(B_ACCEMPTY + 2 * q + buf), accph[buf] ^ 1u);      // the epilogue has drained this accumulator
+                tc_fence_after();
+            }
+            const uint32_t d = tmem + (uint32_t)((2 * q + buf) * a.Npad);
             for (int ca = 0; ca < a.catoms; ++ca) {
-                mbar_wait(bar(B_AFULL + as), aph);
+                if (!have) {   // keep the shared weight ring moving: release the stages without using them
+                    for (int kk = 0; kk < kk2; ++kk) {
+                        mbar_wait(bar(B_WFULL + ws), wph);
+                        if (lane == 0) mbar_arrive(bar(B_WEMPTY + ws));
+                        __syncwarp();
+                        if (++ws == a.w_stages) { ws = 0; wph ^= 1u; }
+                    }
+                    continue;
+                }
+                mbar_wait(bar(B_AFULL + q * A_STAGES + as), aph);
                 // descriptor low words advance by (bytes >> 4): 4 per pixel column (kx), 4 * HW per pixel row (ky);
                 // everything per K atom is adds on running values (an issue thread that rebuilds descriptors paces
                 // the tensor pipe: r1f finding on the stack kernel)
-                const uint32_t ah0 = desc_lo(a_ring + (uint32_t)as * a_stage), al0 = ah0 + ((uint32_t)a.a_half >> 4);
+                const uint32_t ah0 = desc_lo(a_ring + (uint32_t)(q * A_STAGES + as) * a_stage), al0 = ah0 + ((uint32_t)a.a_half >> 4);
                 uint32_t row = 0;
                 int kk = 0;
                 for (int ky = 0; ky < a.k; ++ky, row += 4u * (uint32_t)a.HW) {
@@ -269,8 +292,8 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const __grid_consta
                             tc_mma_hw(d, a_hi + 2, a_hiw, w_lo + 2, b_hiw, idesc, 1);
                             tc_commit(bar(B_WEMPTY + ws));
                             if (kk == kk2 - 1) {
-                                tc_commit(bar(B_AEMPTY + as));
-                                if (ca == a.catoms - 1) tc_commit(bar(B_ACCFULL + buf));
+                                tc_commit(bar(B_AEMPTY + q * A_STAGES + as));
+                                if (ca == a.catoms - 1) tc_commit(bar(B_ACCFULL + 2 * q + buf));
                             }
                         }
                         __syncwarp();
@@ -279,8 +302,10 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const __grid_consta
                 }
                 if (++as == A_STAGES) { as = 0; aph ^= 1u; }
             }
-            accph[buf] ^= 1u;
-            buf ^= 1;
+            if (have) {
+                accph[buf] ^= 1u;
+                buf ^= 1;
+            }
         }
     } else if (warp >= 4) {
         // ===== epilogue ==========================================================================================
@@ -288,44 +313,49 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const __grid_consta
         const float cinv = a.lay[LAY_CINV], s_out = a.lay[LAY_SOUT];
         uint32_t accph[2] = {0, 0};
         int buf = 0;
-        for (int tile = blockIdx.x; tile < a.tiles; tile += gridDim.x) {
-            const int b = tile / per_img, r = tile - b * per_img, ty = r / a.tiles_x, tx = r - ty * a.tiles_x;
-            const int oy = ty * 16 + py, ox = tx * 8 + px;
-            const bool valid = oy < a.Ho && ox < a.Wo;
-            mbar_wait(bar(B_ACCFULL + buf), accph[buf]);
-            tc_fence_after();
-            for (int c = 0; c < a.Npad / 32; ++c) {
-                float v[32];
-                tc_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * a.Npad + c * 32), v);
+        for (int tile0 = blockIdx.x; tile0 < a.tiles; tile0 += nq * gridDim.x) {
+            for (int qq = 0; qq < nq; ++qq) {
+                const int tile = tile0 + qq * (int)gridDim.x;
+                if (tile >= a.tiles) break;
+                const int acc = 2 * qq + buf;                                  // accumulator of issuer qq, buffer buf
+                const int b = tile / per_img, r = tile - b * per_img, ty = r / a.tiles_x, tx = r - ty * a.tiles_x;
+                const int oy = ty * 16 + py, ox = tx * 8 + px;
+                const bool valid = oy < a.Ho && ox < a.Wo;
+                mbar_wait(bar(B_ACCFULL + acc), accph[buf]);
+                tc_fence_after();
+                for (int c = 0; c < a.Npad / 32; ++c) {
+                    float v[32];
+                    tc_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * a.Npad + c * 32), v);
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const int n = c * 32 + i;
-                    float y = fmaf(fmaf(v[i], cinv, vec[n]), vec[a.Npad + n], vec[2 * a.Npad + n]);
-                    v[i] = a.relu ? fmaxf(y, 0.f) : y;
-                }
-                if (valid) {
-                    if (a.out_nchw) {
-                        float *o = a.out_nchw + (((size_t)b * a.N + c * 32) * a.Ho + oy) * a.Wo + ox;
-                        const size_t plane = (size_t)a.Ho * a.Wo;
+                    for (int i = 0; i < 32; ++i) {
+                        const int n = c * 32 + i;
+                        float y = fmaf(fmaf(v[i], cinv, vec[n]), vec[a.Npad + n], vec[2 * a.Npad + n]);
+                        v[i] = a.relu ? fmaxf(y, 0.f) : y;
+                    }
+                    if (valid) {
+                        if (a.out_nchw) {
+                            float *o = a.out_nchw + (((size_t)b * a.N + c * 32) * a.Ho + oy) * a.Wo + ox;
+                            const size_t plane = (size_t)a.Ho * a.Wo;
 #pragma unroll
-                        for (int i = 0; i < 32; ++i)
-                            if (c * 32 + i < a.N) o[(size_t)i * plane] = v[i];
-                    } else {
-                        const size_t off = (((size_t)b * a.Ho + oy) * a.Wo + ox) * a.Cpad_out + c * 32;
-                        uint32_t hi[16], lo[16];
+                            for (int i = 0; i < 32; ++i)
+                                if (c * 32 + i < a.N) o[(size_t)i * plane] = v[i];
+                        } else {
+                            const size_t off = (((size_t)b * a.Ho + oy) * a.Wo + ox) * a.Cpad_out + c * 32;
+                            uint32_t hi[16], lo[16];
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) split2(v[2 * i] * s_out, v[2 * i + 1] * s_out, hi[i], lo[i]);
-                        uint4 *ph4 = reinterpret_cast<uint4 *>(a.out_hi + off), *pl4 = reinterpret_cast<uint4 *>(a.out_lo + off);
+                            for (int i = 0; i < 16; ++i) split2(v[2 * i] * s_out, v[2 * i + 1] * s_out, hi[i], lo[i]);
+                            uint4 *ph4 = reinterpret_cast<uint4 *>(a.out_hi + off), *pl4 = reinterpret_cast<uint4 *>(a.out_lo + off);
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            ph4[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
-                            pl4[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+                            for (int j = 0; j < 4; ++j) {
+                                ph4[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+                                pl4[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+                            }
                         }
                     }
                 }
+                tc_fence_before();
+                mbar_arrive(bar(B_ACCEMPTY + acc));
             }
-            tc_fence_before();
-            mbar_arrive(bar(B_ACCEMPTY + buf));
             accph[buf] ^= 1u;
             buf ^= 1;
         }
@@ -518,8 +548,11 @@ int ctc_conv_layer(const __half *in_hi, const __half *in_lo, int B, int Cpad, in
     a.relu = relu; a.Cpad_out = Cpad_out;
     a.HW = HW;
     a.a_half = (HW * HH * 64 + 1023) & ~1023;
-    const size_t a_bytes = (size_t)ctc::A_STAGES * 2 * a.a_half, w_stage = (size_t)Npad * 128;
-    const size_t misc = 8 * (2 * ctc::A_STAGES + 2 * ctc::MAX_W_STAGES + 4) + 16 + 3 * (size_t)Npad * sizeof(float);
+    // two tiles per weight pass (one issuer warp each) when four accumulators fit in TMEM: halves the weight stream per
+    // pixel and doubles the MMA issue rate, which paces the N = 128 case
+    a.dual = Npad <= 128 && !getenv("EQB_CONV_TC_SINGLE");
+    const size_t a_bytes = (size_t)(a.dual ? 2 : 1) * ctc::A_STAGES * 2 * a.a_half, w_stage = (size_t)Npad * 128;
+    const size_t misc = 8 * (4 * ctc::A_STAGES + 2 * ctc::MAX_W_STAGES + 8) + 16 + 3 * (size_t)Npad * sizeof(float);
     int w_stages = (int)((227 * 1024 - misc - a_bytes) / w_stage);
     if (w_stages > ctc::MAX_W_STAGES) w_stages = ctc::MAX_W_STAGES;
     EQB_UNSUPPORTED(w_stages < 2, "eqb_conv_stack (tcgen05): operand rings do not fit in shared memory (k = %d, N = %d)", k, Npad);
