@@ -17,7 +17,7 @@ assertion on a kornia output (tests/images/canonicalization/test_discrete_group.
 asserts nothing).  It is anchored by (i) the reference's own hand-derived affine matrix in
 equiadapt/images/canonicalization/continuous_group.py:195-204, which is the same
 OpenCV `getRotationMatrix2D` formula, and (ii) the closed-form properties checked in
-tests/test_oracle_kornia.py (rotate(+90) == rot90(k=1) up to fp32 coefficient noise,
+tests/test_oracle_golden.py (rotate(+90) == rot90(k=1) up to fp32 coefficient noise,
 1x1 kernels unchanged, closed-form sampling positions).
 
 Reference call sites of these functions:

@@ -827,3 +827,29 @@ def test_cfg2_index_parity_on_smooth_images(cuda_device):
     assert agree_ours >= agree_ref
     ang = torch.linspace(0.0, 360.0, 9)[:8][idx]
     assert rel_err(y.cpu(), O.canonicalize_image(x, ang, None)) < RTOL
+
+
+def test_host_streamed_pipeline_equals_direct_call(cuda_device):
+    """HostStreamedCanonicalizer (pinned host in / out, sharded H2D / compute / D2H streams) gives bit-identical outputs
+    and the same prior statistic as one un-sharded call on device tensors, including a ragged last shard."""
+    from equiadapt_b200.host_pipeline import HostStreamedCanonicalizer
+    _, GEIC, _, Net = _mods()
+    dev = cuda_device
+    torch.manual_seed(70)
+    net = Net((3, 32, 32), 8, 5, "rotation", 8, 3, device="cpu").to(dev)
+    can = GEIC(net, SimpleNamespace(beta=1.0, input_crop_ratio=0.8, resize_shape=32), (3, 64, 64)).eval()
+    x = torch.rand(77, 3, 64, 64, generator=torch.Generator().manual_seed(71))
+    with torch.no_grad():
+        y = can(x.to(dev))
+        z = can.invert_canonicalization(y, induced_rep_type="scalar")
+        loss, ident = float(can.get_prior_regularization_loss()), float(can.get_identity_metric())
+        x_host, out_host = x.pin_memory(), torch.empty_like(x).pin_memory()
+        pipe = HostStreamedCanonicalizer(can, None, "scalar", shard=16, slots=3, device=dev)
+        for _ in range(2):                      # second call reuses the slots
+            out_host.zero_()
+            l2, i2 = pipe(x_host, out_host)
+            torch.cuda.synchronize()
+            assert torch.equal(out_host, z.cpu())
+            assert abs(float(l2) - loss) < 1e-6 and abs(float(i2) - ident) < 1e-6
+    with pytest.raises(ValueError):
+        pipe(x, out_host)                       # unpinned input
