@@ -306,7 +306,7 @@ struct ConvPlan {
     // tcgen05 inner layers (conv_stack_tc.cu): fp16 hi/lo NHWC ping-pong buffers, packed weights, layer records
     bool tc;
     size_t off_h[2][2], off_wp[16], off_lay, off_absmax, off_rowstat, off_xin[2];
-    int cpad0;             // input channels padded to 32 (layer 0 on the tensor path)
+    int cpad0;             // input channels padded to a whole K atom: 16, or a multiple of 32 (layer 0 on the tensor path)
 };
 
 static int conv_make_plan(int B, int cin, int H, int W, int cout, int k, int G, int L, ConvPlan &p) {
@@ -355,6 +355,7 @@ static int conv_make_plan(int B, int cin, int H, int W, int cout, int k, int G, 
     for (int l = 1; l <= L - 2; ++l)   // every tcgen05 layer's input must hold at least one halo box (8+k-1) x (16+k-1)
         if (p.Wo[l - 1] < 8 + k - 1 || p.Ho[l - 1] < 16 + k - 1) p.tc = false;
     if (W < 8 + k - 1 || H < 16 + k - 1) p.tc = false;
+    p.cpad0 = cin <= 16 ? 16 : (cin + 31) / 32 * 32;
     if (p.tc) {
         off = (off + 1023) & ~(size_t)1023;
         const size_t hbytes = (((size_t)(B > 0 ? B : 1) * p.P[0] * p.Npad * sizeof(__half)) + 1023) & ~(size_t)1023;
@@ -365,10 +366,9 @@ static int conv_make_plan(int B, int cin, int H, int W, int cout, int k, int G, 
             }
         for (int l = 1; l <= L - 2; ++l) {
             p.off_wp[l] = off;
-            off += (ctc_pack_bytes(p.Npad, p.N, k) + 1023) & ~(size_t)1023;
+            off += (ctc_pack_bytes(p.Npad, p.Npad, k) + 1023) & ~(size_t)1023;
         }
-        p.cpad0 = (cin + 31) / 32 * 32;
-        p.off_wp[0] = off; off += (ctc_pack_bytes(p.Npad, cin, k) + 1023) & ~(size_t)1023;
+        p.off_wp[0] = off; off += (ctc_pack_bytes(p.Npad, p.cpad0, k) + 1023) & ~(size_t)1023;
         const size_t xbytes = (((size_t)(B > 0 ? B : 1) * H * W * p.cpad0 * sizeof(__half)) + 1023) & ~(size_t)1023;
         p.off_xin[0] = off; off += xbytes;
         p.off_xin[1] = off; off += xbytes;
@@ -437,11 +437,10 @@ extern "C" int eqb_conv_stack_forward(const float *x, int B, int cin, int H, int
                                     (float *)(ws + p.off_rowstat), st);
             if (e) return e;
             unsigned char *wp = (unsigned char *)(ws + p.off_wp[l]);
-            e = ctc_pack(filters[l], lay_l, p.N, p.cin[l], k, p.Npad, wp, st);
+            const int cpad_in = l == 0 ? p.cpad0 : p.Npad;
+            e = ctc_pack(filters[l], lay_l, p.N, p.cin[l], cpad_in, k, p.Npad, wp, st);
             if (e) return e;
-            int cpad_in = p.Npad;
-            if (l == 0) {   // the network input becomes the first fp16 pair (channels padded to 32)
-                cpad_in = p.cpad0;
+            if (l == 0) {   // the network input becomes the first fp16 pair (channels padded to a whole K atom)
                 __half *xh = (__half *)(ws + p.off_xin[0]), *xl = (__half *)(ws + p.off_xin[1]);
                 e = ctc_input_split(x, (const float *)(ws + p.off_absmax), B, cin, H, W, cpad_in, xh, xl, st);
                 if (e) return e;

@@ -161,6 +161,8 @@ struct Args {
     int B, k, Ho, Wo, N, Npad, catoms, tiles_x, tiles_y, tiles, relu, Cpad_out;
     int HW, a_half, w_stages;              // halo width (8 + k - 1), bytes of one halo box (1024-rounded), weight ring depth
     int dual;                              // two tiles per weight pass, one MMA issuer warp each (Npad <= 128)
+    int cw;                                // channels per K atom: 32 (64-byte rows, SWIZZLE_64B, two K-steps) or 16 (32-byte
+                                           // rows, SWIZZLE_32B, one K-step; used when the layer has <= 16 input channels)
 };
 
 __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap map_hi,
@@ -169,7 +171,8 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const __grid_consta
     const uint32_t base = smem_u32(smem_raw);
     if ((base & 1023u) != 0) __trap();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t a_stage = 2u * (uint32_t)a.a_half, w_stage = (uint32_t)a.Npad * 128u;
+    const uint32_t rowb = 2u * (uint32_t)a.cw;                               // bytes of one operand row (cw fp16 channels)
+    const uint32_t a_stage = 2u * (uint32_t)a.a_half, w_stage = (uint32_t)a.Npad * 2u * rowb;
     const int nq = a.dual ? 2 : 1;                                           // MMA issuers = tiles in flight per weight pass
     const uint32_t a_ring = base, w_ring = base + (uint32_t)nq * A_STAGES * a_stage;   // A ring of issuer q at a_ring + q * A_STAGES * a_stage
     const uint32_t misc = w_ring + (uint32_t)a.w_stages * w_stage;          // barriers, TMEM slot, per-channel vectors
@@ -216,7 +219,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const __grid_consta
         if (lane == 0) {
             int as = 0, ws = 0;
             uint32_t aph = 0, wph = 0;
-            const uint32_t box_bytes = 2u * (uint32_t)(a.HW * (16 + a.k - 1) * 64);
+            const uint32_t box_bytes = 2u * (uint32_t)(a.HW * (16 + a.k - 1)) * rowb;
             // tiles are taken nq at a time: issuer q works on tile0 + q * gridDim.x with the SAME weight stages
             for (int tile0 = blockIdx.x; tile0 < a.tiles; tile0 += nq * gridDim.x) {
                 for (int ca = 0; ca < a.catoms; ++ca) {
@@ -229,8 +232,8 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const __grid_consta
                         mbar_wait(bar(B_AEMPTY + bi), aph ^ 1u);
                         mbar_expect_tx(bar(B_AFULL + bi), box_bytes);
                         const uint32_t dst = a_ring + (uint32_t)bi * a_stage;
-                        tma_load_4d(dst, &map_hi, bar(B_AFULL + bi), ca * 32, ox0, oy0, b);
-                        tma_load_4d(dst + (uint32_t)a.a_half, &map_lo, bar(B_AFULL + bi), ca * 32, ox0, oy0, b);
+                        tma_load_4d(dst, &map_hi, bar(B_AFULL + bi), ca * a.cw, ox0, oy0, b);
+                        tma_load_4d(dst + (uint32_t)a.a_half, &map_lo, bar(B_AFULL + bi), ca * a.cw, ox0, oy0, b);
                     }
                     if (++as == A_STAGES) { as = 0; aph ^= 1u; }
                     for (int kk = 0; kk < kk2; ++kk) {
@@ -247,9 +250,13 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const __grid_consta
         // ===== MMA issuer q (warp 1: q = 0, warp 3: q = 1): its own A ring and accumulators, shared weight stages =====
         const int q = warp == 3 ? 1 : 0;
         const uint32_t idesc = (1u << 4) | ((uint32_t)(a.Npad >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-        // A: group stride = one halo row (HW pixels of 64 bytes); B: 8 rows of 64 bytes
-        const uint32_t a_hiw = ((uint32_t)(a.HW * 64) >> 4) | (1u << 14) | (4u << 29), b_hiw = DESC_HI_64B;
-        const uint32_t w_lo0 = desc_lo(w_ring), w_step = w_stage >> 4, w_lo_off = ((uint32_t)a.Npad * 64u) >> 4;
+        // A: group stride = one halo row (HW pixels of rowb bytes); B: 8 rows of rowb bytes; layout type 4 = SWIZZLE_64B,
+        // 6 = SWIZZLE_32B
+        const uint32_t lt = a.cw == 32 ? 4u : 6u;
+        const uint32_t a_hiw = (((uint32_t)a.HW * rowb) >> 4) | (1u << 14) | (lt << 29), b_hiw = ((8u * rowb) >> 4) | (1u << 14) | (lt << 29);
+        const uint32_t w_lo0 = desc_lo(w_ring), w_step = w_stage >> 4, w_lo_off = ((uint32_t)a.Npad * rowb) >> 4;
+        const uint32_t px16 = rowb >> 4;           // descriptor units (16 bytes) per pixel row of the operand
+        const bool two_steps = a.cw == 32;
         int as = 0, ws = 0;
         uint32_t aph = 0, wph = 0, accph[2] = {0, 0};
         int buf = 0;
@@ -277,19 +284,19 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const __grid_consta
                 const uint32_t ah0 = desc_lo(a_ring + (uint32_t)(q * A_STAGES + as) * a_stage), al0 = ah0 + ((uint32_t)a.a_half >> 4);
                 uint32_t row = 0;
                 int kk = 0;
-                for (int ky = 0; ky < a.k; ++ky, row += 4u * (uint32_t)a.HW) {
+                for (int ky = 0; ky < a.k; ++ky, row += px16 * (uint32_t)a.HW) {
                     for (int kx = 0; kx < a.k; ++kx, ++kk) {
                         mbar_wait(bar(B_WFULL + ws), wph);
                         tc_fence_after();
                         if (elect_one()) {
-                            const uint32_t a_hi = ah0 + row + 4u * (uint32_t)kx, a_lo = al0 + row + 4u * (uint32_t)kx;
+                            const uint32_t a_hi = ah0 + row + px16 * (uint32_t)kx, a_lo = al0 + row + px16 * (uint32_t)kx;
                             const uint32_t w_hi = w_lo0 + (uint32_t)ws * w_step, w_lo = w_hi + w_lo_off;
                             tc_mma_hw(d, a_hi, a_hiw, w_hi, b_hiw, idesc, (ca | kk) != 0);
-                            tc_mma_hw(d, a_hi + 2, a_hiw, w_hi + 2, b_hiw, idesc, 1);
+                            if (two_steps) tc_mma_hw(d, a_hi + 2, a_hiw, w_hi + 2, b_hiw, idesc, 1);
                             tc_mma_hw(d, a_lo, a_hiw, w_hi, b_hiw, idesc, 1);
-                            tc_mma_hw(d, a_lo + 2, a_hiw, w_hi + 2, b_hiw, idesc, 1);
+                            if (two_steps) tc_mma_hw(d, a_lo + 2, a_hiw, w_hi + 2, b_hiw, idesc, 1);
                             tc_mma_hw(d, a_hi, a_hiw, w_lo, b_hiw, idesc, 1);
-                            tc_mma_hw(d, a_hi + 2, a_hiw, w_lo + 2, b_hiw, idesc, 1);
+                            if (two_steps) tc_mma_hw(d, a_hi + 2, a_hiw, w_lo + 2, b_hiw, idesc, 1);
                             tc_commit(bar(B_WEMPTY + ws));
                             if (kk == kk2 - 1) {
                                 tc_commit(bar(B_AEMPTY + q * A_STAGES + as));
@@ -422,23 +429,26 @@ __global__ void __launch_bounds__(256) ctc_layer_stats_kernel(const float *__res
     }
 }
 
-// filter (N, C, k, k) fp32 -> per atom (32-channel group, then ky, kx) an Npad x 64-byte hi image followed by the lo image,
-// SWIZZLE_64B (16-byte chunk index XOR ((n >> 1) & 3)), scaled by sw; rows >= N and channels >= C are zero
+// filter (N, C, k, k) fp32 -> per atom (cw-channel group, then ky, kx) an Npad x (2 cw)-byte hi image followed by the lo
+// image, swizzled for the UMMA descriptor, scaled by sw; rows >= N and channels >= C are zero
 __global__ void ctc_pack_kernel(const float *__restrict__ w, const float *__restrict__ lay, int N, int C, int k, int Npad,
-                                int catoms, unsigned char *__restrict__ out) {
+                                int catoms, int cw, unsigned char *__restrict__ out) {
     const float sw = lay[LAY_SW];
-    const long long total = (long long)k * k * catoms * Npad * 32;
+    const long long total = (long long)k * k * catoms * Npad * cw;
+    const size_t rowb = 2 * (size_t)cw;
     for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-        const int ks = (int)(t % 32), n = (int)((t / 32) % Npad);
-        const int atom = (int)(t / (32LL * Npad));
+        const int ks = (int)(t % cw), n = (int)((t / cw) % Npad);
+        const int atom = (int)(t / ((long long)cw * Npad));
         const int ca = atom / (k * k), kk = atom - ca * (k * k), ky = kk / k, kx = kk - ky * k;
-        const int c = ca * 32 + ks;
+        const int c = ca * cw + ks;
         const float v = (n < N && c < C) ? w[(((size_t)n * C + c) * k + ky) * k + kx] * sw : 0.f;
         const __half hi = __float2half_rn(v), lo = __float2half_rn(v - __half2float(hi));
-        const size_t stage = (size_t)Npad * 128;
-        const size_t off = (size_t)n * 64 + (size_t)((((ks >> 3) ^ ((n >> 1) & 3)) << 4) | ((ks & 7) << 1));
+        const size_t stage = (size_t)Npad * 2 * rowb;
+        // 16-byte chunk index XOR: SWIZZLE_64B (cw = 32): (n >> 1) & 3;  SWIZZLE_32B (cw = 16): (n >> 2) & 1
+        const int x = cw == 32 ? ((n >> 1) & 3) : ((n >> 2) & 1);
+        const size_t off = (size_t)n * rowb + (size_t)((((ks >> 3) ^ x) << 4) | ((ks & 7) << 1));
         *reinterpret_cast<__half *>(out + (size_t)atom * stage + off) = hi;
-        *reinterpret_cast<__half *>(out + (size_t)atom * stage + (size_t)Npad * 64 + off) = lo;
+        *reinterpret_cast<__half *>(out + (size_t)atom * stage + (size_t)Npad * rowb + off) = lo;
     }
 }
 
@@ -479,7 +489,7 @@ static EncodeTiledFn encode_fn() {
     return fn;
 }
 // (C, W, H, B) fp16 NHWC tensor, box 32 x HW x HH x 1 (the 8 x 16 output patch with its halo), SWIZZLE_64B
-static int make_act_map(CUtensorMap *m, const void *ptr, int Cpad, int W, int H, int B, int HW, int HH) {
+static int make_act_map(CUtensorMap *m, const void *ptr, int Cpad, int W, int H, int B, int HW, int HH, int cw) {
     EncodeTiledFn enc = encode_fn();
     if (!enc) {
         set_error("cuTensorMapEncodeTiled is not available from the CUDA driver");
@@ -487,9 +497,10 @@ static int make_act_map(CUtensorMap *m, const void *ptr, int Cpad, int W, int H,
     }
     const cuuint64_t gdim[4] = {(cuuint64_t)Cpad, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
     const cuuint64_t gstride[3] = {(cuuint64_t)Cpad * 2, (cuuint64_t)W * Cpad * 2, (cuuint64_t)H * W * Cpad * 2};
-    const cuuint32_t box[4] = {32, (cuuint32_t)HW, (cuuint32_t)HH, 1}, estr[4] = {1, 1, 1, 1};
+    const cuuint32_t box[4] = {(cuuint32_t)cw, (cuuint32_t)HW, (cuuint32_t)HH, 1}, estr[4] = {1, 1, 1, 1};
     const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void *>(ptr), gdim, gstride, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, cw == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled failed with CUresult %d (C=%d W=%d H=%d B=%d)", (int)r, Cpad, W, H, B);
@@ -505,7 +516,10 @@ bool ctc_eligible(int Npad, int num_layers) {
     return num_layers >= 2 && Npad >= 32 && Npad <= 256;
 }
 
-size_t ctc_pack_bytes(int Npad, int C, int k) { return (size_t)k * k * ((C + 31) / 32) * Npad * 128; }
+// channels per K atom for an operand whose channel count is padded to Cpad: 32 (64-byte rows) or 16 (32-byte rows)
+int ctc_atom_channels(int Cpad) { return Cpad % 32 == 0 ? 32 : 16; }
+
+size_t ctc_pack_bytes(int Npad, int Cpad, int k) { return (size_t)k * k * Cpad * Npad * 4; }
 
 int ctc_layer_stats(const float *w, const float *vecs, int N, int Npad, int K, const float *in_bound_ptr, int tensor_in,
                     float *lay, float *nxt, float *rowstat, cudaStream_t st) {
@@ -524,8 +538,9 @@ int ctc_input_split(const float *x, const float *absmax, int B, int C, int H, in
     return finish_launch("ctc_input_split_kernel");
 }
 
-int ctc_pack(const float *w, const float *lay, int N, int C, int k, int Npad, unsigned char *out, cudaStream_t st) {
-    ctc::ctc_pack_kernel<<<256, 256, 0, st>>>(w, lay, N, C, k, Npad, (C + 31) / 32, out);
+int ctc_pack(const float *w, const float *lay, int N, int C, int Cpad, int k, int Npad, unsigned char *out, cudaStream_t st) {
+    const int cw = ctc_atom_channels(Cpad);
+    ctc::ctc_pack_kernel<<<256, 256, 0, st>>>(w, lay, N, C, k, Npad, Cpad / cw, cw, out);
     return finish_launch("ctc_pack_kernel");
 }
 
@@ -535,23 +550,24 @@ int ctc_conv_layer(const __half *in_hi, const __half *in_lo, int B, int Cpad, in
     const int HW = 8 + k - 1, HH = 16 + k - 1;
     EQB_UNSUPPORTED(HW > 256 || HH > 256, "eqb_conv_stack (tcgen05): kernel size %d too large for one TMA box", k);
     CUtensorMap mh, ml;
-    int e = ctc::make_act_map(&mh, in_hi, Cpad, W, H, B, HW, HH);
+    const int cw = ctc_atom_channels(Cpad);
+    int e = ctc::make_act_map(&mh, in_hi, Cpad, W, H, B, HW, HH, cw);
     if (e) return e;
-    e = ctc::make_act_map(&ml, in_lo, Cpad, W, H, B, HW, HH);
+    e = ctc::make_act_map(&ml, in_lo, Cpad, W, H, B, HW, HH, cw);
     if (e) return e;
     ctc::Args a{};
     a.wpack = wpack; a.bias = vecs; a.scale = vecs + Npad; a.shift = vecs + 2 * Npad; a.lay = lay;
     a.out_nchw = out_nchw; a.out_hi = out_hi; a.out_lo = out_lo;
     a.B = B; a.k = k; a.Ho = H - k + 1; a.Wo = W - k + 1; a.N = N; a.Npad = Npad;
-    a.catoms = Cpad / 32;
+    a.catoms = Cpad / cw; a.cw = cw;
     a.tiles_x = (a.Wo + 7) / 8; a.tiles_y = (a.Ho + 15) / 16; a.tiles = B * a.tiles_x * a.tiles_y;
     a.relu = relu; a.Cpad_out = Cpad_out;
     a.HW = HW;
-    a.a_half = (HW * HH * 64 + 1023) & ~1023;
+    a.a_half = (HW * HH * 2 * cw + 1023) & ~1023;
     // two tiles per weight pass (one issuer warp each) when four accumulators fit in TMEM: halves the weight stream per
     // pixel and doubles the MMA issue rate, which paces the N = 128 case
     a.dual = Npad <= 128 && !getenv("EQB_CONV_TC_SINGLE");
-    const size_t a_bytes = (size_t)(a.dual ? 2 : 1) * ctc::A_STAGES * 2 * a.a_half, w_stage = (size_t)Npad * 128;
+    const size_t a_bytes = (size_t)(a.dual ? 2 : 1) * ctc::A_STAGES * 2 * a.a_half, w_stage = (size_t)Npad * 4 * cw;
     const size_t misc = 8 * (4 * ctc::A_STAGES + 2 * ctc::MAX_W_STAGES + 8) + 16 + 3 * (size_t)Npad * sizeof(float);
     int w_stages = (int)((227 * 1024 - misc - a_bytes) / w_stage);
     if (w_stages > ctc::MAX_W_STAGES) w_stages = ctc::MAX_W_STAGES;
