@@ -355,7 +355,9 @@ def vnsmall_forward(x: torch.Tensor, params: torch.Tensor, n_knn: int, bn_eps: f
         raise ValueError("parameter block has the wrong size")
     b, _, n = x.shape
     out = torch.empty((b, 3, 3), dtype=torch.float32, device=dev)
-    _call("eqb_vnsmall_forward", 1, dev, _ptr(x), b, n, _ptr(params), int(n_knn), float(bn_eps), _ptr(out), _stream(dev))
+    ws = torch.empty((max(int(native.lib().eqb_vnsmall_workspace_bytes(b, n)), 8),), dtype=torch.uint8, device=dev)
+    _call("eqb_vnsmall_forward", 2, dev, _ptr(x), b, n, _ptr(params), int(n_knn), float(bn_eps), _ptr(out), _ptr(ws),
+          ws.numel(), _stream(dev))
     return out
 
 

@@ -172,10 +172,13 @@ EQB_API int eqb_warp_affine(const float *x, float *y, const float *mats, const f
  * `params`: eqb_vnsmall_param_count() floats = the raw tensors of the reference module, concatenated in the order
  *   conv_pos.{map_to_feat.weight, map_to_dir.weight, batchnorm.bn2d.{weight, bias, running_mean, running_var}},
  *   conv1.{map_to_feat.weight, map_to_dir.weight, batchnorm.bn1d.{...}}, bn1.bn1d.{...},
- *   conv2.{map_to_feat.weight, map_to_dir.weight, batchnorm.bn1d.{...}};   bn_eps = the batch norms' eps. */
+ *   conv2.{map_to_feat.weight, map_to_dir.weight, batchnorm.bn1d.{...}};   bn_eps = the batch norms' eps.
+ * `workspace` >= eqb_vnsmall_workspace_bytes(B, N) bytes of device scratch, 8-byte aligned (a cloud is split over
+ * several CTAs when the batch alone cannot fill the GPU). */
 EQB_API int eqb_vnsmall_param_count(void);
+EQB_API int64_t eqb_vnsmall_workspace_bytes(int B, int N);
 EQB_API int eqb_vnsmall_forward(const float *x, int B, int N, const float *params, int n_knn, float bn_eps, float *out,
-                                void *stream);
+                                void *workspace, int64_t workspace_bytes, void *stream);
 /* VNDeepSets.forward (nbody/canonicalization_networks/custom_equivariant_networks.py:106-172; VNDeepSetLayer
  * :175-252; VNLeakyReLU / VNSoftplus custom_group_equivariant_layers.py:7-99) for S systems of 5 consecutive rows:
  * loc, vel (5S,3), charges (5S) (vel / charges may be NULL when no feature uses them), edges (2,E) int64 = rows

@@ -46,8 +46,8 @@ def test_argument_validation_without_gpu(lib):
     assert lib.eqb_conv_stack_workspace_bytes(4, 3, 96, 96, 128, 5, 4, 3) == native.EQB_ERR_UNSUPPORTED   # N = 512 > 256
     assert lib.eqb_conv_stack_workspace_bytes(4, 3, 8, 8, 8, 5, 4, 3) == native.EQB_ERR_INVALID           # map shrinks below k
     assert lib.eqb_vnsmall_param_count() == 1444
-    assert lib.eqb_vnsmall_forward(None, 2, 8, None, 20, 1e-5, None, None) == native.EQB_ERR_INVALID      # k > N
-    assert lib.eqb_vnsmall_forward(None, 2, 64, None, 40, 1e-5, None, None) == native.EQB_ERR_UNSUPPORTED # k > 32
+    assert lib.eqb_vnsmall_forward(None, 2, 8, None, 20, 1e-5, None, None, 0, None) == native.EQB_ERR_INVALID      # k > N
+    assert lib.eqb_vnsmall_forward(None, 2, 64, None, 40, 1e-5, None, None, 0, None) == native.EQB_ERR_UNSUPPORTED # k > 32
     assert lib.eqb_vndeepsets_param_count(1, 16, 4) == 2788
     assert lib.eqb_vndeepsets_forward(None, None, None, None, 0, 3, None, 2, 16, 4, 0, 0, 0, 0, 1, 1, 0, None, None, None, 0,
                                       None, None) == native.EQB_ERR_INVALID                               # in_dim vs feature flags

@@ -23,6 +23,10 @@ x = torch.randn(128, 3, 1024, device=dev)
 with torch.no_grad():
     ms = timeit(lambda: (can(x), can.get_prior_regularization_loss()))
 print(f"cfg4 pointcloud SO(3) B=128 N=1024: {ms:.3f} ms/batch, {128 / ms * 1e3:.0f} clouds/s")
+x16 = x[:16].contiguous()
+with torch.no_grad():
+    ms = timeit(lambda: (can(x16), can.get_prior_regularization_loss()))
+print(f"cfg4 per-GPU shard of the 8-GPU configuration, B=16 N=1024: {ms:.3f} ms/batch, {16 / ms * 1e3:.0f} clouds/s")
 S = 10000
 hp = NS(out_dim=4, hidden_dim=16, layer_pooling="mean", final_pooling="mean", num_layers=4, nonlinearity="relu",
         canon_feature="p", canon_translation=False, angular_feature=0, dropout=0.5, batch_size=S)
