@@ -853,3 +853,19 @@ def test_host_streamed_pipeline_equals_direct_call(cuda_device):
             assert abs(float(l2) - loss) < 1e-6 and abs(float(i2) - ident) < 1e-6
     with pytest.raises(ValueError):
         pipe(x, out_host)                       # unpinned input
+
+
+@pytest.mark.parametrize("b", [1, 2, 3, 17, 150])
+def test_stack_kernels_agree_for_any_batch_size(b, cuda_device):
+    """Work partition of the persistent kernels (items = image x chunk of tiles, clusters of two CTAs) for batch sizes
+    below, at and above the SM count: CTA-pair kernel == single-CTA tcgen05 kernel == SIMT kernel on every row."""
+    _, _, _, Net = _mods()
+    torch.manual_seed(80)
+    net = Net((3, 40, 40), 32, 5, "rotation", 8, 3, device="cpu")        # N = 256, K = 75: pair kernel by default
+    x = torch.rand(b, 3, 40, 40, generator=torch.Generator().manual_seed(81))
+    act_pair = _stack_act(net, x, cuda_device, no_tc=False)
+    act_single = _stack_act(net, x, cuda_device, no_tc=False, no_pair=True)
+    act_simt = _stack_act(net, x, cuda_device, no_tc=True)
+    assert act_pair.shape == (b, 8)
+    assert rel_err(act_pair, act_simt) < 2e-5 and rel_err(act_single, act_simt) < 2e-5
+    assert rel_err(act_pair, act_single) < 2e-6
