@@ -269,6 +269,18 @@ def run_b200(args):
             loss_p, ident_p = float(loss), float(ident)
             torch.cuda.synchronize()
         e2e_s = time.perf_counter() - t0
+        # informational: the training-loop shape of the same step - inputs from pinned host memory, only the loss and
+        # the metric read back (the canonicalized / inverted batches stay on the device for their consumer)
+        for _ in range(2):
+            loss, ident = pipe(x_host, None)
+            float(loss)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            loss, ident = pipe(x_host, None)
+            float(loss), float(ident)
+            torch.cuda.synchronize()
+        e2e_in_s = time.perf_counter() - t0
         # what the link allows: plain pinned copies of the same buffers (the e2e step moves exactly these bytes)
         s1, s2 = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
         zd = torch.empty_like(x)
@@ -349,7 +361,9 @@ def run_b200(args):
                     "ms_per_step": 1e3 * e2e_s / args.e2e_steps,
                     "how": f"HostStreamedCanonicalizer: pinned host -> {args.e2e_shard}-image shards over h2d/compute/d2h "
                            "streams -> pinned host, loss + metric read back every step",
-                    "unpipelined_value": B * world * args.e2e_steps / e2e_serial_s},
+                    "unpipelined_value": B * world * args.e2e_steps / e2e_serial_s,
+                    "inputs_only_value": B * world * args.e2e_steps / e2e_in_s,
+                    "inputs_only_note": "same step with only loss + metric read back (8 bytes D2H): not max-reduced over ranks"},
             "pcie": pcie,
             "gpu_launches": launches * args.steps,
             "gpu_launches_per_step": launches,

@@ -59,17 +59,18 @@ class HostStreamedCanonicalizer:
         if self._x_dev is None or tuple(self._x_dev.shape) != want or self._x_dev.dtype != dtype:
             self._x_dev = torch.empty(want, dtype=dtype, device=self.device)
 
-    def __call__(self, x_host: torch.Tensor, out_host: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    def __call__(self, x_host: torch.Tensor, out_host: Optional[torch.Tensor]) -> Tuple[torch.Tensor, torch.Tensor]:
         """x_host (B,C,H,W) pinned -> out_host (B,C',H,W) pinned; returns (prior loss, identity metric) as
         0-d device tensors.  The call returns with all work enqueued; the caller's current stream waits on
         the last D2H copy, so reading `out_host` after synchronising that stream (or after `.item()` on
-        either returned tensor followed by a stream sync) is safe."""
-        if x_host.is_cuda or out_host.is_cuda:
+        either returned tensor followed by a stream sync) is safe.  out_host = None: nothing but the two scalars
+        leaves the device (the training-loop shape: the canonicalized batch feeds a device-side consumer)."""
+        if x_host.is_cuda or (out_host is not None and out_host.is_cuda):
             raise ValueError("HostStreamedCanonicalizer takes HOST tensors; call the canonicalizer directly on device tensors")
-        if not (x_host.is_pinned() and out_host.is_pinned()):
+        if not (x_host.is_pinned() and (out_host is None or out_host.is_pinned())):
             raise ValueError("host buffers must be pinned (torch.Tensor.pin_memory) for asynchronous copies")
         B = x_host.shape[0]
-        if out_host.shape[0] != B:
+        if out_host is not None and out_host.shape[0] != B:
             raise ValueError("output buffer must hold one result per input sample")
         self._ensure_slots(x_host.shape[1:], x_host.dtype)
         cur = torch.cuda.current_stream(self.device)
@@ -103,10 +104,11 @@ class HostStreamedCanonicalizer:
                 stats_sum = st[:3].clone() if stats_sum is None else stats_sum.add_(st[:3])
                 cmp_done[s] = self.s_cmp.record_event()
                 keep[s] = (y, f, z)
-            with torch.cuda.stream(self.s_d2h):
-                self.s_d2h.wait_event(cmp_done[s])
-                out_host[lo:hi].copy_(z, non_blocking=True)
-                d2h_done[s] = self.s_d2h.record_event()
+            if out_host is not None:
+                with torch.cuda.stream(self.s_d2h):
+                    self.s_d2h.wait_event(cmp_done[s])
+                    out_host[lo:hi].copy_(z, non_blocking=True)
+                    d2h_done[s] = self.s_d2h.record_event()
         self.can.prefetch_prior_allreduce = prefetch
         with torch.cuda.stream(self.s_cmp):
             for ev in d2h_done:
