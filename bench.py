@@ -40,9 +40,9 @@ IMG_BYTES = 2 * 3 * 224 * 224 * 4                      # warp: 1 read + 1 write 
 STACK_FLOP_EXECUTED = 2 * 92 * 92 * 256 * (75 + 256)   # lift + one 1x1 layer; the last layer is folded
 STACK_FLOP_REFERENCE = 2 * 92 * 92 * 256 * (75 + 256 + 256)
 # dram__bytes_read.sum + dram__bytes_write.sum per launch at the default batch of 512, from the ncu --set full
-# captures summarised under profiles/ (r1h: conv stack; r1b: warp kernels); None = not captured
-NCU_TRAFFIC = {"eqb_gconv_stack_run": 57.0e6 + 0.9e6, "eqb_warp_canonicalize": None, "eqb_warp_invert": None,
-               "eqb_crop_resize_aa": None}
+# captures summarised under profiles/r1h_summary.md (pass S: conv stack and warp kernels; pass Q: crop + resize)
+NCU_TRAFFIC = {"eqb_gconv_stack_run": 57.0e6 + 2.0e6, "eqb_warp_canonicalize": 292.6e6 + 261.4e6,
+               "eqb_warp_invert": 292.6e6 + 263.5e6, "eqb_crop_resize_aa": 247.8e6 + 43.3e6}
 
 
 def peaks():
