@@ -135,19 +135,69 @@ def workload_config(batch, n_gpus):
 # B200 arm
 # ---------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock / throttle reasons of one GPU, sampled every ~2 ms by an NVML thread while the timed region runs
+    (nvidia-smi -lms needs ~100 ms to start and cannot resolve a 40 ms region; it is the fallback when NVML is
+    not importable)."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index):
-        self.proc = None
+        import threading
+        self.proc, self.thread, self.samples, self.stop_flag = None, None, [], False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            try:
+                uuid = torch.cuda.get_device_properties(index).uuid
+                h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + str(uuid)).encode())
+            except Exception:
+                vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+                phys = int(vis.split(",")[index]) if vis and vis.split(",")[index].isdigit() else index
+                h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nvml, self.h = pynvml, h
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._run, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.thread = None
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
+                ["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             pass
 
+    def _run(self):
+        n = self.nvml
+        reasons_fn = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self.stop_flag:
+            try:
+                mhz = float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM))
+                mask = int(reasons_fn(self.h))
+                try:
+                    watts = n.nvmlDeviceGetPowerUsage(self.h) / 1e3
+                except Exception:
+                    watts = None
+                self.samples.append((mhz, mask, watts))
+            except Exception:
+                pass
+            time.sleep(0.002)
+
     def stop(self):
+        if self.thread is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=2)
+            n = self.nvml
+            bits = {"hw_slowdown": getattr(n, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                    "hw_thermal_slowdown": getattr(n, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                    "sw_thermal_slowdown": getattr(n, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                    "sw_power_cap": getattr(n, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+            sm = sorted(s[0] for s in self.samples)
+            reasons = sorted(k for k, b in bits.items() if any(s[1] & b for s in self.samples))
+            power = [s[2] for s in self.samples if s[2] is not None]
+            return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz,
+                    "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": reasons, "source": "nvml"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.06)
@@ -172,7 +222,8 @@ class ClockSampler:
                     reasons.add(n)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons),
+                "source": "nvidia-smi"}
 
 
 def run_b200(args):
