@@ -869,3 +869,30 @@ def test_stack_kernels_agree_for_any_batch_size(b, cuda_device):
     assert act_pair.shape == (b, 8)
     assert rel_err(act_pair, act_simt) < 2e-5 and rel_err(act_single, act_simt) < 2e-5
     assert rel_err(act_pair, act_single) < 2e-6
+
+
+@pytest.mark.parametrize("scale", [1e-6, 1e-3, 1.0, 255.0, 1e5])
+def test_stack_operand_scaling_covers_the_input_range(scale, cuda_device):
+    """The fp16 hi/lo operands are pre-scaled by powers of two derived from max|x| per call: images in any range
+    (normalised, 0..255, tiny) keep fp32-grade activations; an all-zero batch and one with a single huge outlier
+    pixel stay finite and match the SIMT fp32 kernel."""
+    _, _, _, Net = _mods()
+    torch.manual_seed(90)
+    net = Net((3, 36, 36), 32, 5, "rotation", 8, 3, device="cpu")
+    with torch.no_grad():
+        for m in net.eqv_network:
+            if hasattr(m, "bias"):
+                m.bias.uniform_(-0.05, 0.05)
+    g = torch.Generator().manual_seed(91)
+    x = (torch.rand(4, 3, 36, 36, generator=g) - 0.3) * scale
+    x[1] = 0.0                                   # an all-zero image inside the batch
+    x[2, 0, 5, 7] = 50.0 * scale                 # one outlier pixel sets the batch maximum
+    lay = [(m.weights.detach().clone(), m.bias.detach().clone()) for m in net.eqv_network if hasattr(m, "weights")]
+    act64 = O.custom_equivariant_network(x.double(), [(w.double(), b.double()) for w, b in lay], 8, False)
+    act_tc = _stack_act(net, x, cuda_device, no_tc=False)
+    act_simt = _stack_act(net, x, cuda_device, no_tc=True)
+    assert torch.isfinite(act_tc).all()
+    assert rel_err(act_simt, act64) < 1e-5
+    assert rel_err(act_tc, act64) < 2e-5
+    zero = _stack_act(net, torch.zeros(2, 3, 36, 36), cuda_device, no_tc=False)   # max|x| = 0: scale falls back to 1
+    assert torch.isfinite(zero).all() and rel_err(zero, _stack_act(net, torch.zeros(2, 3, 36, 36), cuda_device, no_tc=True)) < 1e-5
