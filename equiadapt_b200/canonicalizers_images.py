@@ -8,8 +8,9 @@ and get_action_on_image_features / roll_by_gather of equiadapt/images/utils.py:8
 What the reference does with torchvision Pad/CenterCrop/Resize + kornia rotate/hflip (dozens of
 library launches and three full-size temporaries per call) is here one kernel per step:
 eqb_crop_resize_aa, eqb_group_pool_select, eqb_warp_canonicalize, eqb_warp_invert,
-eqb_orbit_expand, eqb_cosine_group_activations.  Forward (inference) only in this round:
-gradients do not flow through the native kernels.
+eqb_orbit_expand, eqb_cosine_group_activations.  Gradients: the two warps are differentiable in their IMAGE argument
+(eqb_warp_adjoint; enough to train a prediction network through invert_canonicalization behind a frozen canonicalizer);
+the group element and the canonicalization network are not differentiated in this round.
 """
 from __future__ import annotations
 
@@ -65,8 +66,8 @@ def get_action_on_image_features(feature_map: torch.Tensor, group_info_dict: dic
     idx = group_element_dict.get("index")
     if idx is None:
         idx = group_element_to_index(group_element_dict, num_rotations)
-    return ops.warp_invert(feature_map, idx, num_rotations, "reflection" in group_element_dict,
-                           induced_rep_type == "regular")
+    return ops.warp_invert_autograd(feature_map, idx, num_rotations, "reflection" in group_element_dict,
+                                    induced_rep_type == "regular")
 
 
 class _ElementDict(dict):
@@ -161,7 +162,7 @@ class DiscreteGroupImageCanonicalization(DiscreteGroupCanonicalization):
                 "canonicalizing segmentation targets (boxes / masks, discrete_group.py:217-236) is outside the "
                 "B200 hot path (SURVEY.md section 2 row 5)")
         idx = self._element_index(group_element_dict)
-        return ops.warp_canonicalize(x, idx, self.num_rotations, "reflection" in group_element_dict.keys())
+        return ops.warp_canonicalize_autograd(x, idx, self.num_rotations, "reflection" in group_element_dict.keys())
 
     # -- a11 ----------------------------------------------------------------------------------------
     def invert_canonicalization(self, x_canonicalized_out: torch.Tensor, **kwargs: Any) -> torch.Tensor:

@@ -209,6 +209,61 @@ void finish_args(ResampleArgs &a) {
     }
 }
 
+
+// ---- adjoint of the warp (N3, partial): gradient with respect to the warped image -----------------------------
+// out = W(g) in is linear in `in`: grad_in = W(g)^T grad_out.  One thread per destination pixel recomputes the four
+// taps of the forward pass (same geometry as resample_kernel, fp64 coordinates) and scatters w * grad_out into the
+// source gradient with atomicAdd (the summation order of taps that collide is not fixed: results agree to fp32
+// rounding, not bit for bit).  Quarter turns / mirrors have one unit tap per pixel: an exact inverse permutation.
+__global__ void __launch_bounds__(256) resample_adjoint_kernel(const __grid_constant__ ResampleArgs a) {
+    const long long npix = (long long)a.B * a.Hd * a.Wd;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < npix; t += (long long)gridDim.x * blockDim.x) {
+        const int xd = (int)(t % a.Wd), yd = (int)((t / a.Wd) % a.Hd), sample = (int)(t / ((long long)a.Wd * a.Hd));
+        const int g = min(max(a.idx[sample], 0), a.G - 1), r = g % a.N, refl = g >= a.N;
+        int mirror_src = 0, mirror_dst = 0;
+        double sign;
+        if (a.mode == MODE_CANON) { mirror_src = refl; sign = -1.0; }
+        else { mirror_dst = a.reflect && !refl; sign = 1.0; }
+        double c, s;
+        group_cs(a, r, sign, c, s);
+        double a00 = c, a01 = -s, a10 = s, a11 = c;
+        if (mirror_dst) { a00 = -a00; a10 = -a10; }
+        if (mirror_src) { a00 = -a00; a01 = -a01; }
+        const double cx = 0.5 * (a.Ws - 1), cy = 0.5 * (a.Hs - 1);
+        const double u = (double)xd + a.ox, v = (double)yd + a.oy;
+        const double xs = cx + a00 * u + a01 * v, ys = cy + a10 * u + a11 * v;
+        const double xf = floor(xs), yf = floor(ys);
+        const float fx = (float)(xs - xf), fy = (float)(ys - yf);
+        const int x0 = (int)xf, y0 = (int)yf;
+        const int lo_x = -a.pad, hi_x = a.Ws - 1 + a.pad, lo_y = -a.pad, hi_y = a.Hs - 1 + a.pad;
+        float w[4];
+        int off[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int xt = x0 + (k & 1), yt = y0 + (k >> 1);
+            const bool in = xt >= lo_x && xt <= hi_x && yt >= lo_y && yt <= hi_y;
+            w[k] = in ? ((k >> 1) ? fy : 1.f - fy) * ((k & 1) ? fx : 1.f - fx) : 0.f;
+            off[k] = min(max(yt, 0), a.Hs - 1) * a.Ws + min(max(xt, 0), a.Ws - 1);
+        }
+        const size_t plane_s = (size_t)a.Hs * a.Ws, plane_d = (size_t)a.Hd * a.Wd;
+        const float *gy = a.src + (size_t)sample * a.C * plane_d + (size_t)yd * a.Wd + xd;   // src = grad of the warp's output
+        float *gx = a.dst + (size_t)sample * a.C * plane_s;                                    // dst = grad of its input
+        for (int ch = 0; ch < a.C; ++ch) {
+            int cs = ch;
+            if (a.mode == MODE_INV_REGULAR) {
+                const int f = ch / a.G, gg = ch - f * a.G, sh = a.roll[r];
+                const int sg = gg < a.N ? (gg - sh + a.N) % a.N : a.N + (gg - a.N + sh) % a.N;
+                cs = f * a.G + sg;
+            }
+            const float gval = gy[(size_t)ch * plane_d];
+            float *gp = gx + (size_t)cs * plane_s;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (w[k] != 0.f) atomicAdd(gp + off[k], w[k] * gval);
+        }
+    }
+}
+
 static int launch_resample(ResampleArgs &a, int n_dst_samples, cudaStream_t st, const char *what) {
     finish_args(a);
     if (!getenv("EQB_NO_TMA")) {
@@ -316,4 +371,35 @@ extern "C" int eqb_warp_affine(const float *x, float *y, const float *mats, cons
     a.scx = cx; a.scy = cy;
     a.ox = -cx; a.oy = -cy;     // destination pixel relative to the same centre
     return launch_resample(a, B, (cudaStream_t)stream, "eqb_warp_affine");
+}
+
+// ---- N3 (partial): gradient of the discrete warps with respect to their image argument --------------------
+// mode 0: adjoint of eqb_warp_canonicalize, 1: of eqb_warp_invert (scalar), 2: of eqb_warp_invert (regular).
+extern "C" int eqb_warp_adjoint(const float *grad_out, float *grad_in, const int32_t *idx, int B, int C, int H, int W,
+                                int num_rotations, int reflect, int mode, void *stream) {
+    EQB_REQUIRE(B >= 0 && C > 0 && H > 0 && W > 0 && num_rotations > 0, "eqb_warp_adjoint: bad shape");
+    EQB_REQUIRE(mode >= 0 && mode <= 2, "eqb_warp_adjoint: mode must be 0 (canonicalize), 1 (invert scalar) or 2 (invert regular)");
+    const int G = num_rotations * (reflect ? 2 : 1);
+    EQB_REQUIRE(mode != 2 || C % G == 0, "eqb_warp_adjoint: regular representation needs C %% |G| == 0");
+    EQB_REQUIRE(B == 0 || (grad_out && grad_in && idx), "eqb_warp_adjoint: null pointer");
+    if (B == 0) return 0;
+    ResampleArgs a{};
+    a.src = grad_out; a.dst = grad_in; a.idx = idx; a.B = B; a.C = C;
+    a.Hs = a.Hd = H; a.Ws = a.Wd = W;
+    a.N = num_rotations; a.reflect = reflect != 0; a.G = G;
+    a.mode = mode == 0 ? MODE_CANON : mode == 1 ? MODE_INV_SCALAR : MODE_INV_REGULAR;
+    if (mode == 2) {
+        EQB_UNSUPPORTED(num_rotations > 64, "eqb_warp_adjoint: regular representation supports num_rotations <= 64");
+        for (int r = 0; r < num_rotations; ++r) a.roll[r] = (signed char)regular_roll_shift(r, num_rotations);
+    }
+    a.pad = (mode == 0 && C != 1) ? (W + 1) / 2 : 0;
+    a.ox = -0.5 * (W - 1); a.oy = -0.5 * (H - 1);
+    finish_args(a);
+    cudaStream_t st = (cudaStream_t)stream;
+    EQB_CUDA(cudaMemsetAsync(grad_in, 0, (size_t)B * C * H * W * sizeof(float), st));
+    const long long npix = (long long)B * H * W;
+    long long blocks = (npix + 255) / 256;
+    if (blocks > (long long)num_sms() * 32) blocks = (long long)num_sms() * 32;
+    resample_adjoint_kernel<<<(unsigned)blocks, 256, 0, st>>>(a);
+    return finish_launch("eqb_warp_adjoint");
 }

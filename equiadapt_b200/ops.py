@@ -259,6 +259,49 @@ def warp_invert(f: torch.Tensor, idx: torch.Tensor, num_rotations: int, reflect:
     return out
 
 
+def warp_adjoint(grad_out: torch.Tensor, idx: torch.Tensor, num_rotations: int, reflect: bool, mode: int) -> torch.Tensor:
+    """grad of warp_canonicalize (mode 0) / warp_invert scalar (1) / regular (2) with respect to its image argument."""
+    dev = _need_cuda(grad_out, idx)
+    grad_out = _f32(grad_out)
+    idx = _idx32(idx)
+    b, c, h, w = grad_out.shape
+    grad_in = torch.empty_like(grad_out)
+    _call("eqb_warp_adjoint", 1, dev, _ptr(grad_out), _ptr(grad_in), _ptr(idx), b, c, h, w, num_rotations, int(reflect),
+          int(mode), _stream(dev))
+    return grad_in
+
+
+class _WarpFunction(torch.autograd.Function):
+    """Differentiable (in the image argument) wrapper of the two discrete warps; the group index carries no gradient."""
+
+    @staticmethod
+    def forward(ctx, x, idx, num_rotations, reflect, mode):
+        ctx.save_for_backward(idx)
+        ctx.cfg = (num_rotations, reflect, mode)
+        if mode == 0:
+            return warp_canonicalize(x, idx, num_rotations, reflect)
+        return warp_invert(x, idx, num_rotations, reflect, mode == 2)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (idx,) = ctx.saved_tensors
+        num_rotations, reflect, mode = ctx.cfg
+        return warp_adjoint(grad_out.contiguous(), idx, num_rotations, reflect, mode), None, None, None, None
+
+
+def warp_canonicalize_autograd(x: torch.Tensor, idx: torch.Tensor, num_rotations: int, reflect: bool) -> torch.Tensor:
+    """warp_canonicalize that records an autograd node when x requires grad (inference calls stay node-free)."""
+    if torch.is_grad_enabled() and x.requires_grad:
+        return _WarpFunction.apply(x, idx, num_rotations, reflect, 0)
+    return warp_canonicalize(x, idx, num_rotations, reflect)
+
+
+def warp_invert_autograd(f: torch.Tensor, idx: torch.Tensor, num_rotations: int, reflect: bool, regular: bool) -> torch.Tensor:
+    if torch.is_grad_enabled() and f.requires_grad:
+        return _WarpFunction.apply(f, idx, num_rotations, reflect, 2 if regular else 1)
+    return warp_invert(f, idx, num_rotations, reflect, regular)
+
+
 def orbit_expand(x: torch.Tensor, pad: int, out_size: int, num_rotations: int, reflect: bool) -> torch.Tensor:
     dev = _need_cuda(x)
     x = _f32(x)

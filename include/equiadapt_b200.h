@@ -122,6 +122,15 @@ EQB_API int eqb_warp_canonicalize(const float *x, float *y, const int32_t *idx, 
 EQB_API int eqb_warp_invert(const float *f, float *out, const int32_t *idx, int B, int C, int H, int W,
                     int num_rotations, int reflect, int rep, void *stream);
 
+/* ---- N3 (partial)  gradient of the two warps above with respect to their image argument --------
+ * grad_in = W(g)^T grad_out, the adjoint of the (linear) warp: what autograd needs to train a prediction network whose
+ * output goes through invert_canonicalization, or to differentiate canonicalize(x) with respect to x.  The group
+ * element is not differentiated.  mode 0: eqb_warp_canonicalize, 1: eqb_warp_invert scalar, 2: eqb_warp_invert regular.
+ * (The reference gets this from torch autograd through kornia's grid_sample: discrete_group.py:207-215,
+ * images/utils.py:54-79.) */
+EQB_API int eqb_warp_adjoint(const float *grad_out, float *grad_in, const int32_t *idx, int B, int C, int H, int W,
+                             int num_rotations, int reflect, int mode, void *stream);
+
 /* Host-only, no GPU work: the channel shift the reference derives for rotation index r by
  * `(angle / 360.0 * num_rotations).long()` in float32 (images/utils.py:67,:28); equals r for
  * power-of-two N, may truncate to r-1 otherwise (reference quirk reproduced by eqb_warp_invert). */

@@ -896,3 +896,55 @@ def test_stack_operand_scaling_covers_the_input_range(scale, cuda_device):
     assert rel_err(act_tc, act64) < 2e-5
     zero = _stack_act(net, torch.zeros(2, 3, 36, 36), cuda_device, no_tc=False)   # max|x| = 0: scale falls back to 1
     assert torch.isfinite(zero).all() and rel_err(zero, _stack_act(net, torch.zeros(2, 3, 36, 36), cuda_device, no_tc=True)) < 1e-5
+
+
+# ---------------------------------------------------------------------------------------------------
+# N3 (partial): gradients of the warps with respect to their image argument vs torch autograd through the oracle
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("group_type,n", [("rotation", 4), ("rotation", 8), ("roto-reflection", 4), ("roto-reflection", 8)])
+def test_warp_gradients_vs_oracle_autograd(group_type, n, cuda_device):
+    ops = _mods()[0]
+    dev = cuda_device
+    reflect = group_type == "roto-reflection"
+    G = n * (2 if reflect else 1)
+    g = torch.Generator().manual_seed(100 + n + reflect)
+    b, h, w = 2 * G, 40, 40
+    idx = torch.arange(b) % G
+    ang = torch.linspace(0.0, 360.0, n + 1)[:n][idx % n]
+    refl = (idx >= n).float() if reflect else None
+    # canonicalize: d <y, r> / d x
+    x = torch.rand(b, 3, h, w, generator=g)
+    r = torch.randn(b, 3, h, w, generator=g)
+    xo = x.clone().requires_grad_(True)
+    (O.canonicalize_image(xo, ang, refl) * r).sum().backward()
+    xd = x.to(dev).requires_grad_(True)
+    y = ops.warp_canonicalize_autograd(xd, idx.to(dev).int(), n, reflect)
+    (y * r.to(dev)).sum().backward()
+    assert rel_err(xd.grad.cpu(), xo.grad) < RTOL
+    # invert: scalar and regular representations
+    for rep, c in (("scalar", 3), ("regular", 2 * G)):
+        f = torch.randn(b, c, h, w, generator=g)
+        rr = torch.randn(b, c, h, w, generator=g)
+        fo = f.clone().requires_grad_(True)
+        (O.invert_image_features(fo, ang, refl, n, G, rep) * rr).sum().backward()
+        fd = f.to(dev).requires_grad_(True)
+        out = ops.warp_invert_autograd(fd, idx.to(dev).int(), n, reflect, rep == "regular")
+        (out * rr.to(dev)).sum().backward()
+        assert rel_err(fd.grad.cpu(), fo.grad) < RTOL
+
+
+def test_prediction_network_trains_through_invert_canonicalization(cuda_device):
+    """A frozen canonicalizer in front of / behind a trainable prediction network: loss.backward() reaches the
+    prediction network's parameters through invert_canonicalization (the reference's segmentation-style use)."""
+    _, GEIC, _, Net = _mods()
+    dev = cuda_device
+    torch.manual_seed(110)
+    can = GEIC(Net((3, 32, 32), 8, 5, "rotation", 8, 3, device="cpu").to(dev),
+               SimpleNamespace(beta=1.0, input_crop_ratio=0.8, resize_shape=32), (3, 64, 64)).eval()
+    for p in can.parameters():
+        p.requires_grad_(False)
+    pred = torch.nn.Conv2d(3, 8, 3, padding=1).to(dev)
+    x = torch.rand(4, 3, 64, 64, generator=torch.Generator().manual_seed(111)).to(dev)
+    out = can.invert_canonicalization(pred(can(x)), induced_rep_type="regular")
+    out.square().mean().backward()
+    assert pred.weight.grad is not None and torch.isfinite(pred.weight.grad).all() and float(pred.weight.grad.abs().sum()) > 0
