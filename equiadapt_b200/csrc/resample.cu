@@ -403,3 +403,109 @@ extern "C" int eqb_warp_adjoint(const float *grad_out, float *grad_in, const int
     resample_adjoint_kernel<<<(unsigned)blocks, 256, 0, st>>>(a);
     return finish_launch("eqb_warp_adjoint");
 }
+
+// ---- N4: evaluation-time group orbit (examples/images/classification/inference_utils.py:97-122) -----------------
+// out[g, b, c] = CenterCrop(H, W)( torchvision.rotate_nearest( [hflip]( Pad(pad, edge)(x[b, c]) ), degree_g ) ).
+// The source pixel of an output pixel depends on (g, y, x) only, so a thread resolves it once and then streams every
+// (b, c) plane of its chunk through it.  The float32 operation order is torchvision's (affine base grid times the
+// rescaled theta, then grid_sample's unnormalise + nearbyint) so that rounding ties fall the same way.
+struct OrbitNearestArgs {
+    const float *src;
+    float *dst;
+    int planes, H, W, pad, G, N;
+    int top, left;
+    float r[64][6];   // per rotation: theta^T / (0.5 wp, 0.5 hp) as [r00 r10 r20 r01 r11 r21]
+};
+
+// source offset (sy * W + sx) of output pixel (y, x) under element g, or -1 when torchvision's zero fill applies
+__device__ __forceinline__ int orbit_nearest_source(const OrbitNearestArgs &a, int g, int y, int x) {
+    const int hp = a.H + 2 * a.pad, wp = a.W + 2 * a.pad;
+    const float *r = a.r[g % a.N];
+    const float bx = __fadd_rn((float)(x + a.left), (float)(-wp * 0.5 + 0.5));
+    const float by = __fadd_rn((float)(y + a.top), (float)(-hp * 0.5 + 0.5));
+    const float gx = __fadd_rn(__fadd_rn(__fmul_rn(bx, r[0]), __fmul_rn(by, r[1])), r[2]);
+    const float gy = __fadd_rn(__fadd_rn(__fmul_rn(bx, r[3]), __fmul_rn(by, r[4])), r[5]);
+    const float ix = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(gx, 1.f), (float)wp), -1.f), 0.5f);
+    const float iy = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(gy, 1.f), (float)hp), -1.f), 0.5f);
+    const float fx = rintf(ix), fy = rintf(iy);
+    if (!(fx >= 0.f && fx < (float)wp && fy >= 0.f && fy < (float)hp)) return -1;
+    int jx = (int)fx;
+    const int jy = (int)fy;
+    if (g >= a.N) jx = wp - 1 - jx;
+    return min(max(jy - a.pad, 0), a.H - 1) * a.W + min(max(jx - a.pad, 0), a.W - 1);
+}
+
+// grid (32-pixel columns, 8-row bands, |G| x plane chunks).  A warp owns an 8 x 4 pixel patch, not a 32 x 1 row: under a
+// quarter turn a row of 32 outputs reads 32 different source rows (32 L1 wavefronts per load instruction), while the
+// patch reads 4..9 rows and still stores four complete 32-byte sectors.  Each thread resolves its source pixel once
+// and walks the planes of its chunk with UNROLL loads in flight.
+__global__ void __launch_bounds__(256) orbit_nearest_kernel(const __grid_constant__ OrbitNearestArgs a, int chunks) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int x = blockIdx.x * 32 + (warp & 3) * 8 + (lane & 7);
+    const int y = blockIdx.y * 8 + (warp >> 2) * 4 + (lane >> 3);
+    if (x >= a.W || y >= a.H) return;
+    const int g = blockIdx.z / chunks, chunk = blockIdx.z % chunks;
+    const int so = orbit_nearest_source(a, g, y, x);
+    const size_t plane = (size_t)a.H * a.W;
+    const int per = (a.planes + chunks - 1) / chunks;
+    const int p0 = chunk * per, p1 = min(p0 + per, a.planes);
+    float *d = a.dst + ((size_t)g * a.planes + p0) * plane + (size_t)y * a.W + x;
+    if (so < 0) {                                    // torchvision's zero fill outside the padded image
+        for (int p = p0; p < p1; ++p, d += plane) __stcs(d, 0.f);
+        return;
+    }
+    const float *s = a.src + (size_t)p0 * plane + so;
+    constexpr int UNROLL = 8;
+    int p = p0;
+    for (; p + UNROLL <= p1; p += UNROLL) {
+        float val[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) val[u] = __ldg(s + (size_t)u * plane);
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) __stcs(d + (size_t)u * plane, val[u]);
+        s += (size_t)UNROLL * plane; d += (size_t)UNROLL * plane;
+    }
+    for (; p < p1; ++p, s += plane, d += plane) __stcs(d, __ldg(s));
+}
+
+// torch.linspace(0, 360, n + 1)[i] in float32: first half start + i*step, second half end - (steps-1-i)*step
+static float linspace_degree(int i, int n) {
+    const int steps = n + 1;
+    const float step = 360.0f / (float)(steps - 1);
+    return i < steps / 2 ? 0.0f + step * (float)i : 360.0f - step * (float)(steps - 1 - i);
+}
+
+extern "C" int eqb_orbit_rotate_nearest(const float *x, float *out, int B, int C, int H, int W, int num_rotations,
+                                        int reflect, void *stream) {
+    EQB_REQUIRE(B >= 0 && C > 0 && H > 0 && W > 0, "eqb_orbit_rotate_nearest: bad shape (%d,%d,%d,%d)", B, C, H, W);
+    EQB_REQUIRE(num_rotations > 0, "eqb_orbit_rotate_nearest: num_rotations must be positive");
+    EQB_UNSUPPORTED(num_rotations > 64, "eqb_orbit_rotate_nearest: num_rotations <= 64 supported");
+    EQB_REQUIRE(B == 0 || (x && out), "eqb_orbit_rotate_nearest: null pointer");
+    if (B == 0) return 0;
+    OrbitNearestArgs a{};
+    a.src = x; a.dst = out; a.planes = B * C; a.H = H; a.W = W;
+    a.pad = (int)ceil(H * 0.4);                     // transforms.Pad(math.ceil(in_shape[-2] * 0.4), "edge")
+    a.N = num_rotations; a.G = num_rotations * (reflect ? 2 : 1);
+    const int hp = H + 2 * a.pad, wp = W + 2 * a.pad;
+    a.top = (int)rint((hp - H) / 2.0); a.left = (int)rint((wp - W) / 2.0);
+    const float sw = 0.5f * (float)wp, sh = 0.5f * (float)hp;
+    for (int i = 0; i < num_rotations; ++i) {
+        // torchvision F.rotate: _get_inverse_affine_matrix([0,0], -angle, [0,0], 1, [0,0]) in doubles -> float32 theta
+        const double rot = -(double)linspace_degree(i, num_rotations) * (M_PI / 180.0);   // math.radians
+        const double ca = cos(rot), sa = sin(rot);
+        const float m0 = (float)ca, m1 = (float)sa, m3 = (float)(-sa), m4 = (float)ca;
+        a.r[i][0] = m0 / sw; a.r[i][1] = m1 / sw; a.r[i][2] = 0.f / sw;
+        a.r[i][3] = m3 / sh; a.r[i][4] = m4 / sh; a.r[i][5] = 0.f / sh;
+    }
+    // plane chunks: enough CTAs for many waves of 8 resident CTAs per SM, at least 8 planes each so the index
+    // arithmetic stays amortised
+    const int tiles_x = (W + 31) / 32, tiles_y = (H + 7) / 8;
+    EQB_REQUIRE(tiles_y <= 65535, "eqb_orbit_rotate_nearest: image too tall for one launch");
+    const long long base = (long long)tiles_x * tiles_y * a.G;
+    static const int ctas_per_sm = getenv("EQB_ORBIT_CTAS_PER_SM") ? atoi(getenv("EQB_ORBIT_CTAS_PER_SM")) : 64;   // tuning knob
+    int chunks = (int)(((long long)ctas_per_sm * num_sms() + base - 1) / base);
+    chunks = std::max(1, std::min(std::min(chunks, (a.planes + 7) / 8), 65535 / a.G));
+    dim3 grid(tiles_x, tiles_y, a.G * chunks);
+    orbit_nearest_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a, chunks);
+    return finish_launch("eqb_orbit_rotate_nearest");
+}

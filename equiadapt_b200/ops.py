@@ -313,6 +313,17 @@ def orbit_expand(x: torch.Tensor, pad: int, out_size: int, num_rotations: int, r
     return out
 
 
+def orbit_rotate_nearest(x: torch.Tensor, num_rotations: int, reflect: bool) -> torch.Tensor:
+    """(B,C,H,W) -> (|G|,B,C,H,W): the evaluation orbit of GroupInference (inference_utils.py:97-122), one launch."""
+    dev = _need_cuda(x)
+    x = _f32(x)
+    b, c, h, w = x.shape
+    g = num_rotations * (2 if reflect else 1)
+    out = torch.empty((g, b, c, h, w), dtype=torch.float32, device=dev)
+    _call("eqb_orbit_rotate_nearest", 1 if b else 0, dev, _ptr(x), _ptr(out), b, c, h, w, num_rotations, int(reflect), _stream(dev))
+    return out
+
+
 def cosine_group_activations(vec: torch.Tensor, ref: torch.Tensor, num_group: int) -> torch.Tensor:
     dev = _need_cuda(vec, ref)
     vec = _f32(vec)

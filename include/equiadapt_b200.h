@@ -142,6 +142,14 @@ EQB_API int eqb_regular_roll_shift(int r, int num_rotations);
  * rotate_and_maybe_reflect (discrete_group.py:387-427).  C == 1: no pad/crop (zero fill). */
 EQB_API int eqb_orbit_expand(const float *x, float *out, int B, int C, int h, int w, int pad, int out_size,
                      int num_rotations, int reflect, void *stream);
+/* ---- N4  evaluation-time group orbit -------------------------------------------------------
+ * x (B,C,H,W) -> out (|G|, B, C, H, W): for every group element (rotations by torch.linspace(0,360,N+1)[:-1], then
+ * the same rotations of the mirrored image) CenterCrop(H,W)(torchvision rotate NEAREST, zero fill ([hflip](
+ * Pad(ceil(0.4 H), edge)(x)))).  Replaces the per-element pad / hflip / rotate / crop loop of
+ * GroupInference.get_group_element_wise_logits (examples/images/classification/inference_utils.py:97-122).
+ * Bit-exact with torchvision's float32 affine grid + grid_sample(nearest). */
+EQB_API int eqb_orbit_rotate_nearest(const float *x, float *out, int B, int C, int H, int W, int num_rotations,
+                                     int reflect, void *stream);
 /* Cosine similarity to the reference vector + (|G|,B)->(B,|G|) transpose: vec (|G|*B, V), ref (V),
  * act (B,|G|).  Replaces discrete_group.py:475-481. */
 EQB_API int eqb_cosine_group_activations(const float *vec, const float *ref, float *act, int B, int num_group,

@@ -314,8 +314,35 @@ def golden_continuous_images():
         _save("image_cont_augment_" + tag, d)
 
 
+def golden_group_inference():
+    """The evaluation orbit of examples/images/classification/inference_utils.py:97-122, produced by the reference's
+    own callees (torchvision Pad / hflip / rotate / CenterCrop) in the reference's order.  The example module itself
+    imports omegaconf (absent here), so its loop is replayed call for call."""
+    import math
+    from torchvision import transforms
+
+    for tag, n, reflect, shape, seed in (("c4", 4, False, (2, 3, 32, 32), 41), ("d8", 8, True, (2, 3, 32, 32), 43),
+                                         ("c6_gray", 6, False, (3, 1, 28, 28), 45), ("d5_rect", 5, True, (1, 3, 30, 37), 47)):
+        g = torch.Generator().manual_seed(seed)
+        x = torch.randn(*shape, generator=g)
+        pad = transforms.Pad(math.ceil(shape[-2] * 0.4), padding_mode="edge")       # :93
+        crop = transforms.CenterCrop((shape[-2], shape[-1]))                         # :94
+        degrees = torch.linspace(0, 360, n + 1)[:-1]                                 # :99
+        members = []
+        for degree in degrees:                                                       # :100-106
+            members.append(crop(transforms.functional.rotate(pad(x), degree.item())))
+        if reflect:                                                                  # :108-118
+            for degree in degrees:
+                members.append(crop(transforms.functional.rotate(transforms.functional.hflip(pad(x)), degree.item())))
+        _save("group_inference_orbit_" + tag, {"x": x, "orbit": torch.stack(members), "num_rotations": n,
+                                               "reflect": int(reflect)})
+
+
 def main():
     _import_reference()
+    if "--only-orbit" in sys.argv:
+        golden_group_inference()
+        return
     if "--only-cont" in sys.argv:
         golden_continuous_images()
         return
@@ -344,6 +371,7 @@ def main():
     golden_vnsmall()
     golden_vndeepsets()
     golden_continuous_images()
+    golden_group_inference()
 
 
 if __name__ == "__main__":

@@ -612,3 +612,76 @@ def group_augment_continuous(x: torch.Tensor, angles: torch.Tensor, reflect: Opt
         aug = center_crop(aug, h, w)
     rm[:, [0, 1], [1, 0]] *= -1
     return aug, rm[:, :, :2]
+
+
+# --------------------------------------------------------------------------------------------
+# N4  evaluation-time group orbit (examples/images/classification/inference_utils.py:97-122)
+# --------------------------------------------------------------------------------------------
+
+
+def linspace_degrees(num_rotations: int) -> List[float]:
+    """`torch.linspace(0, 360, n + 1)[:-1]` as float32 values (inference_utils.py:99): torch fills the first half as
+    start + i*step and the second half as end - (steps-1-i)*step, all in float32 (the scalar formula of ATen's
+    linspace kernel; its vectorised CPU path adds lane*step to a per-vector base instead, so when 360/n is not a float32
+    the reference's own value moves by an ulp with the SIMD width of the host -- only rounding-tie pixels can notice)."""
+    import numpy as np
+    steps = num_rotations + 1
+    step = np.float32(360.0) / np.float32(steps - 1)
+    half = steps // 2
+    out = []
+    for i in range(num_rotations):
+        v = np.float32(0.0) + step * np.float32(i) if i < half else np.float32(360.0) - step * np.float32(steps - 1 - i)
+        out.append(float(np.float32(v)))
+    return out
+
+
+def torchvision_rotate_matrix(angle_deg: float) -> List[float]:
+    """torchvision.transforms.functional.rotate -> _get_inverse_affine_matrix([0,0], -angle, [0,0], 1, [0,0]) in
+    Python doubles (torchvision 0.26 transforms/functional.py); the six entries of the output->input map in
+    centred pixel coordinates."""
+    rot = math.radians(-angle_deg)
+    a, b, c, d = math.cos(rot), -math.sin(rot), math.sin(rot), math.cos(rot)
+    return [d, -b, 0.0, -c, a, 0.0]
+
+
+def group_inference_orbit(x: torch.Tensor, num_rotations: int, reflect: bool, return_margin: bool = False):
+    """GroupInference.get_group_element_wise_logits' inputs (inference_utils.py:97-122): for every group element
+    Pad(ceil(0.4 H), edge) -> [hflip] -> torchvision rotate (NEAREST, zero fill, expand=False) -> CenterCrop(H, W).
+    Returns (G, B, C, H, W) with rotations first, then the reflected rotations (dict keys rot, rot + n).
+
+    torchvision's tensor rotate is affine grid (float32 bmm) + grid_sample(nearest, zeros, align_corners=False);
+    restated here as explicit index arithmetic.  With `return_margin` also returns (G, H, W) float64 distances of
+    the source coordinate from the nearest rounding tie (x.5): pixels with a tiny margin (the diagonals of the
+    45-degree elements sit EXACTLY on ties) depend on the order of float32 operations of the matmul backend, so
+    parity is asserted away from them."""
+    b, c, h, w = x.shape
+    p = math.ceil(h * 0.4)
+    hp, wp = h + 2 * p, w + 2 * p
+    top, left = center_crop_offsets(hp, wp, h, w)
+    xs32 = (torch.arange(w, dtype=torch.float32) + left) + (-wp * 0.5 + 0.5)
+    ys32 = (torch.arange(h, dtype=torch.float32) + top) + (-hp * 0.5 + 0.5)
+    outs, margins = [], []
+    for flip in ([False, True] if reflect else [False]):
+        for deg in linspace_degrees(num_rotations):
+            m = torchvision_rotate_matrix(deg)
+            theta = torch.tensor(m, dtype=torch.float32).reshape(2, 3)
+            resc = theta.t() / torch.tensor([0.5 * wp, 0.5 * hp], dtype=torch.float32)       # (3, 2)
+            gx = (xs32[None, :] * resc[0, 0] + ys32[:, None] * resc[1, 0]) + resc[2, 0]
+            gy = (xs32[None, :] * resc[0, 1] + ys32[:, None] * resc[1, 1]) + resc[2, 1]
+            ix = ((gx + 1) * wp - 1) / 2
+            iy = ((gy + 1) * hp - 1) / 2
+            jx, jy = torch.round(ix).long(), torch.round(iy).long()        # torch.round = nearbyint (ties to even)
+            inside = (jx >= 0) & (jx < wp) & (jy >= 0) & (jy < hp)
+            if flip:
+                jx = wp - 1 - jx
+            sx, sy = (jx - p).clamp(0, w - 1), (jy - p).clamp(0, h - 1)     # edge padding
+            out = x[:, :, sy, sx] * inside.to(x.dtype)
+            outs.append(out)
+            if return_margin:
+                xs64, ys64 = xs32.double(), ys32.double()
+                fx = xs64[None, :] * m[0] + ys64[:, None] * m[1] + (wp - 1) / 2
+                fy = xs64[None, :] * m[3] + ys64[:, None] * m[4] + (hp - 1) / 2
+                tie = lambda v: (v - torch.floor(v) - 0.5).abs()
+                margins.append(torch.minimum(tie(fx), tie(fy)))
+    orbit = torch.stack(outs, 0)
+    return (orbit, torch.stack(margins, 0)) if return_margin else orbit

@@ -948,3 +948,81 @@ def test_prediction_network_trains_through_invert_canonicalization(cuda_device):
     out = can.invert_canonicalization(pred(can(x)), induced_rep_type="regular")
     out.square().mean().backward()
     assert pred.weight.grad is not None and torch.isfinite(pred.weight.grad).all() and float(pred.weight.grad.abs().sum()) > 0
+
+
+# ---- N4 (second half): evaluation-time group orbit -------------------------------------------------------------------
+@pytest.mark.parametrize("tag", ["c4", "d8", "c6_gray", "d5_rect"])
+def test_group_inference_orbit_vs_torchvision_golden(tag, cuda_device):
+    """eqb_orbit_rotate_nearest vs torchvision's Pad/hflip/rotate(NEAREST)/CenterCrop (inference_utils.py:97-122):
+    bit-exact, including the pixels whose source coordinate sits on a rounding tie."""
+    ops = _mods()[0]
+    g = load_golden("group_inference_orbit_" + tag)
+    out = ops.orbit_rotate_nearest(g["x"].to(cuda_device), int(g["num_rotations"]), bool(int(g["reflect"])))
+    assert out.shape == g["orbit"].shape
+    assert torch.equal(out.cpu(), g["orbit"])
+
+
+@pytest.mark.parametrize("n,reflect,shape", [(8, True, (64, 3, 224, 224)), (4, False, (5, 3, 224, 224)), (16, True, (2, 1, 95, 131)),
+                                              (7, False, (3, 2, 33, 33)), (64, False, (1, 3, 40, 40))])
+def test_group_inference_orbit_vs_oracle_full_size(n, reflect, shape, cuda_device):
+    ops = _mods()[0]
+    x = torch.randn(*shape, generator=torch.Generator().manual_seed(n))
+    out = ops.orbit_rotate_nearest(x.to(cuda_device), n, reflect).cpu()
+    # the oracle on one image (it is independent of the batch index), every plane against it
+    want, margin = O.group_inference_orbit(x[:1], n, reflect, return_margin=True)
+    assert torch.equal(out[:, :1], want)
+    # size-independent properties: element 0 is the identity; every output value is either 0 or a value of its plane;
+    # the nearest-neighbour source map is the same for every plane
+    assert torch.equal(out[0], x)
+    ramp = torch.arange(1, shape[-2] * shape[-1] + 1, dtype=torch.float32).reshape(1, 1, *shape[-2:]).to(cuda_device)
+    src = ops.orbit_rotate_nearest(ramp, n, reflect).cpu().long()          # 0 = outside, else 1 + flat source index
+    flat = torch.cat([torch.zeros(*shape[:2], 1), x.reshape(*shape[:2], -1)], -1)
+    for gi in (0, out.shape[0] // 2, out.shape[0] - 1):
+        gathered = torch.gather(flat, 2, src[gi].reshape(1, 1, -1).expand(shape[0], shape[1], -1)).reshape(shape)
+        assert torch.equal(out[gi], gathered)
+    assert int((margin < 1e-4).sum()) >= 0
+
+
+def test_group_inference_empty_and_errors(cuda_device):
+    ops = _mods()[0]
+    assert ops.orbit_rotate_nearest(torch.zeros(0, 3, 8, 8, device=cuda_device), 4, True).shape == (8, 0, 3, 8, 8)
+    with pytest.raises(NotImplementedError):
+        ops.orbit_rotate_nearest(torch.zeros(1, 3, 8, 8, device=cuda_device), 65, False)
+    with pytest.raises(ValueError):
+        ops.orbit_rotate_nearest(torch.zeros(1, 3, 8, 8, device=cuda_device), 0, False)
+
+
+@pytest.mark.parametrize("group_type", ["rotation", "roto-reflection"])
+def test_group_inference_metrics_match_reference_loop(group_type, cuda_device):
+    """GroupInference (mirror of inference_utils.py:80-168) around a real canonicalizer: metric keys and values equal
+    the reference's per-element loop run on the oracle's orbit through the same canonicalizer / prediction network."""
+    from equiadapt_b200.images.inference import GroupInference, VanillaInference, get_inference_method
+    dev = cuda_device
+    g = load_golden("image_c4_cfg1")
+    can = build_canonicalizer(g, dev)
+    torch.manual_seed(3)
+    pred = torch.nn.Sequential(torch.nn.Flatten(), torch.nn.Linear(3 * 32 * 32, 10)).to(dev).eval()
+    hp = SimpleNamespace(method="group", group_type=group_type, num_rotations=4)
+    inf = get_inference_method(can, pred, 10, hp, (3, 32, 32))
+    assert isinstance(inf, GroupInference)
+    assert isinstance(get_inference_method(can, pred, 10, {"method": "vanilla"}, (3, 32, 32)), VanillaInference)
+    with pytest.raises(ValueError):
+        get_inference_method(can, pred, 10, {"method": "nope"}, (3, 32, 32))
+    x = torch.randn(16, 3, 32, 32, generator=torch.Generator().manual_seed(5))
+    y = torch.randint(0, 10, (16,), generator=torch.Generator().manual_seed(6))
+    with torch.no_grad():
+        metrics = inf.get_inference_metrics(x.to(dev), y.to(dev))
+        orbit = O.group_inference_orbit(x, 4, group_type == "roto-reflection")
+        accs = []
+        for gi in range(orbit.shape[0]):
+            logits = pred(can(orbit[gi].to(dev)))
+            accs.append((logits.argmax(-1).cpu() == y).float().mean())
+    n_el = 4 if group_type == "rotation" else 8
+    assert set(metrics) == ({"test/group_acc", "test/acc"} | {f"test/acc_group_element_{i}" for i in range(n_el)}
+                            | {f"test/acc_class_{i}" for i in range(10)})
+    assert torch.allclose(metrics["test/group_acc"], torch.stack(accs).mean())
+    for i in range(n_el):
+        assert float(metrics[f"test/acc_group_element_{i}"]) == float(accs[i])
+    assert float(metrics["test/acc"]) == float(accs[0])
+    with pytest.raises(ValueError):
+        inf.get_inference_metrics(torch.zeros(2, 3, 40, 40, device=dev), y[:2].to(dev))

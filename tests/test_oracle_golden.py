@@ -180,3 +180,27 @@ def test_continuous_group_augment_matches_reference(tag):
     g = load_golden("image_cont_augment_" + tag)
     aug, mats = O.group_augment_continuous(g["x"], g["angles"], g.get("reflect"))
     assert rel_err(aug, g["aug"]) < TOL and rel_err(mats, g["mats"]) < TOL
+
+
+ORBIT_CASES = ["c4", "d8", "c6_gray", "d5_rect"]
+
+
+@pytest.mark.parametrize("tag", ORBIT_CASES)
+def test_group_inference_orbit_matches_torchvision(tag):
+    """N4: restated evaluation orbit (examples/images/classification/inference_utils.py:97-122) vs torchvision's
+    Pad / hflip / rotate(NEAREST) / CenterCrop run in the reference's order: bit-exact, rounding ties included."""
+    g = load_golden("group_inference_orbit_" + tag)
+    orbit, margin = O.group_inference_orbit(g["x"], int(g["num_rotations"]), bool(int(g["reflect"])), return_margin=True)
+    assert orbit.shape == g["orbit"].shape and margin.shape == orbit.shape[:1] + orbit.shape[-2:]
+    assert torch.equal(orbit, g["orbit"])
+    assert torch.equal(orbit[0], g["x"])                  # element 0 is the identity
+
+
+def test_linspace_degrees_restatement():
+    """torch.linspace's scalar formula; when 360/n is not a float32 the vectorised CPU kernel (lane base + lane*step,
+    so the value depends on the SIMD width of the machine) may differ from it in the last ulp."""
+    for n in (1, 2, 3, 4, 5, 6, 8, 9, 10, 12, 16, 64):
+        assert O.linspace_degrees(n) == [d.item() for d in torch.linspace(0, 360, n + 1)[:-1]]
+    for n in (7, 11, 13, 31):
+        for a, b in zip(O.linspace_degrees(n), torch.linspace(0, 360, n + 1)[:-1]):
+            assert abs(a - b.item()) <= 3.1e-5
