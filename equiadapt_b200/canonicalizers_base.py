@@ -79,6 +79,25 @@ class IdentityCanonicalization(BaseCanonicalization):
         return torch.tensor(1.0)
 
 
+class _PriorCrossEntropy(torch.autograd.Function):
+    """mean_b CE(act_b, class 0) whose VALUE comes from the select kernel's statistic; the backward is the closed form
+    (softmax(act) - e_0) / B on the (B,|G|) activations -- what torch autograd gives for CrossEntropyLoss in the
+    reference (basecanonicalization.py:290-301).  The gradient is that of THIS rank's mean (the reference's loss is
+    rank-local; DDP averages the parameter gradients)."""
+
+    @staticmethod
+    def forward(ctx, group_activations, value):
+        ctx.save_for_backward(group_activations)
+        return value.detach().clone()
+
+    @staticmethod
+    def backward(ctx, grad):
+        (act,) = ctx.saved_tensors
+        g = torch.softmax(act.detach().float(), dim=-1)
+        g[:, 0] -= 1.0
+        return g * (grad / act.shape[0]), None
+
+
 class DiscreteGroupCanonicalization(BaseCanonicalization):
     """Discrete groups: activations (B,|G|) -> one-hot group element, CE prior, identity metric."""
 
@@ -140,7 +159,11 @@ class DiscreteGroupCanonicalization(BaseCanonicalization):
     def get_prior_regularization_loss(self) -> torch.Tensor:
         """mean_b CE(act_b, class 0) (basecanonicalization.py:290-301), from [sum CE, sum id, B]."""
         s = self._global_discrete_stats()
-        return s[0] / s[2] if self._multi_rank() else s[3]   # one rank: the kernel already divided
+        value = s[0] / s[2] if self._multi_rank() else s[3]   # one rank: the kernel already divided
+        act = self.canonicalization_info_dict["group_activations"]
+        if torch.is_grad_enabled() and act.requires_grad:
+            return _PriorCrossEntropy.apply(act, value)
+        return value
 
     def get_identity_metric(self) -> torch.Tensor:
         """mean_b [argmax == 0] (basecanonicalization.py:303-311)."""

@@ -66,8 +66,10 @@ def get_action_on_image_features(feature_map: torch.Tensor, group_info_dict: dic
     idx = group_element_dict.get("index")
     if idx is None:
         idx = group_element_to_index(group_element_dict, num_rotations)
-    return ops.warp_invert_autograd(feature_map, idx, num_rotations, "reflection" in group_element_dict,
-                                    induced_rep_type == "regular")
+    reflect = "reflection" in group_element_dict
+    return ops.warp_invert_autograd(feature_map, idx, num_rotations, reflect, induced_rep_type == "regular",
+                                    rotation=group_element_dict["rotation"],
+                                    reflection=group_element_dict["reflection"] if reflect else None)
 
 
 class _ElementDict(dict):
@@ -162,7 +164,12 @@ class DiscreteGroupImageCanonicalization(DiscreteGroupCanonicalization):
                 "canonicalizing segmentation targets (boxes / masks, discrete_group.py:217-236) is outside the "
                 "B200 hot path (SURVEY.md section 2 row 5)")
         idx = self._element_index(group_element_dict)
-        return ops.warp_canonicalize_autograd(x, idx, self.num_rotations, "reflection" in group_element_dict.keys())
+        reflect = "reflection" in group_element_dict.keys()
+        # in training the element is the straight-through one (:103-121): the warp node hands its angle / flip
+        # gradients back to it, as autograd through kornia's rotate does in the reference
+        return ops.warp_canonicalize_autograd(x, idx, self.num_rotations, reflect,
+                                              rotation=group_element_dict["rotation"],
+                                              reflection=group_element_dict["reflection"] if reflect else None)
 
     # -- a11 ----------------------------------------------------------------------------------------
     def invert_canonicalization(self, x_canonicalized_out: torch.Tensor, **kwargs: Any) -> torch.Tensor:

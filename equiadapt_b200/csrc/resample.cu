@@ -509,3 +509,183 @@ extern "C" int eqb_orbit_rotate_nearest(const float *x, float *out, int B, int C
     orbit_nearest_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a, chunks);
     return finish_launch("eqb_orbit_rotate_nearest");
 }
+
+// ---- N3: gradient of the discrete warps with respect to the GROUP ELEMENT ----------------------------------------
+// In training the reference feeds the warps a straight-through element: rotation (degrees) = sum_g onehot_g * angle_g,
+// reflection = sum_g onehot_g * [g >= N] (discrete_group.py:110-133), so the task loss reaches the canonicalization
+// network through d warp / d rotation (kornia rotate -> grid_sample's grid gradient) and through the flip blend
+// (1 - r) x + r hflip(x) (discrete_group.py:209-210; images/utils.py:59-64).  One thread per destination pixel:
+//   d out / d theta = (d out / d xs) (d xs / d theta) + (d out / d ys) (d ys / d theta), bilinear cell derivatives
+//                     with the forward's validity masks (zero beyond the padded extent, replicate inside it);
+//   d out / d r     = value under the mirrored blend minus value under the plain one.
+// Per-sample sums over (c, y, x) are reduced per block in fp64 and added atomically.
+namespace eqb {
+
+struct ElementGradArgs {
+    ResampleArgs r;          // src = the warp's input image, dst unused
+    const float *grad_out;
+    float *grad_rotation;    // (B), d loss / d rotation in DEGREES
+    float *grad_reflection;  // (B) or null
+};
+
+struct BilinearCell {
+    float wx[2], wy[2], valid[4];
+    int xt[4], yt[4];
+    // taps one step before the cell, used for the symmetric derivative when the sample sits exactly on a lattice line:
+    // (x0-1, y0), (x0-1, y1) when on_x; (x0, y0-1), (x1, y0-1) when on_y
+    bool on_x, on_y;
+    float valid_m[4];
+    int xm[4], ym[4];
+};
+
+__device__ __forceinline__ void bilinear_cell(const ResampleArgs &a, double xs, double ys, BilinearCell &q) {
+    const double xf = floor(xs), yf = floor(ys);
+    const float fx = (float)(xs - xf), fy = (float)(ys - yf);
+    const int x0 = (int)xf, y0 = (int)yf;
+    const int lo_x = -a.pad, hi_x = a.Ws - 1 + a.pad, lo_y = -a.pad, hi_y = a.Hs - 1 + a.pad;
+    q.wx[0] = 1.f - fx; q.wx[1] = fx; q.wy[0] = 1.f - fy; q.wy[1] = fy;
+    q.on_x = fx == 0.f; q.on_y = fy == 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int xk = x0 + (k & 1), yk = y0 + (k >> 1);
+        q.valid[k] = (xk >= lo_x && xk <= hi_x && yk >= lo_y && yk <= hi_y) ? 1.f : 0.f;
+        q.xt[k] = min(max(xk, 0), a.Ws - 1);
+        q.yt[k] = min(max(yk, 0), a.Hs - 1);
+        const int xj = k < 2 ? x0 - 1 : x0 + (k & 1), yj = k < 2 ? y0 + (k & 1) : y0 - 1;
+        q.valid_m[k] = (xj >= lo_x && xj <= hi_x && yj >= lo_y && yj <= hi_y) ? 1.f : 0.f;
+        q.xm[k] = min(max(xj, 0), a.Ws - 1);
+        q.ym[k] = min(max(yj, 0), a.Hs - 1);
+    }
+}
+
+__global__ void __launch_bounds__(256) warp_element_grad_kernel(const __grid_constant__ ElementGradArgs e) {
+    const ResampleArgs &a = e.r;
+    const int sample = blockIdx.y;
+    const int g = min(max(a.idx[sample], 0), a.G - 1), r = g % a.N, refl = g >= a.N;
+    const bool canon = a.mode == MODE_CANON;
+    double c, s;
+    group_cs(a, r, canon ? -1.0 : 1.0, c, s);       // rotate(x, -theta) for canonicalize, rotate(f, +theta) for invert
+    const double dsign = canon ? -1.0 : 1.0;        // d(angle of the matrix) / d(theta)
+    const double cx = 0.5 * (a.Ws - 1), cy = 0.5 * (a.Hs - 1);
+    const size_t plane = (size_t)a.Hs * a.Ws;
+    const float *img = a.src + (size_t)sample * a.C * plane;
+    const float *go = e.grad_out + (size_t)sample * a.C * plane;
+    double acc_rot = 0.0, acc_ref = 0.0;
+    const int npix = a.Hd * a.Wd;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < npix; t += gridDim.x * blockDim.x) {
+        const int xd = t % a.Wd, yd = t / a.Wd;
+        // canonicalize: the blended image (mirrored when refl) is rotated; sample position from (xd, yd).
+        // invert: out(xd) = r R(xd) + (1 - r) R(W-1-xd) with R = rotate(f): the active sample sits at xd when refl = 1
+        // (or there is no reflection at all), at the mirrored column otherwise.
+        const int xa = (!canon && a.reflect && !refl) ? a.Wd - 1 - xd : xd;
+        const double u = (double)xa + a.ox, v = (double)yd + a.oy;
+        const double xs = cx + c * u - s * v, ys = cy + s * u + c * v;
+        const double dxs = dsign * (-s * u - c * v), dys = dsign * (c * u - s * v);     // per radian of theta
+        BilinearCell q;
+        bilinear_cell(a, xs, ys, q);
+        // the other sample of the blend: canonicalize -> same taps in the mirrored image; invert -> R at the mirrored column
+        BilinearCell q2;
+        if (a.reflect && !canon) {
+            const double u2 = (double)(a.Wd - 1 - xa) + a.ox;
+            bilinear_cell(a, cx + c * u2 - s * v, cy + s * u2 + c * v, q2);
+        }
+        const bool flip_src = canon && refl;
+        float sum_rot = 0.f, sum_ref = 0.f;
+        for (int ch = 0; ch < a.C; ++ch) {
+            int cs = ch;
+            if (a.mode == MODE_INV_REGULAR) {
+                const int f = ch / a.G, gg = ch - f * a.G, sh = a.roll[r];
+                const int sg = gg < a.N ? (gg - sh + a.N) % a.N : a.N + (gg - a.N + sh) % a.N;
+                cs = f * a.G + sg;
+            }
+            const float *ip = img + (size_t)cs * plane;
+            const float gval = go[(size_t)ch * plane + (size_t)yd * a.Wd + xd];
+            float val[4], alt = 0.f, cur = 0.f;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int xk = flip_src ? a.Ws - 1 - q.xt[k] : q.xt[k];
+                val[k] = q.valid[k] * __ldg(ip + q.yt[k] * a.Ws + xk);
+                cur += val[k] * q.wx[k & 1] * q.wy[k >> 1];
+                if (canon && a.reflect) alt += q.valid[k] * __ldg(ip + q.yt[k] * a.Ws + (a.Ws - 1 - xk)) * q.wx[k & 1] * q.wy[k >> 1];
+            }
+            // one-sided cell derivatives; exactly on a lattice line (quarter turns: every pixel) the bilinear interpolant
+            // has a kink and the SYMMETRIC derivative is returned -- the mean of the two one-sided values between which
+            // the reference's fp32 coordinates (+-4e-8 off the lattice) choose at random
+            float gx = q.wy[0] * (val[1] - val[0]) + q.wy[1] * (val[3] - val[2]);
+            float gy = q.wx[0] * (val[2] - val[0]) + q.wx[1] * (val[3] - val[1]);
+            if (q.on_x) {
+                const float m0 = q.valid_m[0] * __ldg(ip + q.ym[0] * a.Ws + (flip_src ? a.Ws - 1 - q.xm[0] : q.xm[0]));
+                const float m1 = q.valid_m[1] * __ldg(ip + q.ym[1] * a.Ws + (flip_src ? a.Ws - 1 - q.xm[1] : q.xm[1]));
+                gx = 0.5f * (gx + q.wy[0] * (val[0] - m0) + q.wy[1] * (val[2] - m1));
+            }
+            if (q.on_y) {
+                const float m0 = q.valid_m[2] * __ldg(ip + q.ym[2] * a.Ws + (flip_src ? a.Ws - 1 - q.xm[2] : q.xm[2]));
+                const float m1 = q.valid_m[3] * __ldg(ip + q.ym[3] * a.Ws + (flip_src ? a.Ws - 1 - q.xm[3] : q.xm[3]));
+                gy = 0.5f * (gy + q.wx[0] * (val[0] - m0) + q.wx[1] * (val[1] - m1));
+            }
+            sum_rot += gval * (gx * (float)dxs + gy * (float)dys);
+            if (a.reflect) {
+                if (!canon) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) alt += q2.valid[k] * __ldg(ip + q2.yt[k] * a.Ws + q2.xt[k]) * q2.wx[k & 1] * q2.wy[k >> 1];
+                }
+                // d/dr of r*A + (1-r)*B = A - B, where `cur` is the active member (A when refl = 1, B when refl = 0)
+                sum_ref += gval * (refl ? cur - alt : alt - cur);
+            }
+        }
+        acc_rot += (double)sum_rot;
+        acc_ref += (double)sum_ref;
+    }
+    // block reduction (fp64), one atomic per block and output
+    __shared__ double red[2][8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        acc_rot += __shfl_down_sync(0xffffffffu, acc_rot, o);
+        acc_ref += __shfl_down_sync(0xffffffffu, acc_ref, o);
+    }
+    if (lane == 0) { red[0][warp] = acc_rot; red[1][warp] = acc_ref; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tr = 0.0, tf = 0.0;
+        for (int w = 0; w < 8; ++w) { tr += red[0][w]; tf += red[1][w]; }
+        atomicAdd(e.grad_rotation + sample, (float)(tr * (3.14159265358979323846 / 180.0)));
+        if (e.grad_reflection) atomicAdd(e.grad_reflection + sample, (float)tf);
+    }
+}
+
+}  // namespace eqb
+
+extern "C" int eqb_warp_element_grad(const float *in, const float *grad_out, const int32_t *idx, int B, int C, int H, int W,
+                                     int num_rotations, int reflect, int mode, float *grad_rotation,
+                                     float *grad_reflection, void *stream) {
+    EQB_REQUIRE(B >= 0 && C > 0 && H > 0 && W > 0 && num_rotations > 0, "eqb_warp_element_grad: bad shape");
+    EQB_REQUIRE(mode >= 0 && mode <= 2, "eqb_warp_element_grad: mode must be 0 (canonicalize), 1 (invert scalar) or 2 (invert regular)");
+    const int G = num_rotations * (reflect ? 2 : 1);
+    EQB_REQUIRE(mode != 2 || C % G == 0, "eqb_warp_element_grad: regular representation needs C %% |G| == 0");
+    EQB_REQUIRE(B == 0 || (in && grad_out && idx && grad_rotation), "eqb_warp_element_grad: null pointer");
+    EQB_REQUIRE(B <= 65535, "eqb_warp_element_grad: at most 65535 samples per call");
+    if (B == 0) return 0;
+    ElementGradArgs e{};
+    ResampleArgs &a = e.r;
+    a.src = in; a.dst = nullptr; a.idx = idx; a.B = B; a.C = C;
+    a.Hs = a.Hd = H; a.Ws = a.Wd = W;
+    a.N = num_rotations; a.reflect = reflect != 0; a.G = G;
+    a.mode = mode == 0 ? MODE_CANON : mode == 1 ? MODE_INV_SCALAR : MODE_INV_REGULAR;
+    if (mode == 2) {
+        EQB_UNSUPPORTED(num_rotations > 64, "eqb_warp_element_grad: regular representation supports num_rotations <= 64");
+        for (int r = 0; r < num_rotations; ++r) a.roll[r] = (signed char)regular_roll_shift(r, num_rotations);
+    }
+    a.pad = (mode == 0 && C != 1) ? (W + 1) / 2 : 0;
+    a.ox = -0.5 * (W - 1); a.oy = -0.5 * (H - 1);
+    finish_args(a);
+    e.grad_out = grad_out; e.grad_rotation = grad_rotation; e.grad_reflection = reflect ? grad_reflection : nullptr;
+    cudaStream_t st = (cudaStream_t)stream;
+    EQB_CUDA(cudaMemsetAsync(grad_rotation, 0, (size_t)B * sizeof(float), st));
+    if (e.grad_reflection) EQB_CUDA(cudaMemsetAsync(grad_reflection, 0, (size_t)B * sizeof(float), st));
+    int bx = (H * W + 255) / 256;
+    const int want = std::max(1, (8 * num_sms() + B - 1) / B);
+    bx = std::max(1, std::min(bx, want));
+    warp_element_grad_kernel<<<dim3(bx, B), 256, 0, st>>>(e);
+    return finish_launch("eqb_warp_element_grad");
+}

@@ -40,6 +40,7 @@ _SIGNATURES = {
     "eqb_warp_canonicalize": (C.c_int, [_fp, _fp, _fp] + [_i] * 6 + [_fp]),
     "eqb_warp_invert": (C.c_int, [_fp, _fp, _fp] + [_i] * 7 + [_fp]),
     "eqb_warp_adjoint": (C.c_int, [_fp, _fp, _fp] + [_i] * 7 + [_fp]),
+    "eqb_warp_element_grad": (C.c_int, [_fp, _fp, _fp] + [_i] * 7 + [_fp, _fp, _fp]),
     "eqb_regular_roll_shift": (C.c_int, [_i, _i]),
     "eqb_orbit_expand": (C.c_int, [_fp, _fp] + [_i] * 8 + [_fp]),
     "eqb_orbit_rotate_nearest": (C.c_int, [_fp, _fp] + [_i] * 6 + [_fp]),

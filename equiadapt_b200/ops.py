@@ -271,34 +271,72 @@ def warp_adjoint(grad_out: torch.Tensor, idx: torch.Tensor, num_rotations: int, 
     return grad_in
 
 
+def warp_element_grad(x: torch.Tensor, grad_out: torch.Tensor, idx: torch.Tensor, num_rotations: int, reflect: bool,
+                      mode: int):
+    """(d loss / d rotation [degrees], d loss / d reflection or None) of warp_canonicalize (mode 0) / warp_invert (1, 2)."""
+    dev = _need_cuda(x, grad_out, idx)
+    x, grad_out, idx = _f32(x), _f32(grad_out), _idx32(idx)
+    b, c, h, w = x.shape
+    g_rot = torch.empty(b, dtype=torch.float32, device=dev)
+    g_ref = torch.empty(b, dtype=torch.float32, device=dev) if reflect else None
+    _call("eqb_warp_element_grad", 1 if b else 0, dev, _ptr(x), _ptr(grad_out), _ptr(idx), b, c, h, w, num_rotations,
+          int(reflect), int(mode), _ptr(g_rot), _ptr(g_ref) if reflect else None, _stream(dev))
+    return g_rot, g_ref
+
+
 class _WarpFunction(torch.autograd.Function):
-    """Differentiable (in the image argument) wrapper of the two discrete warps; the group index carries no gradient."""
+    """The two discrete warps as an autograd node: gradients with respect to the image (eqb_warp_adjoint) and to the
+    group element -- rotation in degrees and reflection indicator (eqb_warp_element_grad) -- i.e. what torch autograd
+    derives through kornia's rotate and the flip blend in the reference.  The integer index carries no gradient."""
 
     @staticmethod
-    def forward(ctx, x, idx, num_rotations, reflect, mode):
-        ctx.save_for_backward(idx)
+    def forward(ctx, x, idx, rotation, reflection, num_rotations, reflect, mode):
         ctx.cfg = (num_rotations, reflect, mode)
+        ctx.need_element = (rotation is not None and rotation.requires_grad) or (reflection is not None and reflection.requires_grad)
+        ctx.save_for_backward(idx, x if ctx.need_element else None)
         if mode == 0:
             return warp_canonicalize(x, idx, num_rotations, reflect)
         return warp_invert(x, idx, num_rotations, reflect, mode == 2)
 
     @staticmethod
     def backward(ctx, grad_out):
-        (idx,) = ctx.saved_tensors
+        idx, x = ctx.saved_tensors
         num_rotations, reflect, mode = ctx.cfg
-        return warp_adjoint(grad_out.contiguous(), idx, num_rotations, reflect, mode), None, None, None, None
+        grad_out = grad_out.contiguous()
+        g_x = warp_adjoint(grad_out, idx, num_rotations, reflect, mode) if ctx.needs_input_grad[0] else None
+        g_rot = g_ref = None
+        if ctx.need_element and (ctx.needs_input_grad[2] or ctx.needs_input_grad[3]):
+            g_rot, g_ref = warp_element_grad(x, grad_out, idx, num_rotations, reflect, mode)
+            if not ctx.needs_input_grad[2]:
+                g_rot = None
+            if not ctx.needs_input_grad[3]:
+                g_ref = None
+        return g_x, None, g_rot, g_ref, None, None, None
 
 
-def warp_canonicalize_autograd(x: torch.Tensor, idx: torch.Tensor, num_rotations: int, reflect: bool) -> torch.Tensor:
-    """warp_canonicalize that records an autograd node when x requires grad (inference calls stay node-free)."""
-    if torch.is_grad_enabled() and x.requires_grad:
-        return _WarpFunction.apply(x, idx, num_rotations, reflect, 0)
+def _element_grads(rotation, reflection):
+    rot = rotation if (rotation is not None and rotation.requires_grad) else None
+    ref = reflection if (reflection is not None and reflection.requires_grad) else None
+    return rot, ref
+
+
+def warp_canonicalize_autograd(x: torch.Tensor, idx: torch.Tensor, num_rotations: int, reflect: bool,
+                               rotation: Optional[torch.Tensor] = None, reflection: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """warp_canonicalize that records an autograd node when the image or the (straight-through) element requires
+    grad; inference calls stay node-free.  `rotation` (B, degrees) / `reflection` (B) only receive gradients: the
+    forward value is decided by `idx`."""
+    rot, ref = _element_grads(rotation, reflection)
+    if torch.is_grad_enabled() and (x.requires_grad or rot is not None or ref is not None):
+        return _WarpFunction.apply(x, idx, rot, ref.reshape(-1) if ref is not None else None, num_rotations, reflect, 0)
     return warp_canonicalize(x, idx, num_rotations, reflect)
 
 
-def warp_invert_autograd(f: torch.Tensor, idx: torch.Tensor, num_rotations: int, reflect: bool, regular: bool) -> torch.Tensor:
-    if torch.is_grad_enabled() and f.requires_grad:
-        return _WarpFunction.apply(f, idx, num_rotations, reflect, 2 if regular else 1)
+def warp_invert_autograd(f: torch.Tensor, idx: torch.Tensor, num_rotations: int, reflect: bool, regular: bool,
+                         rotation: Optional[torch.Tensor] = None, reflection: Optional[torch.Tensor] = None) -> torch.Tensor:
+    rot, ref = _element_grads(rotation, reflection)
+    if torch.is_grad_enabled() and (f.requires_grad or rot is not None or ref is not None):
+        return _WarpFunction.apply(f, idx, rot, ref.reshape(-1) if ref is not None else None, num_rotations, reflect,
+                                   2 if regular else 1)
     return warp_invert(f, idx, num_rotations, reflect, regular)
 
 

@@ -131,6 +131,16 @@ EQB_API int eqb_warp_invert(const float *f, float *out, const int32_t *idx, int 
 EQB_API int eqb_warp_adjoint(const float *grad_out, float *grad_in, const int32_t *idx, int B, int C, int H, int W,
                              int num_rotations, int reflect, int mode, void *stream);
 
+/* ---- N3  gradient of the two warps with respect to the GROUP ELEMENT -----------------------------
+ * in: the warp's input image (B,C,H,W); grad_out: d loss / d (warp output).  grad_rotation (B): d loss / d rotation in
+ * DEGREES (the element the reference feeds kornia rotate, discrete_group.py:110-133,213; images/utils.py:57);
+ * grad_reflection (B, may be NULL; ignored unless reflect): d loss / d reflection indicator of the flip blend
+ * (discrete_group.py:209-210; images/utils.py:59-64).  mode as in eqb_warp_adjoint.  Both outputs are overwritten.
+ * With these two the straight-through one-hot of basecanonicalization.py:239-251 trains the canonicalization network. */
+EQB_API int eqb_warp_element_grad(const float *in, const float *grad_out, const int32_t *idx, int B, int C, int H, int W,
+                          int num_rotations, int reflect, int mode, float *grad_rotation, float *grad_reflection,
+                          void *stream);
+
 /* Host-only, no GPU work: the channel shift the reference derives for rotation index r by
  * `(angle / 360.0 * num_rotations).long()` in float32 (images/utils.py:67,:28); equals r for
  * power-of-two N, may truncate to r-1 otherwise (reference quirk reproduced by eqb_warp_invert). */

@@ -1026,3 +1026,149 @@ def test_group_inference_metrics_match_reference_loop(group_type, cuda_device):
     assert float(metrics["test/acc"]) == float(accs[0])
     with pytest.raises(ValueError):
         inf.get_inference_metrics(torch.zeros(2, 3, 40, 40, device=dev), y[:2].to(dev))
+
+
+# ---- N3: gradients with respect to the group element (straight-through training of the canonicalization network) ------
+def _smooth(b, c, h, w, seed):
+    """low-frequency images: the bilinear cell derivative is then close to the derivative of the underlying field"""
+    g = torch.Generator().manual_seed(seed)
+    ys, xs = torch.meshgrid(torch.linspace(0, 1, h), torch.linspace(0, 1, w), indexing="ij")
+    out = torch.zeros(b, c, h, w)
+    for k in range(4):
+        f = torch.rand(b, c, 2, generator=g) * 3 + 0.5
+        ph = torch.rand(b, c, 2, generator=g) * 6.28
+        out += torch.sin(6.28 * f[..., 0, None, None] * xs + ph[..., 0, None, None]) * torch.cos(6.28 * f[..., 1, None, None] * ys + ph[..., 1, None, None])
+    return out / 4
+
+
+@pytest.mark.parametrize("group_type,n", [("rotation", 8), ("roto-reflection", 8), ("rotation", 6), ("roto-reflection", 4),
+                                           ("rotation", 4)])
+def test_warp_element_gradients_vs_oracle_autograd(group_type, n, cuda_device):
+    """eqb_warp_element_grad vs torch autograd through the fp64 oracle (kornia rotate restated + flip blend).
+    Elements that are not quarter turns: 2e-4 relative.  Quarter turns sit exactly on the kinks of the bilinear
+    interpolant (integral source coordinates): the reference lands on either side at random (its fp32 matrix is +-4e-8
+    off the exact permutation) and returns a one-sided derivative; ours returns the symmetric one, checked against the
+    mean of the oracle's gradients at angle +- 1e-3 degrees (the two one-sided values)."""
+    ops = _mods()[0]
+    dev = cuda_device
+    reflect = group_type == "roto-reflection"
+    G = n * (2 if reflect else 1)
+    b, h, w = 2 * G, 40, 40
+    idx = torch.arange(b) % G
+    angles = torch.linspace(0.0, 360.0, n + 1)[:n][idx % n].double()
+    quarter = (angles % 90 == 0)
+    gen = torch.Generator().manual_seed(200 + n + reflect)
+
+    def oracle(fn, delta):
+        a = (angles + delta).clone().requires_grad_(True)
+        r = (idx >= n).double().requires_grad_(True) if reflect else None
+        fn(a, r).backward()
+        return a.grad, (r.grad if reflect else None)
+
+    def check(ours_rot, ours_ref, fn):
+        g0, r0 = oracle(fn, 0.0)
+        gp, _ = oracle(fn, 1e-3)
+        gm, _ = oracle(fn, -1e-3)
+        scale = g0.abs().max()
+        assert ((ours_rot.double() - g0).abs()[~quarter] <= 2e-4 * scale).all()
+        assert ((ours_rot.double() - 0.5 * (gp + gm)).abs()[quarter] <= 2e-3 * scale).all()
+        if reflect:
+            assert rel_err(ours_ref.double(), r0) < 2e-4
+        else:
+            assert ours_ref is None
+
+    x = _smooth(b, 3, h, w, 300 + n)
+    go = torch.randn(b, 3, h, w, generator=gen)
+    o_rot, o_ref = ops.warp_element_grad(x.to(dev), go.to(dev), idx.to(dev).int(), n, reflect, 0)
+    check(o_rot.cpu(), o_ref.cpu() if reflect else None,
+          lambda a, r: (O.canonicalize_image(x.double(), a, r) * go.double()).sum())
+    for mode, rep, c in ((1, "scalar", 3), (2, "regular", 2 * G)):
+        f = _smooth(b, c, h, w, 400 + n + mode)
+        gf = torch.randn(b, c, h, w, generator=gen)
+        o_rot, o_ref = ops.warp_element_grad(f.to(dev), gf.to(dev), idx.to(dev).int(), n, reflect, mode)
+
+        def inverted(a, r):
+            if rep == "scalar":
+                return O.invert_image_features(f.double(), a, r, n, G, "scalar")
+            # regular: the channel roll is `.long()` of the angle (images/utils.py:28,67) and carries no gradient; it is
+            # taken from the exact angles so that the +-1e-3 degree probes do not truncate to a different shift
+            out = O.invert_image_features(f.double(), a, r, n, G, "scalar").reshape(b, c // G, G, h, w)
+            shift = angles.float() / 360.0 * n
+            if reflect:
+                out = torch.cat([O.roll_by_gather(out[:, :, :n], shift), O.roll_by_gather(out[:, :, n:], -shift)], dim=2)
+            else:
+                out = O.roll_by_gather(out, shift)
+            return out.reshape(b, c, h, w)
+
+        assert torch.equal(inverted(angles, (idx >= n).double() if reflect else None),
+                           O.invert_image_features(f.double(), angles, (idx >= n).double() if reflect else None, n, G, rep))
+        check(o_rot.cpu(), o_ref.cpu() if reflect else None, lambda a, r: (inverted(a, r) * gf.double()).sum())
+
+
+@pytest.mark.parametrize("group_type", ["rotation", "roto-reflection"])
+def test_canonicalization_network_trains_through_straight_through_element(group_type, cuda_device):
+    """The reference's training step (examples/images/classification/model.py:71-127) with a torch canonicalization
+    network: task loss -> canonicalize warp -> straight-through one-hot -> network, plus the prior loss.  The gradient of
+    every network parameter equals torch autograd through the oracle chain (same network, fp64)."""
+    from equiadapt_b200.images.canonicalization.discrete_group import GroupEquivariantImageCanonicalization
+    dev = cuda_device
+    n, reflect = 8, group_type == "roto-reflection"
+    G = n * (2 if reflect else 1)
+
+    class Scorer(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.group_type, self.num_rotations = group_type, n
+            self.conv = torch.nn.Conv2d(3, 6, 5)
+            self.fc = torch.nn.Linear(6, G)
+
+        def forward(self, x):
+            return self.fc(torch.tanh(self.conv(x)).mean(dim=(2, 3)))
+
+    torch.manual_seed(210 + reflect)
+    net = Scorer()
+    hp = SimpleNamespace(beta=1.0, input_crop_ratio=1.0, resize_shape=32)
+    can = GroupEquivariantImageCanonicalization(net.to(dev), hp, (3, 32, 32)).train()
+    x = _smooth(8, 3, 32, 32, 220)
+    wtask = torch.randn(8, 3, 32, 32, generator=torch.Generator().manual_seed(221))
+    xc = can(x.to(dev))
+    assert xc.requires_grad
+    loss = (xc * wtask.to(dev)).sum() + 100.0 * can.get_prior_regularization_loss()
+    loss.backward()
+    idx = can.canonicalization_info_dict["group_element"].index.cpu().long()
+    ours = {k: p.grad.detach().cpu().double() for k, p in net.named_parameters()}
+
+    import copy
+    ref = copy.deepcopy(net).cpu().double()
+    xd = x.double()
+    angles = torch.linspace(0.0, 360.0, n + 1)[:n].double()
+    comp = torch.cat([angles, angles]) if reflect else angles
+
+    def reference_step(delta):
+        """loss and parameter gradients of the reference chain, the rotation probed at +delta degrees"""
+        for p in ref.parameters():
+            p.grad = None
+        act = ref(xd)                   # crop ratio 1, resize 32 -> the pre-network transform is the identity
+        assert torch.equal(act.argmax(-1), idx)
+        onehot = torch.nn.functional.one_hot(act.argmax(-1), G).double()
+        soft = torch.softmax(hp.beta * act, -1)
+        st = onehot + soft - soft.detach()                                      # basecanonicalization.py:239-251
+        rot = (st * comp).sum(-1) + delta                                       # discrete_group.py:110-133
+        refl = (st * torch.cat([torch.zeros(n), torch.ones(n)]).double()).sum(-1) if reflect else None
+        yo = O.canonicalize_image(xd, rot, refl)
+        lo = (yo * wtask.double()).sum() + 100.0 * torch.nn.functional.cross_entropy(act, torch.zeros(8, dtype=torch.long))
+        lo.backward()
+        return float(lo.detach()), {k: p.grad.clone() for k, p in ref.named_parameters()}
+
+    lo, _ = reference_step(0.0)
+    assert abs(float(loss.detach()) - lo) < 1e-3 * abs(lo)
+    # quarter-turn samples sit on the kinks of the bilinear interpolant: the reference's gradient there is one of the
+    # two one-sided values (chosen by fp32 noise), ours the symmetric one = the mean of the +-1e-3 degree probes;
+    # for the other samples the two probes agree to O(delta)
+    _, gp = reference_step(1e-3)
+    _, gm = reference_step(-1e-3)
+    for k in gp:
+        assert rel_err(ours[k], 0.5 * (gp[k] + gm[k])) < 2e-3, k
+    # and an optimiser step changes the activations
+    opt = torch.optim.SGD(net.parameters(), lr=1e-3)
+    opt.step()
