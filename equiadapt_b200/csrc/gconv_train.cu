@@ -1,0 +1,324 @@
+// N3: training kernels of the group-conv canonicalization network (CustomEquivariantNetwork).
+//
+// The reference trains this network through torch autograd over, per layer, the filter-orbit construction
+// (custom_group_equivariant_layers.py:62-90, :169-199, :298-334, :461-507), F.conv2d (:104-112, :352-361), ReLU and the
+// final mean (custom_equivariant_networks.py:80-93).  The fused inference stack (gconv_stack*.cu) keeps no
+// activations, so training uses a layer-wise path that does: the forward conv saves every post-ReLU feature map, the
+// backward needs, per layer,
+//     dW_x[n, (ci,ky,kx)] = sum_{b,p} dY[b,n,p] X[b,ci,p+(ky,kx)]              (conv2d_weight_grad_kernel)
+//     dX[b,c,p]           = [X[b,c,p] > 0] sum_n W_x[n,c] dY[b,n,p]            (conv2d_forward_kernel on W_x^T, 1x1, masked)
+//     db_x[n]             = sum_{b,p} dY[b,n,p]                                (plane_sums_kernel, then a (B,N) sum)
+// and the adjoints of the two (linear) filter-orbit maps (orbit_adjoint kernels).  These are fp32 SIMT kernels with
+// 64 x 64 register-blocked tiles: correctness and completeness of the training step first; the tensor-core treatment
+// the inference stack got is the obvious successor (weight gradients are NT GEMMs with K = B*H*W).
+#include <stdlib.h>
+
+#include "common.cuh"
+
+namespace eqb {
+
+constexpr int GT_T = 64;    // tile side (outputs)
+constexpr int GT_K = 16;    // reduction chunk
+constexpr int GT_THREADS = 256;
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Y[b,n,p] = act( bias[n] + sum_kk W[n,kk] * X[b, ci(kk), y(p)+ky(kk), x(p)+kx(kk)] ) [* (mask[b,n,p] > 0)]
+// valid k x k convolution, NCHW fp32.  grid (ceil(P/64), ceil(N/64), B); thread (tx, ty) owns pixels tx*4..+3 and
+// channels ty*4..+3 of the tile.
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(GT_THREADS) conv2d_forward_kernel(const float *__restrict__ X, const float *__restrict__ Wn,
+                                                                    const float *__restrict__ bias, const float *__restrict__ mask,
+                                                                    float *__restrict__ Y, int Cin, int H, int W, int k, int N,
+                                                                    int relu) {
+    __shared__ float ws[GT_K][GT_T + 4];   // [kk][n]
+    __shared__ float xs[GT_K][GT_T + 4];   // [kk][p]
+    const int Ho = H - k + 1, Wo = W - k + 1, P = Ho * Wo, K = Cin * k * k, kk2 = k * k;
+    const int b = blockIdx.z, n0 = blockIdx.y * GT_T, p0 = blockIdx.x * GT_T;
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const float *xb = X + (size_t)b * Cin * H * W;
+    float acc[4][4] = {};
+    // loader roles: 256 threads fill 16 x 64 entries of each tile, 4 per thread
+    const int lk = tid >> 4;            // 0..15  reduction row
+    const int lc = (tid & 15) * 4;      // 0..60  column group
+    int poff[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int p = min(p0 + lc + j, P - 1);
+        poff[j] = (p / Wo) * W + (p % Wo);
+    }
+    for (int k0 = 0; k0 < K; k0 += GT_K) {
+        const int kk = k0 + lk;
+        {   // weights: ws[lk][lc..lc+3] = W[n0+lc+j][kk]
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int n = n0 + lc + j;
+                ws[lk][lc + j] = (kk < K && n < N) ? __ldg(Wn + (size_t)n * K + kk) : 0.f;
+            }
+            // im2col: xs[lk][lc..lc+3] = X[b, ci, y+ky, x+kx]
+            if (kk < K) {
+                const int ci = kk / kk2, r = kk - ci * kk2, ky = r / k, kx = r - ky * k;
+                const float *xp = xb + (size_t)ci * H * W + ky * W + kx;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) xs[lk][lc + j] = __ldg(xp + poff[j]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) xs[lk][lc + j] = 0.f;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < GT_K; ++q) {
+            const float4 wv = *reinterpret_cast<const float4 *>(&ws[q][ty * 4]);
+            const float4 xv = *reinterpret_cast<const float4 *>(&xs[q][tx * 4]);
+            const float wr[4] = {wv.x, wv.y, wv.z, wv.w}, xr[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(wr[i], xr[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int n = n0 + ty * 4 + i;
+        if (n >= N) continue;
+        const float bv = bias ? bias[n] : 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int p = p0 + tx * 4 + j;
+            if (p >= P) continue;
+            const size_t o = ((size_t)b * N + n) * P + p;
+            float v = acc[i][j] + bv;
+            if (relu) v = fmaxf(v, 0.f);
+            if (mask) v = mask[o] > 0.f ? v : 0.f;
+            Y[o] = v;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// dW[n, kk] += sum over this CTA's (b, pixel) range of dY[b,n,p] * X[b, ci(kk), y(p)+ky, x(p)+kx].
+// grid (ceil(K/64), ceil(N/64), splits); the reduction range B*P is cut into `splits` contiguous pieces of whole
+// 16-pixel chunks; partial tiles are added atomically (dW is zeroed by the caller).
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(GT_THREADS) conv2d_weight_grad_kernel(const float *__restrict__ dY, const float *__restrict__ X,
+                                                                        float *__restrict__ dW, int B, int Cin, int H, int W,
+                                                                        int k, int N, int chunks_per_split) {
+    __shared__ float gs[GT_K][GT_T + 4];   // [p][n]
+    __shared__ float xs[GT_K][GT_T + 4];   // [p][kk]
+    const int Ho = H - k + 1, Wo = W - k + 1, P = Ho * Wo, K = Cin * k * k, kk2 = k * k;
+    const int kk0 = blockIdx.x * GT_T, n0 = blockIdx.y * GT_T;
+    const int chunks_per_image = (P + GT_K - 1) / GT_K;
+    const long long total_chunks = (long long)B * chunks_per_image;
+    const long long c_begin = (long long)blockIdx.z * chunks_per_split;
+    const long long c_end = min(total_chunks, c_begin + chunks_per_split);
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    // loader roles: lanes run along the 16 pixels of the chunk (contiguous in memory), thread owns columns lc + 16 j
+    const int lp = tid & 15, lc = tid >> 4;
+    int xoff[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int kk = kk0 + lc + 16 * j;
+        xoff[j] = -1;
+        if (kk < K) {
+            const int ci = kk / kk2, r = kk - ci * kk2, ky = r / k, kx = r - ky * k;
+            xoff[j] = ci * H * W + ky * W + kx;
+        }
+    }
+    float acc[4][4] = {};
+    for (long long c = c_begin; c < c_end; ++c) {
+        const int b = (int)(c / chunks_per_image), pc = (int)(c - (long long)b * chunks_per_image) * GT_K;
+        const float *gyb = dY + ((size_t)b * N) * P;
+        const float *xb = X + (size_t)b * Cin * H * W;
+        const int p = pc + lp;
+        const int pix = p < P ? (p / Wo) * W + (p % Wo) : 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int col = lc + 16 * j, n = n0 + col;
+            gs[lp][col] = (p < P && n < N) ? __ldg(gyb + (size_t)n * P + p) : 0.f;
+            xs[lp][col] = (p < P && xoff[j] >= 0) ? __ldg(xb + xoff[j] + pix) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < GT_K; ++q) {
+            const float4 gv = *reinterpret_cast<const float4 *>(&gs[q][ty * 4]);
+            const float4 xv = *reinterpret_cast<const float4 *>(&xs[q][tx * 4]);
+            const float gr[4] = {gv.x, gv.y, gv.z, gv.w}, xr[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(gr[i], xr[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int n = n0 + ty * 4 + i;
+        if (n >= N) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int kk = kk0 + tx * 4 + j;
+            if (kk < K) atomicAdd(dW + (size_t)n * K + kk, acc[i][j]);
+        }
+    }
+}
+
+// out[row] = sum_p x[row, p]   (fp64 accumulation, one CTA per row)
+__global__ void __launch_bounds__(256) plane_sums_kernel(const float *__restrict__ x, long long P, float *__restrict__ out) {
+    const float *xr = x + (size_t)blockIdx.x * P;
+    double acc = 0.0;
+    for (long long p = threadIdx.x; p < P; p += blockDim.x) acc += (double)__ldg(xr + p);
+    __shared__ double red[8];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += red[w];
+        out[blockIdx.x] = (float)t;
+    }
+}
+
+// dY[b, o*G + g, p] = scale * dact[b, g]     (backward of the mean over (o, p), custom_equivariant_networks.py:91)
+__global__ void __launch_bounds__(256) group_mean_backward_kernel(const float *__restrict__ dact, float *__restrict__ dY,
+                                                                  int N, int G, long long P, float scale) {
+    const int row = blockIdx.x;            // b * N + n
+    const int b = row / N, n = row - b * N;
+    const float v = scale * dact[(size_t)b * G + n % G];
+    float *d = dY + (size_t)row * P;
+    for (long long p = threadIdx.x; p < P; p += blockDim.x) d[p] = v;
+}
+
+// ---- adjoints of the filter orbits (small_ops.cu: lift_orbit_kernel / regular_orbit_kernel) -----------------------
+// orbit[n, kk] = rotated_tap(w_slice, ...) is a 4-tap bilinear gather; its adjoint scatters the same four weights.
+__device__ __forceinline__ void rotated_tap_scatter(float *__restrict__ dw, float gv, int k, int y, int x, int r, int N, bool mirror) {
+    if (mirror) x = k - 1 - x;
+    double c, s;
+    rot_cs(r, N, 1.0, c, s);
+    const double ctr = 0.5 * (k - 1);
+    const double u = x - ctr, v = y - ctr;
+    const double xs = ctr + c * u - s * v, ys = ctr + s * u + c * v;
+    const double xf = floor(xs), yf = floor(ys);
+    const float fx = (float)(xs - xf), fy = (float)(ys - yf);
+    const int x0 = (int)xf, y0 = (int)yf;
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) {
+            const int xi = x0 + dx, yi = y0 + dy;
+            if (xi >= 0 && xi < k && yi >= 0 && yi < k) {
+                const float wt = (dy ? fy : 1.f - fy) * (dx ? fx : 1.f - fx);
+                if (wt != 0.f) atomicAdd(dw + yi * k + xi, wt * gv);
+            }
+        }
+}
+
+__device__ __forceinline__ int regular_src_slice_t(int g, int h, int N) {   // same table as small_ops.cu
+    if (g < N) return h < N ? (h - g + N) % N : N + (h - N + g) % N;
+    const int gp = g - N;
+    return h < N ? N + (h + gp) % N : (h - N - gp + N) % N;
+}
+
+__global__ void lift_orbit_adjoint_kernel(const float *__restrict__ dorbit, float *__restrict__ dw, int cout, int cin, int k,
+                                          int N, int G) {
+    const int kk2 = k * k, K = cin * kk2;
+    const long long total = (long long)cout * G * K;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int kk = (int)(t % K), n = (int)(t / K);
+        const int o = n / G, g = n % G, i = kk / kk2, yx = kk % kk2;
+        rotated_tap_scatter(dw + ((size_t)o * cin + i) * kk2, dorbit[t], k, yx / k, yx % k, g % N, N, g >= N);
+    }
+}
+
+__global__ void regular_orbit_adjoint_kernel(const float *__restrict__ dorbit, float *__restrict__ dw, int cout, int cin, int k,
+                                             int N, int G) {
+    const int kk2 = k * k, K = cin * G * kk2;
+    const long long total = (long long)cout * G * K;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int kk = (int)(t % K), n = (int)(t / K);
+        const int o = n / G, g = n % G, ih = kk / kk2, yx = kk % kk2;
+        const int i = ih / G, h = ih % G;
+        const int src = regular_src_slice_t(g, h, N);
+        rotated_tap_scatter(dw + (((size_t)o * cin + i) * G + src) * kk2, dorbit[t], k, yx / k, yx % k, g % N, N, g >= N);
+    }
+}
+
+}  // namespace eqb
+
+using namespace eqb;
+
+extern "C" int eqb_conv2d_forward(const float *x, const float *w, const float *bias, const float *mask, float *y, int B,
+                                  int cin, int H, int W, int N, int k, int relu, void *stream) {
+    EQB_REQUIRE(B >= 0 && cin > 0 && N > 0 && k > 0 && H >= k && W >= k, "eqb_conv2d_forward: bad shape");
+    EQB_REQUIRE(B == 0 || (x && w && y), "eqb_conv2d_forward: null pointer");
+    EQB_REQUIRE(B <= 65535 && (N + GT_T - 1) / GT_T <= 65535, "eqb_conv2d_forward: grid too large");
+    if (B == 0) return 0;
+    const int P = (H - k + 1) * (W - k + 1);
+    dim3 grid((P + GT_T - 1) / GT_T, (N + GT_T - 1) / GT_T, B);
+    conv2d_forward_kernel<<<grid, GT_THREADS, 0, (cudaStream_t)stream>>>(x, w, bias, mask, y, cin, H, W, k, N, relu);
+    return finish_launch("eqb_conv2d_forward");
+}
+
+extern "C" int eqb_conv2d_weight_grad(const float *dy, const float *x, float *dw, int B, int cin, int H, int W, int N, int k,
+                                      void *stream) {
+    EQB_REQUIRE(B >= 0 && cin > 0 && N > 0 && k > 0 && H >= k && W >= k, "eqb_conv2d_weight_grad: bad shape");
+    EQB_REQUIRE(dw && (B == 0 || (dy && x)), "eqb_conv2d_weight_grad: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int K = cin * k * k, P = (H - k + 1) * (W - k + 1);
+    EQB_CUDA(cudaMemsetAsync(dw, 0, (size_t)N * K * sizeof(float), st));
+    if (B == 0) return 0;
+    const int tiles = ((K + GT_T - 1) / GT_T) * ((N + GT_T - 1) / GT_T);
+    const long long total_chunks = (long long)B * ((P + GT_K - 1) / GT_K);
+    long long splits = (4LL * num_sms() + tiles - 1) / tiles;       // a few waves of CTAs
+    splits = std::max(1LL, std::min(std::min(splits, total_chunks), 65535LL));
+    const long long per = (total_chunks + splits - 1) / splits;
+    splits = (total_chunks + per - 1) / per;
+    EQB_REQUIRE(per < (1LL << 31), "eqb_conv2d_weight_grad: reduction too long");
+    dim3 grid((K + GT_T - 1) / GT_T, (N + GT_T - 1) / GT_T, (unsigned)splits);
+    conv2d_weight_grad_kernel<<<grid, GT_THREADS, 0, st>>>(dy, x, dw, B, cin, H, W, k, N, (int)per);
+    return finish_launch("eqb_conv2d_weight_grad");
+}
+
+extern "C" int eqb_plane_sums(const float *x, int64_t rows, int64_t P, float *out, void *stream) {
+    EQB_REQUIRE(rows >= 0 && P > 0 && rows < (1LL << 31), "eqb_plane_sums: bad shape");
+    EQB_REQUIRE(rows == 0 || (x && out), "eqb_plane_sums: null pointer");
+    if (rows == 0) return 0;
+    plane_sums_kernel<<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>(x, P, out);
+    return finish_launch("eqb_plane_sums");
+}
+
+extern "C" int eqb_group_mean_backward(const float *dact, float *dy, int B, int cout, int num_group, int64_t P, void *stream) {
+    EQB_REQUIRE(B >= 0 && cout > 0 && num_group > 0 && P > 0, "eqb_group_mean_backward: bad shape");
+    EQB_REQUIRE(B == 0 || (dact && dy), "eqb_group_mean_backward: null pointer");
+    const long long rows = (long long)B * cout * num_group;
+    EQB_REQUIRE(rows < (1LL << 31), "eqb_group_mean_backward: too many planes");
+    if (rows == 0) return 0;
+    group_mean_backward_kernel<<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>(dact, dy, cout * num_group, num_group, P,
+                                                                                 (float)(1.0 / ((double)cout * (double)P)));
+    return finish_launch("eqb_group_mean_backward");
+}
+
+extern "C" int eqb_lift_filter_orbit_adjoint(const float *dorbit, float *dw, int cout, int cin, int k, int num_rotations,
+                                             int reflect, void *stream) {
+    EQB_REQUIRE(cout > 0 && cin > 0 && k > 0 && num_rotations > 0 && dorbit && dw, "eqb_lift_filter_orbit_adjoint: bad argument");
+    const int G = num_rotations * (reflect ? 2 : 1);
+    cudaStream_t st = (cudaStream_t)stream;
+    EQB_CUDA(cudaMemsetAsync(dw, 0, (size_t)cout * cin * k * k * sizeof(float), st));
+    const long long total = (long long)cout * G * cin * k * k;
+    lift_orbit_adjoint_kernel<<<(unsigned)std::min<long long>((total + 255) / 256, 4096), 256, 0, st>>>(dorbit, dw, cout, cin, k,
+                                                                                                      num_rotations, G);
+    return finish_launch("eqb_lift_filter_orbit_adjoint");
+}
+
+extern "C" int eqb_regular_filter_orbit_adjoint(const float *dorbit, float *dw, int cout, int cin, int k, int num_rotations,
+                                                int reflect, void *stream) {
+    EQB_REQUIRE(cout > 0 && cin > 0 && k > 0 && num_rotations > 0 && dorbit && dw, "eqb_regular_filter_orbit_adjoint: bad argument");
+    const int G = num_rotations * (reflect ? 2 : 1);
+    cudaStream_t st = (cudaStream_t)stream;
+    EQB_CUDA(cudaMemsetAsync(dw, 0, (size_t)cout * cin * G * k * k * sizeof(float), st));
+    const long long total = (long long)cout * G * cin * G * k * k;
+    regular_orbit_adjoint_kernel<<<(unsigned)std::min<long long>((total + 255) / 256, 4096), 256, 0, st>>>(dorbit, dw, cout, cin, k,
+                                                                                                         num_rotations, G);
+    return finish_launch("eqb_regular_filter_orbit_adjoint");
+}

@@ -123,6 +123,11 @@ class CustomEquivariantNetwork(nn.Module):
         # only: rebuilt when a parameter was modified in place or replaced, reused otherwise.  (The reference
         # rebuilds its orbits on every forward: custom_group_equivariant_layers.py:103, :349-351.)
         params = [p for m in mods for p in (m.weights, m.bias) if p is not None]
+        if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in params):
+            # train() mode: layer-wise path that keeps the feature maps, backward on the N3 kernels (gconv_train.cu).
+            # eval() mode always takes the fused inference stack (no autograd graph).  The gradient with respect to
+            # the input image is not produced (the reference's examples never use it).
+            return ops.gconv_stack_train(x, [(m.weights, m.bias) for m in mods], self.num_rotations, reflect)
         key = tuple((p.data_ptr(), p._version) for p in params)
         if getattr(self, "_packed_key", None) != key:
             self._packed = ops.gconv_stack_pack(lift.weights, lift.bias, [m.weights for m in regs],

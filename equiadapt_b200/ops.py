@@ -97,6 +97,134 @@ def regular_filter_orbit(w: torch.Tensor, num_rotations: int, reflect: bool) -> 
     return out
 
 
+# ---- N3: training kernels of the group-conv network -------------------------------------------------
+def conv2d_forward(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], relu: bool,
+                   mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """[relu](conv2d(x, w) + bias), valid k x k, optionally zeroed where mask <= 0."""
+    dev = _need_cuda(x, w)
+    x, w = _f32(x), _f32(w)
+    b, cin, h, wd = x.shape
+    n, cin2, k, k2 = w.shape
+    if cin2 != cin or k != k2:
+        raise ValueError(f"filter {tuple(w.shape)} does not match input {tuple(x.shape)}")
+    bias = _f32(bias) if bias is not None else None
+    mask = _f32(mask) if mask is not None else None
+    y = torch.empty((b, n, h - k + 1, wd - k + 1), dtype=torch.float32, device=dev)
+    if mask is not None and mask.shape != y.shape:
+        raise ValueError("mask must have the output's shape")
+    _call("eqb_conv2d_forward", 1 if b else 0, dev, _ptr(x), _ptr(w), _ptr(bias) if bias is not None else None,
+          _ptr(mask) if mask is not None else None, _ptr(y), b, cin, h, wd, n, k, int(relu), _stream(dev))
+    return y
+
+
+def conv2d_weight_grad(dy: torch.Tensor, x: torch.Tensor, k: int) -> torch.Tensor:
+    dev = _need_cuda(dy, x)
+    dy, x = _f32(dy), _f32(x)
+    b, cin, h, wd = x.shape
+    n = dy.shape[1]
+    if tuple(dy.shape) != (b, n, h - k + 1, wd - k + 1):
+        raise ValueError("dy does not match a valid k x k convolution of x")
+    dw = torch.empty((n, cin, k, k), dtype=torch.float32, device=dev)
+    _call("eqb_conv2d_weight_grad", 1 if b else 0, dev, _ptr(dy), _ptr(x), _ptr(dw), b, cin, h, wd, n, k, _stream(dev))
+    return dw
+
+
+def plane_sums(x: torch.Tensor) -> torch.Tensor:
+    """(B, C, H, W) -> (B, C) sums over the plane."""
+    dev = _need_cuda(x)
+    x = _f32(x)
+    b, c = x.shape[:2]
+    out = torch.empty((b, c), dtype=torch.float32, device=dev)
+    _call("eqb_plane_sums", 1 if b * c else 0, dev, _ptr(x), b * c, x[0, 0].numel(), _ptr(out), _stream(dev))
+    return out
+
+
+def group_mean_backward(dact: torch.Tensor, cout: int, out_hw: Tuple[int, int]) -> torch.Tensor:
+    dev = _need_cuda(dact)
+    dact = _f32(dact)
+    b, g = dact.shape
+    dy = torch.empty((b, cout * g, out_hw[0], out_hw[1]), dtype=torch.float32, device=dev)
+    _call("eqb_group_mean_backward", 1 if b else 0, dev, _ptr(dact), _ptr(dy), b, cout, g, out_hw[0] * out_hw[1], _stream(dev))
+    return dy
+
+
+def lift_filter_orbit_adjoint(dorbit: torch.Tensor, cout: int, num_rotations: int, reflect: bool) -> torch.Tensor:
+    dev = _need_cuda(dorbit)
+    dorbit = _f32(dorbit)
+    n, cin, k, _ = dorbit.shape
+    dw = torch.empty((cout, cin, k, k), dtype=torch.float32, device=dev)
+    _call("eqb_lift_filter_orbit_adjoint", 1, dev, _ptr(dorbit), _ptr(dw), cout, cin, k, num_rotations, int(reflect), _stream(dev))
+    return dw
+
+
+def regular_filter_orbit_adjoint(dorbit: torch.Tensor, cout: int, num_rotations: int, reflect: bool) -> torch.Tensor:
+    dev = _need_cuda(dorbit)
+    dorbit = _f32(dorbit)
+    g = num_rotations * (2 if reflect else 1)
+    n, cing, k, _ = dorbit.shape
+    cin = cing // g
+    dw = torch.empty((cout, cin, g, k, k), dtype=torch.float32, device=dev)
+    _call("eqb_regular_filter_orbit_adjoint", 1, dev, _ptr(dorbit), _ptr(dw), cout, cin, k, num_rotations, int(reflect), _stream(dev))
+    return dw
+
+
+class _GConvStackTrain(torch.autograd.Function):
+    """CustomEquivariantNetwork.forward as an autograd node for TRAINING (custom_equivariant_networks.py:80-93): layer-wise
+    forward that keeps the post-ReLU feature maps, backward on the N3 kernels (weight gradients, masked 1x1 data
+    gradients, bias sums, filter-orbit adjoints).  Arguments: x, then (weights, bias) per layer, flattened."""
+
+    @staticmethod
+    def forward(ctx, x, num_rotations, reflect, *params):
+        g = num_rotations * (2 if reflect else 1)
+        layers = [(params[i], params[i + 1]) for i in range(0, len(params), 2)]
+        cout = layers[0][0].shape[0]
+        feats, filters = [], []
+        h = x
+        for li, (w, bias) in enumerate(layers):
+            wx = lift_filter_orbit(w.detach(), num_rotations, reflect) if li == 0 else regular_filter_orbit(w.detach(), num_rotations, reflect)
+            bx = bias.detach().repeat_interleave(g) if bias is not None else None        # channel = o*|G| + g
+            feats.append(h)
+            filters.append(wx)
+            h = conv2d_forward(h, wx, bx, relu=li < len(layers) - 1)
+        sums = plane_sums(h)                                                               # (B, cout*|G|)
+        act = sums.reshape(-1, cout, g).sum(1) / float(cout * h.shape[-2] * h.shape[-1])
+        ctx.cfg = (num_rotations, reflect, cout, tuple(h.shape[-2:]), [b is not None for _, b in layers])
+        ctx.save_for_backward(*feats, *filters)
+        return act
+
+    @staticmethod
+    def backward(ctx, dact):
+        num_rotations, reflect, cout, out_hw, has_bias = ctx.cfg
+        g = num_rotations * (2 if reflect else 1)
+        nl = len(has_bias)
+        feats, filters = ctx.saved_tensors[:nl], ctx.saved_tensors[nl:]
+        dy = group_mean_backward(dact.contiguous(), cout, out_hw)
+        grads = [None] * (2 * nl)
+        for li in range(nl - 1, -1, -1):
+            xin, wx = feats[li], filters[li]
+            k = wx.shape[-1]
+            if has_bias[li] and ctx.needs_input_grad[3 + 2 * li + 1]:
+                grads[2 * li + 1] = plane_sums(dy).sum(0).reshape(cout, g).sum(1)
+            if ctx.needs_input_grad[3 + 2 * li]:
+                dwx = conv2d_weight_grad(dy, xin, k)
+                grads[2 * li] = (lift_filter_orbit_adjoint(dwx, cout, num_rotations, reflect) if li == 0
+                                 else regular_filter_orbit_adjoint(dwx, cout, num_rotations, reflect))
+            if li > 0:
+                # data gradient through the 1x1 layer and the ReLU in front of it: conv with W^T, masked by the saved input
+                wt = wx.reshape(wx.shape[0], wx.shape[1]).t().contiguous().reshape(wx.shape[1], wx.shape[0], 1, 1)
+                dy = conv2d_forward(dy, wt, None, relu=False, mask=xin)
+        return (None, None, None, *grads)
+
+
+def gconv_stack_train(x: torch.Tensor, layers, num_rotations: int, reflect: bool) -> torch.Tensor:
+    """Differentiable (in the layer parameters) group activations; `layers` = [(weights, bias or None), ...]."""
+    for li, (w, _) in enumerate(layers):
+        if li > 0 and w.shape[-1] != 1:
+            raise NotImplementedError("training path: regular layers are 1 x 1 (all CustomEquivariantNetwork builds)")
+    flat = [t for pair in layers for t in pair]
+    return _GConvStackTrain.apply(x, num_rotations, reflect, *flat)
+
+
 # ---- a4..a6 -------------------------------------------------------------------------------------
 def _stack_dims(lift_w, reg_w, num_rotations, reflect):
     cout, cin, k, k2 = lift_w.shape

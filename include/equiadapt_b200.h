@@ -224,6 +224,31 @@ EQB_API int eqb_vndeepsets_forward(const float *loc, const float *vel, const flo
                                    int final_pool_mean, int canon_translation, float *rot_vectors, float *translation,
                                    void *workspace, int64_t workspace_bytes, int32_t *bad_edges, void *stream);
 
+/* ---- N3  training kernels of the group-conv canonicalization network ------------------------------
+ * What torch autograd derives in the reference for CustomEquivariantNetwork (custom_equivariant_networks.py:80-93)
+ * through F.conv2d / ReLU / mean (custom_group_equivariant_layers.py:104-112, :352-361) and the filter-orbit
+ * construction (:62-90, :169-199, :298-334, :461-507).  The fused inference stack keeps no activations; training runs
+ * layer by layer on these, saving every post-ReLU feature map.  All tensors NCHW fp32, valid k x k convolution,
+ * w (N, cin, k, k).
+ *   eqb_conv2d_forward:      y = [relu](conv2d(x, w) + bias) [zeroed where mask <= 0]; bias / mask may be NULL.  With w
+ *                            transposed, k = 1 and mask = the saved input feature map it is the data gradient of a 1x1
+ *                            layer through the preceding ReLU.
+ *   eqb_conv2d_weight_grad:  dw[n, ci, ky, kx] = sum_{b,y,x} dy[b,n,y,x] x[b,ci,y+ky,x+kx]  (dw overwritten).
+ *   eqb_plane_sums:          out[row] = sum_p x[row, p] (bias gradients, spatial sums).
+ *   eqb_group_mean_backward: dy[b, o*|G|+g, p] = dact[b,g] / (cout * P), the backward of the final mean.
+ *   eqb_*_filter_orbit_adjoint: gradient of the base weights from the gradient of the expanded filters (the orbit
+ *                            maps are linear: the adjoint scatters the same bilinear taps; dw overwritten). */
+EQB_API int eqb_conv2d_forward(const float *x, const float *w, const float *bias, const float *mask, float *y, int B,
+                       int cin, int H, int W, int N, int k, int relu, void *stream);
+EQB_API int eqb_conv2d_weight_grad(const float *dy, const float *x, float *dw, int B, int cin, int H, int W, int N, int k,
+                           void *stream);
+EQB_API int eqb_plane_sums(const float *x, int64_t rows, int64_t P, float *out, void *stream);
+EQB_API int eqb_group_mean_backward(const float *dact, float *dy, int B, int cout, int num_group, int64_t P, void *stream);
+EQB_API int eqb_lift_filter_orbit_adjoint(const float *dorbit, float *dw, int cout, int cin, int k, int num_rotations,
+                                  int reflect, void *stream);
+EQB_API int eqb_regular_filter_orbit_adjoint(const float *dorbit, float *dw, int cout, int cin, int k, int num_rotations,
+                                     int reflect, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

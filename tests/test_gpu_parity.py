@@ -1172,3 +1172,113 @@ def test_canonicalization_network_trains_through_straight_through_element(group_
     # and an optimiser step changes the activations
     opt = torch.optim.SGD(net.parameters(), lr=1e-3)
     opt.step()
+
+
+# ---- N3: training path of CustomEquivariantNetwork (layer-wise forward + backward kernels) ------------------------------
+@pytest.mark.parametrize("b,cin,h,w,n,k,relu", [(3, 3, 20, 24, 32, 5, True), (2, 70, 9, 11, 130, 1, False), (1, 5, 8, 8, 7, 3, True)])
+def test_conv2d_forward_and_weight_grad_vs_torch(b, cin, h, w, n, k, relu, cuda_device):
+    """eqb_conv2d_forward / eqb_conv2d_weight_grad / eqb_plane_sums vs torch fp64 (F.conv2d and its autograd: what the
+    reference runs, custom_group_equivariant_layers.py:104-112).  fp32 tolerance 1e-5 relative."""
+    ops = _mods()[0]
+    dev = cuda_device
+    g = torch.Generator().manual_seed(b * 100 + n)
+    x = torch.randn(b, cin, h, w, generator=g)
+    wt = torch.randn(n, cin, k, k, generator=g) * 0.2
+    bias = torch.randn(n, generator=g)
+    y = ops.conv2d_forward(x.to(dev), wt.to(dev), bias.to(dev), relu)
+    xd, wd = x.double(), wt.double().requires_grad_(True)
+    yo = torch.nn.functional.conv2d(xd, wd, bias.double())
+    want = torch.relu(yo) if relu else yo
+    assert rel_err(y.cpu().double(), want.detach()) < 1e-5
+    mask = torch.randn(y.shape, generator=g)
+    ym = ops.conv2d_forward(x.to(dev), wt.to(dev), None, False, mask=mask.to(dev))
+    assert rel_err(ym.cpu().double(), (torch.nn.functional.conv2d(xd, wd) * (mask > 0)).detach()) < 1e-5
+    dy = torch.randn(yo.shape, generator=g)
+    (yo * dy.double()).sum().backward()
+    dw = ops.conv2d_weight_grad(dy.to(dev), x.to(dev), k)
+    assert rel_err(dw.cpu().double(), wd.grad) < 1e-5
+    assert rel_err(ops.plane_sums(dy.to(dev)).cpu().double(), dy.double().sum((2, 3))) < 1e-5
+
+
+@pytest.mark.parametrize("n,reflect,k", [(4, False, 5), (8, False, 5), (8, True, 3), (6, True, 1)])
+def test_filter_orbit_adjoints_vs_oracle_autograd(n, reflect, k, cuda_device):
+    ops = _mods()[0]
+    dev = cuda_device
+    G = n * (2 if reflect else 1)
+    g = torch.Generator().manual_seed(n + k)
+    w = torch.randn(6, 3, k, k, generator=g).double().requires_grad_(True)
+    orbit = O.lift_filter_orbit(w, n, reflect)
+    d = torch.randn(orbit.shape, generator=g)
+    (orbit * d.double()).sum().backward()
+    assert rel_err(ops.lift_filter_orbit_adjoint(d.to(dev), 6, n, reflect).cpu().double(), w.grad) < 1e-5
+    wr = torch.randn(4, 5, G, k, k, generator=g).double().requires_grad_(True)
+    orbit = O.regular_filter_orbit(wr, n, reflect)
+    d = torch.randn(orbit.shape, generator=g)
+    (orbit * d.double()).sum().backward()
+    assert rel_err(ops.regular_filter_orbit_adjoint(d.to(dev), 4, n, reflect).cpu().double(), wr.grad) < 1e-5
+
+
+@pytest.mark.parametrize("group_type,n,layers,bias", [("rotation", 8, 3, True), ("roto-reflection", 4, 2, True),
+                                                       ("rotation", 4, 1, False)])
+def test_custom_network_training_gradients_vs_oracle_autograd(group_type, n, layers, bias, cuda_device):
+    """CustomEquivariantNetwork in train(): activations and the gradient of every parameter equal torch autograd
+    through the fp64 oracle network (filter orbits -> conv2d -> ReLU -> mean, custom_equivariant_networks.py:49-93)."""
+    Net = _mods()[3]
+    dev = cuda_device
+    reflect = group_type == "roto-reflection"
+    G = n * (2 if reflect else 1)
+    torch.manual_seed(500 + n + layers)
+    net = Net((3, 28, 28), 6, 5, group_type, n, layers, device="cpu").to(dev).train()
+    mods = [m for m in net.eqv_network if hasattr(m, "weights")]
+    with torch.no_grad():
+        for m in mods:
+            if bias:
+                m.bias.normal_(0, 0.3)
+    if not bias:
+        for m in mods:
+            m.bias = None
+    x = torch.randn(5, 3, 28, 28, generator=torch.Generator().manual_seed(501))
+    dact = torch.randn(5, G, generator=torch.Generator().manual_seed(502))
+    act = net(x.to(dev))
+    assert act.requires_grad
+    (act * dact.to(dev)).sum().backward()
+    ref_layers = [(m.weights.detach().cpu().double().requires_grad_(True),
+                   m.bias.detach().cpu().double().requires_grad_(True) if bias else None) for m in mods]
+    act_o = O.custom_equivariant_network(x.double(), ref_layers, n, reflect)
+    (act_o * dact.double()).sum().backward()
+    assert rel_err(act.detach().cpu().double(), act_o.detach()) < 1e-5
+    for m, (wo, bo) in zip(mods, ref_layers):
+        assert rel_err(m.weights.grad.cpu().double(), wo.grad) < 2e-5
+        if bias:
+            assert rel_err(m.bias.grad.cpu().double(), bo.grad) < 2e-5
+    # eval() keeps using the fused inference stack and agrees with the training path's activations
+    with torch.no_grad():
+        assert rel_err(net.eval()(x.to(dev)).cpu().double(), act_o.detach()) < RTOL
+
+
+def test_full_training_step_of_the_flagship_canonicalizer(cuda_device):
+    """The reference's Lightning step (examples/images/classification/model.py:71-127) on this package's own network:
+    canonicalize -> prediction network -> task loss + prior loss -> backward -> SGD.  Every parameter of the
+    canonicalization network receives a finite gradient and the prior loss goes down over a few steps."""
+    _, GEIC, _, Net = _mods()
+    dev = cuda_device
+    torch.manual_seed(510)
+    net = Net((3, 32, 32), 4, 5, "rotation", 8, 3, device="cpu").to(dev)
+    can = GEIC(net, SimpleNamespace(beta=1.0, input_crop_ratio=0.9, resize_shape=32), (3, 40, 40)).train()
+    pred = torch.nn.Sequential(torch.nn.Conv2d(3, 4, 3), torch.nn.AdaptiveAvgPool2d(1), torch.nn.Flatten(), torch.nn.Linear(4, 10)).to(dev)
+    opt = torch.optim.SGD(list(can.parameters()) + list(pred.parameters()), lr=0.05)
+    x = _smooth(16, 3, 40, 40, 511).to(dev)
+    y = torch.randint(0, 10, (16,), generator=torch.Generator().manual_seed(512)).to(dev)
+    priors = []
+    for step in range(6):
+        opt.zero_grad()
+        logits = pred(can(x))
+        prior = can.get_prior_regularization_loss()
+        loss = torch.nn.functional.cross_entropy(logits, y) + 100.0 * prior
+        loss.backward()
+        for name, p in can.named_parameters():
+            assert p.grad is not None and torch.isfinite(p.grad).all(), name
+        assert any(float(p.grad.abs().sum()) > 0 for p in net.parameters())
+        opt.step()
+        priors.append(float(prior.detach()))
+    assert priors[-1] < priors[0]
