@@ -309,6 +309,39 @@ __global__ void __launch_bounds__(256) cosine_act_kernel(const float *__restrict
     }
 }
 
+// N3: backward of cosine_act_kernel.  With v^ = v / nv, r^ = ref / nr, c = v^ . r^ (nv, nr clamped at eps as above):
+//   d c / d v = r^ / nv - c v / nv^2   (second term absent when |v| sits below the clamp),   d c / d ref symmetric.
+// One warp per row; d ref accumulates over rows with atomics (zeroed by the caller).
+__global__ void __launch_bounds__(256) cosine_act_backward_kernel(const float *__restrict__ vec, const float *__restrict__ ref,
+                                                                  const float *__restrict__ dact, float *__restrict__ dvec,
+                                                                  float *__restrict__ dref, int B, int G, int V) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= B * G) return;
+    const float *v = vec + (size_t)row * V;
+    float vv = 0.f, rr = 0.f;
+    for (int i = lane; i < V; i += 32) {
+        vv = fmaf(v[i], v[i], vv);
+        rr = fmaf(ref[i], ref[i], rr);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        vv += __shfl_xor_sync(0xffffffffu, vv, o);
+        rr += __shfl_xor_sync(0xffffffffu, rr, o);
+    }
+    const float sv = sqrtf(vv), sr = sqrtf(rr);
+    const float nv = fmaxf(sv, 1e-8f), nr = fmaxf(sr, 1e-8f);
+    float dot = 0.f;
+    for (int i = lane; i < V; i += 32) dot = fmaf(ref[i] / nr, v[i] / nv, dot);
+    for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+    const int g = row / B, b = row - g * B;
+    const float go = dact[(size_t)b * G + g];
+    const float kv = sv > 1e-8f ? dot / (nv * nv) : 0.f, kr = sr > 1e-8f ? dot / (nr * nr) : 0.f;
+    for (int i = lane; i < V; i += 32) {
+        if (dvec) dvec[(size_t)row * V + i] = go * (ref[i] / (nr * nv) - kv * v[i]);
+        if (dref) atomicAdd(dref + i, go * (v[i] / (nv * nr) - kr * ref[i]));
+    }
+}
+
 // -------------------------------------------------------------------------------------------------
 // a14..a17: frames
 // -------------------------------------------------------------------------------------------------
@@ -537,6 +570,18 @@ extern "C" int eqb_cosine_group_activations(const float *vec, const float *ref, 
     const int rows = B * num_group;
     cosine_act_kernel<<<(rows + 7) / 8, 256, 0, (cudaStream_t)stream>>>(vec, ref, act, B, num_group, V);
     return finish_launch("eqb_cosine_group_activations");
+}
+
+extern "C" int eqb_cosine_group_activations_backward(const float *vec, const float *ref, const float *dact, float *dvec,
+                                                     float *dref, int B, int num_group, int V, void *stream) {
+    EQB_REQUIRE(B >= 0 && num_group > 0 && V > 0, "eqb_cosine_group_activations_backward: bad shape");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dref) EQB_CUDA(cudaMemsetAsync(dref, 0, (size_t)V * sizeof(float), st));
+    if (B == 0) return 0;
+    EQB_REQUIRE(vec && ref && dact && (dvec || dref), "eqb_cosine_group_activations_backward: null pointer");
+    const int rows = B * num_group;
+    cosine_act_backward_kernel<<<(rows + 7) / 8, 256, 0, st>>>(vec, ref, dact, dvec, dref, B, num_group, V);
+    return finish_launch("eqb_cosine_group_activations_backward");
 }
 
 extern "C" int eqb_gram_schmidt3(const float *v, float *R, int B, int modified, void *stream) {

@@ -51,6 +51,7 @@ _SIGNATURES = {
     "eqb_orbit_expand": (C.c_int, [_fp, _fp] + [_i] * 8 + [_fp]),
     "eqb_orbit_rotate_nearest": (C.c_int, [_fp, _fp] + [_i] * 6 + [_fp]),
     "eqb_cosine_group_activations": (C.c_int, [_fp, _fp, _fp, _i, _i, _i, _fp]),
+    "eqb_cosine_group_activations_backward": (C.c_int, [_fp] * 5 + [_i] * 3 + [_fp]),
     "eqb_gram_schmidt3": (C.c_int, [_fp, _fp, _i, _i, _fp]),
     "eqb_so3_apply": (C.c_int, [_fp, _fp, _fp, _i, _i, _fp]),
     "eqb_e3_apply": (C.c_int, [_fp] * 6 + [_i, _fp]),

@@ -490,7 +490,7 @@ def orbit_rotate_nearest(x: torch.Tensor, num_rotations: int, reflect: bool) -> 
     return out
 
 
-def cosine_group_activations(vec: torch.Tensor, ref: torch.Tensor, num_group: int) -> torch.Tensor:
+def _cosine_group_activations_raw(vec: torch.Tensor, ref: torch.Tensor, num_group: int) -> torch.Tensor:
     dev = _need_cuda(vec, ref)
     vec = _f32(vec)
     ref = _f32(ref).reshape(-1)
@@ -501,6 +501,37 @@ def cosine_group_activations(vec: torch.Tensor, ref: torch.Tensor, num_group: in
     act = torch.empty((b, num_group), dtype=torch.float32, device=dev)
     _call("eqb_cosine_group_activations", 1, dev, _ptr(vec), _ptr(ref), _ptr(act), b, num_group, v, _stream(dev))
     return act
+
+
+class _CosineActivations(torch.autograd.Function):
+    """cosine_group_activations as an autograd node (the optimisation-based variant trains ANY torch network and the
+    reference vector through it: discrete_group.py:475-481)."""
+
+    @staticmethod
+    def forward(ctx, vec, ref, num_group):
+        ctx.save_for_backward(vec, ref)
+        ctx.num_group = num_group
+        return _cosine_group_activations_raw(vec, ref, num_group)
+
+    @staticmethod
+    def backward(ctx, dact):
+        vec, ref = ctx.saved_tensors
+        dev = vec.device
+        v32, r32 = _f32(vec), _f32(ref).reshape(-1)
+        rows, v = v32.shape
+        b = rows // ctx.num_group
+        dvec = torch.empty_like(v32) if ctx.needs_input_grad[0] else None
+        dref = torch.empty(v, dtype=torch.float32, device=dev) if ctx.needs_input_grad[1] else None
+        _call("eqb_cosine_group_activations_backward", 1 if b else 0, dev, _ptr(v32), _ptr(r32), _ptr(_f32(dact)),
+              _ptr(dvec) if dvec is not None else None, _ptr(dref) if dref is not None else None, b, ctx.num_group, v,
+              _stream(dev))
+        return dvec, (dref.reshape(ref.shape) if dref is not None else None), None
+
+
+def cosine_group_activations(vec: torch.Tensor, ref: torch.Tensor, num_group: int) -> torch.Tensor:
+    if torch.is_grad_enabled() and (vec.requires_grad or ref.requires_grad):
+        return _CosineActivations.apply(vec, ref, num_group)
+    return _cosine_group_activations_raw(vec, ref, num_group)
 
 
 # ---- a14 .. a17 -----------------------------------------------------------------------------------

@@ -164,6 +164,10 @@ EQB_API int eqb_orbit_rotate_nearest(const float *x, float *out, int B, int C, i
  * act (B,|G|).  Replaces discrete_group.py:475-481. */
 EQB_API int eqb_cosine_group_activations(const float *vec, const float *ref, float *act, int B, int num_group,
                                  int V, void *stream);
+/* N3: its backward (torch autograd through F.cosine_similarity + transpose in the reference, discrete_group.py:475-481):
+ * dact (B,|G|) -> dvec (|G|*B, V) and / or dref (V); either output may be NULL; both are overwritten. */
+EQB_API int eqb_cosine_group_activations_backward(const float *vec, const float *ref, const float *dact, float *dvec,
+                                          float *dref, int B, int num_group, int V, void *stream);
 
 /* ---- a14..a17  frames ----------------------------------------------------------------------
  * Gram-Schmidt on the three rows of v (B,3,3) -> R (B,3,3).  modified = 0: common/utils.py:22-51;

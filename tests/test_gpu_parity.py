@@ -1282,3 +1282,99 @@ def test_full_training_step_of_the_flagship_canonicalizer(cuda_device):
         opt.step()
         priors.append(float(prior.detach()))
     assert priors[-1] < priors[0]
+
+
+# ---- N3: the optimisation-based variant trains any torch network through the cosine activations ----------------------
+def test_cosine_activations_backward_vs_torch(cuda_device):
+    ops = _mods()[0]
+    dev = cuda_device
+    gen = torch.Generator().manual_seed(600)
+    b, G, v = 7, 8, 37
+    vec = torch.randn(G * b, v, generator=gen)
+    ref = torch.randn(1, v, generator=gen)
+    dact = torch.randn(b, G, generator=gen)
+    vo, ro = vec.double().requires_grad_(True), ref.double().requires_grad_(True)
+    (O.cosine_group_activations(vo, ro, G) * dact.double()).sum().backward()
+    vd, rd = vec.to(dev).requires_grad_(True), ref.to(dev).requires_grad_(True)
+    act = ops.cosine_group_activations(vd, rd, G)
+    (act * dact.to(dev)).sum().backward()
+    assert rel_err(vd.grad.cpu().double(), vo.grad) < 1e-5
+    assert rel_err(rd.grad.cpu().double(), ro.grad) < 1e-5
+    # only the network output requires grad (learn_ref_vec = False)
+    vd2 = vec.to(dev).requires_grad_(True)
+    (ops.cosine_group_activations(vd2, ref.to(dev), G) * dact.to(dev)).sum().backward()
+    assert rel_err(vd2.grad.cpu().double(), vo.grad) < 1e-5
+    assert not ops.cosine_group_activations(vec.to(dev), ref.to(dev), G).requires_grad
+
+
+@pytest.mark.parametrize("group_type", ["rotation", "roto-reflection"])
+def test_optimized_variant_training_gradients_vs_oracle_chain(group_type, cuda_device):
+    """OptimizedGroupEquivariantImageCanonicalization in train() around a small torch CNN (the reference's use: any
+    non-equivariant network): task loss through the canonicalize warp + straight-through element, prior loss and the
+    optimisation-specific loss.  Gradients of the CNN and of the reference vector equal torch autograd through the
+    oracle chain (orbit expand -> CNN -> cosine similarity -> ..., discrete_group.py:387-512), the rotation probed at
+    +-1e-3 degrees for the symmetric derivative at quarter turns."""
+    _, _, OGEIC, _ = _mods()
+    import copy
+    dev = cuda_device
+    n, reflect = 4, group_type == "roto-reflection"
+    G = n * (2 if reflect else 1)
+
+    class CNN(torch.nn.Module):
+        out_vector_size = 12
+
+        def __init__(self):
+            super().__init__()
+            self.conv = torch.nn.Conv2d(3, 5, 5, stride=2)
+            self.fc = torch.nn.Linear(5, 12)
+
+        def forward(self, x):
+            return self.fc(torch.tanh(self.conv(x)).mean(dim=(2, 3)))
+
+    torch.manual_seed(610 + reflect)
+    net = CNN()
+    hp = SimpleNamespace(beta=1.0, input_crop_ratio=1.0, resize_shape=32, group_type=group_type, num_rotations=n,
+                         artifact_err_wt=0, learn_ref_vec=True)
+    can = OGEIC(copy.deepcopy(net).to(dev), hp, (3, 32, 32)).to(dev).train()
+    ref_vec = can.reference_vector.detach().cpu().double().clone()
+    x = _smooth(6, 3, 32, 32, 611)
+    wtask = torch.randn(6, 3, 32, 32, generator=torch.Generator().manual_seed(612))
+    xc = can(x.to(dev))
+    loss = (xc * wtask.to(dev)).sum() + 10.0 * can.get_prior_regularization_loss() + 3.0 * can.get_optimization_specific_loss()
+    loss.backward()
+    idx = can.canonicalization_info_dict["group_element"].index.cpu().long()
+    ours = {k: p.grad.detach().cpu().double() for k, p in can.canonicalization_network.named_parameters()}
+    ours["reference_vector"] = can.reference_vector.grad.detach().cpu().double()
+
+    ref_net = copy.deepcopy(net).double()
+    rv = ref_vec.clone().requires_grad_(True)
+    angles = torch.linspace(0.0, 360.0, n + 1)[:n].double()
+    comp = torch.cat([angles, angles]) if reflect else angles
+    xd = x.double()
+
+    def reference_step(delta):
+        for p in ref_net.parameters():
+            p.grad = None
+        rv.grad = None
+        vec = ref_net(O.group_augment(xd, n, reflect, 32))
+        act = O.cosine_group_activations(vec, rv, G)
+        assert torch.equal(act.argmax(-1), idx)
+        onehot = torch.nn.functional.one_hot(act.argmax(-1), G).double()
+        soft = torch.softmax(hp.beta * act, -1)
+        st = onehot + soft - soft.detach()
+        rot = (st * comp).sum(-1) + delta
+        refl = (st * torch.cat([torch.zeros(n), torch.ones(n)]).double()).sum(-1) if reflect else None
+        lo = ((O.canonicalize_image(xd, rot, refl) * wtask.double()).sum()
+              + 10.0 * torch.nn.functional.cross_entropy(act, torch.zeros(6, dtype=torch.long))
+              + 3.0 * O.optimization_specific_loss(vec, G, 12))
+        lo.backward()
+        g = {k: p.grad.clone() for k, p in ref_net.named_parameters()}
+        g["reference_vector"] = rv.grad.clone()
+        return float(lo.detach()), g
+
+    lo, _ = reference_step(0.0)
+    assert abs(float(loss.detach()) - lo) < 1e-3 * abs(lo)
+    _, gp = reference_step(1e-3)
+    _, gm = reference_step(-1e-3)
+    for k in gp:
+        assert rel_err(ours[k], 0.5 * (gp[k] + gm[k])) < 2e-3, k
