@@ -98,6 +98,23 @@ class _PriorCrossEntropy(torch.autograd.Function):
         return g * (grad / act.shape[0]), None
 
 
+class _PriorMSE(torch.autograd.Function):
+    """MSE(R, I) whose VALUE comes from the statistic kernel; backward 2 (R - I) / (B d d) on the (B,d,d) matrices, what
+    torch autograd gives for MSELoss in the reference (basecanonicalization.py:390-408).  Rank-local mean, as there."""
+
+    @staticmethod
+    def forward(ctx, rep, value):
+        ctx.save_for_backward(rep)
+        return value.detach().clone()
+
+    @staticmethod
+    def backward(ctx, grad):
+        (rep,) = ctx.saved_tensors
+        r = rep.detach().float()
+        eye = torch.eye(r.shape[-1], device=r.device, dtype=r.dtype)
+        return (r - eye) * (2.0 * grad / r.numel()), None
+
+
 class DiscreteGroupCanonicalization(BaseCanonicalization):
     """Discrete groups: activations (B,|G|) -> one-hot group element, CE prior, identity metric."""
 
@@ -194,7 +211,11 @@ class ContinuousGroupCanonicalization(BaseCanonicalization):
     def get_prior_regularization_loss(self) -> torch.Tensor:
         """MSE(R, I) over B*d*d entries (basecanonicalization.py:390-408)."""
         s = self._continuous_stats()
-        return s[0] / s[1] if self._multi_rank() else s[3]
+        value = s[0] / s[1] if self._multi_rank() else s[3]
+        rep = self.canonicalization_info_dict["group_element_matrix_representation"]
+        if torch.is_grad_enabled() and rep.requires_grad:
+            return _PriorMSE.apply(rep, value)
+        return value
 
     def get_identity_metric(self) -> torch.Tensor:
         """1 - MSE(R, I) (basecanonicalization.py:410-430)."""

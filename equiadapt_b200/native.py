@@ -53,6 +53,10 @@ _SIGNATURES = {
     "eqb_cosine_group_activations": (C.c_int, [_fp, _fp, _fp, _i, _i, _i, _fp]),
     "eqb_cosine_group_activations_backward": (C.c_int, [_fp] * 5 + [_i] * 3 + [_fp]),
     "eqb_gram_schmidt3": (C.c_int, [_fp, _fp, _i, _i, _fp]),
+    "eqb_gram_schmidt3_backward": (C.c_int, [_fp, _fp, _fp, _i, _i, _fp]),
+    "eqb_so3_apply_backward": (C.c_int, [_fp] * 5 + [_i, _i, _fp]),
+    "eqb_e3_apply_backward": (C.c_int, [_fp] * 10 + [_i, _fp]),
+    "eqb_e3_invert_backward": (C.c_int, [_fp] * 6 + [_i, _fp]),
     "eqb_so3_apply": (C.c_int, [_fp, _fp, _fp, _i, _i, _fp]),
     "eqb_e3_apply": (C.c_int, [_fp] * 6 + [_i, _fp]),
     "eqb_e3_invert": (C.c_int, [_fp] * 4 + [_i, _fp]),

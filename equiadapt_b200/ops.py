@@ -535,7 +535,7 @@ def cosine_group_activations(vec: torch.Tensor, ref: torch.Tensor, num_group: in
 
 
 # ---- a14 .. a17 -----------------------------------------------------------------------------------
-def gram_schmidt3(v: torch.Tensor, modified: bool = False) -> torch.Tensor:
+def _gram_schmidt3_raw(v: torch.Tensor, modified: bool = False) -> torch.Tensor:
     dev = _need_cuda(v)
     v = _f32(v)
     if v.dim() != 3 or v.shape[1:] != (3, 3):
@@ -545,7 +545,7 @@ def gram_schmidt3(v: torch.Tensor, modified: bool = False) -> torch.Tensor:
     return out
 
 
-def so3_apply(x: torch.Tensor, rot: torch.Tensor) -> torch.Tensor:
+def _so3_apply_raw(x: torch.Tensor, rot: torch.Tensor) -> torch.Tensor:
     dev = _need_cuda(x, rot)
     x = _f32(x)
     rot = _f32(rot)
@@ -557,7 +557,7 @@ def so3_apply(x: torch.Tensor, rot: torch.Tensor) -> torch.Tensor:
     return y
 
 
-def e3_apply(loc: torch.Tensor, vel: torch.Tensor, rot: torch.Tensor, t: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+def _e3_apply_raw(loc: torch.Tensor, vel: torch.Tensor, rot: torch.Tensor, t: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
     dev = _need_cuda(loc, vel, rot, t)
     loc, vel, rot, t = _f32(loc), _f32(vel), _f32(rot), _f32(t)
     m = loc.shape[0]
@@ -568,7 +568,7 @@ def e3_apply(loc: torch.Tensor, vel: torch.Tensor, rot: torch.Tensor, t: torch.T
     return lc, vc
 
 
-def e3_invert(x: torch.Tensor, rot: torch.Tensor, t: torch.Tensor) -> torch.Tensor:
+def _e3_invert_raw(x: torch.Tensor, rot: torch.Tensor, t: torch.Tensor) -> torch.Tensor:
     dev = _need_cuda(x, rot, t)
     x, rot, t = _f32(x), _f32(rot), _f32(t)
     m = x.shape[0]
@@ -577,6 +577,108 @@ def e3_invert(x: torch.Tensor, rot: torch.Tensor, t: torch.Tensor) -> torch.Tens
     y = torch.empty_like(x)
     _call("eqb_e3_invert", 1, dev, _ptr(x), _ptr(rot), _ptr(t), _ptr(y), m, _stream(dev))
     return y
+
+
+def _optr(t):
+    return _ptr(t) if t is not None else None
+
+
+def _wants_grad(*tensors) -> bool:
+    return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors)
+
+
+class _GramSchmidt3(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, v, modified):
+        ctx.save_for_backward(v)
+        ctx.modified = modified
+        return _gram_schmidt3_raw(v, modified)
+
+    @staticmethod
+    def backward(ctx, dR):
+        (v,) = ctx.saved_tensors
+        v32, g = _f32(v), _f32(dR)
+        dv = torch.empty_like(v32)
+        _call("eqb_gram_schmidt3_backward", 1 if v32.shape[0] else 0, v32.device, _ptr(v32), _ptr(g), _ptr(dv), v32.shape[0],
+              int(ctx.modified), _stream(v32.device))
+        return dv, None
+
+
+def gram_schmidt3(v: torch.Tensor, modified: bool = False) -> torch.Tensor:
+    return _GramSchmidt3.apply(v, modified) if _wants_grad(v) else _gram_schmidt3_raw(v, modified)
+
+
+class _So3Apply(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, rot):
+        ctx.save_for_backward(x, rot)
+        return _so3_apply_raw(x, rot)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, rot = ctx.saved_tensors
+        x32, r32, g = _f32(x), _f32(rot), _f32(dy)
+        b, _, n = x32.shape
+        dx = torch.empty_like(x32) if ctx.needs_input_grad[0] else None
+        dr = torch.empty_like(r32) if ctx.needs_input_grad[1] else None
+        _call("eqb_so3_apply_backward", 1 if b * n else 0, x32.device, _ptr(x32), _ptr(r32), _ptr(g), _optr(dx), _optr(dr), b, n,
+              _stream(x32.device))
+        if dr is not None and b * n == 0:
+            dr.zero_()
+        return dx, dr
+
+
+def so3_apply(x: torch.Tensor, rot: torch.Tensor) -> torch.Tensor:
+    return _So3Apply.apply(x, rot) if _wants_grad(x, rot) else _so3_apply_raw(x, rot)
+
+
+class _E3Apply(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, loc, vel, rot, t):
+        ctx.save_for_backward(loc, vel, rot, t)
+        return _e3_apply_raw(loc, vel, rot, t)
+
+    @staticmethod
+    def backward(ctx, dlc, dvc):
+        loc, vel, rot, t = (_f32(a) for a in ctx.saved_tensors)
+        m, dev = loc.shape[0], loc.device
+        need = ctx.needs_input_grad
+        dloc = torch.empty_like(loc) if need[0] else None
+        dvel = torch.empty_like(vel) if need[1] else None
+        dr = torch.empty_like(rot) if need[2] else None
+        dt = torch.empty_like(t) if need[3] else None
+        _call("eqb_e3_apply_backward", 1 if m else 0, dev, _ptr(loc), _ptr(vel), _ptr(rot), _ptr(t),
+              _ptr(_f32(dlc)) if dlc is not None else None, _ptr(_f32(dvc)) if dvc is not None else None,
+              _optr(dloc), _optr(dvel), _optr(dr), _optr(dt), m, _stream(dev))
+        return dloc, dvel, dr, dt
+
+
+def e3_apply(loc: torch.Tensor, vel: torch.Tensor, rot: torch.Tensor, t: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    return _E3Apply.apply(loc, vel, rot, t) if _wants_grad(loc, vel, rot, t) else _e3_apply_raw(loc, vel, rot, t)
+
+
+class _E3Invert(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, rot, t):
+        ctx.save_for_backward(x, rot)
+        return _e3_invert_raw(x, rot, t)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, rot = (_f32(a) for a in ctx.saved_tensors)
+        m, dev = x.shape[0], x.device
+        need = ctx.needs_input_grad
+        g = _f32(dy)
+        dx = torch.empty_like(x) if need[0] else None
+        dr = torch.empty_like(rot) if need[1] else None
+        dt = torch.empty_like(x) if need[2] else None
+        _call("eqb_e3_invert_backward", 1 if m else 0, dev, _ptr(x), _ptr(rot), _ptr(g), _optr(dx), _optr(dr), _optr(dt), m,
+              _stream(dev))
+        return dx, dr, dt
+
+
+def e3_invert(x: torch.Tensor, rot: torch.Tensor, t: torch.Tensor) -> torch.Tensor:
+    return _E3Invert.apply(x, rot, t) if _wants_grad(x, rot, t) else _e3_invert_raw(x, rot, t)
 
 
 def prior_stats_continuous(rep: torch.Tensor) -> torch.Tensor:

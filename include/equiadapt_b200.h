@@ -253,6 +253,19 @@ EQB_API int eqb_lift_filter_orbit_adjoint(const float *dorbit, float *dw, int co
 EQB_API int eqb_regular_filter_orbit_adjoint(const float *dorbit, float *dw, int cout, int cin, int k, int num_rotations,
                                      int reflect, void *stream);
 
+/* ---- N3  backward of the frame path (a14..a17) ----------------------------------------------------
+ * What torch autograd derives in the reference through gram_schmidt (common/utils.py:22-51) / modified Gram-Schmidt
+ * (nbody euclidean_group.py:139-157), the point-cloud bmm (pointcloud continuous_group.py:77-79) and the n-body row
+ * products (euclidean_group.py:114-122, :133-136), so that a torch frame-predicting network trains through the
+ * canonicalizers.  Output pointers may be NULL where a gradient is not wanted (dv excepted); outputs are overwritten. */
+EQB_API int eqb_gram_schmidt3_backward(const float *v, const float *dR, float *dv, int B, int modified, void *stream);
+EQB_API int eqb_so3_apply_backward(const float *x, const float *R, const float *dy, float *dx, float *dR, int B, int N,
+                           void *stream);
+EQB_API int eqb_e3_apply_backward(const float *loc, const float *vel, const float *R, const float *t, const float *dloc_c,
+                          const float *dvel_c, float *dloc, float *dvel, float *dR, float *dt, int M, void *stream);
+EQB_API int eqb_e3_invert_backward(const float *x, const float *R, const float *dy, float *dx, float *dR, float *dt, int M,
+                           void *stream);
+
 #ifdef __cplusplus
 }
 #endif

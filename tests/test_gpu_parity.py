@@ -1378,3 +1378,86 @@ def test_optimized_variant_training_gradients_vs_oracle_chain(group_type, cuda_d
     _, gm = reference_step(-1e-3)
     for k in gp:
         assert rel_err(ours[k], 0.5 * (gp[k] + gm[k])) < 2e-3, k
+
+
+# ---- N3: the frame path (point clouds, n-body) is differentiable -------------------------------------------------------
+@pytest.mark.parametrize("modified", [False, True])
+def test_gram_schmidt_backward_vs_oracle_autograd(modified, cuda_device):
+    ops = _mods()[0]
+    gen = torch.Generator().manual_seed(700 + modified)
+    v = torch.randn(33, 3, 3, generator=gen)
+    dR = torch.randn(33, 3, 3, generator=gen)
+    vo = v.double().requires_grad_(True)
+    ((O.modified_gram_schmidt(vo) if modified else O.gram_schmidt(vo)) * dR.double()).sum().backward()
+    vd = v.to(cuda_device).requires_grad_(True)
+    R = ops.gram_schmidt3(vd, modified=modified)
+    (R * dR.to(cuda_device)).sum().backward()
+    assert rel_err(vd.grad.cpu().double(), vo.grad) < 2e-5
+    assert not ops.gram_schmidt3(v.to(cuda_device), modified=modified).requires_grad
+
+
+def test_frame_apply_backward_vs_oracle_autograd(cuda_device):
+    ops = _mods()[0]
+    dev = cuda_device
+    gen = torch.Generator().manual_seed(710)
+    # SO(3) on point clouds
+    x, R, dy = torch.randn(5, 3, 1500, generator=gen), torch.randn(5, 3, 3, generator=gen), torch.randn(5, 3, 1500, generator=gen)
+    xo, Ro = x.double().requires_grad_(True), R.double().requires_grad_(True)
+    (O.so3_canonicalize(xo, Ro) * dy.double()).sum().backward()
+    xd, Rd = x.to(dev).requires_grad_(True), R.to(dev).requires_grad_(True)
+    (ops.so3_apply(xd, Rd) * dy.to(dev)).sum().backward()
+    assert rel_err(xd.grad.cpu().double(), xo.grad) < 1e-5 and rel_err(Rd.grad.cpu().double(), Ro.grad) < 1e-5
+    Rd2 = R.to(dev).requires_grad_(True)                      # only the frame requires grad (the training case)
+    (ops.so3_apply(x.to(dev), Rd2) * dy.to(dev)).sum().backward()
+    assert rel_err(Rd2.grad.cpu().double(), Ro.grad) < 1e-5
+    # E(3) on particle rows
+    m = 45
+    loc, vel, t = (torch.randn(m, 3, generator=gen) for _ in range(3))
+    Rm = torch.randn(m, 3, 3, generator=gen)
+    gl, gv, gi = (torch.randn(m, 3, generator=gen) for _ in range(3))
+    ref = [a.double().requires_grad_(True) for a in (loc, vel, Rm, t)]
+    cl, cv = O.e3_canonicalize(*ref)
+    ((cl * gl.double()).sum() + (cv * gv.double()).sum()).backward()
+    ours = [a.to(dev).requires_grad_(True) for a in (loc, vel, Rm, t)]
+    cl2, cv2 = ops.e3_apply(*ours)
+    ((cl2 * gl.to(dev)).sum() + (cv2 * gv.to(dev)).sum()).backward()
+    for a, b in zip(ours, ref):
+        assert rel_err(a.grad.cpu().double(), b.grad) < 1e-5
+    ref = [a.double().requires_grad_(True) for a in (loc, Rm, t)]
+    (O.e3_invert(*ref) * gi.double()).sum().backward()
+    ours = [a.to(dev).requires_grad_(True) for a in (loc, Rm, t)]
+    (ops.e3_invert(*ours) * gi.to(dev)).sum().backward()
+    for a, b in zip(ours, ref):
+        assert rel_err(a.grad.cpu().double(), b.grad) < 1e-5
+
+
+def test_pointcloud_canonicalizer_trains_a_torch_frame_network(cuda_device):
+    """EquivariantPointcloudCanonicalization around a torch network: task loss through R x and the MSE prior reach the
+    network's parameters; gradients equal torch autograd through the oracle chain (gram_schmidt -> bmm, MSE(R, I))."""
+    from equiadapt_b200.pointcloud.canonicalization.continuous_group import EquivariantPointcloudCanonicalization
+    import copy
+    dev = cuda_device
+
+    class FrameNet(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.mix = torch.nn.Parameter(torch.randn(3, 6) * 0.5)
+
+        def forward(self, x):                    # (B,3,N) -> (B,3,3): three equivariant vectors (rows)
+            feats = torch.stack([x.mean(-1), (x * x.norm(dim=1, keepdim=True)).mean(-1), x[..., 0], x[..., 1], x[..., 2], x[..., 3]], 1)
+            return torch.einsum("vk,bkc->bvc", self.mix, feats)
+
+    torch.manual_seed(720)
+    net = FrameNet()
+    can = EquivariantPointcloudCanonicalization(copy.deepcopy(net).to(dev), SimpleNamespace()).train()
+    x = torch.randn(6, 3, 200, generator=torch.Generator().manual_seed(721))
+    wt = torch.randn(6, 3, 200, generator=torch.Generator().manual_seed(722))
+    y = can(x.to(dev))
+    loss = (y * wt.to(dev)).sum() + 5.0 * can.get_prior_regularization_loss()
+    loss.backward()
+    ref = copy.deepcopy(net).double()
+    R = O.gram_schmidt(ref(x.double()))
+    lo = (O.so3_canonicalize(x.double(), R) * wt.double()).sum() + 5.0 * torch.nn.functional.mse_loss(R, torch.eye(3).double().expand(6, 3, 3))
+    lo.backward()
+    assert abs(float(loss.detach()) - float(lo.detach())) < 1e-4 * abs(float(lo.detach()))
+    assert rel_err(can.canonicalization_network.mix.grad.cpu().double(), ref.mix.grad) < 2e-5
