@@ -91,7 +91,26 @@ class ContinuousGroupImageCanonicalization(ContinuousGroupCanonicalization):
         p = self.pad_amount
         # centre of the PADDED image by integer division, x <- shape[-2], y <- shape[-1] (:189), in un-padded coordinates
         cx, cy = (h + 2 * p) // 2 - p, (w + 2 * p) // 2 - p
+        if torch.is_grad_enabled() and (rotation_matrices.requires_grad or (refl is not None and refl.requires_grad)):
+            # training: the sampling map the kernel uses, rebuilt with torch algebra exactly as the reference builds its
+            # warp_affine matrix (:186-197), so autograd carries the kernel's d loss / d theta back to the network
+            theta = self._sampling_map(rotation_matrices, h, w, p)
+            return ops.warp_affine_canonicalize_autograd(x, rotation_matrices, refl, p, float(cx), float(cy), theta)
         return ops.warp_affine(x, rotation_matrices, refl, True, p, float(cx), float(cy))
+
+    @staticmethod
+    def _sampling_map(rotation_matrices: torch.Tensor, h: int, w: int, p: int) -> torch.Tensor:
+        """(B,2,3) destination -> source map in un-padded pixel coordinates: the inverse of the reference's 2x3 matrix
+        [R | ((1-a) cx - b cy, b cx + (1-a) cy)] (continuous_group.py:186-197, padded coordinates), shifted by the pad."""
+        alpha, beta = rotation_matrices[:, 0, 0], rotation_matrices[:, 0, 1]
+        cxp, cyp = (h + 2 * p) // 2, (w + 2 * p) // 2
+        affine_part = torch.stack([(1 - alpha) * cxp - beta * cyp, beta * cxp + (1 - alpha) * cyp], dim=1)
+        m = torch.cat([rotation_matrices, affine_part.unsqueeze(-1)], dim=-1)
+        bottom = torch.tensor([0.0, 0.0, 1.0], device=m.device, dtype=m.dtype).expand(m.shape[0], 1, 3)
+        inv = torch.linalg.inv(torch.cat([m, bottom], dim=1))
+        a, s = inv[:, :2, :2], inv[:, :2, 2]
+        pvec = torch.full((2,), float(p), device=m.device, dtype=m.dtype)
+        return torch.cat([a, (a @ pvec + s - pvec).unsqueeze(-1)], dim=-1)
 
     def invert_canonicalization(self, x_canonicalized_out: torch.Tensor, **kwargs: Any) -> torch.Tensor:
         raise NotImplementedError(

@@ -689,3 +689,105 @@ extern "C" int eqb_warp_element_grad(const float *in, const float *grad_out, con
     warp_element_grad_kernel<<<dim3(bx, B), 256, 0, st>>>(e);
     return finish_launch("eqb_warp_element_grad");
 }
+
+// ---- N3: gradient of the continuous warp (eqb_warp_affine, canonicalize direction) with respect to the affine map ----
+// The reference differentiates K.geometry.warp_affine with respect to its 2x3 matrix (continuous_group.py:183-208); the
+// matrix enters through its inverse, the translation column through alpha / beta only, and the reflection through the
+// flip blend.  All of that is tiny (B,3,3) algebra that stays in torch autograd; what needs a kernel is the reduction
+//     d loss / d theta[b] (2x3),  theta = destination -> source map in un-padded pixel coordinates:
+//         xs = t0 xd + t1 yd + t2,  ys = t3 xd + t4 yd + t5,
+//     d loss / d reflection[b]   (value under the mirrored blend minus value under the plain one),
+// with the forward's sampling rules (bilinear, replicate inside the padded extent, zero beyond, symmetric derivative on
+// lattice lines).
+namespace eqb {
+
+struct AffineGradArgs {
+    const float *in, *grad_out, *theta, *refl;
+    float *gtheta, *grefl;
+    int C, H, W, pad;
+};
+
+__global__ void __launch_bounds__(256) warp_affine_grad_kernel(const __grid_constant__ AffineGradArgs e) {
+    const int sample = blockIdx.y;
+    ResampleArgs a{};                 // only the fields bilinear_cell reads
+    a.Hs = e.H; a.Ws = e.W; a.pad = e.pad;
+    const float *th = e.theta + (size_t)sample * 6;
+    const double t0 = th[0], t1 = th[1], t2 = th[2], t3 = th[3], t4 = th[4], t5 = th[5];
+    const bool refl = e.refl && e.refl[sample] > 0.5f;
+    const size_t plane = (size_t)e.H * e.W;
+    const float *img = e.in + (size_t)sample * e.C * plane;
+    const float *go = e.grad_out + (size_t)sample * e.C * plane;
+    double acc[7] = {};
+    const int npix = e.H * e.W;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < npix; t += gridDim.x * blockDim.x) {
+        const int xd = t % e.W, yd = t / e.W;
+        BilinearCell q;
+        bilinear_cell(a, t0 * xd + t1 * yd + t2, t3 * xd + t4 * yd + t5, q);
+        float sgx = 0.f, sgy = 0.f, sref = 0.f;
+        for (int ch = 0; ch < e.C; ++ch) {
+            const float *ip = img + (size_t)ch * plane;
+            const float gval = go[(size_t)ch * plane + t];
+            float val[4], cur = 0.f, alt = 0.f;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int xk = refl ? e.W - 1 - q.xt[k] : q.xt[k];
+                val[k] = q.valid[k] * __ldg(ip + q.yt[k] * e.W + xk);
+                cur += val[k] * q.wx[k & 1] * q.wy[k >> 1];
+                if (e.grefl) alt += q.valid[k] * __ldg(ip + q.yt[k] * e.W + (e.W - 1 - xk)) * q.wx[k & 1] * q.wy[k >> 1];
+            }
+            float gx = q.wy[0] * (val[1] - val[0]) + q.wy[1] * (val[3] - val[2]);
+            float gy = q.wx[0] * (val[2] - val[0]) + q.wx[1] * (val[3] - val[1]);
+            if (q.on_x) {
+                const float m0 = q.valid_m[0] * __ldg(ip + q.ym[0] * e.W + (refl ? e.W - 1 - q.xm[0] : q.xm[0]));
+                const float m1 = q.valid_m[1] * __ldg(ip + q.ym[1] * e.W + (refl ? e.W - 1 - q.xm[1] : q.xm[1]));
+                gx = 0.5f * (gx + q.wy[0] * (val[0] - m0) + q.wy[1] * (val[2] - m1));
+            }
+            if (q.on_y) {
+                const float m0 = q.valid_m[2] * __ldg(ip + q.ym[2] * e.W + (refl ? e.W - 1 - q.xm[2] : q.xm[2]));
+                const float m1 = q.valid_m[3] * __ldg(ip + q.ym[3] * e.W + (refl ? e.W - 1 - q.xm[3] : q.xm[3]));
+                gy = 0.5f * (gy + q.wx[0] * (val[0] - m0) + q.wx[1] * (val[1] - m1));
+            }
+            sgx += gval * gx;
+            sgy += gval * gy;
+            sref += gval * (refl ? cur - alt : alt - cur);
+        }
+        acc[0] += (double)sgx * xd; acc[1] += (double)sgx * yd; acc[2] += (double)sgx;
+        acc[3] += (double)sgy * xd; acc[4] += (double)sgy * yd; acc[5] += (double)sgy;
+        acc[6] += (double)sref;
+    }
+    __shared__ double red[8][7];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < 7; ++i) {
+        double v = acc[i];
+#pragma unroll
+        for (int o = 16; o; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if (lane == 0) red[warp][i] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 7) {
+        double tsum = 0.0;
+        for (int w = 0; w < 8; ++w) tsum += red[w][threadIdx.x];
+        if (threadIdx.x < 6) atomicAdd(e.gtheta + (size_t)sample * 6 + threadIdx.x, (float)tsum);
+        else if (e.grefl) atomicAdd(e.grefl + sample, (float)tsum);
+    }
+}
+
+}  // namespace eqb
+
+extern "C" int eqb_warp_affine_grad(const float *in, const float *grad_out, const float *theta, const float *refl, int B,
+                                    int C, int H, int W, int pad, float *grad_theta, float *grad_refl, void *stream) {
+    EQB_REQUIRE(B >= 0 && C > 0 && H > 0 && W > 0 && pad >= 0, "eqb_warp_affine_grad: bad shape");
+    EQB_REQUIRE(B == 0 || (in && grad_out && theta && grad_theta), "eqb_warp_affine_grad: null pointer");
+    EQB_REQUIRE(!grad_refl || refl, "eqb_warp_affine_grad: grad_refl needs refl");
+    EQB_REQUIRE(B <= 65535, "eqb_warp_affine_grad: at most 65535 samples per call");
+    if (B == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    EQB_CUDA(cudaMemsetAsync(grad_theta, 0, (size_t)B * 6 * sizeof(float), st));
+    if (grad_refl) EQB_CUDA(cudaMemsetAsync(grad_refl, 0, (size_t)B * sizeof(float), st));
+    AffineGradArgs e{in, grad_out, theta, refl, grad_theta, grad_refl, C, H, W, pad};
+    int bx = (H * W + 255) / 256;
+    bx = std::max(1, std::min(bx, std::max(1, (8 * num_sms() + B - 1) / B)));
+    warp_affine_grad_kernel<<<dim3(bx, B), 256, 0, st>>>(e);
+    return finish_launch("eqb_warp_affine_grad");
+}

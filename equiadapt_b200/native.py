@@ -62,6 +62,7 @@ _SIGNATURES = {
     "eqb_e3_invert": (C.c_int, [_fp] * 4 + [_i, _fp]),
     "eqb_prior_stats_continuous": (C.c_int, [_fp, _i, _i, _fp, _fp]),
     "eqb_warp_affine": (C.c_int, [_fp, _fp, _fp, _fp, _i, _i, _i, _i, _i, _i, C.c_double, C.c_double, _fp]),
+    "eqb_warp_affine_grad": (C.c_int, [_fp] * 4 + [_i] * 5 + [_fp, _fp, _fp]),
     "eqb_vnsmall_param_count": (C.c_int, []),
     "eqb_vnsmall_workspace_bytes": (C.c_int64, [_i, _i]),
     "eqb_vnsmall_forward": (C.c_int, [_fp, _i, _i, _fp, _i, C.c_float, _fp, _fp, C.c_int64, _fp]),

@@ -761,3 +761,42 @@ def warp_affine(x: torch.Tensor, mats: torch.Tensor, refl: Optional[torch.Tensor
     _call("eqb_warp_affine", 1, dev, _ptr(x), _ptr(y), _ptr(mats), _ptr(refl), int(mats_forward), b, c, h, w, int(pad),
           float(cx), float(cy), _stream(dev))
     return y
+
+
+
+class _WarpAffineCanon(torch.autograd.Function):
+    """eqb_warp_affine (canonicalize direction) as an autograd node in the sampling map `theta` (B,2,3: destination ->
+    source, un-padded pixel coordinates) and the flip indicator.  The forward VALUE is the tested kernel on the rotation
+    matrices; theta only routes the gradient (the caller builds it with torch algebra from the same matrices, so torch
+    autograd continues through the matrix inverse and the reference's alpha / beta translation column)."""
+
+    @staticmethod
+    def forward(ctx, x, mats, refl_flags, pad, cx, cy, theta, refl_soft):
+        y = warp_affine(x, mats.detach(), refl_flags, True, pad, cx, cy)
+        ctx.save_for_backward(x, theta.detach(), refl_flags)
+        ctx.pad = pad
+        ctx.want_refl = refl_soft is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, theta, refl_flags = ctx.saved_tensors
+        dev = x.device
+        x32, g, th = _f32(x), _f32(dy), _f32(theta).reshape(-1, 6)
+        b, c, h, w = x32.shape
+        rf = _f32(refl_flags).reshape(-1) if refl_flags is not None else None
+        gth = torch.empty((b, 6), dtype=torch.float32, device=dev)
+        grf = torch.empty(b, dtype=torch.float32, device=dev) if (ctx.want_refl and rf is not None) else None
+        _call("eqb_warp_affine_grad", 1 if b else 0, dev, _ptr(x32), _ptr(g), _ptr(th), _optr(rf), b, c, h, w, int(ctx.pad),
+              _ptr(gth), _optr(grf), _stream(dev))
+        return None, None, None, None, None, None, gth.reshape(b, 2, 3), grf
+
+
+def warp_affine_canonicalize_autograd(x: torch.Tensor, mats: torch.Tensor, refl: Optional[torch.Tensor], pad: int, cx: float,
+                                      cy: float, theta: torch.Tensor) -> torch.Tensor:
+    """Continuous canonicalize warp whose gradient flows into `theta` (and `refl` when it requires grad)."""
+    if x.requires_grad:
+        raise NotImplementedError("the continuous warp is not differentiable with respect to the image yet")
+    flags = None if refl is None else refl.detach().reshape(-1)
+    soft = refl.reshape(-1) if (refl is not None and refl.requires_grad) else None
+    return _WarpAffineCanon.apply(x, mats, flags, pad, cx, cy, theta, soft)

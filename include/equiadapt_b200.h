@@ -195,6 +195,13 @@ EQB_API int eqb_prior_stats_continuous(const float *R, int B, int d, float *stat
  * OptimizedSteerableImageCanonicalization.group_augment (:362-412: Pad, affine_grid + grid_sample, CenterCrop). */
 EQB_API int eqb_warp_affine(const float *x, float *y, const float *mats, const float *refl, int mats_forward, int B,
                             int C, int H, int W, int pad, double cx, double cy, void *stream);
+/* N3: gradient of eqb_warp_affine (canonicalize direction) with respect to the sampling map and the flip blend.
+ * theta (B,6): destination -> source affine map in un-padded pixel coordinates, xs = t0 xd + t1 yd + t2,
+ * ys = t3 xd + t4 yd + t5 (the inverse of the reference's 2x3 warp_affine matrix, shifted by the pad; built by the
+ * caller, whose autograd then carries the result back to the network: continuous_group.py:183-208).  refl (B, may be
+ * NULL): 0/1 flip indicator used by the forward; grad_theta (B,6) and grad_refl (B, may be NULL) are overwritten. */
+EQB_API int eqb_warp_affine_grad(const float *in, const float *grad_out, const float *theta, const float *refl, int B, int C,
+                         int H, int W, int pad, float *grad_theta, float *grad_refl, void *stream);
 
 /* ---- N1  frame-predicting vector-neuron networks (eval mode) --------------------------------
  * VNSmall.forward (pointcloud/canonicalization_networks/equivariant_networks.py:128-150; knn :15-33,

@@ -1461,3 +1461,87 @@ def test_pointcloud_canonicalizer_trains_a_torch_frame_network(cuda_device):
     lo.backward()
     assert abs(float(loss.detach()) - float(lo.detach())) < 1e-4 * abs(float(lo.detach()))
     assert rel_err(can.canonicalization_network.mix.grad.cpu().double(), ref.mix.grad) < 2e-5
+
+
+# ---- N3: the continuous (SO(2) / O(2)) image warp is differentiable in the group element ------------------------------
+@pytest.mark.parametrize("with_reflection,shape", [(False, (3, 40, 40)), (True, (3, 36, 36)), (False, (1, 28, 28))])
+def test_continuous_warp_gradients_vs_oracle_autograd(with_reflection, shape, cuda_device):
+    """d canonicalize / d rotation matrix (and / d reflection indicator) of ContinuousGroupImageCanonicalization vs torch
+    autograd through the fp64 oracle (flip blend, pad, kornia warp_affine restated, crop: continuous_group.py:162-210)."""
+    from unittest import mock
+    from equiadapt_b200.images.canonicalization.continuous_group import ContinuousGroupImageCanonicalization
+    dev = cuda_device
+    gen = torch.Generator().manual_seed(800 + with_reflection + shape[0])
+    b = 6
+    x = _smooth(b, *shape, 801)
+    wt = torch.randn(b, *shape, generator=gen)
+    ang = torch.rand(b, generator=gen) * 2 * torch.pi
+    rot = torch.stack([torch.stack([torch.cos(ang), torch.sin(ang)], 1), torch.stack([-torch.sin(ang), torch.cos(ang)], 1)], 1)
+    refl = torch.randint(0, 2, (b, 1, 1, 1), generator=gen).float() if with_reflection else None
+    # The rotation centre is an integer pixel, a FIXED POINT of the map: its source coordinate sits exactly on a kink of the
+    # bilinear interpolant for every angle, and rounding noise alone picks the side (the reference's float32 and float64
+    # autograd differ by up to 8e-3 of the gradient through that one pixel).  Its loss weight is zeroed; everywhere
+    # else float32 and float64 agree to 2e-6.
+    import math
+    p_ = 0 if shape[0] == 1 else math.ceil(shape[-1] * 0.5)
+    c_ = (shape[-1] + 2 * p_) // 2 - p_
+    wt[:, :, c_, c_] = 0
+    ro = rot.double().requires_grad_(True)
+    fo = refl.double().requires_grad_(True) if with_reflection else None
+    (O.canonicalize_image_continuous(x.double(), ro, fo) * wt.double()).sum().backward()
+    # ours, through the class (the element comes from a patched get_groupelement as in the reference's own fixture)
+    can = ContinuousGroupImageCanonicalization(torch.nn.Identity(), SimpleNamespace(input_crop_ratio=0.9, resize_shape=(16, 16)), shape)
+    rd = rot.to(dev).requires_grad_(True)
+    fd = refl.to(dev).requires_grad_(True) if with_reflection else None
+    element = {"rotation": rd.clone()}
+    if with_reflection:
+        element["reflection"] = fd * 1.0
+    with mock.patch.object(can, "get_groupelement", return_value=element):
+        y = can.canonicalize(x.to(dev))
+    assert y.requires_grad
+    (y * wt.to(dev)).sum().backward()
+    assert rel_err(y.detach().cpu().double(), O.canonicalize_image_continuous(x.double(), rot.double(), refl.double() if with_reflection else None)) < RTOL
+    assert rel_err(rd.grad.cpu().double(), ro.grad) < RTOL
+    if with_reflection:
+        assert rel_err(fd.grad.cpu().double(), fo.grad) < RTOL
+
+
+def test_steerable_canonicalizer_trains_a_torch_network(cuda_device):
+    """SteerableImageCanonicalization in train() around a torch network with parameters: task loss through the warp and
+    the MSE prior reach the parameters; gradients equal torch autograd through the oracle chain."""
+    from equiadapt_b200.images.canonicalization.continuous_group import SteerableImageCanonicalization
+    import copy
+    dev = cuda_device
+
+    class Net(torch.nn.Module):
+        group_type = "rotation"
+
+        def __init__(self):
+            super().__init__()
+            self.conv = torch.nn.Conv2d(3, 4, 5)
+            self.fc = torch.nn.Linear(4, 4)
+
+        def forward(self, x):
+            return self.fc(torch.tanh(self.conv(x)).mean(dim=(2, 3))).reshape(-1, 2, 2)
+
+    torch.manual_seed(810)
+    net = Net()
+    can = SteerableImageCanonicalization(copy.deepcopy(net).to(dev), SimpleNamespace(input_crop_ratio=0.8, resize_shape=(32, 32)),
+                                         (3, 64, 64)).train()
+    x = _smooth(5, 3, 64, 64, 811)
+    wt = torch.randn(5, 3, 64, 64, generator=torch.Generator().manual_seed(812))
+    wt[:, :, 32, 32] = 0                   # the rotation's fixed-point pixel (see the test above)
+    y = can(x.to(dev))
+    loss = (y * wt.to(dev)).sum() + 50.0 * can.get_prior_regularization_loss()
+    loss.backward()
+    ref = copy.deepcopy(net)              # the reference chain in its own float32 arithmetic
+    vec = ref(O.pre_network_transform(x, (3, 64, 64), 0.8, (32, 32)))[:, 0]
+    v1 = vec / vec.norm(dim=1, keepdim=True)
+    rot = torch.stack([v1, torch.stack([-v1[:, 1], v1[:, 0]], 1)], 1)
+    neg = rot.clone()
+    neg[:, [0, 1], [1, 0]] *= -1          # the representation the prior sees after the reference's in-place flip (:180)
+    lo = (O.canonicalize_image_continuous(x, rot, None) * wt).sum() + 50.0 * O.prior_loss_continuous(neg)
+    lo.backward()
+    assert abs(float(loss.detach()) - float(lo.detach())) < 1e-3 * abs(float(lo.detach()))
+    for (k, p), (_, q) in zip(can.canonicalization_network.named_parameters(), ref.named_parameters()):
+        assert rel_err(p.grad.cpu().double(), q.grad.double()) < 1e-3, k
