@@ -9,7 +9,7 @@
 //     dX[b,c,p]           = [X[b,c,p] > 0] sum_n W_x[n,c] dY[b,n,p]            (conv2d_forward_kernel on W_x^T, 1x1, masked)
 //     db_x[n]             = sum_{b,p} dY[b,n,p]                                (plane_sums_kernel, then a (B,N) sum)
 // and the adjoints of the two (linear) filter-orbit maps (orbit_adjoint kernels).  These are fp32 SIMT kernels with
-// 64 x 64 register-blocked tiles: correctness and completeness of the training step first; the tensor-core treatment
+// 128 x 128 tiles and 8 x 8 register blocks: correctness and completeness of the training step first; the tensor-core treatment
 // the inference stack got is the obvious successor (weight gradients are NT GEMMs with K = B*H*W).
 #include <stdlib.h>
 
@@ -17,75 +17,89 @@
 
 namespace eqb {
 
-constexpr int GT_T = 64;    // tile side (outputs)
+constexpr int GT_T = 128;   // tile side (outputs): 8 x 8 register block per thread
 constexpr int GT_K = 16;    // reduction chunk
 constexpr int GT_THREADS = 256;
+constexpr int GT_PITCH = GT_T + 4;
+
+// 8 x 8 outer-product update from one reduction row of the two shared-memory tiles: the thread owns rows
+// {4 ty .. +3, 64 + 4 ty .. +3} and columns {4 tx .. +3, 64 + 4 tx .. +3} (two float4 reads per operand, conflict-free)
+__device__ __forceinline__ void gt_fma_row(const float *__restrict__ arow, const float *__restrict__ brow, int ty, int tx,
+                                           float (&acc)[8][8]) {
+    const float4 a0 = *reinterpret_cast<const float4 *>(arow + 4 * ty), a1 = *reinterpret_cast<const float4 *>(arow + 64 + 4 * ty);
+    const float4 b0 = *reinterpret_cast<const float4 *>(brow + 4 * tx), b1 = *reinterpret_cast<const float4 *>(brow + 64 + 4 * tx);
+    const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+    const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+}
+// 4-byte cp.async with zero fill (src_bytes = 0 leaves the destination zeroed): the next chunk streams into the other
+// shared-memory stage while the FMAs of the current one run
+__device__ __forceinline__ void gt_cp4(float *smem_dst, const float *gmem_src, bool valid) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    const int bytes = valid ? 4 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(gmem_src), "r"(bytes));
+}
+__device__ __forceinline__ void gt_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N_>
+__device__ __forceinline__ void gt_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N_) : "memory"); }
+__device__ __forceinline__ int gt_index(int t, int i) { return (i < 4 ? 0 : 60) + 4 * t + i; }   // i-th owned row / column
 
 // ---------------------------------------------------------------------------------------------------------------------
 // Y[b,n,p] = act( bias[n] + sum_kk W[n,kk] * X[b, ci(kk), y(p)+ky(kk), x(p)+kx(kk)] ) [* (mask[b,n,p] > 0)]
-// valid k x k convolution, NCHW fp32.  grid (ceil(P/64), ceil(N/64), B); thread (tx, ty) owns pixels tx*4..+3 and
-// channels ty*4..+3 of the tile.
+// valid k x k convolution, NCHW fp32.  grid (ceil(P/128), ceil(N/128), B).
 // ---------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(GT_THREADS) conv2d_forward_kernel(const float *__restrict__ X, const float *__restrict__ Wn,
                                                                     const float *__restrict__ bias, const float *__restrict__ mask,
                                                                     float *__restrict__ Y, int Cin, int H, int W, int k, int N,
                                                                     int relu) {
-    __shared__ float ws[GT_K][GT_T + 4];   // [kk][n]
-    __shared__ float xs[GT_K][GT_T + 4];   // [kk][p]
+    __shared__ __align__(16) float ws[2][GT_K][GT_PITCH];   // [stage][kk][n]
+    __shared__ __align__(16) float xs[2][GT_K][GT_PITCH];   // [stage][kk][p]
     const int Ho = H - k + 1, Wo = W - k + 1, P = Ho * Wo, K = Cin * k * k, kk2 = k * k;
     const int b = blockIdx.z, n0 = blockIdx.y * GT_T, p0 = blockIdx.x * GT_T;
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const float *xb = X + (size_t)b * Cin * H * W;
-    float acc[4][4] = {};
-    // loader roles: 256 threads fill 16 x 64 entries of each tile, 4 per thread
-    const int lk = tid >> 4;            // 0..15  reduction row
-    const int lc = (tid & 15) * 4;      // 0..60  column group
-    int poff[4];
+    float acc[8][8] = {};
+    // loaders.  Weights: lanes run along the 16 reduction entries of the chunk (contiguous in W[n][.]), thread owns tile
+    // rows wn + 16 j; a lane-per-row layout reads 32 sectors per warp load and competes with the FMAs for the LSU.
+    // Image: column lc = tid & 127 of the tile (contiguous pixels), reduction rows lr + 2 j.
+    const int wk = tid & 15, wn = tid >> 4;
+    const int lc = tid & 127, lr = tid >> 7;
+    const int lp = min(p0 + lc, P - 1);
+    const int pix = (lp / Wo) * W + (lp % Wo);
+    auto issue = [&](int stage, int k0) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const int p = min(p0 + lc + j, P - 1);
-        poff[j] = (p / Wo) * W + (p % Wo);
-    }
-    for (int k0 = 0; k0 < K; k0 += GT_K) {
-        const int kk = k0 + lk;
-        {   // weights: ws[lk][lc..lc+3] = W[n0+lc+j][kk]
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int n = n0 + lc + j;
-                ws[lk][lc + j] = (kk < K && n < N) ? __ldg(Wn + (size_t)n * K + kk) : 0.f;
-            }
-            // im2col: xs[lk][lc..lc+3] = X[b, ci, y+ky, x+kx]
-            if (kk < K) {
-                const int ci = kk / kk2, r = kk - ci * kk2, ky = r / k, kx = r - ky * k;
-                const float *xp = xb + (size_t)ci * H * W + ky * W + kx;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) xs[lk][lc + j] = __ldg(xp + poff[j]);
-            } else {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) xs[lk][lc + j] = 0.f;
-            }
+        for (int j = 0; j < 8; ++j) {
+            const int n = n0 + wn + 16 * j;
+            const bool wok = k0 + wk < K && n < N;
+            gt_cp4(&ws[stage][wk][wn + 16 * j], wok ? Wn + (size_t)n * K + k0 + wk : Wn, wok);
+            const int r = lr + 2 * j, kk = k0 + r;
+            const bool xok = kk < K;
+            const int kc = xok ? kk : 0;
+            const int ci = kc / kk2, rem = kc - ci * kk2, ky = rem / k, kx = rem - ky * k;
+            gt_cp4(&xs[stage][r][lc], xb + (size_t)ci * H * W + ky * W + kx + pix, xok);
         }
+        gt_commit();
+    };
+    issue(0, 0);
+    int stage = 0;
+    for (int k0 = 0; k0 < K; k0 += GT_K, stage ^= 1) {
+        if (k0 + GT_K < K) { issue(stage ^ 1, k0 + GT_K); gt_wait<1>(); } else { gt_wait<0>(); }
         __syncthreads();
 #pragma unroll
-        for (int q = 0; q < GT_K; ++q) {
-            const float4 wv = *reinterpret_cast<const float4 *>(&ws[q][ty * 4]);
-            const float4 xv = *reinterpret_cast<const float4 *>(&xs[q][tx * 4]);
-            const float wr[4] = {wv.x, wv.y, wv.z, wv.w}, xr[4] = {xv.x, xv.y, xv.z, xv.w};
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(wr[i], xr[j], acc[i][j]);
-        }
+        for (int q = 0; q < GT_K; ++q) gt_fma_row(ws[stage][q], xs[stage][q], ty, tx, acc);
         __syncthreads();
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int n = n0 + ty * 4 + i;
+    for (int i = 0; i < 8; ++i) {
+        const int n = n0 + gt_index(ty, i);
         if (n >= N) continue;
         const float bv = bias ? bias[n] : 0.f;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int p = p0 + tx * 4 + j;
+        for (int j = 0; j < 8; ++j) {
+            const int p = p0 + gt_index(tx, j);
             if (p >= P) continue;
             const size_t o = ((size_t)b * N + n) * P + p;
             float v = acc[i][j] + bv;
@@ -98,14 +112,14 @@ __global__ void __launch_bounds__(GT_THREADS) conv2d_forward_kernel(const float 
 
 // ---------------------------------------------------------------------------------------------------------------------
 // dW[n, kk] += sum over this CTA's (b, pixel) range of dY[b,n,p] * X[b, ci(kk), y(p)+ky, x(p)+kx].
-// grid (ceil(K/64), ceil(N/64), splits); the reduction range B*P is cut into `splits` contiguous pieces of whole
+// grid (ceil(K/128), ceil(N/128), splits); the reduction range B*P is cut into `splits` contiguous pieces of whole
 // 16-pixel chunks; partial tiles are added atomically (dW is zeroed by the caller).
 // ---------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(GT_THREADS) conv2d_weight_grad_kernel(const float *__restrict__ dY, const float *__restrict__ X,
                                                                         float *__restrict__ dW, int B, int Cin, int H, int W,
                                                                         int k, int N, int chunks_per_split) {
-    __shared__ float gs[GT_K][GT_T + 4];   // [p][n]
-    __shared__ float xs[GT_K][GT_T + 4];   // [p][kk]
+    __shared__ __align__(16) float gs[2][GT_K][GT_PITCH];   // [stage][p][n]
+    __shared__ __align__(16) float xs[2][GT_K][GT_PITCH];   // [stage][p][kk]
     const int Ho = H - k + 1, Wo = W - k + 1, P = Ho * Wo, K = Cin * k * k, kk2 = k * k;
     const int kk0 = blockIdx.x * GT_T, n0 = blockIdx.y * GT_T;
     const int chunks_per_image = (P + GT_K - 1) / GT_K;
@@ -113,11 +127,11 @@ __global__ void __launch_bounds__(GT_THREADS) conv2d_weight_grad_kernel(const fl
     const long long c_begin = (long long)blockIdx.z * chunks_per_split;
     const long long c_end = min(total_chunks, c_begin + chunks_per_split);
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-    // loader roles: lanes run along the 16 pixels of the chunk (contiguous in memory), thread owns columns lc + 16 j
+    // loaders: lanes run along the 16 pixels of the chunk (contiguous in memory), thread owns columns lc + 16 j (j < 8)
     const int lp = tid & 15, lc = tid >> 4;
-    int xoff[4];
+    int xoff[8];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < 8; ++j) {
         const int kk = kk0 + lc + 16 * j;
         xoff[j] = -1;
         if (kk < K) {
@@ -125,39 +139,39 @@ __global__ void __launch_bounds__(GT_THREADS) conv2d_weight_grad_kernel(const fl
             xoff[j] = ci * H * W + ky * W + kx;
         }
     }
-    float acc[4][4] = {};
-    for (long long c = c_begin; c < c_end; ++c) {
+    float acc[8][8] = {};
+    auto issue = [&](int stage, long long c) {
         const int b = (int)(c / chunks_per_image), pc = (int)(c - (long long)b * chunks_per_image) * GT_K;
         const float *gyb = dY + ((size_t)b * N) * P;
         const float *xb = X + (size_t)b * Cin * H * W;
         const int p = pc + lp;
-        const int pix = p < P ? (p / Wo) * W + (p % Wo) : 0;
+        const bool pok = p < P;
+        const int pix = pok ? (p / Wo) * W + (p % Wo) : 0;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < 8; ++j) {
             const int col = lc + 16 * j, n = n0 + col;
-            gs[lp][col] = (p < P && n < N) ? __ldg(gyb + (size_t)n * P + p) : 0.f;
-            xs[lp][col] = (p < P && xoff[j] >= 0) ? __ldg(xb + xoff[j] + pix) : 0.f;
+            const bool gok = pok && n < N, xok = pok && xoff[j] >= 0;
+            gt_cp4(&gs[stage][lp][col], gok ? gyb + (size_t)n * P + p : dY, gok);
+            gt_cp4(&xs[stage][lp][col], xok ? xb + xoff[j] + pix : X, xok);
         }
+        gt_commit();
+    };
+    if (c_begin < c_end) issue(0, c_begin);
+    int stage = 0;
+    for (long long c = c_begin; c < c_end; ++c, stage ^= 1) {
+        if (c + 1 < c_end) { issue(stage ^ 1, c + 1); gt_wait<1>(); } else { gt_wait<0>(); }
         __syncthreads();
 #pragma unroll
-        for (int q = 0; q < GT_K; ++q) {
-            const float4 gv = *reinterpret_cast<const float4 *>(&gs[q][ty * 4]);
-            const float4 xv = *reinterpret_cast<const float4 *>(&xs[q][tx * 4]);
-            const float gr[4] = {gv.x, gv.y, gv.z, gv.w}, xr[4] = {xv.x, xv.y, xv.z, xv.w};
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(gr[i], xr[j], acc[i][j]);
-        }
+        for (int q = 0; q < GT_K; ++q) gt_fma_row(gs[stage][q], xs[stage][q], ty, tx, acc);
         __syncthreads();
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int n = n0 + ty * 4 + i;
+    for (int i = 0; i < 8; ++i) {
+        const int n = n0 + gt_index(ty, i);
         if (n >= N) continue;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int kk = kk0 + tx * 4 + j;
+        for (int j = 0; j < 8; ++j) {
+            const int kk = kk0 + gt_index(tx, j);
             if (kk < K) atomicAdd(dW + (size_t)n * K + kk, acc[i][j]);
         }
     }
