@@ -190,3 +190,68 @@ def test_prior_statistic_allreduce_world2_gloo(tmp_path):
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0, f"rank {r} failed:\n{o}"
         assert f"rank {r} ok" in o
+
+
+# ---- host-side pieces of the training path (no kernel involved) ----------------------------------------------------------
+def test_prior_loss_nodes_backward_matches_torch_autograd():
+    """_PriorCrossEntropy / _PriorMSE take their VALUE from the statistic kernels; their closed-form backward must equal
+    torch autograd through CrossEntropyLoss / MSELoss (basecanonicalization.py:290-301, :390-408)."""
+    from equiadapt_b200.canonicalizers_base import _PriorCrossEntropy, _PriorMSE
+    g = torch.Generator().manual_seed(0)
+    act = torch.randn(9, 8, generator=g, requires_grad=True)
+    ref = torch.nn.functional.cross_entropy(act, torch.zeros(9, dtype=torch.long))
+    (gr,) = torch.autograd.grad(3.0 * ref, act)
+    act2 = act.detach().clone().requires_grad_(True)
+    out = _PriorCrossEntropy.apply(act2, ref.detach())
+    assert torch.equal(out, ref.detach())
+    (3.0 * out).backward()
+    assert torch.allclose(act2.grad, gr, atol=1e-7)
+    rep = torch.randn(5, 3, 3, generator=g, requires_grad=True)
+    ref = torch.nn.functional.mse_loss(rep, torch.eye(3).expand(5, 3, 3))
+    (gr,) = torch.autograd.grad(2.0 * ref, rep)
+    rep2 = rep.detach().clone().requires_grad_(True)
+    (2.0 * _PriorMSE.apply(rep2, ref.detach())).backward()
+    assert torch.allclose(rep2.grad, gr, atol=1e-7)
+
+
+def test_continuous_sampling_map_is_the_inverse_of_the_reference_matrix():
+    """ContinuousGroupImageCanonicalization._sampling_map: destination -> source map in un-padded pixels == what kornia's
+    warp_affine does with the reference's 2x3 matrix on the padded image followed by the centre crop
+    (continuous_group.py:186-208), checked by pushing pixel coordinates through both."""
+    import math
+    from equiadapt_b200.images.canonicalization.continuous_group import ContinuousGroupImageCanonicalization as C
+    h = w = 36
+    p = math.ceil(w * 0.5)
+    ang = torch.tensor([0.3, 1.7, 4.0], dtype=torch.float64)
+    rot = torch.stack([torch.stack([torch.cos(ang), torch.sin(ang)], 1), torch.stack([-torch.sin(ang), torch.cos(ang)], 1)], 1)
+    rot = rot.clone()
+    rot[:, [0, 1], [1, 0]] *= -1                     # as canonicalize() hands it over (:180)
+    theta = C._sampling_map(rot, h, w, p)
+    cx, cy = (h + 2 * p) // 2, (w + 2 * p) // 2
+    alpha, beta = rot[:, 0, 0], rot[:, 0, 1]
+    m = torch.cat([rot, torch.stack([(1 - alpha) * cx - beta * cy, beta * cx + (1 - alpha) * cy], 1).unsqueeze(-1)], -1)
+    src = torch.tensor([[3.0, 5.0], [20.5, 11.25], [0.0, 35.0]], dtype=torch.float64)        # un-padded source pixels
+    for b in range(3):
+        dst_padded = (m[b, :, :2] @ (src + p).T).T + m[b, :, 2]      # kornia: M maps source to destination
+        dst = dst_padded - p                                          # CenterCrop offset of the padded output
+        back = (theta[b, :, :2] @ dst.T).T + theta[b, :, 2]
+        assert torch.allclose(back, src, atol=1e-9)
+
+
+def test_group_inference_host_logic():
+    from types import SimpleNamespace
+    from equiadapt_b200.images.inference import GroupInference, VanillaInference, get_inference_method
+    ident, pred = torch.nn.Identity(), torch.nn.Sequential(torch.nn.Flatten(), torch.nn.Linear(12, 3))
+    v = get_inference_method(ident, pred, 3, SimpleNamespace(method="vanilla"), (3, 2, 2))
+    assert isinstance(v, VanillaInference) and not isinstance(v, GroupInference)
+    x, y = torch.randn(6, 3, 2, 2), torch.tensor([0, 1, 2, 0, 1, 2])
+    m = v.get_inference_metrics(x, y)
+    assert set(m) == {"test/acc", "test/acc_class_0", "test/acc_class_1", "test/acc_class_2"}
+    gi = get_inference_method(ident, pred, 3, {"method": "group", "group_type": "roto-reflection", "num_rotations": 4}, (3, 2, 2))
+    assert isinstance(gi, GroupInference) and gi.num_group_elements == 8
+    with pytest.raises(ValueError):
+        gi.group_orbit(torch.zeros(1, 3, 4, 4))
+    with pytest.raises(ValueError):
+        get_inference_method(ident, pred, 3, {"method": "other"}, (3, 2, 2))
+    with pytest.raises(RuntimeError):       # CPU tensors never fall back: the orbit kernel needs a CUDA tensor
+        gi.group_orbit(torch.zeros(1, 3, 2, 2))
