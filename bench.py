@@ -304,7 +304,7 @@ def run_b200(args):
         e2e_serial_s = time.perf_counter() - t0
         # the package's host-buffer front end: same step, batch sharded over a 3-stream copy/compute pipeline
         from equiadapt_b200.host_pipeline import HostStreamedCanonicalizer
-        pipe = HostStreamedCanonicalizer(can, None, "scalar", shard=args.e2e_shard, slots=3, device=dev)
+        pipe = HostStreamedCanonicalizer(can, None, "scalar", shard=args.e2e_shard, slots=3, device=dev, ramp=bool(args.e2e_ramp))
         z_serial = z_host.clone()
         z_host.zero_()
         for _ in range(2):
@@ -440,6 +440,7 @@ def main():
     ap.add_argument("--batch", type=int, default=512, help="images per GPU (weak scaling)")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--e2e-shard", type=int, default=64, help="images per stage of the host-buffer pipeline")
+    ap.add_argument("--e2e-ramp", type=int, default=0, help="1: quarter / half shards at both ends of the pipeline (shorter fill and drain)")
     ap.add_argument("--cpu-sample-batch", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -35,11 +35,14 @@ class HostStreamedCanonicalizer:
                     runs on the compute stream, must return a (b, C', H, W) feature map
     shard         : images per pipeline stage
     slots         : device input buffers in flight (>= 2)
+    ramp          : shorten the first and last shards (shard/4, shard/2, shard, ..., shard/2, shard/4): the pipeline's
+                    fill (first H2D before any kernel can run) and drain (last D2H after the last kernel) shrink from one
+                    full shard each to a quarter shard
     """
 
     def __init__(self, canonicalizer, fn: Optional[Callable[[torch.Tensor], torch.Tensor]] = None,
                  induced_rep_type: str = "scalar", shard: int = 64, slots: int = 3,
-                 device: Optional[torch.device] = None):
+                 device: Optional[torch.device] = None, ramp: bool = False):
         if slots < 2:
             raise ValueError("need at least two slots to overlap copies with compute")
         self.can = canonicalizer
@@ -47,12 +50,28 @@ class HostStreamedCanonicalizer:
         self.rep = induced_rep_type
         self.shard = int(shard)
         self.slots = int(slots)
+        self.ramp = bool(ramp)
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.s_h2d = torch.cuda.Stream(self.device)
         self.s_cmp = torch.cuda.Stream(self.device)
         self.s_d2h = torch.cuda.Stream(self.device)
         self._x_dev = None
         self.last_stats: Optional[torch.Tensor] = None
+
+    def shard_bounds(self, B: int):
+        """[(lo, hi)] of the pipeline stages over a batch of B samples."""
+        sizes = []
+        if self.ramp and self.shard >= 4 and B >= 4 * self.shard:
+            head = [self.shard // 4, self.shard // 2]
+            body = B - 2 * sum(head)
+            sizes = head + [self.shard] * (body // self.shard) + ([body % self.shard] if body % self.shard else []) + head[::-1]
+        else:
+            sizes = [self.shard] * (B // self.shard) + ([B % self.shard] if B % self.shard else [])
+        out, lo = [], 0
+        for n in sizes:
+            out.append((lo, lo + n))
+            lo += n
+        return out
 
     def _ensure_slots(self, shape, dtype):
         want = (self.slots, self.shard) + tuple(shape)
@@ -76,15 +95,14 @@ class HostStreamedCanonicalizer:
         cur = torch.cuda.current_stream(self.device)
         for s in (self.s_h2d, self.s_cmp, self.s_d2h):
             s.wait_stream(cur)                      # buffers prepared on the caller's stream are visible
-        n = (B + self.shard - 1) // self.shard
+        bounds = self.shard_bounds(B)
         h2d_done = [None] * self.slots              # input slot filled
         cmp_done = [None] * self.slots              # input slot consumed
         d2h_done = [None] * self.slots              # result of the shard that used this slot copied out
         keep = [None] * self.slots                  # results stay referenced until their D2H finished
         stats_sum = None
         prefetch, self.can.prefetch_prior_allreduce = self.can.prefetch_prior_allreduce, False   # one collective at the end
-        for i in range(n):
-            lo, hi = i * self.shard, min(B, (i + 1) * self.shard)
+        for i, (lo, hi) in enumerate(bounds):
             s = i % self.slots
             xd = self._x_dev[s, : hi - lo]
             with torch.cuda.stream(self.s_h2d):
