@@ -112,7 +112,7 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": r["img_s"], "unit": "img/s", "n_gpus": args.gpus,
         "steps": r["steps"], "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args.batch, args.gpus),
         "cpu_baseline": {"value": r["img_s"], "unit": "img/s", "cores": r["cores"], "kind": "port", "sample": sample},
         "e2e": {"value": r["img_s"], "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -404,7 +404,7 @@ def run_b200(args):
                              "(oracle restatement of the reference path on torch CPU ops)"}
         line = {
             "metric": METRIC, "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(B, world),
             "clocks": clock_info,
             "e2e": {"value": B * world * args.e2e_steps / e2e_s, "unit": "img/s",
@@ -438,12 +438,21 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=512, help="images per GPU (weak scaling)")
+    ap.add_argument("--strong", action="store_true",
+                    help="strong scaling: --batch is the GLOBAL batch, each of the N ranks takes batch / N images (SURVEY 8e asks "
+                         "for both readings; the headline and the driver's runs are weak)")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--e2e-shard", type=int, default=64, help="images per stage of the host-buffer pipeline")
     ap.add_argument("--e2e-ramp", type=int, default=0, help="1: quarter / half shards at both ends of the pipeline (shorter fill and drain)")
     ap.add_argument("--cpu-sample-batch", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    args.scaling = "weak"
+    if args.strong:
+        if args.batch % max(args.gpus, 1):
+            ap.error("--strong needs --batch divisible by --gpus")
+        args.batch //= max(args.gpus, 1)
+        args.scaling = "strong"
     if args.impl == "reference":
         run_reference(args)
     else:
