@@ -314,6 +314,42 @@ def golden_continuous_images():
         _save("image_cont_augment_" + tag, d)
 
 
+def golden_training_step():
+    """N3: parameter gradients of the UNMODIFIED reference in train() mode (torch autograd on CPU).
+    Loss = prior regularisation (basecanonicalization.py:290-301) + a linear functional of the group activations, i.e.
+    everything of the training step that is differentiable without ambiguity: the gradient through kornia's rotate at
+    quarter turns is one-sided and decided by float32 noise, so the task-loss path is pinned against the
+    oracle chain instead (tests/test_gpu_parity.py)."""
+    from equiadapt.images.canonicalization.discrete_group import GroupEquivariantImageCanonicalization
+    from equiadapt.images.canonicalization_networks.custom_equivariant_networks import CustomEquivariantNetwork
+
+    for tag, group_type, n, layers, seed in (("c8", "rotation", 8, 3, 91), ("d4", "roto-reflection", 4, 2, 93)):
+        torch.manual_seed(seed)
+        net = CustomEquivariantNetwork((3, 24, 24), 6, 5, group_type, n, layers, device="cpu")
+        net.group_type, net.num_rotations = group_type, n       # quirk A.4-1
+        with torch.no_grad():
+            for m in net.eqv_network:
+                if hasattr(m, "bias") and m.bias is not None:
+                    m.bias.uniform_(-0.05, 0.05)
+        hp = _HP(beta=1.0, input_crop_ratio=0.9, resize_shape=24)
+        can = GroupEquivariantImageCanonicalization(net, hp, (3, 32, 32)).train()
+        x = smooth_images(6, 3, 32, 32, seed=seed + 1)
+        G = can.num_group
+        wact = torch.randn(6, G, generator=torch.Generator().manual_seed(seed + 2))
+        can(x)                                                   # canonicalize: fills canonicalization_info_dict
+        act = can.canonicalization_info_dict["group_activations"]
+        prior = can.get_prior_regularization_loss()
+        loss = 100.0 * prior + (act * wact).sum()
+        loss.backward()
+        d = {"x": x, "wact": wact, "group_type": group_type, "num_rotations": n, "num_layers": layers, "act": act,
+             "prior": prior, "loss": loss, "in_shape": np.array((3, 32, 32)), "crop_ratio": 0.9, "resize": 24, "beta": 1.0}
+        for i, m in enumerate(net.eqv_network):
+            if hasattr(m, "weights"):
+                d[f"w{i}"], d[f"b{i}"] = m.weights, m.bias
+                d[f"gw{i}"], d[f"gb{i}"] = m.weights.grad, m.bias.grad
+        _save("train_step_" + tag, d)
+
+
 def golden_group_inference():
     """The evaluation orbit of examples/images/classification/inference_utils.py:97-122, produced by the reference's
     own callees (torchvision Pad / hflip / rotate / CenterCrop) in the reference's order.  The example module itself
@@ -342,6 +378,9 @@ def main():
     _import_reference()
     if "--only-orbit" in sys.argv:
         golden_group_inference()
+        return
+    if "--only-train" in sys.argv:
+        golden_training_step()
         return
     if "--only-cont" in sys.argv:
         golden_continuous_images()
@@ -372,6 +411,7 @@ def main():
     golden_vndeepsets()
     golden_continuous_images()
     golden_group_inference()
+    golden_training_step()
 
 
 if __name__ == "__main__":

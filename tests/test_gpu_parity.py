@@ -1545,3 +1545,26 @@ def test_steerable_canonicalizer_trains_a_torch_network(cuda_device):
     assert abs(float(loss.detach()) - float(lo.detach())) < 1e-3 * abs(float(lo.detach()))
     for (k, p), (_, q) in zip(can.canonicalization_network.named_parameters(), ref.named_parameters()):
         assert rel_err(p.grad.cpu().double(), q.grad.double()) < 1e-3, k
+
+
+@pytest.mark.parametrize("tag", ["c8", "d4"])
+def test_training_gradients_vs_unmodified_reference_golden(tag, cuda_device):
+    """The flagship canonicalizer in train() on the golden weights: activations, prior loss and every parameter gradient of
+    loss = 100 * prior + <act, w> equal what the UNMODIFIED reference produced with torch autograd on CPU
+    (tests/golden/train_step_*.npz)."""
+    g = load_golden("train_step_" + tag)
+    dev = cuda_device
+    can = build_canonicalizer(g, dev).train()
+    can(g["x"].to(dev))
+    act = can.canonicalization_info_dict["group_activations"]
+    assert act.requires_grad
+    prior = can.get_prior_regularization_loss()
+    loss = 100.0 * prior + (act * g["wact"].to(dev)).sum()
+    loss.backward()
+    assert rel_err(act.detach().cpu(), g["act"]) < RTOL
+    assert abs(float(prior.detach()) - float(g["prior"])) < 1e-5
+    assert abs(float(loss.detach()) - float(g["loss"])) < 1e-4 * abs(float(g["loss"]))
+    mods = [m for m in can.canonicalization_network.eqv_network if hasattr(m, "weights")]
+    for i, m in enumerate(mods):
+        assert rel_err(m.weights.grad.cpu(), g[f"gw{2 * i}"]) < RTOL, f"weights of layer {i}"
+        assert rel_err(m.bias.grad.cpu(), g[f"gb{2 * i}"]) < RTOL, f"bias of layer {i}"

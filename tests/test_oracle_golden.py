@@ -204,3 +204,24 @@ def test_linspace_degrees_restatement():
     for n in (7, 11, 13, 31):
         for a, b in zip(O.linspace_degrees(n), torch.linspace(0, 360, n + 1)[:-1]):
             assert abs(a - b.item()) <= 3.1e-5
+
+
+@pytest.mark.parametrize("tag", ["c8", "d4"])
+def test_training_gradients_of_the_oracle_match_the_unmodified_reference(tag):
+    """N3 pin: torch autograd through the oracle's restated network (filter orbits -> conv2d -> ReLU -> mean) gives the
+    parameter gradients the UNMODIFIED reference produced in train() mode for loss = 100 * prior + <act, w>
+    (tests/golden/train_step_*.npz, written by oracle/make_golden.py::golden_training_step)."""
+    from conftest import golden_layers
+    g = load_golden("train_step_" + tag)
+    reflect = g["group_type"] == "roto-reflection"
+    n = g["num_rotations"]
+    layers = [(w.clone().requires_grad_(True), b.clone().requires_grad_(True)) for w, b in golden_layers(g)]
+    x = O.pre_network_transform(g["x"], (3, 32, 32), g["crop_ratio"], int(g["resize"]))
+    act = O.custom_equivariant_network(x, layers, n, reflect)
+    assert rel_err(act.detach(), g["act"]) < TOL
+    loss = 100.0 * O.prior_loss_discrete(act) + (act * g["wact"]).sum()
+    assert abs(float(loss) - float(g["loss"])) < 1e-4 * abs(float(g["loss"]))
+    loss.backward()
+    for i, (w, b) in enumerate(layers):
+        assert rel_err(w.grad, g[f"gw{2 * i}"]) < 1e-4
+        assert rel_err(b.grad, g[f"gb{2 * i}"]) < 1e-4
