@@ -350,6 +350,34 @@ def golden_training_step():
         _save("train_step_" + tag, d)
 
 
+def golden_optimized_training():
+    """N3: the optimisation-based variant of the UNMODIFIED reference in train() mode: gradients of
+    loss = 10 * prior + 3 * optimisation-specific loss with respect to the consumer network's OUTPUT (the (|G| B, V) vectors,
+    so the fixture does not depend on that network's architecture) and to the learnable reference vector
+    (discrete_group.py:429-512, basecanonicalization.py:290-301)."""
+    from equiadapt.images.canonicalization.discrete_group import OptimizedGroupEquivariantImageCanonicalization
+    from equiadapt.images.canonicalization_networks.custom_nonequivariant_networks import ConvNetwork
+
+    for tag, group_type, n, seed in (("c8", "rotation", 8, 95), ("d4", "roto-reflection", 4, 97)):
+        torch.manual_seed(seed)
+        net = ConvNetwork((3, 24, 24), out_channels=8, kernel_size=3, num_layers=2, out_vector_size=16)
+        hp = _HP(beta=1.0, input_crop_ratio=0.9, resize_shape=24, group_type=group_type, num_rotations=n,
+                 artifact_err_wt=0, learn_ref_vec=True)
+        can = OptimizedGroupEquivariantImageCanonicalization(net, hp, (3, 32, 32)).train()
+        x = smooth_images(5, 3, 32, 32, seed=seed + 1)
+        can(x)
+        vec = can.canonicalization_info_dict["vector_out"]
+        vec.retain_grad()
+        prior, opt = can.get_prior_regularization_loss(), can.get_optimization_specific_loss()
+        loss = 10.0 * prior + 3.0 * opt
+        loss.backward()
+        _save("opt_train_step_" + tag, {
+            "x": x, "group_type": group_type, "num_rotations": n, "in_shape": np.array((3, 32, 32)), "crop_ratio": 0.9,
+            "resize": 24, "vector_out": vec, "reference_vector": can.reference_vector, "prior": prior, "opt_loss": opt,
+            "loss": loss, "act": can.canonicalization_info_dict["group_activations"],
+            "g_vector_out": vec.grad, "g_reference_vector": can.reference_vector.grad})
+
+
 def golden_group_inference():
     """The evaluation orbit of examples/images/classification/inference_utils.py:97-122, produced by the reference's
     own callees (torchvision Pad / hflip / rotate / CenterCrop) in the reference's order.  The example module itself
@@ -381,6 +409,7 @@ def main():
         return
     if "--only-train" in sys.argv:
         golden_training_step()
+        golden_optimized_training()
         return
     if "--only-cont" in sys.argv:
         golden_continuous_images()
@@ -412,6 +441,7 @@ def main():
     golden_continuous_images()
     golden_group_inference()
     golden_training_step()
+    golden_optimized_training()
 
 
 if __name__ == "__main__":

@@ -1568,3 +1568,34 @@ def test_training_gradients_vs_unmodified_reference_golden(tag, cuda_device):
     for i, m in enumerate(mods):
         assert rel_err(m.weights.grad.cpu(), g[f"gw{2 * i}"]) < RTOL, f"weights of layer {i}"
         assert rel_err(m.bias.grad.cpu(), g[f"gb{2 * i}"]) < RTOL, f"bias of layer {i}"
+
+
+@pytest.mark.parametrize("tag", ["c8", "d4"])
+def test_optimized_variant_training_gradients_vs_unmodified_reference_golden(tag, cuda_device):
+    """OptimizedGroupEquivariantImageCanonicalization in train(): gradients of 10 * prior + 3 * optimisation-specific loss
+    w.r.t. the consumer network's output and the learnable reference vector equal the UNMODIFIED reference's
+    (tests/golden/opt_train_step_*.npz; the network is replayed by its recorded output, as in the forward golden test)."""
+    _, _, OGEIC, _ = _mods()
+    g = load_golden("opt_train_step_" + tag)
+    dev = cuda_device
+    vec = g["vector_out"].to(dev).requires_grad_(True)
+
+    class Net(torch.nn.Module):
+        out_vector_size = vec.shape[1]
+
+        def forward(self, xa):
+            return vec
+
+    hp = SimpleNamespace(beta=1.0, input_crop_ratio=g["crop_ratio"], resize_shape=int(g["resize"]), group_type=g["group_type"],
+                         num_rotations=g["num_rotations"], artifact_err_wt=0, learn_ref_vec=True)
+    can = OGEIC(Net(), hp, tuple(int(v) for v in g["in_shape"])).to(dev).train()
+    with torch.no_grad():
+        can.reference_vector.copy_(g["reference_vector"].to(dev))
+    can(g["x"].to(dev))
+    prior, opt = can.get_prior_regularization_loss(), can.get_optimization_specific_loss()
+    loss = 10.0 * prior + 3.0 * opt
+    loss.backward()
+    assert rel_err(can.canonicalization_info_dict["group_activations"].detach().cpu(), g["act"]) < RTOL
+    assert abs(float(loss.detach()) - float(g["loss"])) < 1e-4 * abs(float(g["loss"]))
+    assert rel_err(vec.grad.cpu(), g["g_vector_out"]) < RTOL
+    assert rel_err(can.reference_vector.grad.cpu(), g["g_reference_vector"]) < RTOL

@@ -225,3 +225,19 @@ def test_training_gradients_of_the_oracle_match_the_unmodified_reference(tag):
     for i, (w, b) in enumerate(layers):
         assert rel_err(w.grad, g[f"gw{2 * i}"]) < 1e-4
         assert rel_err(b.grad, g[f"gb{2 * i}"]) < 1e-4
+
+
+@pytest.mark.parametrize("tag", ["c8", "d4"])
+def test_optimized_variant_training_gradients_match_the_unmodified_reference(tag):
+    """N3 pin: gradients of 10 * prior + 3 * optimisation-specific loss w.r.t. the consumer network's output vectors and the
+    reference vector, oracle chain vs the UNMODIFIED reference class in train() (tests/golden/opt_train_step_*.npz)."""
+    g = load_golden("opt_train_step_" + tag)
+    G = g["num_rotations"] * (2 if g["group_type"] == "roto-reflection" else 1)
+    vec = g["vector_out"].clone().requires_grad_(True)
+    rv = g["reference_vector"].clone().requires_grad_(True)
+    act = O.cosine_group_activations(vec, rv, G)
+    assert rel_err(act.detach(), g["act"]) < TOL
+    loss = 10.0 * O.prior_loss_discrete(act) + 3.0 * O.optimization_specific_loss(vec, G, vec.shape[1])
+    assert abs(float(loss) - float(g["loss"])) < 1e-5 * abs(float(g["loss"]))
+    loss.backward()
+    assert rel_err(vec.grad, g["g_vector_out"]) < 1e-5 and rel_err(rv.grad, g["g_reference_vector"]) < 1e-5
