@@ -136,6 +136,24 @@ def test_shard_bounds_cover_batch():
             assert max(hi - lo for lo, hi in spans) - min(hi - lo for lo, hi in spans) <= 1
 
 
+def test_host_pipeline_stage_bounds():
+    """HostStreamedCanonicalizer.shard_bounds: the stages tile the batch in order, never exceed the slot size, and the
+    ramped schedule shortens the first and last stage to a quarter shard."""
+    from equiadapt_b200.host_pipeline import HostStreamedCanonicalizer as H
+    h = H.__new__(H)
+    for shard in (1, 4, 64):
+        for ramp in (False, True):
+            h.shard, h.ramp = shard, ramp
+            for B in (1, 3, 63, 64, 65, 255, 256, 300, 512):
+                b = h.shard_bounds(B)
+                assert b[0][0] == 0 and b[-1][1] == B
+                assert all(b[i][1] == b[i + 1][0] for i in range(len(b) - 1))
+                assert all(0 < hi - lo <= shard for lo, hi in b)
+    h.shard, h.ramp = 64, True
+    sizes = [hi - lo for lo, hi in h.shard_bounds(512)]
+    assert sizes[:2] == [16, 32] and sizes[-2:] == [32, 16] and sum(sizes) == 512
+
+
 _WORKER = r"""
 import os, sys, torch, torch.distributed as dist
 sys.path.insert(0, {root!r})
