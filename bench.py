@@ -135,7 +135,7 @@ def workload_config(batch, n_gpus):
 # B200 arm
 # ---------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """SM clock / throttle reasons of one GPU, sampled every ~10 ms by an NVML thread while the timed region runs
+    """SM clock / throttle reasons of one GPU, sampled every ~5 ms by an NVML thread while the timed region runs
     (EQB_CLOCK_SAMPLE_MS overrides; at 2 ms the NVML calls of several ranks contend with the CUDA launches of all of them
     on the driver's locks: a 2-rank step at 256 images per GPU measured 1.95 ms against 0.94 ms without the sampler)
     (nvidia-smi -lms needs ~100 ms to start and cannot resolve a 40 ms region; it is the fallback when NVML is
@@ -146,7 +146,7 @@ class ClockSampler:
     def __init__(self, index):
         import threading
         self.proc, self.thread, self.samples, self.stop_flag = None, None, [], False
-        self.interval = float(os.environ.get("EQB_CLOCK_SAMPLE_MS", "10")) / 1e3
+        self.interval = float(os.environ.get("EQB_CLOCK_SAMPLE_MS", "5")) / 1e3
         try:
             import pynvml
             pynvml.nvmlInit()
