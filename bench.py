@@ -136,8 +136,8 @@ def workload_config(batch, n_gpus):
 # ---------------------------------------------------------------------------------------------------
 class ClockSampler:
     """SM clock / throttle reasons of one GPU, sampled every ~5 ms by an NVML thread while the timed region runs
-    (EQB_CLOCK_SAMPLE_MS overrides; at 2 ms the NVML calls of several ranks contend with the CUDA launches of all of them
-    on the driver's locks: a 2-rank step at 256 images per GPU measured 1.95 ms against 0.94 ms without the sampler)
+    (EQB_CLOCK_SAMPLE_MS overrides; every rank polls its own GPU, so the rate is kept moderate: NVML calls take driver locks
+    that CUDA launches of all ranks on the box also need)
     (nvidia-smi -lms needs ~100 ms to start and cannot resolve a 40 ms region; it is the fallback when NVML is
     not importable)."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
