@@ -549,7 +549,10 @@ extern "C" int eqb_group_pool_select(const float *act, int B, int num_rotations,
     EQB_REQUIRE(B >= 0 && num_rotations > 0, "eqb_group_pool_select: bad shape");
     EQB_REQUIRE(stats && (B == 0 || (act && idx && rotation)), "eqb_group_pool_select: null pointer");
     const int G = num_rotations * (reflect ? 2 : 1);
-    const unsigned blocks = grid_for(B, 256, 1024);
+    // one CTA up to 8192 samples (32 per thread): the kernel is latency-bound either way, and a single CTA finishes the
+    // statistic itself - no stream-ordered scratch allocation and no second launch on the path of every step (the
+    // cudaMallocAsync / cudaFreeAsync pair cost 8 us on some boxes of the pool and 60 us on others)
+    const unsigned blocks = B <= 8192 ? 1u : grid_for(B, 256, 1024);
     cudaStream_t st = (cudaStream_t)stream;
     double *scratch = nullptr;
     if (blocks > 1) EQB_CUDA(cudaMallocAsync((void **)&scratch, sizeof(double) * 2 * blocks, st));
