@@ -627,7 +627,8 @@ extern "C" int eqb_prior_stats_continuous(const float *R, int B, int d, float *s
     EQB_REQUIRE(B >= 0 && d > 0 && stats, "eqb_prior_stats_continuous: bad argument");
     EQB_REQUIRE(B == 0 || R, "eqb_prior_stats_continuous: null pointer");
     const long long total = (long long)B * d * d;
-    const unsigned blocks = grid_for(total, 256, 1024);
+    // one CTA up to 256 Ki matrix entries (same reasoning as eqb_group_pool_select: no scratch allocation per call)
+    const unsigned blocks = total <= 262144 ? 1u : grid_for(total, 256, 1024);
     cudaStream_t st = (cudaStream_t)stream;
     double *scratch = nullptr;
     if (blocks > 1) EQB_CUDA(cudaMallocAsync((void **)&scratch, sizeof(double) * blocks, st));
