@@ -273,3 +273,38 @@ def test_group_inference_host_logic():
         get_inference_method(ident, pred, 3, {"method": "other"}, (3, 2, 2))
     with pytest.raises(RuntimeError):       # CPU tensors never fall back: the orbit kernel needs a CUDA tensor
         gi.group_orbit(torch.zeros(1, 3, 2, 2))
+
+
+def test_argument_validation_of_the_training_and_orbit_entry_points(lib):
+    """N3 / N4 entry points reject bad arguments before any CUDA call, and their tensor wrappers never fall back to CPU."""
+    from equiadapt_b200 import native, ops
+    inv, uns = native.EQB_ERR_INVALID, native.EQB_ERR_UNSUPPORTED
+    assert lib.eqb_warp_adjoint(None, None, None, 1, 3, 8, 8, 4, 0, 3, None) == inv                 # mode out of range
+    assert lib.eqb_warp_adjoint(None, None, None, 1, 5, 8, 8, 4, 0, 2, None) == inv                 # regular: C % |G| != 0
+    assert lib.eqb_warp_element_grad(None, None, None, 1, 3, 8, 8, 0, 0, 0, None, None, None) == inv
+    assert lib.eqb_warp_element_grad(None, None, None, 1, 3, 8, 8, 4, 0, 0, None, None, None) == inv    # null pointers
+    assert lib.eqb_warp_affine_grad(None, None, None, None, 1, 3, 8, 8, -1, None, None, None) == inv
+    assert lib.eqb_orbit_rotate_nearest(None, None, 1, 3, 8, 8, 0, 0, None) == inv
+    assert lib.eqb_orbit_rotate_nearest(None, None, 1, 3, 8, 8, 65, 0, None) == uns
+    assert lib.eqb_orbit_rotate_nearest(None, None, 0, 3, 8, 8, 4, 1, None) == 0                    # empty batch: nothing to do
+    assert lib.eqb_conv2d_forward(None, None, None, None, None, 1, 3, 4, 4, 8, 5, 1, None) == inv   # map smaller than the kernel
+    assert lib.eqb_conv2d_weight_grad(None, None, None, 1, 3, 8, 8, 8, 3, None) == inv              # null dw
+    assert lib.eqb_plane_sums(None, 0, 5, None, None) == 0
+    assert lib.eqb_plane_sums(None, 3, 0, None, None) == inv
+    assert lib.eqb_group_mean_backward(None, None, 2, 0, 4, 16, None) == inv
+    assert lib.eqb_lift_filter_orbit_adjoint(None, None, 4, 3, 5, 8, 0, None) == inv
+    assert lib.eqb_regular_filter_orbit_adjoint(None, None, 4, 4, 1, 0, 0, None) == inv
+    assert lib.eqb_cosine_group_activations_backward(None, None, None, None, None, 2, 0, 8, None) == inv
+    assert lib.eqb_gram_schmidt3_backward(None, None, None, 3, 0, None) == inv
+    assert lib.eqb_gram_schmidt3_backward(None, None, None, 0, 0, None) == 0
+    assert lib.eqb_so3_apply_backward(None, None, None, None, None, -1, 4, None) == inv
+    assert lib.eqb_e3_apply_backward(None, None, None, None, None, None, None, None, None, None, 3, None) == inv
+    assert lib.eqb_e3_invert_backward(None, None, None, None, None, None, 3, None) == inv
+    for call in (lambda: ops.warp_element_grad(torch.rand(1, 3, 8, 8), torch.rand(1, 3, 8, 8), torch.zeros(1, dtype=torch.int32), 4, False, 0),
+                 lambda: ops.conv2d_forward(torch.rand(1, 3, 8, 8), torch.rand(4, 3, 3, 3), None, True),
+                 lambda: ops.conv2d_weight_grad(torch.rand(1, 4, 6, 6), torch.rand(1, 3, 8, 8), 3),
+                 lambda: ops.orbit_rotate_nearest(torch.rand(1, 3, 8, 8), 4, False),
+                 lambda: ops.cosine_group_activations(torch.rand(8, 5), torch.rand(1, 5), 4),
+                 lambda: ops.so3_apply(torch.rand(2, 3, 7), torch.rand(2, 3, 3))):
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            call()
