@@ -379,25 +379,22 @@ def golden_optimized_training():
 
 
 def golden_group_inference():
-    """The evaluation orbit of examples/images/classification/inference_utils.py:97-122, produced by the reference's
-    own callees (torchvision Pad / hflip / rotate / CenterCrop) in the reference's order.  The example module itself
-    imports omegaconf (absent here), so its loop is replayed call for call."""
-    import math
-    from torchvision import transforms
+    """The evaluation orbit of the UNMODIFIED reference: GroupInference.get_group_element_wise_logits
+    (examples/images/classification/inference_utils.py:97-122) called with an identity canonicalizer and an identity
+    prediction network, so the "logits" of element g ARE the padded / mirrored / rotated / cropped batch.  The example
+    module imports through the omegaconf stand-in of oracle/shims; Pad / hflip / rotate / CenterCrop are torchvision's."""
+    sys.path.insert(0, os.path.join(REF, "examples", "images", "classification"))
+    import inference_utils  # the reference's example module
 
     for tag, n, reflect, shape, seed in (("c4", 4, False, (2, 3, 32, 32), 41), ("d8", 8, True, (2, 3, 32, 32), 43),
                                          ("c6_gray", 6, False, (3, 1, 28, 28), 45), ("d5_rect", 5, True, (1, 3, 30, 37), 47)):
         g = torch.Generator().manual_seed(seed)
         x = torch.randn(*shape, generator=g)
-        pad = transforms.Pad(math.ceil(shape[-2] * 0.4), padding_mode="edge")       # :93
-        crop = transforms.CenterCrop((shape[-2], shape[-1]))                         # :94
-        degrees = torch.linspace(0, 360, n + 1)[:-1]                                 # :99
-        members = []
-        for degree in degrees:                                                       # :100-106
-            members.append(crop(transforms.functional.rotate(pad(x), degree.item())))
-        if reflect:                                                                  # :108-118
-            for degree in degrees:
-                members.append(crop(transforms.functional.rotate(transforms.functional.hflip(pad(x)), degree.item())))
+        hp = _HP(method="group", group_type="roto-reflection" if reflect else "rotation", num_rotations=n)
+        inf = inference_utils.get_inference_method(torch.nn.Identity(), torch.nn.Identity(), 10, hp, tuple(shape[1:]))
+        with torch.no_grad():
+            logits = inf.get_group_element_wise_logits(x)
+        members = [logits[k] for k in sorted(logits)]
         _save("group_inference_orbit_" + tag, {"x": x, "orbit": torch.stack(members), "num_rotations": n,
                                                "reflect": int(reflect)})
 

@@ -187,8 +187,9 @@ ORBIT_CASES = ["c4", "d8", "c6_gray", "d5_rect"]
 
 @pytest.mark.parametrize("tag", ORBIT_CASES)
 def test_group_inference_orbit_matches_torchvision(tag):
-    """N4: restated evaluation orbit (examples/images/classification/inference_utils.py:97-122) vs torchvision's
-    Pad / hflip / rotate(NEAREST) / CenterCrop run in the reference's order: bit-exact, rounding ties included."""
+    """N4: restated evaluation orbit vs the UNMODIFIED reference's GroupInference.get_group_element_wise_logits
+    (examples/images/classification/inference_utils.py:97-122; identity canonicalizer and prediction network, so the
+    per-element logits are the torchvision Pad / hflip / rotate(NEAREST) / CenterCrop outputs): bit-exact, ties included."""
     g = load_golden("group_inference_orbit_" + tag)
     orbit, margin = O.group_inference_orbit(g["x"], int(g["num_rotations"]), bool(int(g["reflect"])), return_margin=True)
     assert orbit.shape == g["orbit"].shape and margin.shape == orbit.shape[:1] + orbit.shape[-2:]
