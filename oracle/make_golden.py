@@ -399,10 +399,36 @@ def golden_group_inference():
                                                "reflect": int(reflect)})
 
 
+def golden_inference_metrics():
+    """Metric dictionaries of the UNMODIFIED reference's VanillaInference / GroupInference.get_inference_metrics
+    (inference_utils.py:50-77, :124-168) for a fixed linear prediction network and an identity canonicalizer; the
+    per-element logits are stored too, so the host-side metric assembly can be checked without a GPU."""
+    sys.path.insert(0, os.path.join(REF, "examples", "images", "classification"))
+    import inference_utils
+
+    torch.manual_seed(99)
+    pred = torch.nn.Sequential(torch.nn.Flatten(), torch.nn.Linear(3 * 16 * 16, 5))
+    x = torch.randn(24, 3, 16, 16)
+    y = torch.randint(0, 4, (24,))            # class 4 never occurs: exercises the nan -> 0 branch (:63-66)
+    d = {"x": x, "y": y, "weight": pred[1].weight, "bias": pred[1].bias}
+    with torch.no_grad():
+        for name, hp in (("vanilla", _HP(method="vanilla")),
+                         ("group", _HP(method="group", group_type="roto-reflection", num_rotations=4))):
+            inf = inference_utils.get_inference_method(torch.nn.Identity(), pred, 5, hp, (3, 16, 16))
+            m = inf.get_inference_metrics(x, y)
+            d[name + "_keys"] = np.array(sorted(m))
+            d[name + "_values"] = torch.stack([torch.as_tensor(float(m[k])) for k in sorted(m)])
+            if name == "group":
+                logits = inf.get_group_element_wise_logits(x)
+                d["group_logits"] = torch.stack([logits[k] for k in sorted(logits)])
+    _save("inference_metrics", d)
+
+
 def main():
     _import_reference()
     if "--only-orbit" in sys.argv:
         golden_group_inference()
+        golden_inference_metrics()
         return
     if "--only-train" in sys.argv:
         golden_training_step()
@@ -437,6 +463,7 @@ def main():
     golden_vndeepsets()
     golden_continuous_images()
     golden_group_inference()
+    golden_inference_metrics()
     golden_training_step()
     golden_optimized_training()
 

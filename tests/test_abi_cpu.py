@@ -308,3 +308,30 @@ def test_argument_validation_of_the_training_and_orbit_entry_points(lib):
                  lambda: ops.so3_apply(torch.rand(2, 3, 7), torch.rand(2, 3, 3))):
         with pytest.raises(RuntimeError, match="no CPU fallback"):
             call()
+
+
+def test_inference_metrics_match_the_unmodified_reference(monkeypatch):
+    """VanillaInference / GroupInference.get_inference_metrics (host-side assembly: accuracies per class with the nan -> 0
+    rule, per group element, their mean) vs the metric dictionaries the UNMODIFIED reference produced
+    (tests/golden/inference_metrics.npz, inference_utils.py:50-77, :124-168).  The group orbit itself is a kernel and is
+    replayed here from the reference's recorded per-element logits; its parity is a GPU test."""
+    import numpy as np
+    from conftest import GOLDEN_DIR
+    from equiadapt_b200.images.inference import get_inference_method
+    z = np.load(os.path.join(GOLDEN_DIR, "inference_metrics.npz"), allow_pickle=False)
+    x, y = torch.from_numpy(z["x"]), torch.from_numpy(z["y"])
+    pred = torch.nn.Sequential(torch.nn.Flatten(), torch.nn.Linear(3 * 16 * 16, 5))
+    with torch.no_grad():
+        pred[1].weight.copy_(torch.from_numpy(z["weight"]))
+        pred[1].bias.copy_(torch.from_numpy(z["bias"]))
+        van = get_inference_method(torch.nn.Identity(), pred, 5, {"method": "vanilla"}, (3, 16, 16))
+        m = van.get_inference_metrics(x, y)
+        assert sorted(m) == [str(k) for k in z["vanilla_keys"]]
+        assert np.allclose([float(m[k]) for k in sorted(m)], z["vanilla_values"], atol=1e-7)
+        grp = get_inference_method(torch.nn.Identity(), pred, 5,
+                                   {"method": "group", "group_type": "roto-reflection", "num_rotations": 4}, (3, 16, 16))
+        logits = torch.from_numpy(z["group_logits"])
+        monkeypatch.setattr(grp, "get_group_element_wise_logits", lambda _x: {g: logits[g] for g in range(logits.shape[0])})
+        m = grp.get_inference_metrics(x, y)
+        assert sorted(m) == [str(k) for k in z["group_keys"]]
+        assert np.allclose([float(m[k]) for k in sorted(m)], z["group_values"], atol=1e-7)
