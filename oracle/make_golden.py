@@ -218,6 +218,51 @@ def golden_nbody():
     _save("nbody_e3", d)
 
 
+def golden_frames_training():
+    """N3: gradients of the UNMODIFIED reference's point-cloud / n-body canonicalizers in train() mode with respect to the
+    frame network's OUTPUT (the (B,3,3) vectors, the per-row rotation vectors and translations): torch autograd through
+    gram_schmidt + bmm + the MSE prior (pointcloud continuous_group.py:51-134, basecanonicalization.py:390-408) and through
+    modified Gram-Schmidt + the row products + the inverse map (nbody euclidean_group.py:43-157)."""
+    from equiadapt.nbody.canonicalization.euclidean_group import EuclideanGroupNBody
+    from equiadapt.pointcloud.canonicalization.continuous_group import EquivariantPointcloudCanonicalization
+
+    g = torch.Generator().manual_seed(101)
+    x = torch.randn(6, 3, 80, generator=g)
+    w = torch.randn(6, 3, 80, generator=g)
+    vecs = torch.randn(6, 3, 3, generator=g).requires_grad_(True)
+
+    class PNet(torch.nn.Module):
+        def forward(self, _x):
+            return vecs * 1.0
+
+    can = EquivariantPointcloudCanonicalization(PNet(), _HP()).train()
+    loss = (can(x) * w).sum() + 5.0 * can.get_prior_regularization_loss()
+    loss.backward()
+    _save("pointcloud_train", {"x": x, "w": w, "vectors": vecs, "loss": loss, "g_vectors": vecs.grad})
+
+    g = torch.Generator().manual_seed(103)
+    systems, particles = 6, 5
+    m = systems * particles
+    loc, vel = torch.randn(m, 3, generator=g), torch.randn(m, 3, generator=g)
+    rv = torch.randn(systems, 3, 3, generator=g).repeat_interleave(particles, dim=0).requires_grad_(True)
+    t = torch.randn(systems, 3, generator=g).repeat_interleave(particles, dim=0).requires_grad_(True)
+    wl, wv, wi = (torch.randn(m, 3, generator=g) for _ in range(3))
+    pred = torch.randn(m, 3, generator=g)
+
+    class NNet(torch.nn.Module):
+        def forward(self, *a):
+            return rv * 1.0, t * 1.0
+
+    can = EuclideanGroupNBody(NNet()).train()
+    nodes = torch.sqrt(torch.sum(vel ** 2, dim=1)).unsqueeze(1)
+    cl, cv = can(nodes, None, loc=loc, edges=None, vel=vel, edge_attr=None, charges=None)
+    inv = can.invert_canonicalization(pred)
+    loss = (cl * wl).sum() + (cv * wv).sum() + (inv * wi).sum()
+    loss.backward()
+    _save("nbody_train", {"loc": loc, "vel": vel, "rot_vectors": rv, "translation": t, "wl": wl, "wv": wv, "wi": wi,
+                          "pred": pred, "loss": loss, "g_rot_vectors": rv.grad, "g_translation": t.grad})
+
+
 def _randomise_bn(net, g):
     """eval-mode batch norms with non-trivial running statistics and affine parameters"""
     for mod in net.modules():
@@ -433,6 +478,7 @@ def main():
     if "--only-train" in sys.argv:
         golden_training_step()
         golden_optimized_training()
+        golden_frames_training()
         return
     if "--only-cont" in sys.argv:
         golden_continuous_images()
@@ -466,6 +512,7 @@ def main():
     golden_inference_metrics()
     golden_training_step()
     golden_optimized_training()
+    golden_frames_training()
 
 
 if __name__ == "__main__":

@@ -1599,3 +1599,41 @@ def test_optimized_variant_training_gradients_vs_unmodified_reference_golden(tag
     assert abs(float(loss.detach()) - float(g["loss"])) < 1e-4 * abs(float(g["loss"]))
     assert rel_err(vec.grad.cpu(), g["g_vector_out"]) < RTOL
     assert rel_err(can.reference_vector.grad.cpu(), g["g_reference_vector"]) < RTOL
+
+
+def test_frame_path_training_gradients_vs_unmodified_reference_golden(cuda_device):
+    """Point-cloud and n-body canonicalizers in train(): gradients w.r.t. the frame network's outputs equal the UNMODIFIED
+    reference's torch autograd (tests/golden/pointcloud_train.npz, nbody_train.npz)."""
+    from equiadapt_b200.nbody.canonicalization.euclidean_group import EuclideanGroupNBody
+    from equiadapt_b200.pointcloud.canonicalization.continuous_group import EquivariantPointcloudCanonicalization
+    dev = cuda_device
+    g = load_golden("pointcloud_train")
+    vecs = g["vectors"].to(dev).requires_grad_(True)
+
+    class PNet(torch.nn.Module):
+        def forward(self, _x):
+            return vecs * 1.0
+
+    can = EquivariantPointcloudCanonicalization(PNet(), SimpleNamespace()).train()
+    loss = (can(g["x"].to(dev)) * g["w"].to(dev)).sum() + 5.0 * can.get_prior_regularization_loss()
+    loss.backward()
+    assert abs(float(loss.detach()) - float(g["loss"])) < 1e-4 * abs(float(g["loss"]))
+    assert rel_err(vecs.grad.cpu(), g["g_vectors"]) < RTOL
+
+    g = load_golden("nbody_train")
+    rv, t = g["rot_vectors"].to(dev).requires_grad_(True), g["translation"].to(dev).requires_grad_(True)
+
+    class NNet(torch.nn.Module):
+        def forward(self, *a):
+            return rv * 1.0, t * 1.0
+
+    can = EuclideanGroupNBody(NNet()).train()
+    loc, vel = g["loc"].to(dev), g["vel"].to(dev)
+    nodes = torch.sqrt(torch.sum(vel ** 2, dim=1)).unsqueeze(1)
+    cl, cv = can(nodes, None, loc=loc, edges=None, vel=vel, edge_attr=None, charges=None)
+    inv = can.invert_canonicalization(g["pred"].to(dev))
+    loss = (cl * g["wl"].to(dev)).sum() + (cv * g["wv"].to(dev)).sum() + (inv * g["wi"].to(dev)).sum()
+    loss.backward()
+    assert abs(float(loss.detach()) - float(g["loss"])) < 1e-4 * abs(float(g["loss"]))
+    assert rel_err(rv.grad.cpu(), g["g_rot_vectors"]) < RTOL
+    assert rel_err(t.grad.cpu(), g["g_translation"]) < RTOL

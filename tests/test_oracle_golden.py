@@ -242,3 +242,23 @@ def test_optimized_variant_training_gradients_match_the_unmodified_reference(tag
     assert abs(float(loss) - float(g["loss"])) < 1e-5 * abs(float(g["loss"]))
     loss.backward()
     assert rel_err(vec.grad, g["g_vector_out"]) < 1e-5 and rel_err(rv.grad, g["g_reference_vector"]) < 1e-5
+
+
+def test_frame_path_training_gradients_match_the_unmodified_reference():
+    """N3 pin: torch autograd through the oracle's frame functions equals the gradients the UNMODIFIED reference classes
+    produced in train() mode w.r.t. the frame network's outputs (tests/golden/pointcloud_train.npz, nbody_train.npz)."""
+    g = load_golden("pointcloud_train")
+    v = g["vectors"].clone().requires_grad_(True)
+    R = O.gram_schmidt(v)
+    loss = (O.so3_canonicalize(g["x"], R) * g["w"]).sum() + 5.0 * O.prior_loss_continuous(R)
+    assert abs(float(loss) - float(g["loss"])) < 1e-5 * abs(float(g["loss"]))
+    loss.backward()
+    assert rel_err(v.grad, g["g_vectors"]) < 1e-5
+    g = load_golden("nbody_train")
+    rv, t = g["rot_vectors"].clone().requires_grad_(True), g["translation"].clone().requires_grad_(True)
+    R = O.modified_gram_schmidt(rv)
+    cl, cv = O.e3_canonicalize(g["loc"], g["vel"], R, t)
+    loss = (cl * g["wl"]).sum() + (cv * g["wv"]).sum() + (O.e3_invert(g["pred"], R, t) * g["wi"]).sum()
+    assert abs(float(loss) - float(g["loss"])) < 1e-5 * abs(float(g["loss"]))
+    loss.backward()
+    assert rel_err(rv.grad, g["g_rot_vectors"]) < 1e-5 and rel_err(t.grad, g["g_translation"]) < 1e-5
