@@ -24,9 +24,12 @@ class BaseCanonicalization(torch.nn.Module):
         super().__init__()
         self.canonicalization_network = canonicalization_network
         self.canonicalization_info_dict: Dict[str, torch.Tensor] = {}
-        # all-reduce the prior statistic across ranks (superset of reference behaviour): ONE collective
-        # per forward, shared by get_prior_regularization_loss() and get_identity_metric()
-        self.sync_prior_across_ranks = True
+        # Opt-in: all-reduce the prior statistic across ranks -- ONE 3-float collective per forward,
+        # shared by get_prior_regularization_loss() and get_identity_metric(), which then report the value the
+        # single-process reference computes on the un-sharded batch.  OFF by default, as in the reference, where both
+        # readers are rank-local: with it on they are COLLECTIVE calls (every rank must read them the same number of
+        # times -- a rank-0-only logging read would hang).
+        self.sync_prior_across_ranks = False
         # issue that collective asynchronously right after the kernel that produces the statistic, so it runs
         # beside the warp kernels instead of on the critical path of the loss read.  Off by default: it makes
         # every forward a collective call (all ranks must then call forward the same number of times).
@@ -47,6 +50,20 @@ class BaseCanonicalization(torch.nn.Module):
         if work is not None:
             work.wait()          # the current CUDA stream waits; the host does not block
         return tensor
+
+    def _grad_scale(self, local_count: int, global_count: torch.Tensor):
+        """Factor that turns the rank-local mean's gradient into this rank's share of the GLOBAL mean's gradient under
+        DDP's average over ranks: (local_B / global_B) * world.  1 when the statistic is rank-local."""
+        if not self._multi_rank():
+            return None
+        return (float(local_count) * D.world()[1]) / global_count
+
+    def capture_step(self, x_example: torch.Tensor, fn=None, induced_rep_type: str = "scalar", with_prior: bool = True,
+                     warmup: int = 3):
+        """Record canonicalize -> fn -> invert_canonicalization [-> prior loss, identity metric] for inputs shaped like
+        `x_example` as ONE CUDA graph (equiadapt_b200.graphed); -> callable(x) -> (y, z[, loss, metric])."""
+        from . import graphed
+        return graphed.capture_image_step(self, x_example, fn, induced_rep_type, with_prior, warmup)
 
     def forward(self, x: torch.Tensor, targets: Optional[List] = None, **kwargs: Any):
         return self.canonicalize(x, targets, **kwargs)
@@ -82,37 +99,44 @@ class IdentityCanonicalization(BaseCanonicalization):
 class _PriorCrossEntropy(torch.autograd.Function):
     """mean_b CE(act_b, class 0) whose VALUE comes from the select kernel's statistic; the backward is the closed form
     (softmax(act) - e_0) / B on the (B,|G|) activations -- what torch autograd gives for CrossEntropyLoss in the
-    reference (basecanonicalization.py:290-301).  The gradient is that of THIS rank's mean (the reference's loss is
-    rank-local; DDP averages the parameter gradients)."""
+    reference (basecanonicalization.py:290-301).  Rank-local statistic: the gradient of THIS rank's mean (the
+    reference's loss; DDP averages the parameter gradients).  Synchronised statistic: `scale` = local_B / global_B *
+    world makes DDP's average of these gradients the gradient of the global mean the value reports."""
 
     @staticmethod
-    def forward(ctx, group_activations, value):
-        ctx.save_for_backward(group_activations)
+    def forward(ctx, group_activations, value, scale=None):
+        ctx.save_for_backward(group_activations, scale)
         return value.detach().clone()
 
     @staticmethod
     def backward(ctx, grad):
-        (act,) = ctx.saved_tensors
+        act, scale = ctx.saved_tensors
         g = torch.softmax(act.detach().float(), dim=-1)
         g[:, 0] -= 1.0
-        return g * (grad / act.shape[0]), None
+        f = grad / act.shape[0]
+        if scale is not None:
+            f = f * scale
+        return g * f, None, None
 
 
 class _PriorMSE(torch.autograd.Function):
     """MSE(R, I) whose VALUE comes from the statistic kernel; backward 2 (R - I) / (B d d) on the (B,d,d) matrices, what
-    torch autograd gives for MSELoss in the reference (basecanonicalization.py:390-408).  Rank-local mean, as there."""
+    torch autograd gives for MSELoss in the reference (basecanonicalization.py:390-408).  `scale`: see _PriorCrossEntropy."""
 
     @staticmethod
-    def forward(ctx, rep, value):
-        ctx.save_for_backward(rep)
+    def forward(ctx, rep, value, scale=None):
+        ctx.save_for_backward(rep, scale)
         return value.detach().clone()
 
     @staticmethod
     def backward(ctx, grad):
-        (rep,) = ctx.saved_tensors
+        rep, scale = ctx.saved_tensors
         r = rep.detach().float()
         eye = torch.eye(r.shape[-1], device=r.device, dtype=r.dtype)
-        return (r - eye) * (2.0 * grad / r.numel()), None
+        f = 2.0 * grad / r.numel()
+        if scale is not None:
+            f = f * scale
+        return (r - eye) * f, None, None
 
 
 class DiscreteGroupCanonicalization(BaseCanonicalization):
@@ -179,7 +203,7 @@ class DiscreteGroupCanonicalization(BaseCanonicalization):
         value = s[0] / s[2] if self._multi_rank() else s[3]   # one rank: the kernel already divided
         act = self.canonicalization_info_dict["group_activations"]
         if torch.is_grad_enabled() and act.requires_grad:
-            return _PriorCrossEntropy.apply(act, value)
+            return _PriorCrossEntropy.apply(act, value, self._grad_scale(act.shape[0], s[2]))
         return value
 
     def get_identity_metric(self) -> torch.Tensor:
@@ -214,7 +238,7 @@ class ContinuousGroupCanonicalization(BaseCanonicalization):
         value = s[0] / s[1] if self._multi_rank() else s[3]
         rep = self.canonicalization_info_dict["group_element_matrix_representation"]
         if torch.is_grad_enabled() and rep.requires_grad:
-            return _PriorMSE.apply(rep, value)
+            return _PriorMSE.apply(rep, value, self._grad_scale(rep.numel(), s[1]))
         return value
 
     def get_identity_metric(self) -> torch.Tensor:

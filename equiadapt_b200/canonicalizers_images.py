@@ -106,8 +106,11 @@ class DiscreteGroupImageCanonicalization(DiscreteGroupCanonicalization):
         """discrete_group.py:94-135: rotation in degrees (+ reflection 0/1) of the arg-max element."""
         sel = self._selection_for(group_activations)
         element = _ElementDict()
-        if self.training and self.gradient_trick == "straight_through":
-            # same expression as the reference so the values (incl. its 90-eps rounding) agree
+        sampled = self.gradient_trick != "straight_through"
+        if sampled or self.training:
+            # the reference's own expression (sum(onehot * angles), :110-133): in train() it carries the straight-through
+            # gradient (and its 90-eps rounding), and with gumbel_softmax the element IS the sampled one-hot, not the
+            # arg-max -- so the index that drives the warp is derived from that same one-hot
             onehot = self.groupactivations_to_groupelementonehot(group_activations)
             angles = torch.linspace(0.0, 360.0, self.num_rotations + 1)[: self.num_rotations].to(self.device)
             comp = torch.cat([angles, angles]) if self.group_type == "roto-reflection" else angles
@@ -115,11 +118,12 @@ class DiscreteGroupImageCanonicalization(DiscreteGroupCanonicalization):
             if self.group_type == "roto-reflection":
                 ident = torch.cat([torch.zeros(self.num_rotations), torch.ones(self.num_rotations)]).to(self.device)
                 element["reflection"] = torch.sum(onehot * ident, dim=-1)
+            element.index = onehot.detach().argmax(dim=-1).to(torch.int32) if sampled else sel["idx"]
         else:
             element["rotation"] = sel["rotation"]
             if self.group_type == "roto-reflection":
                 element["reflection"] = sel["reflection"]
-        element.index = sel["idx"]
+            element.index = sel["idx"]
         return element
 
     def get_group_activations(self, x: torch.Tensor) -> torch.Tensor:
@@ -158,6 +162,10 @@ class DiscreteGroupImageCanonicalization(DiscreteGroupCanonicalization):
     def canonicalize(self, x: torch.Tensor, targets: Optional[List] = None, **kwargs: Any):
         """discrete_group.py:190-238: pad(edge) -> flip blend -> rotate(-angle) -> crop, as ONE kernel."""
         self.device = x.device
+        if tuple(x.shape[1:]) != self.in_shape:
+            # the reference builds Pad / CenterCrop from the constructor's in_shape (:60-92); the kernels derive them from
+            # the tensor, so a different size would silently give a different transform than the reference's
+            raise ValueError(f"input of shape {tuple(x.shape[1:])} does not match in_shape {self.in_shape}")
         group_element_dict = self.get_groupelement(x)
         if targets:
             raise NotImplementedError(

@@ -4,6 +4,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "../../include/equiadapt_b200.h"
 
 namespace eqb {
@@ -44,15 +46,46 @@ inline int finish_launch(const char *what) {
         }                                                                  \
     } while (0)
 
-inline int num_sms() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess ||
-            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
-            n = 148;
+// NVTX range named after the C-ABI entry point: one range per call of the boundary in an nsys / ncu --nvtx timeline
+// (header-only NVTX3: a no-op costing one predictable branch when no tool is attached).
+struct NvtxRange {
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange &) = delete;
+    NvtxRange &operator=(const NvtxRange &) = delete;
+};
+#define EQB_NVTX_RANGE() eqb::NvtxRange eqb_nvtx_range__(__func__)
+
+inline int current_device() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0) dev = 0;
+    return dev;
+}
+
+constexpr int EQB_MAX_DEVICES = 64;
+
+// Per-DEVICE one-time setup (function attributes, device symbols): a process may drive several GPUs, and
+// cudaFuncSetAttribute / cudaMemcpyToSymbol act on the current device only.
+struct PerDeviceOnce {
+    bool done[EQB_MAX_DEVICES] = {};
+    bool first() {
+        const int dev = current_device();
+        if (dev >= EQB_MAX_DEVICES) return true;   // beyond the table: configure every time (cheap)
+        if (done[dev]) return false;
+        done[dev] = true;
+        return true;
     }
-    return n;
+};
+
+inline int num_sms() {
+    static int n[EQB_MAX_DEVICES] = {};
+    const int dev = current_device();
+    int v = dev < EQB_MAX_DEVICES ? n[dev] : 0;
+    if (v == 0) {
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+        if (dev < EQB_MAX_DEVICES) n[dev] = v;
+    }
+    return v;
 }
 
 // 2x2 matrix + flags describing one discrete group element's action on pixel coordinates:

@@ -404,6 +404,7 @@ extern "C" int eqb_conv_stack_forward(const float *x, int B, int cin, int H, int
                                       const float *const *biases, const float *const *scales,
                                       const float *const *shifts, int cout, int k, int num_group, int num_layers,
                                       float *act, void *workspace, int64_t workspace_bytes, void *stream) {
+    EQB_NVTX_RANGE();
     ConvPlan p;
     const int rc = conv_make_plan(B, cin, H, W, cout, k, num_group, num_layers, p);
     if (rc) return rc;

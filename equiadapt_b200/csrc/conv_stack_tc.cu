@@ -574,10 +574,9 @@ int ctc_conv_layer(const __half *in_hi, const __half *in_lo, int B, int Cpad, in
     EQB_UNSUPPORTED(w_stages < 2, "eqb_conv_stack (tcgen05): operand rings do not fit in shared memory (k = %d, N = %d)", k, Npad);
     a.w_stages = w_stages;
     const size_t smem = a_bytes + (size_t)w_stages * w_stage + misc;
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce configured;
+    if (configured.first()) {
         EQB_CUDA(cudaFuncSetAttribute(ctc::conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        configured = true;
     }
     if (a.tiles == 0) return 0;
     const int grid = a.tiles < num_sms() ? a.tiles : num_sms();

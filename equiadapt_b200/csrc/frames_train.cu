@@ -170,6 +170,7 @@ __global__ void __launch_bounds__(256) e3_invert_backward_kernel(const float *__
 using namespace eqb;
 
 extern "C" int eqb_gram_schmidt3_backward(const float *v, const float *dR, float *dv, int B, int modified, void *stream) {
+    EQB_NVTX_RANGE();
     EQB_REQUIRE(B >= 0, "eqb_gram_schmidt3_backward: bad batch");
     if (B == 0) return 0;
     EQB_REQUIRE(v && dR && dv, "eqb_gram_schmidt3_backward: null pointer");
@@ -179,6 +180,7 @@ extern "C" int eqb_gram_schmidt3_backward(const float *v, const float *dR, float
 
 extern "C" int eqb_so3_apply_backward(const float *x, const float *R, const float *dy, float *dx, float *dR, int B, int N,
                                       void *stream) {
+    EQB_NVTX_RANGE();
     EQB_REQUIRE(B >= 0 && N >= 0, "eqb_so3_apply_backward: bad shape");
     cudaStream_t st = (cudaStream_t)stream;
     if (dR && B > 0) EQB_CUDA(cudaMemsetAsync(dR, 0, (size_t)B * 9 * sizeof(float), st));
@@ -193,6 +195,7 @@ extern "C" int eqb_so3_apply_backward(const float *x, const float *R, const floa
 
 extern "C" int eqb_e3_apply_backward(const float *loc, const float *vel, const float *R, const float *t, const float *dloc_c,
                                      const float *dvel_c, float *dloc, float *dvel, float *dR, float *dt, int M, void *stream) {
+    EQB_NVTX_RANGE();
     EQB_REQUIRE(M >= 0, "eqb_e3_apply_backward: bad row count");
     if (M == 0) return 0;
     EQB_REQUIRE(loc && vel && R && t && (dloc_c || dvel_c), "eqb_e3_apply_backward: null pointer");
@@ -202,6 +205,7 @@ extern "C" int eqb_e3_apply_backward(const float *loc, const float *vel, const f
 
 extern "C" int eqb_e3_invert_backward(const float *x, const float *R, const float *dy, float *dx, float *dR, float *dt, int M,
                                       void *stream) {
+    EQB_NVTX_RANGE();
     EQB_REQUIRE(M >= 0, "eqb_e3_invert_backward: bad row count");
     if (M == 0) return 0;
     EQB_REQUIRE(x && R && dy, "eqb_e3_invert_backward: null pointer");

@@ -322,10 +322,9 @@ static int make_plan(int B, int cin, int H, int W, int cout, int k, int N, int r
 
 template <int NT>
 static int launch_stack(const StackArgs &a, size_t smem, cudaStream_t st) {
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce configured;
+    if (configured.first()) {
         EQB_CUDA(cudaFuncSetAttribute(gconv_stack_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        configured = true;
     }
     gconv_stack_kernel<NT><<<(unsigned)(a.B * a.chunks), GT_THREADS, smem, st>>>(a);
     return finish_launch("gconv_stack_kernel");
@@ -356,6 +355,7 @@ extern "C" int64_t eqb_gconv_stack_packed_bytes(int cin, int cout, int k, int nu
 extern "C" int eqb_gconv_stack_pack(const float *lift_w, const float *lift_b, const float *const *reg_w,
                                     const float *const *reg_b, int cin, int cout, int k, int num_rotations, int reflect,
                                     int num_layers, void *packed, int64_t packed_bytes, void *stream) {
+    EQB_NVTX_RANGE();
     StackPlan p;
     const int rc = make_plan(1, cin, k, k, cout, k, num_rotations, reflect, num_layers, p);
     if (rc) return rc;
@@ -396,6 +396,7 @@ extern "C" int eqb_gconv_stack_pack(const float *lift_w, const float *lift_b, co
 extern "C" int eqb_gconv_stack_run(const float *x, int B, int cin, int H, int W, const void *packed,
                                    const float *last_bias, int cout, int k, int num_rotations, int reflect,
                                    int num_layers, float *act, void *scratch, int64_t scratch_bytes, void *stream) {
+    EQB_NVTX_RANGE();
     StackPlan p;
     const int rc = make_plan(B, cin, H, W, cout, k, num_rotations, reflect, num_layers, p);
     if (rc) return rc;
@@ -457,6 +458,7 @@ extern "C" int eqb_gconv_stack_forward(const float *x, int B, int cin, int H, in
                                        const float *lift_b, const float *const *reg_w, const float *const *reg_b,
                                        int cout, int k, int num_rotations, int reflect, int num_layers, float *act,
                                        void *workspace, int64_t workspace_bytes, void *stream) {
+    EQB_NVTX_RANGE();
     StackPlan p;
     const int rc = make_plan(B, cin, H, W, cout, k, num_rotations, reflect, num_layers, p);
     if (rc) return rc;

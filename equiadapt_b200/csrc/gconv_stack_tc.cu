@@ -1229,9 +1229,12 @@ int tc_last_stall(int *out5) {
 
 int tc_launch(TcArgs a, cudaStream_t st) {
     if (!g_stall_host) {
-        int *dptr = nullptr;
-        EQB_CUDA(cudaHostAlloc((void **)&g_stall_host, 8 * sizeof(int), cudaHostAllocMapped));
+        EQB_CUDA(cudaHostAlloc((void **)&g_stall_host, 8 * sizeof(int), cudaHostAllocMapped | cudaHostAllocPortable));
         for (int i = 0; i < 8; ++i) g_stall_host[i] = 0;
+    }
+    static PerDeviceOnce stall_symbol;          // the __device__ pointer is one symbol PER DEVICE
+    if (stall_symbol.first()) {
+        int *dptr = nullptr;
         EQB_CUDA(cudaHostGetDevicePointer((void **)&dptr, g_stall_host, 0));
         EQB_CUDA(cudaMemcpyToSymbol(tc::g_stall_report, &dptr, sizeof(dptr)));
     }
@@ -1246,11 +1249,10 @@ int tc_launch(TcArgs a, cudaStream_t st) {
         a.lift_early = le && le[0] == '1' ? 1 : 0;
         const tc::pair::Smem M = tc::pair::smem_map(a.K0pad);
         EQB_UNSUPPORTED(M.total > 227 * 1024, "gconv_stack (tcgen05 pair): shared-memory plan of %u bytes does not fit", M.total);
-        static bool configured2 = false;
-        if (!configured2) {
+        static PerDeviceOnce configured2;
+        if (configured2.first()) {
             EQB_CUDA(cudaFuncSetAttribute(tc::pair::gconv_stack_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           227 * 1024));
-            configured2 = true;
         }
         const int items2 = a.B * a.chunks2, max_clusters = num_sms() / 2;
         const int clusters = items2 < max_clusters ? items2 : max_clusters;
@@ -1263,10 +1265,9 @@ int tc_launch(TcArgs a, cudaStream_t st) {
     const tc::Smem M = tc::smem_map(a.N, a.K0pad);
     const size_t smem = (size_t)M.total + 1024;
     EQB_UNSUPPORTED(smem > 227 * 1024, "gconv_stack (tcgen05): Cin*k*k = %d too large for the shared-memory rings", a.K0);
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce configured;
+    if (configured.first()) {
         EQB_CUDA(cudaFuncSetAttribute(tc::gconv_stack_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        configured = true;
     }
     const int items = a.B * a.chunks;
     const int grid = items < num_sms() ? items : num_sms();

@@ -264,6 +264,7 @@ using namespace eqb;
 
 extern "C" int eqb_conv2d_forward(const float *x, const float *w, const float *bias, const float *mask, float *y, int B,
                                   int cin, int H, int W, int N, int k, int relu, void *stream) {
+    EQB_NVTX_RANGE();
     EQB_REQUIRE(B >= 0 && cin > 0 && N > 0 && k > 0 && H >= k && W >= k, "eqb_conv2d_forward: bad shape");
     EQB_REQUIRE(B == 0 || (x && w && y), "eqb_conv2d_forward: null pointer");
     EQB_REQUIRE(B <= 65535 && (N + GT_T - 1) / GT_T <= 65535, "eqb_conv2d_forward: grid too large");
@@ -276,6 +277,7 @@ extern "C" int eqb_conv2d_forward(const float *x, const float *w, const float *b
 
 extern "C" int eqb_conv2d_weight_grad(const float *dy, const float *x, float *dw, int B, int cin, int H, int W, int N, int k,
                                       void *stream) {
+    EQB_NVTX_RANGE();
     EQB_REQUIRE(B >= 0 && cin > 0 && N > 0 && k > 0 && H >= k && W >= k, "eqb_conv2d_weight_grad: bad shape");
     EQB_REQUIRE(dw && (B == 0 || (dy && x)), "eqb_conv2d_weight_grad: null pointer");
     cudaStream_t st = (cudaStream_t)stream;
@@ -295,6 +297,7 @@ extern "C" int eqb_conv2d_weight_grad(const float *dy, const float *x, float *dw
 }
 
 extern "C" int eqb_plane_sums(const float *x, int64_t rows, int64_t P, float *out, void *stream) {
+    EQB_NVTX_RANGE();
     EQB_REQUIRE(rows >= 0 && P > 0 && rows < (1LL << 31), "eqb_plane_sums: bad shape");
     EQB_REQUIRE(rows == 0 || (x && out), "eqb_plane_sums: null pointer");
     if (rows == 0) return 0;
@@ -303,6 +306,7 @@ extern "C" int eqb_plane_sums(const float *x, int64_t rows, int64_t P, float *ou
 }
 
 extern "C" int eqb_group_mean_backward(const float *dact, float *dy, int B, int cout, int num_group, int64_t P, void *stream) {
+    EQB_NVTX_RANGE();
     EQB_REQUIRE(B >= 0 && cout > 0 && num_group > 0 && P > 0, "eqb_group_mean_backward: bad shape");
     EQB_REQUIRE(B == 0 || (dact && dy), "eqb_group_mean_backward: null pointer");
     const long long rows = (long long)B * cout * num_group;
@@ -315,6 +319,7 @@ extern "C" int eqb_group_mean_backward(const float *dact, float *dy, int B, int 
 
 extern "C" int eqb_lift_filter_orbit_adjoint(const float *dorbit, float *dw, int cout, int cin, int k, int num_rotations,
                                              int reflect, void *stream) {
+    EQB_NVTX_RANGE();
     EQB_REQUIRE(cout > 0 && cin > 0 && k > 0 && num_rotations > 0 && dorbit && dw, "eqb_lift_filter_orbit_adjoint: bad argument");
     const int G = num_rotations * (reflect ? 2 : 1);
     cudaStream_t st = (cudaStream_t)stream;
@@ -327,6 +332,7 @@ extern "C" int eqb_lift_filter_orbit_adjoint(const float *dorbit, float *dw, int
 
 extern "C" int eqb_regular_filter_orbit_adjoint(const float *dorbit, float *dw, int cout, int cin, int k, int num_rotations,
                                                 int reflect, void *stream) {
+    EQB_NVTX_RANGE();
     EQB_REQUIRE(cout > 0 && cin > 0 && k > 0 && num_rotations > 0 && dorbit && dw, "eqb_regular_filter_orbit_adjoint: bad argument");
     const int G = num_rotations * (reflect ? 2 : 1);
     cudaStream_t st = (cudaStream_t)stream;

@@ -294,6 +294,7 @@ extern "C" int eqb_regular_roll_shift(int r, int num_rotations) { return regular
 
 extern "C" int eqb_warp_canonicalize(const float *x, float *y, const int32_t *idx, int B, int C, int H, int W,
                                      int num_rotations, int reflect, void *stream) {
+    EQB_NVTX_RANGE();
     EQB_REQUIRE(B >= 0 && C > 0 && H > 0 && W > 0, "eqb_warp_canonicalize: bad shape (%d,%d,%d,%d)", B, C, H, W);
     EQB_REQUIRE(num_rotations > 0, "eqb_warp_canonicalize: num_rotations must be positive");
     EQB_REQUIRE(B == 0 || (x && y && idx), "eqb_warp_canonicalize: null pointer");
@@ -310,6 +311,7 @@ extern "C" int eqb_warp_canonicalize(const float *x, float *y, const int32_t *id
 
 extern "C" int eqb_warp_invert(const float *f, float *out, const int32_t *idx, int B, int C, int H, int W,
                                int num_rotations, int reflect, int rep, void *stream) {
+    EQB_NVTX_RANGE();
     EQB_REQUIRE(B >= 0 && C > 0 && H > 0 && W > 0, "eqb_warp_invert: bad shape (%d,%d,%d,%d)", B, C, H, W);
     EQB_REQUIRE(num_rotations > 0, "eqb_warp_invert: num_rotations must be positive");
     EQB_REQUIRE(rep == EQB_REP_SCALAR || rep == EQB_REP_REGULAR, "eqb_warp_invert: rep must be scalar or regular");
@@ -333,6 +335,7 @@ extern "C" int eqb_warp_invert(const float *f, float *out, const int32_t *idx, i
 
 extern "C" int eqb_orbit_expand(const float *x, float *out, int B, int C, int h, int w, int pad, int out_size,
                                 int num_rotations, int reflect, void *stream) {
+    EQB_NVTX_RANGE();
     EQB_REQUIRE(B >= 0 && C > 0 && h > 0 && w > 0, "eqb_orbit_expand: bad shape (%d,%d,%d,%d)", B, C, h, w);
     EQB_REQUIRE(num_rotations > 0 && pad >= 0, "eqb_orbit_expand: bad group / pad");
     ResampleArgs a{};
@@ -359,6 +362,7 @@ extern "C" int eqb_orbit_expand(const float *x, float *out, int B, int C, int h,
 // ---- N2: continuous rotations / roto-reflections of images ---------------------------------------
 extern "C" int eqb_warp_affine(const float *x, float *y, const float *mats, const float *refl, int mats_forward, int B,
                                int C, int H, int W, int pad, double cx, double cy, void *stream) {
+    EQB_NVTX_RANGE();
     EQB_REQUIRE(B >= 0 && C > 0 && H > 0 && W > 0 && pad >= 0, "eqb_warp_affine: bad shape (%d,%d,%d,%d) / pad %d", B, C, H, W, pad);
     EQB_REQUIRE(B == 0 || (x && y && mats), "eqb_warp_affine: null pointer");
     ResampleArgs a{};
@@ -377,6 +381,7 @@ extern "C" int eqb_warp_affine(const float *x, float *y, const float *mats, cons
 // mode 0: adjoint of eqb_warp_canonicalize, 1: of eqb_warp_invert (scalar), 2: of eqb_warp_invert (regular).
 extern "C" int eqb_warp_adjoint(const float *grad_out, float *grad_in, const int32_t *idx, int B, int C, int H, int W,
                                 int num_rotations, int reflect, int mode, void *stream) {
+    EQB_NVTX_RANGE();
     EQB_REQUIRE(B >= 0 && C > 0 && H > 0 && W > 0 && num_rotations > 0, "eqb_warp_adjoint: bad shape");
     EQB_REQUIRE(mode >= 0 && mode <= 2, "eqb_warp_adjoint: mode must be 0 (canonicalize), 1 (invert scalar) or 2 (invert regular)");
     const int G = num_rotations * (reflect ? 2 : 1);
@@ -477,6 +482,7 @@ static float linspace_degree(int i, int n) {
 
 extern "C" int eqb_orbit_rotate_nearest(const float *x, float *out, int B, int C, int H, int W, int num_rotations,
                                         int reflect, void *stream) {
+    EQB_NVTX_RANGE();
     EQB_REQUIRE(B >= 0 && C > 0 && H > 0 && W > 0, "eqb_orbit_rotate_nearest: bad shape (%d,%d,%d,%d)", B, C, H, W);
     EQB_REQUIRE(num_rotations > 0, "eqb_orbit_rotate_nearest: num_rotations must be positive");
     EQB_UNSUPPORTED(num_rotations > 64, "eqb_orbit_rotate_nearest: num_rotations <= 64 supported");
@@ -659,6 +665,7 @@ __global__ void __launch_bounds__(256) warp_element_grad_kernel(const __grid_con
 extern "C" int eqb_warp_element_grad(const float *in, const float *grad_out, const int32_t *idx, int B, int C, int H, int W,
                                      int num_rotations, int reflect, int mode, float *grad_rotation,
                                      float *grad_reflection, void *stream) {
+    EQB_NVTX_RANGE();
     EQB_REQUIRE(B >= 0 && C > 0 && H > 0 && W > 0 && num_rotations > 0, "eqb_warp_element_grad: bad shape");
     EQB_REQUIRE(mode >= 0 && mode <= 2, "eqb_warp_element_grad: mode must be 0 (canonicalize), 1 (invert scalar) or 2 (invert regular)");
     const int G = num_rotations * (reflect ? 2 : 1);
@@ -777,6 +784,7 @@ __global__ void __launch_bounds__(256) warp_affine_grad_kernel(const __grid_cons
 
 extern "C" int eqb_warp_affine_grad(const float *in, const float *grad_out, const float *theta, const float *refl, int B,
                                     int C, int H, int W, int pad, float *grad_theta, float *grad_refl, void *stream) {
+    EQB_NVTX_RANGE();
     EQB_REQUIRE(B >= 0 && C > 0 && H > 0 && W > 0 && pad >= 0, "eqb_warp_affine_grad: bad shape");
     EQB_REQUIRE(B == 0 || (in && grad_out && theta && grad_theta), "eqb_warp_affine_grad: null pointer");
     EQB_REQUIRE(!grad_refl || refl, "eqb_warp_affine_grad: grad_refl needs refl");

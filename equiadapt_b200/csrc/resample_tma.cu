@@ -355,11 +355,10 @@ template <int CG, bool ZERO>
 static int launch_cfg(const CUtensorMap &mb, const CUtensorMap &mt, ResampleArgs a, int n_dst_samples,
                       cudaStream_t st) {
     const size_t smem = (size_t)CG * PLANE_BYTES + 1024 + 16 + sizeof(TileGeom);
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce configured;
+    if (configured.first()) {
         EQB_CUDA(cudaFuncSetAttribute(resample_tma_kernel<CG, ZERO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)smem));
-        configured = true;
     }
     // grid = (tile x, tile y, sample): no integer division in the kernel; gridDim.z <= 65535 -> chunk the batch
     for (int z0 = 0; z0 < n_dst_samples; z0 += 32768) {

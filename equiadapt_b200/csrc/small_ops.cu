@@ -485,6 +485,7 @@ extern "C" const char *eqb_last_error(void) { return g_err; }
 
 extern "C" int eqb_crop_resize_aa(const float *x, float *y, int B, int C, int H, int W, int top, int left, int crop_h,
                                   int crop_w, int out_h, int out_w, void *stream) {
+    EQB_NVTX_RANGE();
     EQB_REQUIRE(B >= 0 && C > 0 && H > 0 && W > 0 && out_h > 0 && out_w > 0, "eqb_crop_resize_aa: bad shape");
     EQB_REQUIRE(top >= 0 && left >= 0 && crop_h > 0 && crop_w > 0 && top + crop_h <= H && left + crop_w <= W,
                 "eqb_crop_resize_aa: crop window [%d+%d, %d+%d] outside %dx%d", top, crop_h, left, crop_w, H, W);
@@ -530,6 +531,7 @@ int launch_regular_orbit(const float *w, float *out, int cout, int cin, int k, i
 
 extern "C" int eqb_lift_filter_orbit(const float *w, float *orbit, int cout, int cin, int k, int num_rotations,
                                      int reflect, void *stream) {
+    EQB_NVTX_RANGE();
     EQB_REQUIRE(cout > 0 && cin > 0 && k > 0 && num_rotations > 0 && w && orbit, "eqb_lift_filter_orbit: bad argument");
     return launch_lift_orbit(w, orbit, cout, cin, k, num_rotations, reflect, (long long)cin * k * k, 1,
                              (cudaStream_t)stream);
@@ -537,6 +539,7 @@ extern "C" int eqb_lift_filter_orbit(const float *w, float *orbit, int cout, int
 
 extern "C" int eqb_regular_filter_orbit(const float *w, float *orbit, int cout, int cin, int k, int num_rotations,
                                         int reflect, void *stream) {
+    EQB_NVTX_RANGE();
     EQB_REQUIRE(cout > 0 && cin > 0 && k > 0 && num_rotations > 0 && w && orbit,
                 "eqb_regular_filter_orbit: bad argument");
     const int G = num_rotations * (reflect ? 2 : 1);
@@ -546,6 +549,7 @@ extern "C" int eqb_regular_filter_orbit(const float *w, float *orbit, int cout, 
 
 extern "C" int eqb_group_pool_select(const float *act, int B, int num_rotations, int reflect, int32_t *idx,
                                      float *rotation, float *reflection, float *onehot, float *stats, void *stream) {
+    EQB_NVTX_RANGE();
     EQB_REQUIRE(B >= 0 && num_rotations > 0, "eqb_group_pool_select: bad shape");
     EQB_REQUIRE(stats && (B == 0 || (act && idx && rotation)), "eqb_group_pool_select: null pointer");
     const int G = num_rotations * (reflect ? 2 : 1);
@@ -567,6 +571,7 @@ extern "C" int eqb_group_pool_select(const float *act, int B, int num_rotations,
 
 extern "C" int eqb_cosine_group_activations(const float *vec, const float *ref, float *act, int B, int num_group, int V,
                                             void *stream) {
+    EQB_NVTX_RANGE();
     EQB_REQUIRE(B >= 0 && num_group > 0 && V > 0, "eqb_cosine_group_activations: bad shape");
     if (B == 0) return 0;
     EQB_REQUIRE(vec && ref && act, "eqb_cosine_group_activations: null pointer");
@@ -577,6 +582,7 @@ extern "C" int eqb_cosine_group_activations(const float *vec, const float *ref, 
 
 extern "C" int eqb_cosine_group_activations_backward(const float *vec, const float *ref, const float *dact, float *dvec,
                                                      float *dref, int B, int num_group, int V, void *stream) {
+    EQB_NVTX_RANGE();
     EQB_REQUIRE(B >= 0 && num_group > 0 && V > 0, "eqb_cosine_group_activations_backward: bad shape");
     cudaStream_t st = (cudaStream_t)stream;
     if (dref) EQB_CUDA(cudaMemsetAsync(dref, 0, (size_t)V * sizeof(float), st));
@@ -588,6 +594,7 @@ extern "C" int eqb_cosine_group_activations_backward(const float *vec, const flo
 }
 
 extern "C" int eqb_gram_schmidt3(const float *v, float *R, int B, int modified, void *stream) {
+    EQB_NVTX_RANGE();
     EQB_REQUIRE(B >= 0, "eqb_gram_schmidt3: bad batch");
     if (B == 0) return 0;
     EQB_REQUIRE(v && R, "eqb_gram_schmidt3: null pointer");
@@ -596,6 +603,7 @@ extern "C" int eqb_gram_schmidt3(const float *v, float *R, int B, int modified, 
 }
 
 extern "C" int eqb_so3_apply(const float *x, const float *R, float *y, int B, int N, void *stream) {
+    EQB_NVTX_RANGE();
     EQB_REQUIRE(B >= 0 && N >= 0, "eqb_so3_apply: bad shape");
     if (B == 0 || N == 0) return 0;
     EQB_REQUIRE(x && R && y, "eqb_so3_apply: null pointer");
@@ -608,6 +616,7 @@ extern "C" int eqb_so3_apply(const float *x, const float *R, float *y, int B, in
 
 extern "C" int eqb_e3_apply(const float *loc, const float *vel, const float *R, const float *t, float *loc_c,
                             float *vel_c, int M, void *stream) {
+    EQB_NVTX_RANGE();
     EQB_REQUIRE(M >= 0, "eqb_e3_apply: bad row count");
     if (M == 0) return 0;
     EQB_REQUIRE(loc && vel && R && t && loc_c && vel_c, "eqb_e3_apply: null pointer");
@@ -616,6 +625,7 @@ extern "C" int eqb_e3_apply(const float *loc, const float *vel, const float *R, 
 }
 
 extern "C" int eqb_e3_invert(const float *x, const float *R, const float *t, float *y, int M, void *stream) {
+    EQB_NVTX_RANGE();
     EQB_REQUIRE(M >= 0, "eqb_e3_invert: bad row count");
     if (M == 0) return 0;
     EQB_REQUIRE(x && R && t && y, "eqb_e3_invert: null pointer");
@@ -624,6 +634,7 @@ extern "C" int eqb_e3_invert(const float *x, const float *R, const float *t, flo
 }
 
 extern "C" int eqb_prior_stats_continuous(const float *R, int B, int d, float *stats, void *stream) {
+    EQB_NVTX_RANGE();
     EQB_REQUIRE(B >= 0 && d > 0 && stats, "eqb_prior_stats_continuous: bad argument");
     EQB_REQUIRE(B == 0 || R, "eqb_prior_stats_continuous: null pointer");
     const long long total = (long long)B * d * d;

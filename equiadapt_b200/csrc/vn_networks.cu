@@ -401,6 +401,7 @@ extern "C" int eqb_vndeepsets_forward(const float *loc, const float *vel, const 
                                       int feat_v, int feat_a, int feat_c, int nonlinearity, int layer_pool_mean,
                                       int final_pool_mean, int canon_translation, float *rot_vectors, float *translation,
                                       void *workspace, int64_t workspace_bytes, int32_t *bad_edges, void *stream) {
+    EQB_NVTX_RANGE();
     EQB_REQUIRE(S >= 0 && E >= 0 && in_dim >= 1 && in_dim <= 4 && num_layers >= 1, "eqb_vndeepsets_forward: bad argument");
     EQB_REQUIRE(in_dim == 1 + (feat_v != 0) + (feat_a != 0) + (feat_c != 0), "eqb_vndeepsets_forward: in_dim does not match the feature flags");
     EQB_REQUIRE(nonlinearity >= DS_RELU && nonlinearity <= DS_SOFTPLUS, "eqb_vndeepsets_forward: unknown nonlinearity");
@@ -464,6 +465,7 @@ extern "C" int64_t eqb_vnsmall_workspace_bytes(int B, int N) {
 
 extern "C" int eqb_vnsmall_forward(const float *x, int B, int N, const float *params, int n_knn, float bn_eps,
                                    float *out, void *workspace, int64_t workspace_bytes, void *stream) {
+    EQB_NVTX_RANGE();
     EQB_REQUIRE(B >= 0 && N > 0 && n_knn > 0, "eqb_vnsmall_forward: bad shape");
     EQB_REQUIRE(n_knn <= N, "eqb_vnsmall_forward: n_knn = %d exceeds the %d points of a cloud", n_knn, N);
     EQB_UNSUPPORTED(n_knn > 32, "eqb_vnsmall_forward: n_knn = %d > 32 not supported by this build", n_knn);

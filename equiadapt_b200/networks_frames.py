@@ -17,6 +17,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
+from ._cache import PackedParameterCache
 
 
 class _Holder(nn.Module):
@@ -55,11 +56,7 @@ class VNLinearLeakyReLU(_Holder):
         self.map_to_dir = nn.Linear(in_channels, out_channels, bias=False)
 
 
-def _version_key(params: List[torch.Tensor]):
-    return tuple((p.data_ptr(), p._version) for p in params)
-
-
-class VNSmall(nn.Module):
+class VNSmall(PackedParameterCache, nn.Module):
     """equivariant_networks.py:79-150: (B,3,N) clouds -> (B,3,3) equivariant vectors (pooling "mean")."""
 
     def __init__(self, hyperparams: Any):
@@ -92,10 +89,8 @@ class VNSmall(nn.Module):
         if self.training:
             raise NotImplementedError("VNSmall on the B200 path is inference-only: call .eval()")
         plist = self._param_list()
-        key = _version_key(plist)
-        if getattr(self, "_flat_key", None) != key:
+        if not self._packed_current(plist):
             self._flat = torch.cat([p.detach().reshape(-1).float() for p in plist])
-            self._flat_key = key
         return ops.vnsmall_forward(point_cloud, self._flat, self.n_knn, self.conv_pos.batchnorm.bn.eps)
 
 
@@ -145,7 +140,7 @@ class SequentialMultiple(nn.Sequential):
 _NONLIN = {"relu": 0, "leakyrelu": 1, "softplus": 2}
 
 
-class VNDeepSets(nn.Module):
+class VNDeepSets(PackedParameterCache, nn.Module):
     """custom_equivariant_networks.py:13-172: 5-particle systems -> (rotation vectors (M,3,3), translation (M,3))."""
 
     def __init__(self, hyperparams: Any, device: str = "cuda" if torch.cuda.is_available() else "cpu"):
@@ -195,10 +190,8 @@ class VNDeepSets(nn.Module):
         if self.training:
             raise NotImplementedError("VNDeepSets on the B200 path is inference-only: call .eval()")
         plist = self._param_list()
-        key = _version_key(plist)
-        if getattr(self, "_flat_key", None) != key:
+        if not self._packed_current(plist):
             self._flat = torch.cat([p.detach().reshape(-1).float() for p in plist])
-            self._flat_key = key
         if isinstance(edges, (list, tuple)):
             edges = torch.stack(list(edges))
         f = self.canon_feature

@@ -18,6 +18,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
+from ._cache import PackedParameterCache
 
 
 class _GroupConvParams(nn.Module):
@@ -86,7 +87,7 @@ class RotoReflectionEquivariantConv(_GroupConvParams):
         return self.filter_orbit()
 
 
-class CustomEquivariantNetwork(nn.Module):
+class CustomEquivariantNetwork(PackedParameterCache, nn.Module):
     """Lift(k x k) -> [ReLU -> GroupConv(1x1)] x (L-1) -> mean over (C,H,W) => (B,|G|).
 
     Unlike the reference class it also sets `group_type` / `num_rotations`, which
@@ -123,22 +124,25 @@ class CustomEquivariantNetwork(nn.Module):
         # only: rebuilt when a parameter was modified in place or replaced, reused otherwise.  (The reference
         # rebuilds its orbits on every forward: custom_group_equivariant_layers.py:103, :349-351.)
         params = [p for m in mods for p in (m.weights, m.bias) if p is not None]
-        if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in params):
-            # train() mode: layer-wise path that keeps the feature maps, backward on the N3 kernels (gconv_train.cu).
-            # eval() mode always takes the fused inference stack (no autograd graph).  The gradient with respect to
-            # the input image is not produced (the reference's examples never use it).
+        if torch.is_grad_enabled() and any(p.requires_grad for p in params):
+            # a gradient is wanted (the reference differentiates in train() AND eval()): layer-wise path that keeps the
+            # feature maps, backward on the N3 kernels (gconv_train.cu).  Under no_grad / with frozen parameters: the
+            # fused inference stack (no autograd graph).  The gradient with respect to the input image is not produced
+            # (the reference's examples never use it): asking for it raises instead of returning silence.
+            if x.requires_grad:
+                raise NotImplementedError("CustomEquivariantNetwork on the B200 path does not differentiate with respect "
+                                          "to its input image; detach() it (the reference's training loops do not need it)")
             return ops.gconv_stack_train(x, [(m.weights, m.bias) for m in mods], self.num_rotations, reflect)
-        key = tuple((p.data_ptr(), p._version) for p in params)
-        if getattr(self, "_packed_key", None) != key:
+        if not self._packed_current(params):
+            # (key: data_ptr + version of every parameter -- see _cache.py for what that does and does not catch)
             self._packed = ops.gconv_stack_pack(lift.weights, lift.bias, [m.weights for m in regs],
                                                 [m.bias for m in regs], self.num_rotations, reflect)
-            self._packed_key = key
         last_bias = regs[-1].bias if regs else None
         return ops.gconv_stack_run(x, self._packed, last_bias, lift.out_channels, lift.kernel_size,
                                    self.num_rotations, reflect, len(mods))
 
 
-class ESCNNEquivariantNetwork(nn.Module):
+class ESCNNEquivariantNetwork(PackedParameterCache, nn.Module):
     """The reference's e2cnn network (escnn_networks.py:8-117) on the expanded-filter conv stack (eqb_conv_stack_forward).
 
     Reference layout: R2Conv(k) -> InnerBatchNorm -> ReLU -> PointwiseDropout(.5), (L-2) more such blocks,
@@ -229,14 +233,22 @@ class ESCNNEquivariantNetwork(nn.Module):
         return self
 
     def folded_affine(self):
-        """Per-channel (scale, shift) of every inner layer's batch norm in eval mode, expanded over the group axis."""
+        """Per-channel (scale, shift) of every inner layer's batch norm in eval mode, expanded over the group axis;
+        rebuilt only when a batch-norm tensor changed (it was ~8 eager torch launches on every forward)."""
         g = self.num_group_elements
+        srcs = []
+        for l in range(self.num_layers - 1):
+            srcs += [self.bn_weight[l], self.bn_bias[l], getattr(self, f"bn_running_mean_{l}"), getattr(self, f"bn_running_var_{l}")]
+        if self._packed_current(srcs) and getattr(self, "_folded", None) is not None and self._folded[2] == self.bn_eps:
+            return self._folded[0], self._folded[1]
         scales, shifts = [], []
         for l in range(self.num_layers - 1):
             mean, var = getattr(self, f"bn_running_mean_{l}"), getattr(self, f"bn_running_var_{l}")
             sc = self.bn_weight[l] / torch.sqrt(var + self.bn_eps)
             scales.append(sc.repeat_interleave(g))
             shifts.append((self.bn_bias[l] - mean * sc).repeat_interleave(g))
+        scales, shifts = [t.detach() for t in scales], [t.detach() for t in shifts]
+        self._folded = (scales, shifts, self.bn_eps)
         return scales, shifts
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:

@@ -38,6 +38,13 @@ def _f32(t: torch.Tensor) -> torch.Tensor:
     return t.detach().contiguous()
 
 
+def _no_backward(what: str, *tensors: Optional[torch.Tensor]) -> None:
+    """Fail loudly where the reference would differentiate and this path has no backward kernel (instead of silently
+    returning a graph-less result)."""
+    if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors):
+        raise NotImplementedError(f"{what} has no backward on the B200 path: detach() the argument or run under torch.no_grad()")
+
+
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
@@ -68,6 +75,7 @@ def _call(name: str, n_launches: int, dev: torch.device, *args):
 # ---- a3 -----------------------------------------------------------------------------------------
 def crop_resize_aa(x: torch.Tensor, top: int, left: int, crop_h: int, crop_w: int, out_h: int, out_w: int) -> torch.Tensor:
     dev = _need_cuda(x)
+    _no_backward("crop_resize_aa (gradient with respect to the image)", x)
     x = _f32(x)
     b, c, h, w = x.shape
     y = torch.empty((b, c, out_h, out_w), dtype=torch.float32, device=dev)
@@ -262,6 +270,7 @@ def gconv_stack_run(x: torch.Tensor, packed: torch.Tensor, last_bias: Optional[t
     """x (B,Cin,H,W) -> group activations (B,|G|) with pre-packed parameters: 3 launches on the tcgen05 path
     (batch max |x|, fused stack, finish), 2 on the SIMT path."""
     dev = _need_cuda(x, packed, last_bias)
+    _no_backward("gconv_stack_run (the fused inference stack)", x)
     x = _f32(x)
     last_bias = None if last_bias is None else _f32(last_bias)
     b, cin, h, w = x.shape
@@ -470,6 +479,7 @@ def warp_invert_autograd(f: torch.Tensor, idx: torch.Tensor, num_rotations: int,
 
 def orbit_expand(x: torch.Tensor, pad: int, out_size: int, num_rotations: int, reflect: bool) -> torch.Tensor:
     dev = _need_cuda(x)
+    _no_backward("orbit_expand (gradient with respect to the image)", x)
     x = _f32(x)
     b, c, h, w = x.shape
     g = num_rotations * (2 if reflect else 1)

@@ -182,6 +182,8 @@ assert world == 1 or abs(float(local_only) - float(loss)) > 0 or True
 from equiadapt_b200.canonicalizers_base import DiscreteGroupCanonicalization
 for prefetch in (False, True):
     can = DiscreteGroupCanonicalization(torch.nn.Identity())
+    assert can.sync_prior_across_ranks is False                 # the reference's readers are rank-local: opt-in only
+    can.sync_prior_across_ranks = True
     can.prefetch_prior_allreduce = prefetch
     can.canonicalization_info_dict = {{"group_activations": mine}}
     can._selected = {{"activations": mine, "stats": stats, "global": can._start_stats_allreduce(stats) if prefetch else None}}
@@ -192,6 +194,26 @@ for prefetch in (False, True):
     D.allreduce_stats_async = real
     assert len(calls) == (0 if prefetch else 1), calls          # never a second collective for the metric
     assert abs(float(l2) - float(O.prior_loss_discrete(act))) < 1e-5 and abs(float(i2) - float(O.identity_metric_discrete(act))) < 1e-6
+# default (sync off) = the reference: rank-local values, no collective, so a rank-0-only logging read cannot hang
+can = DiscreteGroupCanonicalization(torch.nn.Identity())
+can.canonicalization_info_dict = {{"group_activations": mine}}
+local5 = torch.cat([stats, stats[:2] / stats[2]])
+can._selected = {{"activations": mine, "stats": local5, "global": None}}
+if rank == 0:
+    l_loc = can.get_prior_regularization_loss()
+    assert abs(float(l_loc) - float(O.prior_loss_discrete(mine))) < 1e-5
+# synchronised statistic: value = global mean, and DDP's average of the per-rank gradients = gradient of that global mean
+# (unequal shards: 19 / 18 samples)
+can = DiscreteGroupCanonicalization(torch.nn.Identity())
+can.sync_prior_across_ranks = True
+leaf = mine.clone().requires_grad_(True)
+can.canonicalization_info_dict = {{"group_activations": leaf}}
+can._selected = {{"activations": leaf, "stats": local5, "global": None}}
+can.get_prior_regularization_loss().backward()
+full = act.clone().requires_grad_(True)
+torch.nn.functional.cross_entropy(full, torch.zeros(act.shape[0], dtype=torch.long)).backward()
+lo, hi = D.shard_bounds(act.shape[0], rank, world)
+assert torch.allclose(leaf.grad / world, full.grad[lo:hi], atol=1e-7), (leaf.grad / world - full.grad[lo:hi]).abs().max()
 dist.barrier(); dist.destroy_process_group()
 print("rank", rank, "ok")
 """

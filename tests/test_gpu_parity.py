@@ -91,16 +91,18 @@ def test_image_path_vs_reference_golden(case, cuda_device):
         ref_idx = torch.round(g["rotation"] / 360.0 * n).long() % n
         if reflect:
             ref_idx = ref_idx + n * g["reflection"].long()
-        if torch.equal(idx.long(), ref_idx):
-            assert torch.equal(info["group_element"]["rotation"].cpu(), g["rotation"])
-            assert rel_err(y.cpu(), g["x_canon"]) < RTOL
-            if reflect:
-                assert torch.equal(info["group_element"]["reflection"].cpu(), g["reflection"])
-            for rep in ("regular", "scalar"):
-                inv = can.invert_canonicalization(g[f"f_{rep}"].to(dev), induced_rep_type=rep)
-                assert rel_err(inv.cpu(), g[f"inv_{rep}"]) < RTOL
-        else:  # only legal if every mismatch sits inside the tie band
-            assert in_band > 0
+        # samples whose index equals the reference's are compared element-wise; a differing index is only legal inside
+        # the tie band (and never skips the comparison of the others)
+        same = idx.long() == ref_idx
+        assert int((~same).sum()) <= in_band, "group index differs from the reference outside the tie band"
+        assert int(same.sum()) >= 1
+        assert torch.equal(info["group_element"]["rotation"].cpu()[same], g["rotation"][same])
+        assert rel_err(y.cpu()[same], g["x_canon"][same]) < RTOL
+        if reflect:
+            assert torch.equal(info["group_element"]["reflection"].cpu()[same], g["reflection"][same])
+        for rep in ("regular", "scalar"):
+            inv = can.invert_canonicalization(g[f"f_{rep}"].to(dev), induced_rep_type=rep)
+            assert rel_err(inv.cpu()[same], g[f"inv_{rep}"][same]) < RTOL
         # a13
         assert abs(float(can.get_prior_regularization_loss()) - float(g["prior_loss"])) < 1e-5
         assert float(can.get_identity_metric()) == pytest.approx(float((act.argmax(-1) == 0).float().mean()))
@@ -1637,3 +1639,106 @@ def test_frame_path_training_gradients_vs_unmodified_reference_golden(cuda_devic
     assert abs(float(loss.detach()) - float(g["loss"])) < 1e-4 * abs(float(g["loss"]))
     assert rel_err(rv.grad.cpu(), g["g_rot_vectors"]) < RTOL
     assert rel_err(t.grad.cpu(), g["g_translation"]) < RTOL
+
+
+# ---- round 2: captured step, cache invalidation, second device, sampled element ----------------------------------------
+def _small_c8(dev, seed=70, in_hw=64, resize=32, cout=8):
+    _, GEIC, _, Net = _mods()
+    torch.manual_seed(seed)
+    net = Net((3, resize, resize), cout, 5, "rotation", 8, 3, device="cpu").to(dev)
+    return GEIC(net, SimpleNamespace(beta=1.0, input_crop_ratio=0.8, resize_shape=resize), (3, in_hw, in_hw)).eval()
+
+
+def test_capture_step_replays_the_public_step_bit_exactly(cuda_device):
+    """canonicalizer.capture_step(): ONE graph launch == canonicalize + invert + prior loss + identity metric of the eager
+    public calls, on new data copied into the captured buffer and on the buffer itself."""
+    dev = cuda_device
+    can = _small_c8(dev)
+    gen = torch.Generator().manual_seed(71)
+    x0, x1 = torch.rand(16, 3, 64, 64, generator=gen).to(dev), torch.rand(16, 3, 64, 64, generator=gen).to(dev)
+    step = can.capture_step(x0.clone(), induced_rep_type="scalar")
+    with torch.no_grad():
+        for x in (x1, x0):
+            y, z, loss, ident = step(x)
+            torch.cuda.synchronize()
+            got = (y.clone(), z.clone(), float(loss), float(ident))
+            yr = can(x)
+            zr = can.invert_canonicalization(yr, induced_rep_type="scalar")
+            ref = (yr, zr, float(can.get_prior_regularization_loss()), float(can.get_identity_metric()))
+            assert torch.equal(got[0], ref[0]) and torch.equal(got[1], ref[1]) and got[2:] == ref[2:]
+        step.inputs[0].copy_(x1)
+        y, z, loss, ident = step()                 # no argument: replay on whatever the captured buffer holds
+        torch.cuda.synchronize()
+        assert torch.equal(y, can(x1))
+    with pytest.raises(ValueError):
+        step(x1[:8])
+
+
+def test_packed_operand_cache_follows_parameter_writes(cuda_device):
+    """in-place ops bump the version and repack; writes through .data do not, so invalidate_packed() (also
+    called by load_state_dict / _apply / train) or cache_packed = False is the contract for those."""
+    dev = cuda_device
+    can = _small_c8(dev, seed=72)
+    net = can.canonicalization_network
+    x = torch.rand(4, 3, 32, 32, generator=torch.Generator().manual_seed(73)).to(dev)
+    lift = net.eqv_network[0]
+    with torch.no_grad():
+        a0 = net(x).clone()
+        lift.weights.mul_(1.5)                              # in-place op on the parameter: version bump -> repacked
+        a1 = net(x).clone()
+        assert not torch.equal(a0, a1)
+        lift.weights.data.mul_(2.0)                         # write through .data: invisible to the version counter
+        stale = net(x).clone()
+        assert torch.equal(stale, a1)
+        net.invalidate_packed()
+        a2 = net(x).clone()
+        assert not torch.equal(a2, a1)
+        sd = {k: v.clone() for k, v in net.state_dict().items()}
+        lift.weights.data.mul_(0.5)
+        net.load_state_dict(sd)                             # restores the doubled weights AND drops the cache
+        assert torch.equal(net(x), a2)
+        net.cache_packed = False                            # the reference's behaviour: rebuilt on every forward
+        lift.weights.data.mul_(0.5)
+        assert torch.equal(net(x), a1)
+
+
+def test_second_device_in_one_process(cuda_device):
+    """function attributes / the SM count / the stall-report symbol are per DEVICE; the stack, the TMA warp and the
+    frame kernels must run on cuda:1 after cuda:0 in one process."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    outs = []
+    x = torch.rand(8, 3, 64, 64, generator=torch.Generator().manual_seed(75))
+    for d in (0, 1):
+        dev = torch.device("cuda", d)
+        can = _small_c8(dev, seed=74)
+        with torch.no_grad():
+            y = can(x.to(dev))
+            z = can.invert_canonicalization(y, induced_rep_type="scalar")
+            outs.append((y.cpu(), z.cpu(), float(can.get_prior_regularization_loss())))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1]) and outs[0][2] == outs[1][2]
+
+
+def test_gumbel_softmax_element_is_the_sampled_one(cuda_device):
+    """with gradient_trick = "gumbel_softmax" the reference derives the element from the SAMPLED one-hot
+    (discrete_group.py:94-135); the warp must be driven by that same sample, not by the arg-max."""
+    dev = cuda_device
+    can = _small_c8(dev, seed=76)
+    can.gradient_trick = "gumbel_softmax"
+    ops = _mods()[0]
+    x = torch.rand(32, 3, 64, 64, generator=torch.Generator().manual_seed(77)).to(dev)
+    with torch.no_grad():
+        torch.manual_seed(5)
+        y = can(x)
+        el = can.canonicalization_info_dict["group_element"]
+        angles = torch.linspace(0.0, 360.0, 9)[:8].to(dev)
+        assert torch.equal(el["rotation"], angles[el.index.long()])
+        assert torch.equal(y, ops.warp_canonicalize(x, el.index, 8, False))
+        act = can.canonicalization_info_dict["group_activations"]
+        assert not torch.equal(el.index.long(), act.argmax(-1))      # 32 samples with gaps of 1e-6: the sample differs somewhere
+
+
+def test_input_shape_must_match_in_shape(cuda_device):
+    can = _small_c8(cuda_device, seed=78)
+    with pytest.raises(ValueError):
+        can(torch.rand(2, 3, 48, 48, device=cuda_device))
