@@ -442,7 +442,7 @@ def measure(fn, inputs, steps, warmup, barrier, world, dev, use_graph=True):
     """-> (ms per step max over ranks, mode): fn(*inputs) timed as a captured graph when it captures, eagerly otherwise."""
     import torch.distributed as dist
     from equiadapt_b200 import graphed
-    mode = "eager"
+    mode, g = "eager", None
     call = lambda: fn(*inputs)  # noqa: E731
     with torch.no_grad():
         if use_graph:
@@ -455,6 +455,7 @@ def measure(fn, inputs, steps, warmup, barrier, world, dev, use_graph=True):
         for _ in range(max(warmup, 3)):
             call()
         total, per, _ = timed_steps(call, steps, barrier)
+        call = g = None
     t = torch.tensor([total / steps], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -627,6 +628,7 @@ def index_agreement(can, x_dev, n=32):
     net = make_layers()
     layers = [(m.weights.detach(), m.bias.detach()) for m in net.eqv_network if hasattr(m, "weights")]
     xs = x_dev[:n]
+    sync, can.sync_prior_across_ranks, can.prefetch_prior_allreduce = can.sync_prior_across_ranks, False, False   # rank 0 alone calls this
     with torch.no_grad():
         can(xs)
         act = can.canonicalization_info_dict["group_activations"].float().cpu()
@@ -635,6 +637,7 @@ def index_agreement(can, x_dev, n=32):
         a32 = O.custom_equivariant_network(O.pre_network_transform(xc, IN_SHAPE, CROP, RESIZE), layers, N_ROT, False)
         l64 = [(w.double(), b.double()) for w, b in layers]
         a64 = O.custom_equivariant_network(O.pre_network_transform(xc.double(), IN_SHAPE, CROP, RESIZE), l64, N_ROT, False)
+    can.sync_prior_across_ranks = can.prefetch_prior_allreduce = sync
     i32, i64 = a32.argmax(-1), a64.argmax(-1)
     top2 = a64.topk(2, dim=-1).values
     return {"n": n, "ours_vs_fp64": float((ours == i64).float().mean()), "fp32_port_vs_fp64": float((i32 == i64).float().mean()),
@@ -877,9 +880,27 @@ def run_b200(args):
             "checks": checks,
         }
         print(json.dumps(line))
+    # captured graphs hold NCCL kernels: they must be gone before the communicator is torn down (ncclCommDestroy waits on them)
+    graphed_step = None
+    shutdown(world)
+
+
+def shutdown(world):
+    import gc
+    import threading
+    import torch.distributed as dist
+    gc.collect()
+    torch.cuda.synchronize()
+    sys.stdout.flush()
     if world > 1:
         dist.barrier()
-        dist.destroy_process_group()
+        th = threading.Thread(target=dist.destroy_process_group, daemon=True)
+        th.start()
+        th.join(20.0)
+        if th.is_alive():          # never let a teardown problem turn a finished measurement into a hung job
+            sys.stderr.write("bench.py: destroy_process_group did not return within 20 s; exiting\n")
+            sys.stderr.flush()
+            os._exit(0)
 
 
 def main():

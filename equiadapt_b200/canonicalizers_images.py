@@ -150,7 +150,9 @@ class DiscreteGroupImageCanonicalization(DiscreteGroupCanonicalization):
         if ch > h or cw > w:
             raise NotImplementedError("input_crop_ratio > 1 (zero-padding CenterCrop) is not covered")
         oh, ow = _resize_output_size(ch, cw, self.resize_shape)
-        return ops.crop_resize_aa(x, _center_crop_offset(h, ch), _center_crop_offset(w, cw), ch, cw, oh, ow)
+        # the kernel also leaves max |x_pre[b]| per image on the result for the conv stack's operand scaling
+        return ops.crop_resize_aa(x, _center_crop_offset(h, ch), _center_crop_offset(w, cw), ch, cw, oh, ow,
+                                  with_absmax=not torch.is_grad_enabled() or not x.requires_grad)
 
     # -- a10 ----------------------------------------------------------------------------------------
     def _element_index(self, group_element_dict) -> torch.Tensor:

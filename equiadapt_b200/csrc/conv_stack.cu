@@ -422,7 +422,7 @@ extern "C" int eqb_conv_stack_forward(const float *x, int B, int cin, int H, int
     const __half *tin_hi = nullptr, *tin_lo = nullptr;   // fp16 pair feeding the next tcgen05 layer
     if (p.tc) {
         // operand scales are chained on the device from max |x| (conv_stack_tc.cu)
-        int e = tc_absmax(x, (size_t)B * cin * H * W, (float *)(ws + p.off_absmax), st);
+        int e = tc_absmax(x, 1, (size_t)B * cin * H * W, (float *)(ws + p.off_absmax), st);   // (this stack still scales per call)
         if (e) return e;
     }
     for (int l = 0; l < L; ++l) {

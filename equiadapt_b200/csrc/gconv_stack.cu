@@ -29,7 +29,8 @@ constexpr int GT_PITCH = 68;   // floats per operand row (64 pixels + 4 pad: con
 constexpr int GT_KC = 16;      // K rows per streamed weight chunk
 constexpr int GT_THREADS = 256;
 constexpr int GT_MAX_GEMM = 8;
-constexpr size_t SCRATCH_HEAD = 16;
+// per-call scalars ahead of the partial sums: max |x| of every image (tcgen05 path)
+static inline size_t scratch_head(int B) { return (((size_t)(B > 0 ? B : 1) * sizeof(float)) + 255) & ~(size_t)255; }
 
 struct StackArgs {
     const float *x;
@@ -314,7 +315,7 @@ static int make_plan(int B, int cin, int H, int W, int cout, int k, int N, int r
         if (2 * p.tc2_chunks > max_chunks) max_chunks = 2 * p.tc2_chunks;   // two partial-sum rows per chunk
     }
     p.off_S = off;
-    off += SCRATCH_HEAD;  // per-call scalars ahead of the partial sums: max |x| of the batch (tcgen05 path)
+    off += scratch_head(B);
     off += (size_t)(B > 0 ? B : 1) * max_chunks * p.Npad * sizeof(double);
     p.total = off;
     return 0;
@@ -393,10 +394,9 @@ extern "C" int eqb_gconv_stack_pack(const float *lift_w, const float *lift_b, co
     return 0;
 }
 
-extern "C" int eqb_gconv_stack_run(const float *x, int B, int cin, int H, int W, const void *packed,
-                                   const float *last_bias, int cout, int k, int num_rotations, int reflect,
-                                   int num_layers, float *act, void *scratch, int64_t scratch_bytes, void *stream) {
-    EQB_NVTX_RANGE();
+static int stack_run(const float *x, const float *x_absmax, int B, int cin, int H, int W, const void *packed,
+                     const float *last_bias, int cout, int k, int num_rotations, int reflect, int num_layers, float *act,
+                     void *scratch, int64_t scratch_bytes, void *stream) {
     StackPlan p;
     const int rc = make_plan(B, cin, H, W, cout, k, num_rotations, reflect, num_layers, p);
     if (rc) return rc;
@@ -419,7 +419,7 @@ extern "C" int eqb_gconv_stack_run(const float *x, int B, int cin, int H, int W,
         a.bias[l] = (const float *)(ws + p.off_bias[l]);
         a.Kpad[l] = l == 0 ? p.K0pad : p.Npad;
     }
-    a.S_part = (double *)((char *)scratch + SCRATCH_HEAD);
+    a.S_part = (double *)((char *)scratch + scratch_head(B));
     a.tiles = p.tiles; a.chunks = p.chunks; a.tiles_per_chunk = p.tiles_per_chunk;
     int e, chunks = p.chunks;
     if (p.tc) {
@@ -428,10 +428,14 @@ extern "C" int eqb_gconv_stack_run(const float *x, int B, int cin, int H, int W,
         t.K0 = p.K0; t.N = p.N; t.Npad = p.Npad;
         t.bias1 = a.bias[0]; t.bias2 = a.bias[1];
         t.wpack = (const unsigned char *)(ws + p.off_tc);
-        t.absmax = (const float *)scratch;
         t.S_part = a.S_part;
-        e = tc_absmax(x, (size_t)B * cin * H * W, (float *)scratch, st);
-        if (e) return e;
+        if (x_absmax) {
+            t.absmax = x_absmax;          // the producer of x (eqb_crop_resize_aa_absmax) already reduced max |x| per image
+        } else {
+            t.absmax = (const float *)scratch;
+            e = tc_absmax(x, B, (size_t)cin * H * W, (float *)scratch, st);
+            if (e) return e;
+        }
         t.tiles = p.tc_tiles; t.chunks = p.tc_chunks; t.tiles_per_chunk = p.tc_tiles_per_chunk;
         t.tiles2 = p.tc2_tiles; t.chunks2 = p.tc2_chunks; t.tiles_per_chunk2 = p.tc2_tiles_per_chunk;
         chunks = p.tc_pair ? 2 * p.tc2_chunks : p.tc_chunks;
@@ -452,7 +456,26 @@ extern "C" int eqb_gconv_stack_run(const float *x, int B, int cin, int H, int W,
     return finish_launch("gconv_finish_kernel");
 }
 
+extern "C" int eqb_gconv_stack_run(const float *x, int B, int cin, int H, int W, const void *packed,
+                                   const float *last_bias, int cout, int k, int num_rotations, int reflect,
+                                   int num_layers, float *act, void *scratch, int64_t scratch_bytes, void *stream) {
+    EQB_NVTX_RANGE();
+    return stack_run(x, nullptr, B, cin, H, W, packed, last_bias, cout, k, num_rotations, reflect, num_layers, act, scratch,
+                     scratch_bytes, stream);
+}
+
+extern "C" int eqb_gconv_stack_run_scaled(const float *x, const float *x_absmax, int B, int cin, int H, int W,
+                                          const void *packed, const float *last_bias, int cout, int k, int num_rotations,
+                                          int reflect, int num_layers, float *act, void *scratch, int64_t scratch_bytes,
+                                          void *stream) {
+    EQB_NVTX_RANGE();
+    EQB_REQUIRE(x_absmax, "eqb_gconv_stack_run_scaled: null absmax");
+    return stack_run(x, x_absmax, B, cin, H, W, packed, last_bias, cout, k, num_rotations, reflect, num_layers, act, scratch,
+                     scratch_bytes, stream);
+}
+
 extern "C" int eqb_debug_last_stall(int *out5) { return tc_last_stall(out5); }
+extern "C" int eqb_debug_stack_trace(void *device_buffer, int tiles) { return tc_set_trace((long long *)device_buffer, tiles); }
 
 extern "C" int eqb_gconv_stack_forward(const float *x, int B, int cin, int H, int W, const float *lift_w,
                                        const float *lift_b, const float *const *reg_w, const float *const *reg_b,

@@ -171,6 +171,30 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, float *v) {
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// The same load WITHOUT the wait: the registers are defined only after tc_ld_wait(r) (which carries them as in/out
+// operands, so neither nvcc nor ptxas can schedule a use above the wait).
+__device__ __forceinline__ void tc_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tc_ld_wait(uint32_t (&r)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                   "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]),
+                   "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]),
+                   "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+                 :
+                 : "memory");
+}
+
 // K-major swizzled shared-memory matrix descriptors (cute::UMMA::SmemDescriptor): start address >> 4 in bits [0,14),
 // leading byte offset (unused for swizzled K-major) in [16,30), stride byte offset = 8 rows in [32,46), version 1 in
 // [46,48), layout type in [61,64).
@@ -206,6 +230,33 @@ __host__ __device__ __forceinline__ float pow2_scale(float m) {
     return ldexpf(1.f, 14 - e);
 }
 
+// Packed-buffer header (tc_header_kernel) and the PER-IMAGE operand scales derived from it.  All scales are exact powers
+// of two: the image by ITS OWN max |x| (a.absmax[b]: a sample's activations never depend on its batch-mates, as in the
+// reference, custom_equivariant_networks.py:80-93), the hidden activation by its bound max|x| * R0 + max|b1|.
+struct Hdr {
+    float sw0, sw1, R0, b1max;
+};
+__device__ __forceinline__ Hdr load_hdr(const unsigned char *wpack) {
+    const float *h = reinterpret_cast<const float *>(wpack);
+    Hdr r;
+    r.sw0 = h[0]; r.sw1 = h[1]; r.R0 = h[2]; r.b1max = h[3];
+    return r;
+}
+struct ImageScales {
+    float sx, s1, c1, c2;   // image scale, hidden-activation scale, epilogue-1 factor s1 / (sx sw0), epilogue-2 factor 1 / (s1 sw1)
+};
+__device__ __forceinline__ ImageScales image_scales(const Hdr &h, float amax) {
+    ImageScales r;
+    r.sx = pow2_scale(amax);
+    r.s1 = pow2_scale(amax * h.R0 + h.b1max);
+    r.c1 = r.s1 / (r.sx * h.sw0);
+    r.c2 = 1.f / (r.s1 * h.sw1);
+    return r;
+}
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
@@ -235,7 +286,7 @@ __host__ __device__ inline Smem smem_map(int N, int K0pad) {
     s.a0_ring = o; o += A0_RING * A0_STAGE;               // 32 KB
     s.w_ring = o; o += W_RING * (uint32_t)weight_rows(N) * 64;    // <= 96 KB
     s.koff = o; o += (uint32_t)K0pad * 4;
-    s.bias1 = o; o += (uint32_t)N * 4;
+    s.bias1 = o; o += 2u * (uint32_t)N * 4;                // s1-scaled lift bias, one table per image parity
     s.bias2 = o; o += (uint32_t)N * 4;
     o = (o + 15u) & ~15u;
     s.scal = o; o += 16;                                  // {sx, c1, c2, -}
@@ -327,20 +378,9 @@ __global__ void __launch_bounds__(640, 1) gconv_stack_tc_kernel(const TcArgs a) 
             }
             koff[k] = off;
         }
-        // operand scales (all exact powers of two): image by its per-call maximum, hidden activation by its bound
-        const float *hdr = reinterpret_cast<const float *>(a.wpack);
-        const float sw0 = hdr[0], sw1 = hdr[1], R0 = hdr[2], b1max = hdr[3];
-        const float amax = *a.absmax;
-        const float sx = pow2_scale(amax), s1 = pow2_scale(amax * R0 + b1max);
-        const float c1 = s1 / (sx * sw0), c2 = 1.f / (s1 * sw1);
-        for (int n = threadIdx.x; n < N; n += blockDim.x) {
-            b1[n] = a.bias1[n] * s1;
-            b2[n] = a.bias2[n];
-        }
-        if (threadIdx.x == 0) {
-            float *sc = reinterpret_cast<float *>(sm + M.scal);
-            sc[0] = sx; sc[1] = c1; sc[2] = c2;
-        }
+        // (the operand scales are per IMAGE: every role derives them from a.absmax[b] when it enters a new image)
+        (void)b1;
+        for (int n = threadIdx.x; n < N; n += blockDim.x) b2[n] = a.bias2[n];
     }
     if (warp == 2) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(base + M.tmem_slot), "r"(512)
@@ -488,13 +528,28 @@ __global__ void __launch_bounds__(640, 1) gconv_stack_tc_kernel(const TcArgs a) 
         // as soon as its LAST chunk of the tile is in registers.
         const int grp = warp >= 16 ? 1 : 0, ngrp = a.epi1_groups;
         const int q = warp & 3, row = q * 32 + lane;
-        const float *b1 = reinterpret_cast<const float *>(sm + M.bias1);
-        const float c1 = reinterpret_cast<const float *>(sm + M.scal)[1];
+        float *b1tab = reinterpret_cast<float *>(sm + M.bias1);
+        const float *b1 = b1tab;
+        const Hdr hdr = load_hdr(a.wpack);
+        float c1 = 0.f;
+        int cur_b = -1, par = 1;
         uint32_t tile_phase = 0;
         const uint32_t row_off = (uint32_t)row * 64u, sw = (uint32_t)((row >> 1) & 3);
         const int last_c = NC1 - 1 - ((NC1 - 1 - grp) % ngrp + ngrp) % ngrp;   // last chunk of this group (< grp: none)
         uint32_t seq0 = 0;                                     // sequence number of chunk 0 of the current tile
         for (TileWalk tw(a, items); tw.valid() && grp < ngrp; tw.next()) {
+            if (tw.b != cur_b) {
+                // new image: its scales, and the s1-scaled bias table (double-buffered by image parity: a slower group may
+                // still read the previous image's table; the named barrier keeps the groups at most one image apart)
+                cur_b = tw.b;
+                par ^= 1;
+                const ImageScales sc = image_scales(hdr, __ldg(a.absmax + cur_b));
+                c1 = sc.c1;
+                float *tab = b1tab + par * N;
+                for (int n = grp * 128 + row; n < N; n += 128 * ngrp) tab[n] = __ldg(a.bias1 + n) * sc.s1;
+                named_bar_sync(1, 128 * ngrp);
+                b1 = tab;
+            }
             mbar_wait(bar(B_D1FULL), tile_phase, B_D1FULL);
             tc_fence_after();
             if (last_c < grp) {
@@ -534,7 +589,7 @@ __global__ void __launch_bounds__(640, 1) gconv_stack_tc_kernel(const TcArgs a) 
         // ===== epilogue 2: D2t -> relu(. + b2) -> sum over the valid pixels of this thread's channel ==========
         const int q = warp & 3;
         const float *b2 = reinterpret_cast<const float *>(sm + M.bias2);
-        const float c2 = reinterpret_cast<const float *>(sm + M.scal)[2];
+        const Hdr hdr = load_hdr(a.wpack);
         float bias[2];
         int chan[2];
 #pragma unroll
@@ -546,6 +601,7 @@ __global__ void __launch_bounds__(640, 1) gconv_stack_tc_kernel(const TcArgs a) 
         for (int it = blockIdx.x; it < items; it += gridDim.x) {
             const int b = it / a.chunks, ch = it % a.chunks;
             const int t0 = ch * a.tiles_per_chunk, t1 = min(a.tiles, t0 + a.tiles_per_chunk);
+            const float c2 = image_scales(hdr, __ldg(a.absmax + b)).c2;
             double dacc[2] = {0.0, 0.0};
             for (int t = t0; t < t1; ++t) {
                 const int nvalid = min(TILE_M, a.P - t * TILE_M);  // pixel columns of this tile inside the image
@@ -593,7 +649,8 @@ __global__ void __launch_bounds__(640, 1) gconv_stack_tc_kernel(const TcArgs a) 
         // ===== im2col producers: A0 = scaled patches of the next tile, fp16 hi/lo split, into the A0 ring =====
         const int row = (warp - 12) * 32 + lane;
         const int *koff = reinterpret_cast<const int *>(sm + M.koff);
-        const float sx = reinterpret_cast<const float *>(sm + M.scal)[0];
+        float sx = 1.f;
+        int cur_b = -1;
         Ring<A0_RING> ar;
         const uint32_t row_off = (uint32_t)row * 32u, sw = (uint32_t)((row >> 2) & 1);
         // loads of slab s+1 are in flight while slab s is converted and stored (global latency off the critical path)
@@ -616,6 +673,10 @@ __global__ void __launch_bounds__(640, 1) gconv_stack_tc_kernel(const TcArgs a) 
         float xn[SLAB_K];
         if (tw.valid()) load_slab(xp, valid, 0, xn);
         while (tw.valid()) {
+            if (tw.b != cur_b) {
+                cur_b = tw.b;
+                sx = pow2_scale(__ldg(a.absmax + cur_b));
+            }
             for (int sl = 0; sl < NS0; ++sl) {
                 float x[SLAB_K];
 #pragma unroll
@@ -688,7 +749,7 @@ constexpr int A0_RING = 3, A1_RING = 2;
 constexpr int W1_ATOM = 2 * 128 * 64;      // hi + lo image of one 32-wide K atom of this CTA's 128 channels: 16 KB
 constexpr int W0_SLAB = 2 * 128 * 32;      // hi + lo image of one 16-wide K slab: 8 KB
 enum { B_A0FULL = 0, B_A0EMPTY = B_A0FULL + A0_RING, B_A1FULL = B_A0EMPTY + A0_RING, B_A1EMPTY = B_A1FULL + A1_RING,
-       B_D1FULL = B_A1EMPTY + A1_RING, B_D1EMPTY, B_D2FULL, B_D2EMPTY, B_WLOAD, B_COUNT };
+       B_D1FULL = B_A1EMPTY + A1_RING, B_D1EMPTY, B_D2FULL, B_D2EMPTY, B_WLOAD, B_G2ISSUED, B_COUNT };
 
 struct Smem {
     uint32_t w1, w0, a1_ring, a0_ring, koff, bias1, bias2, scal, bars, tmem_slot, total;
@@ -701,7 +762,7 @@ __host__ __device__ inline Smem smem_map(int K0pad) {
     s.a1_ring = o; o += A1_RING * A1_STAGE;                  // 32 KB
     s.a0_ring = o; o += A0_RING * A0_STAGE;                  // 24 KB
     s.koff = o; o += (uint32_t)K0pad * 4;
-    s.bias1 = o; o += 256 * 4;
+    s.bias1 = o; o += 2 * 256 * 4;                           // s1-scaled lift bias, one table per image parity
     s.bias2 = o; o += 128 * 4;
     s.scal = o; o += 16;
     s.bars = o; o += B_COUNT * 8;
@@ -771,6 +832,17 @@ __device__ __forceinline__ void tc_mma2_f16_lo(uint32_t d_tmem, uint32_t a_lo, u
         : "memory");
 }
 
+// TR(slot): debug timeline, compiled only into the TRACE instantiation (the production kernel carries none of it).
+// Slots per tile: 0 1x1-issuer starts waiting for D2EMPTY, 1 has it, 2-9 A1FULL of atom 0-7 seen (MMAs issued right after);
+// 10 lift issuer starts waiting (G2ISSUED + D1EMPTY), 11 has both, 12-16 A0FULL of slab 0-4 seen; 17 epilogue-1 group 0 sees
+// D1FULL, 18-21 its chunks loaded, 22-25 their A1EMPTY seen; 26 / 27-30 / 31-34 the same for group 1; 35 epilogue-2 group 0
+// sees D2FULL, 36 releases D2t, 37 done; 38-40 the same for group 1; 41-45 im2col: A0EMPTY seen per slab.
+#define TR(slot)                                                                                              \
+    do {                                                                                                      \
+        if (TRACE && trace_on && lane == 0 && tn < a.trace_tiles) a.trace[(size_t)tn * 64 + (slot)] = clock64(); \
+    } while (0)
+
+template <bool TRACE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(768, 1) gconv_stack_pair_kernel(const TcArgs a) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const uint32_t base = smem_u32(smem_raw);
@@ -800,6 +872,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(768, 1) gconv_stack_
         mbar_init(bar(B_D2FULL), 1);
         mbar_init(bar(B_D2EMPTY), 512);      // two epilogue-2 groups of 128 threads in each CTA
         mbar_init(bar(B_WLOAD), 1);
+        mbar_init(bar(B_G2ISSUED), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         // stationary weights: this CTA's 128-channel halves of the packed hi / lo images (layout of tc_pack: a
         // stage = 256 rows; rows [128 rank, +128) of an image are one contiguous, identically swizzled block)
@@ -829,17 +902,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(768, 1) gconv_stack_
             }
             koff[k] = off;
         }
-        const float *hdr = reinterpret_cast<const float *>(a.wpack);
-        const float sw0 = hdr[0], sw1 = hdr[1], R0 = hdr[2], b1max = hdr[3];
-        const float amax = *a.absmax;
-        const float sx = pow2_scale(amax), s1 = pow2_scale(amax * R0 + b1max);
-        const float c1 = s1 / (sx * sw0), c2 = 1.f / (s1 * sw1);
-        for (int n = threadIdx.x; n < 256; n += blockDim.x) b1[n] = a.bias1[n] * s1;
+        // (the operand scales are per IMAGE: every role derives them from a.absmax[b] when it enters a new image)
+        (void)b1;
         for (int n = threadIdx.x; n < 128; n += blockDim.x) b2[n] = a.bias2[128 * rank + n];
-        if (threadIdx.x == 0) {
-            float *sc = reinterpret_cast<float *>(sm + M.scal);
-            sc[0] = sx; sc[1] = c1; sc[2] = c2;
-        }
     }
     if (warp == 2) {
         asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(base + M.tmem_slot), "r"(512)
@@ -856,6 +921,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(768, 1) gconv_stack_
 
     const int items = a.B * a.chunks2;
     const int cid = (int)blockIdx.x >> 1, ncl = (int)gridDim.x >> 1;
+    const bool trace_on = TRACE && a.trace != nullptr && cid == 0 && rank == 0;
+    int tn = 0;                                  // this role's tile counter (trace rows)
     auto walk = [&]() { return TileWalk(a.tiles2, a.chunks2, a.tiles_per_chunk2, items, cid, ncl); };
     // barriers of the leader CTA, as seen from this CTA (cluster address space)
     auto leader_bar = [&](int i) { return map_to_rank(bar(i), 0); };
@@ -871,11 +938,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(768, 1) gconv_stack_
             Ring<A0_RING> r0;
             uint32_t lift_phase = 0;
             const uint32_t a0_lo0 = desc_lo(base + M.a0_ring), w0_lo0 = desc_lo(base + M.w0);
-            for (TileWalk tw = walk(); tw.valid(); tw.next()) {
+            uint32_t tile_no = 0;
+            for (TileWalk tw = walk(); tw.valid(); tw.next(), ++tile_no) {
+                // Order on the (in-order) tensor pipe: ... 1x1 GEMM(t) | lift(t+1) | 1x1 GEMM(t+1) ...  The lift of the next
+                // tile is queued right BEHIND the last 1x1 MMA of the current one, so it executes while epilogue 2 drains
+                // D2t (the only time the pipe would otherwise idle: TMEM is full, D2t cannot be double-buffered).  Issued
+                // any earlier it merely interleaves with the 1x1 MMAs and leaves the drain exposed (profiles/r2_stack.md).
+                TR(10);
+                if (a.lift_after_gemm && tile_no > 0) mbar_wait(bar(B_G2ISSUED), (tile_no - 1u) & 1u, B_G2ISSUED);
                 mbar_wait_cluster(bar(B_D1EMPTY), lift_phase ^ 1u, B_D1EMPTY);
+                TR(11);
                 lift_phase ^= 1u;
                 for (int sl = 0; sl < NS0; ++sl) {
                     mbar_wait_cluster(bar(B_A0FULL + r0.stage), r0.phase, B_A0FULL + r0.stage);
+                    TR(12 + sl);
                     tc_fence_after();
                     if (elect_one()) {
                         const uint32_t a_hi = a0_lo0 + (uint32_t)r0.stage * (A0_STAGE >> 4), a_lo = a_hi + (A0_HALF >> 4);
@@ -889,6 +965,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(768, 1) gconv_stack_
                     __syncwarp();
                     r0.advance();
                 }
+                ++tn;
             }
         }
     } else if (warp == 1) {
@@ -898,9 +975,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(768, 1) gconv_stack_
             uint32_t tile_phase = 0;
             const uint32_t a1_lo0 = desc_lo(base + M.a1_ring), w1_lo0 = desc_lo(base + M.w1);
             for (TileWalk tw = walk(); tw.valid(); tw.next()) {
+                TR(0);
                 mbar_wait_cluster(bar(B_D2EMPTY), tile_phase ^ 1u, B_D2EMPTY);
+                TR(1);
                 for (int kc = 0; kc < NC1; ++kc) {
                     mbar_wait_cluster(bar(B_A1FULL + r1.stage), r1.phase, B_A1FULL + r1.stage);
+                    TR(2 + kc);
                     tc_fence_after();
                     if (elect_one()) {
                         const uint32_t a_hi = a1_lo0 + (uint32_t)r1.stage * (A1_STAGE >> 4), a_lo = a_hi + (A1_HALF >> 4);
@@ -913,12 +993,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(768, 1) gconv_stack_
 #pragma unroll
                         for (int j = 0; j < 2; ++j) tc_mma2_f16_lo<DESC_HI_64B>(tmem_d2, w_lo + 2 * j, a_hi + 2 * j, idesc, 1);
                         tc_commit2(bar(B_A1EMPTY + r1.stage));
-                        if (kc == NC1 - 1) tc_commit2(bar(B_D2FULL));
+                        if (kc == NC1 - 1) {
+                            tc_commit2(bar(B_D2FULL));
+                            mbar_arrive(bar(B_G2ISSUED));      // the lift issuer may queue the next tile's lift now
+                        }
                     }
                     __syncwarp();
                     r1.advance();
                 }
                 tile_phase ^= 1u;
+                ++tn;
             }
         }
     } else if ((warp >= 4 && warp < 8) || (warp >= 16 && warp < 20)) {
@@ -926,8 +1010,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(768, 1) gconv_stack_
         const int grp = warp >= 16 ? 1 : 0;
         if (grp < groups) {
             const int q = warp & 3, row = q * 32 + lane;
-            const float *b1 = reinterpret_cast<const float *>(sm + M.bias1);
-            const float c1 = reinterpret_cast<const float *>(sm + M.scal)[1];
+            float *b1tab = reinterpret_cast<float *>(sm + M.bias1);
+            const float *b1 = b1tab;
+            const Hdr hdr = load_hdr(a.wpack);
+            float c1 = 0.f;
+            int cur_b = -1, par = 1;
             uint32_t tile_phase = 0;
             const uint32_t row_off = (uint32_t)row * 64u, sw = (uint32_t)((row >> 1) & 3);
             const int last_c = NC1 - 1 - ((NC1 - 1 - grp) % groups + groups) % groups;
@@ -935,11 +1022,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(768, 1) gconv_stack_
             const uint32_t d1empty = leader_bar(B_D1EMPTY);
             const uint32_t a1full0 = leader_bar(B_A1FULL);   // barriers are 8 bytes apart in the leader's window too
             for (TileWalk tw = walk(); tw.valid(); tw.next()) {
+                if (tw.b != cur_b) {
+                    // new image: its scales and the s1-scaled bias table (see the single-CTA kernel)
+                    cur_b = tw.b;
+                    par ^= 1;
+                    const ImageScales sc = image_scales(hdr, __ldg(a.absmax + cur_b));
+                    c1 = sc.c1;
+                    float *tab = b1tab + par * 256;
+                    for (int n = grp * 128 + row; n < 256; n += 128 * groups) tab[n] = __ldg(a.bias1 + n) * sc.s1;
+                    named_bar_sync(1, 128 * groups);
+                    b1 = tab;
+                }
                 mbar_wait(bar(B_D1FULL), tile_phase, B_D1FULL);
+                if (q == 0) TR(17 + 9 * grp);
                 tc_fence_after();
                 for (int c = grp; c < NC1; c += groups) {
                     float v[32];
                     tc_ld32(tmem_d1 + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+                    if (q == 0) TR(18 + 9 * grp + (c >> 1));
                     if (c == last_c) {
                         tc_fence_before();
                         mbar_arrive_cluster(d1empty);
@@ -953,6 +1053,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(768, 1) gconv_stack_
                     }
                     const uint32_t seq = seq0 + (uint32_t)c, stage = seq % A1_RING, phase = (seq / A1_RING) & 1u;
                     mbar_wait(bar(B_A1EMPTY + stage), phase ^ 1u, B_A1EMPTY + stage);
+                    if (q == 0) TR(22 + 9 * grp + (c >> 1));
                     const uint32_t hi_row = base + M.a1_ring + stage * A1_STAGE + row_off, lo_row = hi_row + A1_HALF;
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
@@ -965,6 +1066,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(768, 1) gconv_stack_
                 }
                 seq0 += (uint32_t)NC1;
                 tile_phase ^= 1u;
+                ++tn;
             }
         }
     } else if ((warp >= 8 && warp < 12) || (warp >= 20 && warp < 24)) {
@@ -973,7 +1075,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(768, 1) gconv_stack_
         // the critical path between two 1x1 GEMMs); each group emits its own partial-sum row
         const int grp = warp >= 20 ? 1 : 0;
         const int q = warp & 3;
-        const float c2 = reinterpret_cast<const float *>(sm + M.scal)[2];
+        const Hdr hdr = load_hdr(a.wpack);
         const float bv = reinterpret_cast<const float *>(sm + M.bias2)[q * 32 + lane];
         const int chan = 128 * (int)rank + q * 32 + lane;
         const uint32_t d2empty = leader_bar(B_D2EMPTY);
@@ -981,36 +1083,80 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(768, 1) gconv_stack_
         TileWalk tw = walk();
         while (tw.valid()) {
             const int b = tw.b, ch = tw.ch;
+            const float c2 = image_scales(hdr, __ldg(a.absmax + b)).c2;
             double dacc = 0.0;
             bool item_done = false;
             while (!item_done) {
                 const int nvalid = min(256, a.P - tw.t * 256) - 128 * grp;   // valid columns of this group's half
                 mbar_wait(bar(B_D2FULL), tile_phase, B_D2FULL);
+                if (q == 0) TR(35 + 3 * grp);
                 tc_fence_after();
                 float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+                const uint32_t t0 = tmem_d2 + ((uint32_t)(q * 32) << 16) + (uint32_t)(128 * grp);
+                auto add_chunk = [&](const uint32_t (&r)[32], int c) {
+                    if (c * 32 + 32 <= nvalid) {
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    if (c * 32 < nvalid) {  // (uniform)
-                        float v[32];
-                        tc_ld32(tmem_d2 + ((uint32_t)(q * 32) << 16) + (uint32_t)(128 * grp + c * 32), v);
-                        if (c * 32 + 32 <= nvalid) {
+                        for (int i = 0; i < 32; i += 4) {
+                            s0 += fmaxf(fmaf(__uint_as_float(r[i]), c2, bv), 0.f);
+                            s1 += fmaxf(fmaf(__uint_as_float(r[i + 1]), c2, bv), 0.f);
+                            s2 += fmaxf(fmaf(__uint_as_float(r[i + 2]), c2, bv), 0.f);
+                            s3 += fmaxf(fmaf(__uint_as_float(r[i + 3]), c2, bv), 0.f);
+                        }
+                    } else {
 #pragma unroll
-                            for (int i = 0; i < 32; i += 4) {
-                                s0 += fmaxf(fmaf(v[i], c2, bv), 0.f);
-                                s1 += fmaxf(fmaf(v[i + 1], c2, bv), 0.f);
-                                s2 += fmaxf(fmaf(v[i + 2], c2, bv), 0.f);
-                                s3 += fmaxf(fmaf(v[i + 3], c2, bv), 0.f);
+                        for (int i = 0; i < 32; ++i)
+                            if (c * 32 + i < nvalid) s0 += fmaxf(fmaf(__uint_as_float(r[i]), c2, bv), 0.f);
+                    }
+                };
+                // D2t is free for the next 1x1 GEMM the moment this thread's LAST chunk sits in registers
+                auto release = [&]() {
+                    tc_fence_before();
+                    mbar_arrive_cluster(d2empty);
+                    if (q == 0) TR(36 + 3 * grp);
+                };
+                if (a.epi2_pipelined) {
+                    // chunk c+1 is in flight (tcgen05.ld is asynchronous until wait::ld) while chunk c is summed
+                    const int nch = nvalid <= 0 ? 0 : (nvalid >= 128 ? 4 : (nvalid + 31) >> 5);   // (uniform)
+                    uint32_t ra[32], rb[32];
+                    if (nch == 0) {
+                        release();
+                    } else {
+                        tc_ld32_issue(t0, ra);
+                        tc_ld_wait(ra);
+                        if (nch > 1) tc_ld32_issue(t0 + 32u, rb); else release();
+                        add_chunk(ra, 0);
+                        if (nch > 1) {
+                            tc_ld_wait(rb);
+                            if (nch > 2) tc_ld32_issue(t0 + 64u, ra); else release();
+                            add_chunk(rb, 1);
+                            if (nch > 2) {
+                                tc_ld_wait(ra);
+                                if (nch > 3) tc_ld32_issue(t0 + 96u, rb); else release();
+                                add_chunk(ra, 2);
+                                if (nch > 3) {
+                                    tc_ld_wait(rb);
+                                    release();
+                                    add_chunk(rb, 3);
+                                }
                             }
-                        } else {
-#pragma unroll
-                            for (int i = 0; i < 32; ++i)
-                                if (c * 32 + i < nvalid) s0 += fmaxf(fmaf(v[i], c2, bv), 0.f);
                         }
                     }
+                    dacc += (double)((s0 + s1) + (s2 + s3));
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        if (c * 32 < nvalid) {  // (uniform)
+                            uint32_t r[32];
+                            tc_ld32_issue(t0 + (uint32_t)(c * 32), r);
+                            tc_ld_wait(r);
+                            add_chunk(r, c);
+                        }
+                    }
+                    dacc += (double)((s0 + s1) + (s2 + s3));
+                    release();
                 }
-                dacc += (double)((s0 + s1) + (s2 + s3));
-                tc_fence_before();
-                mbar_arrive_cluster(d2empty);
+                if (q == 0) TR(37 + 3 * grp);
+                ++tn;
                 tile_phase ^= 1u;
                 item_done = tw.last_of_item();
                 tw.next();
@@ -1021,7 +1167,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(768, 1) gconv_stack_
         // ===== im2col producers: this CTA's 128 pixels of the pair-tile ============================================
         const int row = (warp - 12) * 32 + lane;
         const int *koff = reinterpret_cast<const int *>(sm + M.koff);
-        const float sx = reinterpret_cast<const float *>(sm + M.scal)[0];
+        float sx = 1.f;
+        int cur_b = -1;
         Ring<A0_RING> ar;
         const uint32_t row_off = (uint32_t)row * 32u, sw = (uint32_t)((row >> 2) & 1);
         const uint32_t a0full0 = leader_bar(B_A0FULL);
@@ -1044,6 +1191,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(768, 1) gconv_stack_
         float xn[SLAB_K];
         if (tw.valid()) load_slab(xp, valid, 0, xn);
         while (tw.valid()) {
+            if (tw.b != cur_b) {
+                cur_b = tw.b;
+                sx = pow2_scale(__ldg(a.absmax + cur_b));
+            }
             for (int sl = 0; sl < NS0; ++sl) {
                 float x[SLAB_K];
 #pragma unroll
@@ -1061,6 +1212,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(768, 1) gconv_stack_
 #pragma unroll
                 for (int i = 0; i < 8; ++i) split2(x[2 * i], x[2 * i + 1], hi[i], lo[i]);
                 mbar_wait(bar(B_A0EMPTY + ar.stage), ar.phase ^ 1u, B_A0EMPTY + ar.stage);
+                if (warp == 12) TR(41 + sl);
                 const uint32_t hi_row = base + M.a0_ring + ar.stage * A0_STAGE + row_off, lo_row = hi_row + A0_HALF;
 #pragma unroll
                 for (int j = 0; j < 2; ++j) {
@@ -1072,8 +1224,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(768, 1) gconv_stack_
                 mbar_arrive_cluster(a0full0 + 8u * (uint32_t)ar.stage);
                 ar.advance();
             }
+            ++tn;
         }
     }
+#undef TR
 
     // ---- teardown -------------------------------------------------------------------------------------------
     tc_fence_before();
@@ -1157,24 +1311,30 @@ __global__ void pack_tc_lift_kernel(const float *__restrict__ Wt, int K, int Npa
     }
 }
 
-// max |x| over n floats -> *out (must be zeroed first); non-negative floats order like their bit patterns
+// out[b] = max |x[b]| over the n floats of image b (out zeroed first); grid (blocks per image, B); non-negative floats
+// order like their bit patterns, NaN -> +inf (so a NaN image poisons only ITS OWN scale)
 __global__ void __launch_bounds__(256) absmax_kernel(const float *__restrict__ x, size_t n, int vec,
                                                      float *__restrict__ out) {
+    const float *xb = x + (size_t)blockIdx.y * n;
     float m = 0.f;
     const size_t n4 = vec ? n / 4 : 0, stride = (size_t)gridDim.x * blockDim.x;
-    const float4 *x4 = reinterpret_cast<const float4 *>(x);
+    const float4 *x4 = reinterpret_cast<const float4 *>(xb);
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
         const float4 v = __ldg(x4 + i);
         m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+        if (!(v.x == v.x) || !(v.y == v.y) || !(v.z == v.z) || !(v.w == v.w)) m = __int_as_float(0x7f800000);
     }
-    for (size_t i = n4 * 4 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) m = fmaxf(m, fabsf(x[i]));
+    for (size_t i = n4 * 4 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        m = fmaxf(m, fabsf(xb[i]));
+        if (!(xb[i] == xb[i])) m = __int_as_float(0x7f800000);
+    }
     for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
     __shared__ float red[8];
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
     __syncthreads();
     if (threadIdx.x == 0) {
         for (int w = 1; w < 8; ++w) m = fmaxf(m, red[w]);
-        atomicMax(reinterpret_cast<unsigned int *>(out), __float_as_uint(m));
+        atomicMax(reinterpret_cast<unsigned int *>(out + blockIdx.y), __float_as_uint(m));
     }
 }
 
@@ -1209,17 +1369,30 @@ int tc_pack(const float *Wt0, int K0, const float *Wt1, const float *bias1, int 
     return finish_launch("pack_tc_weights");
 }
 
-int tc_absmax(const float *x, size_t n, float *absmax, cudaStream_t st) {
-    EQB_CUDA(cudaMemsetAsync(absmax, 0, sizeof(float), st));
-    size_t blocks = (n / 4 + 255) / 256;
-    const size_t cap = (size_t)num_sms() * 8;
-    if (blocks > cap) blocks = cap;
-    if (blocks < 1) blocks = 1;
-    tc::absmax_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, n, ((uintptr_t)x & 15) == 0, absmax);
+int tc_absmax(const float *x, int B, size_t n, float *absmax, cudaStream_t st) {
+    EQB_CUDA(cudaMemsetAsync(absmax, 0, (size_t)B * sizeof(float), st));
+    // a few blocks per image when the batch alone cannot fill the GPU; the float4 path needs every image 16-byte aligned
+    size_t per = (n / 4 + 255) / 256;
+    const size_t want = ((size_t)num_sms() * 8 + B - 1) / (size_t)B;
+    if (per > want) per = want;
+    if (per < 1) per = 1;
+    const int vec = ((uintptr_t)x & 15) == 0 && (n & 3) == 0;
+    for (int b0 = 0; b0 < B; b0 += 65535) {
+        const int nb = B - b0 < 65535 ? B - b0 : 65535;
+        tc::absmax_kernel<<<dim3((unsigned)per, (unsigned)nb), 256, 0, st>>>(x + (size_t)b0 * n, n, vec, absmax + b0);
+    }
     return finish_launch("absmax_kernel");
 }
 
 static int *g_stall_host = nullptr;
+static long long *g_trace = nullptr;
+static int g_trace_tiles = 0;
+
+int tc_set_trace(long long *device_buffer, int tiles) {
+    g_trace = device_buffer;
+    g_trace_tiles = device_buffer ? tiles : 0;
+    return 0;
+}
 
 int tc_last_stall(int *out5) {
     if (!g_stall_host) return 0;
@@ -1247,16 +1420,27 @@ int tc_launch(TcArgs a, cudaStream_t st) {
         // CTA-pair kernel: one cluster of two CTAs per TPC, stationary weights
         a.epi1_groups = eg && eg[0] == '1' ? 1 : 2;
         a.lift_early = le && le[0] == '1' ? 1 : 0;
+        // A/B knobs, default OFF: both were measured SLOWER on B200 (1 416 -> 1 447 / 1 473 us, profiles/r2_stack.md): queuing
+        // the lift behind the 1x1 GEMM hides the D2t drain but exposes the ~1 500 cycles epilogue 1 needs to deliver the
+        // first A1 atom after D1FULL, and the drain is not bound by the latency of tcgen05.ld
+        const char *lo = getenv("EQB_TC_LIFT_ORDER"), *ep = getenv("EQB_TC_EPI2_PIPE");
+        a.lift_after_gemm = lo && lo[0] == '1' ? 1 : 0;
+        a.epi2_pipelined = ep && ep[0] == '1' ? 1 : 0;
         const tc::pair::Smem M = tc::pair::smem_map(a.K0pad);
         EQB_UNSUPPORTED(M.total > 227 * 1024, "gconv_stack (tcgen05 pair): shared-memory plan of %u bytes does not fit", M.total);
         static PerDeviceOnce configured2;
         if (configured2.first()) {
-            EQB_CUDA(cudaFuncSetAttribute(tc::pair::gconv_stack_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            EQB_CUDA(cudaFuncSetAttribute(tc::pair::gconv_stack_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          227 * 1024));
+            EQB_CUDA(cudaFuncSetAttribute(tc::pair::gconv_stack_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           227 * 1024));
         }
         const int items2 = a.B * a.chunks2, max_clusters = num_sms() / 2;
         const int clusters = items2 < max_clusters ? items2 : max_clusters;
-        tc::pair::gconv_stack_pair_kernel<<<2 * clusters, 768, M.total, st>>>(a);
+        a.trace = g_trace;
+        a.trace_tiles = g_trace_tiles;
+        if (a.trace) tc::pair::gconv_stack_pair_kernel<true><<<2 * clusters, 768, M.total, st>>>(a);
+        else tc::pair::gconv_stack_pair_kernel<false><<<2 * clusters, 768, M.total, st>>>(a);
         return finish_launch("gconv_stack_pair_kernel");
     }
     a.epi1_groups = eg && eg[0] == '2' ? 2 : 1;

@@ -11,11 +11,14 @@ struct TcArgs {
     int K0, K0pad, N, Npad;      // lift K = cin*k*k (padded to 32), N = Cout*|G|, Npad = stride of bias / S_part rows
     const float *bias1, *bias2;  // expanded biases (Npad)
     const unsigned char *wpack;  // header + fp16 UMMA weight images (tc_pack)
-    const float *absmax;         // device scalar: max |x| over this call's batch (tc_absmax)
+    const float *absmax;         // (B) device floats: max |x| of every image (tc_absmax or eqb_crop_resize_aa_absmax)
     double *S_part;              // [B][chunks][Npad] channel sums of the last executed layer
     int tiles, chunks, tiles_per_chunk;  // 128-pixel tiles per image, grouped into chunks (= work items)
     int tiles2, chunks2, tiles_per_chunk2;  // the same in 256-pixel pair-tiles (CTA-pair kernel)
     int epi1_groups, lift_early;         // pipeline shape (set by tc_launch)
+    long long *trace;            // debug timeline (eqb_debug_stack_trace): [tile][64 slots] of clock64() from cluster 0 / CTA 0, or null
+    int trace_tiles;
+    int lift_after_gemm, epi2_pipelined; // CTA-pair kernel: lift of tile t+1 queued behind the last 1x1 MMA of tile t; LDTM of chunk c+1 in flight while chunk c is summed
 };
 
 bool tc_eligible(int N, int K0, int n_gemm);
@@ -24,8 +27,9 @@ size_t tc_pack_bytes(int N, int K0);
 // Wt0 [K0pad][Npad], Wt1 [Npad][Npad]: K-major fp32 operands built by the filter-orbit kernels; bias1: expanded (Npad)
 int tc_pack(const float *Wt0, int K0, const float *Wt1, const float *bias1, int Npad, int N, unsigned char *out,
             cudaStream_t st);
-int tc_absmax(const float *x, size_t n, float *absmax, cudaStream_t st);
+int tc_absmax(const float *x, int B, size_t n_per_image, float *absmax, cudaStream_t st);   // absmax[b] = max |x[b]|
 int tc_launch(TcArgs a, cudaStream_t st);
+int tc_set_trace(long long *device_buffer, int tiles);   // next CTA-pair launches record a timeline (null: off)
 int tc_last_stall(int *out5);  // {flag, block, warp, barrier id, parity} of the first pipeline stall that trapped
 
 }  // namespace eqb

@@ -1,5 +1,7 @@
 // Shared declarations of the group-action resampling kernels (resample.cu: generic path, resample_tma.cu: TMA path).
 #pragma once
+#include <cuda.h>
+
 #include "common.cuh"
 
 namespace eqb {
@@ -55,5 +57,9 @@ __device__ __forceinline__ void group_cs(const ResampleArgs &a, int r, double si
 // *handled = 0 (launching nothing) when the tensor does not meet the TMA layout rules (16-byte aligned base,
 // row pitch a multiple of 16 bytes, at least one 52x48 box) so that the caller takes the generic kernel.
 int launch_resample_tma(const ResampleArgs &a, int n_dst_samples, cudaStream_t st, const char *what, int *handled);
+
+// 3-D tensor map over a contiguous fp32 (planes, H, W) tensor with a (box_w, box_h, 1) box (resample_tma.cu)
+int make_plane_map(CUtensorMap *m, const float *src, int W, int H, long long planes, int box_w, int box_h,
+                   CUtensorMapSwizzle swz);
 
 }  // namespace eqb

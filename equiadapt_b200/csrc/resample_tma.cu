@@ -329,7 +329,7 @@ static EncodeTiledFn encode_tiled_fn() {
     return fn;
 }
 
-static int make_plane_map(CUtensorMap *m, const float *src, int W, int H, long long planes, int box_w, int box_h,
+int make_plane_map(CUtensorMap *m, const float *src, int W, int H, long long planes, int box_w, int box_h,
                           CUtensorMapSwizzle swz) {
     EncodeTiledFn enc = encode_tiled_fn();
     if (!enc) {

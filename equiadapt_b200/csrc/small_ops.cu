@@ -1,6 +1,7 @@
 // Latency-bound pieces of the hot path: pre-network crop+resize (a3), filter orbits (a4/a5),
 // group pool / select + prior statistic (a9/a13), cosine activations (a12), frames (a14..a17).
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <algorithm>
 
@@ -483,9 +484,14 @@ using namespace eqb;
 extern "C" int eqb_abi_version(void) { return EQB_ABI_VERSION; }
 extern "C" const char *eqb_last_error(void) { return g_err; }
 
-extern "C" int eqb_crop_resize_aa(const float *x, float *y, int B, int C, int H, int W, int top, int left, int crop_h,
-                                  int crop_w, int out_h, int out_w, void *stream) {
-    EQB_NVTX_RANGE();
+namespace eqb {
+int launch_crop_resize_tma(const float *x, float *y, float *amax, int B, int C, int H, int W, int top, int left, int ch,
+                           int cw, int oh, int ow, cudaStream_t st, int *handled);   // crop_resize_tma.cu
+int tc_absmax(const float *x, int B, size_t n_per_image, float *absmax, cudaStream_t st);   // gconv_stack_tc.cu
+}
+
+static int crop_resize(const float *x, float *y, float *amax, int B, int C, int H, int W, int top, int left, int crop_h,
+                       int crop_w, int out_h, int out_w, void *stream) {
     EQB_REQUIRE(B >= 0 && C > 0 && H > 0 && W > 0 && out_h > 0 && out_w > 0, "eqb_crop_resize_aa: bad shape");
     EQB_REQUIRE(top >= 0 && left >= 0 && crop_h > 0 && crop_w > 0 && top + crop_h <= H && left + crop_w <= W,
                 "eqb_crop_resize_aa: crop window [%d+%d, %d+%d] outside %dx%d", top, crop_h, left, crop_w, H, W);
@@ -495,6 +501,15 @@ extern "C" int eqb_crop_resize_aa(const float *x, float *y, int B, int C, int H,
                     "eqb_crop_resize_aa: down-scale factor above %d not supported", (AA_MAX_TAPS - 2) / 2);
     if (B == 0) return 0;
     EQB_REQUIRE(x && y, "eqb_crop_resize_aa: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (amax) EQB_CUDA(cudaMemsetAsync(amax, 0, (size_t)B * sizeof(float), st));
+    // TMA-staged kernel (crop_resize_tma.cu) when the tensor meets the TMA layout rules; same bits as the scalar kernel
+    if (!getenv("EQB_RESIZE_SCALAR")) {
+        int handled = 0;
+        const int e = launch_crop_resize_tma(x, y, amax, B, C, H, W, top, left, crop_h, crop_w, out_h, out_w, st, &handled);
+        if (e) return e;
+        if (handled) return 0;
+    }
     const int bands = (out_h + RS_ROWS - 1) / RS_ROWS, chunks = (out_w + RS_COLS - 1) / RS_COLS;
     const long long blocks = (long long)B * C * bands * chunks;
     EQB_REQUIRE(blocks < (1LL << 31), "eqb_crop_resize_aa: grid too large");
@@ -507,9 +522,24 @@ extern "C" int eqb_crop_resize_aa(const float *x, float *y, int B, int C, int H,
     const bool narrow = (int)(2 * sup_x + 2) <= 6;
     auto kern = narrow ? crop_resize_aa_kernel<6> : crop_resize_aa_kernel<AA_MAX_TAPS>;
     if (smem > 48 * 1024) EQB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<(unsigned)blocks, block, smem, (cudaStream_t)stream>>>(x, y, H, W, top, left, crop_h, crop_w, out_h, out_w, sy,
-                                                                 sx, bands, chunks, strip_rows);
-    return finish_launch("eqb_crop_resize_aa");
+    kern<<<(unsigned)blocks, block, smem, st>>>(x, y, H, W, top, left, crop_h, crop_w, out_h, out_w, sy, sx, bands, chunks,
+                                                strip_rows);
+    int e = finish_launch("eqb_crop_resize_aa");
+    if (e || !amax) return e;
+    return tc_absmax(y, B, (size_t)C * out_h * out_w, amax, st);
+}
+
+extern "C" int eqb_crop_resize_aa(const float *x, float *y, int B, int C, int H, int W, int top, int left, int crop_h,
+                                  int crop_w, int out_h, int out_w, void *stream) {
+    EQB_NVTX_RANGE();
+    return crop_resize(x, y, nullptr, B, C, H, W, top, left, crop_h, crop_w, out_h, out_w, stream);
+}
+
+extern "C" int eqb_crop_resize_aa_absmax(const float *x, float *y, float *y_absmax, int B, int C, int H, int W, int top,
+                                         int left, int crop_h, int crop_w, int out_h, int out_w, void *stream) {
+    EQB_NVTX_RANGE();
+    EQB_REQUIRE(y_absmax || B == 0, "eqb_crop_resize_aa_absmax: null absmax");
+    return crop_resize(x, y, y_absmax, B, C, H, W, top, left, crop_h, crop_w, out_h, out_w, stream);
 }
 
 namespace eqb {

@@ -23,6 +23,7 @@ _SIGNATURES = {
     "eqb_abi_version": (C.c_int, []),
     "eqb_last_error": (C.c_char_p, []),
     "eqb_crop_resize_aa": (C.c_int, [_fp, _fp] + [_i] * 10 + [_fp]),
+    "eqb_crop_resize_aa_absmax": (C.c_int, [_fp, _fp, _fp] + [_i] * 10 + [_fp]),
     "eqb_lift_filter_orbit": (C.c_int, [_fp, _fp] + [_i] * 5 + [_fp]),
     "eqb_regular_filter_orbit": (C.c_int, [_fp, _fp] + [_i] * 5 + [_fp]),
     "eqb_gconv_stack_workspace_bytes": (C.c_int64, [_i] * 9),
@@ -32,10 +33,12 @@ _SIGNATURES = {
     "eqb_gconv_stack_pack": (C.c_int, [_fp, _fp, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)] + [_i] * 6
                              + [_fp, C.c_int64, _fp]),
     "eqb_gconv_stack_run": (C.c_int, [_fp] + [_i] * 4 + [_fp, _fp] + [_i] * 5 + [_fp, _fp, C.c_int64, _fp]),
+    "eqb_gconv_stack_run_scaled": (C.c_int, [_fp, _fp] + [_i] * 4 + [_fp, _fp] + [_i] * 5 + [_fp, _fp, C.c_int64, _fp]),
     "eqb_conv_stack_workspace_bytes": (C.c_int64, [_i] * 8),
     "eqb_conv_stack_forward": (C.c_int, [_fp] + [_i] * 4 + [C.POINTER(C.c_void_p)] * 4 + [_i] * 4
                                + [_fp, _fp, C.c_int64, _fp]),
     "eqb_debug_last_stall": (C.c_int, [C.POINTER(C.c_int)]),
+    "eqb_debug_stack_trace": (C.c_int, [_fp, _i]),
     "eqb_group_pool_select": (C.c_int, [_fp, _i, _i, _i, _fp, _fp, _fp, _fp, _fp, _fp]),
     "eqb_warp_canonicalize": (C.c_int, [_fp, _fp, _fp] + [_i] * 6 + [_fp]),
     "eqb_warp_invert": (C.c_int, [_fp, _fp, _fp] + [_i] * 7 + [_fp]),

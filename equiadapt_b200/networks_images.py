@@ -138,8 +138,10 @@ class CustomEquivariantNetwork(PackedParameterCache, nn.Module):
             self._packed = ops.gconv_stack_pack(lift.weights, lift.bias, [m.weights for m in regs],
                                                 [m.bias for m in regs], self.num_rotations, reflect)
         last_bias = regs[-1].bias if regs else None
+        # per-image max |x| left on the tensor by the canonicalizer's crop + resize kernel (ops.crop_resize_aa), if any
+        amax = getattr(x, "_eqb_absmax", None)
         return ops.gconv_stack_run(x, self._packed, last_bias, lift.out_channels, lift.kernel_size,
-                                   self.num_rotations, reflect, len(mods))
+                                   self.num_rotations, reflect, len(mods), x_absmax=amax)
 
 
 class ESCNNEquivariantNetwork(PackedParameterCache, nn.Module):

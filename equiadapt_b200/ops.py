@@ -73,12 +73,22 @@ def _call(name: str, n_launches: int, dev: torch.device, *args):
 
 
 # ---- a3 -----------------------------------------------------------------------------------------
-def crop_resize_aa(x: torch.Tensor, top: int, left: int, crop_h: int, crop_w: int, out_h: int, out_w: int) -> torch.Tensor:
+def crop_resize_aa(x: torch.Tensor, top: int, left: int, crop_h: int, crop_w: int, out_h: int, out_w: int,
+                   with_absmax: bool = False) -> torch.Tensor:
+    """CenterCrop + antialiased resize.  with_absmax: the kernel also reduces max |y[b]| per image and the result carries
+    it as `y._eqb_absmax` (B floats) -- the per-image operand scale CustomEquivariantNetwork hands to the conv stack, so no
+    separate pass over y is launched."""
     dev = _need_cuda(x)
     _no_backward("crop_resize_aa (gradient with respect to the image)", x)
     x = _f32(x)
     b, c, h, w = x.shape
     y = torch.empty((b, c, out_h, out_w), dtype=torch.float32, device=dev)
+    if with_absmax:
+        amax = torch.empty((max(b, 1),), dtype=torch.float32, device=dev)
+        _call("eqb_crop_resize_aa_absmax", 1, dev, _ptr(x), _ptr(y), _ptr(amax), b, c, h, w, top, left, crop_h, crop_w, out_h,
+              out_w, _stream(dev))
+        y._eqb_absmax = amax
+        return y
     _call("eqb_crop_resize_aa", 1, dev, _ptr(x), _ptr(y), b, c, h, w, top, left, crop_h, crop_w, out_h, out_w, _stream(dev))
     return y
 
@@ -266,10 +276,11 @@ def gconv_stack_pack(lift_w: torch.Tensor, lift_b: Optional[torch.Tensor], reg_w
 
 
 def gconv_stack_run(x: torch.Tensor, packed: torch.Tensor, last_bias: Optional[torch.Tensor], cout: int, k: int,
-                    num_rotations: int, reflect: bool, n_layers: int) -> torch.Tensor:
-    """x (B,Cin,H,W) -> group activations (B,|G|) with pre-packed parameters: 3 launches on the tcgen05 path
-    (batch max |x|, fused stack, finish), 2 on the SIMT path."""
-    dev = _need_cuda(x, packed, last_bias)
+                    num_rotations: int, reflect: bool, n_layers: int, x_absmax: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x (B,Cin,H,W) -> group activations (B,|G|) with pre-packed parameters.  x_absmax (B floats: max |x[b]|, as left by
+    crop_resize_aa(with_absmax=True)) saves the per-image max pass: 2 launches on the tcgen05 path (fused stack, finish)
+    instead of 3."""
+    dev = _need_cuda(x, packed, last_bias, x_absmax)
     _no_backward("gconv_stack_run (the fused inference stack)", x)
     x = _f32(x)
     last_bias = None if last_bias is None else _f32(last_bias)
@@ -284,8 +295,14 @@ def gconv_stack_run(x: torch.Tensor, packed: torch.Tensor, last_bias: Optional[t
         raise ValueError("packed parameter buffer does not belong to this network configuration")
     scratch = torch.empty((max(scratch_bytes, 16),), dtype=torch.uint8, device=dev)
     act = torch.empty((b, g), dtype=torch.float32, device=dev)
-    _call("eqb_gconv_stack_run", 3, dev, _ptr(x), b, cin, h, w, _ptr(packed), _ptr(last_bias), cout, k, num_rotations,
-          int(reflect), n_layers, _ptr(act), _ptr(scratch), scratch_bytes, _stream(dev))
+    if x_absmax is not None:
+        if x_absmax.dtype != torch.float32 or x_absmax.numel() < b:
+            raise ValueError("x_absmax must hold one float32 per image")
+        _call("eqb_gconv_stack_run_scaled", 2, dev, _ptr(x), _ptr(x_absmax), b, cin, h, w, _ptr(packed), _ptr(last_bias), cout, k,
+              num_rotations, int(reflect), n_layers, _ptr(act), _ptr(scratch), scratch_bytes, _stream(dev))
+    else:
+        _call("eqb_gconv_stack_run", 3, dev, _ptr(x), b, cin, h, w, _ptr(packed), _ptr(last_bias), cout, k, num_rotations,
+              int(reflect), n_layers, _ptr(act), _ptr(scratch), scratch_bytes, _stream(dev))
     return act
 
 

@@ -43,6 +43,10 @@ EQB_API const char *eqb_last_error(void);
  * x (B,C,H,W) -> y (B,C,out_h,out_w); the crop window is [top,top+crop_h) x [left,left+crop_w). */
 EQB_API int eqb_crop_resize_aa(const float *x, float *y, int B, int C, int H, int W, int top, int left,
                        int crop_h, int crop_w, int out_h, int out_w, void *stream);
+/* The same transform, additionally leaving y_absmax[b] = max |y[b]| (B floats): the per-IMAGE operand scale of the conv
+ * stack (eqb_gconv_stack_run_scaled), reduced inside the resize kernel instead of by a second pass over y. */
+EQB_API int eqb_crop_resize_aa_absmax(const float *x, float *y, float *y_absmax, int B, int C, int H, int W, int top,
+                                      int left, int crop_h, int crop_w, int out_h, int out_w, void *stream);
 
 /* ---- a4 / a5  filter orbits ---------------------------------------------------------------
  * Lift: w (Cout,Cin,k,k) -> orbit (Cout*|G|, Cin, k, k), channel = o*|G|+g.
@@ -80,6 +84,13 @@ EQB_API int eqb_gconv_stack_pack(const float *lift_w, const float *lift_b, const
 EQB_API int eqb_gconv_stack_run(const float *x, int B, int cin, int H, int W, const void *packed,
                                 const float *last_bias, int cout, int k, int num_rotations, int reflect,
                                 int num_layers, float *act, void *scratch, int64_t scratch_bytes, void *stream);
+/* eqb_gconv_stack_run with x_absmax[b] = max |x[b]| (B floats) supplied by the producer of x (eqb_crop_resize_aa_absmax)
+ * instead of being reduced here.  Either way the fp16 operand split is scaled PER IMAGE: the activations of a sample do not
+ * depend on the other samples of the batch (custom_equivariant_networks.py:80-93 is per-sample). */
+EQB_API int eqb_gconv_stack_run_scaled(const float *x, const float *x_absmax, int B, int cin, int H, int W,
+                                       const void *packed, const float *last_bias, int cout, int k, int num_rotations,
+                                       int reflect, int num_layers, float *act, void *scratch, int64_t scratch_bytes,
+                                       void *stream);
 
 /* ---- a7  e2cnn-style conv stack with EXPANDED filters -> group activations ------------------
  * ESCNNEquivariantNetwork.forward in eval() (escnn_networks.py:93-117; modules built at :66-91):
@@ -99,6 +110,10 @@ EQB_API int eqb_conv_stack_forward(const float *x, int B, int cin, int H, int W,
 /* Diagnostics: the tcgen05 stack kernel bounds every pipeline wait (~2 s); if one expires the kernel traps instead of
  * hanging and leaves {flag, block, warp, barrier id, parity} here (host memory).  Returns flag (0 = no stall seen). */
 EQB_API int eqb_debug_last_stall(int *out5);
+/* Diagnostics: device_buffer (tiles x 64 int64, zeroed by the caller) receives clock64() stamps of the pipeline events of the
+ * first `tiles` pair-tiles of cluster 0 in every following CTA-pair stack launch (slot table: csrc/gconv_stack_tc.cu);
+ * null switches it off.  The traced kernel is a separate instantiation: production launches carry no instrumentation. */
+EQB_API int eqb_debug_stack_trace(void *device_buffer, int tiles);
 
 /* ---- a9 + a13  group pool / select + prior statistic --------------------------------------
  * act (B,|G|) -> idx int32 (B) = first arg-max, rotation (B) in degrees, reflection (B) 0/1 (may be

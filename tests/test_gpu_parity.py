@@ -1742,3 +1742,51 @@ def test_input_shape_must_match_in_shape(cuda_device):
     can = _small_c8(cuda_device, seed=78)
     with pytest.raises(ValueError):
         can(torch.rand(2, 3, 48, 48, device=cuda_device))
+
+
+def test_stack_activations_do_not_depend_on_batch_mates(cuda_device):
+    """the fp16 operand split is scaled PER IMAGE, so a sample's activations are bit-identical whatever
+    shares its batch, and an image 1e6 times fainter than its neighbour keeps full relative accuracy (with one scale per
+    call it lost its low-order bits).  Pair kernel shape (N = 256) and single-CTA shape (N = 64)."""
+    _, _, _, Net = _mods()
+    dev = cuda_device
+    for cout, n_rot in ((32, 8), (16, 4)):
+        torch.manual_seed(80 + cout)
+        net = Net((3, 40, 40), cout, 5, "rotation", n_rot, 3, device="cpu")
+        layers = [(m.weights.detach().clone(), m.bias.detach().clone()) for m in net.eqv_network if hasattr(m, "weights")]
+        net = net.to(dev).eval()
+        g = torch.Generator().manual_seed(81)
+        x = torch.rand(6, 3, 40, 40, generator=g)
+        scales = torch.tensor([1.0, 1e-6, 1e4, 3e-3, 1.0, 77.0]).view(-1, 1, 1, 1)
+        xa = (x * scales).to(dev)
+        xb = xa.clone()
+        xb[2] = xb[2] * 1e-4            # change ONE image: every other row must not move by a bit
+        xb[5] = 0.0
+        with torch.no_grad():
+            a, b = net(xa), net(xb)
+            keep = [0, 1, 3, 4]
+            assert torch.equal(a[keep], b[keep])
+            assert bool(torch.isfinite(b).all())                       # an all-zero image scales by 1
+            ref = O.custom_equivariant_network(xa.cpu().double(), [(w.double(), bb.double()) for w, bb in layers], n_rot, False)
+            err = (a.cpu().double() - ref).abs().amax(dim=1) / ref.abs().amax(dim=1)
+            assert float(err.max()) < 2e-6, err
+            single = torch.cat([net(xa[i:i + 1]) for i in range(6)])
+            assert rel_err(single.cpu(), a.cpu()) < 1e-6
+
+
+def test_tma_resize_equals_scalar_kernel_and_leaves_per_image_absmax(cuda_device, monkeypatch):
+    """The TMA-staged crop + resize returns the same bits as the scalar kernel (same taps, same FMA order), for aligned and
+    unaligned crop offsets, and eqb_crop_resize_aa_absmax leaves max |y[b]| per image."""
+    ops = _mods()[0]
+    dev = cuda_device
+    g = torch.Generator().manual_seed(82)
+    for (c, h, w, top, left, ch, cw, oh, ow) in ((3, 224, 224, 22, 22, 180, 180, 96, 96), (3, 64, 64, 3, 3, 58, 58, 32, 32),
+                                                 (1, 40, 48, 0, 4, 40, 40, 33, 17), (2, 32, 32, 2, 2, 29, 29, 32, 32)):
+        x = (torch.randn(5, c, h, w, generator=g) * torch.tensor([1.0, 1e-3, 50.0, 1.0, 0.0]).view(-1, 1, 1, 1)).to(dev)
+        y = ops.crop_resize_aa(x, top, left, ch, cw, oh, ow, with_absmax=True)
+        monkeypatch.setenv("EQB_RESIZE_SCALAR", "1")
+        y_ref = ops.crop_resize_aa(x, top, left, ch, cw, oh, ow, with_absmax=True)
+        monkeypatch.delenv("EQB_RESIZE_SCALAR")
+        assert torch.equal(y, y_ref)
+        want = y_ref.abs().amax(dim=(1, 2, 3))
+        assert torch.equal(y._eqb_absmax[:5], want) and torch.equal(y_ref._eqb_absmax[:5], want)
