@@ -23,7 +23,7 @@ namespace rs2 {
 
 constexpr int MAX_TAPS = 16;
 constexpr int BAND = 24;          // output rows per CTA
-constexpr int THREADS2 = 256;
+constexpr int THREADS2 = 384;
 
 struct Axis {       // 17 words: odd stride -> conflict-free per-lane reads of the weights
     int lo_n;       // lo | n << 20
@@ -50,6 +50,12 @@ __device__ __forceinline__ void axis(int i, int in_size, float scale, Axis &ax) 
 }
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ float lds(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
 
 struct Args {
     float *y;
@@ -145,16 +151,32 @@ __global__ void __launch_bounds__(THREADS2) crop_resize_tma_kernel(const __grid_
                     : "memory");
             }
         }
-        // horizontal pass (same FMA order per output as the scalar kernel)
+        // horizontal pass (same FMA order per output as the scalar kernel): four rows per iteration, 32-bit shared-memory
+        // addresses, taps predicated on this thread's tap count (no branches)
+        const uint32_t strip_s = smem_u32(strip) + 4u * (uint32_t)ox;
+        const uint32_t ow4 = 4u * (uint32_t)a.ow;
         if (col_ok) {
-            const float *cp = box + a.dx + xlo;
-            for (int r = threadIdx.y; r < nr; r += blockDim.y) {
-                const float *rp = cp + (size_t)r * a.box_w;
+            const uint32_t cp = smem_u32(box) + 4u * (uint32_t)(a.dx + xlo), pitch = 4u * (uint32_t)a.box_w;
+            const int by = blockDim.y;
+            int r = threadIdx.y;
+            for (; r + 3 * by < nr; r += 4 * by) {
+                float h[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int i = 0; i < MAXT; ++i) {
+                    if (i < xn) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) h[q] = fmaf(lds(cp + (uint32_t)(r + q * by) * pitch + 4u * i), wx[i], h[q]);
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) sts(strip_s + (uint32_t)(r + q * by) * ow4, h[q]);
+            }
+            for (; r < nr; r += by) {
                 float h = 0.f;
 #pragma unroll
                 for (int i = 0; i < MAXT; ++i)
-                    if (i < xn) h = fmaf(rp[i], wx[i], h);
-                strip[r * a.ow + ox] = h;
+                    if (i < xn) h = fmaf(lds(cp + (uint32_t)r * pitch + 4u * i), wx[i], h);
+                sts(strip_s + (uint32_t)r * ow4, h);
             }
         }
         __syncthreads();               // strip complete; nobody reads this box any more
@@ -162,15 +184,22 @@ __global__ void __launch_bounds__(THREADS2) crop_resize_tma_kernel(const __grid_
             const int next = item + STAGES * (int)gridDim.x;
             if (next < a.items) issue(next, stage);
         }
-        // vertical pass
+        // vertical pass: taps predicated on the row's tap count, weights of the row in registers
         float m = 0.f;
         if (col_ok) {
             float *yp = a.y + ((size_t)plane * a.oh + oy0) * a.ow + ox;
             for (int oy = threadIdx.y; oy < nrows; oy += blockDim.y) {
                 const Axis &ay = ty[oy0 + oy];
                 const int lo = (ay.lo_n & 0xfffff) - row_lo, n = ay.lo_n >> 20;
+                const uint32_t sp = strip_s + (uint32_t)lo * ow4;
                 float acc = 0.f;
-                for (int j = 0; j < n; ++j) acc = fmaf(strip[(lo + j) * a.ow + ox], ay.w[j], acc);
+                if (n <= MAXT) {
+#pragma unroll
+                    for (int j = 0; j < MAXT; ++j)
+                        if (j < n) acc = fmaf(lds(sp + (uint32_t)j * ow4), ay.w[j], acc);
+                } else {
+                    for (int j = 0; j < n; ++j) acc = fmaf(lds(sp + (uint32_t)j * ow4), ay.w[j], acc);
+                }
                 yp[(size_t)oy * a.ow] = acc;
                 m = fmaxf(m, fabsf(acc));
                 if (!(acc == acc)) m = __int_as_float(0x7f800000);   // NaN poisons only its own image's scale: +inf
