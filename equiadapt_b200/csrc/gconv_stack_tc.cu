@@ -1241,6 +1241,494 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(768, 1) gconv_stack_
 
 }  // namespace pair
 
+// =====================================================================================================================
+// CTA-PAIR kernel, second generation ("pair2"): same geometry and arithmetic as `pair` above, re-pipelined from a timeline
+// of that kernel (eqb_debug_stack_trace, profiles/r2_stack.md): per 256-pixel tile the tensor pipe needs 8 064 cycles, the
+// kernel took 10 900, and the difference is the drain of D2t -- TMEM is full (D1 256 + D2t 256 columns), so the next 1x1
+// GEMM cannot start until epilogue 2 has pulled the accumulator out (~2 100 cycles + ~500 of signalling), and nothing else
+// was queued on the pipe during that time because the next tile's lift had already run, interleaved with the 1x1 MMAs.
+//   * lift AFTER the 1x1 GEMM: the lift of tile t+1 is queued right behind the last 1x1 MMA of tile t and executes WHILE
+//     D2t(t) drains (D1 is free by then: the last A1 atom of tile t exists, so epilogue 1 has read all of D1(t));
+//   * lift in two channel passes (N = 128 each: D1 columns [0,128) then [128,256)), each with its own "full" barrier, so
+//     epilogue 1 starts on the first four K atoms while the second pass still runs.  A pass takes 64 W0 rows from each CTA,
+//     which permutes the channel <-> D1 column map to atoms {0,1,4,5 | 2,3,6,7}; the 1x1 GEMM follows with the matching W1
+//     K atom (the sum over K does not care about the order);
+//   * every slab of a tile's patch matrix stays resident (A0 ring = 5 stages): both passes read it, and the im2col
+//     producers get the whole 1x1 GEMM to refill it; the 16 KB this costs come from W0, which is no longer stationary but
+//     streamed as 4 KB half-slabs (this CTA's 64 channels of one pass, hi + lo) through a 5-stage cp.async.bulk ring by the
+//     otherwise idle warp 0 (80 KB per tile and CTA from L2).  The peer CTA's "landed" is forwarded to the leader's "ready"
+//     barrier by its idle warp 1 (a bulk copy can only signal a barrier of the CTA it writes to).
+// =====================================================================================================================
+namespace pair2 {
+
+using namespace pair;
+
+constexpr int A0_RING = 5, A1_RING = 2, W0_RING = 5;   // W0 ring = one lift pass: pass 0 of the next tile is prefetched whole during the 1x1 GEMM
+constexpr int W0_HALF = 2 * 64 * 32;       // hi + lo image of one 16-wide K slab for the 64 channels of one pass: 4 KB
+enum { B_A0FULL = 0, B_A0EMPTY = B_A0FULL + A0_RING, B_A1FULL = B_A0EMPTY + A0_RING, B_A1EMPTY = B_A1FULL + A1_RING,
+       B_D1FULL = B_A1EMPTY + A1_RING, B_D2FULL = B_D1FULL + 2, B_D2EMPTY, B_WLOAD, B_G2A, B_G2B, B_W0EMPTY,
+       B_W0LAND = B_W0EMPTY + W0_RING, B_W0RDY = B_W0LAND + W0_RING, B_COUNT = B_W0RDY + W0_RING };
+
+struct Smem {
+    uint32_t w1, w0_ring, a1_ring, a0_ring, koff, bias1, bias2, bars, tmem_slot, total;
+};
+__host__ __device__ inline Smem smem_map(int K0pad) {
+    Smem s;
+    uint32_t o = 0;
+    s.w1 = o; o += 8 * W1_ATOM;                              // 128 KB
+    s.w0_ring = o; o += W0_RING * W0_HALF;                   // 20 KB
+    s.a1_ring = o; o += A1_RING * A1_STAGE;                  // 32 KB
+    s.a0_ring = o; o += A0_RING * A0_STAGE;                  // 40 KB
+    s.koff = o; o += (uint32_t)K0pad * 4;
+    s.bias1 = o; o += 2 * 256 * 4;                           // s1-scaled lift bias, one table per image parity
+    s.bias2 = o; o += 128 * 4;
+    s.bars = o; o += B_COUNT * 8;
+    s.tmem_slot = o; o += 16;
+    s.total = o;
+    return s;
+}
+
+// D1 column chunk (32 columns) -> channel atom it holds (see the header): chunks 0-3 come from pass 0, 4-7 from pass 1
+__device__ __forceinline__ int chunk_atom(int c) { return (c & 1) | ((c & 2) << 1) | ((c & 4) >> 1); }
+
+// Trace slots (TRACE instantiation only): 0 1x1-issuer starts waiting for D2EMPTY, 1 has it, 2-9 A1FULL of atom 0-7 seen;
+// 10 lift issuer starts waiting for G2ISSUED, 11 has it, 12-16 pass-0 operands of slab 0-4 ready, 46-50 pass-1 operands
+// ready; 17 epilogue-1 group 0 sees D1FULL[0], 18-21 its chunks loaded, 22-25 their A1EMPTY seen; 26 / 27-30 / 31-34 the
+// same for group 1; 35 epilogue-2 group 0 sees D2FULL, 36 releases D2t, 37 done; 38-40 the same for group 1; 41-45 im2col:
+// A0EMPTY seen per slab.
+#define TR(slot)                                                                                              \
+    do {                                                                                                      \
+        if (TRACE && trace_on && lane == 0 && tn < a.trace_tiles) a.trace[(size_t)tn * 64 + (slot)] = clock64(); \
+    } while (0)
+
+template <bool TRACE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(768, 1) gconv_stack_pair2_kernel(const TcArgs a) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    const uint32_t base = smem_u32(smem_raw);
+    unsigned char *sm = smem_raw;
+    const Smem M = smem_map(a.K0pad);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_rank();
+    const uint32_t bars = base + M.bars;
+    auto bar = [&](int i) { return bars + 8u * (uint32_t)i; };
+    const int NS0 = a.K0pad / SLAB_K;
+    constexpr int NC1 = 8;                       // N = 256: 32-wide K atoms of the 1x1 GEMM
+    const int groups = a.epi1_groups;
+    const int lift_at = a.lift_at;               // pass 0 of the next tile's lift is queued behind this K atom of the 1x1 GEMM
+    if ((base & 1023u) != 0) __trap();           // swizzled operand images need the 1024-byte aligned window
+    const unsigned char *img = a.wpack + HDR_BYTES;
+    const uint32_t gstage = 256u * 64u;          // bytes of one packed stage in global memory (tc_pack)
+
+    // ---- one-time setup -------------------------------------------------------------------------------------
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < A0_RING; ++i) {
+            mbar_init(bar(B_A0FULL + i), 256);   // 128 im2col threads of each CTA
+            mbar_init(bar(B_A0EMPTY + i), 1);
+        }
+        for (int i = 0; i < A1_RING; ++i) {
+            mbar_init(bar(B_A1FULL + i), 256);   // 128 epilogue-1 threads (one group) of each CTA
+            mbar_init(bar(B_A1EMPTY + i), 1);
+        }
+        mbar_init(bar(B_D1FULL), 1);
+        mbar_init(bar(B_D1FULL + 1), 1);
+        mbar_init(bar(B_D2FULL), 1);
+        mbar_init(bar(B_D2EMPTY), 512);      // two epilogue-2 groups of 128 threads in each CTA
+        mbar_init(bar(B_WLOAD), 1);
+        mbar_init(bar(B_G2A), 1);
+        mbar_init(bar(B_G2B), 1);
+        for (int i = 0; i < W0_RING; ++i) {
+            mbar_init(bar(B_W0EMPTY + i), 1);
+            mbar_init(bar(B_W0LAND + i), 1);     // (peer CTA) its own half-slab has landed
+            mbar_init(bar(B_W0RDY + i), 2);      // (leader) leader's copy landed [arrive.expect_tx] + peer's forwarded arrive
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        // stationary W1: this CTA's 128-channel halves of the packed hi / lo images
+        mbar_expect_tx(bar(B_WLOAD), 8u * W1_ATOM);
+        for (int c = 0; c < 8; ++c) {
+            const unsigned char *src = img + (size_t)(NS0 + 2 * c) * gstage;
+            bulk_load(base + M.w1 + c * W1_ATOM, src + rank * 8192u, 8192u, bar(B_WLOAD));                  // hi
+            bulk_load(base + M.w1 + c * W1_ATOM + 8192u, src + gstage + rank * 8192u, 8192u, bar(B_WLOAD));  // lo
+        }
+    }
+    {
+        int *koff = reinterpret_cast<int *>(sm + M.koff);
+        float *b2 = reinterpret_cast<float *>(sm + M.bias2);
+        const int kk2 = a.ksz * a.ksz;
+        for (int k = threadIdx.x; k < a.K0pad; k += blockDim.x) {
+            int off = -1;
+            if (k < a.K0) {
+                const int c = k / kk2, rem = k - c * kk2, ky = rem / a.ksz, kx = rem - ky * a.ksz;
+                off = (c * a.H + ky) * a.W + kx;
+            }
+            koff[k] = off;
+        }
+        for (int n = threadIdx.x; n < 128; n += blockDim.x) b2[n] = a.bias2[128 * rank + n];
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(base + M.tmem_slot), "r"(512)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    mbar_wait(bar(B_WLOAD), 0, B_WLOAD);   // this CTA's stationary weights have landed ...
+    cluster_sync();          // ... in BOTH CTAs, and both CTAs' barriers are initialised, before anybody starts
+    tc_fence_after();
+    const uint32_t tmem = *reinterpret_cast<volatile uint32_t *>(sm + M.tmem_slot);
+    const uint32_t tmem_d1 = tmem, tmem_d2 = tmem + 256;
+
+    const int items = a.B * a.chunks2;
+    const int cid = (int)blockIdx.x >> 1, ncl = (int)gridDim.x >> 1;
+    const bool trace_on = TRACE && a.trace != nullptr && cid == 0 && rank == 0;
+    int tn = 0;                                  // this role's tile counter (trace rows, barrier phases)
+    auto walk = [&]() { return TileWalk(a.tiles2, a.chunks2, a.tiles_per_chunk2, items, cid, ncl); };
+    auto leader_bar = [&](int i) { return map_to_rank(bar(i), 0); };
+
+    // M = 256 (pair), fp16 operands, fp32 accumulate, both K-major; N = 256 (1x1 GEMM) / 128 (one lift pass)
+    const uint32_t idesc = (1u << 4) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+    const uint32_t idesc_lift = (1u << 4) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+    if (warp == 0) {
+        // ===== W0 producer (both CTAs): half-slabs of this CTA's lift weights, pass-major, through the ring ==========
+        if (lane == 0) {
+            uint32_t wseq = 0;
+            for (TileWalk tw = walk(); tw.valid(); tw.next()) {
+                for (int p = 0; p < 2; ++p) {
+                    for (int sl = 0; sl < NS0; ++sl, ++wseq) {
+                        const uint32_t s = wseq % W0_RING, ph = (wseq / W0_RING) & 1u;
+                        mbar_wait(bar(B_W0EMPTY + s), ph ^ 1u, B_W0EMPTY + s);
+                        // the leader's copy completes on the "ready" barrier itself, the peer's on its "landed" barrier
+                        const uint32_t fullbar = rank == 0 ? bar(B_W0RDY + s) : bar(B_W0LAND + s);
+                        mbar_expect_tx(fullbar, (uint32_t)W0_HALF);
+                        const unsigned char *src = img + (size_t)sl * gstage + (size_t)(128u * rank + 64u * p) * 32u;
+                        const uint32_t dst = base + M.w0_ring + s * W0_HALF;
+                        bulk_load(dst, src, 2048u, fullbar);                      // hi rows
+                        bulk_load(dst + 2048u, src + 256u * 32u, 2048u, fullbar); // lo rows
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (rank == 0) {
+            // ===== 1x1-GEMM issuer (leader CTA) =====================================================================
+            Ring<A1_RING> r1;
+            uint32_t tile_phase = 0;
+            const uint32_t a1_lo0 = desc_lo(base + M.a1_ring), w1_lo0 = desc_lo(base + M.w1);
+            for (TileWalk tw = walk(); tw.valid(); tw.next()) {
+                TR(0);
+                mbar_wait_cluster(bar(B_D2EMPTY), tile_phase ^ 1u, B_D2EMPTY);
+                TR(1);
+                for (int kc = 0; kc < NC1; ++kc) {
+                    mbar_wait_cluster(bar(B_A1FULL + r1.stage), r1.phase, B_A1FULL + r1.stage);
+                    TR(2 + kc);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint32_t a_hi = a1_lo0 + (uint32_t)r1.stage * (A1_STAGE >> 4), a_lo = a_hi + (A1_HALF >> 4);
+                        const uint32_t w_hi = w1_lo0 + (uint32_t)chunk_atom(kc) * (W1_ATOM >> 4), w_lo = w_hi + (8192u >> 4);
+#pragma unroll
+                        for (int j = 0; j < 2; ++j)
+                            tc_mma2_f16_lo<DESC_HI_64B>(tmem_d2, w_hi + 2 * j, a_hi + 2 * j, idesc, j ? 1u : (uint32_t)(kc != 0));
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) tc_mma2_f16_lo<DESC_HI_64B>(tmem_d2, w_hi + 2 * j, a_lo + 2 * j, idesc, 1);
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) tc_mma2_f16_lo<DESC_HI_64B>(tmem_d2, w_lo + 2 * j, a_hi + 2 * j, idesc, 1);
+                        tc_commit2(bar(B_A1EMPTY + r1.stage));
+                        if (kc == lift_at) mbar_arrive(bar(B_G2A));   // the lift issuer may queue pass 0 of the next tile
+                        if (kc == NC1 - 1) {
+                            tc_commit2(bar(B_D2FULL));
+                            mbar_arrive(bar(B_G2B));                  // ... and pass 1
+                        }
+                    }
+                    __syncwarp();
+                    r1.advance();
+                }
+                tile_phase ^= 1u;
+                ++tn;
+            }
+        } else {
+            // ===== peer CTA: forward "my half-slab has landed" to the leader's ready barrier ========================
+            if (lane == 0) {
+                uint32_t wseq = 0;
+                const uint32_t rdy0 = leader_bar(B_W0RDY);
+                for (TileWalk tw = walk(); tw.valid(); tw.next()) {
+                    for (int i = 0; i < 2 * NS0; ++i, ++wseq) {
+                        const uint32_t s = wseq % W0_RING, ph = (wseq / W0_RING) & 1u;
+                        mbar_wait(bar(B_W0LAND + s), ph, B_W0LAND + s);
+                        mbar_arrive_cluster(rdy0 + 8u * s);
+                    }
+                }
+            }
+        }
+    } else if (warp == 3) {
+        // ===== lift-GEMM issuer (leader CTA only): two passes of N = 128 behind the last 1x1 MMA of the previous tile =====
+        if (rank == 0) {
+            uint32_t wseq = 0, tile_no = 0;
+            const uint32_t a0_lo0 = desc_lo(base + M.a0_ring), w0_lo0 = desc_lo(base + M.w0_ring);
+            for (TileWalk tw = walk(); tw.valid(); tw.next(), ++tile_no) {
+                // Pass 0.  Its operands (the tile's five patch slabs, five W0 half-slabs) were produced during the previous
+                // 1x1 GEMM: confirm them BEFORE waiting for the issue slot, then queue all its MMAs back to back (a barrier
+                // poll costs ~130 cycles, a slab's three N = 128 MMAs only 192).
+                for (int sl = 0; sl < NS0; ++sl) {
+                    const uint32_t w = wseq + (uint32_t)sl;
+                    mbar_wait_cluster(bar(B_A0FULL + sl), tile_no & 1u, B_A0FULL + sl);
+                    mbar_wait_cluster(bar(B_W0RDY + w % W0_RING), (w / W0_RING) & 1u, B_W0RDY + w % W0_RING);
+                    TR(12 + sl);
+                }
+                TR(10);
+                if (tile_no > 0) mbar_wait(bar(B_G2A), (tile_no - 1u) & 1u, B_G2A);
+                TR(11);
+                tc_fence_after();
+                if (elect_one()) {
+                    for (int sl = 0; sl < NS0; ++sl) {
+                        const uint32_t s = (wseq + (uint32_t)sl) % W0_RING;
+                        const uint32_t a_hi = a0_lo0 + (uint32_t)sl * (A0_STAGE >> 4), a_lo = a_hi + (A0_HALF >> 4);
+                        const uint32_t w_hi = w0_lo0 + s * (W0_HALF >> 4), w_lo = w_hi + (2048u >> 4);
+                        tc_mma2_f16_lo<DESC_HI_32B>(tmem_d1, a_hi, w_hi, idesc_lift, sl != 0);
+                        tc_mma2_f16_lo<DESC_HI_32B>(tmem_d1, a_lo, w_hi, idesc_lift, 1);
+                        tc_mma2_f16_lo<DESC_HI_32B>(tmem_d1, a_hi, w_lo, idesc_lift, 1);
+                        tc_commit2(bar(B_W0EMPTY + s));
+                    }
+                    tc_commit2(bar(B_D1FULL));
+                }
+                __syncwarp();
+                wseq += (uint32_t)NS0;
+                // Pass 1: its W0 half-slabs stream in behind pass 0 (ring = one pass); off the critical path (epilogue 1 needs
+                // D1 columns [128,256) only after four K atoms of the 1x1 GEMM)
+                if (tile_no > 0) mbar_wait(bar(B_G2B), (tile_no - 1u) & 1u, B_G2B);   // D1 columns [128,256) of the previous tile are read
+                for (int sl = 0; sl < NS0; ++sl, ++wseq) {
+                    const uint32_t s = wseq % W0_RING, ph = (wseq / W0_RING) & 1u;
+                    mbar_wait_cluster(bar(B_W0RDY + s), ph, B_W0RDY + s);
+                    TR(46 + sl);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint32_t a_hi = a0_lo0 + (uint32_t)sl * (A0_STAGE >> 4), a_lo = a_hi + (A0_HALF >> 4);
+                        const uint32_t w_hi = w0_lo0 + s * (W0_HALF >> 4), w_lo = w_hi + (2048u >> 4);
+                        const uint32_t d = tmem_d1 + 128u;
+                        tc_mma2_f16_lo<DESC_HI_32B>(d, a_hi, w_hi, idesc_lift, sl != 0);
+                        tc_mma2_f16_lo<DESC_HI_32B>(d, a_lo, w_hi, idesc_lift, 1);
+                        tc_mma2_f16_lo<DESC_HI_32B>(d, a_hi, w_lo, idesc_lift, 1);
+                        tc_commit2(bar(B_W0EMPTY + s));
+                        tc_commit2(bar(B_A0EMPTY + sl));
+                        if (sl == NS0 - 1) tc_commit2(bar(B_D1FULL + 1));
+                    }
+                    __syncwarp();
+                }
+                ++tn;
+            }
+        }
+    } else if ((warp >= 4 && warp < 8) || (warp >= 16 && warp < 20)) {
+        // ===== epilogue 1: this CTA's pixels of D1 -> A1 K atoms in this CTA's shared memory ====================
+        const int grp = warp >= 16 ? 1 : 0;
+        if (grp < groups) {
+            const int q = warp & 3, row = q * 32 + lane;
+            float *b1tab = reinterpret_cast<float *>(sm + M.bias1);
+            const float *b1 = b1tab;
+            const Hdr hdr = load_hdr(a.wpack);
+            float c1 = 0.f;
+            int cur_b = -1, par = 1;
+            uint32_t tile_phase = 0;
+            const uint32_t row_off = (uint32_t)row * 64u, sw = (uint32_t)((row >> 1) & 3);
+            uint32_t seq0 = 0;
+            const uint32_t a1full0 = leader_bar(B_A1FULL);   // barriers are 8 bytes apart in the leader's window too
+            for (TileWalk tw = walk(); tw.valid(); tw.next()) {
+                if (tw.b != cur_b) {
+                    // new image: its scales and the s1-scaled bias table (see the single-CTA kernel)
+                    cur_b = tw.b;
+                    par ^= 1;
+                    const ImageScales sc = image_scales(hdr, __ldg(a.absmax + cur_b));
+                    c1 = sc.c1;
+                    float *tab = b1tab + par * 256;
+                    for (int n = grp * 128 + row; n < 256; n += 128 * groups) tab[n] = __ldg(a.bias1 + n) * sc.s1;
+                    named_bar_sync(1, 128 * groups);
+                    b1 = tab;
+                }
+                int seen = 0;                                   // lift passes whose "full" barrier this thread has passed
+                for (int c = grp; c < NC1; c += groups) {
+                    const int need = (c >> 2) + 1;
+                    while (seen < need) {
+                        mbar_wait(bar(B_D1FULL + seen), tile_phase, B_D1FULL + seen);
+                        if (q == 0 && seen == 0) TR(17 + 9 * grp);
+                        ++seen;
+                        tc_fence_after();
+                    }
+                    float v[32];
+                    tc_ld32(tmem_d1 + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+                    if (q == 0) TR(18 + 9 * grp + (c >> 1));
+                    const float *bb = b1 + chunk_atom(c) * 32;
+                    uint32_t hi[16], lo[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const float x0 = fmaxf(fmaf(v[2 * i], c1, bb[2 * i]), 0.f);
+                        const float x1 = fmaxf(fmaf(v[2 * i + 1], c1, bb[2 * i + 1]), 0.f);
+                        split2(x0, x1, hi[i], lo[i]);
+                    }
+                    const uint32_t seq = seq0 + (uint32_t)c, stage = seq % A1_RING, phase = (seq / A1_RING) & 1u;
+                    mbar_wait(bar(B_A1EMPTY + stage), phase ^ 1u, B_A1EMPTY + stage);
+                    if (q == 0) TR(22 + 9 * grp + (c >> 1));
+                    const uint32_t hi_row = base + M.a1_ring + stage * A1_STAGE + row_off, lo_row = hi_row + A1_HALF;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const uint32_t col = ((uint32_t)j ^ sw) << 4;
+                        st_shared_v4(hi_row + col, hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+                        st_shared_v4(lo_row + col, lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+                    }
+                    // D1 of this tile is overwritten by the next tile's lift, which the issuers order behind the A1FULL of
+                    // this group's LAST chunk: order this thread's tcgen05.ld's before that arrive
+                    if ((c & 3) + groups >= 4) tc_fence_before();   // (last chunk of this group in either half of D1)
+                    fence_async_smem();
+                    mbar_arrive_cluster(a1full0 + 8u * stage);
+                }
+                seq0 += (uint32_t)NC1;
+                tile_phase ^= 1u;
+                ++tn;
+            }
+        }
+    } else if ((warp >= 8 && warp < 12) || (warp >= 20 && warp < 24)) {
+        // ===== epilogue 2: this CTA's 128 channels of D2t -> spatial sums over the 256 pixel columns ============
+        const int grp = warp >= 20 ? 1 : 0;
+        const int q = warp & 3;
+        const Hdr hdr = load_hdr(a.wpack);
+        const float bv = reinterpret_cast<const float *>(sm + M.bias2)[q * 32 + lane];
+        const int chan = 128 * (int)rank + q * 32 + lane;
+        const uint32_t d2empty = leader_bar(B_D2EMPTY);
+        uint32_t tile_phase = 0;
+        TileWalk tw = walk();
+        while (tw.valid()) {
+            const int b = tw.b, ch = tw.ch;
+            const float c2 = image_scales(hdr, __ldg(a.absmax + b)).c2;
+            double dacc = 0.0;
+            bool item_done = false;
+            while (!item_done) {
+                const int nvalid = min(256, a.P - tw.t * 256) - 128 * grp;   // valid columns of this group's half
+                mbar_wait(bar(B_D2FULL), tile_phase, B_D2FULL);
+                if (q == 0) TR(35 + 3 * grp);
+                tc_fence_after();
+                float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+                const uint32_t t0 = tmem_d2 + ((uint32_t)(q * 32) << 16) + (uint32_t)(128 * grp);
+                auto add_chunk = [&](const uint32_t (&r)[32], int c) {
+                    if (c * 32 + 32 <= nvalid) {
+#pragma unroll
+                        for (int i = 0; i < 32; i += 4) {
+                            s0 += fmaxf(fmaf(__uint_as_float(r[i]), c2, bv), 0.f);
+                            s1 += fmaxf(fmaf(__uint_as_float(r[i + 1]), c2, bv), 0.f);
+                            s2 += fmaxf(fmaf(__uint_as_float(r[i + 2]), c2, bv), 0.f);
+                            s3 += fmaxf(fmaf(__uint_as_float(r[i + 3]), c2, bv), 0.f);
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            if (c * 32 + i < nvalid) s0 += fmaxf(fmaf(__uint_as_float(r[i]), c2, bv), 0.f);
+                    }
+                };
+                // D2t is free for the next 1x1 GEMM the moment this thread's LAST chunk sits in registers: the drain is on
+                // the critical path of the tile (TMEM is full, D2t is single-buffered), the summation is not
+                auto release = [&]() {
+                    tc_fence_before();
+                    mbar_arrive_cluster(d2empty);
+                    if (q == 0) TR(36 + 3 * grp);
+                };
+                {
+                    // one chunk at a time (two in flight cost 32 more registers, spills, and measured 5 % slower); the release
+                    // goes out as soon as the LAST chunk is loaded, before it is summed
+                    const int nch = nvalid <= 0 ? 0 : (nvalid >= 128 ? 4 : (nvalid + 31) >> 5);   // (uniform)
+                    if (nch == 0) release();
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        if (c < nch) {
+                            uint32_t r[32];
+                            tc_ld32_issue(t0 + (uint32_t)(c * 32), r);
+                            tc_ld_wait(r);
+                            if (c == nch - 1) release();
+                            add_chunk(r, c);
+                        }
+                    }
+                    dacc += (double)((s0 + s1) + (s2 + s3));
+                }
+                if (q == 0) TR(37 + 3 * grp);
+                tile_phase ^= 1u;
+                ++tn;
+                item_done = tw.last_of_item();
+                tw.next();
+            }
+            a.S_part[((size_t)b * (2 * a.chunks2) + 2 * ch + grp) * a.Npad + chan] = dacc;
+        }
+    } else if (warp >= 12 && warp < 16) {
+        // ===== im2col producers: this CTA's 128 pixels of the pair-tile; ring stage = slab ============================
+        const int row = (warp - 12) * 32 + lane;
+        const int *koff = reinterpret_cast<const int *>(sm + M.koff);
+        float sx = 1.f;
+        int cur_b = -1;
+        uint32_t tile_no = 0;
+        const uint32_t row_off = (uint32_t)row * 32u, sw = (uint32_t)((row >> 2) & 1);
+        const uint32_t a0full0 = leader_bar(B_A0FULL);
+        auto tile_ptr = [&](const TileWalk &w, bool &valid) {
+            const int p = w.t * 256 + 128 * (int)rank + row;
+            valid = p < a.P;
+            const int oy = valid ? p / a.Wo : 0, ox = valid ? p - oy * a.Wo : 0;
+            return a.x + (size_t)w.b * a.cin * a.H * a.W + (size_t)oy * a.W + ox;
+        };
+        auto load_slab = [&](const float *xp, bool valid, int sl, float *x) {
+#pragma unroll
+            for (int i = 0; i < SLAB_K; ++i) {
+                const int off = koff[sl * SLAB_K + i];
+                x[i] = (valid && off >= 0) ? __ldg(xp + off) : 0.f;
+            }
+        };
+        TileWalk tw = walk();
+        bool valid = false;
+        const float *xp = tw.valid() ? tile_ptr(tw, valid) : a.x;
+        float xn[SLAB_K];
+        if (tw.valid()) load_slab(xp, valid, 0, xn);
+        while (tw.valid()) {
+            if (tw.b != cur_b) {
+                cur_b = tw.b;
+                sx = pow2_scale(__ldg(a.absmax + cur_b));
+            }
+            for (int sl = 0; sl < NS0; ++sl) {
+                float x[SLAB_K];
+#pragma unroll
+                for (int i = 0; i < SLAB_K; ++i) x[i] = xn[i] * sx;
+                if (sl + 1 < NS0) {
+                    load_slab(xp, valid, sl + 1, xn);
+                } else {
+                    tw.next();
+                    if (tw.valid()) {
+                        xp = tile_ptr(tw, valid);
+                        load_slab(xp, valid, 0, xn);
+                    }
+                }
+                uint32_t hi[8], lo[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) split2(x[2 * i], x[2 * i + 1], hi[i], lo[i]);
+                mbar_wait(bar(B_A0EMPTY + sl), (tile_no & 1u) ^ 1u, B_A0EMPTY + sl);
+                if (warp == 12) TR(41 + sl);
+                const uint32_t hi_row = base + M.a0_ring + (uint32_t)sl * A0_STAGE + row_off, lo_row = hi_row + A0_HALF;
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const uint32_t col = ((uint32_t)j ^ sw) << 4;
+                    st_shared_v4(hi_row + col, hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+                    st_shared_v4(lo_row + col, lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+                }
+                fence_async_smem();
+                mbar_arrive_cluster(a0full0 + 8u * (uint32_t)sl);
+            }
+            ++tile_no;
+            ++tn;
+        }
+    }
+#undef TR
+
+    // ---- teardown -------------------------------------------------------------------------------------------
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync();          // no CTA leaves while its peer may still arrive on its barriers or read its shared memory
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+    }
+}
+
+}  // namespace pair2
+
 // Header of the packed buffer: power-of-two operand scales and the pieces of the hidden-activation bound.
 //   hdr[0] = sw0 (lift weights), hdr[1] = sw1 (1x1 weights), hdr[2] = R0 = max_n sum_k |W0[k][n]|, hdr[3] = max |b1|
 __global__ void __launch_bounds__(256) tc_header_kernel(const float *__restrict__ Wt0, int K0, const float *__restrict__ Wt1,
@@ -1439,6 +1927,23 @@ int tc_launch(TcArgs a, cudaStream_t st) {
         const int clusters = items2 < max_clusters ? items2 : max_clusters;
         a.trace = g_trace;
         a.trace_tiles = g_trace_tiles;
+        const char *p2 = getenv("EQB_TC_PAIR2"), *la = getenv("EQB_TC_LIFT_AT");
+        a.lift_at = la && la[0] >= '3' && la[0] <= '7' ? la[0] - '0' : 5;
+        if (!(p2 && p2[0] == '0')) {
+            // second-generation pipeline (lift behind the 1x1 GEMM in two channel passes, resident patch slabs, streamed W0)
+            const tc::pair2::Smem M2 = tc::pair2::smem_map(a.K0pad);
+            EQB_UNSUPPORTED(M2.total > 227 * 1024, "gconv_stack (tcgen05 pair2): shared-memory plan of %u bytes does not fit", M2.total);
+            static PerDeviceOnce configured3;
+            if (configured3.first()) {
+                EQB_CUDA(cudaFuncSetAttribute(tc::pair2::gconv_stack_pair2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              227 * 1024));
+                EQB_CUDA(cudaFuncSetAttribute(tc::pair2::gconv_stack_pair2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              227 * 1024));
+            }
+            if (a.trace) tc::pair2::gconv_stack_pair2_kernel<true><<<2 * clusters, 768, M2.total, st>>>(a);
+            else tc::pair2::gconv_stack_pair2_kernel<false><<<2 * clusters, 768, M2.total, st>>>(a);
+            return finish_launch("gconv_stack_pair2_kernel");
+        }
         if (a.trace) tc::pair::gconv_stack_pair_kernel<true><<<2 * clusters, 768, M.total, st>>>(a);
         else tc::pair::gconv_stack_pair_kernel<false><<<2 * clusters, 768, M.total, st>>>(a);
         return finish_launch("gconv_stack_pair_kernel");

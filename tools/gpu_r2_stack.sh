@@ -1,12 +1,14 @@
 #!/bin/bash
-# A/B of the pair-kernel pipeline knobs + timeline traces + parity tests of the stack.
+# A/B of the pair kernels + timeline traces + parity tests of the stack.  tools/gpu_r2_stack.sh <tag> [env settings to sweep...]
 set -u
-OUT=gpurun_out/${1:-r2d}; mkdir -p $OUT
-for cfg in "EQB_TC_LIFT_ORDER=0 EQB_TC_EPI2_PIPE=0" "EQB_TC_LIFT_ORDER=0 EQB_TC_EPI2_PIPE=1" "EQB_TC_LIFT_ORDER=1 EQB_TC_EPI2_PIPE=0" "EQB_TC_LIFT_ORDER=1 EQB_TC_EPI2_PIPE=1"; do
+OUT=gpurun_out/${1:-r2d}; mkdir -p $OUT; shift
+for cfg in "EQB_TC_PAIR2=0" "$@"; do
   env $cfg timeout 120 python tools/bench_stack.py 2>&1 | tail -1 | tee -a $OUT/ab.txt
 done
-EQB_TC_LIFT_ORDER=0 EQB_TC_EPI2_PIPE=0 timeout 120 python tools/trace_stack.py 10 3 > $OUT/trace_00.txt 2>&1
-EQB_TC_LIFT_ORDER=1 EQB_TC_EPI2_PIPE=0 timeout 120 python tools/trace_stack.py 10 3 > $OUT/trace_10.txt 2>&1
-EQB_TC_LIFT_ORDER=1 EQB_TC_EPI2_PIPE=1 timeout 120 python tools/trace_stack.py 10 3 > $OUT/trace_11.txt 2>&1
-head -2 $OUT/trace_00.txt | tail -1; head -2 $OUT/trace_10.txt | tail -1; head -2 $OUT/trace_11.txt | tail -1
-timeout 600 python -m pytest tests -m gpu -x -q -k "stack or tcgen05 or golden or capture or smoke" 2>&1 | tail -2 | tee $OUT/pytest.log
+timeout 120 python tools/trace_stack.py 10 3 > $OUT/trace_p2.txt 2>&1
+head -2 $OUT/trace_p2.txt | tail -1
+timeout 600 python -m pytest tests -m gpu -x -q -k "stack or tcgen05 or golden or capture or smoke or batch_mates" 2>&1 | tail -3 | tee $OUT/pytest.log
+python -c "
+from equiadapt_b200 import native
+import ctypes
+o=(ctypes.c_int*5)(); print('stall', native.lib().eqb_debug_last_stall(o), list(o))"

@@ -21,7 +21,7 @@ t = buf.cpu().view(TILES, 64)
 names = {0: "I1 wait D2EMPTY", 1: "I1 got D2EMPTY", 10: "L wait", 11: "L got D1EMPTY(+G2)", 17: "E1g0 D1FULL", 26: "E1g1 D1FULL",
          35: "E2g0 D2FULL", 36: "E2g0 release", 37: "E2g0 done", 38: "E2g1 D2FULL", 39: "E2g1 release", 40: "E2g1 done"}
 for k in range(8): names[2 + k] = f"I1 A1FULL atom{k}"
-for k in range(5): names[12 + k] = f"L A0FULL slab{k}"; names[41 + k] = f"IM A0EMPTY slab{k}"
+for k in range(5): names[12 + k] = f"L A0FULL slab{k}"; names[41 + k] = f"IM A0EMPTY slab{k}"; names[46 + k] = f"L pass1 slab{k}"
 for k in range(4):
     names[18 + k] = f"E1g0 ld atom{2*k}"; names[22 + k] = f"E1g0 A1EMPTY atom{2*k}"
     names[27 + k] = f"E1g1 ld atom{2*k+1}"; names[31 + k] = f"E1g1 A1EMPTY atom{2*k+1}"
