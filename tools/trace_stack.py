@@ -28,6 +28,9 @@ for k in range(4):
 print({k: v for k, v in os.environ.items() if k.startswith("EQB_")})
 per = (t[T0 + NT, 1] - t[T0, 1]).item() / NT
 print(f"tile period over tiles {T0}..{T0+NT}: {per:.0f} cycles (MMA floor 8064)")
+d = [(t[i + 1, 1] - t[i, 1]).item() for i in range(2, TILES - 2)]
+print("per-tile periods (I1 got D2EMPTY -> next), tiles 2..:", d)
+print(f"mean over tiles 4..{TILES-4}: {(t[TILES-4, 1] - t[4, 1]).item() / (TILES - 8):.0f} cycles")
 origin = t[T0, 1].item()
 ev = []
 for tile in range(T0, T0 + NT):
