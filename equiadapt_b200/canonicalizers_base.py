@@ -156,7 +156,11 @@ class DiscreteGroupCanonicalization(BaseCanonicalization):
     def _select(self, group_activations: torch.Tensor):
         """One kernel: arg-max index, angle, reflection flag, one-hot and the prior statistic."""
         reflect = self.group_type == "roto-reflection"
-        idx, rot, refl, onehot, stats = ops.group_pool_select(group_activations, self.num_rotations, reflect)
+        fused = getattr(group_activations, "_eqb_selection", None)
+        if fused is not None and fused[0] == self.num_rotations and fused[1] == reflect:
+            idx, rot, refl, onehot, stats = fused[2:]          # selected inside the network's finish kernel (same bits)
+        else:
+            idx, rot, refl, onehot, stats = ops.group_pool_select(group_activations, self.num_rotations, reflect)
         self._selected = {"activations": group_activations, "idx": idx, "rotation": rot, "reflection": refl,
                           "onehot": onehot, "stats": stats, "global": None}
         if self.prefetch_prior_allreduce:

@@ -30,7 +30,9 @@ constexpr int GT_KC = 16;      // K rows per streamed weight chunk
 constexpr int GT_THREADS = 256;
 constexpr int GT_MAX_GEMM = 8;
 // per-call scalars ahead of the partial sums: max |x| of every image (tcgen05 path)
-static inline size_t scratch_head(int B) { return (((size_t)(B > 0 ? B : 1) * sizeof(float)) + 255) & ~(size_t)255; }
+// and the per-image cross entropies / identity flags of the fused select (2 B doubles)
+static inline size_t scratch_amax(int B) { return (((size_t)(B > 0 ? B : 1) * sizeof(float)) + 255) & ~(size_t)255; }
+static inline size_t scratch_head(int B) { return scratch_amax(B) + (((size_t)(B > 0 ? B : 1) * 2 * sizeof(double) + 255) & ~(size_t)255); }
 
 struct StackArgs {
     const float *x;
@@ -209,14 +211,30 @@ __global__ void expand_bias_kernel(const float *__restrict__ bias, float *__rest
         out[n] = (bias && n < N) ? bias[n / G] : 0.f;
 }
 
-// one block per image: S = sum of chunk partials; act[g] = S . M[:,g] / (Cout*P) + mean(last bias)
+// Fused group pool / select (a9 + a13) riding on the finish kernel: what eqb_group_pool_select computes from the activations
+// (small_ops.cu: same per-sample arithmetic, same order of the batch sums, hence the same bits), so a canonicalizer step needs
+// no separate select launch.  All pointers null -> plain finish.
+struct SelectOut {
+    int32_t *idx;
+    float *rotation, *reflection, *onehot, *stats;   // reflection / onehot may be null
+    double *per_image;                               // scratch: [B] cross entropies, then [B] identity flags
+    unsigned int *ticket;                            // zero at entry, reset by the last block
+    int N;                                           // rotations (|G| = N or 2 N)
+};
+
+// one block per image: S = sum of chunk partials; act[g] = S . M[:,g] / (Cout*P) + mean(last bias); warp w owns the group
+// elements g = w, w + 8, ...; [select:] thread 0 picks the element, the last block to finish reduces the batch statistic
 __global__ void __launch_bounds__(256) gconv_finish_kernel(const double *__restrict__ S_part,
                                                            const double *__restrict__ M,
                                                            const float *__restrict__ last_bias, int cout, int chunks,
-                                                           int Npad, int G, double inv_count, float *__restrict__ act) {
+                                                           int Npad, int G, double inv_count, float *__restrict__ act,
+                                                           const SelectOut sel) {
     extern __shared__ double S[];  // [Npad]
-    __shared__ double red[8];
-    const int b = blockIdx.x;
+    __shared__ float act_s[64];
+    __shared__ double s_ce[8], s_id[8];
+    __shared__ unsigned int s_last;
+    const int b = blockIdx.x, B = gridDim.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int n = threadIdx.x; n < Npad; n += blockDim.x) {
         double s = 0.0;
         for (int c = 0; c < chunks; ++c) s += S_part[((size_t)b * chunks + c) * Npad + n];
@@ -228,24 +246,80 @@ __global__ void __launch_bounds__(256) gconv_finish_kernel(const double *__restr
         for (int o = 0; o < cout; ++o) bmean += (double)last_bias[o];
         bmean /= cout;
     }
-    for (int g = 0; g < G; ++g) {
+    for (int g = warp; g < G; g += 8) {
         double v = 0.0;
-        for (int n = threadIdx.x; n < Npad; n += blockDim.x) v += S[n] * M[(size_t)n * G + g];
+        for (int n = lane; n < Npad; n += 32) v += S[n] * M[(size_t)n * G + g];
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            double t = 0.0;
-            for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
-            act[(size_t)b * G + g] = (float)(t * inv_count + bmean);
+        if (lane == 0) {
+            const float a = (float)(v * inv_count + bmean);
+            act[(size_t)b * G + g] = a;
+            if (g < 64) act_s[g] = a;
         }
-        __syncthreads();
+    }
+    if (!sel.idx) return;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        // per-sample part of group_pool_select_kernel, verbatim
+        const float *a = act_s;
+        float best = a[0];
+        int bi = 0;
+        for (int g = 1; g < G; ++g) {
+            const float v = a[g];
+            if (v > best || (v != v && best == best)) {
+                best = v;
+                bi = g;
+            }
+        }
+        float se = 0.f;
+        for (int g = 0; g < G; ++g) se += expf(a[g] - best);
+        sel.per_image[b] = (double)((best + logf(se)) - a[0]);
+        sel.per_image[B + b] = bi == 0 ? 1.0 : 0.0;
+        sel.idx[b] = bi;
+        const int N = sel.N, r = bi % N;
+        const float step = 360.0f / (float)N;
+        sel.rotation[b] = (r < (N + 1) / 2) ? __fmul_rn(step, (float)r) : 360.0f - __fmul_rn(step, (float)(N - r));
+        if (sel.reflection) sel.reflection[b] = bi >= N ? 1.f : 0.f;
+        if (sel.onehot)
+            for (int g = 0; g < G; ++g) sel.onehot[(size_t)b * G + g] = g == bi ? 1.f : 0.f;
+        __threadfence();
+        s_last = atomicAdd(sel.ticket, 1u) == (unsigned int)(B - 1) ? 1u : 0u;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    // last block: the batch statistic in the summation order of group_pool_select_kernel's single-CTA path
+    __threadfence();
+    double ce = 0.0, ident = 0.0;
+    for (int i = threadIdx.x; i < B; i += blockDim.x) {
+        ce += __ldcg(sel.per_image + i);
+        ident += __ldcg(sel.per_image + B + i);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        ce += __shfl_xor_sync(0xffffffffu, ce, o);
+        ident += __shfl_xor_sync(0xffffffffu, ident, o);
+    }
+    if (lane == 0) {
+        s_ce[warp] = ce;
+        s_id[warp] = ident;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double c = 0.0, d = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
+            c += s_ce[w];
+            d += s_id[w];
+        }
+        sel.stats[0] = (float)c;
+        sel.stats[1] = (float)d;
+        sel.stats[2] = (float)B;
+        sel.stats[3] = (float)(c / (double)B);
+        sel.stats[4] = (float)(d / (double)B);
+        *sel.ticket = 0u;                 // ready for the next launch
     }
 }
 
 struct StackPlan {
     int G, N, Npad, K0, K0pad, Ho, Wo, P, rows, n_gemm, tiles, chunks, tiles_per_chunk;
-    size_t off_wt[GT_MAX_GEMM], off_bias[GT_MAX_GEMM], off_M, off_tc, off_S, total;
+    size_t off_wt[GT_MAX_GEMM], off_bias[GT_MAX_GEMM], off_M, off_tc, off_ticket, off_S, total;
     size_t smem;
     // tcgen05 path (gconv_stack_tc.cu): 128-pixel tiles, its own chunking
     bool tc;
@@ -314,6 +388,9 @@ static int make_plan(int B, int cin, int H, int W, int cout, int k, int N, int r
         p.tc2_chunks = (p.tc2_tiles + p.tc2_tiles_per_chunk - 1) / p.tc2_tiles_per_chunk;
         if (2 * p.tc2_chunks > max_chunks) max_chunks = 2 * p.tc2_chunks;   // two partial-sum rows per chunk
     }
+    off = (off + 15) & ~(size_t)15;
+    p.off_ticket = off;      // last-block ticket of the fused select (zeroed by the pack call, reset by the kernel)
+    off += 64;
     p.off_S = off;
     off += scratch_head(B);
     off += (size_t)(B > 0 ? B : 1) * max_chunks * p.Npad * sizeof(double);
@@ -370,6 +447,7 @@ extern "C" int eqb_gconv_stack_pack(const float *lift_w, const float *lift_b, co
     const int L = num_layers, reflect01 = reflect != 0;
     // filter orbits as zero-padded K-major GEMM operands, expanded biases, fold matrix
     EQB_CUDA(cudaMemsetAsync(ws, 0, p.off_bias[0], st));
+    EQB_CUDA(cudaMemsetAsync(ws + p.off_ticket, 0, 64, st));
     int e = launch_lift_orbit(lift_w, (float *)(ws + p.off_wt[0]), cout, cin, k, num_rotations, reflect01, 1, p.Npad, st);
     if (e) return e;
     for (int l = 1; l < p.n_gemm; ++l) {
@@ -396,7 +474,7 @@ extern "C" int eqb_gconv_stack_pack(const float *lift_w, const float *lift_b, co
 
 static int stack_run(const float *x, const float *x_absmax, int B, int cin, int H, int W, const void *packed,
                      const float *last_bias, int cout, int k, int num_rotations, int reflect, int num_layers, float *act,
-                     void *scratch, int64_t scratch_bytes, void *stream) {
+                     SelectOut sel, void *scratch, int64_t scratch_bytes, void *stream) {
     StackPlan p;
     const int rc = make_plan(B, cin, H, W, cout, k, num_rotations, reflect, num_layers, p);
     if (rc) return rc;
@@ -450,9 +528,15 @@ static int stack_run(const float *x, const float *x_absmax, int B, int cin, int 
     }
     if (e) return e;
     const double inv_count = 1.0 / ((double)cout * (double)p.P);
+    if (sel.idx) {
+        EQB_UNSUPPORTED(p.G > 64, "eqb_gconv_stack_run_select: more than 64 group elements");
+        sel.per_image = (double *)((char *)scratch + scratch_amax(B));
+        sel.ticket = (unsigned int *)(const_cast<char *>(ws) + p.off_ticket);
+        sel.N = num_rotations;
+    }
     gconv_finish_kernel<<<B, 256, p.Npad * sizeof(double), st>>>(a.S_part, (const double *)(ws + p.off_M),
                                                                 L > 1 ? last_bias : nullptr, cout, chunks, p.Npad, p.G,
-                                                                inv_count, act);
+                                                                inv_count, act, sel);
     return finish_launch("gconv_finish_kernel");
 }
 
@@ -460,8 +544,8 @@ extern "C" int eqb_gconv_stack_run(const float *x, int B, int cin, int H, int W,
                                    const float *last_bias, int cout, int k, int num_rotations, int reflect,
                                    int num_layers, float *act, void *scratch, int64_t scratch_bytes, void *stream) {
     EQB_NVTX_RANGE();
-    return stack_run(x, nullptr, B, cin, H, W, packed, last_bias, cout, k, num_rotations, reflect, num_layers, act, scratch,
-                     scratch_bytes, stream);
+    return stack_run(x, nullptr, B, cin, H, W, packed, last_bias, cout, k, num_rotations, reflect, num_layers, act, SelectOut{},
+                     scratch, scratch_bytes, stream);
 }
 
 extern "C" int eqb_gconv_stack_run_scaled(const float *x, const float *x_absmax, int B, int cin, int H, int W,
@@ -470,8 +554,25 @@ extern "C" int eqb_gconv_stack_run_scaled(const float *x, const float *x_absmax,
                                           void *stream) {
     EQB_NVTX_RANGE();
     EQB_REQUIRE(x_absmax, "eqb_gconv_stack_run_scaled: null absmax");
-    return stack_run(x, x_absmax, B, cin, H, W, packed, last_bias, cout, k, num_rotations, reflect, num_layers, act, scratch,
-                     scratch_bytes, stream);
+    return stack_run(x, x_absmax, B, cin, H, W, packed, last_bias, cout, k, num_rotations, reflect, num_layers, act, SelectOut{},
+                     scratch, scratch_bytes, stream);
+}
+
+extern "C" int eqb_gconv_stack_run_select(const float *x, const float *x_absmax, int B, int cin, int H, int W,
+                                          void *packed, const float *last_bias, int cout, int k, int num_rotations,
+                                          int reflect, int num_layers, float *act, int32_t *idx, float *rotation,
+                                          float *reflection, float *onehot, float *stats, void *scratch,
+                                          int64_t scratch_bytes, void *stream) {
+    EQB_NVTX_RANGE();
+    EQB_REQUIRE(stats && (B == 0 || (idx && rotation)), "eqb_gconv_stack_run_select: null pointer");
+    if (B == 0) {   // the statistic of an empty batch, as eqb_group_pool_select leaves it
+        EQB_CUDA(cudaMemsetAsync(stats, 0, 5 * sizeof(float), (cudaStream_t)stream));
+        return 0;
+    }
+    SelectOut sel{};
+    sel.idx = idx; sel.rotation = rotation; sel.reflection = reflect ? reflection : nullptr; sel.onehot = onehot; sel.stats = stats;
+    return stack_run(x, x_absmax, B, cin, H, W, packed, last_bias, cout, k, num_rotations, reflect, num_layers, act, sel,
+                     scratch, scratch_bytes, stream);
 }
 
 extern "C" int eqb_debug_last_stall(int *out5) { return tc_last_stall(out5); }

@@ -34,6 +34,7 @@ _SIGNATURES = {
                              + [_fp, C.c_int64, _fp]),
     "eqb_gconv_stack_run": (C.c_int, [_fp] + [_i] * 4 + [_fp, _fp] + [_i] * 5 + [_fp, _fp, C.c_int64, _fp]),
     "eqb_gconv_stack_run_scaled": (C.c_int, [_fp, _fp] + [_i] * 4 + [_fp, _fp] + [_i] * 5 + [_fp, _fp, C.c_int64, _fp]),
+    "eqb_gconv_stack_run_select": (C.c_int, [_fp, _fp] + [_i] * 4 + [_fp, _fp] + [_i] * 5 + [_fp] * 6 + [_fp, C.c_int64, _fp]),
     "eqb_conv_stack_workspace_bytes": (C.c_int64, [_i] * 8),
     "eqb_conv_stack_forward": (C.c_int, [_fp] + [_i] * 4 + [C.POINTER(C.c_void_p)] * 4 + [_i] * 4
                                + [_fp, _fp, C.c_int64, _fp]),

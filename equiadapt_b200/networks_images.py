@@ -114,6 +114,7 @@ class CustomEquivariantNetwork(PackedParameterCache, nn.Module):
         self.num_rotations = num_rotations
         self.out_channels = out_channels
         self.kernel_size = kernel_size
+        self.fuse_select = True       # group pool / select rides on the finish kernel of the fused stack (ops.gconv_stack_run)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         """(B,Cin,H,W) -> group activations (B,|G|): custom_equivariant_networks.py:80-93, one fused call."""
@@ -140,8 +141,10 @@ class CustomEquivariantNetwork(PackedParameterCache, nn.Module):
         last_bias = regs[-1].bias if regs else None
         # per-image max |x| left on the tensor by the canonicalizer's crop + resize kernel (ops.crop_resize_aa), if any
         amax = getattr(x, "_eqb_absmax", None)
+        # the finish kernel also selects the group element (what the canonicalizer would launch eqb_group_pool_select for) and
+        # leaves the selection on the result; a caller that only wants the activations ignores it
         return ops.gconv_stack_run(x, self._packed, last_bias, lift.out_channels, lift.kernel_size,
-                                   self.num_rotations, reflect, len(mods), x_absmax=amax)
+                                   self.num_rotations, reflect, len(mods), x_absmax=amax, select=self.fuse_select)
 
 
 class ESCNNEquivariantNetwork(PackedParameterCache, nn.Module):

@@ -276,10 +276,13 @@ def gconv_stack_pack(lift_w: torch.Tensor, lift_b: Optional[torch.Tensor], reg_w
 
 
 def gconv_stack_run(x: torch.Tensor, packed: torch.Tensor, last_bias: Optional[torch.Tensor], cout: int, k: int,
-                    num_rotations: int, reflect: bool, n_layers: int, x_absmax: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """x (B,Cin,H,W) -> group activations (B,|G|) with pre-packed parameters.  x_absmax (B floats: max |x[b]|, as left by
-    crop_resize_aa(with_absmax=True)) saves the per-image max pass: 2 launches on the tcgen05 path (fused stack, finish)
-    instead of 3."""
+                    num_rotations: int, reflect: bool, n_layers: int, x_absmax: Optional[torch.Tensor] = None,
+                    select: bool = False) -> torch.Tensor:
+    """x (B,Cin,H,W) -> group activations (B,|G|) with pre-packed parameters.
+    x_absmax (B floats: max |x[b]|, as left by crop_resize_aa(with_absmax=True)) saves the per-image max pass.
+    select: the finish kernel also does the group pool / select of group_pool_select() on its own output and the result
+    carries it as `act._eqb_selection = (num_rotations, reflect, idx, rotation, reflection, onehot, stats)`, so the
+    canonicalizer needs no select launch: 2 launches per call (fused stack, finish + select)."""
     dev = _need_cuda(x, packed, last_bias, x_absmax)
     _no_backward("gconv_stack_run (the fused inference stack)", x)
     x = _f32(x)
@@ -295,9 +298,19 @@ def gconv_stack_run(x: torch.Tensor, packed: torch.Tensor, last_bias: Optional[t
         raise ValueError("packed parameter buffer does not belong to this network configuration")
     scratch = torch.empty((max(scratch_bytes, 16),), dtype=torch.uint8, device=dev)
     act = torch.empty((b, g), dtype=torch.float32, device=dev)
-    if x_absmax is not None:
-        if x_absmax.dtype != torch.float32 or x_absmax.numel() < b:
-            raise ValueError("x_absmax must hold one float32 per image")
+    if x_absmax is not None and (x_absmax.dtype != torch.float32 or x_absmax.numel() < b):
+        raise ValueError("x_absmax must hold one float32 per image")
+    if select:
+        idx = torch.empty((b,), dtype=torch.int32, device=dev)
+        rot = torch.empty((b,), dtype=torch.float32, device=dev)
+        refl = torch.empty((b,), dtype=torch.float32, device=dev) if reflect else None
+        onehot = torch.empty((b, g), dtype=torch.float32, device=dev)
+        stats = torch.empty((5,), dtype=torch.float32, device=dev)
+        _call("eqb_gconv_stack_run_select", 2 if x_absmax is not None else 3, dev, _ptr(x), _ptr(x_absmax), b, cin, h, w,
+              _ptr(packed), _ptr(last_bias), cout, k, num_rotations, int(reflect), n_layers, _ptr(act), _ptr(idx), _ptr(rot),
+              _ptr(refl), _ptr(onehot), _ptr(stats), _ptr(scratch), scratch_bytes, _stream(dev))
+        act._eqb_selection = (num_rotations, bool(reflect), idx, rot, refl, onehot, stats)
+    elif x_absmax is not None:
         _call("eqb_gconv_stack_run_scaled", 2, dev, _ptr(x), _ptr(x_absmax), b, cin, h, w, _ptr(packed), _ptr(last_bias), cout, k,
               num_rotations, int(reflect), n_layers, _ptr(act), _ptr(scratch), scratch_bytes, _stream(dev))
     else:

@@ -92,6 +92,15 @@ EQB_API int eqb_gconv_stack_run_scaled(const float *x, const float *x_absmax, in
                                        int reflect, int num_layers, float *act, void *scratch, int64_t scratch_bytes,
                                        void *stream);
 
+/* eqb_gconv_stack_run_scaled (x_absmax may be NULL: reduced here) with the group pool / select of eqb_group_pool_select
+ * (a9 + a13, basecanonicalization.py:221-256, :290-311; discrete_group.py:94-135) fused into its finish kernel: same
+ * outputs, bit for bit, as calling eqb_group_pool_select on `act`, without the extra launch.  `packed` is written (a
+ * 4-byte ticket the kernel resets itself): one network instance must not run on two streams at once. */
+EQB_API int eqb_gconv_stack_run_select(const float *x, const float *x_absmax, int B, int cin, int H, int W, void *packed,
+                                       const float *last_bias, int cout, int k, int num_rotations, int reflect,
+                                       int num_layers, float *act, int32_t *idx, float *rotation, float *reflection,
+                                       float *onehot, float *stats, void *scratch, int64_t scratch_bytes, void *stream);
+
 /* ---- a7  e2cnn-style conv stack with EXPANDED filters -> group activations ------------------
  * ESCNNEquivariantNetwork.forward in eval() (escnn_networks.py:93-117; modules built at :66-91):
  *   [ conv2d k x k (valid) + bias -> scale * . + shift (InnerBatchNorm, eval) -> ReLU ] x (L-1)

@@ -1790,3 +1790,42 @@ def test_tma_resize_equals_scalar_kernel_and_leaves_per_image_absmax(cuda_device
         assert torch.equal(y, y_ref)
         want = y_ref.abs().amax(dim=(1, 2, 3))
         assert torch.equal(y._eqb_absmax[:5], want) and torch.equal(y_ref._eqb_absmax[:5], want)
+
+
+def test_select_fused_into_the_finish_kernel_equals_the_select_kernel(cuda_device):
+    """eqb_gconv_stack_run_select == eqb_gconv_stack_run + eqb_group_pool_select, bit for bit (index, angle, reflection,
+    one-hot, the 5-float statistic), for C8 and D4, on consecutive calls (the last-block ticket resets itself), and the
+    canonicalizer picks the fused selection up without launching the select kernel."""
+    ops, GEIC, _, Net = _mods()
+    dev = cuda_device
+    for group_type, n_rot, cout in (("rotation", 8, 32), ("roto-reflection", 4, 8)):
+        torch.manual_seed(90)
+        net = Net((3, 40, 40), cout, 5, group_type, n_rot, 3, device="cpu").to(dev).eval()
+        reflect = group_type == "roto-reflection"
+        for trial, b in enumerate((37, 5, 37)):
+            x = torch.rand(b, 3, 40, 40, generator=torch.Generator().manual_seed(91 + trial)).to(dev)
+            with torch.no_grad():
+                net.fuse_select = True
+                act = net(x)
+                fused = act._eqb_selection
+                net.fuse_select = False
+                act_plain = net(x)
+                assert not hasattr(act_plain, "_eqb_selection")
+                assert torch.equal(act, act_plain)
+                idx, rot, refl, onehot, stats = ops.group_pool_select(act_plain, n_rot, reflect)
+            assert fused[0] == n_rot and fused[1] == reflect
+            assert torch.equal(fused[2], idx) and torch.equal(fused[3], rot) and torch.equal(fused[5], onehot)
+            assert (fused[4] is None and refl is None) or torch.equal(fused[4], refl)
+            assert torch.equal(fused[6], stats), (fused[6], stats)
+        net.fuse_select = True
+        can = GEIC(net, SimpleNamespace(beta=1.0, input_crop_ratio=0.8, resize_shape=40), (3, 64, 64)).eval()
+        xs = torch.rand(9, 3, 64, 64, generator=torch.Generator().manual_seed(95)).to(dev)
+        with torch.no_grad():
+            can(xs)                                # (eval() dropped the packed operands: the first call re-packs)
+            n0 = ops.launch_count
+            can(xs)
+            used = ops.launch_count - n0           # crop + resize (1), stack + finish/select (2), warp (1)
+            assert used == 4, used
+            want = ops.group_pool_select(can.canonicalization_info_dict["group_activations"], n_rot, reflect)
+            assert torch.equal(can.canonicalization_info_dict["group_element"].index, want[0])
+            assert float(can.get_prior_regularization_loss()) == float(want[4][3])
