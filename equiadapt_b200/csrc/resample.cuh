@@ -14,6 +14,8 @@ constexpr int PIX = TILE * TILE / THREADS;  // 4 pixels per thread
 
 enum { MODE_CANON = 0, MODE_INV_SCALAR = 1, MODE_INV_REGULAR = 2, MODE_ORBIT = 3, MODE_AFFINE = 4 };
 
+struct TileGeom;   // per-(group element, tile) geometry of the TMA kernel (resample_tma.cu)
+
 struct ResampleArgs {
     const float *src;
     float *dst;
@@ -39,6 +41,8 @@ struct ResampleArgs {
     const float *refl;
     int mats_forward;
     double scx, scy;
+    // TMA path, discrete modes: [G][tiles_y * tiles_x] table built once per call shape (null: every CTA computes its own)
+    const TileGeom *geom;
 };
 
 // fills tiles_x / tiles_y / cs

@@ -21,6 +21,7 @@
 // Algorithmic traffic per sample: 1 read + 1 write of the image (SURVEY.md 8d "W"); the 2x footprint overlap of
 // rotated tiles is served by L2.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include <algorithm>
 
@@ -87,6 +88,105 @@ __device__ __forceinline__ int regular_src_channel(const ResampleArgs &a, int cs
     return f * a.G + sg;
 }
 
+// Geometry of the 32x32 destination tile at (tx0, ty0) under group element g (discrete modes) or the matrix of sample
+// `sample_s` (MODE_AFFINE): fp64 throughout (~400 instructions), evaluated once per (g, tile) into a table by
+// tile_geometry_kernel instead of by every CTA (it was ~1.2 us of every CTA's ~4.5 us life).
+__device__ TileGeom tile_geometry(const ResampleArgs &a, int g, int sample_s, int tx0, int ty0) {
+    TileGeom geo;
+    int r = 0, mirror_src = 0, mirror_dst = 0;
+    double sign = 1.0;
+    if (a.mode == MODE_ORBIT) {
+        r = g % a.N;
+        mirror_dst = g >= a.N;  // rotate, THEN hflip (discrete_group.py:404-406)
+        sign = -1.0;
+    } else if (a.mode != MODE_AFFINE) {
+        r = g % a.N;
+        const int refl = g >= a.N;
+        if (a.mode == MODE_CANON) {
+            mirror_src = refl;  // hflip, THEN rotate(-theta) (discrete_group.py:209-213)
+            sign = -1.0;
+        } else {
+            mirror_dst = a.reflect && !refl;  // images/utils.py:59-64 (reference quirk A.4-2)
+            sign = 1.0;
+        }
+    }
+    double a00, a01, a10, a11;
+    double cx = 0.5 * (a.Ws - 1), cy = 0.5 * (a.Hs - 1);
+    if (a.mode == MODE_AFFINE) {   // per-sample 2x2 matrix (continuous groups), see resample.cu
+        const float *m = a.mats + 4 * (size_t)sample_s;
+        const double m00 = m[0], m01 = m[1], m10 = m[2], m11 = m[3];
+        if (a.mats_forward) {
+            const double det = m00 * m11 - m01 * m10;
+            a00 = m11 / det; a01 = -m01 / det; a10 = -m10 / det; a11 = m00 / det;
+        } else {
+            a00 = m00; a01 = m01; a10 = m10; a11 = m11;
+        }
+        cx = a.scx; cy = a.scy;
+        if (a.refl && a.refl[sample_s] > 0.5f) {
+            a00 = -a00; a01 = -a01;
+            cx = (double)(a.Ws - 1) - cx;
+        }
+    } else {
+        double c, s;
+        group_cs(a, r, sign, c, s);
+        a00 = c; a01 = -s; a10 = s; a11 = c;
+        if (mirror_dst) { a00 = -a00; a10 = -a10; }
+        if (mirror_src) { a00 = -a00; a01 = -a01; }
+    }
+    // a signed permutation matrix (quarter turns / mirrors): candidates for the exact path
+    const bool unit = (fabs(a00) == 1.0 && a01 == 0.0 && a10 == 0.0 && fabs(a11) == 1.0) ||
+                      (a00 == 0.0 && fabs(a01) == 1.0 && fabs(a10) == 1.0 && a11 == 0.0);
+    // ---- source footprint of the tile ----------------------------------------------------------
+    const int tw = min(TILE, a.Wd - tx0), th = min(TILE, a.Hd - ty0);
+    const double u0 = (double)tx0 + a.ox, v0 = (double)ty0 + a.oy;
+    const double xs_org = cx + a00 * u0 + a01 * v0, ys_org = cy + a10 * u0 + a11 * v0;  // source of (tx0,ty0)
+    const double dw = (double)(tw - 1), dh = (double)(th - 1);
+    const double xmin = xs_org + fmin(a00 * dw, 0.0) + fmin(a01 * dh, 0.0);
+    const double xmax = xs_org + fmax(a00 * dw, 0.0) + fmax(a01 * dh, 0.0);
+    const double ymin = ys_org + fmin(a10 * dw, 0.0) + fmin(a11 * dh, 0.0);
+    const double ymax = ys_org + fmax(a10 * dw, 0.0) + fmax(a11 * dh, 0.0);
+    const int fxmin = (int)floor(xmin), fxmax = (int)floor(xmax), fymin = (int)floor(ymin), fymax = (int)floor(ymax);
+    // exact tile: quarter turn (cos / sin are exact 0 / +-1 there), integral source coordinates, no clamping,
+    // source tile starting on a 16-byte boundary (always true for square images whose side is a multiple of 4)
+    // footprint of any rotation fits the 52 x 48 box; a matrix that expands the tile (not a group element) cannot
+    const bool fits = (xmax - xmin) <= 46.0 && (ymax - ymin) <= 46.0 && xmin > -1e9 && xmax < 1e9 && ymin > -1e9 && ymax < 1e9;
+    const bool exact = unit && xs_org == floor(xs_org) && ys_org == floor(ys_org) && fxmin >= 0 &&
+                       fxmax <= a.Ws - 1 && fymin >= 0 && fymax <= a.Hs - 1 && (fxmin & 3) == 0;
+    // interior tile: every tap, even one pixel beyond the fp64 footprint (fp32 rounding of the per-pixel
+    // coordinates may floor() to the neighbour), lies inside the image -> no clamping in the pixel loop
+    const bool interior = !exact && fits && fxmin >= 1 && fxmax + 2 <= a.Ws - 1 && fymin >= 1 && fymax + 2 <= a.Hs - 1;
+    int box_x, box_y, y_lo = 0, cx_lo = 0, cx_hi = 0, bhm1 = 0;
+    if (exact) {
+        box_x = fxmin; box_y = fymin;
+    } else if (interior) {
+        box_x = (fxmin - 1) & ~3; box_y = fymin - 1; y_lo = box_y;     // <= 1 + 46 + 1 + 3 = 51 < 52 wide
+    } else {
+        const int x_lo = min(max(fxmin, 0), a.Ws - 1);
+        y_lo = min(max(fymin, 0), a.Hs - 1);
+        box_x = x_lo & ~3; box_y = y_lo;                               // 16-byte aligned start
+        cx_lo = x_lo - box_x;                                          // taps are clamped into [cx_lo, cx_hi]
+        cx_hi = min(min(max(fxmax + 1, 0), a.Ws - 1) - box_x, BOXW - 1);   // <= 46 + 3 for a group element
+        bhm1 = min(min(max(fymax + 1, 0), a.Hs - 1) - y_lo, BOXH - 1);     // <= 46
+        cx_lo = min(cx_lo, cx_hi);
+    }
+    geo.exact = exact; geo.interior = interior; geo.box_x = box_x; geo.box_y = box_y; geo.y_lo = y_lo;
+    geo.cx_lo = cx_lo; geo.cx_hi = cx_hi; geo.bhm1 = bhm1;
+    geo.bx = (float)(xs_org - (double)box_x); geo.by = (float)(ys_org - (double)box_y);
+    geo.f00 = (float)a00; geo.f01 = (float)a01; geo.f10 = (float)a10; geo.f11 = (float)a11;
+    geo.i00 = (int)a00; geo.i01 = (int)a01; geo.i10 = (int)a10; geo.i11 = (int)a11;
+    geo.sx0 = (int)xs_org - box_x; geo.sy0 = (int)ys_org - box_y;
+    geo.r = r; geo.plane0 = 0;
+    return geo;
+}
+
+__global__ void tile_geometry_kernel(const ResampleArgs a, TileGeom *__restrict__ table) {
+    const int tiles = a.tiles_x * a.tiles_y;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= a.G * tiles) return;
+    const int g = t / tiles, tile = t - g * tiles;
+    table[t] = tile_geometry(a, g, 0, (tile % a.tiles_x) * TILE, (tile / a.tiles_x) * TILE);
+}
+
 template <int CG, bool ZERO>
 __global__ void __launch_bounds__(THREADS, 6) resample_tma_kernel(const __grid_constant__ CUtensorMap map_box,
                                                                   const __grid_constant__ CUtensorMap map_tile,
@@ -106,106 +206,25 @@ __global__ void __launch_bounds__(THREADS, 6) resample_tma_kernel(const __grid_c
         if (lane == 0) {
             mbar_init(bar, 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        }
-        // ---- group element of this sample -> A ------------------------------------------------------
-        int sample_s, r = 0, mirror_src = 0, mirror_dst = 0;
-        double sign = 1.0;
-        if (a.mode == MODE_AFFINE) {
-            sample_s = sample_d;
-        } else if (a.mode == MODE_ORBIT) {
-            const int g = sample_d / a.B;
-            sample_s = sample_d - g * a.B;
-            r = g % a.N;
-            mirror_dst = g >= a.N;  // rotate, THEN hflip (discrete_group.py:404-406)
-            sign = -1.0;
-        } else {
-            sample_s = sample_d;
-            const int g = min(max(a.idx[sample_s], 0), a.G - 1);
-            r = g % a.N;
-            const int refl = g >= a.N;
-            if (a.mode == MODE_CANON) {
-                mirror_src = refl;  // hflip, THEN rotate(-theta) (discrete_group.py:209-213)
-                sign = -1.0;
-            } else {
-                mirror_dst = a.reflect && !refl;  // images/utils.py:59-64 (reference quirk A.4-2)
-                sign = 1.0;
+            // group element of this sample -> geometry of the tile: from the per-call-shape table (one 80-byte read) for the
+            // discrete modes, computed here for per-sample matrices
+            int sample_s = sample_d, g = 0;
+            if (a.mode == MODE_ORBIT) {
+                g = sample_d / a.B;
+                sample_s = sample_d - g * a.B;
+            } else if (a.mode != MODE_AFFINE) {
+                g = min(max(a.idx[sample_s], 0), a.G - 1);
             }
-        }
-        double a00, a01, a10, a11;
-        double cx = 0.5 * (a.Ws - 1), cy = 0.5 * (a.Hs - 1);
-        if (a.mode == MODE_AFFINE) {   // per-sample 2x2 matrix (continuous groups), see resample.cu
-            const float *m = a.mats + 4 * (size_t)sample_s;
-            const double m00 = m[0], m01 = m[1], m10 = m[2], m11 = m[3];
-            if (a.mats_forward) {
-                const double det = m00 * m11 - m01 * m10;
-                a00 = m11 / det; a01 = -m01 / det; a10 = -m10 / det; a11 = m00 / det;
-            } else {
-                a00 = m00; a01 = m01; a10 = m10; a11 = m11;
-            }
-            cx = a.scx; cy = a.scy;
-            if (a.refl && a.refl[sample_s] > 0.5f) {
-                a00 = -a00; a01 = -a01;
-                cx = (double)(a.Ws - 1) - cx;
-            }
-        } else {
-            double c, s;
-            group_cs(a, r, sign, c, s);
-            a00 = c; a01 = -s; a10 = s; a11 = c;
-            if (mirror_dst) { a00 = -a00; a10 = -a10; }
-            if (mirror_src) { a00 = -a00; a01 = -a01; }
-        }
-        // a signed permutation matrix (quarter turns / mirrors): candidates for the exact path
-        const bool unit = (fabs(a00) == 1.0 && a01 == 0.0 && a10 == 0.0 && fabs(a11) == 1.0) ||
-                          (a00 == 0.0 && fabs(a01) == 1.0 && fabs(a10) == 1.0 && a11 == 0.0);
-        // ---- source footprint of the tile ----------------------------------------------------------
-        const int tw = min(TILE, a.Wd - tx0), th = min(TILE, a.Hd - ty0);
-        const double u0 = (double)tx0 + a.ox, v0 = (double)ty0 + a.oy;
-        const double xs_org = cx + a00 * u0 + a01 * v0, ys_org = cy + a10 * u0 + a11 * v0;  // source of (tx0,ty0)
-        const double dw = (double)(tw - 1), dh = (double)(th - 1);
-        const double xmin = xs_org + fmin(a00 * dw, 0.0) + fmin(a01 * dh, 0.0);
-        const double xmax = xs_org + fmax(a00 * dw, 0.0) + fmax(a01 * dh, 0.0);
-        const double ymin = ys_org + fmin(a10 * dw, 0.0) + fmin(a11 * dh, 0.0);
-        const double ymax = ys_org + fmax(a10 * dw, 0.0) + fmax(a11 * dh, 0.0);
-        const int fxmin = (int)floor(xmin), fxmax = (int)floor(xmax), fymin = (int)floor(ymin), fymax = (int)floor(ymax);
-        // exact tile: quarter turn (cos / sin are exact 0 / +-1 there), integral source coordinates, no clamping,
-        // source tile starting on a 16-byte boundary (always true for square images whose side is a multiple of 4)
-        // footprint of any rotation fits the 52 x 48 box; a matrix that expands the tile (not a group element) cannot
-        const bool fits = (xmax - xmin) <= 46.0 && (ymax - ymin) <= 46.0 && xmin > -1e9 && xmax < 1e9 && ymin > -1e9 && ymax < 1e9;
-        const bool exact = unit && xs_org == floor(xs_org) && ys_org == floor(ys_org) && fxmin >= 0 &&
-                           fxmax <= a.Ws - 1 && fymin >= 0 && fymax <= a.Hs - 1 && (fxmin & 3) == 0;
-        // interior tile: every tap, even one pixel beyond the fp64 footprint (fp32 rounding of the per-pixel
-        // coordinates may floor() to the neighbour), lies inside the image -> no clamping in the pixel loop
-        const bool interior = !exact && fits && fxmin >= 1 && fxmax + 2 <= a.Ws - 1 && fymin >= 1 && fymax + 2 <= a.Hs - 1;
-        int box_x, box_y, y_lo = 0, cx_lo = 0, cx_hi = 0, bhm1 = 0;
-        if (exact) {
-            box_x = fxmin; box_y = fymin;
-        } else if (interior) {
-            box_x = (fxmin - 1) & ~3; box_y = fymin - 1; y_lo = box_y;     // <= 1 + 46 + 1 + 3 = 51 < 52 wide
-        } else {
-            const int x_lo = min(max(fxmin, 0), a.Ws - 1);
-            y_lo = min(max(fymin, 0), a.Hs - 1);
-            box_x = x_lo & ~3; box_y = y_lo;                               // 16-byte aligned start
-            cx_lo = x_lo - box_x;                                          // taps are clamped into [cx_lo, cx_hi]
-            cx_hi = min(min(max(fxmax + 1, 0), a.Ws - 1) - box_x, BOXW - 1);   // <= 46 + 3 for a group element
-            bhm1 = min(min(max(fymax + 1, 0), a.Hs - 1) - y_lo, BOXH - 1);     // <= 46
-            cx_lo = min(cx_lo, cx_hi);
-        }
-        const int plane0 = sample_s * a.C;  // first source plane of this sample in the (W,H,B*C) tensor map
-        if (lane == 0) {
+            if (a.geom) geo = a.geom[(size_t)g * (a.tiles_x * a.tiles_y) + blockIdx.y * a.tiles_x + blockIdx.x];
+            else geo = tile_geometry(a, g, sample_s, tx0, ty0);
+            geo.plane0 = sample_s * a.C;   // first source plane of this sample in the (W,H,B*C) tensor map
             // first pass of the TMA loads goes out before anybody else needs the geometry
             const int nc = min(CG, a.C);
-            mbar_expect_tx(bar, (uint32_t)nc * (exact ? TILE_BYTES : BOX_BYTES));
+            mbar_expect_tx(bar, (uint32_t)nc * (geo.exact ? TILE_BYTES : BOX_BYTES));
             for (int cc = 0; cc < nc; ++cc) {
-                const int cs = a.mode == MODE_INV_REGULAR ? regular_src_channel(a, cc, r) : cc;
-                tma_load_3d(base + cc * PLANE_BYTES, exact ? &map_tile : &map_box, bar, box_x, box_y, plane0 + cs);
+                const int cs = a.mode == MODE_INV_REGULAR ? regular_src_channel(a, cc, geo.r) : cc;
+                tma_load_3d(base + cc * PLANE_BYTES, geo.exact ? &map_tile : &map_box, bar, geo.box_x, geo.box_y, geo.plane0 + cs);
             }
-            geo.exact = exact; geo.interior = interior; geo.box_x = box_x; geo.box_y = box_y; geo.y_lo = y_lo;
-            geo.cx_lo = cx_lo; geo.cx_hi = cx_hi; geo.bhm1 = bhm1;
-            geo.bx = (float)(xs_org - (double)box_x); geo.by = (float)(ys_org - (double)box_y);
-            geo.f00 = (float)a00; geo.f01 = (float)a01; geo.f10 = (float)a10; geo.f11 = (float)a11;
-            geo.i00 = (int)a00; geo.i01 = (int)a01; geo.i10 = (int)a10; geo.i11 = (int)a11;
-            geo.sx0 = (int)xs_org - box_x; geo.sy0 = (int)ys_org - box_y;
-            geo.r = r; geo.plane0 = plane0;
         }
     }
     __syncthreads();
@@ -369,8 +388,52 @@ static int launch_cfg(const CUtensorMap &mb, const CUtensorMap &mt, ResampleArgs
     return 0;
 }
 
-int launch_resample_tma(const ResampleArgs &a, int n_dst_samples, cudaStream_t st, const char *what, int *handled) {
+// Geometry tables, one per (device, call shape), built on first use by tile_geometry_kernel and kept for the life of the
+// process (a few KB each).  Building one allocates device memory, which a stream capture forbids: capture after a warm-up
+// call (graphed.CapturedStep does), as for every other lazily created resource of this library.
+struct GeomKey {
+    int dev, mode, N, reflect, G, Hs, Ws, Hd, Wd, pad, has_cs;
+    double ox, oy;
+    bool operator==(const GeomKey &o) const {
+        return dev == o.dev && mode == o.mode && N == o.N && reflect == o.reflect && G == o.G && Hs == o.Hs && Ws == o.Ws &&
+               Hd == o.Hd && Wd == o.Wd && pad == o.pad && has_cs == o.has_cs && ox == o.ox && oy == o.oy;
+    }
+};
+static int geometry_table(const ResampleArgs &a, cudaStream_t st, const TileGeom **out) {
+    constexpr int MAX_TABLES = 64;
+    static GeomKey keys[MAX_TABLES];
+    static TileGeom *tables[MAX_TABLES];
+    static int count = 0;
+    *out = nullptr;
+    if (a.mode == MODE_AFFINE || a.G <= 0 || a.G > 64 || getenv("EQB_WARP_NO_TABLE")) return 0;
+    const GeomKey k{current_device(), a.mode, a.N, a.reflect, a.G, a.Hs, a.Ws, a.Hd, a.Wd, a.pad, a.has_cs, a.ox, a.oy};
+    for (int i = 0; i < count; ++i)
+        if (keys[i] == k) {
+            *out = tables[i];
+            return 0;
+        }
+    if (count == MAX_TABLES) return 0;           // beyond the cache: CTAs compute their own geometry
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cap) == cudaSuccess && cap != cudaStreamCaptureStatusNone) return 0;   // (no allocation in a capture)
+    const int n = a.G * a.tiles_x * a.tiles_y;
+    TileGeom *t = nullptr;
+    EQB_CUDA(cudaMalloc((void **)&t, (size_t)n * sizeof(TileGeom)));
+    ResampleArgs b = a;
+    b.geom = nullptr;
+    tile_geometry_kernel<<<(n + 127) / 128, 128, 0, st>>>(b, t);
+    EQB_CUDA(cudaGetLastError());
+    EQB_CUDA(cudaStreamSynchronize(st));         // other streams may use the table from now on
+    keys[count] = k;
+    tables[count] = t;
+    ++count;
+    *out = t;
+    return 0;
+}
+
+int launch_resample_tma(const ResampleArgs &a_in, int n_dst_samples, cudaStream_t st, const char *what, int *handled) {
     *handled = 0;
+    ResampleArgs a = a_in;
+    a.geom = nullptr;
     const long long planes = (long long)a.B * a.C;
     if (((uintptr_t)a.src & 15) != 0 || (a.Ws & 3) != 0 || a.Ws < BOXW || a.Hs < BOXH || planes <= 0 ||
         planes >= (1LL << 31) || (long long)a.C * a.Hd * a.Wd >= (1LL << 31) || a.tiles_y > 65535)
@@ -381,7 +444,9 @@ int launch_resample_tma(const ResampleArgs &a, int n_dst_samples, cudaStream_t s
         return 0;
     }
     CUtensorMap mb, mt;
-    int e = make_plane_map(&mb, a.src, a.Ws, a.Hs, planes, BOXW, BOXH, CU_TENSOR_MAP_SWIZZLE_NONE);
+    int e = geometry_table(a, st, &a.geom);
+    if (e) return e;
+    e = make_plane_map(&mb, a.src, a.Ws, a.Hs, planes, BOXW, BOXH, CU_TENSOR_MAP_SWIZZLE_NONE);
     if (e) return e;
     e = make_plane_map(&mt, a.src, a.Ws, a.Hs, planes, TILE, TILE, CU_TENSOR_MAP_SWIZZLE_128B);
     if (e) return e;

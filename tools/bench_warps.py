@@ -29,3 +29,9 @@ for b in (32, 256):
     us = timeit(lambda: ops.orbit_expand(xr, 48, 96, 4, True))
     byt = xr.numel() * 4 * (1 + 8)
     print(f"orbit expand D4, {b}x3x96x96 -> {8 * b}x3x96x96: {us:.1f} us, {byt / us / 1e3:.0f} GB/s = {byt / us / 1e3 / peak:.3f} of HBM peak")
+# the bench step's case: every sample on an odd C8 element (all-bilinear tiles)
+idx_odd = (torch.randint(0, 4, (512,), device=dev, dtype=torch.int32) * 2 + 1)
+us = timeit(lambda: ops.warp_canonicalize(x3, idx_odd, 8, False))
+print(f"canonicalize (all odd C8 elements), 512x3x224x224: {us:.1f} us, {2 * x3.numel() * 4 / us / 1e3 / peak:.3f} of HBM peak")
+us = timeit(lambda: ops.warp_invert(x3, idx_odd, 8, False, False))
+print(f"invert scalar (all odd C8 elements), 512x3x224x224: {us:.1f} us, {2 * x3.numel() * 4 / us / 1e3 / peak:.3f} of HBM peak")
