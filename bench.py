@@ -817,26 +817,29 @@ def run_b200(args):
         step_us = sum(k["avg_us"] * k["calls_per_step"] for k in kernels.values())
         dom = max(kernels, key=lambda n: kernels[n]["avg_us"] * kernels[n]["calls_per_step"])
         rooflines = {}
-        if "eqb_gconv_stack_run" in kernels:
+        stack_key = next((k for k in kernels if k.startswith("eqb_gconv_stack_run")), None)
+        if stack_key:
             # SURVEY.md 8d "N": algorithmic work = the contraction as the REFERENCE computes it (2.544 GFLOP/img);
             # the kernel executes 1.434 GFLOP/img (last layer folded through the mean) x 3 (fp16 hi/lo operand split).
             # Peak = the BURST bf16 figure (a kernel timed alone over a 40 ms region), the sustained one beside it.
-            us = kernels["eqb_gconv_stack_run"]["avg_us"]
+            us = kernels[stack_key]["avg_us"]
             ach = STACK_FLOP_REFERENCE * B / (us * 1e-6) / 1e12
-            rooflines["eqb_gconv_stack_run"] = {
+            rooflines[stack_key] = {
                 "bound": "tensor", "achieved": ach, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
                 "frac": ach / pk["bf16_tflops"], "frac_of_sustained_peak": ach / pk["bf16_tflops_sustained"],
                 "traffic": traffic.get("eqb_gconv_stack_run"),
                 "executed_tflops": 3 * STACK_FLOP_EXECUTED * B / (us * 1e-6) / 1e12,
                 "note": ("algorithmic FLOPs = the reference's dense contraction, 2.544 GFLOP/img (SURVEY 8d), against the bf16 "
                          "tensor peak (" + pk["source"] + ", burst); executed_tflops = what the tensor pipe runs: 1.434 GFLOP/img "
-                         "(last layer folded) x 3 fp16 hi/lo products of kind::f16 MMA")}
-        for name, byt in (("eqb_warp_canonicalize", IMG_BYTES), ("eqb_warp_invert", IMG_BYTES),
-                          ("eqb_crop_resize_aa", (3 * 180 * 180 + 3 * 96 * 96) * 4)):
-            if name in kernels:
+                         "(last layer folded) x 3 fp16 hi/lo products of kind::f16 MMA; the call = CTA-pair tcgen05 stack kernel + "
+                         "finish kernel (fold, group select, prior statistic)")}
+        for prefix, byt in (("eqb_warp_canonicalize", IMG_BYTES), ("eqb_warp_invert", IMG_BYTES),
+                            ("eqb_crop_resize_aa", (3 * 180 * 180 + 3 * 96 * 96) * 4)):
+            name = next((k for k in kernels if k.startswith(prefix)), None)
+            if name:
                 ach = byt * B / (kernels[name]["avg_us"] * 1e-6) / 1e9
                 rooflines[name] = {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                                   "frac": ach / pk["hbm_gbs"], "traffic": traffic.get(name)}
+                                   "frac": ach / pk["hbm_gbs"], "traffic": traffic.get(prefix)}
         for name in kernels:
             kernels[name]["share_of_step"] = kernels[name]["avg_us"] * kernels[name]["calls_per_step"] / step_us
         cpu = None
