@@ -1315,6 +1315,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(768, 1) gconv_stack_
     constexpr int NC1 = 8;                       // N = 256: 32-wide K atoms of the 1x1 GEMM
     const int groups = a.epi1_groups;
     const int lift_at = a.lift_at;               // pass 0 of the next tile's lift is queued behind this K atom of the 1x1 GEMM
+    // Issuer-side waits on barriers the peer CTA arrives on.  cta_waits: plain (CTA-scope acquire) try_wait as CUTLASS's
+    // ClusterBarrier::wait does -- what these barriers publish is read by the tensor core through the async proxy, made visible
+    // by the producers' fence.proxy.async and ordered by tcgen05.fence::after_thread_sync; the cluster-scope acquire variant
+    // costs noticeably more per poll
+    const bool cta_waits = a.cta_waits != 0;
+    auto mbar_wait_fast = [&](uint32_t b, uint32_t parity, int id) {
+        if (cta_waits) mbar_wait(b, parity, id);
+        else mbar_wait_cluster(b, parity, id);
+    };
     if ((base & 1023u) != 0) __trap();           // swizzled operand images need the 1024-byte aligned window
     const unsigned char *img = a.wpack + HDR_BYTES;
     const uint32_t gstage = 256u * 64u;          // bytes of one packed stage in global memory (tc_pack)
@@ -1414,11 +1423,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(768, 1) gconv_stack_
             uint32_t tile_phase = 0;
             const uint32_t a1_lo0 = desc_lo(base + M.a1_ring), w1_lo0 = desc_lo(base + M.w1);
             for (TileWalk tw = walk(); tw.valid(); tw.next()) {
+                // the first A1 atom of a tile is ready long before D2t is drained: confirm it FIRST, so that the poll (a
+                // few hundred cycles even on a completed barrier) is off the drain -> first-MMA critical path
+                mbar_wait_fast(bar(B_A1FULL + r1.stage), r1.phase, B_A1FULL + r1.stage);
                 TR(0);
-                mbar_wait_cluster(bar(B_D2EMPTY), tile_phase ^ 1u, B_D2EMPTY);
+                mbar_wait_fast(bar(B_D2EMPTY), tile_phase ^ 1u, B_D2EMPTY);
                 TR(1);
                 for (int kc = 0; kc < NC1; ++kc) {
-                    mbar_wait_cluster(bar(B_A1FULL + r1.stage), r1.phase, B_A1FULL + r1.stage);
+                    if (kc) mbar_wait_fast(bar(B_A1FULL + r1.stage), r1.phase, B_A1FULL + r1.stage);
                     TR(2 + kc);
                     tc_fence_after();
                     if (elect_one()) {
@@ -1936,6 +1948,8 @@ int tc_launch(TcArgs a, cudaStream_t st) {
         a.trace_tiles = g_trace_tiles;
         const char *p2 = getenv("EQB_TC_PAIR2"), *la = getenv("EQB_TC_LIFT_AT");
         a.lift_at = la && la[0] >= '3' && la[0] <= '7' ? la[0] - '0' : 5;
+        const char *cw = getenv("EQB_TC_CTA_WAITS");
+        a.cta_waits = cw && cw[0] == '1' ? 1 : 0;
         if (!(p2 && p2[0] == '0')) {
             // second-generation pipeline (lift behind the 1x1 GEMM in two channel passes, resident patch slabs, streamed W0)
             const tc::pair2::Smem M2 = tc::pair2::smem_map(a.K0pad);
