@@ -729,7 +729,7 @@ def prior_stats_continuous(rep: torch.Tensor) -> torch.Tensor:
     if d != d2:
         raise ValueError("expected square group-element matrices")
     stats = torch.empty((5,), dtype=torch.float32, device=dev)
-    _call("eqb_prior_stats_continuous", 1 if b * d * d <= 262144 else 2, dev, _ptr(rep), b, d, _ptr(stats), _stream(dev))
+    _call("eqb_prior_stats_continuous", 1, dev, _ptr(rep), b, d, _ptr(stats), _stream(dev))
     return stats
 
 
