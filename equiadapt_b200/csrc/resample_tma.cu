@@ -187,73 +187,19 @@ __global__ void tile_geometry_kernel(const ResampleArgs a, TileGeom *__restrict_
     table[t] = tile_geometry(a, g, 0, (tile % a.tiles_x) * TILE, (tile / a.tiles_x) * TILE);
 }
 
+// One channel pass (nc <= CG planes starting at channel c0) of one 32x32 destination tile whose source box(es) sit in shared
+// memory at sm0: shared by the one-tile-per-CTA kernel and the persistent kernel.  8 warps: lane = x, warp = first row.
 template <int CG, bool ZERO>
-__global__ void __launch_bounds__(THREADS, 6) resample_tma_kernel(const __grid_constant__ CUtensorMap map_box,
-                                                                  const __grid_constant__ CUtensorMap map_tile,
-                                                                  const __grid_constant__ ResampleArgs a) {
-    extern __shared__ unsigned char smem_raw[];
-    // [CG planes, 10 KB apart, 1024-aligned][mbarrier][TileGeom]
-    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    unsigned char *aligned = smem_raw + (base - smem_u32(smem_raw));
-    const uint32_t bar = base + CG * PLANE_BYTES;
-    TileGeom &geo = *reinterpret_cast<TileGeom *>(aligned + CG * PLANE_BYTES + 16);
-
-    const int sample_d = blockIdx.z + a.sample0;  // destination sample
-    const int ty0 = blockIdx.y * TILE, tx0 = blockIdx.x * TILE;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-
-    if (warp == 0) {
-        if (lane == 0) {
-            mbar_init(bar, 1);
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-            // group element of this sample -> geometry of the tile: from the per-call-shape table (one 80-byte read) for the
-            // discrete modes, computed here for per-sample matrices
-            int sample_s = sample_d, g = 0;
-            if (a.mode == MODE_ORBIT) {
-                g = sample_d / a.B;
-                sample_s = sample_d - g * a.B;
-            } else if (a.mode != MODE_AFFINE) {
-                g = min(max(a.idx[sample_s], 0), a.G - 1);
-            }
-            if (a.geom) geo = a.geom[(size_t)g * (a.tiles_x * a.tiles_y) + blockIdx.y * a.tiles_x + blockIdx.x];
-            else geo = tile_geometry(a, g, sample_s, tx0, ty0);
-            geo.plane0 = sample_s * a.C;   // first source plane of this sample in the (W,H,B*C) tensor map
-            // first pass of the TMA loads goes out before anybody else needs the geometry
-            const int nc = min(CG, a.C);
-            mbar_expect_tx(bar, (uint32_t)nc * (geo.exact ? TILE_BYTES : BOX_BYTES));
-            for (int cc = 0; cc < nc; ++cc) {
-                const int cs = a.mode == MODE_INV_REGULAR ? regular_src_channel(a, cc, geo.r) : cc;
-                tma_load_3d(base + cc * PLANE_BYTES, geo.exact ? &map_tile : &map_box, bar, geo.box_x, geo.box_y, geo.plane0 + cs);
-            }
-        }
-    }
-    __syncthreads();
-
+__device__ __forceinline__ void resample_tile_pass(const ResampleArgs &a, const TileGeom &geo, uint32_t sm0, int sample_d,
+                                                   int tx0, int ty0, int c0, int nc, int warp, int lane) {
     const bool exact = geo.exact != 0;
     const int xd = tx0 + lane;
+    if (xd >= a.Wd) return;
     const int plane_d = a.Hd * a.Wd;                       // host guarantees C * Hd * Wd < 2^31
     float *dst_px = a.dst + (size_t)sample_d * a.C * plane_d + (size_t)(ty0 + warp) * a.Wd + xd;
     const int row_step = (THREADS / 32) * a.Wd;            // this thread's pixels are 8 rows apart
     const int rows_left = a.Hd - ty0 - warp;               // pixel p is inside the image iff p*8 < rows_left
-    const uint32_t sm0 = base;
-
-    uint32_t parity = 0;
-    for (int c0 = 0; c0 < a.C; c0 += CG) {
-        const int nc = min(CG, a.C - c0);
-        if (c0) {
-            __syncthreads();  // every thread is done reading the planes of the previous pass
-            if (threadIdx.x == 0) {
-                mbar_expect_tx(bar, (uint32_t)nc * (exact ? TILE_BYTES : BOX_BYTES));
-                for (int cc = 0; cc < nc; ++cc) {
-                    const int cs = a.mode == MODE_INV_REGULAR ? regular_src_channel(a, c0 + cc, geo.r) : c0 + cc;
-                    tma_load_3d(base + cc * PLANE_BYTES, exact ? &map_tile : &map_box, bar, geo.box_x, geo.box_y,
-                                geo.plane0 + cs);
-                }
-            }
-        }
-        mbar_wait(bar, parity);
-        parity ^= 1u;
-        if (xd >= a.Wd) continue;  // (no barrier below this point inside the pass)
+    {
         float *dp = dst_px + (size_t)c0 * plane_d;
         if (exact) {
             const int sxl = geo.sx0 + geo.i00 * lane + geo.i01 * warp, syl = geo.sy0 + geo.i10 * lane + geo.i11 * warp;
@@ -330,6 +276,146 @@ __global__ void __launch_bounds__(THREADS, 6) resample_tma_kernel(const __grid_c
     }
 }
 
+template <int CG, bool ZERO>
+__global__ void __launch_bounds__(THREADS, 6) resample_tma_kernel(const __grid_constant__ CUtensorMap map_box,
+                                                                  const __grid_constant__ CUtensorMap map_tile,
+                                                                  const __grid_constant__ ResampleArgs a) {
+    extern __shared__ unsigned char smem_raw[];
+    // [CG planes, 10 KB apart, 1024-aligned][mbarrier][TileGeom]
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    unsigned char *aligned = smem_raw + (base - smem_u32(smem_raw));
+    const uint32_t bar = base + CG * PLANE_BYTES;
+    TileGeom &geo = *reinterpret_cast<TileGeom *>(aligned + CG * PLANE_BYTES + 16);
+
+    const int sample_d = blockIdx.z + a.sample0;  // destination sample
+    const int ty0 = blockIdx.y * TILE, tx0 = blockIdx.x * TILE;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_init(bar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            // group element of this sample -> geometry of the tile: from the per-call-shape table (one 80-byte read) for the
+            // discrete modes, computed here for per-sample matrices
+            int sample_s = sample_d, g = 0;
+            if (a.mode == MODE_ORBIT) {
+                g = sample_d / a.B;
+                sample_s = sample_d - g * a.B;
+            } else if (a.mode != MODE_AFFINE) {
+                g = min(max(a.idx[sample_s], 0), a.G - 1);
+            }
+            if (a.geom) geo = a.geom[(size_t)g * (a.tiles_x * a.tiles_y) + blockIdx.y * a.tiles_x + blockIdx.x];
+            else geo = tile_geometry(a, g, sample_s, tx0, ty0);
+            geo.plane0 = sample_s * a.C;   // first source plane of this sample in the (W,H,B*C) tensor map
+            // first pass of the TMA loads goes out before anybody else needs the geometry
+            const int nc = min(CG, a.C);
+            mbar_expect_tx(bar, (uint32_t)nc * (geo.exact ? TILE_BYTES : BOX_BYTES));
+            for (int cc = 0; cc < nc; ++cc) {
+                const int cs = a.mode == MODE_INV_REGULAR ? regular_src_channel(a, cc, geo.r) : cc;
+                tma_load_3d(base + cc * PLANE_BYTES, geo.exact ? &map_tile : &map_box, bar, geo.box_x, geo.box_y, geo.plane0 + cs);
+            }
+        }
+    }
+    __syncthreads();
+
+    const uint32_t sm0 = base;
+    uint32_t parity = 0;
+    for (int c0 = 0; c0 < a.C; c0 += CG) {
+        const int nc = min(CG, a.C - c0);
+        if (c0) {
+            __syncthreads();  // every thread is done reading the planes of the previous pass
+            if (threadIdx.x == 0) {
+                mbar_expect_tx(bar, (uint32_t)nc * (geo.exact ? TILE_BYTES : BOX_BYTES));
+                for (int cc = 0; cc < nc; ++cc) {
+                    const int cs = a.mode == MODE_INV_REGULAR ? regular_src_channel(a, c0 + cc, geo.r) : c0 + cc;
+                    tma_load_3d(base + cc * PLANE_BYTES, geo.exact ? &map_tile : &map_box, bar, geo.box_x, geo.box_y,
+                                geo.plane0 + cs);
+                }
+            }
+        }
+        mbar_wait(bar, parity);
+        parity ^= 1u;
+        resample_tile_pass<CG, ZERO>(a, geo, sm0, sample_d, tx0, ty0, c0, nc, warp, lane);
+    }
+}
+
+// Persistent variant: 3 CTAs per SM, each with a producer warp (warp 8: geometry of the next work unit from the table, TMA
+// loads into the other buffer) and 8 consumer warps (the pass above).  A work unit = (destination tile, channel pass); units
+// are dealt round-robin, tile x fastest, so the CTAs of a wave work on neighbouring tiles and their overlapping footprints
+// meet in L2.  The one-tile-per-CTA kernel above leaves the load/store pipe idle while a CTA computes its geometry, waits
+// for its box and winds down (6 CTAs per SM overlap only statistically: LSU 63 % busy, 0.70 of the HBM peak on all-bilinear
+// tiles); here the box of unit k+1 lands while unit k is computed.
+constexpr int P_THREADS = THREADS + 32;
+struct UnitInfo {
+    TileGeom geo;
+    int sample_d, tx0, ty0, c0, nc, pad_;
+};
+
+template <int CG, bool ZERO>
+__global__ void __launch_bounds__(P_THREADS, 3) resample_tma_persistent_kernel(const __grid_constant__ CUtensorMap map_box,
+                                                                               const __grid_constant__ CUtensorMap map_tile,
+                                                                               const __grid_constant__ ResampleArgs a,
+                                                                               const int total_units, const int passes) {
+    extern __shared__ unsigned char smem_raw[];
+    // [2 buffers x CG planes, 10 KB apart, 1024-aligned][full[2], empty[2]][UnitInfo[2]]
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    unsigned char *aligned = smem_raw + (base - smem_u32(smem_raw));
+    const uint32_t bars = base + 2 * CG * PLANE_BYTES;
+    UnitInfo *info = reinterpret_cast<UnitInfo *>(aligned + 2 * CG * PLANE_BYTES + 32);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+        mbar_init(bars, 1);          // full[0]
+        mbar_init(bars + 8, 1);      // full[1]
+        mbar_init(bars + 16, 8);     // empty[0]: one arrival per consumer warp
+        mbar_init(bars + 24, 8);     // empty[1]
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int tiles_per_sample = a.tiles_x * a.tiles_y;
+    if (warp == 8) {
+        if (lane == 0) {
+            int k = 0;
+            for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x, ++k) {
+                const int s = k & 1;
+                mbar_wait(bars + 16 + 8 * s, (((uint32_t)k >> 1) & 1u) ^ 1u);     // consumers are done with this buffer
+                const int pass = unit % passes, tile = unit / passes;
+                const int sample_d = tile / tiles_per_sample, t2 = tile - sample_d * tiles_per_sample;
+                const int tyi = t2 / a.tiles_x, txi = t2 - tyi * a.tiles_x;
+                int sample_s = sample_d, g = 0;
+                if (a.mode == MODE_ORBIT) {
+                    g = sample_d / a.B;
+                    sample_s = sample_d - g * a.B;
+                } else if (a.mode != MODE_AFFINE) {
+                    g = min(max(a.idx[sample_s], 0), a.G - 1);
+                }
+                UnitInfo &u = info[s];
+                if (a.geom) u.geo = a.geom[(size_t)g * tiles_per_sample + t2];
+                else u.geo = tile_geometry(a, g, sample_s, txi * TILE, tyi * TILE);
+                u.geo.plane0 = sample_s * a.C;
+                u.sample_d = sample_d; u.tx0 = txi * TILE; u.ty0 = tyi * TILE;
+                u.c0 = pass * CG; u.nc = min(CG, a.C - pass * CG);
+                const uint32_t full = bars + 8 * s, dst = base + s * CG * PLANE_BYTES;
+                mbar_expect_tx(full, (uint32_t)u.nc * (u.geo.exact ? TILE_BYTES : BOX_BYTES));
+                for (int cc = 0; cc < u.nc; ++cc) {
+                    const int cs = a.mode == MODE_INV_REGULAR ? regular_src_channel(a, u.c0 + cc, u.geo.r) : u.c0 + cc;
+                    tma_load_3d(dst + cc * PLANE_BYTES, u.geo.exact ? &map_tile : &map_box, full, u.geo.box_x, u.geo.box_y,
+                                u.geo.plane0 + cs);
+                }
+            }
+        }
+    } else {
+        int k = 0;
+        for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x, ++k) {
+            const int s = k & 1;
+            mbar_wait(bars + 8 * s, ((uint32_t)k >> 1) & 1u);
+            const UnitInfo &u = info[s];
+            resample_tile_pass<CG, ZERO>(a, u.geo, base + s * CG * PLANE_BYTES, u.sample_d, u.tx0, u.ty0, u.c0, u.nc, warp, lane);
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bars + 16 + 8 * s) : "memory");
+        }
+    }
+}
+
 // ---- host side ------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
@@ -373,6 +459,27 @@ int make_plane_map(CUtensorMap *m, const float *src, int W, int H, long long pla
 template <int CG, bool ZERO>
 static int launch_cfg(const CUtensorMap &mb, const CUtensorMap &mt, ResampleArgs a, int n_dst_samples,
                       cudaStream_t st) {
+    const char *pe = getenv("EQB_WARP_PERSISTENT");
+    const int passes = (a.C + CG - 1) / CG;
+    const long long units = (long long)a.tiles_x * a.tiles_y * n_dst_samples * passes;
+    // Persistent producer / consumer kernel where it measured faster: 3-channel images of >= 128 x 128 (canonicalize 132.9 ->
+    // 122.8 us, invert 133.4 -> 125.5 us on all-bilinear C8 elements at 512 x 3 x 224 x 224).  With four channels per pass its two
+    // buffers leave room for two CTAs per SM only (regular-representation invert: 315 -> 354 us) and on small images (orbit
+    // expand at 96 x 96: 50 -> 58 us) the 24 instead of 48 warps per SM cost more than the prefetch gains.
+    const bool want_persistent = pe ? pe[0] != '0' : (CG == 3 && a.Hs >= 128 && a.Ws >= 128);
+    if (want_persistent && units < (1LL << 31)) {
+        // the box of work unit k+1 lands while unit k is computed
+        const size_t smem = (size_t)2 * CG * PLANE_BYTES + 1024 + 32 + 2 * sizeof(UnitInfo);
+        static PerDeviceOnce configured_p;
+        if (configured_p.first()) {
+            EQB_CUDA(cudaFuncSetAttribute(resample_tma_persistent_kernel<CG, ZERO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)smem));
+        }
+        const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(3, (size_t)(227 * 1024) / (smem + 1024)));
+        const long long grid = std::min<long long>(units, (long long)per_sm * num_sms());
+        resample_tma_persistent_kernel<CG, ZERO><<<(unsigned)grid, P_THREADS, smem, st>>>(mb, mt, a, (int)units, passes);
+        return 0;
+    }
     const size_t smem = (size_t)CG * PLANE_BYTES + 1024 + 16 + sizeof(TileGeom);
     static PerDeviceOnce configured;
     if (configured.first()) {
