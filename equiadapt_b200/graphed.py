@@ -13,6 +13,10 @@ Semantics are the reference's (basecanonicalization.py:43-93): the captured call
 `canonicalizer(x)` -> `fn` -> `invert_canonicalization` -> `get_prior_regularization_loss` / `get_identity_metric`;
 the returned tensors and `canonicalization_info_dict` are static buffers that every replay overwrites.
 All ranks must capture and replay the same number of times when the prior statistic is synchronised.
+
+A captured step is an INFERENCE artefact: it replays the kernels on the buffers that existed at capture time, among them the
+packed filter orbits of the canonicalization network (networks_images.py).  After a parameter update (optimizer step,
+load_state_dict) capture again -- the eager calls repack by themselves, a graph cannot.
 """
 from __future__ import annotations
 
