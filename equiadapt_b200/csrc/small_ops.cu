@@ -203,11 +203,16 @@ __global__ void regular_orbit_kernel(const float *__restrict__ w, float *__restr
 // identity counts are reduced per block with warp shuffles and finished, in block order (so the
 // result is run-to-run deterministic), by the last block to arrive.
 // -------------------------------------------------------------------------------------------------
+// per-launch slots of the multi-block path (per-device globals; the host hands the slots out round-robin)
+constexpr int SEL_BLOCKS = 1024, SEL_SLOTS = 8;
+__device__ unsigned int g_sel_ticket[SEL_SLOTS];
+__device__ double g_sel_partial[SEL_SLOTS][2 * SEL_BLOCKS];
+
 __global__ void __launch_bounds__(256) group_pool_select_kernel(const float *__restrict__ act, int B, int N, int G,
                                                                 int32_t *__restrict__ idx, float *__restrict__ rotation,
                                                                 float *__restrict__ reflection,
                                                                 float *__restrict__ onehot, float *__restrict__ stats,
-                                                                double *__restrict__ partial) {
+                                                                int slot) {
     double ce = 0.0, ident = 0.0;
     for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) {
         const float *a = act + (size_t)b * G;
@@ -249,37 +254,25 @@ __global__ void __launch_bounds__(256) group_pool_select_kernel(const float *__r
             c += s_ce[w];
             d += s_id[w];
         }
-        if (gridDim.x == 1) {
-            stats[0] = (float)c;
-            stats[1] = (float)d;
-            stats[2] = (float)B;
-            stats[3] = (float)(c / (double)B);   // this batch's own means: read directly when there is one rank
-            stats[4] = (float)(d / (double)B);
-        } else {
-            partial[2 * blockIdx.x] = c;
-            partial[2 * blockIdx.x + 1] = d;
+        if (gridDim.x > 1) {
+            // several blocks (B > 8192): partials to a per-launch slot, the last block to finish adds them in block order
+            g_sel_partial[slot][2 * blockIdx.x] = c;
+            g_sel_partial[slot][2 * blockIdx.x + 1] = d;
+            __threadfence();
+            if (atomicAdd(&g_sel_ticket[slot], 1u) != gridDim.x - 1) return;
+            __threadfence();
+            c = d = 0.0;
+            for (unsigned int k = 0; k < gridDim.x; ++k) {
+                c += __ldcg(&g_sel_partial[slot][2 * k]);
+                d += __ldcg(&g_sel_partial[slot][2 * k + 1]);
+            }
+            g_sel_ticket[slot] = 0u;
         }
-    }
-}
-
-// sums `n` block partials (stride-2 pairs) in block order: run-to-run deterministic
-__global__ void finish_stats_kernel(const double *__restrict__ partial, int n, int pairs, float third,
-                                    float *__restrict__ stats) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    double c = 0.0, d = 0.0;
-    for (int k = 0; k < n; ++k) {
-        c += partial[pairs * k];
-        if (pairs == 2) d += partial[2 * k + 1];
-    }
-    stats[0] = (float)c;
-    stats[1] = pairs == 2 ? (float)d : third;
-    stats[2] = pairs == 2 ? third : 0.f;
-    if (pairs == 2) {
-        stats[3] = (float)(c / (double)third);
-        stats[4] = (float)(d / (double)third);
-    } else {
-        stats[3] = (float)(c / (double)third);
-        stats[4] = 1.f - stats[3];
+        stats[0] = (float)c;
+        stats[1] = (float)d;
+        stats[2] = (float)B;
+        stats[3] = (float)(c / (double)B);   // this batch's own means: read directly when there is one rank
+        stats[4] = (float)(d / (double)B);
     }
 }
 
@@ -605,16 +598,12 @@ extern "C" int eqb_group_pool_select(const float *act, int B, int num_rotations,
     // one CTA up to 8192 samples (32 per thread): the kernel is latency-bound either way, and a single CTA finishes the
     // statistic itself - no stream-ordered scratch allocation and no second launch on the path of every step (the
     // cudaMallocAsync / cudaFreeAsync pair cost 8 us on some boxes of the pool and 60 us on others)
-    const unsigned blocks = B <= 8192 ? 1u : grid_for(B, 256, 1024);
+    const unsigned blocks = B <= 8192 ? 1u : grid_for(B, 256, SEL_BLOCKS);
     cudaStream_t st = (cudaStream_t)stream;
-    double *scratch = nullptr;
-    if (blocks > 1) EQB_CUDA(cudaMallocAsync((void **)&scratch, sizeof(double) * 2 * blocks, st));
+    static unsigned int next_slot = 0;
+    const int slot = (int)(next_slot++ % SEL_SLOTS);
     group_pool_select_kernel<<<blocks, 256, 0, st>>>(act, B, num_rotations, G, idx, rotation,
-                                                     reflect ? reflection : nullptr, onehot, stats, scratch);
-    if (blocks > 1) {
-        finish_stats_kernel<<<1, 32, 0, st>>>(scratch, (int)blocks, 2, (float)B, stats);
-        EQB_CUDA(cudaFreeAsync(scratch, st));
-    }
+                                                     reflect ? reflection : nullptr, onehot, stats, slot);
     return finish_launch("eqb_group_pool_select");
 }
 

@@ -389,7 +389,7 @@ def group_pool_select(act: torch.Tensor, num_rotations: int, reflect: bool, want
     refl = torch.empty((b,), dtype=torch.float32, device=dev) if reflect else None
     onehot = torch.empty((b, g), dtype=torch.float32, device=dev) if want_onehot else None
     stats = torch.empty((5,), dtype=torch.float32, device=dev)
-    _call("eqb_group_pool_select", 1 if b <= 8192 else 2, dev, _ptr(act), b, num_rotations, int(reflect), _ptr(idx),
+    _call("eqb_group_pool_select", 1, dev, _ptr(act), b, num_rotations, int(reflect), _ptr(idx),
           _ptr(rot), _ptr(refl), _ptr(onehot), _ptr(stats), _stream(dev))
     return idx, rot, refl, onehot, stats
 
