@@ -372,8 +372,8 @@ static int conv_make_plan(int B, int cin, int H, int W, int cout, int k, int G, 
         const size_t xbytes = (((size_t)(B > 0 ? B : 1) * H * W * p.cpad0 * sizeof(__half)) + 1023) & ~(size_t)1023;
         p.off_xin[0] = off; off += xbytes;
         p.off_xin[1] = off; off += xbytes;
-        p.off_lay = off; off += (size_t)(L + 1) * LAY_FLOATS * sizeof(float);
-        p.off_absmax = off; off += 64;
+        p.off_lay = off; off += (size_t)(L + 1) * (B > 0 ? B : 1) * LAY_FLOATS * sizeof(float);   // one record per layer AND image
+        p.off_absmax = off; off += (((size_t)(B > 0 ? B : 1) * sizeof(float)) + 63) & ~(size_t)63;
         p.off_rowstat = off; off += (size_t)2 * p.Npad * sizeof(float);
     }
     p.total = off;
@@ -422,7 +422,7 @@ extern "C" int eqb_conv_stack_forward(const float *x, int B, int cin, int H, int
     const __half *tin_hi = nullptr, *tin_lo = nullptr;   // fp16 pair feeding the next tcgen05 layer
     if (p.tc) {
         // operand scales are chained on the device from max |x| (conv_stack_tc.cu)
-        int e = tc_absmax(x, 1, (size_t)B * cin * H * W, (float *)(ws + p.off_absmax), st);   // (this stack still scales per call)
+        int e = tc_absmax(x, B, (size_t)cin * H * W, (float *)(ws + p.off_absmax), st);   // max |x| of every image
         if (e) return e;
     }
     for (int l = 0; l < L; ++l) {
@@ -432,10 +432,10 @@ extern "C" int eqb_conv_stack_forward(const float *x, int B, int cin, int H, int
             float *vec = (float *)(ws + p.off_vec[l]);
             conv_vec_kernel<<<1, 256, 0, st>>>(biases ? biases[l] : nullptr, scales ? scales[l] : nullptr,
                                                shifts ? shifts[l] : nullptr, vec, p.N, p.Npad);
-            float *lay_l = lay + (size_t)l * LAY_FLOATS;
+            float *lay_l = lay + (size_t)l * B * LAY_FLOATS;          // B records of this layer
             const float *bound_in = l == 0 ? (const float *)(ws + p.off_absmax) : lay_l + LAY_INBOUND;
-            int e = ctc_layer_stats(filters[l], vec, p.N, p.Npad, p.K[l], bound_in, 1, lay_l, lay_l + LAY_FLOATS,
-                                    (float *)(ws + p.off_rowstat), st);
+            int e = ctc_layer_stats(filters[l], vec, p.N, p.Npad, p.K[l], bound_in, l == 0 ? 1 : LAY_FLOATS, B, 1, lay_l,
+                                    lay_l + (size_t)B * LAY_FLOATS, (float *)(ws + p.off_rowstat), st);
             if (e) return e;
             unsigned char *wp = (unsigned char *)(ws + p.off_wp[l]);
             const int cpad_in = l == 0 ? p.cpad0 : p.Npad;

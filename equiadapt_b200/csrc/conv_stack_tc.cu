@@ -317,7 +317,6 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const __grid_consta
     } else if (warp >= 4) {
         // ===== epilogue ==========================================================================================
         const int q = warp & 3, row = q * 32 + lane, py = row >> 3, px = row & 7;   // TMEM lane = py * 8 + px
-        const float cinv = a.lay[LAY_CINV], s_out = a.lay[LAY_SOUT];
         uint32_t accph[2] = {0, 0};
         int buf = 0;
         for (int tile0 = blockIdx.x; tile0 < a.tiles; tile0 += nq * gridDim.x) {
@@ -328,6 +327,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const __grid_consta
                 const int b = tile / per_img, r = tile - b * per_img, ty = r / a.tiles_x, tx = r - ty * a.tiles_x;
                 const int oy = ty * 16 + py, ox = tx * 8 + px;
                 const bool valid = oy < a.Ho && ox < a.Wo;
+                const float cinv = a.lay[(size_t)b * LAY_FLOATS + LAY_CINV], s_out = a.lay[(size_t)b * LAY_FLOATS + LAY_SOUT];   // this image's scales
                 mbar_wait(bar(B_ACCFULL + acc), accph[buf]);
                 tc_fence_after();
                 for (int c = 0; c < a.Npad / 32; ++c) {
@@ -399,11 +399,16 @@ __global__ void __launch_bounds__(128) ctc_row_stats_kernel(const float *__restr
         rowstat[2 * n + 1] = (red[1][0] + red[1][1]) + (red[1][2] + red[1][3]);
     }
 }
+// One block per IMAGE: the operand scales are chained per image from ITS max |x| (a sample's activations never depend on
+// its batch-mates; the weight scale sw is the same in every record).  in_bound of image b = in_bound_ptr[b * in_stride].
 __global__ void __launch_bounds__(256) ctc_layer_stats_kernel(const float *__restrict__ rowstat, const float *__restrict__ vecs,
                                                               int N, int Npad, const float *__restrict__ in_bound_ptr,
-                                                              int tensor_in, float *__restrict__ lay, float *__restrict__ nxt) {
+                                                              int in_stride, int tensor_in, float *__restrict__ lay_all,
+                                                              float *__restrict__ nxt_all) {
     __shared__ float red[2][256];
-    const float in_bound = *in_bound_ptr;
+    const int b = blockIdx.x;
+    float *lay = lay_all + (size_t)b * LAY_FLOATS, *nxt = nxt_all + (size_t)b * LAY_FLOATS;
+    const float in_bound = in_bound_ptr[(size_t)b * in_stride];
     float wmax = 0.f, ob = 0.f;
     for (int n = threadIdx.x; n < N; n += blockDim.x) {
         wmax = fmaxf(wmax, rowstat[2 * n]);
@@ -457,13 +462,13 @@ __global__ void ctc_pack_kernel(const float *__restrict__ w, const float *__rest
 __global__ void __launch_bounds__(256) ctc_input_split_kernel(const float *__restrict__ x, const float *__restrict__ absmax,
                                                               int B, int C, int H, int W, int Cpad, __half *__restrict__ hi,
                                                               __half *__restrict__ lo) {
-    const float s = pow2_scale(*absmax);
     const size_t npix = (size_t)B * H * W, plane = (size_t)H * W;
     const int pairs = Cpad / 2;
     for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < npix * pairs; t += (size_t)gridDim.x * blockDim.x) {
         const size_t pix = t / pairs;
         const int c = 2 * (int)(t - pix * pairs);
         const size_t b = pix / plane, r = pix - b * plane;
+        const float s = pow2_scale(absmax[b]);          // per image
         const float v0 = c < C ? x[(b * C + c) * plane + r] * s : 0.f;
         const float v1 = c + 1 < C ? x[(b * C + c + 1) * plane + r] * s : 0.f;
         uint32_t h, l;
@@ -521,10 +526,10 @@ int ctc_atom_channels(int Cpad) { return Cpad % 32 == 0 ? 32 : 16; }
 
 size_t ctc_pack_bytes(int Npad, int Cpad, int k) { return (size_t)k * k * Cpad * Npad * 4; }
 
-int ctc_layer_stats(const float *w, const float *vecs, int N, int Npad, int K, const float *in_bound_ptr, int tensor_in,
-                    float *lay, float *nxt, float *rowstat, cudaStream_t st) {
+int ctc_layer_stats(const float *w, const float *vecs, int N, int Npad, int K, const float *in_bound_ptr, int in_stride, int B,
+                    int tensor_in, float *lay, float *nxt, float *rowstat, cudaStream_t st) {
     ctc::ctc_row_stats_kernel<<<N, 128, 0, st>>>(w, K, rowstat);
-    ctc::ctc_layer_stats_kernel<<<1, 256, 0, st>>>(rowstat, vecs, N, Npad, in_bound_ptr, tensor_in, lay, nxt);
+    ctc::ctc_layer_stats_kernel<<<B, 256, 0, st>>>(rowstat, vecs, N, Npad, in_bound_ptr, in_stride, tensor_in, lay, nxt);
     return finish_launch("ctc_layer_stats_kernel");
 }
 

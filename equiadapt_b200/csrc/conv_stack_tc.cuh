@@ -14,8 +14,8 @@ int ctc_atom_channels(int Cpad);       // channels per K atom for an operand pad
 size_t ctc_pack_bytes(int Npad, int Cpad, int k);
 // w (N, K) fp32 filter, vecs = [bias | scale | shift] (3 x Npad); tensor_in: this layer consumes fp16 hi/lo operands;
 // rowstat: 2 * N floats of device scratch
-int ctc_layer_stats(const float *w, const float *vecs, int N, int Npad, int K, const float *in_bound_ptr, int tensor_in,
-                    float *lay, float *nxt, float *rowstat, cudaStream_t st);
+int ctc_layer_stats(const float *w, const float *vecs, int N, int Npad, int K, const float *in_bound_ptr, int in_stride, int B,
+                    int tensor_in, float *lay, float *nxt, float *rowstat, cudaStream_t st);
 // x (B, C, H, W) fp32 -> fp16 hi / lo NHWC with C padded to Cpad, scaled by pow2(*absmax)
 int ctc_input_split(const float *x, const float *absmax, int B, int C, int H, int W, int Cpad, __half *hi, __half *lo,
                     cudaStream_t st);

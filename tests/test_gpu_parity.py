@@ -1829,3 +1829,25 @@ def test_select_fused_into_the_finish_kernel_equals_the_select_kernel(cuda_devic
             want = ops.group_pool_select(can.canonicalization_info_dict["group_activations"], n_rot, reflect)
             assert torch.equal(can.canonicalization_info_dict["group_element"].index, want[0])
             assert float(can.get_prior_regularization_loss()) == float(want[4][3])
+
+
+def test_escnn_stack_activations_do_not_depend_on_batch_mates(cuda_device):
+    """a7: the e2cnn-style stack chains its fp16 operand scales per IMAGE as well (layer records per image): rows are
+    bit-identical whatever shares the batch, and a faint image keeps its relative accuracy next to a bright one."""
+    from equiadapt_b200.images.canonicalization_networks.escnn_networks import ESCNNEquivariantNetwork
+    dev = cuda_device
+    torch.manual_seed(96)
+    net = ESCNNEquivariantNetwork((3, 40, 40), 8, 5, "rotation", 4, 3, device=str(dev)).eval()
+    x = torch.rand(5, 3, 40, 40, generator=torch.Generator().manual_seed(97))
+    xa = (x * torch.tensor([1.0, 1e-5, 300.0, 2e-2, 1.0]).view(-1, 1, 1, 1)).to(dev)
+    xb = xa.clone()
+    xb[2] = xb[2] * 1e-3
+    with torch.no_grad():
+        a, b = net(xa), net(xb)
+        assert torch.equal(a[[0, 1, 3, 4]], b[[0, 1, 3, 4]])
+        scales, shifts = net.folded_affine()
+        ref = O.expanded_conv_network(xa.cpu().double(), [f.detach().cpu().double() for f in net.filters],
+                                      [bb.detach().cpu().double() for bb in net.biases],
+                                      [t.cpu().double() for t in scales], [t.cpu().double() for t in shifts], 4)
+    err = (a.cpu().double() - ref).abs().amax(dim=1) / ref.abs().amax(dim=1)
+    assert float(err.max()) < 1e-4, err
