@@ -185,6 +185,24 @@ __device__ __forceinline__ void tc_ld32_issue(uint32_t taddr, uint32_t (&r)[32])
         : "r"(taddr)
         : "memory");
 }
+// 16-column pieces (two of them in flight cost the registers of one 32-column load)
+__device__ __forceinline__ void tc_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+// wait::ld completes EVERY outstanding tcgen05.ld of the thread; the in/out operands tie the consumers of `r` behind it
+__device__ __forceinline__ void tc_ld_wait16(uint32_t (&r)[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                   "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+                 :
+                 : "memory");
+}
 __device__ __forceinline__ void tc_ld_wait(uint32_t (&r)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;"
                  : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
@@ -214,11 +232,38 @@ __device__ __forceinline__ uint64_t umma_desc32(uint32_t saddr) {
            ((uint64_t)6 << 61);
 }
 
-// x -> (hi, lo) fp16 pair images of two neighbouring elements, packed for a 32-bit store
+// ---- packed fp32 pairs (sm_100: FFMA2 / FADD2, one issue slot for two lanes; same IEEE results as the scalar ops) ----
+__device__ __forceinline__ uint64_t f2_pack(float a, float b) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void f2_unpack(uint64_t v, float &a, float &b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ uint64_t f2_sub(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+
+// x -> (hi, lo) fp16 pair images of two neighbouring elements, packed for a 32-bit store.  (The mixed-precision FMA of
+// sm_100, FHFMA = f16 * f16 + f32, gives the residual in one instruction per element but measured SLOWER in the stack
+// kernel: 1 310 vs 1 288 us.)
 __device__ __forceinline__ void split2(float x0, float x1, uint32_t &hi, uint32_t &lo) {
     const __half2 h = __floats2half2_rn(x0, x1);
     const float2 hf = __half22float2(h);
-    const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+    float r0, r1;
+    f2_unpack(f2_sub(f2_pack(x0, x1), f2_pack(hf.x, hf.y)), r0, r1);
+    const __half2 l = __floats2half2_rn(r0, r1);
     hi = *reinterpret_cast<const uint32_t *>(&h);
     lo = *reinterpret_cast<const uint32_t *>(&l);
 }
@@ -1314,6 +1359,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(768, 1) gconv_stack_
     const int NS0 = a.K0pad / SLAB_K;
     constexpr int NC1 = 8;                       // N = 256: 32-wide K atoms of the 1x1 GEMM
     const int groups = a.epi1_groups;
+    const bool split = a.epi1_split != 0 && groups == 2;   // the two epilogue-1 groups share every atom (16 channels each)
     const int lift_at = a.lift_at;               // pass 0 of the next tile's lift is queued behind this K atom of the 1x1 GEMM
     // Issuer-side waits on barriers the peer CTA arrives on.  cta_waits: plain (CTA-scope acquire) try_wait as CUTLASS's
     // ClusterBarrier::wait does -- what these barriers publish is read by the tensor core through the async proxy, made visible
@@ -1335,7 +1381,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(768, 1) gconv_stack_
             mbar_init(bar(B_A0EMPTY + i), 1);
         }
         for (int i = 0; i < A1_RING; ++i) {
-            mbar_init(bar(B_A1FULL + i), 256);   // 128 epilogue-1 threads (one group) of each CTA
+            mbar_init(bar(B_A1FULL + i), split ? 512 : 256);   // 128 epilogue-1 threads of each CTA (both groups when they share every atom)
             mbar_init(bar(B_A1EMPTY + i), 1);
         }
         mbar_init(bar(B_D1FULL), 1);
@@ -1553,6 +1599,64 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(768, 1) gconv_stack_
                     named_bar_sync(1, 128 * groups);
                     b1 = tab;
                 }
+                if (split) {
+                    // Both groups convert EVERY atom, 16 of its 32 channels each: an atom reaches the 1x1 issuer after half
+                    // the conversion time (the first atom of a tile is on the drain -> first-MMA critical path), and the
+                    // 16-column load of the next atom is in flight while this one is converted.
+                    const uint32_t tq = tmem_d1 + ((uint32_t)(q * 32) << 16) + 16u * (uint32_t)grp;
+                    const uint64_t c1c1 = f2_pack(c1, c1);
+                    auto convert_store = [&](const uint32_t (&v)[16], int c) {
+                        const float4 *bb = reinterpret_cast<const float4 *>(b1 + chunk_atom(c) * 32 + 16 * grp);
+                        uint32_t hi[8], lo[8];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float4 b4 = bb[i];
+                            float x0, x1, x2, x3;
+                            f2_unpack(f2_fma(f2_pack(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1])), c1c1, f2_pack(b4.x, b4.y)), x0, x1);
+                            f2_unpack(f2_fma(f2_pack(__uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3])), c1c1, f2_pack(b4.z, b4.w)), x2, x3);
+                            split2(fmaxf(x0, 0.f), fmaxf(x1, 0.f), hi[2 * i], lo[2 * i]);
+                            split2(fmaxf(x2, 0.f), fmaxf(x3, 0.f), hi[2 * i + 1], lo[2 * i + 1]);
+                        }
+                        const uint32_t seq = seq0 + (uint32_t)c, stage = seq % A1_RING, phase = (seq / A1_RING) & 1u;
+                        mbar_wait(bar(B_A1EMPTY + stage), phase ^ 1u, B_A1EMPTY + stage);
+                        if (q == 0 && !(c & 1)) TR(22 + 9 * grp + (c >> 1));
+                        const uint32_t hi_row = base + M.a1_ring + stage * A1_STAGE + row_off, lo_row = hi_row + A1_HALF;
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) {
+                            const uint32_t col = ((uint32_t)(2 * grp + j) ^ sw) << 4;
+                            st_shared_v4(hi_row + col, hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+                            st_shared_v4(lo_row + col, lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+                        }
+                        tc_fence_before();      // this thread's tcgen05.ld's of D1 before the arrive the next lift is ordered behind
+                        fence_async_smem();
+                        mbar_arrive_cluster(a1full0 + 8u * stage);
+                    };
+                    uint32_t va[16], vb[16];
+                    mbar_wait(bar(B_D1FULL), tile_phase, B_D1FULL);
+                    if (q == 0) TR(17 + 9 * grp);
+                    tc_fence_after();
+                    tc_ld16_issue(tq, va);
+#pragma unroll
+                    for (int c = 0; c < NC1; c += 2) {
+                        tc_ld_wait16(va);
+                        if (q == 0) TR(18 + 9 * grp + (c >> 1));
+                        tc_ld16_issue(tq + (uint32_t)((c + 1) * 32), vb);
+                        convert_store(va, c);
+                        tc_ld_wait16(vb);
+                        if (c + 2 < NC1) {
+                            if (c + 2 == 4) {
+                                mbar_wait(bar(B_D1FULL + 1), tile_phase, B_D1FULL + 1);
+                                tc_fence_after();
+                            }
+                            tc_ld16_issue(tq + (uint32_t)((c + 2) * 32), va);
+                        }
+                        convert_store(vb, c + 1);
+                    }
+                    seq0 += (uint32_t)NC1;
+                    tile_phase ^= 1u;
+                    ++tn;
+                    continue;
+                }
                 int seen = 0;                                   // lift passes whose "full" barrier this thread has passed
                 for (int c = grp; c < NC1; c += groups) {
                     const int need = (c >> 2) + 1;
@@ -1565,13 +1669,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(768, 1) gconv_stack_
                     float v[32];
                     tc_ld32(tmem_d1 + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
                     if (q == 0) TR(18 + 9 * grp + (c >> 1));
-                    const float *bb = b1 + chunk_atom(c) * 32;
+                    const float4 *bb = reinterpret_cast<const float4 *>(b1 + chunk_atom(c) * 32);
+                    const uint64_t c1c1 = f2_pack(c1, c1);
                     uint32_t hi[16], lo[16];
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const float x0 = fmaxf(fmaf(v[2 * i], c1, bb[2 * i]), 0.f);
-                        const float x1 = fmaxf(fmaf(v[2 * i + 1], c1, bb[2 * i + 1]), 0.f);
-                        split2(x0, x1, hi[i], lo[i]);
+                    for (int i = 0; i < 8; ++i) {
+                        const float4 b4 = bb[i];   // (same address in every lane: one broadcast wavefront)
+                        float x0, x1, x2, x3;
+                        f2_unpack(f2_fma(f2_pack(v[4 * i], v[4 * i + 1]), c1c1, f2_pack(b4.x, b4.y)), x0, x1);
+                        f2_unpack(f2_fma(f2_pack(v[4 * i + 2], v[4 * i + 3]), c1c1, f2_pack(b4.z, b4.w)), x2, x3);
+                        split2(fmaxf(x0, 0.f), fmaxf(x1, 0.f), hi[2 * i], lo[2 * i]);
+                        split2(fmaxf(x2, 0.f), fmaxf(x3, 0.f), hi[2 * i + 1], lo[2 * i + 1]);
                     }
                     const uint32_t seq = seq0 + (uint32_t)c, stage = seq % A1_RING, phase = (seq / A1_RING) & 1u;
                     mbar_wait(bar(B_A1EMPTY + stage), phase ^ 1u, B_A1EMPTY + stage);
@@ -1620,21 +1728,29 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(768, 1) gconv_stack_
                 mbar_wait(bar(B_D2FULL), tile_phase, B_D2FULL);
                 if (q == 0) TR(35 + 3 * grp);
                 tc_fence_after();
-                float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+                // four running sums held as two packed pairs (FADD2): (s0, s1) and (s2, s3)
+                uint64_t s01 = 0ull, s23 = 0ull;
+                auto total = [&]() {
+                    float s0, s1, s2, s3;
+                    f2_unpack(s01, s0, s1);
+                    f2_unpack(s23, s2, s3);
+                    return (double)((s0 + s1) + (s2 + s3));
+                };
                 const uint32_t t0 = tmem_d2 + ((uint32_t)(q * 32) << 16) + (uint32_t)(128 * grp);
                 auto add_chunk = [&](const uint32_t (&r)[32], int c) {
                     if (c * 32 + 32 <= nvalid) {
 #pragma unroll
                         for (int i = 0; i < 32; i += 4) {
-                            s0 += fmaxf(__uint_as_float(r[i]), tcut);
-                            s1 += fmaxf(__uint_as_float(r[i + 1]), tcut);
-                            s2 += fmaxf(__uint_as_float(r[i + 2]), tcut);
-                            s3 += fmaxf(__uint_as_float(r[i + 3]), tcut);
+                            s01 = f2_add(s01, f2_pack(fmaxf(__uint_as_float(r[i]), tcut), fmaxf(__uint_as_float(r[i + 1]), tcut)));
+                            s23 = f2_add(s23, f2_pack(fmaxf(__uint_as_float(r[i + 2]), tcut), fmaxf(__uint_as_float(r[i + 3]), tcut)));
                         }
                     } else {
+                        float s0, s1;
+                        f2_unpack(s01, s0, s1);
 #pragma unroll
                         for (int i = 0; i < 32; ++i)
                             if (c * 32 + i < nvalid) s0 += fmaxf(__uint_as_float(r[i]), tcut);
+                        s01 = f2_pack(s0, s1);
                     }
                 };
                 // D2t is free for the next 1x1 GEMM the moment this thread's LAST chunk sits in registers: the drain is on
@@ -1644,7 +1760,30 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(768, 1) gconv_stack_
                     mbar_arrive_cluster(d2empty);
                     if (q == 0) TR(36 + 3 * grp);
                 };
-                {
+                if (a.epi2_pipelined && nvalid >= 128) {
+                    // (knob) full half-tile: eight 16-column pieces, the next one in flight while the current one is summed
+                    uint32_t ra[16], rb[16];
+                    auto add16 = [&](const uint32_t (&r)[16]) {
+#pragma unroll
+                        for (int i = 0; i < 16; i += 4) {
+                            s01 = f2_add(s01, f2_pack(fmaxf(__uint_as_float(r[i]), tcut), fmaxf(__uint_as_float(r[i + 1]), tcut)));
+                            s23 = f2_add(s23, f2_pack(fmaxf(__uint_as_float(r[i + 2]), tcut), fmaxf(__uint_as_float(r[i + 3]), tcut)));
+                        }
+                    };
+                    tc_ld16_issue(t0, ra);
+                    tc_ld_wait16(ra);
+#pragma unroll
+                    for (int c = 0; c < 8; c += 2) {
+                        tc_ld16_issue(t0 + (uint32_t)(16 * (c + 1)), rb);
+                        add16(ra);
+                        tc_ld_wait16(rb);
+                        if (c + 2 < 8) tc_ld16_issue(t0 + (uint32_t)(16 * (c + 2)), ra);
+                        else release();
+                        add16(rb);
+                        if (c + 2 < 8) tc_ld_wait16(ra);
+                    }
+                    dacc += total();
+                } else {
                     // one chunk at a time (two in flight cost 32 more registers, spills, and measured 5 % slower); the release
                     // goes out as soon as the LAST chunk is loaded, before it is summed
                     const int nch = nvalid <= 0 ? 0 : (nvalid >= 128 ? 4 : (nvalid + 31) >> 5);   // (uniform)
@@ -1659,7 +1798,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(768, 1) gconv_stack_
                             add_chunk(r, c);
                         }
                     }
-                    dacc += (double)((s0 + s1) + (s2 + s3));
+                    dacc += total();
                 }
                 if (q == 0) TR(37 + 3 * grp);
                 tile_phase ^= 1u;
@@ -1927,12 +2066,15 @@ int tc_launch(TcArgs a, cudaStream_t st) {
         // CTA-pair kernel: one cluster of two CTAs per TPC, stationary weights
         a.epi1_groups = eg && eg[0] == '1' ? 1 : 2;
         a.lift_early = le && le[0] == '1' ? 1 : 0;
-        // A/B knobs, default OFF: both were measured SLOWER on B200 (1 416 -> 1 447 / 1 473 us, profiles/r2_stack.md): queuing
-        // the lift behind the 1x1 GEMM hides the D2t drain but exposes the ~1 500 cycles epilogue 1 needs to deliver the
-        // first A1 atom after D1FULL, and the drain is not bound by the latency of tcgen05.ld
+        // A/B knobs of the first-generation pair kernel, default OFF: both were measured SLOWER on B200 (1 416 -> 1 447 /
+        // 1 473 us, profiles/r2_stack.md): queuing the lift behind the 1x1 GEMM hides the D2t drain but exposes the ~1 500
+        // cycles epilogue 1 needs to deliver the first A1 atom after D1FULL, and two 32-column loads in flight spill.
+        // pair2 drains D2t in 16-column pieces with the next piece in flight (same registers as one 32-column load):
+        // default ON there (1 324 -> 1 288 us)
         const char *lo = getenv("EQB_TC_LIFT_ORDER"), *ep = getenv("EQB_TC_EPI2_PIPE");
+        const bool use_pair2 = !(getenv("EQB_TC_PAIR2") && getenv("EQB_TC_PAIR2")[0] == '0');
         a.lift_after_gemm = lo && lo[0] == '1' ? 1 : 0;
-        a.epi2_pipelined = ep && ep[0] == '1' ? 1 : 0;
+        a.epi2_pipelined = use_pair2 ? (ep && ep[0] == '0' ? 0 : 1) : (ep && ep[0] == '1' ? 1 : 0);
         const tc::pair::Smem M = tc::pair::smem_map(a.K0pad);
         EQB_UNSUPPORTED(M.total > 227 * 1024, "gconv_stack (tcgen05 pair): shared-memory plan of %u bytes does not fit", M.total);
         static PerDeviceOnce configured2;
@@ -1946,11 +2088,12 @@ int tc_launch(TcArgs a, cudaStream_t st) {
         const int clusters = items2 < max_clusters ? items2 : max_clusters;
         a.trace = g_trace;
         a.trace_tiles = g_trace_tiles;
-        const char *p2 = getenv("EQB_TC_PAIR2"), *la = getenv("EQB_TC_LIFT_AT");
+        const char *la = getenv("EQB_TC_LIFT_AT");
         a.lift_at = la && la[0] >= '3' && la[0] <= '7' ? la[0] - '0' : 5;
-        const char *cw = getenv("EQB_TC_CTA_WAITS");
+        const char *cw = getenv("EQB_TC_CTA_WAITS"), *es = getenv("EQB_TC_EPI1_SPLIT");
+        a.epi1_split = es && es[0] == '0' ? 0 : 1;   // default on: 1 294 -> 1 284 us
         a.cta_waits = cw && cw[0] == '1' ? 1 : 0;
-        if (!(p2 && p2[0] == '0')) {
+        if (use_pair2) {
             // second-generation pipeline (lift behind the 1x1 GEMM in two channel passes, resident patch slabs, streamed W0)
             const tc::pair2::Smem M2 = tc::pair2::smem_map(a.K0pad);
             EQB_UNSUPPORTED(M2.total > 227 * 1024, "gconv_stack (tcgen05 pair2): shared-memory plan of %u bytes does not fit", M2.total);
