@@ -1475,6 +1475,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(768, 1) gconv_stack_
                 TR(0);
                 mbar_wait_fast(bar(B_D2EMPTY), tile_phase ^ 1u, B_D2EMPTY);
                 TR(1);
+                // The last pair-tile of an image is mostly padding (P = 8 464: 16 of 256 pixels): when its pixels all sit in
+                // the leader's half, shrink the MMA's N to them (N / 2 rows of B from each CTA: columns [0, N/2) of D2t come
+                // from the leader's rows, the rest from the peer's padding rows, which epilogue 2 never sums).  The valid
+                // columns get the same bits; measured -0.4 % per call (epilogue 1 still converts the whole tile).
+                const int rem = a.P - tw.t * 256;
+                const uint32_t idesc_t =
+                    (a.tail_n && rem <= 128) ? ((1u << 4) | ((uint32_t)((2 * ((rem + 7) & ~7)) >> 3) << 17) | ((uint32_t)(256 >> 4) << 24)) : idesc;
                 for (int kc = 0; kc < NC1; ++kc) {
                     if (kc) mbar_wait_fast(bar(B_A1FULL + r1.stage), r1.phase, B_A1FULL + r1.stage);
                     TR(2 + kc);
@@ -1484,11 +1491,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(768, 1) gconv_stack_
                         const uint32_t w_hi = w1_lo0 + (uint32_t)chunk_atom(kc) * (W1_ATOM >> 4), w_lo = w_hi + (8192u >> 4);
 #pragma unroll
                         for (int j = 0; j < 2; ++j)
-                            tc_mma2_f16_lo<DESC_HI_64B>(tmem_d2, w_hi + 2 * j, a_hi + 2 * j, idesc, j ? 1u : (uint32_t)(kc != 0));
+                            tc_mma2_f16_lo<DESC_HI_64B>(tmem_d2, w_hi + 2 * j, a_hi + 2 * j, idesc_t, j ? 1u : (uint32_t)(kc != 0));
 #pragma unroll
-                        for (int j = 0; j < 2; ++j) tc_mma2_f16_lo<DESC_HI_64B>(tmem_d2, w_hi + 2 * j, a_lo + 2 * j, idesc, 1);
+                        for (int j = 0; j < 2; ++j) tc_mma2_f16_lo<DESC_HI_64B>(tmem_d2, w_hi + 2 * j, a_lo + 2 * j, idesc_t, 1);
 #pragma unroll
-                        for (int j = 0; j < 2; ++j) tc_mma2_f16_lo<DESC_HI_64B>(tmem_d2, w_lo + 2 * j, a_hi + 2 * j, idesc, 1);
+                        for (int j = 0; j < 2; ++j) tc_mma2_f16_lo<DESC_HI_64B>(tmem_d2, w_lo + 2 * j, a_hi + 2 * j, idesc_t, 1);
                         tc_commit2(bar(B_A1EMPTY + r1.stage));
                         if (kc == lift_at) mbar_arrive(bar(B_G2A));   // the lift issuer may queue pass 0 of the next tile
                         if (kc == NC1 - 1) {
@@ -1605,6 +1612,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(768, 1) gconv_stack_
                     // 16-column load of the next atom is in flight while this one is converted.
                     const uint32_t tq = tmem_d1 + ((uint32_t)(q * 32) << 16) + 16u * (uint32_t)grp;
                     const uint64_t c1c1 = f2_pack(c1, c1);
+                    // Tail tile shrunk by the issuer: only the leader's first N / 2 rows are read -- the other warps keep the
+                    // barrier protocol (an arrive must still follow the stage's release) and skip loads, conversion, stores
+                    const int rem = a.P - tw.t * 256;
+                    if (a.tail_n && rem <= 128 && !(rank == 0 && q * 32 < ((rem + 7) & ~7))) {
+                        mbar_wait(bar(B_D1FULL), tile_phase, B_D1FULL);
+                        mbar_wait(bar(B_D1FULL + 1), tile_phase, B_D1FULL + 1);
+                        for (int c = 0; c < NC1; ++c) {
+                            const uint32_t seq = seq0 + (uint32_t)c, stage = seq % A1_RING, phase = (seq / A1_RING) & 1u;
+                            mbar_wait(bar(B_A1EMPTY + stage), phase ^ 1u, B_A1EMPTY + stage);
+                            mbar_arrive_cluster(a1full0 + 8u * stage);
+                        }
+                        seq0 += (uint32_t)NC1;
+                        tile_phase ^= 1u;
+                        ++tn;
+                        continue;
+                    }
                     auto convert_store = [&](const uint32_t (&v)[16], int c) {
                         const float4 *bb = reinterpret_cast<const float4 *>(b1 + chunk_atom(c) * 32 + 16 * grp);
                         uint32_t hi[8], lo[8];
@@ -2091,6 +2114,8 @@ int tc_launch(TcArgs a, cudaStream_t st) {
         const char *la = getenv("EQB_TC_LIFT_AT");
         a.lift_at = la && la[0] >= '3' && la[0] <= '7' ? la[0] - '0' : 5;
         const char *cw = getenv("EQB_TC_CTA_WAITS"), *es = getenv("EQB_TC_EPI1_SPLIT");
+        const char *tn_ = getenv("EQB_TC_TAIL_N");
+        a.tail_n = tn_ && tn_[0] == '0' ? 0 : 1;
         a.epi1_split = es && es[0] == '0' ? 0 : 1;   // default on: 1 294 -> 1 284 us
         a.cta_waits = cw && cw[0] == '1' ? 1 : 0;
         if (use_pair2) {

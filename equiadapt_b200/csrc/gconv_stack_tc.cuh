@@ -20,6 +20,7 @@ struct TcArgs {
     int trace_tiles;
     int cta_waits;               // pair2 kernel: issuer polls with CTA-scope acquire (knob)
     int lift_at;                 // pair2 kernel: K atom of the 1x1 GEMM behind which pass 0 of the next tile's lift is queued
+    int tail_n;                          // pair2: 1x1 MMAs of an image's last tile shrunk to its valid pixels
     int epi1_split;                      // pair2: both epilogue-1 groups convert every atom (16 channels each)
     int lift_after_gemm, epi2_pipelined; // CTA-pair kernel: lift of tile t+1 queued behind the last 1x1 MMA of tile t; LDTM of chunk c+1 in flight while chunk c is summed
 };
