@@ -39,7 +39,7 @@ for rep in reps:
         for frag, call in CALL.items():
             if frag in name:
                 key = call
-        if "resample_tma_kernel" in name:
+        if "resample_tma_kernel" in name or "resample_tma_persistent_kernel" in name:
             key = "eqb_warp_canonicalize" if warp_seen == 0 else "eqb_warp_invert"
             warp_seen += 1
         if key and key not in traffic:
