@@ -22,6 +22,7 @@ constexpr int VN_C1 = 21;   // 64 // 3 hidden vector channels (fixed by the refe
 constexpr int VN_C2 = 4;    // 12 // 3 output vector channels, the first 3 are used (:150)
 constexpr float VN_EPS = 1e-6f;
 constexpr int VN_MAX_THREADS = 512;
+constexpr int VN_CAP = 8;     // pending neighbour candidates per lane between two insertion rounds
 
 // flat parameter block (floats), raw tensors of the reference module in this order:
 //   conv_pos: map_to_feat (21x3), map_to_dir (21x3), batchnorm.bn2d {weight, bias, running_mean, running_var} (4x21)
@@ -58,6 +59,8 @@ __global__ void __launch_bounds__(VN_THREADS, 1) vnsmall_kernel(const float *__r
     float *xx = xs + 3 * N;        // [N]  |x_i|^2
     float *P = xx + N;             // staged parameters, batch norms folded to (scale, shift) pairs
     int *nbr = reinterpret_cast<int *>(P + VP_TOTAL);   // [K][VN_THREADS] neighbour lists (dynamic indexing lives here)
+    float *bufv = reinterpret_cast<float *>(nbr + K * VN_THREADS);   // [VN_CAP][VN_THREADS] pending candidates: value,
+    int *bufi = reinterpret_cast<int *>(bufv + VN_CAP * VN_THREADS); //                       index
     __shared__ double red[VN_THREADS / 32][9];
     // grid (clouds, splits): CTA (b, sp) owns points [sp * per, (sp + 1) * per) of cloud b - small batches (the 16 clouds
     // per GPU of BASELINE configs[3]) still fill the SMs; every CTA stages the whole cloud (all points are candidates)
@@ -88,29 +91,56 @@ __global__ void __launch_bounds__(VN_THREADS, 1) vnsmall_kernel(const float *__r
 #pragma unroll
     for (int q = 0; q < 9; ++q) total[q] = 0.f;
 
-    for (int i = i_lo + tid; i < i_hi; i += VN_THREADS) {
+    // (warp-uniform trip count: lanes past the end of the split redo its last point and are left out of the sum)
+    for (int i0 = i_lo; i0 < i_hi; i0 += VN_THREADS) {
+        const bool live = i0 + tid < i_hi;
+        const int i = live ? i0 + tid : i_hi - 1;
         const float xi0 = xs[i], xi1 = xs[N + i], xi2 = xs[2 * N + i], xxi = xx[i];
         // ---- k nearest neighbours: the k largest of (-xx_j - inner_ij) - xx_i, inner = -2 x_i.x_j (:28-32) ------------
+        // A sorted insertion costs ~6 K instructions and a warp pays for it whenever ANY lane inserts -- with one point per
+        // lane that is nearly every candidate (r3o profile: 60 % of the kernel's instructions).  So candidates that beat the
+        // lane's k-th best are only APPENDED to a small per-lane buffer in shared memory; the warp runs the insertions when
+        // some lane's buffer is full (and once at the end).  Same neighbours in the same order (ties: lower index first).
         float val[K];
         int id[K];
 #pragma unroll
         for (int s = 0; s < K; ++s) { val[s] = -INFINITY; id[s] = i; }
+        float thr = -INFINITY;
+        int cnt = 0;
+        auto flush = [&]() {
+#pragma unroll 1
+            for (int e = 0; e < VN_CAP; ++e) {
+                if (e < cnt) {
+                    float cv = bufv[e * VN_THREADS + tid];
+                    int ci = bufi[e * VN_THREADS + tid];
+                    if (cv > thr) {
+#pragma unroll
+                        for (int s = 0; s < K; ++s) {
+                            if (cv > val[s]) {
+                                const float tv = val[s]; val[s] = cv; cv = tv;
+                                const int ti = id[s]; id[s] = ci; ci = ti;
+                            }
+                        }
+                        // the admission threshold is the k-th best (k <= K: static indexing keeps the list in registers)
+#pragma unroll
+                        for (int s = 0; s < K; ++s)
+                            if (s == k - 1) thr = val[s];
+                    }
+                }
+            }
+            cnt = 0;
+        };
         for (int j = 0; j < N; ++j) {
             const float m = fmaf(xi2, xs[2 * N + j], fmaf(xi1, xs[N + j], xi0 * xs[j]));
             const float pd = (-xx[j] - (-2.f * m)) - xxi;
-            if (pd > val[K - 1]) {
-                float cv = pd;
-                int ci = j;
-#pragma unroll
-                for (int s = 0; s < K; ++s) {
-                    if (s < k && cv > val[s]) {
-                        const float tv = val[s]; val[s] = cv; cv = tv;
-                        const int ti = id[s]; id[s] = ci; ci = ti;
-                    }
-                }
-                if (k < K) val[K - 1] = val[k - 1];   // the admission threshold is the k-th best
+            if (pd > thr) {
+                bufv[cnt * VN_THREADS + tid] = pd;
+                bufi[cnt * VN_THREADS + tid] = j;
+                ++cnt;
             }
+            if (__any_sync(0xffffffffu, cnt == VN_CAP)) flush();
         }
+        flush();
         // ---- edges -> VNLinearLeakyReLU(3 -> 21) -> mean over the neighbours ----------------------------------------
         float h[VN_C1][3];
 #pragma unroll
@@ -173,7 +203,7 @@ __global__ void __launch_bounds__(VN_THREADS, 1) vnsmall_kernel(const float *__r
             vn_bn(p2[c2], P[VP_BN2 + c2], P[VP_BN2 + VN_C2 + c2]);
             vn_relu(p2[c2], d2[c2]);
 #pragma unroll
-            for (int dd = 0; dd < 3; ++dd) total[3 * c2 + dd] += p2[c2][dd];
+            for (int dd = 0; dd < 3; ++dd) total[3 * c2 + dd] += live ? p2[c2][dd] : 0.f;
         }
     }
     // ---- mean over the points (:150) -----------------------------------------------------------------------------
@@ -479,7 +509,7 @@ extern "C" int eqb_vnsmall_forward(const float *x, int B, int N, const float *pa
     // there is at most one cloud per SM; EQB_VN_THREADS=256 selects the other build
     const char *tv = getenv("EQB_VN_THREADS");
     const int threads = tv && atoi(tv) == 256 ? 256 : 512;
-    const size_t smem = ((size_t)4 * N + VP_TOTAL + (size_t)(n_knn == 20 ? 20 : 32) * threads) * sizeof(float);
+    const size_t smem = ((size_t)4 * N + VP_TOTAL + (size_t)((n_knn == 20 ? 20 : 32) + 2 * VN_CAP) * threads) * sizeof(float);
     EQB_UNSUPPORTED(smem > 200 * 1024, "eqb_vnsmall_forward: clouds of %d points do not fit in shared memory", N);
     cudaStream_t st = (cudaStream_t)stream;
 #define EQB_VN_LAUNCH(KK, TT)                                                                                          \
