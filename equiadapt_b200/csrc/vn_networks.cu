@@ -22,7 +22,7 @@ constexpr int VN_C1 = 21;   // 64 // 3 hidden vector channels (fixed by the refe
 constexpr int VN_C2 = 4;    // 12 // 3 output vector channels, the first 3 are used (:150)
 constexpr float VN_EPS = 1e-6f;
 constexpr int VN_MAX_THREADS = 512;
-constexpr int VN_CAP = 8;     // pending neighbour candidates per lane between two insertion rounds
+constexpr int VN_CAP = 16;    // pending neighbour candidates per lane between two insertion rounds
 
 // flat parameter block (floats), raw tensors of the reference module in this order:
 //   conv_pos: map_to_feat (21x3), map_to_dir (21x3), batchnorm.bn2d {weight, bias, running_mean, running_var} (4x21)
@@ -61,6 +61,7 @@ __global__ void __launch_bounds__(VN_THREADS, 1) vnsmall_kernel(const float *__r
     int *nbr = reinterpret_cast<int *>(P + VP_TOTAL);   // [K][VN_THREADS] neighbour lists (dynamic indexing lives here)
     float *bufv = reinterpret_cast<float *>(nbr + K * VN_THREADS);   // [VN_CAP][VN_THREADS] pending candidates: value,
     int *bufi = reinterpret_cast<int *>(bufv + VN_CAP * VN_THREADS); //                       index
+    float4 *x4 = reinterpret_cast<float4 *>(bufi + VN_CAP * VN_THREADS);   // [N] (x, y, z, |x|^2): one 16-byte broadcast per candidate
     __shared__ double red[VN_THREADS / 32][9];
     // grid (clouds, splits): CTA (b, sp) owns points [sp * per, (sp + 1) * per) of cloud b - small batches (the 16 clouds
     // per GPU of BASELINE configs[3]) still fill the SMs; every CTA stages the whole cloud (all points are candidates)
@@ -84,6 +85,7 @@ __global__ void __launch_bounds__(VN_THREADS, 1) vnsmall_kernel(const float *__r
     for (int i = tid; i < N; i += VN_THREADS) {
         const float a0 = xs[i], a1 = xs[N + i], a2 = xs[2 * N + i];
         xx[i] = a0 * a0 + a1 * a1 + a2 * a2;   // torch.sum(x**2, dim=1): ((a0^2 + a1^2) + a2^2)
+        x4[i] = make_float4(a0, a1, a2, xx[i]);
     }
     __syncthreads();
 
@@ -107,20 +109,26 @@ __global__ void __launch_bounds__(VN_THREADS, 1) vnsmall_kernel(const float *__r
         for (int s = 0; s < K; ++s) { val[s] = -INFINITY; id[s] = i; }
         float thr = -INFINITY;
         int cnt = 0;
+        float *bv = bufv + tid;               // this lane's next free slot (slots are VN_THREADS apart)
+        int *bi = bufi + tid;
         auto flush = [&]() {
 #pragma unroll 1
             for (int e = 0; e < VN_CAP; ++e) {
                 if (e < cnt) {
-                    float cv = bufv[e * VN_THREADS + tid];
-                    int ci = bufi[e * VN_THREADS + tid];
+                    const float cv = bufv[e * VN_THREADS + tid];
+                    const int ci = bufi[e * VN_THREADS + tid];
                     if (cv > thr) {
+                        // shift-insert into the descending list, bottom up: slot s takes its upper neighbour when the
+                        // candidate beats that one, the candidate when it beats only slot s, else it keeps its value
+                        bool above[K];
 #pragma unroll
-                        for (int s = 0; s < K; ++s) {
-                            if (cv > val[s]) {
-                                const float tv = val[s]; val[s] = cv; cv = tv;
-                                const int ti = id[s]; id[s] = ci; ci = ti;
-                            }
+                        for (int s = 0; s < K; ++s) above[s] = cv > val[s];
+#pragma unroll
+                        for (int s = K - 1; s >= 1; --s) {
+                            val[s] = above[s - 1] ? val[s - 1] : (above[s] ? cv : val[s]);
+                            id[s] = above[s - 1] ? id[s - 1] : (above[s] ? ci : id[s]);
                         }
+                        if (above[0]) { val[0] = cv; id[0] = ci; }
                         // the admission threshold is the k-th best (k <= K: static indexing keeps the list in registers)
 #pragma unroll
                         for (int s = 0; s < K; ++s)
@@ -129,18 +137,40 @@ __global__ void __launch_bounds__(VN_THREADS, 1) vnsmall_kernel(const float *__r
                 }
             }
             cnt = 0;
+            bv = bufv + tid;
+            bi = bufi + tid;
         };
-        for (int j = 0; j < N; ++j) {
-            const float m = fmaf(xi2, xs[2 * N + j], fmaf(xi1, xs[N + j], xi0 * xs[j]));
-            const float pd = (-xx[j] - (-2.f * m)) - xxi;
+        auto candidate = [&](const float4 c, int j) {
+            const float m = fmaf(xi2, c.z, fmaf(xi1, c.y, xi0 * c.x));
+            const float pd = (-c.w - (-2.f * m)) - xxi;
             if (pd > thr) {
-                bufv[cnt * VN_THREADS + tid] = pd;
-                bufi[cnt * VN_THREADS + tid] = j;
+                *bv = pd;
+                *bi = j;
+                bv += VN_THREADS;
+                bi += VN_THREADS;
                 ++cnt;
             }
-            if (__any_sync(0xffffffffu, cnt == VN_CAP)) flush();
+        };
+        // four candidates per round; a round starts with room for four in every lane's buffer.  ONE call site for the
+        // insertion rounds: the unrolled K-slot insertion is ~1 000 instructions and the kernel is already bound by
+        // instruction fetch when it is inlined three times (r3q profile)
+#pragma unroll 1
+        for (int j = 0;; j += 4) {
+            const bool done = j >= N;
+            if (done || __any_sync(0xffffffffu, cnt > VN_CAP - 4)) {
+                flush();
+                if (done) break;
+            }
+            if (j + 4 <= N) {
+                const float4 c0 = x4[j], c1 = x4[j + 1], c2 = x4[j + 2], c3 = x4[j + 3];   // (same address in every lane: broadcast)
+                candidate(c0, j);
+                candidate(c1, j + 1);
+                candidate(c2, j + 2);
+                candidate(c3, j + 3);
+            } else {
+                for (int q = j; q < N; ++q) candidate(x4[q], q);
+            }
         }
-        flush();
         // ---- edges -> VNLinearLeakyReLU(3 -> 21) -> mean over the neighbours ----------------------------------------
         float h[VN_C1][3];
 #pragma unroll
@@ -509,7 +539,7 @@ extern "C" int eqb_vnsmall_forward(const float *x, int B, int N, const float *pa
     // there is at most one cloud per SM; EQB_VN_THREADS=256 selects the other build
     const char *tv = getenv("EQB_VN_THREADS");
     const int threads = tv && atoi(tv) == 256 ? 256 : 512;
-    const size_t smem = ((size_t)4 * N + VP_TOTAL + (size_t)((n_knn == 20 ? 20 : 32) + 2 * VN_CAP) * threads) * sizeof(float);
+    const size_t smem = ((size_t)8 * N + VP_TOTAL + (size_t)((n_knn == 20 ? 20 : 32) + 2 * VN_CAP) * threads) * sizeof(float);
     EQB_UNSUPPORTED(smem > 200 * 1024, "eqb_vnsmall_forward: clouds of %d points do not fit in shared memory", N);
     cudaStream_t st = (cudaStream_t)stream;
 #define EQB_VN_LAUNCH(KK, TT)                                                                                          \
