@@ -40,6 +40,7 @@
 
 #include "common.cuh"
 #include "gconv_stack_tc.cuh"
+#include "resample.cuh"
 
 namespace eqb {
 
@@ -1910,6 +1911,291 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(768, 1) gconv_stack_
 
 }  // namespace pair2
 
+// =====================================================================================================================
+// pw: 1x1 convolution of a whole feature map on the CTA-pair tensor pipeline (training path, N3):
+//     y[b, n, p] = [relu](sum_c w[n, c] x[b, c, p] + bias[n])   [zeroed where mask[b, n, p] <= 0]
+// for N = C = 256 -- the regular layers of CustomEquivariantNetwork in train() mode (feature maps kept) and, with w
+// transposed and mask = the saved input of the layer, their data gradient through the preceding ReLU
+// (custom_group_equivariant_layers.py:298-334 after the filter orbit; eqb_conv2d_forward's contract).
+// Same numerics as the stack kernel: fp16 hi/lo split of both operands (3 MMAs per product, ~22-bit significands),
+// power-of-two operand scales (per IMAGE for x), fp32 accumulation in TMEM.
+//   warp 0      (both CTAs) TMA: fp32 boxes [32 channels x 128 pixels] of x -> 3-stage staging ring (16 KB each)
+//   warps 4-11  (both CTAs) converters: thread = (pixel, channel half): 16 staged values -> scaled fp16 hi / lo -> the K-major
+//               64-byte-swizzled B-operand atom [128 pixels x 32 channels] of this CTA (2-stage ring)
+//   warp 1      (leader)    8 atoms x 6 MMAs (cta_group::2, M = 256 channels, N = 256 pixels) into D[tile & 1]
+//   warps 12-19 (both CTAs) epilogue: this CTA's 128 channels x 256 pixels of D -> scale, bias, ReLU, mask -> y (each thread
+//               one channel row, 128 contiguous bytes per 32-column chunk); max |y| per image for the next layer's scale
+// TMEM holds two accumulators (2 x 256 columns): the epilogue of tile t runs under the MMAs of tile t + 1.
+// Bound: x read once + y written once (+ mask read): 1.1-1.7 GB per call at B = 64 against 213 GFLOP of MMAs: HBM.
+namespace pw {
+
+using namespace pair;
+
+constexpr int XS_RING = 3, A_RING = 2;
+constexpr int XS_STAGE = 32 * 128 * 4;
+enum { B_XFULL = 0, B_XEMPTY = B_XFULL + XS_RING, B_AFULL = B_XEMPTY + XS_RING, B_AEMPTY = B_AFULL + A_RING,
+       B_DFULL = B_AEMPTY + A_RING, B_DEMPTY = B_DFULL + 2, B_WLOAD = B_DEMPTY + 2, B_COUNT };
+
+struct Smem {
+    uint32_t w1, xs, a1, bars, tmem_slot, total;
+};
+__host__ __device__ inline Smem smem_map() {
+    Smem s;
+    uint32_t o = 0;
+    s.w1 = o; o += 8 * W1_ATOM;              // 128 KB: this CTA's 128 rows of w, hi + lo, 8 K atoms
+    s.xs = o; o += XS_RING * XS_STAGE;       // 48 KB
+    s.a1 = o; o += A_RING * A1_STAGE;        // 32 KB
+    s.bars = o; o += B_COUNT * 8;
+    s.tmem_slot = o; o += 16;
+    s.total = o;
+    return s;
+}
+
+struct Args {
+    const unsigned char *wpack;   // header {sw} + 8 atoms x (hi stage, lo stage) of 256 rows x 64 bytes (pw_pack_kernel)
+    const float *bias, *mask, *absmax_in;
+    float *y, *absmax_out;
+    int B, P, tiles, relu;        // tiles = pair-tiles (256 pixels) per image
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(768, 1) pw_conv_kernel(const __grid_constant__ CUtensorMap xmap, const Args a) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    const uint32_t base = smem_u32(smem_raw);
+    unsigned char *sm = smem_raw;
+    const Smem M = smem_map();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_rank();
+    const uint32_t bars = base + M.bars;
+    auto bar = [&](int i) { return bars + 8u * (uint32_t)i; };
+    auto leader_bar = [&](int i) { return map_to_rank(bar(i), 0); };
+    if ((base & 1023u) != 0) __trap();
+    const unsigned char *img = a.wpack + HDR_BYTES;
+    const uint32_t gstage = 256u * 64u;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < XS_RING; ++i) {
+            mbar_init(bar(B_XFULL + i), 1);
+            mbar_init(bar(B_XEMPTY + i), 256);     // this CTA's converter threads
+        }
+        for (int i = 0; i < A_RING; ++i) {
+            mbar_init(bar(B_AFULL + i), 512);      // converter threads of both CTAs
+            mbar_init(bar(B_AEMPTY + i), 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(bar(B_DFULL + i), 1);
+            mbar_init(bar(B_DEMPTY + i), 512);     // epilogue threads of both CTAs
+        }
+        mbar_init(bar(B_WLOAD), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_expect_tx(bar(B_WLOAD), 8u * W1_ATOM);
+        for (int c = 0; c < 8; ++c) {
+            const unsigned char *src = img + (size_t)(2 * c) * gstage;
+            bulk_load(base + M.w1 + c * W1_ATOM, src + rank * 8192u, 8192u, bar(B_WLOAD));
+            bulk_load(base + M.w1 + c * W1_ATOM + 8192u, src + gstage + rank * 8192u, 8192u, bar(B_WLOAD));
+        }
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(base + M.tmem_slot), "r"(512)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    mbar_wait(bar(B_WLOAD), 0, 100 + B_WLOAD);
+    cluster_sync();
+    tc_fence_after();
+    const uint32_t tmem = *reinterpret_cast<volatile uint32_t *>(sm + M.tmem_slot);
+    const float sw = *reinterpret_cast<const float *>(a.wpack);
+
+    const int cid = (int)blockIdx.x >> 1, ncl = (int)gridDim.x >> 1;
+    const int total = a.B * a.tiles;
+    const uint32_t idesc = (1u << 4) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+
+    if (warp == 0) {
+        // ===== TMA producer: 8 boxes per tile ================================================================================
+        if (lane == 0) {
+            uint32_t seq = 0;
+            for (int T = cid; T < total; T += ncl) {
+                const int b = T / a.tiles, t = T - b * a.tiles;
+                for (int kc = 0; kc < 8; ++kc, ++seq) {
+                    const uint32_t s = seq % XS_RING, ph = (seq / XS_RING) & 1u;
+                    mbar_wait(bar(B_XEMPTY + s), ph ^ 1u, 100 + B_XEMPTY + s);
+                    mbar_expect_tx(bar(B_XFULL + s), (uint32_t)XS_STAGE);
+                    // pixels past the end of the plane are zero-filled by the TMA unit
+                    asm volatile(
+                        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                        ::"r"(base + M.xs + s * XS_STAGE), "l"((uint64_t)&xmap), "r"(bar(B_XFULL + s)),
+                          "r"(t * 256 + 128 * (int)rank), "r"(b * 256 + 32 * kc), "r"(0)
+                        : "memory");
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (rank == 0) {
+            // ===== MMA issuer =================================================================================================
+            Ring<A_RING> ra;
+            const uint32_t a_lo0 = desc_lo(base + M.a1), w_lo0 = desc_lo(base + M.w1);
+            int n = 0;
+            for (int T = cid; T < total; T += ncl, ++n) {
+                const uint32_t d = (uint32_t)n & 1u, dph = ((uint32_t)n >> 1) & 1u;
+                mbar_wait_cluster(bar(B_DEMPTY + d), dph ^ 1u, 100 + B_DEMPTY + d);
+                for (int kc = 0; kc < 8; ++kc) {
+                    mbar_wait_cluster(bar(B_AFULL + ra.stage), ra.phase, 100 + B_AFULL + ra.stage);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint32_t a_hi = a_lo0 + (uint32_t)ra.stage * (A1_STAGE >> 4), a_lo = a_hi + (A1_HALF >> 4);
+                        const uint32_t w_hi = w_lo0 + (uint32_t)kc * (W1_ATOM >> 4), w_lo = w_hi + (8192u >> 4);
+                        const uint32_t dt = tmem + 256u * d;
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) tc_mma2_f16_lo<DESC_HI_64B>(dt, w_hi + 2 * j, a_hi + 2 * j, idesc, j ? 1u : (uint32_t)(kc != 0));
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) tc_mma2_f16_lo<DESC_HI_64B>(dt, w_hi + 2 * j, a_lo + 2 * j, idesc, 1);
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) tc_mma2_f16_lo<DESC_HI_64B>(dt, w_lo + 2 * j, a_hi + 2 * j, idesc, 1);
+                        tc_commit2(bar(B_AEMPTY + ra.stage));
+                        if (kc == 7) tc_commit2(bar(B_DFULL + d));
+                    }
+                    __syncwarp();
+                    ra.advance();
+                }
+            }
+        }
+    } else if (warp >= 4 && warp < 12) {
+        // ===== converters: staged fp32 box -> this CTA's rows of the B-operand atom ==========================================
+        const int tc_ = (int)threadIdx.x - 128, px = tc_ & 127, h = tc_ >> 7;
+        const uint32_t row_off = (uint32_t)px * 64u, swz = (uint32_t)((px >> 1) & 3);
+        const uint32_t afull0 = leader_bar(B_AFULL);
+        uint32_t seq = 0, aseq = 0;
+        for (int T = cid; T < total; T += ncl) {
+            const int b = T / a.tiles;
+            const float sx = pow2_scale(__ldg(a.absmax_in + b));
+            for (int kc = 0; kc < 8; ++kc, ++seq, ++aseq) {
+                const uint32_t s = seq % XS_RING, ph = (seq / XS_RING) & 1u;
+                mbar_wait(bar(B_XFULL + s), ph, 100 + B_XFULL + s);
+                const float *xs = reinterpret_cast<const float *>(sm + M.xs + s * XS_STAGE) + (16 * h) * 128 + px;
+                float v[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = xs[i * 128];
+                mbar_arrive(bar(B_XEMPTY + s));          // (release: the loads above are performed)
+                uint32_t hi[8], lo[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) split2(v[2 * i] * sx, v[2 * i + 1] * sx, hi[i], lo[i]);
+                const uint32_t sa = aseq % A_RING, pa = (aseq / A_RING) & 1u;
+                mbar_wait(bar(B_AEMPTY + sa), pa ^ 1u, 100 + B_AEMPTY + sa);
+                const uint32_t hi_row = base + M.a1 + sa * A1_STAGE + row_off, lo_row = hi_row + A1_HALF;
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const uint32_t col = ((uint32_t)(2 * h + j) ^ swz) << 4;
+                    st_shared_v4(hi_row + col, hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+                    st_shared_v4(lo_row + col, lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+                }
+                fence_async_smem();
+                mbar_arrive_cluster(afull0 + 8u * sa);
+            }
+        }
+    } else if (warp >= 12 && warp < 20) {
+        // ===== epilogue: D[tile & 1] -> y =====================================================================================
+        const int q = warp & 3, g = (warp - 12) >> 2;
+        const int chan = 128 * (int)rank + 32 * q + lane;
+        const float bv = a.bias ? __ldg(a.bias + chan) : 0.f;
+        const uint32_t dempty0 = leader_bar(B_DEMPTY);
+        int n = 0, cur_b = -1;
+        float m = 0.f;
+        auto flush_max = [&]() {
+            if (a.absmax_out && cur_b >= 0) {
+                for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+                if (lane == 0) atomicMax(reinterpret_cast<unsigned int *>(a.absmax_out + cur_b), __float_as_uint(m));
+            }
+            m = 0.f;
+        };
+        float cs = 0.f;
+        for (int T = cid; T < total; T += ncl, ++n) {
+            const int b = T / a.tiles, t = T - b * a.tiles;
+            if (b != cur_b) {
+                flush_max();
+                cur_b = b;
+                cs = 1.f / (pow2_scale(__ldg(a.absmax_in + b)) * sw);     // powers of two: exact
+            }
+            const uint32_t d = (uint32_t)n & 1u, dph = ((uint32_t)n >> 1) & 1u;
+            mbar_wait(bar(B_DFULL + d), dph, 100 + B_DFULL + d);
+            tc_fence_after();
+            const uint32_t t0 = tmem + 256u * d + ((uint32_t)(q * 32) << 16) + (uint32_t)(128 * g);
+            const int p0 = t * 256 + 128 * g;
+            const size_t off = ((size_t)b * 256 + chan) * (size_t)a.P + p0;
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+                const int nvalid = min(32, a.P - (p0 + 32 * c));       // (uniform; P % 4 == 0)
+                if (nvalid > 0) {
+                    uint32_t r[32];
+                    tc_ld32_issue(t0 + (uint32_t)(32 * c), r);
+                    tc_ld_wait(r);
+                    float *yp = a.y + off + 32 * c;
+                    const float *mp = a.mask ? a.mask + off + 32 * c : nullptr;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        if (4 * i < nvalid) {
+                            float4 o;
+                            o.x = fmaf(__uint_as_float(r[4 * i]), cs, bv);
+                            o.y = fmaf(__uint_as_float(r[4 * i + 1]), cs, bv);
+                            o.z = fmaf(__uint_as_float(r[4 * i + 2]), cs, bv);
+                            o.w = fmaf(__uint_as_float(r[4 * i + 3]), cs, bv);
+                            if (a.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                            if (mp) {
+                                const float4 k4 = __ldg(reinterpret_cast<const float4 *>(mp) + i);
+                                o.x = k4.x > 0.f ? o.x : 0.f; o.y = k4.y > 0.f ? o.y : 0.f;
+                                o.z = k4.z > 0.f ? o.z : 0.f; o.w = k4.w > 0.f ? o.w : 0.f;
+                            }
+                            m = fmaxf(m, fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fmaxf(fabsf(o.z), fabsf(o.w))));
+                            reinterpret_cast<float4 *>(yp)[i] = o;
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive_cluster(dempty0 + 8u * d);
+        }
+        flush_max();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+    }
+}
+
+// {sw} = power-of-two scale of w (N x K floats, row-major)
+__global__ void __launch_bounds__(256) pw_header_kernel(const float *__restrict__ w, int n, float *__restrict__ hdr) {
+    __shared__ float red[256];
+    float m = 0.f;
+    for (int i = threadIdx.x; i < n; i += 256) m = fmaxf(m, fabsf(w[i]));
+    red[threadIdx.x] = m;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) red[threadIdx.x] = fmaxf(red[threadIdx.x], red[threadIdx.x + o]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) hdr[0] = pow2_scale(red[0]);
+}
+// w[n][k] (256 x 256) -> UMMA images, the layout pack_tc_weights_kernel gives the 1x1 layer of the stack
+__global__ void pw_pack_kernel(const float *__restrict__ w, const float *__restrict__ hdr, unsigned char *__restrict__ out) {
+    const float sw = hdr[0];
+    const int total = 8 * 256 * ATOM_K;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+        const int ks = t % ATOM_K, n = (t / ATOM_K) % 256, atom = t / (ATOM_K * 256);
+        const float v = w[(size_t)n * 256 + atom * ATOM_K + ks] * sw;
+        const __half hi = __float2half_rn(v), lo = __float2half_rn(v - __half2float(hi));
+        const size_t stage = (size_t)256 * 64;
+        const size_t off = (size_t)n * 64 + (size_t)((((ks >> 3) ^ ((n >> 1) & 3)) << 4) | ((ks & 7) << 1));
+        *reinterpret_cast<__half *>(out + (size_t)(2 * atom) * stage + off) = hi;
+        *reinterpret_cast<__half *>(out + (size_t)(2 * atom + 1) * stage + off) = lo;
+    }
+}
+
+}  // namespace pw
+
 // Header of the packed buffer: power-of-two operand scales and the pieces of the hidden-activation bound.
 //   hdr[0] = sw0 (lift weights), hdr[1] = sw1 (1x1 weights), hdr[2] = R0 = max_n sum_k |W0[k][n]|, hdr[3] = max |b1|
 __global__ void __launch_bounds__(256) tc_header_kernel(const float *__restrict__ Wt0, int K0, const float *__restrict__ Wt1,
@@ -2069,7 +2355,8 @@ int tc_last_stall(int *out5) {
     return g_stall_host[0];
 }
 
-int tc_launch(TcArgs a, cudaStream_t st) {
+// host-mapped record the bounded pipeline waits write before they trap (eqb_debug_last_stall)
+static int ensure_stall_report() {
     if (!g_stall_host) {
         EQB_CUDA(cudaHostAlloc((void **)&g_stall_host, 8 * sizeof(int), cudaHostAllocMapped | cudaHostAllocPortable));
         for (int i = 0; i < 8; ++i) g_stall_host[i] = 0;
@@ -2080,6 +2367,69 @@ int tc_launch(TcArgs a, cudaStream_t st) {
         EQB_CUDA(cudaHostGetDevicePointer((void **)&dptr, g_stall_host, 0));
         EQB_CUDA(cudaMemcpyToSymbol(tc::g_stall_report, &dptr, sizeof(dptr)));
     }
+    return 0;
+}
+
+// 1x1 convolution (N = cin = 256) of a whole NCHW feature map on the tensor pipe: see tc::pw.  *handled = 0 when the shape
+// or the alignment is outside what the kernel takes (the caller runs the fp32 SIMT kernel), or with EQB_TRAIN_TC=0.
+int tc_pw_conv(const float *x, const float *w, const float *bias, const float *mask, float *y, int B, int cin, long long P,
+               int N, int relu, cudaStream_t st, int *handled) {
+    *handled = 0;
+    const char *e = getenv("EQB_TRAIN_TC");
+    if (e && e[0] == '0') return 0;
+    if (cin != 256 || N != 256 || P <= 0 || (P & 3) != 0 || P >= (1LL << 30) || B <= 0 || (long long)B * 256 >= (1LL << 31)) return 0;
+    if ((((uintptr_t)x | (uintptr_t)y | (uintptr_t)mask) & 15) != 0) return 0;
+    if (int err = ensure_stall_report()) return err;
+    // packed weights + per-image maxima: one persistent buffer per (device, stream) -- stream-ordered allocation costs
+    // milliseconds per call once the pool is trimmed at every synchronisation of a training step (measured: 15 -> 65 ms)
+    const size_t wbytes = (size_t)tc::HDR_BYTES + 16 * 16384;
+    struct Scratch { int dev; cudaStream_t st; unsigned char *ptr; size_t bytes; };
+    static Scratch cache[16];
+    static int used = 0;
+    const size_t need = wbytes + (size_t)B * sizeof(float);
+    int dev = 0;
+    EQB_CUDA(cudaGetDevice(&dev));
+    Scratch *sc = nullptr;
+    for (int i = 0; i < used; ++i)
+        if (cache[i].dev == dev && cache[i].st == st) sc = &cache[i];
+    if (!sc) {
+        EQB_UNSUPPORTED(used >= 16, "tc_pw_conv: more than %d (device, stream) pairs in one process", 16);
+        sc = &cache[used++];
+        *sc = Scratch{dev, st, nullptr, 0};
+    }
+    if (sc->bytes < need) {
+        if (sc->ptr) {
+            EQB_CUDA(cudaStreamSynchronize(st));
+            EQB_CUDA(cudaFree(sc->ptr));
+            sc->ptr = nullptr; sc->bytes = 0;
+        }
+        EQB_CUDA(cudaMalloc((void **)&sc->ptr, need));
+        sc->bytes = need;
+    }
+    unsigned char *scratch = sc->ptr;
+    float *absmax = reinterpret_cast<float *>(scratch + wbytes);
+    if (int err = tc_absmax(x, B, (size_t)256 * (size_t)P, absmax, st)) return err;
+    tc::pw::pw_header_kernel<<<1, 256, 0, st>>>(w, 256 * 256, reinterpret_cast<float *>(scratch));
+    tc::pw::pw_pack_kernel<<<64, 256, 0, st>>>(w, reinterpret_cast<const float *>(scratch), scratch + tc::HDR_BYTES);
+    CUtensorMap map;
+    if (int err = make_plane_map(&map, x, (int)P, B * 256, 1, 128, 32, CU_TENSOR_MAP_SWIZZLE_NONE)) return err;
+    tc::pw::Args a{};
+    a.wpack = scratch; a.bias = bias; a.mask = mask; a.absmax_in = absmax; a.y = y; a.absmax_out = nullptr;
+    a.B = B; a.P = (int)P; a.tiles = (int)((P + 255) / 256); a.relu = relu;
+    const tc::pw::Smem M = tc::pw::smem_map();
+    static PerDeviceOnce configured;
+    if (configured.first())
+        EQB_CUDA(cudaFuncSetAttribute(tc::pw::pw_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    const long long total = (long long)B * a.tiles;
+    const int max_clusters = num_sms() / 2;
+    const int clusters = total < max_clusters ? (int)total : max_clusters;
+    tc::pw::pw_conv_kernel<<<2 * clusters, 768, M.total, st>>>(map, a);
+    *handled = 1;
+    return finish_launch("pw_conv_kernel");
+}
+
+int tc_launch(TcArgs a, cudaStream_t st) {
+    if (int err = ensure_stall_report()) return err;
     a.K0pad = (a.K0 + tc::SLAB_K - 1) / tc::SLAB_K * tc::SLAB_K;
     // Pipeline-shape knobs, defaults = the measured best (profiles/r1h_summary.md): with the kernel bound by
     // shared-memory bandwidth (UMMA operand reads + weight stages + epilogue stores) a second epilogue-1 group

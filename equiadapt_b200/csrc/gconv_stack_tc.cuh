@@ -33,6 +33,9 @@ int tc_pack(const float *Wt0, int K0, const float *Wt1, const float *bias1, int 
             cudaStream_t st);
 int tc_absmax(const float *x, int B, size_t n_per_image, float *absmax, cudaStream_t st);   // absmax[b] = max |x[b]|
 int tc_launch(TcArgs a, cudaStream_t st);
+// 1x1 convolution with N = cin = 256 on the tensor pipe (training path); *handled = 0: shape not taken, run the SIMT kernel
+int tc_pw_conv(const float *x, const float *w, const float *bias, const float *mask, float *y, int B, int cin, long long P,
+               int N, int relu, cudaStream_t st, int *handled);
 int tc_set_trace(long long *device_buffer, int tiles);   // next CTA-pair launches record a timeline (null: off)
 int tc_last_stall(int *out5);  // {flag, block, warp, barrier id, parity} of the first pipeline stall that trapped
 

@@ -14,6 +14,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "gconv_stack_tc.cuh"
 
 namespace eqb {
 
@@ -270,6 +271,12 @@ extern "C" int eqb_conv2d_forward(const float *x, const float *w, const float *b
     EQB_REQUIRE(B <= 65535 && (N + GT_T - 1) / GT_T <= 65535, "eqb_conv2d_forward: grid too large");
     if (B == 0) return 0;
     const int P = (H - k + 1) * (W - k + 1);
+    if (k == 1) {
+        // 256 -> 256 channels: CTA-pair tcgen05 kernel with the fp16 hi/lo operand split (gconv_stack_tc.cu, namespace pw)
+        int handled = 0;
+        if (int err = tc_pw_conv(x, w, bias, mask, y, B, cin, (long long)P, N, relu, (cudaStream_t)stream, &handled)) return err;
+        if (handled) return 0;
+    }
     dim3 grid((P + GT_T - 1) / GT_T, (N + GT_T - 1) / GT_T, B);
     conv2d_forward_kernel<<<grid, GT_THREADS, 0, (cudaStream_t)stream>>>(x, w, bias, mask, y, cin, H, W, k, N, relu);
     return finish_launch("eqb_conv2d_forward");

@@ -1202,6 +1202,41 @@ def test_conv2d_forward_and_weight_grad_vs_torch(b, cin, h, w, n, k, relu, cuda_
     assert rel_err(ops.plane_sums(dy.to(dev)).cpu().double(), dy.double().sum((2, 3))) < 1e-5
 
 
+@pytest.mark.parametrize("b,h,w", [(2, 16, 16), (3, 20, 20), (2, 92, 92), (1, 4, 20)])
+def test_pointwise_conv_tensor_core_path_vs_torch(b, h, w, cuda_device, monkeypatch):
+    """eqb_conv2d_forward with k = 1, 256 -> 256 channels takes the CTA-pair tcgen05 kernel (csrc/gconv_stack_tc.cu,
+    namespace pw: fp16 hi/lo operand split, per-image power-of-two scales, fp32 accumulation in TMEM): the regular layers of
+    CustomEquivariantNetwork in train() and their data gradient (custom_group_equivariant_layers.py:298-334).  Against torch
+    fp64 per image -- images of very different ranges share the batch -- at 4e-6 of the image's max |y| (the tensor core's
+    fp32 accumulation truncates: ~1.5e-6 measured; the SIMT kernel gives ~3e-7), and against the SIMT kernel (EQB_TRAIN_TC=0)."""
+    ops = _mods()[0]
+    dev = cuda_device
+    g = torch.Generator().manual_seed(b * 1000 + h)
+    x = (torch.randn(b, 256, h, w, generator=g) * torch.logspace(-2, 2, b)[:, None, None, None]).to(dev)
+    wt = (torch.randn(256, 256, 1, 1, generator=g) / 16).to(dev)
+    bias = torch.randn(256, generator=g).to(dev)
+    mask = torch.randn(b, 256, h, w, generator=g).to(dev)
+
+    def check(y, want):
+        scale = want.abs().amax(dim=(1, 2, 3), keepdim=True).clamp_min(1e-30)
+        return float(((y.double() - want).abs() / scale).max())
+
+    lin = torch.einsum("nc,bchw->bnhw", wt[:, :, 0, 0].double(), x.double())
+    want_f = (lin + bias.double()[None, :, None, None]).clamp_min(0)
+    want_g = torch.where(mask > 0, lin, torch.zeros_like(lin))
+    y_f = ops.conv2d_forward(x, wt, bias, True)
+    y_g = ops.conv2d_forward(x, wt, None, False, mask=mask)
+    assert check(y_f, want_f) < 4e-6 and check(y_g, want_g) < 4e-6
+    monkeypatch.setenv("EQB_TRAIN_TC", "0")
+    s_f = ops.conv2d_forward(x, wt, bias, True)
+    s_g = ops.conv2d_forward(x, wt, None, False, mask=mask)
+    assert check(s_f, want_f) < 1e-6 and check(s_g, want_g) < 1e-6
+    assert not torch.equal(s_f, y_f)          # (two different kernels really ran)
+    # masked-out and ReLU-clamped positions are exact zeros on both paths
+    assert torch.equal(y_g == 0, (mask <= 0) | (y_g == 0)) and bool((y_g[mask <= 0] == 0).all())
+    assert bool((y_f >= 0).all())
+
+
 @pytest.mark.parametrize("n,reflect,k", [(4, False, 5), (8, False, 5), (8, True, 3), (6, True, 1)])
 def test_filter_orbit_adjoints_vs_oracle_autograd(n, reflect, k, cuda_device):
     ops = _mods()[0]

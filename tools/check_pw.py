@@ -1,0 +1,45 @@
+"""eqb_conv2d_forward with k = 1, 256 -> 256 channels: tcgen05 kernel (tc::pw) against an fp64 torch reference and the SIMT kernel; timing at
+the training shape (64 x 256 x 92 x 92).  Development aid.  tools/check_pw.py"""
+import os, sys, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from equiadapt_b200 import ops
+
+torch.manual_seed(0)
+dev = "cuda"
+
+
+def ref(x, w, bias, relu, mask):
+    y = torch.einsum("nc,bchw->bnhw", w[:, :, 0, 0].double(), x.double())
+    if bias is not None: y = y + bias.double()[None, :, None, None]
+    if relu: y = y.clamp_min(0)
+    if mask is not None: y = torch.where(mask > 0, y, torch.zeros_like(y))
+    return y
+
+
+for (B, H, W) in ((2, 16, 16), (3, 20, 20), (2, 92, 92), (1, 4, 5 * 4)):
+    for relu, use_mask, use_bias in ((True, False, True), (False, True, False)):
+        # heterogeneous ranges per image: the operand scale is per image
+        x = torch.randn(B, 256, H, W, device=dev) * torch.logspace(-2, 2, B, device=dev)[:, None, None, None]
+        w = torch.randn(256, 256, 1, 1, device=dev) / 16
+        bias = torch.randn(256, device=dev) if use_bias else None
+        mask = torch.randn(B, 256, H, W, device=dev) if use_mask else None
+        y = ops.conv2d_forward(x, w, bias, relu, mask)
+        torch.cuda.synchronize()
+        r = ref(x, w, bias, relu, mask)
+        scale = r.abs().amax(dim=(1, 2, 3), keepdim=True).clamp_min(1e-30)
+        err = ((y.double() - r).abs() / scale).max().item()
+        print(f"B={B} HxW={H}x{W} relu={relu} mask={use_mask}: max err / max|y| per image = {err:.3e}", "OK" if err < 2e-6 else "FAIL")
+
+B, H, W = 64, 92, 92
+x = torch.randn(B, 256, H, W, device=dev)
+w = torch.randn(256, 256, 1, 1, device=dev) / 16
+bias = torch.randn(256, device=dev)
+mask = torch.randn(B, 256, H, W, device=dev)
+for name, args in (("forward relu+bias", (x, w, bias, True, None)), ("dgrad with mask", (x, w, None, False, mask))):
+    for _ in range(2): ops.conv2d_forward(*args)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5): ops.conv2d_forward(*args)
+    e1.record(); torch.cuda.synchronize()
+    print(f"{name}: {e0.elapsed_time(e1) / 5 * 1e3:.0f} us per call (EQB_TRAIN_TC={os.environ.get('EQB_TRAIN_TC', '1')})")
