@@ -2196,6 +2196,217 @@ __global__ void pw_pack_kernel(const float *__restrict__ w, const float *__restr
 
 }  // namespace pw
 
+// =====================================================================================================================
+// wg: weight gradient of the same 1x1 layers, dw[n, c] = sum_{b, p} dy[b, n, p] x[b, c, p]  (N = C = 256; the reduction runs
+// over B * P = 541 696 pixels at the training shape).  Both operands are K-major in global memory as they are (pixels are
+// contiguous), so the pipeline is: TMA boxes [128 rows x 32 pixels] of dy and of x (128-byte swizzle, so that a thread can
+// read its row with conflict-free 16-byte loads) -> converters (thread = one row of one operand: 32 values -> scaled fp16
+// hi / lo -> 64-byte-swizzled atom row) -> 6 MMAs per 32-pixel atom into ONE TMEM accumulator per CTA pair.  The pixel range
+// is split over the clusters (split-K); each adds its 256 x 256 partial into dw (zeroed by the caller) with fp32 atomics,
+// like the SIMT kernel's split-K.  Operand scales are powers of two of the BATCH maxima (one accumulator sums over images).
+// Bound: dy and x read once (1.1 GB at B = 64) against 213 GFLOP of MMAs: HBM.
+namespace wg {
+
+using namespace pair;
+
+constexpr int XS_RING = 3, A_RING = 3;
+constexpr int XS_STAGE = 2 * 128 * 128;      // dy box + x box, 128 rows x 32 floats each: 32 KB
+constexpr int AT_STAGE = 2 * A1_STAGE;       // A atom (dy rows) + B atom (x rows), hi + lo each: 32 KB
+enum { B_XFULL = 0, B_XEMPTY = B_XFULL + XS_RING, B_AFULL = B_XEMPTY + XS_RING, B_AEMPTY = B_AFULL + A_RING,
+       B_DFULL = B_AEMPTY + A_RING, B_COUNT };
+
+struct Smem {
+    uint32_t xs, at, bars, tmem_slot, red, total;
+};
+__host__ __device__ inline Smem smem_map() {
+    Smem s;
+    uint32_t o = 0;
+    s.xs = o; o += XS_RING * XS_STAGE;       // 96 KB
+    s.at = o; o += A_RING * AT_STAGE;        // 96 KB
+    s.bars = o; o += B_COUNT * 8;
+    s.tmem_slot = o; o += 16;
+    s.red = o; o += 2 * 32 * 4;
+    s.total = o;
+    return s;
+}
+
+struct Args {
+    const float *absmax_dy, *absmax_x;   // (B) each
+    float *dw;
+    int B, P, api;                       // api = 32-pixel atoms per image
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(768, 1)
+    pw_wgrad_kernel(const __grid_constant__ CUtensorMap dymap, const __grid_constant__ CUtensorMap xmap, const Args a) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    const uint32_t base = smem_u32(smem_raw);
+    unsigned char *sm = smem_raw;
+    const Smem M = smem_map();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_rank();
+    const uint32_t bars = base + M.bars;
+    auto bar = [&](int i) { return bars + 8u * (uint32_t)i; };
+    auto leader_bar = [&](int i) { return map_to_rank(bar(i), 0); };
+    if ((base & 1023u) != 0) __trap();
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < XS_RING; ++i) {
+            mbar_init(bar(B_XFULL + i), 1);
+            mbar_init(bar(B_XEMPTY + i), 256);
+        }
+        for (int i = 0; i < A_RING; ++i) {
+            mbar_init(bar(B_AFULL + i), 512);
+            mbar_init(bar(B_AEMPTY + i), 1);
+        }
+        mbar_init(bar(B_DFULL), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(base + M.tmem_slot), "r"(256)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    // batch maxima of the two operands -> their power-of-two scales
+    float *red = reinterpret_cast<float *>(sm + M.red);
+    {
+        float m0 = 0.f, m1 = 0.f;
+        for (int b = threadIdx.x; b < a.B; b += blockDim.x) {
+            m0 = fmaxf(m0, __ldg(a.absmax_dy + b));
+            m1 = fmaxf(m1, __ldg(a.absmax_x + b));
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, o));
+            m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, o));
+        }
+        if (lane == 0) { red[warp] = m0; red[32 + warp] = m1; }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync();
+    tc_fence_after();
+    const uint32_t tmem = *reinterpret_cast<volatile uint32_t *>(sm + M.tmem_slot);
+    float s_dy, s_x;
+    {
+        float m0 = 0.f, m1 = 0.f;
+        for (int w = 0; w < 24; ++w) { m0 = fmaxf(m0, red[w]); m1 = fmaxf(m1, red[32 + w]); }
+        s_dy = pow2_scale(m0);
+        s_x = pow2_scale(m1);
+    }
+
+    const int cid = (int)blockIdx.x >> 1, ncl = (int)gridDim.x >> 1;
+    const long long total = (long long)a.B * a.api;
+    const long long per = (total + ncl - 1) / ncl;
+    const long long A0 = (long long)cid * per, A1 = A0 + per < total ? A0 + per : total;
+    const uint32_t idesc = (1u << 4) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t seq = 0;
+            for (long long A = A0; A < A1; ++A, ++seq) {
+                const int b = (int)(A / a.api), ka = (int)(A - (long long)b * a.api);
+                const uint32_t s = seq % XS_RING, ph = (seq / XS_RING) & 1u;
+                mbar_wait(bar(B_XEMPTY + s), ph ^ 1u, 200 + B_XEMPTY + s);
+                mbar_expect_tx(bar(B_XFULL + s), (uint32_t)XS_STAGE);
+                const uint32_t dst = base + M.xs + s * XS_STAGE;
+                asm volatile(
+                    "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                    ::"r"(dst), "l"((uint64_t)&dymap), "r"(bar(B_XFULL + s)), "r"(32 * ka), "r"(b * 256 + 128 * (int)rank), "r"(0)
+                    : "memory");
+                asm volatile(
+                    "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                    ::"r"(dst + 128u * 128u), "l"((uint64_t)&xmap), "r"(bar(B_XFULL + s)), "r"(32 * ka), "r"(b * 256 + 128 * (int)rank), "r"(0)
+                    : "memory");
+            }
+        }
+    } else if (warp == 1) {
+        if (rank == 0) {
+            Ring<A_RING> ra;
+            const uint32_t at_lo0 = desc_lo(base + M.at);
+            for (long long A = A0; A < A1; ++A) {
+                mbar_wait_cluster(bar(B_AFULL + ra.stage), ra.phase, 200 + B_AFULL + ra.stage);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t dy_hi = at_lo0 + (uint32_t)ra.stage * (AT_STAGE >> 4), dy_lo = dy_hi + (A1_HALF >> 4);
+                    const uint32_t x_hi = dy_hi + (A1_STAGE >> 4), x_lo = x_hi + (A1_HALF >> 4);
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) tc_mma2_f16_lo<DESC_HI_64B>(tmem, dy_hi + 2 * j, x_hi + 2 * j, idesc, j ? 1u : (uint32_t)(A != A0));
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) tc_mma2_f16_lo<DESC_HI_64B>(tmem, dy_lo + 2 * j, x_hi + 2 * j, idesc, 1);
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) tc_mma2_f16_lo<DESC_HI_64B>(tmem, dy_hi + 2 * j, x_lo + 2 * j, idesc, 1);
+                    tc_commit2(bar(B_AEMPTY + ra.stage));
+                    if (A + 1 == A1) tc_commit2(bar(B_DFULL));
+                }
+                __syncwarp();
+                ra.advance();
+            }
+        }
+    } else if (warp >= 4 && warp < 12) {
+        // ===== converters: thread = one row of one operand ===================================================================
+        const int tcv = (int)threadIdx.x - 128, r = tcv & 127, o = tcv >> 7;
+        const float sc = o ? s_x : s_dy;
+        const uint32_t src_row = (uint32_t)o * (128u * 128u) + (uint32_t)r * 128u, sx7 = (uint32_t)(r & 7);
+        const uint32_t dst_row = (uint32_t)o * A1_STAGE + (uint32_t)r * 64u, swz = (uint32_t)((r >> 1) & 3);
+        const uint32_t afull0 = leader_bar(B_AFULL);
+        uint32_t seq = 0;
+        for (long long A = A0; A < A1; ++A, ++seq) {
+            const uint32_t s = seq % XS_RING, ph = (seq / XS_RING) & 1u;
+            mbar_wait(bar(B_XFULL + s), ph, 200 + B_XFULL + s);
+            const unsigned char *box = sm + M.xs + s * XS_STAGE + src_row;
+            float4 v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = *reinterpret_cast<const float4 *>(box + (((uint32_t)j ^ sx7) << 4));
+            mbar_arrive(bar(B_XEMPTY + s));
+            uint32_t hi[16], lo[16];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                split2(v[j].x * sc, v[j].y * sc, hi[2 * j], lo[2 * j]);
+                split2(v[j].z * sc, v[j].w * sc, hi[2 * j + 1], lo[2 * j + 1]);
+            }
+            const uint32_t sa = seq % A_RING, pa = (seq / A_RING) & 1u;
+            mbar_wait(bar(B_AEMPTY + sa), pa ^ 1u, 200 + B_AEMPTY + sa);
+            const uint32_t hi_row = base + M.at + sa * AT_STAGE + dst_row, lo_row = hi_row + A1_HALF;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const uint32_t col = ((uint32_t)c ^ swz) << 4;
+                st_shared_v4(hi_row + col, hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
+                st_shared_v4(lo_row + col, lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
+            }
+            fence_async_smem();
+            mbar_arrive_cluster(afull0 + 8u * sa);
+        }
+    } else if (warp >= 12 && warp < 20) {
+        // ===== epilogue: this CTA's 128 rows of the partial -> dw ============================================================
+        if (A1 > A0) {
+            const int q = warp & 3, g = (warp - 12) >> 2;
+            const int n = 128 * (int)rank + 32 * q + lane;
+            const float cs = 1.f / (s_dy * s_x);
+            mbar_wait(bar(B_DFULL), 0, 200 + B_DFULL);
+            tc_fence_after();
+            const uint32_t t0 = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(128 * g);
+            float *dst = a.dw + (size_t)n * 256 + 128 * g;
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+                uint32_t rr[32];
+                tc_ld32_issue(t0 + (uint32_t)(32 * c), rr);
+                tc_ld_wait(rr);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) atomicAdd(dst + 32 * c + i, __uint_as_float(rr[i]) * cs);
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256) : "memory");
+    }
+}
+
+}  // namespace wg
+
 // Header of the packed buffer: power-of-two operand scales and the pieces of the hidden-activation bound.
 //   hdr[0] = sw0 (lift weights), hdr[1] = sw1 (1x1 weights), hdr[2] = R0 = max_n sum_k |W0[k][n]|, hdr[3] = max |b1|
 __global__ void __launch_bounds__(256) tc_header_kernel(const float *__restrict__ Wt0, int K0, const float *__restrict__ Wt1,
@@ -2370,30 +2581,20 @@ static int ensure_stall_report() {
     return 0;
 }
 
-// 1x1 convolution (N = cin = 256) of a whole NCHW feature map on the tensor pipe: see tc::pw.  *handled = 0 when the shape
-// or the alignment is outside what the kernel takes (the caller runs the fp32 SIMT kernel), or with EQB_TRAIN_TC=0.
-int tc_pw_conv(const float *x, const float *w, const float *bias, const float *mask, float *y, int B, int cin, long long P,
-               int N, int relu, cudaStream_t st, int *handled) {
-    *handled = 0;
-    const char *e = getenv("EQB_TRAIN_TC");
-    if (e && e[0] == '0') return 0;
-    if (cin != 256 || N != 256 || P <= 0 || (P & 3) != 0 || P >= (1LL << 30) || B <= 0 || (long long)B * 256 >= (1LL << 31)) return 0;
-    if ((((uintptr_t)x | (uintptr_t)y | (uintptr_t)mask) & 15) != 0) return 0;
-    if (int err = ensure_stall_report()) return err;
-    // packed weights + per-image maxima: one persistent buffer per (device, stream) -- stream-ordered allocation costs
-    // milliseconds per call once the pool is trimmed at every synchronisation of a training step (measured: 15 -> 65 ms)
-    const size_t wbytes = (size_t)tc::HDR_BYTES + 16 * 16384;
+// Packed weights + per-image maxima of the training kernels: one persistent buffer per (device, stream) -- stream-ordered
+// allocation costs milliseconds per call once the pool is trimmed at every synchronisation of a training step (measured:
+// the step went from 15 to 65 ms with cudaMallocAsync here).
+static int pw_scratch(cudaStream_t st, size_t need, unsigned char **out) {
     struct Scratch { int dev; cudaStream_t st; unsigned char *ptr; size_t bytes; };
     static Scratch cache[16];
     static int used = 0;
-    const size_t need = wbytes + (size_t)B * sizeof(float);
     int dev = 0;
     EQB_CUDA(cudaGetDevice(&dev));
     Scratch *sc = nullptr;
     for (int i = 0; i < used; ++i)
         if (cache[i].dev == dev && cache[i].st == st) sc = &cache[i];
     if (!sc) {
-        EQB_UNSUPPORTED(used >= 16, "tc_pw_conv: more than %d (device, stream) pairs in one process", 16);
+        EQB_UNSUPPORTED(used >= 16, "training kernels: more than %d (device, stream) pairs in one process", 16);
         sc = &cache[used++];
         *sc = Scratch{dev, st, nullptr, 0};
     }
@@ -2406,7 +2607,54 @@ int tc_pw_conv(const float *x, const float *w, const float *bias, const float *m
         EQB_CUDA(cudaMalloc((void **)&sc->ptr, need));
         sc->bytes = need;
     }
-    unsigned char *scratch = sc->ptr;
+    *out = sc->ptr;
+    return 0;
+}
+
+// Weight gradient of a 1x1 layer with N = cin = 256 on the tensor pipe (tc::wg); dw must be zeroed by the caller.
+int tc_pw_wgrad(const float *dy, const float *x, float *dw, int B, int cin, long long P, int N, cudaStream_t st, int *handled) {
+    *handled = 0;
+    const char *e = getenv("EQB_TRAIN_TC");
+    if (e && e[0] == '0') return 0;
+    if (cin != 256 || N != 256 || P <= 0 || (P & 3) != 0 || P >= (1LL << 30) || B <= 0 || (long long)B * 256 >= (1LL << 31)) return 0;
+    if ((((uintptr_t)x | (uintptr_t)dy) & 15) != 0) return 0;
+    if (int err = ensure_stall_report()) return err;
+    unsigned char *scratch = nullptr;
+    const size_t wbytes = (size_t)tc::HDR_BYTES + 16 * 16384;         // (the forward's region of the same buffer stays untouched)
+    if (int err = pw_scratch(st, wbytes + 3 * (size_t)B * sizeof(float), &scratch)) return err;
+    float *am_dy = reinterpret_cast<float *>(scratch + wbytes) + B, *am_x = am_dy + B;
+    if (int err = tc_absmax(dy, B, (size_t)256 * (size_t)P, am_dy, st)) return err;
+    if (int err = tc_absmax(x, B, (size_t)256 * (size_t)P, am_x, st)) return err;
+    CUtensorMap dymap, xmap;
+    if (int err = make_plane_map(&dymap, dy, (int)P, B * 256, 1, 32, 128, CU_TENSOR_MAP_SWIZZLE_128B)) return err;
+    if (int err = make_plane_map(&xmap, x, (int)P, B * 256, 1, 32, 128, CU_TENSOR_MAP_SWIZZLE_128B)) return err;
+    tc::wg::Args a{};
+    a.absmax_dy = am_dy; a.absmax_x = am_x; a.dw = dw; a.B = B; a.P = (int)P; a.api = (int)((P + 31) / 32);
+    const tc::wg::Smem M = tc::wg::smem_map();
+    static PerDeviceOnce configured;
+    if (configured.first())
+        EQB_CUDA(cudaFuncSetAttribute(tc::wg::pw_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    const long long total = (long long)B * a.api;
+    const int max_clusters = num_sms() / 2;
+    const int clusters = total < max_clusters ? (int)total : max_clusters;
+    tc::wg::pw_wgrad_kernel<<<2 * clusters, 768, M.total, st>>>(dymap, xmap, a);
+    *handled = 1;
+    return finish_launch("pw_wgrad_kernel");
+}
+
+// 1x1 convolution (N = cin = 256) of a whole NCHW feature map on the tensor pipe: see tc::pw.  *handled = 0 when the shape
+// or the alignment is outside what the kernel takes (the caller runs the fp32 SIMT kernel), or with EQB_TRAIN_TC=0.
+int tc_pw_conv(const float *x, const float *w, const float *bias, const float *mask, float *y, int B, int cin, long long P,
+               int N, int relu, cudaStream_t st, int *handled) {
+    *handled = 0;
+    const char *e = getenv("EQB_TRAIN_TC");
+    if (e && e[0] == '0') return 0;
+    if (cin != 256 || N != 256 || P <= 0 || (P & 3) != 0 || P >= (1LL << 30) || B <= 0 || (long long)B * 256 >= (1LL << 31)) return 0;
+    if ((((uintptr_t)x | (uintptr_t)y | (uintptr_t)mask) & 15) != 0) return 0;
+    if (int err = ensure_stall_report()) return err;
+    const size_t wbytes = (size_t)tc::HDR_BYTES + 16 * 16384;
+    unsigned char *scratch = nullptr;
+    if (int err = pw_scratch(st, wbytes + (size_t)B * sizeof(float), &scratch)) return err;
     float *absmax = reinterpret_cast<float *>(scratch + wbytes);
     if (int err = tc_absmax(x, B, (size_t)256 * (size_t)P, absmax, st)) return err;
     tc::pw::pw_header_kernel<<<1, 256, 0, st>>>(w, 256 * 256, reinterpret_cast<float *>(scratch));

@@ -43,3 +43,24 @@ for name, args in (("forward relu+bias", (x, w, bias, True, None)), ("dgrad with
     for _ in range(5): ops.conv2d_forward(*args)
     e1.record(); torch.cuda.synchronize()
     print(f"{name}: {e0.elapsed_time(e1) / 5 * 1e3:.0f} us per call (EQB_TRAIN_TC={os.environ.get('EQB_TRAIN_TC', '1')})")
+
+# ---- weight gradient ---------------------------------------------------------------------------------------------------
+for (B, H, W) in ((2, 16, 16), (3, 20, 20), (2, 92, 92), (5, 4, 20)):
+    x = torch.randn(B, 256, H, W, device=dev) * torch.logspace(-1, 1, B, device=dev)[:, None, None, None]
+    dy = torch.randn(B, 256, H, W, device=dev) * torch.logspace(1, -1, B, device=dev)[:, None, None, None]
+    dw = ops.conv2d_weight_grad(dy, x, 1)
+    torch.cuda.synchronize()
+    r = torch.einsum("bnhw,bchw->nc", dy.double(), x.double())
+    err = ((dw[:, :, 0, 0].double() - r).abs().max() / r.abs().max()).item()
+    print(f"wgrad B={B} HxW={H}x{W}: max err / max|dw| = {err:.3e}", "OK" if err < 4e-6 else "FAIL")
+B, H, W = 64, 92, 92
+x = torch.randn(B, 256, H, W, device=dev)
+dy = torch.randn(B, 256, H, W, device=dev)
+for _ in range(2): ops.conv2d_weight_grad(dy, x, 1)
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(5): dw = ops.conv2d_weight_grad(dy, x, 1)
+e1.record(); torch.cuda.synchronize()
+r = torch.einsum("bnp,bcp->nc", dy.flatten(2).double(), x.flatten(2).double())
+print(f"wgrad 64x256x92x92: {e0.elapsed_time(e1) / 5 * 1e3:.0f} us per call, err {((dw[:, :, 0, 0].double() - r).abs().max() / r.abs().max()).item():.3e}")
