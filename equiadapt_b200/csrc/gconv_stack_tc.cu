@@ -1922,29 +1922,35 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(768, 1) gconv_stack_
 //   warp 0      (both CTAs) TMA: fp32 boxes [32 channels x 128 pixels] of x -> 3-stage staging ring (16 KB each)
 //   warps 4-11  (both CTAs) converters: thread = (pixel, channel half): 16 staged values -> scaled fp16 hi / lo -> the K-major
 //               64-byte-swizzled B-operand atom [128 pixels x 32 channels] of this CTA (2-stage ring)
-//   warp 1      (leader)    8 atoms x 6 MMAs (cta_group::2, M = 256 channels, N = 256 pixels) into D[tile & 1]
-//   warps 12-19 (both CTAs) epilogue: this CTA's 128 channels x 256 pixels of D -> scale, bias, ReLU, mask -> y (each thread
-//               one channel row, 128 contiguous bytes per 32-column chunk); max |y| per image for the next layer's scale
+//   warp 1      (leader)    8 atoms x 6 MMAs (cta_group::2, M = 256 pixels, N = 256 channels) into D[tile & 1]
+//   warps 12-19 (both CTAs) epilogue: this CTA's 128 pixels x 256 channels of D -> scale, bias, ReLU, mask -> y; lane = pixel,
+//               so every store and mask load of a warp is one 128-byte line (with channels on the lanes -- the stack
+//               kernel's orientation -- each lane wrote its own row: 446 / 827 us per call instead of 3xx, r3 notes)
 // TMEM holds two accumulators (2 x 256 columns): the epilogue of tile t runs under the MMAs of tile t + 1.
 // Bound: x read once + y written once (+ mask read): 1.1-1.7 GB per call at B = 64 against 213 GFLOP of MMAs: HBM.
 namespace pw {
 
 using namespace pair;
 
-constexpr int XS_RING = 3, A_RING = 2;
+// EVEN ring depths: the two converter groups take alternate atoms, so with an even ring a slot always belongs to the same
+// group and that group sees every phase of its barriers.  (With 3 stages a group skipped every other phase of a slot, and
+// a parity wait cannot tell "my atom has landed" from "the atom two phases earlier had": a timing-dependent launch failure.)
+constexpr int XS_RING = 4, A_RING = 2;
+static_assert(XS_RING % 2 == 0 && A_RING % 2 == 0, "ring slots must map to a fixed converter group");
 constexpr int XS_STAGE = 32 * 128 * 4;
 enum { B_XFULL = 0, B_XEMPTY = B_XFULL + XS_RING, B_AFULL = B_XEMPTY + XS_RING, B_AEMPTY = B_AFULL + A_RING,
        B_DFULL = B_AEMPTY + A_RING, B_DEMPTY = B_DFULL + 2, B_WLOAD = B_DEMPTY + 2, B_COUNT };
 
 struct Smem {
-    uint32_t w1, xs, a1, bars, tmem_slot, total;
+    uint32_t w1, xs, a1, bias, bars, tmem_slot, total;
 };
 __host__ __device__ inline Smem smem_map() {
     Smem s;
     uint32_t o = 0;
     s.w1 = o; o += 8 * W1_ATOM;              // 128 KB: this CTA's 128 rows of w, hi + lo, 8 K atoms
-    s.xs = o; o += XS_RING * XS_STAGE;       // 48 KB
+    s.xs = o; o += XS_RING * XS_STAGE;       // 64 KB
     s.a1 = o; o += A_RING * A1_STAGE;        // 32 KB
+    s.bias = o; o += 256 * 4;
     s.bars = o; o += B_COUNT * 8;
     s.tmem_slot = o; o += 16;
     s.total = o;
@@ -1956,9 +1962,10 @@ struct Args {
     const float *bias, *mask, *absmax_in;
     float *y, *absmax_out;
     int B, P, tiles, relu;        // tiles = pair-tiles (256 pixels) per image
+    int debug;                    // (development) 1: no stores, 2: no mask loads
 };
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(768, 1) pw_conv_kernel(const __grid_constant__ CUtensorMap xmap, const Args a) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(640, 1) pw_conv_kernel(const __grid_constant__ CUtensorMap xmap, const Args a) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const uint32_t base = smem_u32(smem_raw);
     unsigned char *sm = smem_raw;
@@ -1975,10 +1982,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(768, 1) pw_conv_kern
     if (threadIdx.x == 0) {
         for (int i = 0; i < XS_RING; ++i) {
             mbar_init(bar(B_XFULL + i), 1);
-            mbar_init(bar(B_XEMPTY + i), 256);     // this CTA's converter threads
+            mbar_init(bar(B_XEMPTY + i), 128);     // one converter group of this CTA
         }
         for (int i = 0; i < A_RING; ++i) {
-            mbar_init(bar(B_AFULL + i), 512);      // converter threads of both CTAs
+            mbar_init(bar(B_AFULL + i), 256);      // one converter group of each CTA
             mbar_init(bar(B_AEMPTY + i), 1);
         }
         for (int i = 0; i < 2; ++i) {
@@ -1994,6 +2001,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(768, 1) pw_conv_kern
             bulk_load(base + M.w1 + c * W1_ATOM + 8192u, src + gstage + rank * 8192u, 8192u, bar(B_WLOAD));
         }
     }
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) reinterpret_cast<float *>(sm + M.bias)[i] = a.bias ? __ldg(a.bias + i) : 0.f;
     if (warp == 2) {
         asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(base + M.tmem_slot), "r"(512)
                      : "memory");
@@ -2047,11 +2055,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(768, 1) pw_conv_kern
                         const uint32_t w_hi = w_lo0 + (uint32_t)kc * (W1_ATOM >> 4), w_lo = w_hi + (8192u >> 4);
                         const uint32_t dt = tmem + 256u * d;
 #pragma unroll
-                        for (int j = 0; j < 2; ++j) tc_mma2_f16_lo<DESC_HI_64B>(dt, w_hi + 2 * j, a_hi + 2 * j, idesc, j ? 1u : (uint32_t)(kc != 0));
+                        // D[pixel lanes][channel columns]: the pixel atoms are the M-side operand, this CTA's 128 rows of w
+                        // half of the N side -- so that the epilogue's lanes run along pixels (coalesced y and mask)
+                        for (int j = 0; j < 2; ++j) tc_mma2_f16_lo<DESC_HI_64B>(dt, a_hi + 2 * j, w_hi + 2 * j, idesc, j ? 1u : (uint32_t)(kc != 0));
 #pragma unroll
-                        for (int j = 0; j < 2; ++j) tc_mma2_f16_lo<DESC_HI_64B>(dt, w_hi + 2 * j, a_lo + 2 * j, idesc, 1);
+                        for (int j = 0; j < 2; ++j) tc_mma2_f16_lo<DESC_HI_64B>(dt, a_lo + 2 * j, w_hi + 2 * j, idesc, 1);
 #pragma unroll
-                        for (int j = 0; j < 2; ++j) tc_mma2_f16_lo<DESC_HI_64B>(dt, w_lo + 2 * j, a_hi + 2 * j, idesc, 1);
+                        for (int j = 0; j < 2; ++j) tc_mma2_f16_lo<DESC_HI_64B>(dt, a_hi + 2 * j, w_lo + 2 * j, idesc, 1);
                         tc_commit2(bar(B_AEMPTY + ra.stage));
                         if (kc == 7) tc_commit2(bar(B_DFULL + d));
                     }
@@ -2061,31 +2071,35 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(768, 1) pw_conv_kern
             }
         }
     } else if (warp >= 4 && warp < 12) {
-        // ===== converters: staged fp32 box -> this CTA's rows of the B-operand atom ==========================================
-        const int tc_ = (int)threadIdx.x - 128, px = tc_ & 127, h = tc_ >> 7;
+        // ===== converters: staged fp32 box -> this CTA's rows of the pixel-operand atom.  Two groups of 128 threads take
+        // alternate atoms (thread = pixel, all 32 channels of the atom): with all eight warps on the SAME atom the pipeline ran
+        // one atom per ~1 900 cycles -- the latency of one conversion (wait, 16 loads, split, wait, stores, proxy fence,
+        // remote arrive) -- whatever the depth of the rings ====================================================================
+        const int tc_ = (int)threadIdx.x - 128, px = tc_ & 127, grp = tc_ >> 7;
         const uint32_t row_off = (uint32_t)px * 64u, swz = (uint32_t)((px >> 1) & 3);
         const uint32_t afull0 = leader_bar(B_AFULL);
-        uint32_t seq = 0, aseq = 0;
-        for (int T = cid; T < total; T += ncl) {
+        uint32_t seq0 = 0;
+        for (int T = cid; T < total; T += ncl, seq0 += 8) {
             const int b = T / a.tiles;
             const float sx = pow2_scale(__ldg(a.absmax_in + b));
-            for (int kc = 0; kc < 8; ++kc, ++seq, ++aseq) {
+            for (int kc = grp; kc < 8; kc += 2) {
+                const uint32_t seq = seq0 + (uint32_t)kc;
                 const uint32_t s = seq % XS_RING, ph = (seq / XS_RING) & 1u;
                 mbar_wait(bar(B_XFULL + s), ph, 100 + B_XFULL + s);
-                const float *xs = reinterpret_cast<const float *>(sm + M.xs + s * XS_STAGE) + (16 * h) * 128 + px;
-                float v[16];
+                const float *xs = reinterpret_cast<const float *>(sm + M.xs + s * XS_STAGE) + px;
+                float v[32];
 #pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] = xs[i * 128];
+                for (int i = 0; i < 32; ++i) v[i] = xs[i * 128];
                 mbar_arrive(bar(B_XEMPTY + s));          // (release: the loads above are performed)
-                uint32_t hi[8], lo[8];
+                uint32_t hi[16], lo[16];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) split2(v[2 * i] * sx, v[2 * i + 1] * sx, hi[i], lo[i]);
-                const uint32_t sa = aseq % A_RING, pa = (aseq / A_RING) & 1u;
+                for (int i = 0; i < 16; ++i) split2(v[2 * i] * sx, v[2 * i + 1] * sx, hi[i], lo[i]);
+                const uint32_t sa = seq % A_RING, pa = (seq / A_RING) & 1u;
                 mbar_wait(bar(B_AEMPTY + sa), pa ^ 1u, 100 + B_AEMPTY + sa);
                 const uint32_t hi_row = base + M.a1 + sa * A1_STAGE + row_off, lo_row = hi_row + A1_HALF;
 #pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    const uint32_t col = ((uint32_t)(2 * h + j) ^ swz) << 4;
+                for (int j = 0; j < 4; ++j) {
+                    const uint32_t col = ((uint32_t)j ^ swz) << 4;
                     st_shared_v4(hi_row + col, hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
                     st_shared_v4(lo_row + col, lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
                 }
@@ -2094,10 +2108,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(768, 1) pw_conv_kern
             }
         }
     } else if (warp >= 12 && warp < 20) {
-        // ===== epilogue: D[tile & 1] -> y =====================================================================================
+        // ===== epilogue: D[tile & 1] -> y.  Lane = pixel (this CTA's 128 of the pair-tile), column = channel: every store
+        // and every mask load of a warp is one 128-byte line ================================================================
         const int q = warp & 3, g = (warp - 12) >> 2;
-        const int chan = 128 * (int)rank + 32 * q + lane;
-        const float bv = a.bias ? __ldg(a.bias + chan) : 0.f;
+        const int px = 128 * (int)rank + 32 * q + lane;
+        const float *bias_s = reinterpret_cast<const float *>(sm + M.bias) + 128 * g;
         const uint32_t dempty0 = leader_bar(B_DEMPTY);
         int n = 0, cur_b = -1;
         float m = 0.f;
@@ -2120,39 +2135,49 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(768, 1) pw_conv_kern
             mbar_wait(bar(B_DFULL + d), dph, 100 + B_DFULL + d);
             tc_fence_after();
             const uint32_t t0 = tmem + 256u * d + ((uint32_t)(q * 32) << 16) + (uint32_t)(128 * g);
-            const int p0 = t * 256 + 128 * g;
-            const size_t off = ((size_t)b * 256 + chan) * (size_t)a.P + p0;
-#pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-                const int nvalid = min(32, a.P - (p0 + 32 * c));       // (uniform; P % 4 == 0)
-                if (nvalid > 0) {
-                    uint32_t r[32];
-                    tc_ld32_issue(t0 + (uint32_t)(32 * c), r);
-                    tc_ld_wait(r);
-                    float *yp = a.y + off + 32 * c;
-                    const float *mp = a.mask ? a.mask + off + 32 * c : nullptr;
+            const int p = t * 256 + px;
+            const bool valid = p < a.P;
+            const size_t off = ((size_t)b * 256 + 128 * g) * (size_t)a.P + (valid ? p : 0);
+            float *yp = a.y + off;
+            const float *mp = a.mask ? a.mask + off : nullptr;
+            // sixteen channels at a time; the mask values of the NEXT piece are in flight while this one is finished
+            // (the loads of a warp are 128-byte lines, but a warp that waits for each batch of them keeps too few bytes
+            // in flight to cover its share of the HBM bandwidth)
+            const bool use_mask = mp && !(a.debug & 2);
+            float ka[16], kb[16];
+            auto load_mask = [&](float (&k)[16], int c) {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        if (4 * i < nvalid) {
-                            float4 o;
-                            o.x = fmaf(__uint_as_float(r[4 * i]), cs, bv);
-                            o.y = fmaf(__uint_as_float(r[4 * i + 1]), cs, bv);
-                            o.z = fmaf(__uint_as_float(r[4 * i + 2]), cs, bv);
-                            o.w = fmaf(__uint_as_float(r[4 * i + 3]), cs, bv);
-                            if (a.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-                            if (mp) {
-                                const float4 k4 = __ldg(reinterpret_cast<const float4 *>(mp) + i);
-                                o.x = k4.x > 0.f ? o.x : 0.f; o.y = k4.y > 0.f ? o.y : 0.f;
-                                o.z = k4.z > 0.f ? o.z : 0.f; o.w = k4.w > 0.f ? o.w : 0.f;
-                            }
-                            m = fmaxf(m, fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fmaxf(fabsf(o.z), fabsf(o.w))));
-                            reinterpret_cast<float4 *>(yp)[i] = o;
-                        }
+                for (int i = 0; i < 16; ++i) k[i] = (use_mask && valid) ? __ldg(mp + (size_t)(16 * c + i) * a.P) : 1.f;
+            };
+            auto finish = [&](const uint32_t (&r)[16], const float (&k)[16], int c) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    float v = fmaf(__uint_as_float(r[i]), cs, bias_s[16 * c + i]);
+                    if (a.relu) v = fmaxf(v, 0.f);
+                    v = k[i] > 0.f ? v : 0.f;
+                    if (valid) {
+                        m = fmaxf(m, fabsf(v));
+                        if (!(a.debug & 1)) yp[(size_t)(16 * c + i) * a.P] = v;
                     }
                 }
+            };
+            load_mask(ka, 0);
+#pragma unroll 1
+            for (int c = 0; c < 8; c += 2) {
+                uint32_t r[16];
+                tc_ld16_issue(t0 + (uint32_t)(16 * c), r);
+                load_mask(kb, c + 1);
+                tc_ld_wait16(r);
+                finish(r, ka, c);
+                tc_ld16_issue(t0 + (uint32_t)(16 * (c + 1)), r);
+                if (c + 2 < 8) load_mask(ka, c + 2);
+                tc_ld_wait16(r);
+                if (c + 2 == 8) {                  // D is in registers: the issuer may start the tile after next
+                    tc_fence_before();
+                    mbar_arrive_cluster(dempty0 + 8u * d);
+                }
+                finish(r, kb, c + 1);
             }
-            tc_fence_before();
-            mbar_arrive_cluster(dempty0 + 8u * d);
         }
         flush_max();
     }
@@ -2209,7 +2234,8 @@ namespace wg {
 
 using namespace pair;
 
-constexpr int XS_RING = 3, A_RING = 3;
+constexpr int XS_RING = 4, A_RING = 2;       // even: a slot always belongs to the same converter group (see pw)
+static_assert(XS_RING % 2 == 0 && A_RING % 2 == 0, "ring slots must map to a fixed converter group");
 constexpr int XS_STAGE = 2 * 128 * 128;      // dy box + x box, 128 rows x 32 floats each: 32 KB
 constexpr int AT_STAGE = 2 * A1_STAGE;       // A atom (dy rows) + B atom (x rows), hi + lo each: 32 KB
 enum { B_XFULL = 0, B_XEMPTY = B_XFULL + XS_RING, B_AFULL = B_XEMPTY + XS_RING, B_AEMPTY = B_AFULL + A_RING,
@@ -2221,8 +2247,8 @@ struct Smem {
 __host__ __device__ inline Smem smem_map() {
     Smem s;
     uint32_t o = 0;
-    s.xs = o; o += XS_RING * XS_STAGE;       // 96 KB
-    s.at = o; o += A_RING * AT_STAGE;        // 96 KB
+    s.xs = o; o += XS_RING * XS_STAGE;       // 128 KB
+    s.at = o; o += A_RING * AT_STAGE;        // 64 KB
     s.bars = o; o += B_COUNT * 8;
     s.tmem_slot = o; o += 16;
     s.red = o; o += 2 * 32 * 4;
@@ -2236,7 +2262,7 @@ struct Args {
     int B, P, api;                       // api = 32-pixel atoms per image
 };
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(768, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(640, 1)
     pw_wgrad_kernel(const __grid_constant__ CUtensorMap dymap, const __grid_constant__ CUtensorMap xmap, const Args a) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const uint32_t base = smem_u32(smem_raw);
@@ -2288,7 +2314,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(768, 1)
     float s_dy, s_x;
     {
         float m0 = 0.f, m1 = 0.f;
-        for (int w = 0; w < 24; ++w) { m0 = fmaxf(m0, red[w]); m1 = fmaxf(m1, red[32 + w]); }
+        for (int w = 0; w < 20; ++w) { m0 = fmaxf(m0, red[w]); m1 = fmaxf(m1, red[32 + w]); }
         s_dy = pow2_scale(m0);
         s_x = pow2_scale(m1);
     }
@@ -2341,15 +2367,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(768, 1)
                 ra.advance();
             }
         }
-    } else if (warp >= 4 && warp < 12) {
-        // ===== converters: thread = one row of one operand ===================================================================
-        const int tcv = (int)threadIdx.x - 128, r = tcv & 127, o = tcv >> 7;
+    } else if (warp >= 4 && warp < 20) {
+        // ===== converters: thread = one row of one operand; two groups of 256 threads take alternate atoms (one conversion
+        // is ~1 900 cycles of latency; see pw) =================================================================================
+        const int tcv = (int)threadIdx.x - 128, grp = tcv >> 8, r = tcv & 127, o = (tcv >> 7) & 1;
         const float sc = o ? s_x : s_dy;
         const uint32_t src_row = (uint32_t)o * (128u * 128u) + (uint32_t)r * 128u, sx7 = (uint32_t)(r & 7);
         const uint32_t dst_row = (uint32_t)o * A1_STAGE + (uint32_t)r * 64u, swz = (uint32_t)((r >> 1) & 3);
         const uint32_t afull0 = leader_bar(B_AFULL);
-        uint32_t seq = 0;
-        for (long long A = A0; A < A1; ++A, ++seq) {
+        for (long long A = A0 + grp; A < A1; A += 2) {
+            const uint32_t seq = (uint32_t)(A - A0);
             const uint32_t s = seq % XS_RING, ph = (seq / XS_RING) & 1u;
             mbar_wait(bar(B_XFULL + s), ph, 200 + B_XFULL + s);
             const unsigned char *box = sm + M.xs + s * XS_STAGE + src_row;
@@ -2375,10 +2402,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(768, 1)
             fence_async_smem();
             mbar_arrive_cluster(afull0 + 8u * sa);
         }
-    } else if (warp >= 12 && warp < 20) {
-        // ===== epilogue: this CTA's 128 rows of the partial -> dw ============================================================
-        if (A1 > A0) {
-            const int q = warp & 3, g = (warp - 12) >> 2;
+        // ===== epilogue (warps 4-11, after their last atom): this CTA's 128 rows of the partial -> dw =========================
+        if (warp < 12 && A1 > A0) {
+            const int q = warp & 3, g = (warp - 4) >> 2;
             const int n = 128 * (int)rank + 32 * q + lane;
             const float cs = 1.f / (s_dy * s_x);
             mbar_wait(bar(B_DFULL), 0, 200 + B_DFULL);
@@ -2612,7 +2638,8 @@ static int pw_scratch(cudaStream_t st, size_t need, unsigned char **out) {
 }
 
 // Weight gradient of a 1x1 layer with N = cin = 256 on the tensor pipe (tc::wg); dw must be zeroed by the caller.
-int tc_pw_wgrad(const float *dy, const float *x, float *dw, int B, int cin, long long P, int N, cudaStream_t st, int *handled) {
+int tc_pw_wgrad(const float *dy, const float *x, float *dw, int B, int cin, long long P, int N, const float *dy_absmax,
+                const float *x_absmax, cudaStream_t st, int *handled) {
     *handled = 0;
     const char *e = getenv("EQB_TRAIN_TC");
     if (e && e[0] == '0') return 0;
@@ -2623,8 +2650,10 @@ int tc_pw_wgrad(const float *dy, const float *x, float *dw, int B, int cin, long
     const size_t wbytes = (size_t)tc::HDR_BYTES + 16 * 16384;         // (the forward's region of the same buffer stays untouched)
     if (int err = pw_scratch(st, wbytes + 3 * (size_t)B * sizeof(float), &scratch)) return err;
     float *am_dy = reinterpret_cast<float *>(scratch + wbytes) + B, *am_x = am_dy + B;
-    if (int err = tc_absmax(dy, B, (size_t)256 * (size_t)P, am_dy, st)) return err;
-    if (int err = tc_absmax(x, B, (size_t)256 * (size_t)P, am_x, st)) return err;
+    if (dy_absmax) am_dy = const_cast<float *>(dy_absmax);
+    else if (int err = tc_absmax(dy, B, (size_t)256 * (size_t)P, am_dy, st)) return err;
+    if (x_absmax) am_x = const_cast<float *>(x_absmax);
+    else if (int err = tc_absmax(x, B, (size_t)256 * (size_t)P, am_x, st)) return err;
     CUtensorMap dymap, xmap;
     if (int err = make_plane_map(&dymap, dy, (int)P, B * 256, 1, 32, 128, CU_TENSOR_MAP_SWIZZLE_128B)) return err;
     if (int err = make_plane_map(&xmap, x, (int)P, B * 256, 1, 32, 128, CU_TENSOR_MAP_SWIZZLE_128B)) return err;
@@ -2637,7 +2666,7 @@ int tc_pw_wgrad(const float *dy, const float *x, float *dw, int B, int cin, long
     const long long total = (long long)B * a.api;
     const int max_clusters = num_sms() / 2;
     const int clusters = total < max_clusters ? (int)total : max_clusters;
-    tc::wg::pw_wgrad_kernel<<<2 * clusters, 768, M.total, st>>>(dymap, xmap, a);
+    tc::wg::pw_wgrad_kernel<<<2 * clusters, 640, M.total, st>>>(dymap, xmap, a);   // warps 0-2 + 16 converter warps
     *handled = 1;
     return finish_launch("pw_wgrad_kernel");
 }
@@ -2645,7 +2674,7 @@ int tc_pw_wgrad(const float *dy, const float *x, float *dw, int B, int cin, long
 // 1x1 convolution (N = cin = 256) of a whole NCHW feature map on the tensor pipe: see tc::pw.  *handled = 0 when the shape
 // or the alignment is outside what the kernel takes (the caller runs the fp32 SIMT kernel), or with EQB_TRAIN_TC=0.
 int tc_pw_conv(const float *x, const float *w, const float *bias, const float *mask, float *y, int B, int cin, long long P,
-               int N, int relu, cudaStream_t st, int *handled) {
+               int N, int relu, const float *x_absmax, float *y_absmax, cudaStream_t st, int *handled) {
     *handled = 0;
     const char *e = getenv("EQB_TRAIN_TC");
     if (e && e[0] == '0') return 0;
@@ -2656,14 +2685,17 @@ int tc_pw_conv(const float *x, const float *w, const float *bias, const float *m
     unsigned char *scratch = nullptr;
     if (int err = pw_scratch(st, wbytes + (size_t)B * sizeof(float), &scratch)) return err;
     float *absmax = reinterpret_cast<float *>(scratch + wbytes);
-    if (int err = tc_absmax(x, B, (size_t)256 * (size_t)P, absmax, st)) return err;
+    if (x_absmax) absmax = const_cast<float *>(x_absmax);       // the producer of x already knows its per-image maxima
+    else if (int err = tc_absmax(x, B, (size_t)256 * (size_t)P, absmax, st)) return err;
+    if (y_absmax) EQB_CUDA(cudaMemsetAsync(y_absmax, 0, (size_t)B * sizeof(float), st));
     tc::pw::pw_header_kernel<<<1, 256, 0, st>>>(w, 256 * 256, reinterpret_cast<float *>(scratch));
     tc::pw::pw_pack_kernel<<<64, 256, 0, st>>>(w, reinterpret_cast<const float *>(scratch), scratch + tc::HDR_BYTES);
     CUtensorMap map;
     if (int err = make_plane_map(&map, x, (int)P, B * 256, 1, 128, 32, CU_TENSOR_MAP_SWIZZLE_NONE)) return err;
     tc::pw::Args a{};
-    a.wpack = scratch; a.bias = bias; a.mask = mask; a.absmax_in = absmax; a.y = y; a.absmax_out = nullptr;
+    a.wpack = scratch; a.bias = bias; a.mask = mask; a.absmax_in = absmax; a.y = y; a.absmax_out = y_absmax;
     a.B = B; a.P = (int)P; a.tiles = (int)((P + 255) / 256); a.relu = relu;
+    a.debug = getenv("EQB_PW_DEBUG") ? atoi(getenv("EQB_PW_DEBUG")) : 0;
     const tc::pw::Smem M = tc::pw::smem_map();
     static PerDeviceOnce configured;
     if (configured.first())
@@ -2671,7 +2703,7 @@ int tc_pw_conv(const float *x, const float *w, const float *bias, const float *m
     const long long total = (long long)B * a.tiles;
     const int max_clusters = num_sms() / 2;
     const int clusters = total < max_clusters ? (int)total : max_clusters;
-    tc::pw::pw_conv_kernel<<<2 * clusters, 768, M.total, st>>>(map, a);
+    tc::pw::pw_conv_kernel<<<2 * clusters, 640, M.total, st>>>(map, a);   // warps 0-2 + 8 converters + 8 epilogue
     *handled = 1;
     return finish_launch("pw_conv_kernel");
 }

@@ -35,9 +35,10 @@ int tc_absmax(const float *x, int B, size_t n_per_image, float *absmax, cudaStre
 int tc_launch(TcArgs a, cudaStream_t st);
 // 1x1 convolution with N = cin = 256 on the tensor pipe (training path); *handled = 0: shape not taken, run the SIMT kernel
 int tc_pw_conv(const float *x, const float *w, const float *bias, const float *mask, float *y, int B, int cin, long long P,
-               int N, int relu, cudaStream_t st, int *handled);
+               int N, int relu, const float *x_absmax, float *y_absmax, cudaStream_t st, int *handled);   // maxima: (B) or null
 // ... and its weight gradient dw[n, c] = sum_{b, p} dy[b, n, p] x[b, c, p] (dw zeroed by the caller; split-K fp32 atomics)
-int tc_pw_wgrad(const float *dy, const float *x, float *dw, int B, int cin, long long P, int N, cudaStream_t st, int *handled);
+int tc_pw_wgrad(const float *dy, const float *x, float *dw, int B, int cin, long long P, int N, const float *dy_absmax,
+                const float *x_absmax, cudaStream_t st, int *handled);
 int tc_set_trace(long long *device_buffer, int tiles);   // next CTA-pair launches record a timeline (null: off)
 int tc_last_stall(int *out5);  // {flag, block, warp, barrier id, parity} of the first pipeline stall that trapped
 

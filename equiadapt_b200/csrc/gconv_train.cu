@@ -263,27 +263,38 @@ __global__ void regular_orbit_adjoint_kernel(const float *__restrict__ dorbit, f
 
 using namespace eqb;
 
-extern "C" int eqb_conv2d_forward(const float *x, const float *w, const float *bias, const float *mask, float *y, int B,
-                                  int cin, int H, int W, int N, int k, int relu, void *stream) {
+// x_absmax (in) / y_absmax (out): per-image max |.| (B floats each, may be NULL).  The tensor-core kernels scale their fp16
+// operand split per image; a caller that chains layers hands the maxima on instead of paying a pass over the feature map.
+extern "C" int eqb_conv2d_forward_scaled(const float *x, const float *w, const float *bias, const float *mask, float *y, int B,
+                                         int cin, int H, int W, int N, int k, int relu, const float *x_absmax, float *y_absmax,
+                                         void *stream) {
     EQB_NVTX_RANGE();
     EQB_REQUIRE(B >= 0 && cin > 0 && N > 0 && k > 0 && H >= k && W >= k, "eqb_conv2d_forward: bad shape");
     EQB_REQUIRE(B == 0 || (x && w && y), "eqb_conv2d_forward: null pointer");
     EQB_REQUIRE(B <= 65535 && (N + GT_T - 1) / GT_T <= 65535, "eqb_conv2d_forward: grid too large");
     if (B == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
     const int P = (H - k + 1) * (W - k + 1);
     if (k == 1) {
         // 256 -> 256 channels: CTA-pair tcgen05 kernel with the fp16 hi/lo operand split (gconv_stack_tc.cu, namespace pw)
         int handled = 0;
-        if (int err = tc_pw_conv(x, w, bias, mask, y, B, cin, (long long)P, N, relu, (cudaStream_t)stream, &handled)) return err;
+        if (int err = tc_pw_conv(x, w, bias, mask, y, B, cin, (long long)P, N, relu, x_absmax, y_absmax, st, &handled)) return err;
         if (handled) return 0;
     }
     dim3 grid((P + GT_T - 1) / GT_T, (N + GT_T - 1) / GT_T, B);
-    conv2d_forward_kernel<<<grid, GT_THREADS, 0, (cudaStream_t)stream>>>(x, w, bias, mask, y, cin, H, W, k, N, relu);
-    return finish_launch("eqb_conv2d_forward");
+    conv2d_forward_kernel<<<grid, GT_THREADS, 0, st>>>(x, w, bias, mask, y, cin, H, W, k, N, relu);
+    if (int err = finish_launch("eqb_conv2d_forward")) return err;
+    if (y_absmax) return tc_absmax(y, B, (size_t)N * (size_t)P, y_absmax, st);
+    return 0;
 }
 
-extern "C" int eqb_conv2d_weight_grad(const float *dy, const float *x, float *dw, int B, int cin, int H, int W, int N, int k,
-                                      void *stream) {
+extern "C" int eqb_conv2d_forward(const float *x, const float *w, const float *bias, const float *mask, float *y, int B,
+                                  int cin, int H, int W, int N, int k, int relu, void *stream) {
+    return eqb_conv2d_forward_scaled(x, w, bias, mask, y, B, cin, H, W, N, k, relu, nullptr, nullptr, stream);
+}
+
+extern "C" int eqb_conv2d_weight_grad_scaled(const float *dy, const float *x, float *dw, int B, int cin, int H, int W, int N,
+                                             int k, const float *dy_absmax, const float *x_absmax, void *stream) {
     EQB_NVTX_RANGE();
     EQB_REQUIRE(B >= 0 && cin > 0 && N > 0 && k > 0 && H >= k && W >= k, "eqb_conv2d_weight_grad: bad shape");
     EQB_REQUIRE(dw && (B == 0 || (dy && x)), "eqb_conv2d_weight_grad: null pointer");
@@ -293,7 +304,7 @@ extern "C" int eqb_conv2d_weight_grad(const float *dy, const float *x, float *dw
     if (B == 0) return 0;
     if (k == 1) {
         int handled = 0;
-        if (int err = tc_pw_wgrad(dy, x, dw, B, cin, (long long)P, N, st, &handled)) return err;
+        if (int err = tc_pw_wgrad(dy, x, dw, B, cin, (long long)P, N, dy_absmax, x_absmax, st, &handled)) return err;
         if (handled) return 0;
     }
     const int tiles = ((K + GT_T - 1) / GT_T) * ((N + GT_T - 1) / GT_T);
@@ -306,6 +317,11 @@ extern "C" int eqb_conv2d_weight_grad(const float *dy, const float *x, float *dw
     dim3 grid((K + GT_T - 1) / GT_T, (N + GT_T - 1) / GT_T, (unsigned)splits);
     conv2d_weight_grad_kernel<<<grid, GT_THREADS, 0, st>>>(dy, x, dw, B, cin, H, W, k, N, (int)per);
     return finish_launch("eqb_conv2d_weight_grad");
+}
+
+extern "C" int eqb_conv2d_weight_grad(const float *dy, const float *x, float *dw, int B, int cin, int H, int W, int N, int k,
+                                      void *stream) {
+    return eqb_conv2d_weight_grad_scaled(dy, x, dw, B, cin, H, W, N, k, nullptr, nullptr, stream);
 }
 
 extern "C" int eqb_plane_sums(const float *x, int64_t rows, int64_t P, float *out, void *stream) {

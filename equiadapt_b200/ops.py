@@ -116,10 +116,24 @@ def regular_filter_orbit(w: torch.Tensor, num_rotations: int, reflect: bool) -> 
 
 
 # ---- N3: training kernels of the group-conv network -------------------------------------------------
+def _known_amax(t: torch.Tensor) -> Optional[torch.Tensor]:
+    """Per-sample max |t| recorded by the op that produced `t` (valid only while `t` has not been written in place since)."""
+    rec = getattr(t, "_eqb_amax", None)
+    if rec is not None and rec[1] == t._version and rec[0].device == t.device:
+        return rec[0]
+    return None
+
+
+def _record_amax(t: torch.Tensor, amax: torch.Tensor) -> None:
+    t._eqb_amax = (amax, t._version)
+
+
 def conv2d_forward(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], relu: bool,
                    mask: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """[relu](conv2d(x, w) + bias), valid k x k, optionally zeroed where mask <= 0."""
+    """[relu](conv2d(x, w) + bias), valid k x k, optionally zeroed where mask <= 0.  The result carries its per-sample max |y|
+    (the 1x1 tensor-core layers scale their operands per sample; chained calls hand the maxima on, eqb_conv2d_forward_scaled)."""
     dev = _need_cuda(x, w)
+    x_amax = _known_amax(x)
     x, w = _f32(x), _f32(w)
     b, cin, h, wd = x.shape
     n, cin2, k, k2 = w.shape
@@ -130,20 +144,25 @@ def conv2d_forward(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor
     y = torch.empty((b, n, h - k + 1, wd - k + 1), dtype=torch.float32, device=dev)
     if mask is not None and mask.shape != y.shape:
         raise ValueError("mask must have the output's shape")
-    _call("eqb_conv2d_forward", 1 if b else 0, dev, _ptr(x), _ptr(w), _ptr(bias) if bias is not None else None,
-          _ptr(mask) if mask is not None else None, _ptr(y), b, cin, h, wd, n, k, int(relu), _stream(dev))
+    y_amax = torch.empty((b,), dtype=torch.float32, device=dev)
+    _call("eqb_conv2d_forward_scaled", 1 if b else 0, dev, _ptr(x), _ptr(w), _ptr(bias) if bias is not None else None,
+          _ptr(mask) if mask is not None else None, _ptr(y), b, cin, h, wd, n, k, int(relu),
+          _ptr(x_amax) if x_amax is not None else None, _ptr(y_amax), _stream(dev))
+    _record_amax(y, y_amax)
     return y
 
 
 def conv2d_weight_grad(dy: torch.Tensor, x: torch.Tensor, k: int) -> torch.Tensor:
     dev = _need_cuda(dy, x)
+    dy_amax, x_amax = _known_amax(dy), _known_amax(x)
     dy, x = _f32(dy), _f32(x)
     b, cin, h, wd = x.shape
     n = dy.shape[1]
     if tuple(dy.shape) != (b, n, h - k + 1, wd - k + 1):
         raise ValueError("dy does not match a valid k x k convolution of x")
     dw = torch.empty((n, cin, k, k), dtype=torch.float32, device=dev)
-    _call("eqb_conv2d_weight_grad", 1 if b else 0, dev, _ptr(dy), _ptr(x), _ptr(dw), b, cin, h, wd, n, k, _stream(dev))
+    _call("eqb_conv2d_weight_grad_scaled", 1 if b else 0, dev, _ptr(dy), _ptr(x), _ptr(dw), b, cin, h, wd, n, k,
+          _ptr(dy_amax) if dy_amax is not None else None, _ptr(x_amax) if x_amax is not None else None, _stream(dev))
     return dw
 
 
@@ -163,6 +182,8 @@ def group_mean_backward(dact: torch.Tensor, cout: int, out_hw: Tuple[int, int]) 
     b, g = dact.shape
     dy = torch.empty((b, cout * g, out_hw[0], out_hw[1]), dtype=torch.float32, device=dev)
     _call("eqb_group_mean_backward", 1 if b else 0, dev, _ptr(dact), _ptr(dy), b, cout, g, out_hw[0] * out_hw[1], _stream(dev))
+    # dy[b, o*|G|+g, p] = dact[b, g] / (cout * P): its per-sample maximum costs nothing to state
+    _record_amax(dy, (dact.abs().amax(dim=1) / float(cout * out_hw[0] * out_hw[1])).contiguous())
     return dy
 
 
@@ -207,6 +228,7 @@ class _GConvStackTrain(torch.autograd.Function):
         sums = plane_sums(h)                                                               # (B, cout*|G|)
         act = sums.reshape(-1, cout, g).sum(1) / float(cout * h.shape[-2] * h.shape[-1])
         ctx.cfg = (num_rotations, reflect, cout, tuple(h.shape[-2:]), [b is not None for _, b in layers])
+        ctx.amax = [_known_amax(f) for f in feats]      # (python attributes do not survive save_for_backward)
         ctx.save_for_backward(*feats, *filters)
         return act
 
@@ -220,6 +242,8 @@ class _GConvStackTrain(torch.autograd.Function):
         grads = [None] * (2 * nl)
         for li in range(nl - 1, -1, -1):
             xin, wx = feats[li], filters[li]
+            if ctx.amax[li] is not None:
+                _record_amax(xin, ctx.amax[li])
             k = wx.shape[-1]
             if has_bias[li] and ctx.needs_input_grad[3 + 2 * li + 1]:
                 grads[2 * li + 1] = plane_sums(dy).sum(0).reshape(cout, g).sum(1)
