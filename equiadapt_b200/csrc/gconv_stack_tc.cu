@@ -1919,9 +1919,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(768, 1) gconv_stack_
 // (custom_group_equivariant_layers.py:298-334 after the filter orbit; eqb_conv2d_forward's contract).
 // Same numerics as the stack kernel: fp16 hi/lo split of both operands (3 MMAs per product, ~22-bit significands),
 // power-of-two operand scales (per IMAGE for x), fp32 accumulation in TMEM.
-//   warp 0      (both CTAs) TMA: fp32 boxes [32 channels x 128 pixels] of x -> 3-stage staging ring (16 KB each)
-//   warps 4-11  (both CTAs) converters: thread = (pixel, channel half): 16 staged values -> scaled fp16 hi / lo -> the K-major
-//               64-byte-swizzled B-operand atom [128 pixels x 32 channels] of this CTA (2-stage ring)
+//   warps 4-11  (both CTAs) converters: thread = pixel, two groups on alternate atoms: 32 channel values from global memory
+//               (coalesced per channel) -> scaled fp16 hi / lo -> the K-major 64-byte-swizzled operand atom [128 pixels x 32
+//               channels] of this CTA (4-stage ring)
 //   warp 1      (leader)    8 atoms x 6 MMAs (cta_group::2, M = 256 pixels, N = 256 channels) into D[tile & 1]
 //   warps 12-19 (both CTAs) epilogue: this CTA's 128 pixels x 256 channels of D -> scale, bias, ReLU, mask -> y; lane = pixel,
 //               so every store and mask load of a warp is one 128-byte line (with channels on the lanes -- the stack
@@ -1932,25 +1932,24 @@ namespace pw {
 
 using namespace pair;
 
-// EVEN ring depths: the two converter groups take alternate atoms, so with an even ring a slot always belongs to the same
+// EVEN ring depth: the two converter groups take alternate atoms, so with an even ring a slot always belongs to the same
 // group and that group sees every phase of its barriers.  (With 3 stages a group skipped every other phase of a slot, and
-// a parity wait cannot tell "my atom has landed" from "the atom two phases earlier had": a timing-dependent launch failure.)
-constexpr int XS_RING = 4, A_RING = 2;
-static_assert(XS_RING % 2 == 0 && A_RING % 2 == 0, "ring slots must map to a fixed converter group");
-constexpr int XS_STAGE = 32 * 128 * 4;
-enum { B_XFULL = 0, B_XEMPTY = B_XFULL + XS_RING, B_AFULL = B_XEMPTY + XS_RING, B_AEMPTY = B_AFULL + A_RING,
-       B_DFULL = B_AEMPTY + A_RING, B_DEMPTY = B_DFULL + 2, B_WLOAD = B_DEMPTY + 2, B_COUNT };
+// a parity wait cannot tell "my slot was released" from "it had been released two phases earlier": a timing-dependent
+// launch failure.)
+constexpr int A_RING = 4;
+static_assert(A_RING % 2 == 0, "ring slots must map to a fixed converter group");
+enum { B_AFULL = 0, B_AEMPTY = B_AFULL + A_RING, B_DFULL = B_AEMPTY + A_RING, B_DEMPTY = B_DFULL + 2, B_WLOAD = B_DEMPTY + 2, B_COUNT };
 
 struct Smem {
-    uint32_t w1, xs, a1, bias, bars, tmem_slot, total;
+    uint32_t w1, a1, bias, koff, bars, tmem_slot, total;
 };
 __host__ __device__ inline Smem smem_map() {
     Smem s;
     uint32_t o = 0;
     s.w1 = o; o += 8 * W1_ATOM;              // 128 KB: this CTA's 128 rows of w, hi + lo, 8 K atoms
-    s.xs = o; o += XS_RING * XS_STAGE;       // 64 KB
-    s.a1 = o; o += A_RING * A1_STAGE;        // 32 KB
+    s.a1 = o; o += A_RING * A1_STAGE;        // 64 KB
     s.bias = o; o += 256 * 4;
+    s.koff = o; o += 256 * 4;                // element offset of reduction index k inside an image (-1: padding)
     s.bars = o; o += B_COUNT * 8;
     s.tmem_slot = o; o += 16;
     s.total = o;
@@ -1959,13 +1958,14 @@ __host__ __device__ inline Smem smem_map() {
 
 struct Args {
     const unsigned char *wpack;   // header {sw} + 8 atoms x (hi stage, lo stage) of 256 rows x 64 bytes (pw_pack_kernel)
-    const float *bias, *mask, *absmax_in;
+    const float *x, *bias, *mask, *absmax_in;
     float *y, *absmax_out;
-    int B, P, tiles, relu;        // tiles = pair-tiles (256 pixels) per image
+    int B, P, tiles, relu;        // P = output pixels per image, tiles = pair-tiles (256 pixels) per image
+    int cin, H, W, Wo, ksz, K, natoms;   // valid ksz x ksz convolution: K = cin * ksz^2 <= 256, natoms = ceil(K / 32)
     int debug;                    // (development) 1: no stores, 2: no mask loads
 };
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(640, 1) pw_conv_kernel(const __grid_constant__ CUtensorMap xmap, const Args a) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(640, 1) pw_conv_kernel(const Args a) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const uint32_t base = smem_u32(smem_raw);
     unsigned char *sm = smem_raw;
@@ -1980,10 +1980,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(640, 1) pw_conv_kern
     const uint32_t gstage = 256u * 64u;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < XS_RING; ++i) {
-            mbar_init(bar(B_XFULL + i), 1);
-            mbar_init(bar(B_XEMPTY + i), 128);     // one converter group of this CTA
-        }
         for (int i = 0; i < A_RING; ++i) {
             mbar_init(bar(B_AFULL + i), 256);      // one converter group of each CTA
             mbar_init(bar(B_AEMPTY + i), 1);
@@ -1994,14 +1990,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(640, 1) pw_conv_kern
         }
         mbar_init(bar(B_WLOAD), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        mbar_expect_tx(bar(B_WLOAD), 8u * W1_ATOM);
-        for (int c = 0; c < 8; ++c) {
+        mbar_expect_tx(bar(B_WLOAD), (uint32_t)a.natoms * W1_ATOM);
+        for (int c = 0; c < a.natoms; ++c) {
             const unsigned char *src = img + (size_t)(2 * c) * gstage;
             bulk_load(base + M.w1 + c * W1_ATOM, src + rank * 8192u, 8192u, bar(B_WLOAD));
             bulk_load(base + M.w1 + c * W1_ATOM + 8192u, src + gstage + rank * 8192u, 8192u, bar(B_WLOAD));
         }
     }
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) reinterpret_cast<float *>(sm + M.bias)[i] = a.bias ? __ldg(a.bias + i) : 0.f;
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+        reinterpret_cast<float *>(sm + M.bias)[i] = a.bias ? __ldg(a.bias + i) : 0.f;
+        int off = -1;
+        if (i < a.K) {
+            const int kk2 = a.ksz * a.ksz, c = i / kk2, rem = i - c * kk2, ky = rem / a.ksz, kx = rem - ky * a.ksz;
+            off = (c * a.H + ky) * a.W + kx;
+        }
+        reinterpret_cast<int *>(sm + M.koff)[i] = off;
+    }
     if (warp == 2) {
         asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(base + M.tmem_slot), "r"(512)
                      : "memory");
@@ -2019,26 +2023,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(640, 1) pw_conv_kern
     const int total = a.B * a.tiles;
     const uint32_t idesc = (1u << 4) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
 
-    if (warp == 0) {
-        // ===== TMA producer: 8 boxes per tile ================================================================================
-        if (lane == 0) {
-            uint32_t seq = 0;
-            for (int T = cid; T < total; T += ncl) {
-                const int b = T / a.tiles, t = T - b * a.tiles;
-                for (int kc = 0; kc < 8; ++kc, ++seq) {
-                    const uint32_t s = seq % XS_RING, ph = (seq / XS_RING) & 1u;
-                    mbar_wait(bar(B_XEMPTY + s), ph ^ 1u, 100 + B_XEMPTY + s);
-                    mbar_expect_tx(bar(B_XFULL + s), (uint32_t)XS_STAGE);
-                    // pixels past the end of the plane are zero-filled by the TMA unit
-                    asm volatile(
-                        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-                        ::"r"(base + M.xs + s * XS_STAGE), "l"((uint64_t)&xmap), "r"(bar(B_XFULL + s)),
-                          "r"(t * 256 + 128 * (int)rank), "r"(b * 256 + 32 * kc), "r"(0)
-                        : "memory");
-                }
-            }
-        }
-    } else if (warp == 1) {
+    if (warp == 1) {
         if (rank == 0) {
             // ===== MMA issuer =================================================================================================
             Ring<A_RING> ra;
@@ -2047,7 +2032,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(640, 1) pw_conv_kern
             for (int T = cid; T < total; T += ncl, ++n) {
                 const uint32_t d = (uint32_t)n & 1u, dph = ((uint32_t)n >> 1) & 1u;
                 mbar_wait_cluster(bar(B_DEMPTY + d), dph ^ 1u, 100 + B_DEMPTY + d);
-                for (int kc = 0; kc < 8; ++kc) {
+                for (int kc = 0; kc < a.natoms; ++kc) {
                     mbar_wait_cluster(bar(B_AFULL + ra.stage), ra.phase, 100 + B_AFULL + ra.stage);
                     tc_fence_after();
                     if (elect_one()) {
@@ -2063,7 +2048,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(640, 1) pw_conv_kern
 #pragma unroll
                         for (int j = 0; j < 2; ++j) tc_mma2_f16_lo<DESC_HI_64B>(dt, a_hi + 2 * j, w_lo + 2 * j, idesc, 1);
                         tc_commit2(bar(B_AEMPTY + ra.stage));
-                        if (kc == 7) tc_commit2(bar(B_DFULL + d));
+                        if (kc == a.natoms - 1) tc_commit2(bar(B_DFULL + d));
                     }
                     __syncwarp();
                     ra.advance();
@@ -2071,26 +2056,32 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(640, 1) pw_conv_kern
             }
         }
     } else if (warp >= 4 && warp < 12) {
-        // ===== converters: staged fp32 box -> this CTA's rows of the pixel-operand atom.  Two groups of 128 threads take
-        // alternate atoms (thread = pixel, all 32 channels of the atom): with all eight warps on the SAME atom the pipeline ran
-        // one atom per ~1 900 cycles -- the latency of one conversion (wait, 16 loads, split, wait, stores, proxy fence,
-        // remote arrive) -- whatever the depth of the rings ====================================================================
+        // ===== converters: x -> this CTA's rows of the pixel-operand atom.  Thread = pixel; two groups of 128 threads take
+        // alternate atoms.  The 32 channel values of an atom come straight from global memory (for a fixed channel a warp reads
+        // one 128-byte line; 4 KB in flight per warp): staging the same boxes through TMA ran at one 16 KB box per ~2 000
+        // cycles per CTA whatever the ring depth (2.1 TB/s over the GPU, r3 notes) =============================================
         const int tc_ = (int)threadIdx.x - 128, px = tc_ & 127, grp = tc_ >> 7;
         const uint32_t row_off = (uint32_t)px * 64u, swz = (uint32_t)((px >> 1) & 3);
         const uint32_t afull0 = leader_bar(B_AFULL);
+        const int *koff = reinterpret_cast<const int *>(sm + M.koff);
         uint32_t seq0 = 0;
-        for (int T = cid; T < total; T += ncl, seq0 += 8) {
-            const int b = T / a.tiles;
+        for (int T = cid; T < total; T += ncl, seq0 += (uint32_t)a.natoms) {
+            const int b = T / a.tiles, t = T - b * a.tiles;
             const float sx = pow2_scale(__ldg(a.absmax_in + b));
-            for (int kc = grp; kc < 8; kc += 2) {
+            const int p = t * 256 + 128 * (int)rank + px;
+            const bool valid = p < a.P;
+            const int oy = valid ? p / a.Wo : 0, ox = valid ? p - oy * a.Wo : 0;
+            const float *xp = a.x + (size_t)b * a.cin * a.H * a.W + (size_t)oy * a.W + ox;
+            for (int kc = 0; kc < a.natoms; ++kc) {
                 const uint32_t seq = seq0 + (uint32_t)kc;
-                const uint32_t s = seq % XS_RING, ph = (seq / XS_RING) & 1u;
-                mbar_wait(bar(B_XFULL + s), ph, 100 + B_XFULL + s);
-                const float *xs = reinterpret_cast<const float *>(sm + M.xs + s * XS_STAGE) + px;
+                if ((int)(seq & 1u) != grp) continue;      // a ring slot (seq % A_RING, A_RING even) always belongs to one group
+                const int *ko = koff + 32 * kc;
                 float v[32];
 #pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] = xs[i * 128];
-                mbar_arrive(bar(B_XEMPTY + s));          // (release: the loads above are performed)
+                for (int i = 0; i < 32; ++i) {
+                    const int off = ko[i];
+                    v[i] = (valid && off >= 0) ? __ldg(xp + off) : 0.f;
+                }
                 uint32_t hi[16], lo[16];
 #pragma unroll
                 for (int i = 0; i < 16; ++i) split2(v[2 * i] * sx, v[2 * i + 1] * sx, hi[i], lo[i]);
@@ -2204,13 +2195,16 @@ __global__ void __launch_bounds__(256) pw_header_kernel(const float *__restrict_
     }
     if (threadIdx.x == 0) hdr[0] = pow2_scale(red[0]);
 }
-// w[n][k] (256 x 256) -> UMMA images, the layout pack_tc_weights_kernel gives the 1x1 layer of the stack
-__global__ void pw_pack_kernel(const float *__restrict__ w, const float *__restrict__ hdr, unsigned char *__restrict__ out) {
+// w[n][k] (256 x K, K <= 256) -> UMMA images of ceil(K / 32) atoms (zero beyond K), the layout pack_tc_weights_kernel gives
+// the 1x1 layer of the stack
+__global__ void pw_pack_kernel(const float *__restrict__ w, int K, int natoms, const float *__restrict__ hdr,
+                               unsigned char *__restrict__ out) {
     const float sw = hdr[0];
-    const int total = 8 * 256 * ATOM_K;
+    const int total = natoms * 256 * ATOM_K;
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
         const int ks = t % ATOM_K, n = (t / ATOM_K) % 256, atom = t / (ATOM_K * 256);
-        const float v = w[(size_t)n * 256 + atom * ATOM_K + ks] * sw;
+        const int k = atom * ATOM_K + ks;
+        const float v = k < K ? w[(size_t)n * K + k] * sw : 0.f;
         const __half hi = __float2half_rn(v), lo = __float2half_rn(v - __half2float(hi));
         const size_t stage = (size_t)256 * 64;
         const size_t off = (size_t)n * 64 + (size_t)((((ks >> 3) ^ ((n >> 1) & 3)) << 4) | ((ks & 7) << 1));
@@ -2671,30 +2665,31 @@ int tc_pw_wgrad(const float *dy, const float *x, float *dw, int B, int cin, long
     return finish_launch("pw_wgrad_kernel");
 }
 
-// 1x1 convolution (N = cin = 256) of a whole NCHW feature map on the tensor pipe: see tc::pw.  *handled = 0 when the shape
-// or the alignment is outside what the kernel takes (the caller runs the fp32 SIMT kernel), or with EQB_TRAIN_TC=0.
-int tc_pw_conv(const float *x, const float *w, const float *bias, const float *mask, float *y, int B, int cin, long long P,
-               int N, int relu, const float *x_absmax, float *y_absmax, cudaStream_t st, int *handled) {
+// Valid k x k convolution with N = 256 output channels and cin * k * k <= 256 of a whole NCHW batch on the tensor pipe (the
+// 1x1 layers AND the 5x5 lift of the training path): see tc::pw.  *handled = 0 when the shape is outside what the kernel
+// takes (the caller runs the fp32 SIMT kernel), or with EQB_TRAIN_TC=0.
+int tc_pw_conv(const float *x, const float *w, const float *bias, const float *mask, float *y, int B, int cin, int H, int W,
+               int N, int k, int relu, const float *x_absmax, float *y_absmax, cudaStream_t st, int *handled) {
     *handled = 0;
     const char *e = getenv("EQB_TRAIN_TC");
     if (e && e[0] == '0') return 0;
-    if (cin != 256 || N != 256 || P <= 0 || (P & 3) != 0 || P >= (1LL << 30) || B <= 0 || (long long)B * 256 >= (1LL << 31)) return 0;
-    if ((((uintptr_t)x | (uintptr_t)y | (uintptr_t)mask) & 15) != 0) return 0;
+    const long long K = (long long)cin * k * k, P = (long long)(H - k + 1) * (W - k + 1);
+    if (N != 256 || K > 256 || P <= 0 || P >= (1LL << 30) || B <= 0 || (long long)cin * H * W >= (1LL << 31)) return 0;
     if (int err = ensure_stall_report()) return err;
     const size_t wbytes = (size_t)tc::HDR_BYTES + 16 * 16384;
     unsigned char *scratch = nullptr;
     if (int err = pw_scratch(st, wbytes + (size_t)B * sizeof(float), &scratch)) return err;
     float *absmax = reinterpret_cast<float *>(scratch + wbytes);
     if (x_absmax) absmax = const_cast<float *>(x_absmax);       // the producer of x already knows its per-image maxima
-    else if (int err = tc_absmax(x, B, (size_t)256 * (size_t)P, absmax, st)) return err;
+    else if (int err = tc_absmax(x, B, (size_t)cin * H * W, absmax, st)) return err;
     if (y_absmax) EQB_CUDA(cudaMemsetAsync(y_absmax, 0, (size_t)B * sizeof(float), st));
-    tc::pw::pw_header_kernel<<<1, 256, 0, st>>>(w, 256 * 256, reinterpret_cast<float *>(scratch));
-    tc::pw::pw_pack_kernel<<<64, 256, 0, st>>>(w, reinterpret_cast<const float *>(scratch), scratch + tc::HDR_BYTES);
-    CUtensorMap map;
-    if (int err = make_plane_map(&map, x, (int)P, B * 256, 1, 128, 32, CU_TENSOR_MAP_SWIZZLE_NONE)) return err;
+    const int natoms = (int)((K + 31) / 32);
+    tc::pw::pw_header_kernel<<<1, 256, 0, st>>>(w, (int)(256 * K), reinterpret_cast<float *>(scratch));
+    tc::pw::pw_pack_kernel<<<64, 256, 0, st>>>(w, (int)K, natoms, reinterpret_cast<const float *>(scratch), scratch + tc::HDR_BYTES);
     tc::pw::Args a{};
-    a.wpack = scratch; a.bias = bias; a.mask = mask; a.absmax_in = absmax; a.y = y; a.absmax_out = y_absmax;
+    a.x = x; a.wpack = scratch; a.bias = bias; a.mask = mask; a.absmax_in = absmax; a.y = y; a.absmax_out = y_absmax;
     a.B = B; a.P = (int)P; a.tiles = (int)((P + 255) / 256); a.relu = relu;
+    a.cin = cin; a.H = H; a.W = W; a.Wo = W - k + 1; a.ksz = k; a.K = (int)K; a.natoms = natoms;
     a.debug = getenv("EQB_PW_DEBUG") ? atoi(getenv("EQB_PW_DEBUG")) : 0;
     const tc::pw::Smem M = tc::pw::smem_map();
     static PerDeviceOnce configured;
@@ -2703,7 +2698,7 @@ int tc_pw_conv(const float *x, const float *w, const float *bias, const float *m
     const long long total = (long long)B * a.tiles;
     const int max_clusters = num_sms() / 2;
     const int clusters = total < max_clusters ? (int)total : max_clusters;
-    tc::pw::pw_conv_kernel<<<2 * clusters, 640, M.total, st>>>(map, a);   // warps 0-2 + 8 converters + 8 epilogue
+    tc::pw::pw_conv_kernel<<<2 * clusters, 640, M.total, st>>>(a);   // warps 0-2 + 8 converters + 8 epilogue
     *handled = 1;
     return finish_launch("pw_conv_kernel");
 }

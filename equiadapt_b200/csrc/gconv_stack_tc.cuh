@@ -33,9 +33,10 @@ int tc_pack(const float *Wt0, int K0, const float *Wt1, const float *bias1, int 
             cudaStream_t st);
 int tc_absmax(const float *x, int B, size_t n_per_image, float *absmax, cudaStream_t st);   // absmax[b] = max |x[b]|
 int tc_launch(TcArgs a, cudaStream_t st);
-// 1x1 convolution with N = cin = 256 on the tensor pipe (training path); *handled = 0: shape not taken, run the SIMT kernel
-int tc_pw_conv(const float *x, const float *w, const float *bias, const float *mask, float *y, int B, int cin, long long P,
-               int N, int relu, const float *x_absmax, float *y_absmax, cudaStream_t st, int *handled);   // maxima: (B) or null
+// valid k x k convolution with N = 256 and cin * k * k <= 256 on the tensor pipe (training path); *handled = 0: shape not
+// taken, run the SIMT kernel.  x_absmax / y_absmax: per-image maxima, (B) floats or null
+int tc_pw_conv(const float *x, const float *w, const float *bias, const float *mask, float *y, int B, int cin, int H, int W,
+               int N, int k, int relu, const float *x_absmax, float *y_absmax, cudaStream_t st, int *handled);
 // ... and its weight gradient dw[n, c] = sum_{b, p} dy[b, n, p] x[b, c, p] (dw zeroed by the caller; split-K fp32 atomics)
 int tc_pw_wgrad(const float *dy, const float *x, float *dw, int B, int cin, long long P, int N, const float *dy_absmax,
                 const float *x_absmax, cudaStream_t st, int *handled);

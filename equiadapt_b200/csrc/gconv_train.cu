@@ -275,10 +275,11 @@ extern "C" int eqb_conv2d_forward_scaled(const float *x, const float *w, const f
     if (B == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     const int P = (H - k + 1) * (W - k + 1);
-    if (k == 1) {
-        // 256 -> 256 channels: CTA-pair tcgen05 kernel with the fp16 hi/lo operand split (gconv_stack_tc.cu, namespace pw)
+    {
+        // 256 output channels, cin * k * k <= 256 (the lift and the 1x1 layers of the flagship network): CTA-pair tcgen05
+        // kernel with the fp16 hi/lo operand split (gconv_stack_tc.cu, namespace pw)
         int handled = 0;
-        if (int err = tc_pw_conv(x, w, bias, mask, y, B, cin, (long long)P, N, relu, x_absmax, y_absmax, st, &handled)) return err;
+        if (int err = tc_pw_conv(x, w, bias, mask, y, B, cin, H, W, N, k, relu, x_absmax, y_absmax, st, &handled)) return err;
         if (handled) return 0;
     }
     dim3 grid((P + GT_T - 1) / GT_T, (N + GT_T - 1) / GT_T, B);

@@ -44,6 +44,26 @@ for name, args in (("forward relu+bias", (x, w, bias, True, None)), ("dgrad with
     e1.record(); torch.cuda.synchronize()
     print(f"{name}: {e0.elapsed_time(e1) / 5 * 1e3:.0f} us per call (EQB_TRAIN_TC={os.environ.get('EQB_TRAIN_TC', '1')})")
 
+# ---- k x k with cin * k * k <= 256 (the lift of the flagship network: 3 -> 256 channels, 5 x 5) ---------------------------
+for (B, cin, H, W, k) in ((2, 3, 20, 24, 5), (3, 3, 96, 96, 5), (2, 7, 15, 13, 3), (1, 256, 9, 9, 1)):
+    x = torch.randn(B, cin, H, W, device=dev) * torch.logspace(-1, 1, B, device=dev)[:, None, None, None]
+    w = torch.randn(256, cin, k, k, device=dev) / 8
+    bias = torch.randn(256, device=dev)
+    y = ops.conv2d_forward(x, w, bias, True)
+    torch.cuda.synchronize()
+    r = torch.nn.functional.conv2d(x.double(), w.double(), bias.double()).clamp_min(0)
+    scale = r.abs().amax(dim=(1, 2, 3), keepdim=True).clamp_min(1e-30)
+    err = ((y.double() - r).abs() / scale).max().item()
+    print(f"conv B={B} cin={cin} {H}x{W} k={k}: max err / max|y| per image = {err:.3e}", "OK" if err < 4e-6 else "FAIL")
+x = torch.randn(64, 3, 96, 96, device=dev); w = torch.randn(256, 3, 5, 5, device=dev) / 8; bias = torch.randn(256, device=dev)
+for _ in range(2): ops.conv2d_forward(x, w, bias, True)
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(5): ops.conv2d_forward(x, w, bias, True)
+e1.record(); torch.cuda.synchronize()
+print(f"lift forward 64x3x96x96 -> 256 ch: {e0.elapsed_time(e1) / 5 * 1e3:.0f} us per call (EQB_TRAIN_TC={os.environ.get('EQB_TRAIN_TC', '1')})")
+
 # ---- weight gradient ---------------------------------------------------------------------------------------------------
 for (B, H, W) in ((2, 16, 16), (3, 20, 20), (2, 92, 92), (5, 4, 20)):
     x = torch.randn(B, 256, H, W, device=dev) * torch.logspace(-1, 1, B, device=dev)[:, None, None, None]
