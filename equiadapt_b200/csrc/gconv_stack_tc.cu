@@ -2254,6 +2254,10 @@ struct Args {
     const float *absmax_dy, *absmax_x;   // (B) each
     float *dw;
     int B, P, api;                       // api = 32-pixel atoms per image
+    // gather mode (k x k filters with K = cin * ksz^2 <= 128, the lift): the x operand's rows are the K patch taps, gathered
+    // by the converters from the (small, cache-resident) input images instead of arriving by TMA; Nx = K rounded up to 16
+    const float *x;
+    int gather, cin, H, W, Wo, ksz, K, Nx;
 };
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(640, 1)
@@ -2317,7 +2321,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(640, 1)
     const long long total = (long long)a.B * a.api;
     const long long per = (total + ncl - 1) / ncl;
     const long long A0 = (long long)cid * per, A1 = A0 + per < total ? A0 + per : total;
-    const uint32_t idesc = (1u << 4) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+    const int Nx = a.gather ? a.Nx : 256;       // columns of the accumulator = rows of the x operand over both CTAs
+    const uint32_t idesc = (1u << 4) | ((uint32_t)(Nx >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
 
     if (warp == 0) {
         if (lane == 0) {
@@ -2326,13 +2331,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(640, 1)
                 const int b = (int)(A / a.api), ka = (int)(A - (long long)b * a.api);
                 const uint32_t s = seq % XS_RING, ph = (seq / XS_RING) & 1u;
                 mbar_wait(bar(B_XEMPTY + s), ph ^ 1u, 200 + B_XEMPTY + s);
-                mbar_expect_tx(bar(B_XFULL + s), (uint32_t)XS_STAGE);
+                mbar_expect_tx(bar(B_XFULL + s), a.gather ? 128u * 128u : (uint32_t)XS_STAGE);
                 const uint32_t dst = base + M.xs + s * XS_STAGE;
                 asm volatile(
                     "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
                     ::"r"(dst), "l"((uint64_t)&dymap), "r"(bar(B_XFULL + s)), "r"(32 * ka), "r"(b * 256 + 128 * (int)rank), "r"(0)
                     : "memory");
-                asm volatile(
+                if (!a.gather) asm volatile(
                     "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
                     ::"r"(dst + 128u * 128u), "l"((uint64_t)&xmap), "r"(bar(B_XFULL + s)), "r"(32 * ka), "r"(b * 256 + 128 * (int)rank), "r"(0)
                     : "memory");
@@ -2375,8 +2380,31 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(640, 1)
             mbar_wait(bar(B_XFULL + s), ph, 200 + B_XFULL + s);
             const unsigned char *box = sm + M.xs + s * XS_STAGE + src_row;
             float4 v[8];
+            if (o == 1 && a.gather) {
+                // row r of this CTA's half of the patch operand = tap k of the filter; its 32 values = that tap under the
+                // atom's 32 output pixels (which wrap over output rows)
+                const int k = (Nx >> 1) * (int)rank + r;
+                const bool row_ok = r < (Nx >> 1) && k < a.K;
+                float t[32];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = *reinterpret_cast<const float4 *>(box + (((uint32_t)j ^ sx7) << 4));
+                for (int j = 0; j < 32; ++j) t[j] = 0.f;
+                if (row_ok) {
+                    const int b = (int)(A / a.api), ka = (int)(A - (long long)b * a.api);
+                    const int kk2 = a.ksz * a.ksz, c = k / kk2, rem = k - c * kk2, ky = rem / a.ksz, kx = rem - ky * a.ksz;
+                    const float *xb = a.x + ((size_t)b * a.cin + c) * a.H * a.W + (size_t)ky * a.W + kx;
+                    int pp = 32 * ka, oy = pp / a.Wo, ox = pp - oy * a.Wo;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        if (pp + j < a.P) t[j] = __ldg(xb + (size_t)oy * a.W + ox);
+                        if (++ox == a.Wo) { ox = 0; ++oy; }
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = make_float4(t[4 * j], t[4 * j + 1], t[4 * j + 2], t[4 * j + 3]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = *reinterpret_cast<const float4 *>(box + (((uint32_t)j ^ sx7) << 4));
+            }
             mbar_arrive(bar(B_XEMPTY + s));
             uint32_t hi[16], lo[16];
 #pragma unroll
@@ -2404,14 +2432,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(640, 1)
             mbar_wait(bar(B_DFULL), 0, 200 + B_DFULL);
             tc_fence_after();
             const uint32_t t0 = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(128 * g);
-            float *dst = a.dw + (size_t)n * 256 + 128 * g;
+            const int Kw = a.gather ? a.K : 256;            // row length of dw; accumulator column j = reduction row j
+            float *dst = a.dw + (size_t)n * Kw + 128 * g;
 #pragma unroll 1
             for (int c = 0; c < 4; ++c) {
+                if (128 * g + 32 * c >= Nx) break;          // (uniform)
                 uint32_t rr[32];
                 tc_ld32_issue(t0 + (uint32_t)(32 * c), rr);
                 tc_ld_wait(rr);
 #pragma unroll
-                for (int i = 0; i < 32; ++i) atomicAdd(dst + 32 * c + i, __uint_as_float(rr[i]) * cs);
+                for (int i = 0; i < 32; ++i)
+                    if (128 * g + 32 * c + i < Kw) atomicAdd(dst + 32 * c + i, __uint_as_float(rr[i]) * cs);
             }
         }
     }
@@ -2631,14 +2662,18 @@ static int pw_scratch(cudaStream_t st, size_t need, unsigned char **out) {
     return 0;
 }
 
-// Weight gradient of a 1x1 layer with N = cin = 256 on the tensor pipe (tc::wg); dw must be zeroed by the caller.
-int tc_pw_wgrad(const float *dy, const float *x, float *dw, int B, int cin, long long P, int N, const float *dy_absmax,
+// Weight gradient of the same layers on the tensor pipe (tc::wg): N = 256 and either a 1x1 layer with cin = 256 (both operands
+// by TMA) or k x k with cin * k * k <= 128 (patch operand gathered: the lift); dw must be zeroed by the caller.
+int tc_pw_wgrad(const float *dy, const float *x, float *dw, int B, int cin, int H, int W, int N, int k, const float *dy_absmax,
                 const float *x_absmax, cudaStream_t st, int *handled) {
     *handled = 0;
     const char *e = getenv("EQB_TRAIN_TC");
     if (e && e[0] == '0') return 0;
-    if (cin != 256 || N != 256 || P <= 0 || (P & 3) != 0 || P >= (1LL << 30) || B <= 0 || (long long)B * 256 >= (1LL << 31)) return 0;
-    if ((((uintptr_t)x | (uintptr_t)dy) & 15) != 0) return 0;
+    const long long K = (long long)cin * k * k, P = (long long)(H - k + 1) * (W - k + 1);
+    const bool dense = k == 1 && cin == 256;
+    const bool gather = !dense && K <= 128;
+    if (N != 256 || !(dense || gather) || P <= 0 || (P & 3) != 0 || P >= (1LL << 30) || B <= 0 || (long long)B * 256 >= (1LL << 31)) return 0;
+    if (((uintptr_t)dy & 15) != 0 || (dense && ((uintptr_t)x & 15) != 0) || (long long)cin * H * W >= (1LL << 31)) return 0;
     if (int err = ensure_stall_report()) return err;
     unsigned char *scratch = nullptr;
     const size_t wbytes = (size_t)tc::HDR_BYTES + 16 * 16384;         // (the forward's region of the same buffer stays untouched)
@@ -2647,12 +2682,18 @@ int tc_pw_wgrad(const float *dy, const float *x, float *dw, int B, int cin, long
     if (dy_absmax) am_dy = const_cast<float *>(dy_absmax);
     else if (int err = tc_absmax(dy, B, (size_t)256 * (size_t)P, am_dy, st)) return err;
     if (x_absmax) am_x = const_cast<float *>(x_absmax);
-    else if (int err = tc_absmax(x, B, (size_t)256 * (size_t)P, am_x, st)) return err;
+    else if (int err = tc_absmax(x, B, (size_t)cin * H * W, am_x, st)) return err;
     CUtensorMap dymap, xmap;
     if (int err = make_plane_map(&dymap, dy, (int)P, B * 256, 1, 32, 128, CU_TENSOR_MAP_SWIZZLE_128B)) return err;
-    if (int err = make_plane_map(&xmap, x, (int)P, B * 256, 1, 32, 128, CU_TENSOR_MAP_SWIZZLE_128B)) return err;
+    if (dense) {
+        if (int err = make_plane_map(&xmap, x, (int)P, B * 256, 1, 32, 128, CU_TENSOR_MAP_SWIZZLE_128B)) return err;
+    } else {
+        xmap = dymap;                                                   // (unused in gather mode)
+    }
     tc::wg::Args a{};
     a.absmax_dy = am_dy; a.absmax_x = am_x; a.dw = dw; a.B = B; a.P = (int)P; a.api = (int)((P + 31) / 32);
+    a.x = x; a.gather = gather ? 1 : 0; a.cin = cin; a.H = H; a.W = W; a.Wo = W - k + 1; a.ksz = k; a.K = (int)K;
+    a.Nx = (int)((K + 15) / 16 * 16);
     const tc::wg::Smem M = tc::wg::smem_map();
     static PerDeviceOnce configured;
     if (configured.first())

@@ -303,9 +303,9 @@ extern "C" int eqb_conv2d_weight_grad_scaled(const float *dy, const float *x, fl
     const int K = cin * k * k, P = (H - k + 1) * (W - k + 1);
     EQB_CUDA(cudaMemsetAsync(dw, 0, (size_t)N * K * sizeof(float), st));
     if (B == 0) return 0;
-    if (k == 1) {
+    {
         int handled = 0;
-        if (int err = tc_pw_wgrad(dy, x, dw, B, cin, (long long)P, N, dy_absmax, x_absmax, st, &handled)) return err;
+        if (int err = tc_pw_wgrad(dy, x, dw, B, cin, H, W, N, k, dy_absmax, x_absmax, st, &handled)) return err;
         if (handled) return 0;
     }
     const int tiles = ((K + GT_T - 1) / GT_T) * ((N + GT_T - 1) / GT_T);

@@ -1237,6 +1237,51 @@ def test_pointwise_conv_tensor_core_path_vs_torch(b, h, w, cuda_device, monkeypa
     assert bool((y_f >= 0).all())
 
 
+@pytest.mark.parametrize("b,cin,h,w,k", [(2, 3, 20, 24, 5), (3, 3, 96, 96, 5), (2, 7, 14, 12, 3), (2, 256, 16, 16, 1), (5, 256, 4, 20, 1)])
+def test_tensor_core_training_convs_vs_torch(b, cin, h, w, k, cuda_device, monkeypatch):
+    """The training GEMMs with 256 output channels on the tensor pipe (csrc/gconv_stack_tc.cu, namespaces pw / wg): forward of
+    the 5x5 lift (patch taps gathered by the converters, cin*k*k <= 256) and of the 1x1 layers, and both weight gradients
+    (1x1: dy and x by TMA; k x k: patch operand gathered, cin*k*k <= 128), against torch fp64 (F.conv2d and its autograd, what
+    the reference runs: custom_group_equivariant_layers.py:104-112, :298-334) at 4e-6 of the result's max (1e-4 at the
+    training shape's K = 541 696, tools/check_pw.py), and against the SIMT kernels.  Samples of very different ranges share the
+    batch; chained calls hand the per-sample maxima on (eqb_conv2d_*_scaled) and must give the same bits as unchained ones."""
+    ops = _mods()[0]
+    dev = cuda_device
+    g = torch.Generator().manual_seed(b * 1000 + h * 10 + k)
+    x = (torch.randn(b, cin, h, w, generator=g) * torch.logspace(-1, 1, b)[:, None, None, None]).to(dev)
+    wt = (torch.randn(256, cin, k, k, generator=g) / 8).to(dev)
+    bias = torch.randn(256, generator=g).to(dev)
+    dy = torch.randn(b, 256, h - k + 1, w - k + 1, generator=g).to(dev)
+    wd = wt.double().requires_grad_(True)
+    yo = torch.nn.functional.conv2d(x.double(), wd, bias.double())
+    (yo * dy.double()).sum().backward()
+    want_y = yo.detach().clamp_min(0)
+
+    def err_y(y):
+        scale = want_y.abs().amax(dim=(1, 2, 3), keepdim=True).clamp_min(1e-30)
+        return float(((y.double() - want_y).abs() / scale).max())
+
+    def err_w(dw):
+        return float((dw.double() - wd.grad).abs().max() / wd.grad.abs().max())
+
+    y = ops.conv2d_forward(x, wt, bias, True)
+    dw = ops.conv2d_weight_grad(dy, x, k)
+    assert err_y(y) < 4e-6 and err_w(dw) < 4e-6
+    assert ops._known_amax(y) is not None and torch.equal(ops._known_amax(y), y.abs().amax(dim=(1, 2, 3)))
+    # chained: the maxima recorded on y feed the next layer's operand scale -- same bits as a tensor without the record
+    if cin == 256:
+        y2a = ops.conv2d_forward(y, wt, None, False)
+        y2b = ops.conv2d_forward(y.clone(), wt, None, False)
+        assert torch.equal(y2a, y2b)
+        y.mul_(2.0)                                   # an in-place write invalidates the record
+        assert ops._known_amax(y) is None
+    monkeypatch.setenv("EQB_TRAIN_TC", "0")
+    ys = ops.conv2d_forward(x, wt, bias, True)
+    dws = ops.conv2d_weight_grad(dy, x, k)
+    assert err_y(ys) < 1e-6 and err_w(dws) < 2e-6
+    assert not torch.equal(ys, y if cin != 256 else ys + 1)
+
+
 @pytest.mark.parametrize("n,reflect,k", [(4, False, 5), (8, False, 5), (8, True, 3), (6, True, 1)])
 def test_filter_orbit_adjoints_vs_oracle_autograd(n, reflect, k, cuda_device):
     ops = _mods()[0]

@@ -84,3 +84,22 @@ for _ in range(5): dw = ops.conv2d_weight_grad(dy, x, 1)
 e1.record(); torch.cuda.synchronize()
 r = torch.einsum("bnp,bcp->nc", dy.flatten(2).double(), x.flatten(2).double())
 print(f"wgrad 64x256x92x92: {e0.elapsed_time(e1) / 5 * 1e3:.0f} us per call, err {((dw[:, :, 0, 0].double() - r).abs().max() / r.abs().max()).item():.3e}")
+
+# ---- weight gradient of k x k filters (patch operand gathered) ----------------------------------------------------------
+for (B, cin, H, W, k) in ((2, 3, 20, 24, 5), (3, 3, 96, 96, 5), (2, 7, 14, 12, 3)):
+    x = torch.randn(B, cin, H, W, device=dev) * torch.logspace(-1, 1, B, device=dev)[:, None, None, None]
+    dy = torch.randn(B, 256, H - k + 1, W - k + 1, device=dev)
+    dw = ops.conv2d_weight_grad(dy, x, k)
+    torch.cuda.synchronize()
+    wd = torch.zeros(256, cin, k, k, dtype=torch.float64, device=dev, requires_grad=True)
+    (torch.nn.functional.conv2d(x.double(), wd) * dy.double()).sum().backward()
+    err = ((dw.double() - wd.grad).abs().max() / wd.grad.abs().max()).item()
+    print(f"wgrad k x k: B={B} cin={cin} {H}x{W} k={k}: max err / max|dw| = {err:.3e}", "OK" if err < 4e-6 else "FAIL")
+x = torch.randn(64, 3, 96, 96, device=dev); dy = torch.randn(64, 256, 92, 92, device=dev)
+for _ in range(2): ops.conv2d_weight_grad(dy, x, 5)
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(5): ops.conv2d_weight_grad(dy, x, 5)
+e1.record(); torch.cuda.synchronize()
+print(f"lift wgrad 64x3x96x96, dy 64x256x92x92: {e0.elapsed_time(e1) / 5 * 1e3:.0f} us per call (EQB_TRAIN_TC={os.environ.get('EQB_TRAIN_TC', '1')})")
