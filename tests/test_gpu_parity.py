@@ -1265,6 +1265,7 @@ def test_tensor_core_training_convs_vs_torch(b, cin, h, w, k, cuda_device, monke
         return float((dw.double() - wd.grad).abs().max() / wd.grad.abs().max())
 
     y = ops.conv2d_forward(x, wt, bias, True)
+    y0 = y.clone()
     dw = ops.conv2d_weight_grad(dy, x, k)
     assert err_y(y) < 4e-6 and err_w(dw) < 4e-6
     assert ops._known_amax(y) is not None and torch.equal(ops._known_amax(y), y.abs().amax(dim=(1, 2, 3)))
@@ -1279,7 +1280,7 @@ def test_tensor_core_training_convs_vs_torch(b, cin, h, w, k, cuda_device, monke
     ys = ops.conv2d_forward(x, wt, bias, True)
     dws = ops.conv2d_weight_grad(dy, x, k)
     assert err_y(ys) < 1e-6 and err_w(dws) < 2e-6
-    assert not torch.equal(ys, y if cin != 256 else ys + 1)
+    assert not torch.equal(ys, y0)                    # (two different kernels really ran)
 
 
 @pytest.mark.parametrize("n,reflect,k", [(4, False, 5), (8, False, 5), (8, True, 3), (6, True, 1)])
