@@ -2253,6 +2253,7 @@ __host__ __device__ inline Smem smem_map() {
 struct Args {
     const float *absmax_dy, *absmax_x;   // (B) each
     float *dw;
+    float *dy_rowsum;                    // (256) or null: sum_{b,p} dy[b, n, p], the bias gradient, folded into the converters (zeroed by the host side)
     int B, P, api;                       // api = 32-pixel atoms per image
     // gather mode (k x k filters with K = cin * ksz^2 <= 128, the lift): the x operand's rows are the K patch taps, gathered
     // by the converters from the (small, cache-resident) input images instead of arriving by TMA; Nx = K rounded up to 16
@@ -2374,6 +2375,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(640, 1)
         const uint32_t src_row = (uint32_t)o * (128u * 128u) + (uint32_t)r * 128u, sx7 = (uint32_t)(r & 7);
         const uint32_t dst_row = (uint32_t)o * A1_STAGE + (uint32_t)r * 64u, swz = (uint32_t)((r >> 1) & 3);
         const uint32_t afull0 = leader_bar(B_AFULL);
+        float rowsum = 0.f;
         for (long long A = A0 + grp; A < A1; A += 2) {
             const uint32_t seq = (uint32_t)(A - A0);
             const uint32_t s = seq % XS_RING, ph = (seq / XS_RING) & 1u;
@@ -2406,6 +2408,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(640, 1)
                 for (int j = 0; j < 8; ++j) v[j] = *reinterpret_cast<const float4 *>(box + (((uint32_t)j ^ sx7) << 4));
             }
             mbar_arrive(bar(B_XEMPTY + s));
+            if (o == 0) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) rowsum += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+            }
             uint32_t hi[16], lo[16];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -2424,6 +2430,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(640, 1)
             fence_async_smem();
             mbar_arrive_cluster(afull0 + 8u * sa);
         }
+        if (a.dy_rowsum && o == 0) atomicAdd(a.dy_rowsum + 128 * (int)rank + r, rowsum);
         // ===== epilogue (warps 4-11, after their last atom): this CTA's 128 rows of the partial -> dw =========================
         if (warp < 12 && A1 > A0) {
             const int q = warp & 3, g = (warp - 4) >> 2;
@@ -2664,8 +2671,8 @@ static int pw_scratch(cudaStream_t st, size_t need, unsigned char **out) {
 
 // Weight gradient of the same layers on the tensor pipe (tc::wg): N = 256 and either a 1x1 layer with cin = 256 (both operands
 // by TMA) or k x k with cin * k * k <= 128 (patch operand gathered: the lift); dw must be zeroed by the caller.
-int tc_pw_wgrad(const float *dy, const float *x, float *dw, int B, int cin, int H, int W, int N, int k, const float *dy_absmax,
-                const float *x_absmax, cudaStream_t st, int *handled) {
+int tc_pw_wgrad(const float *dy, const float *x, float *dw, float *dy_rowsum, int B, int cin, int H, int W, int N, int k,
+                const float *dy_absmax, const float *x_absmax, cudaStream_t st, int *handled) {
     *handled = 0;
     const char *e = getenv("EQB_TRAIN_TC");
     if (e && e[0] == '0') return 0;
@@ -2692,6 +2699,7 @@ int tc_pw_wgrad(const float *dy, const float *x, float *dw, int B, int cin, int 
     }
     tc::wg::Args a{};
     a.absmax_dy = am_dy; a.absmax_x = am_x; a.dw = dw; a.B = B; a.P = (int)P; a.api = (int)((P + 31) / 32);
+    a.dy_rowsum = dy_rowsum;
     a.x = x; a.gather = gather ? 1 : 0; a.cin = cin; a.H = H; a.W = W; a.Wo = W - k + 1; a.ksz = k; a.K = (int)K;
     a.Nx = (int)((K + 15) / 16 * 16);
     const tc::wg::Smem M = tc::wg::smem_map();

@@ -38,8 +38,8 @@ int tc_launch(TcArgs a, cudaStream_t st);
 int tc_pw_conv(const float *x, const float *w, const float *bias, const float *mask, float *y, int B, int cin, int H, int W,
                int N, int k, int relu, const float *x_absmax, float *y_absmax, cudaStream_t st, int *handled);
 // ... and its weight gradient dw[n, c] = sum_{b, p} dy[b, n, p] x[b, c, p] (dw zeroed by the caller; split-K fp32 atomics)
-int tc_pw_wgrad(const float *dy, const float *x, float *dw, int B, int cin, int H, int W, int N, int k, const float *dy_absmax,
-                const float *x_absmax, cudaStream_t st, int *handled);
+int tc_pw_wgrad(const float *dy, const float *x, float *dw, float *dy_rowsum, int B, int cin, int H, int W, int N, int k,
+                const float *dy_absmax, const float *x_absmax, cudaStream_t st, int *handled);   // dy_rowsum: (N), zeroed, or null
 int tc_set_trace(long long *device_buffer, int tiles);   // next CTA-pair launches record a timeline (null: off)
 int tc_last_stall(int *out5);  // {flag, block, warp, barrier id, parity} of the first pipeline stall that trapped
 

@@ -294,20 +294,43 @@ extern "C" int eqb_conv2d_forward(const float *x, const float *w, const float *b
     return eqb_conv2d_forward_scaled(x, w, bias, mask, y, B, cin, H, W, N, k, relu, nullptr, nullptr, stream);
 }
 
+// out[n] = sum_{b, p} dy[b, n, p] (the SIMT path's version of the row sums the tensor-core kernel folds into its converters)
+__global__ void __launch_bounds__(256) channel_sums_kernel(const float *__restrict__ dy, int B, int N, long long P,
+                                                           float *__restrict__ out) {
+    __shared__ float red[8];
+    const int n = blockIdx.x;
+    float acc = 0.f;
+    for (int b = 0; b < B; ++b) {
+        const float *row = dy + ((size_t)b * N + n) * P;
+        for (long long p = threadIdx.x; p < P; p += 256) acc += row[p];
+    }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int w = 0; w < 8; ++w) t += red[w];
+        out[n] = t;
+    }
+}
+
 extern "C" int eqb_conv2d_weight_grad_scaled(const float *dy, const float *x, float *dw, int B, int cin, int H, int W, int N,
-                                             int k, const float *dy_absmax, const float *x_absmax, void *stream) {
+                                             int k, const float *dy_absmax, const float *x_absmax, float *dy_rowsum,
+                                             void *stream) {
     EQB_NVTX_RANGE();
     EQB_REQUIRE(B >= 0 && cin > 0 && N > 0 && k > 0 && H >= k && W >= k, "eqb_conv2d_weight_grad: bad shape");
     EQB_REQUIRE(dw && (B == 0 || (dy && x)), "eqb_conv2d_weight_grad: null pointer");
     cudaStream_t st = (cudaStream_t)stream;
     const int K = cin * k * k, P = (H - k + 1) * (W - k + 1);
     EQB_CUDA(cudaMemsetAsync(dw, 0, (size_t)N * K * sizeof(float), st));
+    if (dy_rowsum) EQB_CUDA(cudaMemsetAsync(dy_rowsum, 0, (size_t)N * sizeof(float), st));
     if (B == 0) return 0;
     {
         int handled = 0;
-        if (int err = tc_pw_wgrad(dy, x, dw, B, cin, H, W, N, k, dy_absmax, x_absmax, st, &handled)) return err;
+        if (int err = tc_pw_wgrad(dy, x, dw, dy_rowsum, B, cin, H, W, N, k, dy_absmax, x_absmax, st, &handled)) return err;
         if (handled) return 0;
     }
+    if (dy_rowsum) channel_sums_kernel<<<N, 256, 0, st>>>(dy, B, N, (long long)P, dy_rowsum);
     const int tiles = ((K + GT_T - 1) / GT_T) * ((N + GT_T - 1) / GT_T);
     const long long total_chunks = (long long)B * ((P + GT_K - 1) / GT_K);
     long long splits = (4LL * num_sms() + tiles - 1) / tiles;       // a few waves of CTAs
@@ -322,7 +345,7 @@ extern "C" int eqb_conv2d_weight_grad_scaled(const float *dy, const float *x, fl
 
 extern "C" int eqb_conv2d_weight_grad(const float *dy, const float *x, float *dw, int B, int cin, int H, int W, int N, int k,
                                       void *stream) {
-    return eqb_conv2d_weight_grad_scaled(dy, x, dw, B, cin, H, W, N, k, nullptr, nullptr, stream);
+    return eqb_conv2d_weight_grad_scaled(dy, x, dw, B, cin, H, W, N, k, nullptr, nullptr, nullptr, stream);
 }
 
 extern "C" int eqb_plane_sums(const float *x, int64_t rows, int64_t P, float *out, void *stream) {

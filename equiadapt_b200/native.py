@@ -48,7 +48,7 @@ _SIGNATURES = {
     "eqb_conv2d_forward": (C.c_int, [_fp] * 5 + [_i] * 7 + [_fp]),
     "eqb_conv2d_weight_grad": (C.c_int, [_fp] * 3 + [_i] * 6 + [_fp]),
     "eqb_conv2d_forward_scaled": (C.c_int, [_fp] * 5 + [_i] * 7 + [_fp] * 3),
-    "eqb_conv2d_weight_grad_scaled": (C.c_int, [_fp] * 3 + [_i] * 6 + [_fp] * 3),
+    "eqb_conv2d_weight_grad_scaled": (C.c_int, [_fp] * 3 + [_i] * 6 + [_fp] * 4),
     "eqb_plane_sums": (C.c_int, [_fp, C.c_int64, C.c_int64, _fp, _fp]),
     "eqb_group_mean_backward": (C.c_int, [_fp, _fp, _i, _i, _i, C.c_int64, _fp]),
     "eqb_lift_filter_orbit_adjoint": (C.c_int, [_fp, _fp] + [_i] * 5 + [_fp]),

@@ -152,7 +152,9 @@ def conv2d_forward(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor
     return y
 
 
-def conv2d_weight_grad(dy: torch.Tensor, x: torch.Tensor, k: int) -> torch.Tensor:
+def conv2d_weight_grad(dy: torch.Tensor, x: torch.Tensor, k: int, with_bias_grad: bool = False):
+    """dw[n, ci, ky, kx] = sum_{b,y,x} dy[b,n,y,x] x[b,ci,y+ky,x+kx]; with_bias_grad: also sum_{b,y,x} dy[b,n,y,x] (N,), from the
+    same pass over dy -> (dw, dbias)."""
     dev = _need_cuda(dy, x)
     dy_amax, x_amax = _known_amax(dy), _known_amax(x)
     dy, x = _f32(dy), _f32(x)
@@ -161,9 +163,11 @@ def conv2d_weight_grad(dy: torch.Tensor, x: torch.Tensor, k: int) -> torch.Tenso
     if tuple(dy.shape) != (b, n, h - k + 1, wd - k + 1):
         raise ValueError("dy does not match a valid k x k convolution of x")
     dw = torch.empty((n, cin, k, k), dtype=torch.float32, device=dev)
+    db = torch.empty((n,), dtype=torch.float32, device=dev) if with_bias_grad else None
     _call("eqb_conv2d_weight_grad_scaled", 1 if b else 0, dev, _ptr(dy), _ptr(x), _ptr(dw), b, cin, h, wd, n, k,
-          _ptr(dy_amax) if dy_amax is not None else None, _ptr(x_amax) if x_amax is not None else None, _stream(dev))
-    return dw
+          _ptr(dy_amax) if dy_amax is not None else None, _ptr(x_amax) if x_amax is not None else None,
+          _ptr(db) if db is not None else None, _stream(dev))
+    return (dw, db) if with_bias_grad else dw
 
 
 def plane_sums(x: torch.Tensor) -> torch.Tensor:
@@ -245,10 +249,15 @@ class _GConvStackTrain(torch.autograd.Function):
             if ctx.amax[li] is not None:
                 _record_amax(xin, ctx.amax[li])
             k = wx.shape[-1]
-            if has_bias[li] and ctx.needs_input_grad[3 + 2 * li + 1]:
+            want_b = has_bias[li] and ctx.needs_input_grad[3 + 2 * li + 1]
+            want_w = ctx.needs_input_grad[3 + 2 * li]
+            if want_b and not want_w:
                 grads[2 * li + 1] = plane_sums(dy).sum(0).reshape(cout, g).sum(1)
-            if ctx.needs_input_grad[3 + 2 * li]:
-                dwx = conv2d_weight_grad(dy, xin, k)
+            if want_w:
+                dwx = conv2d_weight_grad(dy, xin, k, with_bias_grad=want_b)
+                if want_b:
+                    dwx, db = dwx                       # (the bias gradient comes out of the same pass over dy)
+                    grads[2 * li + 1] = db.reshape(cout, g).sum(1)
                 grads[2 * li] = (lift_filter_orbit_adjoint(dwx, cout, num_rotations, reflect) if li == 0
                                  else regular_filter_orbit_adjoint(dwx, cout, num_rotations, reflect))
             if li > 0:

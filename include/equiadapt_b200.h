@@ -281,12 +281,13 @@ EQB_API int eqb_conv2d_weight_grad(const float *dy, const float *x, float *dw, i
  * 1x1 layers with 256 channels run on the tensor pipe with a per-image power-of-two operand scale (csrc/gconv_stack_tc.cu,
  * namespaces pw / wg); a caller that chains layers passes the maxima the previous call produced (y_absmax) instead of
  * paying a pass over a 555 MB feature map per call.  x_absmax / dy_absmax must be >= the true maxima (an under-estimate
- * overflows the fp16 split) and should be within 2x of them (an over-estimate costs precision). */
+ * overflows the fp16 split) and should be within 2x of them (an over-estimate costs precision).  dy_rowsum (N floats or
+ * NULL) receives sum_{b,y,x} dy[b,n,y,x] -- the bias gradient of the layer -- from the same pass over dy. */
 EQB_API int eqb_conv2d_forward_scaled(const float *x, const float *w, const float *bias, const float *mask, float *y, int B,
                               int cin, int H, int W, int N, int k, int relu, const float *x_absmax, float *y_absmax,
                               void *stream);
 EQB_API int eqb_conv2d_weight_grad_scaled(const float *dy, const float *x, float *dw, int B, int cin, int H, int W, int N,
-                                  int k, const float *dy_absmax, const float *x_absmax, void *stream);
+                                  int k, const float *dy_absmax, const float *x_absmax, float *dy_rowsum, void *stream);
 EQB_API int eqb_plane_sums(const float *x, int64_t rows, int64_t P, float *out, void *stream);
 EQB_API int eqb_group_mean_backward(const float *dact, float *dy, int B, int cout, int num_group, int64_t P, void *stream);
 EQB_API int eqb_lift_filter_orbit_adjoint(const float *dorbit, float *dw, int cout, int cin, int k, int num_rotations,

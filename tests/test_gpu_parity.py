@@ -1268,6 +1268,9 @@ def test_tensor_core_training_convs_vs_torch(b, cin, h, w, k, cuda_device, monke
     y0 = y.clone()
     dw = ops.conv2d_weight_grad(dy, x, k)
     assert err_y(y) < 4e-6 and err_w(dw) < 4e-6
+    dw2, db = ops.conv2d_weight_grad(dy, x, k, with_bias_grad=True)       # bias gradient from the same pass over dy
+    assert torch.allclose(dw2, dw, rtol=0, atol=4e-6 * float(dw.abs().max()))   # (split-K atomics: order varies)
+    assert rel_err(db.cpu().double(), dy.double().sum((0, 2, 3)).cpu()) < 1e-5
     assert ops._known_amax(y) is not None and torch.equal(ops._known_amax(y), y.abs().amax(dim=(1, 2, 3)))
     # chained: the maxima recorded on y feed the next layer's operand scale -- same bits as a tensor without the record
     if cin == 256:
@@ -1278,8 +1281,9 @@ def test_tensor_core_training_convs_vs_torch(b, cin, h, w, k, cuda_device, monke
         assert ops._known_amax(y) is None
     monkeypatch.setenv("EQB_TRAIN_TC", "0")
     ys = ops.conv2d_forward(x, wt, bias, True)
-    dws = ops.conv2d_weight_grad(dy, x, k)
+    dws, dbs = ops.conv2d_weight_grad(dy, x, k, with_bias_grad=True)
     assert err_y(ys) < 1e-6 and err_w(dws) < 2e-6
+    assert rel_err(dbs.cpu().double(), dy.double().sum((0, 2, 3)).cpu()) < 1e-5
     assert not torch.equal(ys, y0)                    # (two different kernels really ran)
 
 
