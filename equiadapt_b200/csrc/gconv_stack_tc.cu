@@ -2407,7 +2407,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(640, 1)
 #pragma unroll
                 for (int j = 0; j < 8; ++j) v[j] = *reinterpret_cast<const float4 *>(box + (((uint32_t)j ^ sx7) << 4));
             }
-            mbar_arrive(bar(B_XEMPTY + s));
             if (o == 0) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) rowsum += (v[j].x + v[j].y) + (v[j].z + v[j].w);
@@ -2418,6 +2417,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(640, 1)
                 split2(v[j].x * sc, v[j].y * sc, hi[2 * j], lo[2 * j]);
                 split2(v[j].z * sc, v[j].w * sc, hi[2 * j + 1], lo[2 * j + 1]);
             }
+            // release the staged box only AFTER its values have been consumed: an arrive issued right behind the loads can be
+            // performed before they have read shared memory, and with a shallow ring the TMA unit refills the slot at once
+            // (XS_RING = 2 gave 2e-3 errors in dw; with four stages the refill comes three atoms later and never showed)
+            mbar_arrive(bar(B_XEMPTY + s));
             const uint32_t sa = seq % A_RING, pa = (seq / A_RING) & 1u;
             mbar_wait(bar(B_AEMPTY + sa), pa ^ 1u, 200 + B_AEMPTY + sa);
             const uint32_t hi_row = base + M.at + sa * AT_STAGE + dst_row, lo_row = hi_row + A1_HALF;
