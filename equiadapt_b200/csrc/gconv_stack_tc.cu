@@ -1919,9 +1919,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(768, 1) gconv_stack_
 // (custom_group_equivariant_layers.py:298-334 after the filter orbit; eqb_conv2d_forward's contract).
 // Same numerics as the stack kernel: fp16 hi/lo split of both operands (3 MMAs per product, ~22-bit significands),
 // power-of-two operand scales (per IMAGE for x), fp32 accumulation in TMEM.
-//   warps 4-11  (both CTAs) converters: thread = pixel, two groups on alternate atoms: 32 channel values from global memory
-//               (coalesced per channel) -> scaled fp16 hi / lo -> the K-major 64-byte-swizzled operand atom [128 pixels x 32
-//               channels] of this CTA (4-stage ring)
+//   warps 4-11  (both CTAs) converters: thread = (pixel, half atom): 16 reduction values from global memory (coalesced per
+//               channel), the next atom's loads in flight -> scaled fp16 hi / lo -> the K-major 64-byte-swizzled operand atom
+//               [128 pixels x 32 channels] of this CTA (4-stage ring)
 //   warp 1      (leader)    8 atoms x 6 MMAs (cta_group::2, M = 256 pixels, N = 256 channels) into D[tile & 1]
 //   warps 12-19 (both CTAs) epilogue: this CTA's 128 pixels x 256 channels of D -> scale, bias, ReLU, mask -> y; lane = pixel,
 //               so every store and mask load of a warp is one 128-byte line (with channels on the lanes -- the stack
@@ -1932,12 +1932,7 @@ namespace pw {
 
 using namespace pair;
 
-// EVEN ring depth: the two converter groups take alternate atoms, so with an even ring a slot always belongs to the same
-// group and that group sees every phase of its barriers.  (With 3 stages a group skipped every other phase of a slot, and
-// a parity wait cannot tell "my slot was released" from "it had been released two phases earlier": a timing-dependent
-// launch failure.)
 constexpr int A_RING = 4;
-static_assert(A_RING % 2 == 0, "ring slots must map to a fixed converter group");
 enum { B_AFULL = 0, B_AEMPTY = B_AFULL + A_RING, B_DFULL = B_AEMPTY + A_RING, B_DEMPTY = B_DFULL + 2, B_WLOAD = B_DEMPTY + 2, B_COUNT };
 
 struct Smem {
@@ -1962,7 +1957,7 @@ struct Args {
     float *y, *absmax_out;
     int B, P, tiles, relu;        // P = output pixels per image, tiles = pair-tiles (256 pixels) per image
     int cin, H, W, Wo, ksz, K, natoms;   // valid ksz x ksz convolution: K = cin * ksz^2 <= 256, natoms = ceil(K / 32)
-    int debug;                    // (development) 1: no stores, 2: no mask loads
+    int debug;                    // (development) 1: no stores, 2: no mask loads, 4: no operand loads, 8: no MMAs
 };
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(640, 1) pw_conv_kernel(const Args a) {
@@ -1981,7 +1976,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(640, 1) pw_conv_kern
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < A_RING; ++i) {
-            mbar_init(bar(B_AFULL + i), 256);      // one converter group of each CTA
+            mbar_init(bar(B_AFULL + i), 512);      // the 256 converter threads of each CTA
             mbar_init(bar(B_AEMPTY + i), 1);
         }
         for (int i = 0; i < 2; ++i) {
@@ -2039,14 +2034,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(640, 1) pw_conv_kern
                         const uint32_t a_hi = a_lo0 + (uint32_t)ra.stage * (A1_STAGE >> 4), a_lo = a_hi + (A1_HALF >> 4);
                         const uint32_t w_hi = w_lo0 + (uint32_t)kc * (W1_ATOM >> 4), w_lo = w_hi + (8192u >> 4);
                         const uint32_t dt = tmem + 256u * d;
-#pragma unroll
                         // D[pixel lanes][channel columns]: the pixel atoms are the M-side operand, this CTA's 128 rows of w
                         // half of the N side -- so that the epilogue's lanes run along pixels (coalesced y and mask)
-                        for (int j = 0; j < 2; ++j) tc_mma2_f16_lo<DESC_HI_64B>(dt, a_hi + 2 * j, w_hi + 2 * j, idesc, j ? 1u : (uint32_t)(kc != 0));
+                        if (!(a.debug & 8)) {
 #pragma unroll
-                        for (int j = 0; j < 2; ++j) tc_mma2_f16_lo<DESC_HI_64B>(dt, a_lo + 2 * j, w_hi + 2 * j, idesc, 1);
+                            for (int j = 0; j < 2; ++j) tc_mma2_f16_lo<DESC_HI_64B>(dt, a_hi + 2 * j, w_hi + 2 * j, idesc, j ? 1u : (uint32_t)(kc != 0));
 #pragma unroll
-                        for (int j = 0; j < 2; ++j) tc_mma2_f16_lo<DESC_HI_64B>(dt, a_hi + 2 * j, w_lo + 2 * j, idesc, 1);
+                            for (int j = 0; j < 2; ++j) tc_mma2_f16_lo<DESC_HI_64B>(dt, a_lo + 2 * j, w_hi + 2 * j, idesc, 1);
+#pragma unroll
+                            for (int j = 0; j < 2; ++j) tc_mma2_f16_lo<DESC_HI_64B>(dt, a_hi + 2 * j, w_lo + 2 * j, idesc, 1);
+                        }
                         tc_commit2(bar(B_AEMPTY + ra.stage));
                         if (kc == a.natoms - 1) tc_commit2(bar(B_DFULL + d));
                     }
@@ -2056,46 +2053,80 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(640, 1) pw_conv_kern
             }
         }
     } else if (warp >= 4 && warp < 12) {
-        // ===== converters: x -> this CTA's rows of the pixel-operand atom.  Thread = pixel; two groups of 128 threads take
-        // alternate atoms.  The 32 channel values of an atom come straight from global memory (for a fixed channel a warp reads
-        // one 128-byte line; 4 KB in flight per warp): staging the same boxes through TMA ran at one 16 KB box per ~2 000
-        // cycles per CTA whatever the ring depth (2.1 TB/s over the GPU, r3 notes) =============================================
-        const int tc_ = (int)threadIdx.x - 128, px = tc_ & 127, grp = tc_ >> 7;
+        // ===== converters: x -> this CTA's rows of the pixel-operand atom.  Thread = (pixel, half of the atom's 32 reduction
+        // indices); the 16 values come straight from global memory (for the 1x1 layers one coalesced line per channel and
+        // warp; for the lift the patch taps through the offset table), and the loads of the NEXT atom are in flight while this
+        // one is scaled, split and stored.  (Staging the same boxes through TMA, deeper rings, two groups on alternate atoms,
+        // one arrive per warp: all the same ~2 000 cycles per atom -- and so is the kernel with loads, MMAs, stores and mask
+        // reads switched off (EQB_PW_DEBUG=15): what bounds it is the ~20 k warp-instructions per tile of converter and
+        // epilogue arithmetic at an IPC near 1 with 16 resident warps, r3 notes in DESIGN.md 4.4) ================================
+        const int tc_ = (int)threadIdx.x - 128, px = tc_ & 127, h = tc_ >> 7;
         const uint32_t row_off = (uint32_t)px * 64u, swz = (uint32_t)((px >> 1) & 3);
         const uint32_t afull0 = leader_bar(B_AFULL);
-        const int *koff = reinterpret_cast<const int *>(sm + M.koff);
-        uint32_t seq0 = 0;
-        for (int T = cid; T < total; T += ncl, seq0 += (uint32_t)a.natoms) {
+        const int *koff = reinterpret_cast<const int *>(sm + M.koff) + 16 * h;
+        struct Ctx { const float *xp; bool valid; float sx; };
+        auto tile_ctx = [&](int T) {
+            Ctx c;
             const int b = T / a.tiles, t = T - b * a.tiles;
-            const float sx = pow2_scale(__ldg(a.absmax_in + b));
             const int p = t * 256 + 128 * (int)rank + px;
-            const bool valid = p < a.P;
-            const int oy = valid ? p / a.Wo : 0, ox = valid ? p - oy * a.Wo : 0;
-            const float *xp = a.x + (size_t)b * a.cin * a.H * a.W + (size_t)oy * a.W + ox;
-            for (int kc = 0; kc < a.natoms; ++kc) {
-                const uint32_t seq = seq0 + (uint32_t)kc;
-                if ((int)(seq & 1u) != grp) continue;      // a ring slot (seq % A_RING, A_RING even) always belongs to one group
-                const int *ko = koff + 32 * kc;
-                float v[32];
+            c.valid = p < a.P;
+            const int oy = c.valid ? p / a.Wo : 0, ox = c.valid ? p - oy * a.Wo : 0;
+            c.xp = a.x + (size_t)b * a.cin * a.H * a.W + (size_t)oy * a.W + ox;
+            c.sx = pow2_scale(__ldg(a.absmax_in + b));
+            return c;
+        };
+        auto load16 = [&](const Ctx &c, int kc, float (&v)[16]) {
+            const int *ko = koff + 32 * kc;
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const int off = ko[i];
-                    v[i] = (valid && off >= 0) ? __ldg(xp + off) : 0.f;
+            for (int i = 0; i < 16; ++i) {
+                const int off = ko[i];
+                v[i] = (c.valid && off >= 0 && !(a.debug & 4)) ? __ldg(c.xp + off) : 0.f;
+            }
+        };
+        auto convert_store = [&](const Ctx &c, uint32_t seq, const float (&v)[16]) {
+            uint32_t hi[8], lo[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) split2(v[2 * i] * c.sx, v[2 * i + 1] * c.sx, hi[i], lo[i]);
+            const uint32_t sa = seq % A_RING, pa = (seq / A_RING) & 1u;
+            mbar_wait(bar(B_AEMPTY + sa), pa ^ 1u, 100 + B_AEMPTY + sa);
+            const uint32_t hi_row = base + M.a1 + sa * A1_STAGE + row_off, lo_row = hi_row + A1_HALF;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const uint32_t col = ((uint32_t)(2 * h + j) ^ swz) << 4;
+                st_shared_v4(hi_row + col, hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+                st_shared_v4(lo_row + col, lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+            }
+            fence_async_smem();
+            mbar_arrive_cluster(afull0 + 8u * sa);     // (one arrive per warp instead of per thread measured no faster)
+        };
+        int T = cid, kc = 0;
+        uint32_t seq = 0;
+        if (T < total) {
+            Ctx cur = tile_ctx(T), nxt = cur;
+            float va[16], vb[16];
+            load16(cur, kc, va);
+            while (true) {
+                // next atom (possibly of the next tile): its loads go out before this atom is converted
+                int Tn = T, kn = kc + 1;
+                if (kn == a.natoms) { kn = 0; Tn += ncl; }
+                const bool more = Tn < total;
+                if (more) {
+                    nxt = Tn == T ? cur : tile_ctx(Tn);
+                    load16(nxt, kn, vb);
                 }
-                uint32_t hi[16], lo[16];
-#pragma unroll
-                for (int i = 0; i < 16; ++i) split2(v[2 * i] * sx, v[2 * i + 1] * sx, hi[i], lo[i]);
-                const uint32_t sa = seq % A_RING, pa = (seq / A_RING) & 1u;
-                mbar_wait(bar(B_AEMPTY + sa), pa ^ 1u, 100 + B_AEMPTY + sa);
-                const uint32_t hi_row = base + M.a1 + sa * A1_STAGE + row_off, lo_row = hi_row + A1_HALF;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const uint32_t col = ((uint32_t)j ^ swz) << 4;
-                    st_shared_v4(hi_row + col, hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
-                    st_shared_v4(lo_row + col, lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+                convert_store(cur, seq++, va);
+                if (!more) break;
+                T = Tn; kc = kn; cur = nxt;
+                Tn = T; kn = kc + 1;
+                if (kn == a.natoms) { kn = 0; Tn += ncl; }
+                const bool more2 = Tn < total;
+                if (more2) {
+                    nxt = Tn == T ? cur : tile_ctx(Tn);
+                    load16(nxt, kn, va);
                 }
-                fence_async_smem();
-                mbar_arrive_cluster(afull0 + 8u * sa);
+                convert_store(cur, seq++, vb);
+                if (!more2) break;
+                T = Tn; kc = kn; cur = nxt;
             }
         }
     } else if (warp >= 12 && warp < 20) {
