@@ -38,6 +38,8 @@
 #include <cuda_fp16.h>
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 #include "gconv_stack_tc.cuh"
 #include "resample.cuh"
@@ -2164,41 +2166,64 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(640, 1) pw_conv_kern
             const float *mp = a.mask ? a.mask + off : nullptr;
             // sixteen channels at a time; the mask values of the NEXT piece are in flight while this one is finished
             // (the loads of a warp are 128-byte lines, but a warp that waits for each batch of them keeps too few bytes
-            // in flight to cover its share of the HBM bandwidth)
+            // in flight to cover its share of the HBM bandwidth).  The kernel is bound by the instruction count of this
+            // loop and the converters', so it is specialised on its uniform switches and addresses with one wide
+            // multiply-add per element (byte offset (16 c + i) * 4 P from the tile's base)
             const bool use_mask = mp && !(a.debug & 2);
-            float ka[16], kb[16];
-            auto load_mask = [&](float (&k)[16], int c) {
+            const uint32_t P4 = 4u * (uint32_t)a.P;
+            const char *ybase = reinterpret_cast<const char *>(yp), *mbase = reinterpret_cast<const char *>(mp);
+            auto run = [&](auto mask_c, auto relu_c, auto max_c) {
+                constexpr bool MASK = decltype(mask_c)::value, RELU = decltype(relu_c)::value, MAXT = decltype(max_c)::value;
+                float ka[16], kb[16];
+                auto load_mask = [&](float (&k)[16], int c) {
+                    if (MASK) {
 #pragma unroll
-                for (int i = 0; i < 16; ++i) k[i] = (use_mask && valid) ? __ldg(mp + (size_t)(16 * c + i) * a.P) : 1.f;
-            };
-            auto finish = [&](const uint32_t (&r)[16], const float (&k)[16], int c) {
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    float v = fmaf(__uint_as_float(r[i]), cs, bias_s[16 * c + i]);
-                    if (a.relu) v = fmaxf(v, 0.f);
-                    v = k[i] > 0.f ? v : 0.f;
-                    if (valid) {
-                        m = fmaxf(m, fabsf(v));
-                        if (!(a.debug & 1)) yp[(size_t)(16 * c + i) * a.P] = v;
+                        for (int i = 0; i < 16; ++i)
+                            k[i] = valid ? __ldg(reinterpret_cast<const float *>(mbase + (size_t)((uint32_t)(16 * c + i) * P4))) : 0.f;
                     }
+                };
+                auto finish = [&](const uint32_t (&r)[16], const float (&k)[16], int c) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        float v = fmaf(__uint_as_float(r[i]), cs, bias_s[16 * c + i]);
+                        if (RELU) v = fmaxf(v, 0.f);
+                        if (MASK) v = k[i] > 0.f ? v : 0.f;
+                        if (valid) {
+                            if (MAXT) m = fmaxf(m, fabsf(v));
+                            if (!(a.debug & 1))
+                                *reinterpret_cast<float *>(const_cast<char *>(ybase) + (size_t)((uint32_t)(16 * c + i) * P4)) = v;
+                        }
+                    }
+                };
+                load_mask(ka, 0);
+#pragma unroll 1
+                for (int c = 0; c < 8; c += 2) {
+                    uint32_t r[16];
+                    tc_ld16_issue(t0 + (uint32_t)(16 * c), r);
+                    load_mask(kb, c + 1);
+                    tc_ld_wait16(r);
+                    finish(r, ka, c);
+                    tc_ld16_issue(t0 + (uint32_t)(16 * (c + 1)), r);
+                    if (c + 2 < 8) load_mask(ka, c + 2);
+                    tc_ld_wait16(r);
+                    if (c + 2 == 8) {                  // D is in registers: the issuer may start the tile after next
+                        tc_fence_before();
+                        mbar_arrive_cluster(dempty0 + 8u * d);
+                    }
+                    finish(r, kb, c + 1);
                 }
             };
-            load_mask(ka, 0);
-#pragma unroll 1
-            for (int c = 0; c < 8; c += 2) {
-                uint32_t r[16];
-                tc_ld16_issue(t0 + (uint32_t)(16 * c), r);
-                load_mask(kb, c + 1);
-                tc_ld_wait16(r);
-                finish(r, ka, c);
-                tc_ld16_issue(t0 + (uint32_t)(16 * (c + 1)), r);
-                if (c + 2 < 8) load_mask(ka, c + 2);
-                tc_ld_wait16(r);
-                if (c + 2 == 8) {                  // D is in registers: the issuer may start the tile after next
-                    tc_fence_before();
-                    mbar_arrive_cluster(dempty0 + 8u * d);
-                }
-                finish(r, kb, c + 1);
+            using T_ = std::true_type;
+            using F_ = std::false_type;
+            const bool track = a.absmax_out != nullptr;
+            if (use_mask && a.relu) {
+                if (track) run(T_{}, T_{}, T_{}); else run(T_{}, T_{}, F_{});
+            } else if (use_mask) {     // (the data gradient of the training step)
+                if (track) run(T_{}, F_{}, T_{}); else run(T_{}, F_{}, F_{});
+            } else if (a.relu) {
+                if (track) run(F_{}, T_{}, T_{}); else run(F_{}, T_{}, F_{});
+            } else {
+                if (track) run(F_{}, F_{}, T_{}); else run(F_{}, F_{}, F_{});
             }
         }
         flush_max();
