@@ -247,6 +247,11 @@ __device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
     return d;
 }
+__device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
 __device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
     uint64_t d;
     asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
@@ -2078,17 +2083,25 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(640, 1) pw_conv_kern
             return c;
         };
         auto load16 = [&](const Ctx &c, int kc, float (&v)[16]) {
-            const int *ko = koff + 32 * kc;
+            const int4 *ko = reinterpret_cast<const int4 *>(koff + 32 * kc);     // (four offsets per broadcast load)
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const int off = ko[i];
-                v[i] = (c.valid && off >= 0 && !(a.debug & 4)) ? __ldg(c.xp + off) : 0.f;
+            for (int i = 0; i < 4; ++i) {
+                const int4 o4 = ko[i];
+                v[4 * i] = (c.valid && o4.x >= 0 && !(a.debug & 4)) ? __ldg(c.xp + o4.x) : 0.f;
+                v[4 * i + 1] = (c.valid && o4.y >= 0 && !(a.debug & 4)) ? __ldg(c.xp + o4.y) : 0.f;
+                v[4 * i + 2] = (c.valid && o4.z >= 0 && !(a.debug & 4)) ? __ldg(c.xp + o4.z) : 0.f;
+                v[4 * i + 3] = (c.valid && o4.w >= 0 && !(a.debug & 4)) ? __ldg(c.xp + o4.w) : 0.f;
             }
         };
         auto convert_store = [&](const Ctx &c, uint32_t seq, const float (&v)[16]) {
             uint32_t hi[8], lo[8];
+            const uint64_t s2 = f2_pack(c.sx, c.sx);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) split2(v[2 * i] * c.sx, v[2 * i + 1] * c.sx, hi[i], lo[i]);
+            for (int i = 0; i < 8; ++i) {
+                float x0, x1;
+                f2_unpack(f2_mul(f2_pack(v[2 * i], v[2 * i + 1]), s2), x0, x1);
+                split2(x0, x1, hi[i], lo[i]);
+            }
             const uint32_t sa = seq % A_RING, pa = (seq / A_RING) & 1u;
             mbar_wait(bar(B_AEMPTY + sa), pa ^ 1u, 100 + B_AEMPTY + sa);
             const uint32_t hi_row = base + M.a1 + sa * A1_STAGE + row_off, lo_row = hi_row + A1_HALF;
@@ -2183,9 +2196,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(640, 1) pw_conv_kern
                     }
                 };
                 auto finish = [&](const uint32_t (&r)[16], const float (&k)[16], int c) {
+                    float vv[16];
+                    const uint64_t cs2 = f2_pack(cs, cs);
+                    const float2 *b2 = reinterpret_cast<const float2 *>(bias_s + 16 * c);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float2 bb = b2[i];
+                        f2_unpack(f2_fma(f2_pack(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), cs2, f2_pack(bb.x, bb.y)),
+                                  vv[2 * i], vv[2 * i + 1]);
+                    }
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
-                        float v = fmaf(__uint_as_float(r[i]), cs, bias_s[16 * c + i]);
+                        float v = vv[i];
                         if (RELU) v = fmaxf(v, 0.f);
                         if (MASK) v = k[i] > 0.f ? v : 0.f;
                         if (valid) {
