@@ -2485,15 +2485,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(640, 1)
 #pragma unroll
                 for (int j = 0; j < 8; ++j) v[j] = *reinterpret_cast<const float4 *>(box + (((uint32_t)j ^ sx7) << 4));
             }
-            if (o == 0) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) rowsum += (v[j].x + v[j].y) + (v[j].z + v[j].w);
-            }
+            // (packed fp32 pairs: the kernel is bound by the converters' instruction count, like pw)
             uint32_t hi[16], lo[16];
+            const uint64_t sc2 = f2_pack(sc, sc);
+            uint64_t rs2 = 0ull;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                split2(v[j].x * sc, v[j].y * sc, hi[2 * j], lo[2 * j]);
-                split2(v[j].z * sc, v[j].w * sc, hi[2 * j + 1], lo[2 * j + 1]);
+                const uint64_t p0 = f2_pack(v[j].x, v[j].y), p1 = f2_pack(v[j].z, v[j].w);
+                if (o == 0) rs2 = f2_add(rs2, f2_add(p0, p1));
+                float x0, x1, x2, x3;
+                f2_unpack(f2_mul(p0, sc2), x0, x1);
+                f2_unpack(f2_mul(p1, sc2), x2, x3);
+                split2(x0, x1, hi[2 * j], lo[2 * j]);
+                split2(x2, x3, hi[2 * j + 1], lo[2 * j + 1]);
+            }
+            if (o == 0) {
+                float r0, r1;
+                f2_unpack(rs2, r0, r1);
+                rowsum += r0 + r1;
             }
             // release the staged box only AFTER its values have been consumed: an arrive issued right behind the loads can be
             // performed before they have read shared memory, and with a shallow ring the TMA unit refills the slot at once
