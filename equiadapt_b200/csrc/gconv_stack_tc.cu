@@ -1856,10 +1856,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(768, 1) gconv_stack_
             return a.x + (size_t)w.b * a.cin * a.H * a.W + (size_t)oy * a.W + ox;
         };
         auto load_slab = [&](const float *xp, bool valid, int sl, float *x) {
+            const int4 *ko = reinterpret_cast<const int4 *>(koff + sl * SLAB_K);     // (four offsets per broadcast load)
 #pragma unroll
-            for (int i = 0; i < SLAB_K; ++i) {
-                const int off = koff[sl * SLAB_K + i];
-                x[i] = (valid && off >= 0) ? __ldg(xp + off) : 0.f;
+            for (int i = 0; i < SLAB_K / 4; ++i) {
+                const int4 o4 = ko[i];
+                x[4 * i] = (valid && o4.x >= 0) ? __ldg(xp + o4.x) : 0.f;
+                x[4 * i + 1] = (valid && o4.y >= 0) ? __ldg(xp + o4.y) : 0.f;
+                x[4 * i + 2] = (valid && o4.z >= 0) ? __ldg(xp + o4.z) : 0.f;
+                x[4 * i + 3] = (valid && o4.w >= 0) ? __ldg(xp + o4.w) : 0.f;
             }
         };
         TileWalk tw = walk();
@@ -1875,7 +1879,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(768, 1) gconv_stack_
             for (int sl = 0; sl < NS0; ++sl) {
                 float x[SLAB_K];
 #pragma unroll
-                for (int i = 0; i < SLAB_K; ++i) x[i] = xn[i] * sx;
+                for (int i = 0; i < SLAB_K; i += 2) f2_unpack(f2_mul(f2_pack(xn[i], xn[i + 1]), f2_pack(sx, sx)), x[i], x[i + 1]);
                 if (sl + 1 < NS0) {
                     load_slab(xp, valid, sl + 1, xn);
                 } else {
