@@ -187,20 +187,26 @@ __global__ void __launch_bounds__(THREADS2) crop_resize_tma_kernel(const __grid_
         // vertical pass: taps predicated on the row's tap count, weights of the row in registers
         float m = 0.f;
         if (col_ok) {
-            float *yp = a.y + ((size_t)plane * a.oh + oy0) * a.ow + ox;
-            for (int oy = threadIdx.y; oy < nrows; oy += blockDim.y) {
-                const Axis &ay = ty[oy0 + oy];
-                const int lo = (ay.lo_n & 0xfffff) - row_lo, n = ay.lo_n >> 20;
-                const uint32_t sp = strip_s + (uint32_t)lo * ow4;
+            // (running addresses: the pass is bound by its instruction count -- 52 per output with the multiplies in the loop)
+            float *yp = a.y + ((size_t)plane * a.oh + oy0 + threadIdx.y) * a.ow + ox;
+            const size_t ystep = (size_t)blockDim.y * a.ow;
+            const uint32_t ty_s = smem_u32(ty + oy0);
+            for (int oy = threadIdx.y; oy < nrows; oy += blockDim.y, yp += ystep) {
+                const uint32_t ay_s = ty_s + (uint32_t)oy * (uint32_t)sizeof(Axis);
+                const int lo_n = __float_as_int(lds(ay_s));
+                const int lo = (lo_n & 0xfffff) - row_lo, n = lo_n >> 20;
+                uint32_t sp = strip_s + (uint32_t)lo * ow4;
                 float acc = 0.f;
                 if (n <= MAXT) {
 #pragma unroll
-                    for (int j = 0; j < MAXT; ++j)
-                        if (j < n) acc = fmaf(lds(sp + (uint32_t)j * ow4), ay.w[j], acc);
+                    for (int j = 0; j < MAXT; ++j) {
+                        if (j < n) acc = fmaf(lds(sp), lds(ay_s + 4u + 4u * j), acc);
+                        sp += ow4;
+                    }
                 } else {
-                    for (int j = 0; j < n; ++j) acc = fmaf(lds(sp + (uint32_t)j * ow4), ay.w[j], acc);
+                    for (int j = 0; j < n; ++j, sp += ow4) acc = fmaf(lds(sp), lds(ay_s + 4u + 4u * j), acc);
                 }
-                yp[(size_t)oy * a.ow] = acc;
+                *yp = acc;
                 m = fmaxf(m, fabsf(acc));
                 if (!(acc == acc)) m = __int_as_float(0x7f800000);   // NaN poisons only its own image's scale: +inf
             }
