@@ -1923,22 +1923,25 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(768, 1) gconv_stack_
 }  // namespace pair2
 
 // =====================================================================================================================
-// pw: 1x1 convolution of a whole feature map on the CTA-pair tensor pipeline (training path, N3):
-//     y[b, n, p] = [relu](sum_c w[n, c] x[b, c, p] + bias[n])   [zeroed where mask[b, n, p] <= 0]
-// for N = C = 256 -- the regular layers of CustomEquivariantNetwork in train() mode (feature maps kept) and, with w
-// transposed and mask = the saved input of the layer, their data gradient through the preceding ReLU
-// (custom_group_equivariant_layers.py:298-334 after the filter orbit; eqb_conv2d_forward's contract).
+// pw: convolutions of the training path (N3) on the CTA-pair tensor pipeline:
+//     y[b, n, p] = [relu](sum_k w[n, k] patch[b, k, p] + bias[n])   [zeroed where mask[b, n, p] <= 0]
+// for N = 256 output channels and K = cin * ksz^2 <= 256 -- the 5x5 lift and the 1x1 regular layers of
+// CustomEquivariantNetwork in train() mode (feature maps kept) and, with w transposed and mask = the saved input of the layer,
+// the data gradient of a 1x1 layer through the preceding ReLU (custom_group_equivariant_layers.py:62-112, :298-334 after the
+// filter orbit; eqb_conv2d_forward's contract).
 // Same numerics as the stack kernel: fp16 hi/lo split of both operands (3 MMAs per product, ~22-bit significands),
 // power-of-two operand scales (per IMAGE for x), fp32 accumulation in TMEM.
-//   warps 4-11  (both CTAs) converters: thread = (pixel, half atom): 16 reduction values from global memory (coalesced per
-//               channel), the next atom's loads in flight -> scaled fp16 hi / lo -> the K-major 64-byte-swizzled operand atom
-//               [128 pixels x 32 channels] of this CTA (4-stage ring)
-//   warp 1      (leader)    8 atoms x 6 MMAs (cta_group::2, M = 256 pixels, N = 256 channels) into D[tile & 1]
+//   warps 4-11  (both CTAs) converters: thread = (pixel, half atom): 16 reduction values from global memory (1x1: one coalesced
+//               line per channel and warp; k x k: patch taps through an offset table), the next atom's loads in flight ->
+//               scaled fp16 hi / lo -> the K-major 64-byte-swizzled operand atom [128 pixels x 32] of this CTA (4-stage ring)
+//   warp 1      (leader)    ceil(K / 32) atoms x 6 MMAs (cta_group::2, M = 256 pixels, N = 256 channels) into D[tile & 1]
 //   warps 12-19 (both CTAs) epilogue: this CTA's 128 pixels x 256 channels of D -> scale, bias, ReLU, mask -> y; lane = pixel,
 //               so every store and mask load of a warp is one 128-byte line (with channels on the lanes -- the stack
-//               kernel's orientation -- each lane wrote its own row: 446 / 827 us per call instead of 3xx, r3 notes)
+//               kernel's orientation -- each lane wrote its own row: 446 / 827 us per call instead of 3xx); max |y| per
+//               sample for the next layer's operand scale
 // TMEM holds two accumulators (2 x 256 columns): the epilogue of tile t runs under the MMAs of tile t + 1.
-// Bound: x read once + y written once (+ mask read): 1.1-1.7 GB per call at B = 64 against 213 GFLOP of MMAs: HBM.
+// Traffic: x read once + y written once (+ mask read): 1.1-1.7 GB per 1x1 call at B = 64 against 213 GFLOP of MMAs.  What
+// bounds it is neither: the instruction count of the converters and the epilogue.
 namespace pw {
 
 using namespace pair;
