@@ -112,11 +112,9 @@ class DiscreteGroupImageCanonicalization(DiscreteGroupCanonicalization):
             # gradient (and its 90-eps rounding), and with gumbel_softmax the element IS the sampled one-hot, not the
             # arg-max -- so the index that drives the warp is derived from that same one-hot
             onehot = self.groupactivations_to_groupelementonehot(group_activations)
-            angles = torch.linspace(0.0, 360.0, self.num_rotations + 1)[: self.num_rotations].to(self.device)
-            comp = torch.cat([angles, angles]) if self.group_type == "roto-reflection" else angles
+            comp, ident = self._element_tables(onehot.device)
             element["rotation"] = torch.sum(onehot * comp, dim=-1)
             if self.group_type == "roto-reflection":
-                ident = torch.cat([torch.zeros(self.num_rotations), torch.ones(self.num_rotations)]).to(self.device)
                 element["reflection"] = torch.sum(onehot * ident, dim=-1)
             element.index = onehot.detach().argmax(dim=-1).to(torch.int32) if sampled else sel["idx"]
         else:
@@ -125,6 +123,19 @@ class DiscreteGroupImageCanonicalization(DiscreteGroupCanonicalization):
                 element["reflection"] = sel["reflection"]
             element.index = sel["idx"]
         return element
+
+    def _element_tables(self, device: torch.device):
+        """The reference's per-call constants (discrete_group.py:110-133): angles of the group elements and the reflection
+        indicator, built on the CPU exactly as there (same fp32 bits) and kept on the device -- the reference uploads them on
+        every call, a pageable host-to-device copy that also makes the step impossible to capture in a CUDA graph."""
+        cache = self.__dict__.setdefault("_eqb_element_tables", {})
+        key = (str(device), self.num_rotations, self.group_type)
+        if key not in cache:
+            angles = torch.linspace(0.0, 360.0, self.num_rotations + 1)[: self.num_rotations]
+            comp = torch.cat([angles, angles]) if self.group_type == "roto-reflection" else angles
+            ident = torch.cat([torch.zeros(self.num_rotations), torch.ones(self.num_rotations)])
+            cache[key] = (comp.to(device), ident.to(device))
+        return cache[key]
 
     def get_group_activations(self, x: torch.Tensor) -> torch.Tensor:
         raise NotImplementedError(

@@ -2754,6 +2754,13 @@ static int pw_scratch(cudaStream_t st, size_t need, unsigned char **out) {
         *sc = Scratch{dev, st, nullptr, 0};
     }
     if (sc->bytes < need) {
+        // (growing the buffer allocates and synchronises: not inside a stream capture -- run the step once on the capture
+        // stream before capturing it, as CapturedStep / tools/bench_train.py do)
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        EQB_CUDA(cudaStreamIsCapturing(st, &cap));
+        EQB_UNSUPPORTED(cap != cudaStreamCaptureStatusNone,
+                        "training kernels: scratch for this (device, stream) must exist before the stream is captured (%zu bytes needed): "
+                        "warm the step up on the capture stream first", need);
         if (sc->ptr) {
             EQB_CUDA(cudaStreamSynchronize(st));
             EQB_CUDA(cudaFree(sc->ptr));
