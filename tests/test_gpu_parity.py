@@ -1371,6 +1371,52 @@ def test_full_training_step_of_the_flagship_canonicalizer(cuda_device):
     assert priors[-1] < priors[0]
 
 
+def test_training_step_is_cuda_graph_capturable(cuda_device):
+    """Forward + losses + backward of the flagship canonicalizer (32 channels x C8 = 256: the tensor-core training kernels)
+    captured as ONE CUDA graph on the stream it was warmed up on: the replay leaves the same loss and, within the run-to-run
+    noise of the split-K atomics, the same parameter gradients as the eager step.  (The reference uploads its angle table on
+    every call, discrete_group.py:110-117 -- a pageable copy no graph can contain; here the table stays on the device.)"""
+    _, GEIC, _, Net = _mods()
+    dev = cuda_device
+    torch.manual_seed(520)
+    net = Net((3, 32, 32), 32, 5, "rotation", 8, 3, device="cpu").to(dev)
+    can = GEIC(net, SimpleNamespace(beta=1.0, input_crop_ratio=0.9, resize_shape=32), (3, 40, 40)).train()
+    x = _smooth(6, 3, 40, 40, 521).to(dev)
+    w = torch.randn(6, 3, 40, 40, generator=torch.Generator().manual_seed(522)).to(dev)
+    params = [p for p in can.parameters() if p.requires_grad]
+
+    def step():
+        for p in params:
+            p.grad = None
+        loss = (can(x) * w).mean() + 100.0 * can.get_prior_regularization_loss()
+        loss.backward()
+        return loss
+
+    side = torch.cuda.Stream(dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            loss_eager = step()
+    torch.cuda.current_stream(dev).wait_stream(side)
+    torch.cuda.synchronize(dev)
+    g_eager = [p.grad.clone() for p in params]
+    for p in params:
+        p.grad = None
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=side, capture_error_mode="thread_local"):
+        loss_graph = (can(x) * w).mean() + 100.0 * can.get_prior_regularization_loss()
+        loss_graph.backward()
+    for _ in range(2):
+        graph.replay()
+    torch.cuda.synchronize(dev)
+    assert abs(float(loss_graph.detach()) - float(loss_eager.detach())) <= 1e-5 * abs(float(loss_eager.detach()))
+    for p, ge in zip(params, g_eager):
+        scale = float(ge.abs().max())
+        if scale > 1e-4:                       # (a softmax-invariant bias has a mathematically zero gradient: noise only)
+            assert float((p.grad - ge).abs().max()) < 1e-4 * scale
+    del graph
+
+
 # ---- N3: the optimisation-based variant trains any torch network through the cosine activations ----------------------
 def test_cosine_activations_backward_vs_torch(cuda_device):
     ops = _mods()[0]
