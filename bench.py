@@ -713,6 +713,18 @@ def run_b200(args):
         ops.event_log = {}
         eager_ms, eager_per, _ = timed_steps(lambda: step(x), args.steps, barrier)
         log, ops.event_log = ops.event_log, None
+        kernels_pass = "the eager pass"
+        if world > 1:
+            # Per-kernel times for `kernels` / `rooflines` WITHOUT the collective in flight: the all-reduce kernel, issued beside
+            # the warp kernels, waits for the slowest rank ON the SMs, and in an eager pass that wait is another rank's Python
+            # thread (warps measured 125 -> 170 us at N = 2..8 that way; the graph-timed step shows +40 us for the whole step).
+            s0, p0 = can.sync_prior_across_ranks, can.prefetch_prior_allreduce
+            can.sync_prior_across_ranks = can.prefetch_prior_allreduce = False
+            ops.event_log = {}
+            timed_steps(lambda: step(x), args.steps, barrier)
+            log, ops.event_log = ops.event_log, None
+            can.sync_prior_across_ranks, can.prefetch_prior_allreduce = s0, p0
+            kernels_pass = "a second eager pass with the prior all-reduce switched off (rank-local statistic)"
         z_e, loss_e, ident_e = step(x)
         graph_equal = None
         if graphed_step is not None:
@@ -859,7 +871,7 @@ def run_b200(args):
             "step_ms": dict(step_stats(per_step), max_over_ranks=float(t[5]), min_over_ranks=float(tmin[0])),
             "eager": {"value": B * world * args.steps / (eager_ms * 1e-3), "ms_per_step": eager_ms / args.steps,
                       "step_ms": step_stats(eager_per),
-                      "note": "same K steps as eager ctypes calls with two CUDA events around each (the pass `kernels` comes from)"},
+                      "note": "same K steps as eager ctypes calls with two CUDA events around each; `kernels` / `rooflines` come from " + kernels_pass},
             "clocks": clock_info,
             "e2e": {"value": B * world * args.e2e_steps / e2e_s, "unit": "img/s",
                     "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": z_host.numel() * 4 + 8,
