@@ -311,6 +311,9 @@ def test_argument_validation_of_the_training_and_orbit_entry_points(lib):
     assert lib.eqb_orbit_rotate_nearest(None, None, 0, 3, 8, 8, 4, 1, None) == 0                    # empty batch: nothing to do
     assert lib.eqb_conv2d_forward(None, None, None, None, None, 1, 3, 4, 4, 8, 5, 1, None) == inv   # map smaller than the kernel
     assert lib.eqb_conv2d_weight_grad(None, None, None, 1, 3, 8, 8, 8, 3, None) == inv              # null dw
+    assert lib.eqb_conv2d_forward_scaled(None, None, None, None, None, 1, 3, 4, 4, 8, 5, 1, None, None, None) == inv
+    assert lib.eqb_conv2d_forward_scaled(None, None, None, None, None, 0, 3, 8, 8, 8, 5, 1, None, None, None) == 0   # empty batch
+    assert lib.eqb_conv2d_weight_grad_scaled(None, None, None, 1, 3, 8, 8, 8, 3, None, None, None, None) == inv      # null dw
     assert lib.eqb_plane_sums(None, 0, 5, None, None) == 0
     assert lib.eqb_plane_sums(None, 3, 0, None, None) == inv
     assert lib.eqb_group_mean_backward(None, None, 2, 0, 4, 16, None) == inv
@@ -357,3 +360,21 @@ def test_inference_metrics_match_the_unmodified_reference(monkeypatch):
         m = grp.get_inference_metrics(x, y)
         assert sorted(m) == [str(k) for k in z["group_keys"]]
         assert np.allclose([float(m[k]) for k in sorted(m)], z["group_values"], atol=1e-7)
+
+
+def test_recorded_sample_maxima_follow_the_tensor_version():
+    """ops._record_amax / _known_amax (the per-sample maxima the tensor-core training convolutions hand from call to call,
+    eqb_conv2d_*_scaled): the record is bound to the tensor's version counter, so any in-place write drops it, and it does not
+    travel with views, clones or detached copies."""
+    from equiadapt_b200 import ops
+    t = torch.arange(12.0).reshape(3, 4)
+    assert ops._known_amax(t) is None
+    amax = t.abs().amax(dim=1)
+    ops._record_amax(t, amax)
+    assert ops._known_amax(t) is amax
+    assert ops._known_amax(t.clone()) is None and ops._known_amax(t.detach()) is None and ops._known_amax(t[:2]) is None
+    t.mul_(2.0)
+    assert ops._known_amax(t) is None                 # stale after an in-place write
+    ops._record_amax(t, t.abs().amax(dim=1))
+    t[0, 0] = 100.0
+    assert ops._known_amax(t) is None
